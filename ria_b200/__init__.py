@@ -1,0 +1,10 @@
+"""ria_b200 -- B200-native batched receive chain for the RIA HF modem (hot path only).
+
+Python here is plumbing (torch for device memory / streams / torch.distributed); all compute
+is hand-written sm_100a CUDA in libria_b200.so behind the C ABI of include/ria_b200.h.
+There is no CPU fallback.
+"""
+from ._lib import Context, RiaError, LIB_PATH, exported_symbols, lib  # noqa: F401
+from . import fec  # noqa: F401
+
+__all__ = ["Context", "RiaError", "LIB_PATH", "exported_symbols", "lib", "fec"]

@@ -1,0 +1,79 @@
+// Internal declarations shared by the translation units of libria_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ria_b200.h"
+
+namespace ria {
+
+// ---------------------------------------------------------------------------------------------
+// LDPC code tables (host side: ldpc_code.cpp)
+// ---------------------------------------------------------------------------------------------
+struct LdpcCodeHost {
+    int rate = -1;
+    int k = 0, m = 0, n = 0, n_edges = 0;
+    int dv_max = 0;                         // max degree over the k info variables
+    std::vector<int32_t> row_ptr;           // m+1
+    std::vector<int32_t> edge_var;          // n_edges, H_rows order (identity edge last in each row)
+    // device-layout tables
+    std::vector<uint16_t> chk_var;          // [m][8]: info-variable index per slot, 0xFFFF = unused;
+                                            //         slot 7 holds the number of INFO edges of the check
+    std::vector<uint16_t> var_slot;         // [dv_max][k]: c2v slot ids of variable j, ascending
+                                            //         check index; 0xFFFF = unused
+};
+
+const LdpcCodeHost& ldpc_code_host(int rate);   // cached, thread-safe; throws on bad rate
+bool ldpc_rate_valid(int rate);
+
+struct LdpcCodeDev {
+    bool ready = false;
+    int k = 0, m = 0, dv_max = 0;
+    uint16_t* chk_var = nullptr;
+    uint16_t* var_slot = nullptr;
+};
+
+}  // namespace ria
+
+// ---------------------------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------------------------
+struct ria_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;      // stream all work is issued on
+    cudaStream_t own_stream = nullptr;  // created by us (destroyed with the ctx)
+    cudaStream_t copy_stream = nullptr; // H2D/D2H staging for *_host entry points
+    std::string last_error;
+    int64_t launches = 0;
+    ria::LdpcCodeDev ldpc[8];
+    unsigned int* work_counter = nullptr;   // device, dynamic tile scheduler
+    // staging for *_host entry points (grown on demand)
+    void* stage_dev[2] = {nullptr, nullptr};
+    size_t stage_dev_bytes[2] = {0, 0};
+    void* stage_pin[2] = {nullptr, nullptr};
+    size_t stage_pin_bytes[2] = {0, 0};
+    cudaEvent_t stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace ria {
+
+int set_error(ria_ctx* ctx, int code, const char* fmt, ...);
+int ensure_stage(ria_ctx* ctx, int which, size_t dev_bytes, size_t pin_bytes);
+int ldpc_tables_dev(ria_ctx* ctx, int rate, const LdpcCodeDev** out);
+
+}  // namespace ria
+
+#define RIA_CUDA(ctx, expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return ria::set_error((ctx), RIA_E_CUDA, "%s failed: %s (%s:%d)", #expr,         \
+                                  cudaGetErrorString(_e), __FILE__, __LINE__);               \
+    } while (0)

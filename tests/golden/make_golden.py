@@ -1,0 +1,62 @@
+"""Generates the committed golden fixtures from the UNMODIFIED reference (oracle/_ref).
+
+Run here (needs /root/reference to have been compiled by `make -C oracle ref`):
+    python tests/golden/make_golden.py
+The reference ships no known-answer vectors of its own, so these are outputs
+of the reference itself on seeded inputs; the GPU box checks against them without the
+reference tree.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle.bindings import (Ref, R1_4, R1_2, R2_3, R3_4, R5_6, RATE_K, RATE_MAX_ITER,  # noqa: E402
+                             awgn_llrs, unpack_bits)
+
+
+def ldpc_golden(ref, out_dir):
+    rng = np.random.default_rng(20261018)
+    # Es/N0 per rate chosen so that the set mixes early converging, late converging and failing cws
+    esn0 = {R1_4: -2.5, R1_2: 1.8, R2_3: 4.3, R3_4: 5.3, R5_6: 6.5}
+    n_cw = 48
+    out = {}
+    for rate in (R1_4, R1_2, R2_3, R3_4, R5_6):
+        k = RATE_K[rate]
+        llr = np.zeros((n_cw, 648), np.float32)
+        data = rng.integers(0, 256, size=(n_cw, k // 8), dtype=np.uint8)
+        for i in range(n_cw):
+            cw = ref.ldpc_encode(rate, data[i])[:81]
+            llr[i] = awgn_llrs(unpack_bits(cw), esn0[rate] + (i % 3) * 0.7, rng)
+        # a few adversarial rows: zeros, huge values, -0.0, inf, NaN
+        llr[40] = 0.0
+        llr[41] = np.where(rng.random(648) < 0.5, 1e6, -1e6).astype(np.float32)
+        llr[42, ::7] = -0.0
+        llr[43, 5] = np.inf
+        llr[43, 9] = -np.inf
+        llr[44, 3] = np.nan
+        llr[45] = np.abs(llr[45])          # all-zero codeword
+        out[f"r{rate}_llr"] = llr
+        out[f"r{rate}_data"] = data
+        for tag, factor in (("a", 0.75), ("b", 0.9375)):
+            info, ok, iters = ref.ldpc_decode_batch(rate, llr, RATE_MAX_ITER[rate], factor, 68)
+            out[f"r{rate}_{tag}_info"] = info
+            out[f"r{rate}_{tag}_ok"] = ok
+            out[f"r{rate}_{tag}_iters"] = iters
+        # H structure as seen through the encoder: column j of H_data = parity of unit vector e_j
+        cols = np.zeros((k, 648 - k), np.uint8)
+        for j in range(k):
+            d = np.zeros((k + 7) // 8, np.uint8)
+            d[j // 8] = 0x80 >> (j % 8)
+            cols[j] = unpack_bits(ref.ldpc_encode(rate, d)[:81])[k:]
+        out[f"r{rate}_hdata_cols"] = np.packbits(cols, axis=1)
+    np.savez_compressed(os.path.join(out_dir, "ldpc_golden.npz"), **out)
+    print("ldpc_golden.npz written:", {k: v.shape for k, v in out.items() if k.endswith("iters")})
+
+
+if __name__ == "__main__":
+    ref = Ref()
+    ldpc_golden(ref, HERE)
