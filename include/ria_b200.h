@@ -87,6 +87,116 @@ int ria_ldpc_decode_batch_host(ria_ctx* ctx, int rate, int max_iter, float min_s
                                const float* llr, int64_t n_cw,
                                uint8_t* info, int info_stride, uint8_t* ok, int32_t* iters);
 
+
+/* ---- OFDM presynced receive chain ---------------------------------------------------------- */
+/* POD mirror of the RX-relevant fields of ultra::ModemConfig (include/ultra/types.hpp:193-289).
+ * Defaults of the reference: sample_rate 48000, center_freq 1500, fft_size 1024,
+ * num_carriers 59, cp_mode 1 (MEDIUM -> 48*(fft/512) = 96 samples), symbol_guard 0. */
+typedef struct {
+    uint32_t sample_rate;
+    uint32_t center_freq;
+    uint32_t fft_size;        /* 1024 (the only size the kernels are built for)          */
+    uint32_t num_carriers;    /* <= 64                                                   */
+    uint32_t cp_mode;         /* CyclicPrefixMode: 0 SHORT, 1 MEDIUM, 2 LONG             */
+    uint32_t symbol_guard;
+    uint32_t use_pilots;      /* ModemConfig::use_pilots                                 */
+    uint32_t pilot_spacing;   /* ModemConfig::pilot_spacing (pilot every N-th carrier)   */
+    uint32_t modulation;      /* ria_modulation                                          */
+    uint32_t training_symbols;/* LTS symbols in front of the data (reference always 2)   */
+} ria_modem_config;
+
+/* Fill `cfg` with the reference defaults for a (modulation, code rate) pair the way
+ * OFDMChirpWaveform::configure does (src/waveform/ofdm_chirp_waveform.cpp:79-105,
+ * ofdm_link_adaptation.hpp:26-64): use_pilots = 1, pilot_spacing = recommendedPilotSpacing. */
+int ria_modem_config_for(int modulation, int rate, ria_modem_config* cfg);
+/* samples per OFDM symbol (ModemConfig::getSymbolDuration) and data carriers of a config */
+int ria_ofdm_symbol_samples(const ria_modem_config* cfg);
+int ria_ofdm_data_carriers(const ria_modem_config* cfg);
+int ria_ofdm_pilot_carriers(const ria_modem_config* cfg);
+
+/* Batched replacement for OFDMChirpWaveform::process (src/waveform/ofdm_chirp_waveform.cpp:
+ * 391-468) = setFrequencyOffsetWithPhase + OFDMDemodulator::processPresynced
+ * (src/ofdm/demodulator.cpp:1250-1414; toBaseband/extractSymbol/estimateChannelFromLTS/
+ * updateChannelEstimate/equalize in src/ofdm/channel_equalizer.cpp; demodulateSymbol and
+ * soft_demap in src/ofdm/demodulator.cpp:208-508, src/ofdm/soft_demap.hpp).
+ *
+ *   samples_dev   fp32, frame f starts at samples_dev + f*frame_stride and holds frame_len
+ *                 samples beginning at the first LTS symbol (what process() is handed)
+ *   cfo_hz_dev    [n] per-frame CFO passed to setFrequencyOffsetWithPhase (may be NULL = 0)
+ *   phase_dev     [n] per-frame initial correction phase in radians (may be NULL = 0)
+ *   llr_dev       [n][llr_stride] soft bits in the reference's order (symbol-major, carrier,
+ *                 bit); positions >= n_llr[f] are zero
+ *   n_llr_dev     [n] soft bits produced = data_symbols * data_carriers * bits_per_carrier
+ *   snr_db_dev    [n] OFDMDemodulator::getEstimatedSNR()   (may be NULL)
+ *   cfo_out_dev   [n] OFDMDemodulator::getFrequencyOffset() after LTS refinement (may be NULL)
+ *   fading_dev    [n] OFDMDemodulator::getFadingIndex()    (may be NULL)
+ * Frames shorter than one symbol yield n_llr = 0 (processPresynced returns false). */
+int ria_ofdm_presynced_batch_dev(ria_ctx* ctx, const ria_modem_config* cfg,
+                                 const float* samples_dev, int64_t frame_stride, int32_t frame_len,
+                                 const float* cfo_hz_dev, const float* phase_dev, int64_t n_frames,
+                                 float* llr_dev, int32_t llr_stride, int32_t* n_llr_dev,
+                                 float* snr_db_dev, float* cfo_out_dev, float* fading_dev);
+
+/* Debug/parity taps of the same kernel: frequency-domain bins of every symbol for the used
+ * carriers ([n][n_symbols][num_carriers] interleaved re,im; logical carrier order) and the
+ * channel estimate after the LTS ([n][num_carriers] re,im).  Either may be NULL. */
+int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_config* cfg,
+                                      const float* samples_dev, int64_t frame_stride, int32_t frame_len,
+                                      const float* cfo_hz_dev, const float* phase_dev, int64_t n_frames,
+                                      float* llr_dev, int32_t llr_stride, int32_t* n_llr_dev,
+                                      float* snr_db_dev, float* cfo_out_dev, float* fading_dev,
+                                      float* bins_dev, float* h_lts_dev);
+
+/* ---- fixed 4-codeword frame: de-interleave + LDPC + header/CRC ---------------------------- */
+typedef struct {
+    uint8_t  cw_ok[4];        /* per codeword parity success (CodewordStatus::decoded)      */
+    int32_t  cw_iters[4];     /* per codeword LDPCDecoder::lastIterations()                 */
+    uint8_t  all_ok;          /* CodewordStatus::allSuccess()                               */
+    uint8_t  header_valid;    /* v2::parseHeader(...).valid on the reassembled bytes        */
+    uint8_t  frame_crc_ok;    /* data frame: frame CRC over header+payload (deserialize)    */
+    uint8_t  type;            /* HeaderInfo::type                                           */
+    uint16_t seq;
+    uint16_t payload_len;
+    uint32_t src_hash;
+    uint32_t dst_hash;
+    uint8_t  total_cw;
+    uint8_t  pad[3];
+} ria_frame_status;
+
+/* Batched first pass of v2::decodeFixedFrame (src/protocol/frame_v2.cpp:1335-1385, 1548-1556):
+ * FrameInterleaver::deinterleave (src/fec/frame_interleaver.cpp:96-124), optional
+ * ChannelInterleaver::deinterleave (src/fec/ldpc_decoder.cpp:552-625) with
+ * bits_per_symbol, 4 x LDPCDecoder::decodeSoft(factor 0.9375, getRecommendedIterations(rate)),
+ * take bytes_per_cw bytes per codeword, then v2::parseHeader + frame CRC
+ * (src/protocol/frame_v2.cpp:115-128, 1195-1253, 555-600).  The retry ladder (:1389-1546) is
+ * NOT run.
+ *   soft_dev   [n][soft_stride] >= 2592 soft bits per frame (soft_stride >= 2592)
+ *   data_dev   [n][4*bytes_per_cw] reassembled info bytes (codewords that failed are zeros)
+ *   status_dev [n] */
+int ria_frame_decode_batch_dev(ria_ctx* ctx, int rate, int use_channel_interleave,
+                               int bits_per_symbol, const float* soft_dev, int32_t soft_stride,
+                               int64_t n_frames, uint8_t* data_dev, ria_frame_status* status_dev);
+
+/* Whole receive chain for OFDM data frames: presynced demod -> frame decode, one call.
+ * Device buffers; llr scratch is owned by the context. */
+int ria_ofdm_rx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg, int rate,
+                           int use_channel_interleave,
+                           const float* samples_dev, int64_t frame_stride, int32_t frame_len,
+                           const float* cfo_hz_dev, const float* phase_dev, int64_t n_frames,
+                           uint8_t* data_dev, ria_frame_status* status_dev, float* snr_db_dev);
+
+/* Same with HOST buffers: chunked H2D -> demod -> decode -> D2H inside the call. */
+int ria_ofdm_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg, int rate,
+                            int use_channel_interleave,
+                            const float* samples, int64_t frame_stride, int32_t frame_len,
+                            const float* cfo_hz, const float* phase, int64_t n_frames,
+                            uint8_t* data, ria_frame_status* status, float* snr_db);
+
+/* CRC-16/CCITT-FALSE as ControlFrame::calculateCRC (src/protocol/frame_v2.cpp:115-128); host. */
+uint16_t ria_crc16(const uint8_t* data, size_t len);
+/* ChannelInterleaver step: findCoprimeStep (src/fec/ldpc_decoder.cpp:552-577); host. */
+int ria_channel_interleaver_step(int bits_per_symbol, int total_bits);
+
 #ifdef __cplusplus
 }
 #endif

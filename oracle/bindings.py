@@ -42,6 +42,43 @@ class _Code(C.Structure):
                 ("edge_var", C.c_int * 4096)]
 
 
+class ModemConfig(C.Structure):
+    """Same layout as ria_modem_config (include/ria_b200.h)."""
+    _fields_ = [(n, C.c_uint32) for n in (
+        "sample_rate", "center_freq", "fft_size", "num_carriers", "cp_mode", "symbol_guard",
+        "use_pilots", "pilot_spacing", "modulation", "training_symbols")]
+
+    @classmethod
+    def make(cls, modulation, pilot_spacing, use_pilots=1, cp_mode=1, num_carriers=59):
+        return cls(48000, 1500, 1024, num_carriers, cp_mode, 0, use_pilots, pilot_spacing,
+                   modulation, 2)
+
+    def symbol_samples(self):
+        return self.fft_size + (32, 48, 64)[self.cp_mode] * (self.fft_size // 512) + self.symbol_guard
+
+    def pilots(self):
+        if not self.use_pilots:
+            return 0
+        return (self.num_carriers + self.pilot_spacing - 1) // self.pilot_spacing
+
+    def data_carriers(self):
+        return self.num_carriers - self.pilots()
+
+
+class FrameStatus(C.Structure):
+    """Same layout as ria_frame_status (include/ria_b200.h)."""
+    _fields_ = [("cw_ok", C.c_uint8 * 4), ("cw_iters", C.c_int32 * 4), ("all_ok", C.c_uint8),
+                ("header_valid", C.c_uint8), ("frame_crc_ok", C.c_uint8), ("type", C.c_uint8),
+                ("seq", C.c_uint16), ("payload_len", C.c_uint16), ("src_hash", C.c_uint32),
+                ("dst_hash", C.c_uint32), ("total_cw", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+# ultra::Modulation (include/ultra/types.hpp:27-39)
+DBPSK, BPSK, DQPSK, QPSK, D8PSK, QAM8, QAM16, QAM32, QAM64 = range(9)
+BITS_PER_CARRIER = {DBPSK: 1, BPSK: 1, DQPSK: 2, QPSK: 2, D8PSK: 3, QAM8: 3, QAM16: 4, QAM32: 5, QAM64: 6}
+BYTES_PER_CW = {R1_4: 20, R1_2: 40, R2_3: 54, R3_4: 60, R5_6: 67}
+
+
 class Port:
     """Plain-C restatement (oracle/*.c)."""
 
@@ -116,6 +153,28 @@ class Ref:
                                            C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ref_ldpc_decode_soft.restype = C.c_int
         L.ref_ldpc_decode_batch.argtypes = [C.c_void_p, _f32p, C.c_int, _u8p, C.c_int, _u8p, _i32p]
+        cfgp = C.POINTER(ModemConfig)
+        L.ref_ofdm_tx_frame.argtypes = [cfgp, _u8p, C.c_int, _f32p, C.c_int]
+        L.ref_ofdm_tx_frame.restype = C.c_int
+        L.ref_ofdm_demod_new.argtypes = [cfgp]
+        L.ref_ofdm_demod_new.restype = C.c_void_p
+        L.ref_ofdm_demod_free.argtypes = [C.c_void_p]
+        fp = C.POINTER(C.c_float)
+        L.ref_ofdm_process_presynced.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_float,
+                                                 _f32p, C.c_int, C.POINTER(C.c_int), fp, fp, fp, C.c_void_p]
+        L.ref_ofdm_process_presynced.restype = C.c_int
+        L.ref_fft_forward.argtypes = [C.c_int, _f32p, _f32p]
+        L.ref_ofdm_symbol_bins.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_float, _f32p]
+        L.ref_encode_fixed_frame.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
+        L.ref_encode_fixed_frame.restype = C.c_int
+        L.ref_frame_decode_first_pass.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _u8p, _u8p, _i32p]
+        L.ref_decode_fixed_frame_full.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _u8p]
+        L.ref_parse_header.argtypes = [_u8p, C.c_int, C.POINTER(FrameStatus)]
+        L.ref_crc16.argtypes = [_u8p, C.c_int]
+        L.ref_crc16.restype = C.c_uint16
+        L.ref_make_data_frame.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _u8p, C.c_int, _u8p, C.c_int]
+        L.ref_make_data_frame.restype = C.c_int
+        self._demods = {}
 
     @staticmethod
     def available() -> bool:
@@ -148,6 +207,89 @@ class Ref:
         self.lib.ref_ldpc_decode_batch(h, llr, n, out, out_stride, ok, iters)
         self.lib.ref_ldpc_decoder_free(h)
         return out, ok, iters
+
+
+    # ---- OFDM ----
+    def ofdm_tx_frame(self, cfg: ModemConfig, data) -> np.ndarray:
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        cap = cfg.symbol_samples() * (2 + len(data) * 8 // max(1, cfg.data_carriers()) + 4)
+        out = np.zeros(cap, np.float32)
+        n = self.lib.ref_ofdm_tx_frame(C.byref(cfg), data, len(data), out, cap)
+        assert n >= 0, n
+        return out[:n].copy()
+
+    def _demod(self, cfg: ModemConfig):
+        key = bytes(cfg)
+        if key not in self._demods:
+            self._demods[key] = self.lib.ref_ofdm_demod_new(C.byref(cfg))
+        return self._demods[key]
+
+    def ofdm_process_presynced(self, cfg: ModemConfig, samples, cfo_hz=0.0, phase=0.0):
+        """-> dict(ready, soft, snr_db, cfo, fading, h)   (one frame)"""
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        cap = 8192
+        soft = np.zeros(cap, np.float32)
+        n_soft = C.c_int(0)
+        snr, cfo, fad = C.c_float(0), C.c_float(0), C.c_float(0)
+        h = np.zeros((cfg.num_carriers, 2), np.float32)
+        ready = self.lib.ref_ofdm_process_presynced(
+            self._demod(cfg), samples, len(samples), cfo_hz, phase, soft, cap, C.byref(n_soft),
+            C.byref(snr), C.byref(cfo), C.byref(fad), h.ctypes.data)
+        return dict(ready=bool(ready), soft=soft[: n_soft.value].copy(), snr_db=snr.value,
+                    cfo=cfo.value, fading=fad.value, h=h[:, 0] + 1j * h[:, 1])
+
+    def fft_forward(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out = np.zeros_like(x)
+        self.lib.ref_fft_forward(len(x), x.view(np.float32), out.view(np.float32))
+        return out
+
+    def ofdm_symbol_bins(self, cfg: ModemConfig, samples, n_sym, cfo_hz=0.0, phase=0.0):
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        bins = np.zeros((n_sym, cfg.num_carriers, 2), np.float32)
+        self.lib.ref_ofdm_symbol_bins(self._demod(cfg), samples, n_sym, cfo_hz, phase, bins)
+        return bins[..., 0] + 1j * bins[..., 1]
+
+    # ---- fixed frame ----
+    def encode_fixed_frame(self, data, rate, use_ci, bps) -> np.ndarray:
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        out = np.zeros(400, np.uint8)
+        n = self.lib.ref_encode_fixed_frame(data, len(data), rate, int(use_ci), bps, out, len(out))
+        assert n == 324, n
+        return out[:n].copy()
+
+    def frame_decode_first_pass(self, soft, rate, use_ci, bps):
+        soft = np.ascontiguousarray(soft, dtype=np.float32)
+        assert soft.size >= 2592
+        data = np.zeros(4 * BYTES_PER_CW[rate], np.uint8)
+        ok = np.zeros(4, np.uint8)
+        iters = np.zeros(4, np.int32)
+        self.lib.ref_frame_decode_first_pass(soft, rate, int(use_ci), bps, data, ok, iters)
+        return data, ok, iters
+
+    def decode_fixed_frame_full(self, soft, rate, use_ci, bps):
+        soft = np.ascontiguousarray(soft, dtype=np.float32)
+        data = np.zeros(4 * BYTES_PER_CW[rate], np.uint8)
+        ok = np.zeros(4, np.uint8)
+        self.lib.ref_decode_fixed_frame_full(soft, soft.size, rate, int(use_ci), bps, data, ok)
+        return data, ok
+
+    def parse_header(self, data) -> FrameStatus:
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        st = FrameStatus()
+        self.lib.ref_parse_header(data, len(data), C.byref(st))
+        return st
+
+    def crc16(self, data) -> int:
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        return int(self.lib.ref_crc16(data, len(data)))
+
+    def make_data_frame(self, src: str, dst: str, seq: int, payload) -> bytes:
+        payload = np.ascontiguousarray(np.frombuffer(bytes(payload), dtype=np.uint8))
+        out = np.zeros(len(payload) + 64, np.uint8)
+        n = self.lib.ref_make_data_frame(src.encode(), dst.encode(), seq, payload, len(payload), out, len(out))
+        assert n > 0
+        return out[:n].tobytes()
 
 
 # ---------------------------------------------------------------------------------------------

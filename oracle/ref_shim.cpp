@@ -11,7 +11,15 @@
 
 #include "ultra/types.hpp"
 #include "ultra/fec.hpp"
+#include "ultra/ofdm.hpp"
+#include "ultra/dsp.hpp"
 #include "ultra/logging.hpp"
+#include "ofdm/demodulator_impl.hpp"      // private Impl, reached with -fno-access-control (taps)
+#include "fec/frame_interleaver.hpp"
+#include "fec/ldpc_codec.hpp"
+#include "protocol/frame_v2.hpp"
+
+#include "ria_b200.h"                     // POD config / status structs shared with the product ABI
 
 #include <cstdint>
 #include <cstring>
@@ -81,6 +89,193 @@ void ref_ldpc_decode_batch(void* h, const float* llr, int n_cw, uint8_t* out, in
         std::memset(out + static_cast<size_t>(c) * out_stride, 0, out_stride);
         std::memcpy(out + static_cast<size_t>(c) * out_stride, b.data(), n);
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// OFDM  (include/ultra/ofdm.hpp)
+// ---------------------------------------------------------------------------------------------
+static ModemConfig to_cfg(const ria_modem_config* c) {
+    ModemConfig m;
+    m.sample_rate = c->sample_rate;
+    m.center_freq = c->center_freq;
+    m.fft_size = c->fft_size;
+    m.num_carriers = c->num_carriers;
+    m.cp_mode = static_cast<CyclicPrefixMode>(c->cp_mode);
+    m.symbol_guard = c->symbol_guard;
+    m.use_pilots = c->use_pilots != 0;
+    m.pilot_spacing = c->pilot_spacing;
+    m.modulation = static_cast<Modulation>(c->modulation);
+    return m;
+}
+
+// TX of one frame exactly as OFDMChirpWaveform does after the chirp:
+// generateTrainingSymbols(2) (modulator.cpp:528-582) + modulate(data, mod) (modulator.cpp:348-477).
+int ref_ofdm_tx_frame(const ria_modem_config* c, const uint8_t* data, int len, float* out, int cap) {
+    ModemConfig m = to_cfg(c);
+    OFDMModulator mod(m);
+    Samples tr = mod.generateTrainingSymbols(static_cast<int>(c->training_symbols));
+    Samples d = mod.modulate(ByteSpan(data, static_cast<size_t>(len)), m.modulation);
+    int n = static_cast<int>(tr.size() + d.size());
+    if (n > cap) return -n;
+    std::memcpy(out, tr.data(), tr.size() * sizeof(float));
+    std::memcpy(out + tr.size(), d.data(), d.size() * sizeof(float));
+    return n;
+}
+
+struct RefOfdmDemod {
+    ModemConfig cfg;
+    OFDMDemodulator dem;
+    explicit RefOfdmDemod(const ModemConfig& m) : cfg(m), dem(m) {}
+};
+
+void* ref_ofdm_demod_new(const ria_modem_config* c) { return new RefOfdmDemod(to_cfg(c)); }
+void ref_ofdm_demod_free(void* h) { delete static_cast<RefOfdmDemod*>(h); }
+
+// What OFDMChirpWaveform::process does with one frame (ofdm_chirp_waveform.cpp:391-468):
+// setFrequencyOffsetWithPhase(cfo, phase); processPresynced(samples, training); drain soft bits.
+// Returns processPresynced's bool.  h_lts/bins are optional taps read from the private Impl.
+int ref_ofdm_process_presynced(void* h, const float* samples, int n, float cfo_hz, float phase,
+                               float* soft, int soft_cap, int* n_soft, float* snr_db,
+                               float* cfo_out, float* fading, float* h_final /*[num_carriers][2]*/) {
+    auto* d = static_cast<RefOfdmDemod*>(h);
+    d->dem.reset();
+    d->dem.setFrequencyOffsetWithPhase(cfo_hz, phase);
+    bool ready = d->dem.processPresynced(SampleSpan(samples, static_cast<size_t>(n)), 2);
+    if (snr_db) *snr_db = d->dem.getEstimatedSNR();
+    if (cfo_out) *cfo_out = d->dem.getFrequencyOffset();
+    if (fading) *fading = d->dem.getFadingIndex();
+    if (h_final) {
+        auto& im = *d->dem.impl_;
+        for (size_t i = 0; i < im.all_carrier_fft_indices.size(); ++i) {
+            Complex v = im.channel_estimate[im.all_carrier_fft_indices[i]];
+            h_final[2 * i] = v.real();
+            h_final[2 * i + 1] = v.imag();
+        }
+    }
+    int total = 0;
+    for (;;) {
+        std::vector<float> chunk = d->dem.getSoftBits();
+        if (chunk.empty()) break;
+        if (total + static_cast<int>(chunk.size()) <= soft_cap)
+            std::memcpy(soft + total, chunk.data(), chunk.size() * sizeof(float));
+        total += static_cast<int>(chunk.size());
+    }
+    *n_soft = total;
+    return ready ? 1 : 0;
+}
+
+// ultra::FFT::forward (src/dsp/fft.cpp:130-146), interleaved re/im
+void ref_fft_forward(int size, const float* in, float* out) {
+    FFT fft(static_cast<size_t>(size));
+    fft.forward(reinterpret_cast<const Complex*>(in), reinterpret_cast<Complex*>(out));
+}
+
+// Per-symbol taps: toBaseband + extractSymbol (channel_equalizer.cpp:99-187) of the first
+// n_sym symbols of a frame with the mixer running from 0, CFO correction as given.
+// bins: [n_sym][num_carriers][2] in logical carrier order.
+void ref_ofdm_symbol_bins(void* h, const float* samples, int n_sym, float cfo_hz, float phase, float* bins) {
+    auto* d = static_cast<RefOfdmDemod*>(h);
+    d->dem.reset();
+    d->dem.setFrequencyOffsetWithPhase(cfo_hz, phase);
+    auto& im = *d->dem.impl_;
+    im.mixer.reset();
+    const size_t L = im.symbol_samples;
+    const size_t nc = im.all_carrier_fft_indices.size();
+    for (int s = 0; s < n_sym; ++s) {
+        auto bb = im.toBaseband(SampleSpan(samples + s * L, L));
+        auto fd = im.extractSymbol(bb, 0);
+        for (size_t i = 0; i < nc; ++i) {
+            Complex v = fd[im.all_carrier_fft_indices[i]];
+            bins[(s * nc + i) * 2] = v.real();
+            bins[(s * nc + i) * 2 + 1] = v.imag();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed 4-codeword frame  (src/protocol/frame_v2.cpp:1285-1385)
+// ---------------------------------------------------------------------------------------------
+int ref_encode_fixed_frame(const uint8_t* data, int len, int rate, int use_ci, int bps, uint8_t* out, int cap) {
+    Bytes in(data, data + len);
+    Bytes coded = protocol::v2::encodeFixedFrame(in, static_cast<CodeRate>(rate), use_ci != 0, static_cast<size_t>(bps));
+    int n = static_cast<int>(coded.size());
+    if (n > cap) return -n;
+    std::memcpy(out, coded.data(), coded.size());
+    return n;
+}
+
+// First pass of decodeFixedFrame composed from the reference's own pieces, no retry ladder:
+// FrameInterleaver::deinterleave -> ChannelInterleaver::deinterleave -> decodeSoft x4.
+void ref_frame_decode_first_pass(const float* soft, int rate, int use_ci, int bps,
+                                 uint8_t* data /*[4*bytes_per_cw]*/, uint8_t* ok, int32_t* iters) {
+    using namespace fec;
+    std::vector<float> v(soft, soft + FrameInterleaver::TOTAL_FRAME_BITS);
+    auto cws = FrameInterleaver::deinterleave(v);
+    CodeRate r = static_cast<CodeRate>(rate);
+    LDPCDecoder dec(r);
+    dec.setMaxIterations(LDPCCodec::getRecommendedIterations(r));
+    dec.setMinSumFactor(0.9375f);
+    size_t bpc = protocol::v2::getBytesPerCodeword(r);
+    std::unique_ptr<ChannelInterleaver> il;
+    if (use_ci) il = std::make_unique<ChannelInterleaver>(static_cast<size_t>(bps), 648);
+    for (int c = 0; c < 4; ++c) {
+        std::vector<float> bits = cws[c];
+        if (il) bits = il->deinterleave(bits);
+        Bytes b = dec.decodeSoft(bits);
+        ok[c] = dec.lastDecodeSuccess() ? 1 : 0;
+        iters[c] = dec.lastIterations();
+        std::memset(data + c * bpc, 0, bpc);
+        if (ok[c] && b.size() >= bpc) std::memcpy(data + c * bpc, b.data(), bpc);
+    }
+}
+
+// The reference's complete decodeFixedFrame (with its retry ladder and repair passes).
+void ref_decode_fixed_frame_full(const float* soft, int n_soft, int rate, int use_ci, int bps,
+                                 uint8_t* data, uint8_t* ok) {
+    std::vector<float> v(soft, soft + n_soft);
+    CodeRate r = static_cast<CodeRate>(rate);
+    auto st = protocol::v2::decodeFixedFrame(v, r, use_ci != 0, static_cast<size_t>(bps));
+    size_t bpc = protocol::v2::getBytesPerCodeword(r);
+    for (int c = 0; c < 4; ++c) {
+        ok[c] = st.decoded[c] ? 1 : 0;
+        std::memset(data + c * bpc, 0, bpc);
+        if (st.decoded[c] && st.data[c].size() >= bpc) std::memcpy(data + c * bpc, st.data[c].data(), bpc);
+    }
+}
+
+// v2::parseHeader (frame_v2.cpp:1195-1253) + DataFrame::deserialize frame CRC (:555-600)
+void ref_parse_header(const uint8_t* data, int len, ria_frame_status* st) {
+    Bytes b(data, data + len);
+    auto hi = protocol::v2::parseHeader(b);
+    st->header_valid = hi.valid ? 1 : 0;
+    st->type = static_cast<uint8_t>(hi.type);
+    st->seq = hi.seq;
+    st->src_hash = hi.src_hash;
+    st->dst_hash = hi.dst_hash;
+    st->total_cw = hi.total_cw;
+    st->payload_len = hi.payload_len;
+    st->frame_crc_ok = 0;
+    if (hi.valid && !hi.is_control) {
+        auto f = protocol::v2::DataFrame::deserialize(ByteSpan(data, static_cast<size_t>(len)));
+        st->frame_crc_ok = f.has_value() ? 1 : 0;
+    }
+}
+
+uint16_t ref_crc16(const uint8_t* data, int len) {
+    return protocol::v2::ControlFrame::calculateCRC(data, static_cast<size_t>(len));
+}
+
+// Build a serialized v2 data frame (DataFrame::makeData + serialize) for test inputs.
+int ref_make_data_frame(const char* src, const char* dst, int seq, const uint8_t* payload, int len,
+                        uint8_t* out, int cap) {
+    Bytes p(payload, payload + len);
+    auto f = protocol::v2::DataFrame::makeData(src, dst, static_cast<uint16_t>(seq), p);
+    Bytes s = f.serialize();
+    int n = static_cast<int>(s.size());
+    if (n > cap) return -n;
+    std::memcpy(out, s.data(), s.size());
+    return n;
 }
 
 }  // extern "C"

@@ -6,5 +6,6 @@ There is no CPU fallback.
 """
 from ._lib import Context, RiaError, LIB_PATH, exported_symbols, lib  # noqa: F401
 from . import fec  # noqa: F401
+from . import ofdm  # noqa: F401
 
-__all__ = ["Context", "RiaError", "LIB_PATH", "exported_symbols", "lib", "fec"]
+__all__ = ["Context", "RiaError", "LIB_PATH", "exported_symbols", "lib", "fec", "ofdm"]

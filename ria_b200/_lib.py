@@ -34,6 +34,21 @@ _SIGNATURES = {
     "ria_ldpc_get_matrix": (_i32, [_i32, _vp, _vp]),
     "ria_ldpc_decode_batch_dev": (_i32, [_vp, _i32, _i32, _f32, _vp, _i64, _vp, _i32, _vp, _vp]),
     "ria_ldpc_decode_batch_host": (_i32, [_vp, _i32, _i32, _f32, _vp, _i64, _vp, _i32, _vp, _vp]),
+    "ria_modem_config_for": (_i32, [_i32, _i32, _vp]),
+    "ria_ofdm_symbol_samples": (_i32, [_vp]),
+    "ria_ofdm_data_carriers": (_i32, [_vp]),
+    "ria_ofdm_pilot_carriers": (_i32, [_vp]),
+    "ria_ofdm_presynced_batch_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64,
+                                            _vp, _i32, _vp, _vp, _vp, _vp]),
+    "ria_ofdm_presynced_batch_taps_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64,
+                                                 _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ria_frame_decode_batch_dev": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _vp]),
+    "ria_ofdm_rx_frames_dev": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _i64,
+                                      _vp, _vp, _vp]),
+    "ria_ofdm_rx_frames_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _i64,
+                                       _vp, _vp, _vp]),
+    "ria_crc16": (C.c_uint16, [_vp, C.c_size_t]),
+    "ria_channel_interleaver_step": (_i32, [_i32, _i32]),
 }
 
 

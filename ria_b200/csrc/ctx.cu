@@ -34,6 +34,16 @@ int ensure_stage(ria_ctx* ctx, int which, size_t dev_bytes, size_t pin_bytes) {
     return RIA_OK;
 }
 
+int ensure_scratch(ria_ctx* ctx, size_t bytes) {
+    if (bytes > ctx->scratch_bytes) {
+        if (ctx->scratch) RIA_CUDA(ctx, cudaFree(ctx->scratch));
+        ctx->scratch = nullptr; ctx->scratch_bytes = 0;
+        RIA_CUDA(ctx, cudaMalloc(&ctx->scratch, bytes));
+        ctx->scratch_bytes = bytes;
+    }
+    return RIA_OK;
+}
+
 }  // namespace ria
 
 extern "C" const char* ria_version(void) { return "ria_b200 0.1 (sm_100a)"; }
@@ -88,6 +98,8 @@ extern "C" int ria_ctx_destroy(ria_ctx* ctx) {
         if (t.chk_var) cudaFree(t.chk_var);
         if (t.var_slot) cudaFree(t.var_slot);
     }
+    for (auto* t : ctx->ofdm_tables) ria::ofdm_tables_free(t);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->work_counter) cudaFree(ctx->work_counter);
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);

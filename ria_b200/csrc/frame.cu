@@ -1,0 +1,263 @@
+// Fixed 4-codeword frame decode (first pass of v2::decodeFixedFrame) and the fused OFDM receive
+// chain entry points.
+//
+//   ria_frame_decode_batch_dev : FrameInterleaver::deinterleave + ChannelInterleaver::deinterleave
+//                                (fused into the LDPC kernel's load, ldpc.cu) -> 4 x decodeSoft ->
+//                                reassemble + v2::parseHeader + CRC-16 (this file)
+//   ria_ofdm_rx_frames_dev/host: OFDM presynced demod (ofdm.cu) -> frame decode, one call
+//
+// Reference: src/protocol/frame_v2.cpp:1335-1385, 1548-1556 (decodeFixedFrame first pass),
+// :115-128 (CRC-16/CCITT-FALSE), :1195-1253 (parseHeader), :555-600 (frame CRC),
+// src/protocol/frame_v2.hpp:222-228 (isControlFrame), :676-692 (bytes per codeword).
+
+#include "ofdm_tables.h"
+
+namespace ria {
+
+int ldpc_launch(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor, const float* llr_dev, int64_t n_cw,
+                int frame_mode, int soft_stride, int step,
+                uint8_t* info_dev, int info_stride, uint8_t* ok_dev, int32_t* iters_dev);
+
+namespace {
+
+constexpr int kFrameBits = 4 * RIA_LDPC_N;     // FrameInterleaver::TOTAL_FRAME_BITS = 2592
+constexpr int kInfoStride = 64;                // per-codeword info bytes in the scratch buffer
+
+// LDPCCodec::getRecommendedIterations, src/fec/ldpc_codec.hpp:86-96
+int recommended_iterations(int rate) {
+    switch (rate) {
+        case RIA_R3_4: return 60;
+        case RIA_R2_3: return 70;
+        case RIA_R1_2: return 80;
+        case RIA_R1_3: return 60;
+        case RIA_R1_4: return 50;
+        default: return 50;
+    }
+}
+
+__device__ __forceinline__ uint16_t crc16_dev(const uint8_t* d, int len) {
+    uint16_t crc = 0xFFFF;
+    for (int i = 0; i < len; ++i) {
+        crc ^= static_cast<uint16_t>(static_cast<uint16_t>(d[i]) << 8);
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+            crc = (crc & 0x8000) ? static_cast<uint16_t>((crc << 1) ^ 0x1021) : static_cast<uint16_t>(crc << 1);
+    }
+    return crc;
+}
+
+__device__ __forceinline__ bool is_control_frame(uint8_t t) {
+    return t == 0x10 || t == 0x11 || t == 0x16 || t == 0x17 || t == 0x20 || t == 0x21 || t == 0x15 || t == 0x40;
+}
+
+// One thread per frame: reassemble the 4 x bytes_per_cw info bytes (failed codewords stay zero,
+// CodewordStatus::data is only filled on success), parse the header and check the CRCs.
+__global__ void frame_status_kernel(const uint8_t* __restrict__ info, const uint8_t* __restrict__ ok,
+                                    const int32_t* __restrict__ iters, long long n_frames, int bpc,
+                                    uint8_t* __restrict__ data, ria_frame_status* __restrict__ status) {
+    const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (f >= n_frames) return;
+    uint8_t* out = data + f * 4 * bpc;
+    ria_frame_status st;
+    memset(&st, 0, sizeof st);
+    bool all = true;
+    for (int c = 0; c < 4; ++c) {
+        const long long cw = f * 4 + c;
+        st.cw_ok[c] = ok[cw];
+        st.cw_iters[c] = iters[cw];
+        all = all && ok[cw];
+        for (int b = 0; b < bpc; ++b) out[c * bpc + b] = ok[cw] ? info[cw * kInfoStride + b] : 0;
+    }
+    st.all_ok = all ? 1 : 0;
+    // v2::parseHeader on codeword 0 (needs >= 20 bytes and a decoded CW0, reassemble():1030-1051)
+    if (st.cw_ok[0] && bpc >= 20) {
+        const uint8_t* h = out;
+        const uint16_t magic = static_cast<uint16_t>((h[0] << 8) | h[1]);
+        if (magic == 0x554C) {
+            st.type = h[2];
+            st.seq = static_cast<uint16_t>((h[4] << 8) | h[5]);
+            st.src_hash = (static_cast<uint32_t>(h[6]) << 16) | (static_cast<uint32_t>(h[7]) << 8) | h[8];
+            st.dst_hash = (static_cast<uint32_t>(h[9]) << 16) | (static_cast<uint32_t>(h[10]) << 8) | h[11];
+            if (is_control_frame(st.type)) {
+                const uint16_t rx = static_cast<uint16_t>((h[18] << 8) | h[19]);
+                if (rx == crc16_dev(h, 18)) { st.header_valid = 1; st.total_cw = 1; st.payload_len = 0; }
+            } else {
+                st.total_cw = h[12];
+                st.payload_len = static_cast<uint16_t>((h[13] << 8) | h[14]);
+                const uint16_t rx = static_cast<uint16_t>((h[15] << 8) | h[16]);
+                if (rx == crc16_dev(h, 15)) st.header_valid = 1;
+                // frame CRC over header + payload (DataFrame::deserialize :590-596); needs every
+                // codeword that carries part of the frame
+                const int expected = 17 + st.payload_len + 2;
+                if (st.header_valid && expected <= 4 * bpc) {
+                    bool have = true;
+                    for (int c = 0; c < 4; ++c) if (c * bpc < expected && !st.cw_ok[c]) have = false;
+                    if (have) {
+                        const uint16_t frx = static_cast<uint16_t>((h[expected - 2] << 8) | h[expected - 1]);
+                        st.frame_crc_ok = (frx == crc16_dev(h, expected - 2)) ? 1 : 0;
+                    }
+                }
+            }
+        }
+    }
+    status[f] = st;
+}
+
+int bytes_per_codeword(int rate) {
+    int k = 0;
+    if (ria_ldpc_params(rate, &k, nullptr, nullptr) != RIA_OK) return -1;
+    return k / 8;
+}
+
+// scratch layout for n frames: info [4n][64] | ok [4n] | iters [4n] (+ llr [n][llr_stride] for the chain)
+struct Scratch {
+    uint8_t* info; uint8_t* ok; int32_t* iters; float* llr; int32_t* n_llr;
+};
+
+int carve_scratch(ria_ctx* ctx, int64_t n_frames, int llr_stride, Scratch& s) {
+    const size_t n_cw = static_cast<size_t>(n_frames) * 4;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+    const size_t o_info = take(n_cw * kInfoStride);
+    const size_t o_ok = take(n_cw);
+    const size_t o_it = take(n_cw * 4);
+    const size_t o_llr = take(static_cast<size_t>(n_frames) * llr_stride * 4);
+    const size_t o_nl = take(static_cast<size_t>(n_frames) * 4);
+    int rc = ensure_scratch(ctx, off);
+    if (rc != RIA_OK) return rc;
+    unsigned char* b = static_cast<unsigned char*>(ctx->scratch);
+    s.info = b + o_info; s.ok = b + o_ok; s.iters = reinterpret_cast<int32_t*>(b + o_it);
+    s.llr = reinterpret_cast<float*>(b + o_llr); s.n_llr = reinterpret_cast<int32_t*>(b + o_nl);
+    return RIA_OK;
+}
+
+int frame_decode_impl(ria_ctx* ctx, int rate, int use_ci, int bits_per_symbol, const float* soft_dev,
+                      int32_t soft_stride, int64_t n_frames, const Scratch& s, uint8_t* data_dev,
+                      ria_frame_status* status_dev) {
+    const int bpc = bytes_per_codeword(rate);
+    if (bpc < 0) return set_error(ctx, RIA_E_INVAL, "frame: bad rate %d", rate);
+    int step = 0;
+    if (use_ci) {
+        if (bits_per_symbol <= 0) return set_error(ctx, RIA_E_INVAL, "frame: bits_per_symbol must be > 0");
+        step = channel_interleaver_step(bits_per_symbol, RIA_LDPC_N);
+    }
+    int rc = ldpc_launch(ctx, rate, recommended_iterations(rate), 0.9375f, soft_dev, n_frames * 4,
+                         1, soft_stride, step, s.info, kInfoStride, s.ok, s.iters);
+    if (rc != RIA_OK) return rc;
+    const int threads = 128;
+    const unsigned blocks = static_cast<unsigned>((n_frames + threads - 1) / threads);
+    frame_status_kernel<<<blocks, threads, 0, ctx->stream>>>(s.info, s.ok, s.iters, n_frames, bpc, data_dev, status_dev);
+    RIA_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return RIA_OK;
+}
+
+}  // namespace
+}  // namespace ria
+
+extern "C" int ria_frame_decode_batch_dev(ria_ctx* ctx, int rate, int use_channel_interleave,
+                                          int bits_per_symbol, const float* soft_dev, int32_t soft_stride,
+                                          int64_t n_frames, uint8_t* data_dev, ria_frame_status* status_dev) {
+    using namespace ria;
+    if (!ctx) return RIA_E_INVAL;
+    if (n_frames < 0) return set_error(ctx, RIA_E_INVAL, "frame: negative size");
+    if (n_frames == 0) return RIA_OK;
+    if (!soft_dev || !data_dev || !status_dev) return set_error(ctx, RIA_E_INVAL, "frame: null buffer");
+    if (soft_stride < kFrameBits) return set_error(ctx, RIA_E_INVAL, "frame: need >= 2592 soft bits per frame");
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    Scratch s{};
+    int rc = carve_scratch(ctx, n_frames, 0, s);
+    if (rc != RIA_OK) return rc;
+    return frame_decode_impl(ctx, rate, use_channel_interleave, bits_per_symbol, soft_dev, soft_stride, n_frames,
+                             s, data_dev, status_dev);
+}
+
+extern "C" int ria_ofdm_rx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg, int rate,
+                                      int use_channel_interleave,
+                                      const float* samples_dev, int64_t frame_stride, int32_t frame_len,
+                                      const float* cfo_hz_dev, const float* phase_dev, int64_t n_frames,
+                                      uint8_t* data_dev, ria_frame_status* status_dev, float* snr_db_dev) {
+    using namespace ria;
+    if (!ctx || !cfg) return RIA_E_INVAL;
+    if (n_frames < 0) return set_error(ctx, RIA_E_INVAL, "rx: negative size");
+    if (n_frames == 0) return RIA_OK;
+    if (!samples_dev || !data_dev || !status_dev) return set_error(ctx, RIA_E_INVAL, "rx: null buffer");
+    if (const char* err = ofdm_config_error(*cfg)) return set_error(ctx, RIA_E_UNSUPPORTED, "ofdm: %s", err);
+    const int sym = ofdm_symbol_samples(*cfg);
+    const int nd = ria_ofdm_data_carriers(cfg);
+    const int bps = nd * ofdm_bits_per_carrier(cfg->modulation);
+    const int n_sym = frame_len / sym;
+    const int n_llr = (n_sym > 2 ? n_sym - 2 : 0) * bps;
+    if (n_llr < kFrameBits)
+        return set_error(ctx, RIA_E_INVAL, "rx: frame_len %d yields %d soft bits, a 4-codeword frame needs 2592", frame_len, n_llr);
+    const int llr_stride = (n_llr + 3) & ~3;
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    Scratch s{};
+    int rc = carve_scratch(ctx, n_frames, llr_stride, s);
+    if (rc != RIA_OK) return rc;
+    rc = ria_ofdm_presynced_batch_dev(ctx, cfg, samples_dev, frame_stride, frame_len, cfo_hz_dev, phase_dev, n_frames,
+                                      s.llr, llr_stride, s.n_llr, snr_db_dev, nullptr, nullptr);
+    if (rc != RIA_OK) return rc;
+    return frame_decode_impl(ctx, rate, use_channel_interleave, bps, s.llr, llr_stride, n_frames, s, data_dev, status_dev);
+}
+
+extern "C" int ria_ofdm_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg, int rate,
+                                       int use_channel_interleave,
+                                       const float* samples, int64_t frame_stride, int32_t frame_len,
+                                       const float* cfo_hz, const float* phase, int64_t n_frames,
+                                       uint8_t* data, ria_frame_status* status, float* snr_db) {
+    using namespace ria;
+    if (!ctx || !cfg) return RIA_E_INVAL;
+    if (n_frames < 0 || frame_len <= 0 || frame_stride < frame_len) return set_error(ctx, RIA_E_INVAL, "rx: bad sizes");
+    if (n_frames == 0) return RIA_OK;
+    if (!samples || !data || !status) return set_error(ctx, RIA_E_INVAL, "rx: null buffer");
+    const int bpc = bytes_per_codeword(rate);
+    if (bpc < 0) return set_error(ctx, RIA_E_INVAL, "rx: bad rate %d", rate);
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    // Chunked pipeline on the context stream with two staging buffers; the H2D of chunk c+1 is
+    // issued on the copy stream so it overlaps the kernels of chunk c.
+    const int64_t chunk = 8192;
+    const size_t in_b = static_cast<size_t>(chunk) * frame_len * sizeof(float);
+    const size_t aux_b = static_cast<size_t>(chunk) * 8;                       // cfo + phase
+    const size_t out_b = static_cast<size_t>(chunk) * (4 * bpc + sizeof(ria_frame_status) + 4);
+    for (int b = 0; b < 2; ++b) {
+        int rc = ensure_stage(ctx, b, in_b + aux_b + out_b + 1024, 0);
+        if (rc != RIA_OK) return rc;
+    }
+    cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+    // stage_ev[0..1]: "compute of buffer b finished"  stage_ev[2..3]: "H2D of buffer b finished"
+    int buf = 0;
+    for (int64_t off = 0; off < n_frames; off += chunk, buf ^= 1) {
+        const int64_t n = (n_frames - off < chunk) ? (n_frames - off) : chunk;
+        unsigned char* base = static_cast<unsigned char*>(ctx->stage_dev[buf]);
+        float* d_samp = reinterpret_cast<float*>(base);
+        float* d_cfo = reinterpret_cast<float*>(base + in_b);
+        float* d_ph = d_cfo + chunk;
+        ria_frame_status* d_st = reinterpret_cast<ria_frame_status*>(base + in_b + aux_b);
+        float* d_snr = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(d_st) + static_cast<size_t>(chunk) * sizeof(ria_frame_status));
+        uint8_t* d_data = reinterpret_cast<uint8_t*>(d_snr + chunk);
+        // buffer reuse: wait until the kernels + D2H that used it two chunks ago are done
+        RIA_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->stage_ev[buf], 0));
+        if (frame_stride == frame_len) {
+            RIA_CUDA(ctx, cudaMemcpyAsync(d_samp, samples + off * frame_stride, static_cast<size_t>(n) * frame_len * sizeof(float),
+                                          cudaMemcpyHostToDevice, cs));
+        } else {
+            RIA_CUDA(ctx, cudaMemcpy2DAsync(d_samp, static_cast<size_t>(frame_len) * 4, samples + off * frame_stride,
+                                            static_cast<size_t>(frame_stride) * 4, static_cast<size_t>(frame_len) * 4,
+                                            static_cast<size_t>(n), cudaMemcpyHostToDevice, cs));
+        }
+        if (cfo_hz) RIA_CUDA(ctx, cudaMemcpyAsync(d_cfo, cfo_hz + off, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, cs));
+        if (phase) RIA_CUDA(ctx, cudaMemcpyAsync(d_ph, phase + off, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, cs));
+        RIA_CUDA(ctx, cudaEventRecord(ctx->stage_ev[2 + buf], cs));
+        RIA_CUDA(ctx, cudaStreamWaitEvent(s, ctx->stage_ev[2 + buf], 0));
+        int rc = ria_ofdm_rx_frames_dev(ctx, cfg, rate, use_channel_interleave, d_samp, frame_len, frame_len,
+                                        cfo_hz ? d_cfo : nullptr, phase ? d_ph : nullptr, n, d_data, d_st, d_snr);
+        if (rc != RIA_OK) return rc;
+        RIA_CUDA(ctx, cudaMemcpyAsync(data + off * 4 * bpc, d_data, static_cast<size_t>(n) * 4 * bpc, cudaMemcpyDeviceToHost, s));
+        RIA_CUDA(ctx, cudaMemcpyAsync(status + off, d_st, static_cast<size_t>(n) * sizeof(ria_frame_status), cudaMemcpyDeviceToHost, s));
+        if (snr_db) RIA_CUDA(ctx, cudaMemcpyAsync(snr_db + off, d_snr, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, s));
+        RIA_CUDA(ctx, cudaEventRecord(ctx->stage_ev[buf], s));
+    }
+    RIA_CUDA(ctx, cudaStreamSynchronize(s));
+    return RIA_OK;
+}

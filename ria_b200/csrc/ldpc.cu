@@ -44,6 +44,12 @@ __device__ __forceinline__ float clamp50(float x) {
     return (-50.0f < y) ? y : -50.0f;
 }
 
+struct LdpcGather {
+    int frame_mode;     // 0: llr_g is [n_cw][648];  1: llr_g is [n_frames][soft_stride], n_cw = 4 n_frames
+    int soft_stride;
+    int step;           // ChannelInterleaver step, 0 = no channel interleaving
+};
+
 struct CheckIn {
     float v[7];      // v2c per slot (0..5 info, 6 identity)
     int cnt;         // number of info edges
@@ -78,7 +84,7 @@ __device__ __forceinline__ void check_update(const CheckIn& in, float factor, fl
 
 template <int W>
 __global__ void __launch_bounds__(W * 32)
-ldpc_decode_kernel(const float* __restrict__ llr_g, long long n_cw,
+ldpc_decode_kernel(const float* __restrict__ llr_g, long long n_cw, const LdpcGather gather,
                    const uint16_t* __restrict__ chk_var_g, const uint16_t* __restrict__ var_slot_g,
                    int k, int m, int dv_max, int max_iter, float factor,
                    uint8_t* __restrict__ info_g, int info_stride,
@@ -105,8 +111,6 @@ ldpc_decode_kernel(const float* __restrict__ llr_g, long long n_cw,
     }
     __syncthreads();
 
-    const int kbytes = (k + 7) >> 3;
-
     for (;;) {
         long long cw;
         {
@@ -116,11 +120,24 @@ ldpc_decode_kernel(const float* __restrict__ llr_g, long long n_cw,
         }
         if (cw >= n_cw) break;
 
-        // ---- load the codeword's 648 LLRs (162 x float4, coalesced, streaming) ----
-        {
+        if (!gather.frame_mode) {
+            // ---- load the codeword's 648 LLRs (162 x float4, coalesced, streaming) ----
             const float4* src = reinterpret_cast<const float4*>(llr_g + cw * kN);
             float4* dst = reinterpret_cast<float4*>(llr);
             for (int i = lane; i < kN / 4; i += 32) dst[i] = __ldcs(src + i);
+        } else {
+            // ---- fixed 4-codeword frame: codeword c of frame f, de-interleaved on the fly ----
+            // FrameInterleaver::deinterleave (src/fec/frame_interleaver.cpp:37-47, 96-124):
+            //   cw_soft[c][b] = frame_soft[4 b + (c + b) % 4]
+            // ChannelInterleaver::deinterleave (src/fec/ldpc_decoder.cpp:600-625):
+            //   out[p] = cw_soft[(p * step) % 648]
+            const long long fr = cw >> 2;
+            const int c = static_cast<int>(cw & 3);
+            const float* src = llr_g + fr * gather.soft_stride;
+            for (int p = lane; p < kN; p += 32) {
+                const int b = gather.step ? (p * gather.step) % kN : p;
+                llr[p] = __ldg(src + 4 * b + ((c + b) & 3));
+            }
         }
         __syncwarp();
         for (int j = lane; j < k; j += 32) tot[j] = llr[j];
@@ -188,7 +205,7 @@ ldpc_decode_kernel(const float* __restrict__ llr_g, long long n_cw,
         }
 
         // ---- outputs: pack info hard bits MSB-first (ldpc_decoder.cpp:240-257) ----
-        for (int b = lane; b < kbytes; b += 32) {
+        for (int b = lane; b < info_stride; b += 32) {     // bytes past ceil(k/8) are zeroed
             unsigned byte = 0;
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
@@ -237,6 +254,12 @@ int ldpc_tables_dev(ria_ctx* ctx, int rate, const LdpcCodeDev** out) {
 
 }  // namespace ria
 
+namespace ria {
+int ldpc_launch(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor, const float* llr_dev, int64_t n_cw,
+                int frame_mode, int soft_stride, int step,
+                uint8_t* info_dev, int info_stride, uint8_t* ok_dev, int32_t* iters_dev);
+}
+
 extern "C" int ria_ldpc_decode_batch_dev(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor,
                                          const float* llr_dev, int64_t n_cw,
                                          uint8_t* info_dev, int info_stride,
@@ -248,6 +271,13 @@ extern "C" int ria_ldpc_decode_batch_dev(ria_ctx* ctx, int rate, int max_iter, f
     if (!llr_dev || !info_dev || !ok_dev || !iters_dev) return set_error(ctx, RIA_E_INVAL, "ldpc: null buffer");
     if ((reinterpret_cast<uintptr_t>(llr_dev) & 15) != 0)
         return set_error(ctx, RIA_E_INVAL, "ldpc: llr_dev must be 16-byte aligned");
+    return ldpc_launch(ctx, rate, max_iter, min_sum_factor, llr_dev, n_cw, 0, 0, 0, info_dev, info_stride, ok_dev, iters_dev);
+}
+
+int ria::ldpc_launch(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor, const float* llr_dev, int64_t n_cw,
+                     int frame_mode, int soft_stride, int step,
+                     uint8_t* info_dev, int info_stride, uint8_t* ok_dev, int32_t* iters_dev) {
+    using namespace ria;
     RIA_CUDA(ctx, cudaSetDevice(ctx->device));
     const LdpcCodeDev* t = nullptr;
     int rc = ldpc_tables_dev(ctx, rate, &t);
@@ -265,8 +295,9 @@ extern "C" int ria_ldpc_decode_batch_dev(ria_ctx* ctx, int rate, int max_iter, f
     long long grid = static_cast<long long>(ctx->sm_count) * ctas_per_sm;
     if (grid > want) grid = want;
     RIA_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int), ctx->stream));
+    LdpcGather gather{frame_mode, soft_stride, step};
     kern<<<static_cast<unsigned>(grid), W * 32, smem, ctx->stream>>>(
-        llr_dev, n_cw, t->chk_var, t->var_slot, t->k, t->m, t->dv_max, max_iter, min_sum_factor,
+        llr_dev, n_cw, gather, t->chk_var, t->var_slot, t->k, t->m, t->dv_max, max_iter, min_sum_factor,
         info_dev, info_stride, ok_dev, iters_dev, ctx->work_counter);
     RIA_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

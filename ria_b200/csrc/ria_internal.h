@@ -32,6 +32,8 @@ struct LdpcCodeHost {
 const LdpcCodeHost& ldpc_code_host(int rate);   // cached, thread-safe; throws on bad rate
 bool ldpc_rate_valid(int rate);
 
+struct OfdmTablesDev;   // ofdm_tables.h
+
 struct LdpcCodeDev {
     bool ready = false;
     int k = 0, m = 0, dv_max = 0;
@@ -53,7 +55,11 @@ struct ria_ctx {
     std::string last_error;
     int64_t launches = 0;
     ria::LdpcCodeDev ldpc[8];
-    unsigned int* work_counter = nullptr;   // device, dynamic tile scheduler
+    unsigned int* work_counter = nullptr;   // device, dynamic tile schedulers (one slot per kernel)
+    std::vector<ria::OfdmTablesDev*> ofdm_tables;
+    // scratch owned by the context for the fused chain entry points
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
     // staging for *_host entry points (grown on demand)
     void* stage_dev[2] = {nullptr, nullptr};
     size_t stage_dev_bytes[2] = {0, 0};
@@ -67,6 +73,9 @@ namespace ria {
 int set_error(ria_ctx* ctx, int code, const char* fmt, ...);
 int ensure_stage(ria_ctx* ctx, int which, size_t dev_bytes, size_t pin_bytes);
 int ldpc_tables_dev(ria_ctx* ctx, int rate, const LdpcCodeDev** out);
+int ofdm_tables_dev(ria_ctx* ctx, const ria_modem_config& cfg, int need_nco, const OfdmTablesDev** out);
+void ofdm_tables_free(OfdmTablesDev* t);
+int ensure_scratch(ria_ctx* ctx, size_t bytes);
 
 }  // namespace ria
 

@@ -1,0 +1,323 @@
+"""Host-side mirror of the reference OFDM receive interfaces over the C ABI.
+
+  * ``ModemConfig``        <- ultra::ModemConfig, RX-relevant fields (include/ultra/types.hpp:193-289)
+  * ``OFDMDemodulator``    <- ultra::OFDMDemodulator presynced path (include/ultra/ofdm.hpp:58-139,
+                              src/ofdm/demodulator.cpp:1212-1221, 1250-1414)
+  * ``OFDMChirpWaveform``  <- the RX half of ultra::OFDMChirpWaveform / IWaveform
+                              (src/waveform/ofdm_chirp_waveform.cpp:79-105, 391-485,
+                               src/waveform/waveform_interface.hpp:47-220)
+  * ``decode_fixed_frame_batch`` <- first pass of v2::decodeFixedFrame
+                              (src/protocol/frame_v2.cpp:1335-1385) + v2::parseHeader
+  * ``OfdmRxChain``        <- the flat batched driver that replaces StreamingDecoder's per-frame
+                              decodeCurrentFrame for a batch of presynced frames.
+
+Batch methods take CUDA tensors (torch is only used for device memory and streams).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ._lib import Context, RiaError, lib
+from .fec import code_params, default_context
+
+# ultra::Modulation (include/ultra/types.hpp:27-39)
+DBPSK, BPSK, DQPSK, QPSK, D8PSK, QAM8, QAM16, QAM32, QAM64 = range(9)
+QAM256 = 10
+_BITS = {DBPSK: 1, BPSK: 1, DQPSK: 2, QPSK: 2, D8PSK: 3, QAM8: 3, QAM16: 4, QAM32: 5, QAM64: 6, QAM256: 8}
+
+
+def getBitsPerSymbol(mod: int) -> int:
+    return _BITS.get(int(mod), 1)
+
+
+class ModemConfig(C.Structure):
+    """ria_modem_config (include/ria_b200.h)."""
+    _fields_ = [(n, C.c_uint32) for n in (
+        "sample_rate", "center_freq", "fft_size", "num_carriers", "cp_mode", "symbol_guard",
+        "use_pilots", "pilot_spacing", "modulation", "training_symbols")]
+
+    @classmethod
+    def default(cls, modulation=QPSK, use_pilots=0, pilot_spacing=2, cp_mode=1, num_carriers=59):
+        """ModemConfig{} defaults of the reference (1024 FFT, 59 carriers, MEDIUM CP)."""
+        return cls(48000, 1500, 1024, num_carriers, cp_mode, 0, use_pilots, pilot_spacing, modulation, 2)
+
+    @classmethod
+    def for_waveform(cls, modulation: int, rate: int):
+        """What OFDMChirpWaveform::configure(mod, rate) produces."""
+        c = cls()
+        if lib().ria_modem_config_for(int(modulation), int(rate), C.addressof(c)) != 0:
+            raise ValueError("bad modulation / rate")
+        return c
+
+    @classmethod
+    def high_throughput(cls, modulation=QAM64):
+        """presets::high_throughput(): pilots every 4th carrier (15 pilots / 44 data)."""
+        return cls.default(modulation, use_pilots=1, pilot_spacing=4)
+
+    def getSymbolDuration(self) -> int:
+        return lib().ria_ofdm_symbol_samples(C.addressof(self))
+
+    def getDataCarriers(self) -> int:
+        return lib().ria_ofdm_data_carriers(C.addressof(self))
+
+    def getPilotCarriers(self) -> int:
+        return lib().ria_ofdm_pilot_carriers(C.addressof(self))
+
+    def bitsPerSymbol(self) -> int:
+        return self.getDataCarriers() * getBitsPerSymbol(self.modulation)
+
+
+class FrameStatus(C.Structure):
+    """ria_frame_status (include/ria_b200.h)."""
+    _fields_ = [("cw_ok", C.c_uint8 * 4), ("cw_iters", C.c_int32 * 4), ("all_ok", C.c_uint8),
+                ("header_valid", C.c_uint8), ("frame_crc_ok", C.c_uint8), ("type", C.c_uint8),
+                ("seq", C.c_uint16), ("payload_len", C.c_uint16), ("src_hash", C.c_uint32),
+                ("dst_hash", C.c_uint32), ("total_cw", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+FRAME_STATUS_DTYPE = np.dtype([
+    ("cw_ok", np.uint8, 4), ("cw_iters", np.int32, 4), ("all_ok", np.uint8), ("header_valid", np.uint8),
+    ("frame_crc_ok", np.uint8), ("type", np.uint8), ("seq", np.uint16), ("payload_len", np.uint16),
+    ("src_hash", np.uint32), ("dst_hash", np.uint32), ("total_cw", np.uint8), ("pad", np.uint8, 3)],
+    align=True)
+assert FRAME_STATUS_DTYPE.itemsize == C.sizeof(FrameStatus)
+
+
+def crc16(data: bytes) -> int:
+    """ControlFrame::calculateCRC (src/protocol/frame_v2.cpp:115-128)."""
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(bytes(data))
+    return int(lib().ria_crc16(C.addressof(buf), len(data)))
+
+
+def channel_interleaver_step(bits_per_symbol: int, total_bits: int = 648) -> int:
+    return int(lib().ria_channel_interleaver_step(int(bits_per_symbol), int(total_bits)))
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class OFDMDemodulator:
+    """Presynced path of ultra::OFDMDemodulator, batched."""
+
+    def __init__(self, config: ModemConfig, ctx: Optional[Context] = None):
+        self.config = config
+        self._ctx = ctx
+        config.getSymbolDuration()
+
+    @property
+    def ctx(self) -> Context:
+        if self._ctx is None:
+            self._ctx = default_context()
+        return self._ctx
+
+    def soft_bits_per_frame(self, frame_len: int) -> int:
+        n_sym = frame_len // self.config.getSymbolDuration()
+        return max(0, n_sym - 2) * self.config.bitsPerSymbol()
+
+    def process_presynced_batch(self, samples: torch.Tensor, cfo_hz: Optional[torch.Tensor] = None,
+                                phase: Optional[torch.Tensor] = None, taps: bool = False):
+        """samples: CUDA fp32 [n_frames, frame_len] (each row starts at the first LTS symbol).
+
+        Returns dict(llr [n, stride], n_llr [n], snr_db, cfo, fading [, bins, h_lts])."""
+        if not (isinstance(samples, torch.Tensor) and samples.is_cuda):
+            raise RiaError("process_presynced_batch wants CUDA tensors (no CPU fallback)")
+        if samples.dtype != torch.float32 or samples.dim() != 2:
+            raise ValueError("samples must be fp32 [n_frames, frame_len]")
+        if samples.stride(1) != 1:
+            samples = samples.contiguous()
+        n, frame_len = samples.shape
+        dev = samples.device
+        n_llr = self.soft_bits_per_frame(frame_len)
+        stride = max(4, (n_llr + 3) & ~3)
+        out = dict(
+            llr=torch.empty((n, stride), dtype=torch.float32, device=dev),
+            n_llr=torch.empty((n,), dtype=torch.int32, device=dev),
+            snr_db=torch.empty((n,), dtype=torch.float32, device=dev),
+            cfo=torch.empty((n,), dtype=torch.float32, device=dev),
+            fading=torch.empty((n,), dtype=torch.float32, device=dev))
+        nc = self.config.num_carriers
+        n_sym = frame_len // self.config.getSymbolDuration()
+        bins = h_lts = None
+        if taps:
+            bins = torch.zeros((n, max(n_sym, 1), nc, 2), dtype=torch.float32, device=dev)
+            h_lts = torch.zeros((n, nc, 2), dtype=torch.float32, device=dev)
+        for t in (cfo_hz, phase):
+            if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.numel() == n):
+                raise ValueError("cfo_hz / phase must be CUDA fp32 [n_frames]")
+        ctx = self.ctx
+        ctx.set_stream(torch.cuda.current_stream(dev))
+        ctx.check(lib().ria_ofdm_presynced_batch_taps_dev(
+            ctx.handle, C.addressof(self.config), _ptr(samples), samples.stride(0), frame_len,
+            _ptr(cfo_hz), _ptr(phase), n, _ptr(out["llr"]), stride, _ptr(out["n_llr"]),
+            _ptr(out["snr_db"]), _ptr(out["cfo"]), _ptr(out["fading"]), _ptr(bins), _ptr(h_lts)))
+        if taps:
+            out["bins"] = torch.view_as_complex(bins)
+            out["h_lts"] = torch.view_as_complex(h_lts)
+        return out
+
+
+def decode_fixed_frame_batch(soft: torch.Tensor, rate: int, use_channel_interleave: bool,
+                             bits_per_symbol: int, ctx: Optional[Context] = None):
+    """First pass of v2::decodeFixedFrame for a batch: soft CUDA fp32 [n, >=2592].
+
+    Returns (data u8 [n, 4*bytes_per_cw], status structured array on the device as uint8 tensor
+    viewable with FRAME_STATUS_DTYPE after .cpu().numpy())."""
+    if not (isinstance(soft, torch.Tensor) and soft.is_cuda and soft.dtype == torch.float32 and soft.dim() == 2):
+        raise RiaError("decode_fixed_frame_batch wants a CUDA fp32 [n, >=2592] tensor")
+    if soft.stride(1) != 1:
+        soft = soft.contiguous()
+    ctx = ctx or default_context()
+    n = soft.shape[0]
+    bpc = code_params(rate)[0] // 8
+    data = torch.empty((n, 4 * bpc), dtype=torch.uint8, device=soft.device)
+    status = torch.empty((n, FRAME_STATUS_DTYPE.itemsize), dtype=torch.uint8, device=soft.device)
+    ctx.set_stream(torch.cuda.current_stream(soft.device))
+    ctx.check(lib().ria_frame_decode_batch_dev(
+        ctx.handle, int(rate), int(bool(use_channel_interleave)), int(bits_per_symbol),
+        _ptr(soft), soft.stride(0), n, _ptr(data), _ptr(status)))
+    return data, status
+
+
+def status_array(status: torch.Tensor) -> np.ndarray:
+    return status.cpu().numpy().view(FRAME_STATUS_DTYPE).reshape(-1)
+
+
+class OfdmRxChain:
+    """Presynced OFDM data frames -> info bytes + per-frame status, one C call per batch."""
+
+    def __init__(self, config: ModemConfig, rate: int, use_channel_interleave: bool = True,
+                 ctx: Optional[Context] = None):
+        self.config = config
+        self.rate = int(rate)
+        self.use_ci = bool(use_channel_interleave)
+        self._ctx = ctx
+        self.bytes_per_cw = code_params(rate)[0] // 8
+
+    @property
+    def ctx(self) -> Context:
+        if self._ctx is None:
+            self._ctx = default_context()
+        return self._ctx
+
+    def process_batch(self, samples: torch.Tensor, cfo_hz=None, phase=None):
+        if not (isinstance(samples, torch.Tensor) and samples.is_cuda and samples.dtype == torch.float32):
+            raise RiaError("process_batch wants CUDA fp32 [n_frames, frame_len] (no CPU fallback)")
+        if samples.stride(1) != 1:
+            samples = samples.contiguous()
+        n, frame_len = samples.shape
+        dev = samples.device
+        data = torch.empty((n, 4 * self.bytes_per_cw), dtype=torch.uint8, device=dev)
+        status = torch.empty((n, FRAME_STATUS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        snr = torch.empty((n,), dtype=torch.float32, device=dev)
+        ctx = self.ctx
+        ctx.set_stream(torch.cuda.current_stream(dev))
+        ctx.check(lib().ria_ofdm_rx_frames_dev(
+            ctx.handle, C.addressof(self.config), self.rate, int(self.use_ci), _ptr(samples),
+            samples.stride(0), frame_len, _ptr(cfo_hz), _ptr(phase), n, _ptr(data), _ptr(status), _ptr(snr)))
+        return data, status, snr
+
+    def process_batch_host(self, samples: np.ndarray, cfo_hz=None, phase=None):
+        """Host buffers (numpy, ideally backed by pinned memory) through ria_ofdm_rx_frames_host."""
+        assert samples.dtype == np.float32 and samples.ndim == 2 and samples.strides[1] == 4
+        n, frame_len = samples.shape
+        data = np.empty((n, 4 * self.bytes_per_cw), np.uint8)
+        status = np.empty(n, FRAME_STATUS_DTYPE)
+        snr = np.empty(n, np.float32)
+        ctx = self.ctx
+        ctx.check(lib().ria_ofdm_rx_frames_host(
+            ctx.handle, C.addressof(self.config), self.rate, int(self.use_ci),
+            samples.ctypes.data, samples.strides[0] // 4, frame_len,
+            cfo_hz.ctypes.data if cfo_hz is not None else None,
+            phase.ctypes.data if phase is not None else None,
+            n, data.ctypes.data, status.ctypes.data, snr.ctypes.data))
+        return data, status, snr
+
+
+class OFDMChirpWaveform:
+    """RX half of ultra::OFDMChirpWaveform (IWaveform) with batch = 1 semantics.
+
+    configure / setFrequencyOffset / setAbsoluteTrainingPosition / process / getSoftBits /
+    estimatedSNR / estimatedCFO / getFadingIndex / reset behave like the reference class
+    (src/waveform/ofdm_chirp_waveform.cpp); detectSync/detectDataSync are provided by
+    ria_b200.sync once the correlator kernels land."""
+
+    def __init__(self, config: Optional[ModemConfig] = None, ctx: Optional[Context] = None):
+        self._ctx = ctx
+        if config is None:
+            # default constructor: 512 FFT / 30 carriers is not a size the batched kernels are
+            # built for; the 1024-FFT profile every tool uses is the default here
+            config = ModemConfig.for_waveform(DQPSK, 2)
+        self.config_ = config
+        self.cfo_hz_ = 0.0
+        self.last_cfo_ = 0.0
+        self.last_snr_ = 0.0
+        self.last_fading_ = 0.0
+        self.training_start_sample_ = 0
+        self.abs_training_start_ = None
+        self.soft_bits_ = np.zeros(0, np.float32)
+        self._dem = OFDMDemodulator(self.config_, ctx)
+
+    def configure(self, mod: int, rate: int) -> None:
+        if mod not in (DBPSK, DQPSK, D8PSK, QPSK, BPSK, QAM16, QAM32, QAM64):
+            mod = DQPSK                                   # ofdm_chirp_waveform.cpp:81-87
+        self.config_ = ModemConfig.for_waveform(mod, rate)
+        self._dem = OFDMDemodulator(self.config_, self._ctx)
+
+    def setFrequencyOffset(self, cfo_hz: float) -> None:
+        self.cfo_hz_ = float(np.float32(cfo_hz))
+
+    def setAbsoluteTrainingPosition(self, pos: int) -> None:
+        self.abs_training_start_ = int(pos)
+
+    def getSamplesPerSymbol(self) -> int:
+        return self.config_.getSymbolDuration()
+
+    def process(self, samples) -> bool:
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        if samples.size < self.getSamplesPerSymbol():
+            return False
+        # initial CFO phase, ofdm_chirp_waveform.cpp:404-413 (fp32 with double-promoted pi)
+        ref = self.abs_training_start_ if self.abs_training_start_ is not None else self.training_start_sample_
+        ph = np.float32(-2.0 * np.pi * np.float64(np.float32(self.cfo_hz_)) * ref / self.config_.sample_rate)
+        # the reference evaluates -2.0f*M_PI*cfo*pos/sample_rate left to right in double
+        while float(ph) > np.pi:
+            ph = np.float32(np.float64(ph) - 2.0 * np.pi)
+        while float(ph) < -np.pi:
+            ph = np.float32(np.float64(ph) + 2.0 * np.pi)
+        dev = torch.device("cuda", self._dem.ctx.device)
+        x = torch.from_numpy(samples).to(dev).unsqueeze(0)
+        cfo = torch.tensor([self.cfo_hz_], dtype=torch.float32, device=dev)
+        pht = torch.tensor([float(ph)], dtype=torch.float32, device=dev)
+        out = self._dem.process_presynced_batch(x, cfo, pht)
+        torch.cuda.synchronize(dev)
+        n = int(out["n_llr"][0].item())
+        ready = n >= 648
+        if ready:
+            self.soft_bits_ = out["llr"][0, :n].cpu().numpy()
+            self.last_snr_ = float(out["snr_db"][0].item())
+            self.cfo_hz_ = float(out["cfo"][0].item())
+            self.last_cfo_ = self.cfo_hz_
+        self.last_fading_ = float(out["fading"][0].item())
+        return ready
+
+    def getSoftBits(self) -> np.ndarray:
+        bits, self.soft_bits_ = self.soft_bits_, np.zeros(0, np.float32)   # moves out (:470-472)
+        return bits
+
+    def estimatedSNR(self) -> float:
+        return self.last_snr_
+
+    def estimatedCFO(self) -> float:
+        return self.last_cfo_ if abs(self.last_cfo_) > 0.1 else self.cfo_hz_
+
+    def getFadingIndex(self) -> float:
+        return self.last_fading_
+
+    def reset(self) -> None:
+        self.soft_bits_ = np.zeros(0, np.float32)
+        self.abs_training_start_ = None               # CFO is preserved across reset (:474-485)

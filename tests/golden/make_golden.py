@@ -57,6 +57,37 @@ def ldpc_golden(ref, out_dir):
     print("ldpc_golden.npz written:", {k: v.shape for k, v in out.items() if k.endswith("iters")})
 
 
+def ofdm_golden(ref, out_dir):
+    from tests.ofdm_common import CASES, apply_cfo, awgn, make_cfg, tx_frame
+    out = {}
+    for name, mod, spacing, use_pilots, rate, snr_db in CASES:
+        cfg = make_cfg(mod, spacing, use_pilots)
+        rng = np.random.default_rng(abs(hash(name)) % (1 << 31) if False else sum(map(ord, name)))
+        rxs, softs, snrs, cfo_out, cfos, phases = [], [], [], [], [], []
+        for i in range(3):
+            tx, _, _ = tx_frame(ref, cfg, rate, rng, seq=i)
+            cfo = (0.0, 1.7, -3.2)[i]
+            rx = awgn(apply_cfo(tx, cfo) if cfo else tx, snr_db, rng)
+            est = np.float32(cfo + (0.0, 0.1, 1.2)[i])
+            ph = np.float32((0.0, 0.5, -2.0)[i])
+            r = ref.ofdm_process_presynced(cfg, rx, float(est), float(ph))
+            rxs.append(rx.astype(np.float16).astype(np.float32))   # store quantised samples (smaller file)
+            r = ref.ofdm_process_presynced(cfg, rxs[-1], float(est), float(ph))
+            softs.append(r["soft"]); snrs.append(r["snr_db"]); cfo_out.append(r["cfo"])
+            cfos.append(est); phases.append(ph)
+        out[f"{name}_rx"] = np.stack(rxs).astype(np.float16)
+        out[f"{name}_soft"] = np.stack(softs)
+        out[f"{name}_snr"] = np.array(snrs, np.float32)
+        out[f"{name}_cfo_out"] = np.array(cfo_out, np.float32)
+        out[f"{name}_cfo"] = np.array(cfos, np.float32)
+        out[f"{name}_phase"] = np.array(phases, np.float32)
+    np.savez_compressed(os.path.join(out_dir, "ofdm_golden.npz"), **out)
+    print("ofdm_golden.npz written")
+
+
 if __name__ == "__main__":
     ref = Ref()
-    ldpc_golden(ref, HERE)
+    if "ldpc" in sys.argv[1:] or len(sys.argv) == 1:
+        ldpc_golden(ref, HERE)
+    if "ofdm" in sys.argv[1:] or len(sys.argv) == 1:
+        ofdm_golden(ref, HERE)

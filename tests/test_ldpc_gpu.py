@@ -136,9 +136,15 @@ def test_full_size_properties(ctx, port):
     okf = ok.bool()
     assert okf.float().mean().item() > 0.97
     want_info = torch.from_numpy(datas).cuda().repeat(n // 256, 1)
-    # a decoder "ok" that is a wrong codeword is possible in principle but rare; bit errors
-    # among ok codewords must be far below the raw channel error rate
-    wrong = (info[okf] != want_info[okf]).any(dim=1).float().mean().item()
+    # The reference's R3/4 H leaves 162 of the 486 info bits with degree 0 (SURVEY.md section 7
+    # "Quirks"): parity can pass while those bits carry raw channel errors.  Bits that ARE in
+    # some check must be right whenever the decoder says ok (undetected errors are rare).
+    row_ptr, edge_var = fec.get_matrix(rate)
+    prot = np.zeros(488, np.uint8)
+    prot[edge_var[edge_var < k]] = 1
+    assert prot[:k].sum() == 324
+    mask = torch.from_numpy(np.packbits(prot)).cuda()
+    wrong = (((info[okf] ^ want_info[okf]) & mask) != 0).any(dim=1).float().mean().item()
     assert wrong < 1e-3
     assert (iters[okf] < 60).all() and (iters[~okf] == 60).all()
     idx = torch.randperm(n, device="cuda", generator=gen)[:4096]
@@ -150,3 +156,6 @@ def test_full_size_properties(ctx, port):
     # noiseless: converges at iteration index 0
     info0, ok0, it0 = dec.decode_batch((8.0 * s[:4096]).contiguous())
     assert ok0.all() and (it0 == 0).all() and (info0 == want_info[:4096]).all()
+    # padding bytes of a wider stride are zeroed
+    info1, _, _ = dec.decode_batch((8.0 * s[:64]).contiguous(), 72)
+    assert (info1[:, 61:] == 0).all() and (info1[:, :61] == want_info[:64]).all()

@@ -1,0 +1,183 @@
+"""GPU: OFDM presynced demod + fixed-frame decode through the C ABI vs the unmodified reference
+(oracle/_ref) on identical received sample buffers, and vs the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.bindings import BITS_PER_CARRIER, BYTES_PER_CW
+from tests.ofdm_common import CASES, apply_cfo, awgn, llr_close, make_cfg, tx_frame
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ofdm_golden.npz")
+
+
+def _to_ria_cfg(cfg):
+    from ria_b200 import ofdm
+    return ofdm.ModemConfig.from_buffer_copy(bytes(cfg))
+
+
+def _run_gpu(ctx, cfg, frames, cfo=None, phase=None, taps=True):
+    import torch
+    from ria_b200 import ofdm
+    dem = ofdm.OFDMDemodulator(_to_ria_cfg(cfg), ctx)
+    x = torch.from_numpy(np.stack(frames)).cuda()
+    c = torch.from_numpy(np.asarray(cfo, np.float32)).cuda() if cfo is not None else None
+    p = torch.from_numpy(np.asarray(phase, np.float32)).cuda() if phase is not None else None
+    out = dem.process_presynced_batch(x, c, p, taps=taps)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def _compare(ref, cfg, frames, out, cfos, phases, exact_bins):
+    worst = 0.0
+    for i, rx in enumerate(frames):
+        r = ref.ofdm_process_presynced(cfg, rx, float(cfos[i]), float(phases[i]))
+        n = int(out["n_llr"][i])
+        assert n == len(r["soft"]), (n, len(r["soft"]))
+        got = out["llr"][i, :n]
+        ok = llr_close(got, r["soft"])
+        assert ok.all(), (i, np.abs(got - r["soft"]).max(), got[~ok][:5], r["soft"][~ok][:5])
+        worst = max(worst, float(np.abs(got - r["soft"]).max()))
+        assert abs(out["snr_db"][i] - r["snr_db"]) <= 1e-3 * max(1.0, abs(r["snr_db"]))
+        assert abs(out["cfo"][i] - r["cfo"]) <= 1e-4 * max(1.0, abs(r["cfo"]))
+        assert abs(out["fading"][i] - r["fading"]) <= 1e-4
+        n_sym = len(rx) // cfg.symbol_samples()
+        bins = ref.ofdm_symbol_bins(cfg, rx, n_sym, float(out["cfo"][i]) if False else float(cfos[i]), float(phases[i]))
+        if exact_bins:
+            # no CFO rotation: every operation of the path is IEEE-exact -> FFT bins bit-identical
+            assert np.array_equal(out["bins"][i][:2], bins[:2].astype(np.complex64))
+    return worst
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_presynced_matches_reference_awgn(ctx, ref, case):
+    name, mod, spacing, use_pilots, rate, snr_db = case
+    cfg = make_cfg(mod, spacing, use_pilots)
+    rng = np.random.default_rng(sum(map(ord, name)))
+    frames = []
+    for i in range(12):
+        tx, _, _ = tx_frame(ref, cfg, rate, rng, seq=i)
+        frames.append(awgn(tx, snr_db + (i % 3) * 2 - 2, rng))
+    zeros = np.zeros(len(frames), np.float32)
+    out = _run_gpu(ctx, cfg, frames, zeros, zeros)
+    _compare(ref, cfg, frames, out, zeros, zeros, exact_bins=True)
+    # FFT bins of every symbol are bit-exact when no CFO correction is active
+    for i, rx in enumerate(frames):
+        n_sym = len(rx) // cfg.symbol_samples()
+        if abs(out["cfo"][i]) < 0.01:      # LTS residual did not switch the rotation on
+            bins = ref.ofdm_symbol_bins(cfg, rx, n_sym)
+            assert np.array_equal(out["bins"][i], bins.astype(np.complex64))
+
+
+@pytest.mark.parametrize("case", CASES[:3] + CASES[6:7], ids=[c[0] for c in CASES[:3] + CASES[6:7]])
+def test_presynced_matches_reference_with_cfo(ctx, ref, case):
+    name, mod, spacing, use_pilots, rate, snr_db = case
+    cfg = make_cfg(mod, spacing, use_pilots)
+    rng = np.random.default_rng(7 + sum(map(ord, name)))
+    frames, cfos, phases = [], [], []
+    for i in range(12):
+        tx, _, _ = tx_frame(ref, cfg, rate, rng, seq=i)
+        true_cfo = float(rng.uniform(-5, 5))
+        rx = awgn(apply_cfo(tx, true_cfo), snr_db, rng)
+        frames.append(rx)
+        # the sync stage hands over an estimate that is off by a bit (exercises the LTS residual
+        # refinement and the re-run, channel_equalizer.cpp:304-382)
+        cfos.append(np.float32(true_cfo + (0.0, 0.2, -1.5, 2.5)[i % 4]))
+        phases.append(np.float32(rng.uniform(-3.1, 3.1)))
+    out = _run_gpu(ctx, cfg, frames, cfos, phases)
+    _compare(ref, cfg, frames, out, cfos, phases, exact_bins=False)
+    # FFT outputs within 1e-4 relative (to the symbol's peak bin) with the CFO rotation active
+    for i, rx in enumerate(frames[:4]):
+        r = ref.ofdm_symbol_bins(cfg, rx, 2, float(cfos[i]), float(phases[i]))
+        got = out["bins"][i][:2]
+        # the tap shows the bins of the LAST LTS pass; only comparable when no re-run happened
+        if abs(out["cfo"][i] - cfos[i]) < 1e-6:
+            assert np.abs(got - r).max() <= 1e-4 * np.abs(r).max()
+
+
+def test_frame_decode_matches_reference(ctx, ref):
+    """OFDM demod -> deinterleave -> LDPC x4 -> header/CRC, bit-exact payload bits, CRC flags and
+    LDPC iteration counts (BASELINE configs[3] and [0] at their nominal SNR)."""
+    import torch
+    from ria_b200 import ofdm
+    for case in CASES[:2]:
+        name, mod, spacing, use_pilots, rate, snr_db = case
+        cfg = make_cfg(mod, spacing, use_pilots)
+        rng = np.random.default_rng(99)
+        frames, sent = [], []
+        for i in range(16):
+            tx, frame, bps = tx_frame(ref, cfg, rate, rng, seq=100 + i)
+            frames.append(awgn(tx, snr_db - (6 if i % 4 == 3 else 0), rng))   # some marginal frames
+            sent.append(frame)
+        chain = ofdm.OfdmRxChain(_to_ria_cfg(cfg), rate, True, ctx)
+        data, status, snr = chain.process_batch(torch.from_numpy(np.stack(frames)).cuda())
+        torch.cuda.synchronize()
+        data = data.cpu().numpy()
+        st = ofdm.status_array(status)
+        n_good = 0
+        for i, rx in enumerate(frames):
+            r = ref.ofdm_process_presynced(cfg, rx, 0.0, 0.0)
+            w_data, w_ok, w_it = ref.frame_decode_first_pass(r["soft"], rate, True, bps)
+            assert np.array_equal(st["cw_ok"][i], w_ok), (i, st["cw_ok"][i], w_ok)
+            assert np.array_equal(st["cw_iters"][i], w_it), (i, st["cw_iters"][i], w_it)
+            assert np.array_equal(data[i], w_data)
+            hs = ref.parse_header(w_data)
+            assert st["header_valid"][i] == hs.header_valid
+            if hs.header_valid:
+                assert st["seq"][i] == hs.seq and st["payload_len"][i] == hs.payload_len
+                assert st["src_hash"][i] == hs.src_hash and st["dst_hash"][i] == hs.dst_hash
+                assert st["total_cw"][i] == hs.total_cw and st["type"][i] == hs.type
+            if w_ok.all():
+                assert st["frame_crc_ok"][i] == hs.frame_crc_ok
+                n_good += int(bytes(data[i][: len(sent[i])]) == sent[i])
+        assert n_good >= 10
+
+
+def test_golden_fixtures(ctx):
+    """Committed outputs of the reference (tests/golden/make_golden.py) -- runs without oracle/_ref."""
+    g = np.load(GOLD)
+    from oracle.bindings import ModemConfig
+    for name, mod, spacing, use_pilots, rate, snr_db in CASES:
+        if f"{name}_rx" not in g:
+            continue
+        cfg = make_cfg(mod, spacing, use_pilots)
+        rx = g[f"{name}_rx"].astype(np.float32)
+        cfo, ph = g[f"{name}_cfo"], g[f"{name}_phase"]
+        out = _run_gpu(ctx, cfg, list(rx), cfo, ph, taps=False)
+        want = g[f"{name}_soft"]
+        for i in range(len(rx)):
+            n = int(out["n_llr"][i])
+            assert n == want.shape[1]
+            assert llr_close(out["llr"][i, :n], want[i]).all()
+            assert abs(out["snr_db"][i] - g[f"{name}_snr"][i]) < 1e-3 * max(1, abs(g[f"{name}_snr"][i]))
+            assert abs(out["cfo"][i] - g[f"{name}_cfo_out"][i]) < 1e-4 * max(1, abs(g[f"{name}_cfo_out"][i]))
+
+
+def test_edge_cases(ctx, ref):
+    """Short / ragged inputs: fewer than one symbol, exactly the LTS, trailing partial symbol."""
+    import torch
+    from ria_b200 import ofdm
+    name, mod, spacing, use_pilots, rate, snr_db = CASES[0]
+    cfg = make_cfg(mod, spacing, use_pilots)
+    rng = np.random.default_rng(5)
+    tx, _, _ = tx_frame(ref, cfg, rate, rng)
+    rx = awgn(tx, snr_db, rng)
+    L = cfg.symbol_samples()
+    dem = ofdm.OFDMDemodulator(_to_ria_cfg(cfg), ctx)
+    for n in (L - 1, 2 * L, 2 * L + 5, 3 * L, 5 * L + 700, len(rx)):
+        out = dem.process_presynced_batch(torch.from_numpy(rx[:n]).cuda().unsqueeze(0))
+        torch.cuda.synchronize()
+        r = ref.ofdm_process_presynced(cfg, rx[:n]) if n >= 2 * L else dict(soft=np.zeros(0, np.float32))
+        assert int(out["n_llr"][0]) == len(r["soft"])
+        if len(r["soft"]):
+            assert llr_close(out["llr"][0, : len(r["soft"])].cpu().numpy(), r["soft"]).all()
+    # empty batch
+    out = dem.process_presynced_batch(torch.zeros((0, len(rx)), device="cuda"))
+    assert out["llr"].shape[0] == 0
+    # unsupported configuration is rejected loudly (no silent fallback)
+    import ria_b200
+    bad = _to_ria_cfg(cfg)
+    bad.fft_size = 512
+    with pytest.raises(ria_b200.RiaError):
+        ofdm.OFDMDemodulator(bad, ctx).process_presynced_batch(torch.zeros((1, 4000), device="cuda"))
