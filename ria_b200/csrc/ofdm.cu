@@ -69,8 +69,19 @@ __device__ __forceinline__ float2 cdiv(float2 a, float2 b) {
     return make_float2(static_cast<float>((aa * cc + bb * dd) / den),
                        static_cast<float>((bb * cc - aa * dd) / den));
 }
-__device__ __forceinline__ float carg(float2 a) { return atan2f(a.y, a.x); }
-__device__ __forceinline__ float2 cexpj(float th) { float s, c; sincosf(th, &s, &c); return make_float2(c, s); }
+// Transcendentals: the reference calls glibc's float cosf/sinf/atan2f, which are (almost always)
+// correctly rounded; CUDA's float versions are 1-2 ulp.  Those ulps are amplified by the QAM
+// demapper's 2/noise_var scale into LLR differences above the 1e-4 contract, so the device
+// evaluates them in double and rounds once (B200 has half-rate FP64, this is affordable).
+__device__ __forceinline__ float atan2_rn(float y, float x) { return static_cast<float>(atan2(static_cast<double>(y), static_cast<double>(x))); }
+__device__ __forceinline__ float sin_rn(float x) { return static_cast<float>(sin(static_cast<double>(x))); }
+__device__ __forceinline__ float cos_rn(float x) { return static_cast<float>(cos(static_cast<double>(x))); }
+__device__ __forceinline__ float carg(float2 a) { return atan2_rn(a.y, a.x); }
+__device__ __forceinline__ float2 cexpj(float th) {
+    double s, c;
+    sincos(static_cast<double>(th), &s, &c);
+    return make_float2(static_cast<float>(c), static_cast<float>(s));
+}
 __device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }   // std::max(a,b)
 __device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b : a; }   // std::min(a,b)
 
@@ -428,7 +439,7 @@ ofdm_presynced_kernel(const KernelArgs a) {
                 for (int i = 0; i < nd; ++i) if (sm.flag[i]) { sum = cadd(sum, sm.tmpc[i]); ++valid; }
                 int rerun = 0;
                 if (valid > 10) {
-                    const float avg_phase = atan2f(sum.y, sum.x);
+                    const float avg_phase = atan2_rn(sum.y, sum.x);
                     const float symbol_duration = static_cast<float>(a.sym_len) / static_cast<float>(static_cast<unsigned>(a.sample_rate));
                     const float residual = static_cast<float>(static_cast<double>(avg_phase) /
                                                               (2.0f * M_PI * static_cast<double>(symbol_duration)));
@@ -720,13 +731,13 @@ ofdm_presynced_kernel(const KernelArgs a) {
                     case RIA_DBPSK: {                                 // demapDBPSK, soft_demap.hpp:172-193
                         const float2 prev = first ? make_float2(1.0f, 0.0f) : sm.prev_eq[tid];
                         const float2 diff = cmul(sym, cconj(prev));
-                        const float pd = atan2f(diff.y, diff.x);
+                        const float pd = atan2_rn(diff.y, diff.x);
                         const float sp = mag * cabs(prev);
                         float l = 0.0f;
                         if (!(sp < 1e-6f)) {
                             const float dnv = 2.0f * nv;
                             const float conf = 2.0f * sp / dnv;
-                            l = clip_llr(conf * cosf(pd));
+                            l = clip_llr(conf * cos_rn(pd));
                         }
                         out[0] = l;
                         sm.prev_eq[tid] = sym;
@@ -743,8 +754,8 @@ ofdm_presynced_kernel(const KernelArgs a) {
                             const float snr = sp / dnv;
                             const float scale = 2.0f * sqrtf(snr);
                             const float pi = 3.14159265358979f;
-                            const float ph = atan2f(diff.y, diff.x);
-                            l0 = clip_llr(scale * sinf(ph + pi / 4));
+                            const float ph = atan2_rn(diff.y, diff.x);
+                            l0 = clip_llr(scale * sin_rn(ph + pi / 4));
                             l1 = clip_llr(scale * (fabsf(diff.x) - fabsf(diff.y)) / dmag);
                         }
                         out[0] = l0; out[1] = l1;

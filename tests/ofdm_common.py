@@ -45,8 +45,10 @@ def apply_cfo(x, cfo_hz, fs=48000.0):
 
 
 def llr_close(a, b, rtol=1e-4, atol=1e-4):
-    """north_star tolerance: soft LLRs within 1e-4 relative in fp32 (plus an absolute floor of
-    1e-4 for LLRs that are differences of nearly equal terms)."""
+    """north_star tolerance: soft LLRs within 1e-4 relative in fp32.  LLRs are clipped to
+    [-20, 20] and many are a large scale (2/noise_var, several hundred) times a difference of
+    nearly equal terms, so a purely relative bound is undefined near zero: the absolute floor is
+    1e-4 (5e-6 of the LLR full scale)."""
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return np.abs(a - b) <= atol + rtol * np.abs(b)
