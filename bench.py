@@ -3,10 +3,17 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
-One "step" is one pass of the receive hot path over one batch of synthetic input that is already
-resident in HBM.  Rank 0 prints ONE JSON line.  For N > 1 the driver launches this file under
-torch.distributed.run (one rank per GPU, NCCL); frames are sharded across ranks (weak scaling:
-fixed per-GPU batch) and the only collective is an all-reduce of the error counters.
+One "step" is one pass of the receive hot path over one batch of synthetic received frames that
+are already resident in HBM.  Rank 0 prints ONE JSON line.  For N > 1 the driver launches this
+file under torch.distributed.run (one rank per GPU, NCCL); frames are sharded across ranks (weak
+scaling: fixed per-GPU batch, no data-path collective) and the only exchange is one all-reduce of
+the error counters.
+
+Workloads
+  ofdm_qam64   (default) BASELINE.json configs[3]: OFDM QAM64 R3/4 coherent, 15 pilots, 1024-FFT
+               CP 96, AWGN 28 dB, 1M frames per GPU: presynced demod -> de-interleave -> 4 x LDPC
+               -> header/CRC, i.e. "decoded frames/s".
+  ldpc         BASELINE.json configs[1]: LDPC R1/4..R3/4 decode of 1M codewords per rate.
 """
 from __future__ import annotations
 
@@ -23,6 +30,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+KK_LDPC, KK_OFDM_DEMOD, KK_FRAME_STATUS, KK_AWGN = 0, 1, 2, 3
 
 
 # ---------------------------------------------------------------------------------------------
@@ -56,6 +65,7 @@ class ClockSampler:
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            time.sleep(0.3)
         except Exception:
             self.proc = None
 
@@ -91,10 +101,191 @@ class ClockSampler:
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# workload: OFDM QAM64 R3/4 full receive chain (BASELINE.json configs[3])
+# ---------------------------------------------------------------------------------------------
+
+class OfdmQam64Workload:
+    name = "ofdm_qam64_r34_15pilots_awgn28dB"
+    metric = "decoded_frames_per_s"
+    unit = "frames/s"
+    dtype = "f32"
+    MOD, RATE, SPACING, SNR_DB = 8, 4, 4, 28.0          # QAM64, R3/4, pilot every 4th carrier
+    POOL = 64
+
+    def __init__(self, n_frames: int):
+        self.n = n_frames
+        self._pool = None
+        self.frame_len = 12 * 1120
+
+    def cfg(self):
+        from ria_b200 import ofdm
+        return ofdm.ModemConfig.high_throughput(self.MOD)
+
+    def pool_host(self, seed=11):
+        """POOL distinct clean TX frames (host numpy TX synthesiser) and their frame bytes."""
+        if self._pool is None:
+            from ria_b200 import txsynth
+            self._pool = txsynth.make_frame_pool(self.cfg(), self.RATE, self.POOL, seed=seed)
+            self.frame_len = self._pool[0].shape[1]
+        return self._pool
+
+    def describe(self):
+        c = self.cfg()
+        L = c.getSymbolDuration()
+        return {"workload": self.name, "frames_per_gpu": self.n, "frame_samples": self.frame_len,
+                "modulation": "QAM64", "code_rate": "R3/4", "fft": 1024, "cp": L - 1024,
+                "carriers": 59, "pilots": c.getPilotCarriers(), "data_carriers": c.getDataCarriers(),
+                "channel": f"AWGN {self.SNR_DB} dB, generated on the device (Philox), "
+                           f"{self.POOL} distinct TX frames x per-frame noise",
+                "chain": "mix+CFO+CP+FFT1024+LTS/pilot est+MMSE+QAM64 LLR -> frame/channel "
+                         "de-interleave -> 4x LDPC R3/4 (0.9375, 60 it) -> header+CRC16",
+                "l2": "input batch (53.8 GB at 1M frames) exceeds the 126 MB L2; no flush needed"}
+
+    def setup(self, ctx, device, rank, world):
+        import torch
+        from ria_b200 import ofdm, sim
+        self.torch, self.ctx = torch, ctx
+        pool, raw = self.pool_host()
+        self.pool_dev = torch.from_numpy(pool).to(device)
+        bpc4 = 4 * 60
+        sent = np.zeros((self.POOL, bpc4), np.uint8)
+        for i, fr in enumerate(raw):
+            sent[i, : len(fr)] = np.frombuffer(fr, np.uint8)
+        self.sent_dev = torch.from_numpy(sent).to(device)
+        self.sent_len = len(raw[0])
+        self.first_id = rank * self.n                       # global frame ids: sharding-independent noise
+        self.samples = sim.awgn_batch(self.pool_dev, self.n, self.SNR_DB, seed=2026,
+                                      first_frame_id=self.first_id, ctx=ctx)
+        self.chain = ofdm.OfdmRxChain(self.cfg(), self.RATE, True, ctx)
+        self.out = None
+        torch.cuda.synchronize()
+
+    def step(self):
+        self.out = self.chain.process_batch(self.samples)
+
+    def launches_per_step(self):
+        return 3
+
+    def units_per_step(self):
+        return float(self.n)
+
+    def samples_per_step(self):
+        return float(self.n) * self.frame_len
+
+    # dominant kernel = OFDM demod: algorithmic bytes per frame = samples in + LLRs out
+    dominant_kind = KK_OFDM_DEMOD
+    dominant_name = "ofdm_presynced_kernel"
+
+    def dominant_bytes_per_launch(self):
+        n_llr = 10 * 44 * 6
+        return self.n * (self.frame_len * 4 + n_llr * 4)
+
+    def counters(self):
+        """[frames, frames_ok (4/4 cw + header + frame CRC), cw_fail, frames_payload_wrong, sum_iters]"""
+        torch = self.torch
+        from ria_b200 import ofdm
+        data, status, snr = self.out
+        st = status.view(torch.uint8)
+        dt = ofdm.FRAME_STATUS_DTYPE
+        off = {k: dt.fields[k][1] for k in dt.names}
+        cw_ok = st[:, off["cw_ok"]:off["cw_ok"] + 4]
+        iters = st[:, off["cw_iters"]:off["cw_iters"] + 16].contiguous().view(torch.int32)
+        ok = (st[:, off["all_ok"]] == 1) & (st[:, off["header_valid"]] == 1) & (st[:, off["frame_crc_ok"]] == 1)
+        ids = (torch.arange(self.n, device=data.device) + self.first_id) % self.POOL
+        want = self.sent_dev[ids][:, : self.sent_len]
+        wrong = (data[:, : self.sent_len] != want).any(dim=1) & ok
+        c = torch.zeros(5, dtype=torch.int64, device=data.device)
+        c[0] = self.n
+        c[1] = ok.sum()
+        c[2] = (cw_ok == 0).sum()
+        c[3] = wrong.sum()
+        c[4] = iters.sum()
+        return c
+
+    def counter_dict(self, c):
+        return {"frames": int(c[0]), "frames_ok": int(c[1]), "cw_fail": int(c[2]),
+                "crc_ok_but_payload_wrong": int(c[3]), "mean_ldpc_iters": float(c[4]) / max(1, 4 * int(c[0]))}
+
+    # ---- end to end: HOST buffers through ria_ofdm_rx_frames_host ----
+    def setup_e2e(self, n_e2e):
+        torch = self.torch
+        self.e2e_n = n_e2e = min(n_e2e, self.n)
+        pin = torch.empty((n_e2e, self.frame_len), dtype=torch.float32, pin_memory=True)
+        pin.copy_(self.samples[:n_e2e])
+        torch.cuda.synchronize()
+        self._pin = pin
+        self.e2e_host = pin.numpy()
+
+    def step_e2e(self):
+        return self.chain.process_batch_host(self.e2e_host)
+
+    def e2e_units(self):
+        return float(self.e2e_n)
+
+    def e2e_bytes(self):
+        from ria_b200 import ofdm
+        return (self.e2e_n * self.frame_len * 4,
+                self.e2e_n * (240 + ofdm.FRAME_STATUS_DTYPE.itemsize + 4))
+
+
+def _cpu_ofdm_worker(args):
+    """One process per core: make its own received frames (untimed), then time the reference's
+    processPresynced + first-pass decodeFixedFrame + parseHeader on them."""
+    _, n_frames, seed, kind = args
+    from oracle.bindings import ModemConfig, Ref
+    wl = OfdmQam64Workload(n_frames)
+    ref = Ref()
+    pool, raw = wl.pool_host()
+    cfg = ModemConfig.from_buffer_copy(bytes(wl.cfg()))
+    rng = np.random.default_rng(seed)
+    bps = cfg.data_carriers() * 6
+    frames = []
+    for i in range(n_frames):
+        tx = pool[i % len(pool)]
+        p = float(np.mean(tx.astype(np.float64) ** 2))
+        frames.append((tx + rng.standard_normal(len(tx)).astype(np.float32) *
+                       np.float32(np.sqrt(p / 10 ** (wl.SNR_DB / 10)))).astype(np.float32))
+    ok = 0
+    t0 = time.perf_counter()
+    for rx in frames:
+        r = ref.ofdm_process_presynced(cfg, rx, 0.0, 0.0)
+        data, cw_ok, _ = ref.frame_decode_first_pass(r["soft"], wl.RATE, True, bps)
+        st = ref.parse_header(data)
+        ok += int(cw_ok.all() and st.frame_crc_ok)
+    return time.perf_counter() - t0, ok
+
+
+_OFDM_POOL_CACHE = {}
+
+
+def cpu_baseline_ofdm(wl, frames_per_core):
+    import multiprocessing as mp
+    from oracle.bindings import Ref
+    if not Ref.available():
+        return {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference",
+                "sample": "oracle/_ref/libria_ref.so not present"}
+    cores = host_cores()
+    jobs = [("ofdm_qam64", frames_per_core, 1000 + 17 * c, "reference") for c in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_ofdm_worker, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    rate = sum(frames_per_core / b for b, _ in res)
+    ok = sum(o for _, o in res)
+    return {"value": rate, "unit": "frames/s", "cores": cores, "kind": "reference",
+            "sample": f"{frames_per_core} frames per core x {cores} cores "
+                      f"({ok}/{frames_per_core * cores} decoded with valid CRC), reference "
+                      f"processPresynced + first-pass decodeFixedFrame + parseHeader, one process "
+                      f"per core, {wall:.1f} s wall, {max(b for b, _ in res):.1f} s max busy"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -106,26 +297,30 @@ class LdpcWorkload:
     (LLR model of tools/test_chase_cache.cpp:20-34; Es/N0 and decoder settings of SURVEY.md 8d)."""
 
     name = "ldpc_r14_r34_1M_cw_per_rate"
-    RATES = (0, 2, 3, 4)                       # R1/4, R1/2, R2/3, R3/4
+    metric = "decoded_frames_per_s"
+    unit = "frames/s"
+    dtype = "f32"
+    RATES = (0, 2, 3, 4)
     ESN0 = {0: 1.0, 2: 4.0, 3: 6.0, 4: 7.0}
     MAX_ITER = {0: 50, 2: 80, 3: 70, 4: 60}
-    FACTOR = 0.9375                            # decodeFixedFrame / robustDecodeSingleCW setting
-    CW_PER_FRAME = 4                           # v2 fixed frame = 4 codewords
+    FACTOR = 0.9375
+    CW_PER_FRAME = 4
+    dominant_kind = KK_LDPC
+    dominant_name = "ldpc_decode_kernel"
 
     def __init__(self, n_cw: int):
         self.n_cw = n_cw
 
-    # -- synthetic input: encode with the library's own H (systematic: parity = H_data . info) --
+    def describe(self):
+        return {"workload": self.name, "codewords_per_rate_per_gpu": self.n_cw,
+                "rates": "R1/4,R1/2,R2/3,R3/4", "esn0_db": "1,4,6,7", "min_sum_factor": self.FACTOR,
+                "max_iter": "50,80,70,60", "frame": "4 codewords (v2 fixed frame)",
+                "l2": "inputs (2.7 GB per rate) exceed the 126 MB L2; no flush needed"}
+
     def _codeword_bits(self, rate, n_distinct, rng):
-        from ria_b200 import fec
-        k, m, _ = fec.code_params(rate)
-        row_ptr, edge_var = fec.get_matrix(rate)
-        info = rng.integers(0, 2, size=(n_distinct, k), dtype=np.uint8)
-        par = np.zeros((n_distinct, m), np.uint8)
-        for i in range(m):
-            vs = edge_var[row_ptr[i]:row_ptr[i + 1] - 1]
-            par[:, i] = info[:, vs].sum(axis=1) & 1
-        return np.concatenate([info, par], axis=1)
+        from ria_b200 import fec, txsynth
+        k = fec.code_params(rate)[0]
+        return txsynth.ldpc_encode_bits(rng.integers(0, 2, size=(n_distinct, k), dtype=np.uint8), rate)
 
     def make_llr_host(self, rate, n, seed):
         rng = np.random.default_rng(seed)
@@ -135,15 +330,11 @@ class LdpcWorkload:
         noise = rng.standard_normal(s.shape, dtype=np.float32) / np.sqrt(snr)
         return (2.0 * (s + noise) * snr).astype(np.float32), bits
 
-    def setup(self, ctx, device, rank):
+    def setup(self, ctx, device, rank, world):
         import torch
         from ria_b200 import fec
-        self.torch = torch
-        self.ctx = ctx
-        self.dec = {}
-        self.llr = {}
-        self.info_ref = {}
-        self.prot_mask = {}
+        self.torch, self.ctx = torch, ctx
+        self.dec, self.llr, self.info_ref, self.prot_mask = {}, {}, {}, {}
         gen = torch.Generator(device=device).manual_seed(1234 + rank)
         for rate in self.RATES:
             rng = np.random.default_rng(99 + rate)
@@ -172,30 +363,22 @@ class LdpcWorkload:
         torch.cuda.synchronize()
 
     def step(self):
-        out = {}
-        for rate in self.RATES:
-            out[rate] = self.dec[rate].decode_batch(self.llr[rate])
-        self.out = out
+        self.out = {rate: self.dec[rate].decode_batch(self.llr[rate]) for rate in self.RATES}
 
     def launches_per_step(self):
         return len(self.RATES)
 
-    def units_per_step(self):      # frames (4 codewords each)
+    def units_per_step(self):
         return len(self.RATES) * self.n_cw / self.CW_PER_FRAME
 
     def samples_per_step(self):
         return 0.0
 
-    def algorithmic_bytes_per_step(self):
+    def dominant_bytes_per_launch(self):
         from ria_b200 import fec
-        b = 0
-        for rate in self.RATES:
-            k = fec.code_params(rate)[0]
-            b += self.n_cw * (648 * 4 + (k + 7) // 8 + 1 + 4)
-        return b
+        return sum(self.n_cw * (648 * 4 + (fec.code_params(r)[0] + 7) // 8 + 5) for r in self.RATES) / len(self.RATES)
 
     def counters(self):
-        """[cw, cw_fail, info_byte_errors_among_ok, sum_iters]"""
         torch = self.torch
         c = torch.zeros(4, dtype=torch.int64, device="cuda")
         for rate in self.RATES:
@@ -208,11 +391,13 @@ class LdpcWorkload:
             c[3] += iters.sum()
         return c
 
-    # -- end to end: host buffers through the *_host C ABI entry --
+    def counter_dict(self, c):
+        return {"codewords": int(c[0]), "cw_fail": int(c[1]), "ok_but_wrong_protected_bits": int(c[2]),
+                "mean_iters": float(c[3]) / max(1, int(c[0]))}
+
     def setup_e2e(self, n_e2e):
         self.e2e_n = n_e2e
-        self.e2e_llr = {}
-        self._pinned = []
+        self.e2e_llr, self._pinned = {}, []
         for rate in self.RATES:
             host, _ = self.make_llr_host(rate, n_e2e, 555 + rate)
             pin = self.torch.empty(host.shape, dtype=self.torch.float32, pin_memory=True)
@@ -221,10 +406,7 @@ class LdpcWorkload:
             self.e2e_llr[rate] = pin.numpy()
 
     def step_e2e(self):
-        res = {}
-        for rate in self.RATES:
-            res[rate] = self.dec[rate].decode_batch_host(self.e2e_llr[rate])
-        return res
+        return {rate: self.dec[rate].decode_batch_host(self.e2e_llr[rate]) for rate in self.RATES}
 
     def e2e_units(self):
         return len(self.RATES) * self.e2e_n / self.CW_PER_FRAME
@@ -235,13 +417,8 @@ class LdpcWorkload:
         d2h = sum(self.e2e_n * ((fec.code_params(r)[0] + 7) // 8 + 1 + 4) for r in self.RATES)
         return h2d, d2h
 
-    # -- CPU baseline: the unmodified reference, one process per host core --
-    def cpu_sample(self, per_rate):
-        return {rate: self.make_llr_host(rate, per_rate, 777 + rate)[0] for rate in self.RATES}
-
 
 def _cpu_ldpc_worker(args):
-    """One process per core: synthesise its own sample (untimed), then time the decode."""
     n, seed, kind = args
     from oracle.bindings import Port, Ref
     wl = LdpcWorkload(n)
@@ -255,14 +432,11 @@ def _cpu_ldpc_worker(args):
     return elapsed
 
 
-def cpu_baseline_ldpc(wl: LdpcWorkload, per_rate_per_core: int):
-    """Times the reference's own LDPCDecoder on the host cores: every core decodes
-    per_rate_per_core codewords of each rate (one process per core; the reference is not
-    thread-safe).  Throughput = sum over cores of (codewords / busy time)."""
+def cpu_baseline_ldpc(wl, per_rate_per_core):
     import multiprocessing as mp
     from oracle.bindings import Ref
     kind = "reference" if Ref.available() else "port"
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = host_cores()
     jobs = [(per_rate_per_core, 1000 + 17 * c, kind) for c in range(cores)]
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
@@ -272,8 +446,13 @@ def cpu_baseline_ldpc(wl: LdpcWorkload, per_rate_per_core: int):
     rate_sum = sum(per_core_cw / b for b in busy)
     return {"value": rate_sum / wl.CW_PER_FRAME, "unit": "frames/s", "cores": cores, "kind": kind,
             "sample": f"{per_rate_per_core} codewords per rate per core x {cores} cores "
-                      f"({cores * per_core_cw} codewords), {wall:.1f} s wall, "
-                      f"{max(busy):.1f} s max busy per core"}
+                      f"({cores * per_core_cw} codewords), {wall:.1f} s wall, {max(busy):.1f} s max busy"}
+
+
+def make_workload(args):
+    if args.workload == "ldpc":
+        return LdpcWorkload(args.batch or (1 << 20)), cpu_baseline_ldpc, args.cpu_sample or 4096
+    return OfdmQam64Workload(args.batch or (1 << 20)), cpu_baseline_ofdm, args.cpu_sample or 6000
 
 
 # ---------------------------------------------------------------------------------------------
@@ -281,29 +460,29 @@ def cpu_baseline_ldpc(wl: LdpcWorkload, per_rate_per_core: int):
 # ---------------------------------------------------------------------------------------------
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, on
+    a bounded sample of the same workload.  Rank 0 only."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    wl = LdpcWorkload(args.batch)
-    per = max(64, args.cpu_sample)
-    vals = []
+    import ria_b200  # noqa: F401  (host-side input synthesis only; no GPU work on this arm)
+    wl, cpu_fn, sample = make_workload(args)
+    if isinstance(wl, OfdmQam64Workload):
+        wl.pool_host()                      # built once here, inherited by the forked workers
     for _ in range(args.warmup):
-        cpu_baseline_ldpc(wl, max(16, per // 8))
-    for _ in range(args.steps):
-        vals.append(cpu_baseline_ldpc(wl, per))
-    v = float(np.mean([x["value"] for x in vals]))
-    last = vals[-1]
+        cpu_fn(wl, max(16, sample // 16))
+    runs = [cpu_fn(wl, sample) for _ in range(max(1, args.steps))]
+    v = float(np.mean([r["value"] for r in runs]))
+    last = runs[-1]
+    units = last["cores"] * sample * (len(wl.RATES) / wl.CW_PER_FRAME if isinstance(wl, LdpcWorkload) else 1)
     line = {
-        "impl": "reference", "metric": "decoded_frames_per_s", "value": v, "unit": "frames/s",
+        "impl": "reference", "metric": wl.metric, "value": v, "unit": wl.unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * (last["cores"] * len(wl.RATES) * per / wl.CW_PER_FRAME) / v,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": wl.name, "note": "reference LDPCDecoder::decodeSoft on host cores, "
-                   "bounded sample of the same workload"},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": last["cores"], "kind": last["kind"],
+        "ms_per_step": 1e3 * units / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.describe(),
+        "cpu_baseline": {"value": v, "unit": wl.unit, "cores": last["cores"], "kind": last["kind"],
                          "sample": last["sample"]},
-        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": v, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -314,10 +493,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ria_b200", choices=["ria_b200", "reference"])
-    ap.add_argument("--workload", default="ldpc")
-    ap.add_argument("--batch", type=int, default=1 << 20, help="codewords per rate per GPU")
-    ap.add_argument("--e2e-batch", type=int, default=1 << 17)
-    ap.add_argument("--cpu-sample", type=int, default=4096, help="codewords per rate per core")
+    ap.add_argument("--workload", default="ofdm_qam64", choices=["ofdm_qam64", "ldpc"])
+    ap.add_argument("--batch", type=int, default=0, help="frames (or codewords per rate) per GPU")
+    ap.add_argument("--e2e-batch", type=int, default=1 << 16)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="frames (codewords per rate) per core")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -340,21 +519,23 @@ def main():
 
     ctx = ria_b200.Context(local)
     stream = torch.cuda.Stream(device)
-    wl = LdpcWorkload(args.batch)
+    wl, cpu_fn, cpu_sample = make_workload(args)
+    warmup = max(args.warmup, 3)
     with torch.cuda.stream(stream):
-        wl.setup(ctx, device, rank)
+        wl.setup(ctx, device, rank, world)
 
         def barrier():
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
 
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(warmup):
             wl.step()
         barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        ctx.set_timing(True)
         l0 = ctx.launch_count
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
@@ -365,30 +546,29 @@ def main():
         barrier()
         ms = ev0.elapsed_time(ev1)
         launches = ctx.launch_count - l0
+        kern_ms = {k: ctx.get_timing(k) for k in (KK_LDPC, KK_OFDM_DEMOD, KK_FRAME_STATUS)}
+        ctx.set_timing(False)
         clocks = sampler.stop() if rank == 0 else None
 
-        # error counters: the only cross-GPU exchange of the path (one all-reduce)
+        # error counters: the only cross-GPU exchange of the path (one NCCL all-reduce)
         cnt = wl.counters()
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
-        ms_per_step = ms_max / args.steps
-        units = wl.units_per_step() * world
-        value = units / (ms_per_step * 1e-3)
+        ms_per_step = float(t.item()) / args.steps
+        value = wl.units_per_step() * world / (ms_per_step * 1e-3)
 
-        # end to end through the host-buffer C ABI (H2D + kernels + D2H inside the timed region)
+        # end to end through the host-buffer C ABI (pinned host input, H2D + kernels + D2H timed)
         wl.setup_e2e(args.e2e_batch)
         wl.step_e2e()
         barrier()
-        t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
         for _ in range(e2e_steps):
             wl.step_e2e()
         barrier()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_value = wl.e2e_units() * world / float(te.item())
@@ -396,34 +576,35 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        alg = wl.algorithmic_bytes_per_step() / wl.launches_per_step()
-        kern_s = (ms / args.steps) * 1e-3 / wl.launches_per_step()
-        achieved = alg / kern_s / 1e9
-        c = cnt.cpu().numpy()
+        dom_ms, dom_n = kern_ms[wl.dominant_kind]
+        kern_s = dom_ms / max(1, dom_n) * 1e-3
+        achieved = wl.dominant_bytes_per_launch() / kern_s / 1e9
+        step_ms_local = ms / args.steps
         line = {
-            "metric": "decoded_frames_per_s", "value": value, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": wl.metric, "value": value, "unit": wl.unit,
+            "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl.name, "codewords_per_rate_per_gpu": args.batch,
-                       "rates": "R1/4,R1/2,R2/3,R3/4", "esn0_db": "1,4,6,7",
-                       "min_sum_factor": wl.FACTOR, "max_iter": "50,80,70,60",
-                       "frame": "4 codewords (v2 fixed frame)",
-                       "l2": "inputs (2.7 GB per rate) exceed the 126 MB L2; no flush needed"},
-            "codewords_per_s": value * wl.CW_PER_FRAME,
-            "counters": {"codewords": int(c[0]), "cw_fail": int(c[1]),
-                         "ok_but_wrong_protected_bits": int(c[2]), "mean_iters": float(c[3]) / max(1, int(c[0]))},
+            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.describe(),
+            "rx_msamples_per_s": wl.samples_per_step() * world / (ms_per_step * 1e-3) / 1e6,
+            "counters": wl.counter_dict(cnt.cpu().numpy()),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "ldpc_decode_kernel", "note": "LDPC is SM/shared-memory bound "
-                         "by design (SURVEY 8d); HBM fraction reported for the contract"},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "batch": args.e2e_batch},
+                         "kernel": wl.dominant_name, "kernel_ms_per_launch": kern_s * 1e3,
+                         "algorithmic_bytes_per_launch": wl.dominant_bytes_per_launch(),
+                         "note": "see DESIGN.md: this kernel is FP32-issue / shared-memory bound, "
+                                 "not HBM bound; the HBM fraction is what the contract asks for"},
+            "kernel_share_of_step": {
+                "ldpc_decode_kernel": kern_ms[KK_LDPC][0] / args.steps / step_ms_local,
+                "ofdm_presynced_kernel": kern_ms[KK_OFDM_DEMOD][0] / args.steps / step_ms_local,
+                "frame_status_kernel": kern_ms[KK_FRAME_STATUS][0] / args.steps / step_ms_local},
+            "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "batch": getattr(wl, "e2e_n", args.e2e_batch),
+                    "api": "ria_ofdm_rx_frames_host / ria_ldpc_decode_batch_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_ldpc(wl, args.cpu_sample)
+            line["cpu_baseline"] = cpu_fn(wl, cpu_sample)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -55,6 +55,12 @@ int  ria_ctx_set_stream(ria_ctx* ctx, void* cuda_stream);
 int  ria_ctx_synchronize(ria_ctx* ctx);
 const char* ria_last_error(const ria_ctx* ctx);
 const char* ria_version(void);
+/* Per-kernel timing for bench.py: when enabled, every kernel launch is bracketed by CUDA events on
+ * the context stream; get_timing sums the elapsed time of all launches of one kind since enable.
+ * kinds: 0 LDPC, 1 OFDM demod, 2 frame status/CRC, 3 AWGN channel, 4 MC-DPSK demod, 5 ZC sync,
+ * 6 chirp sync, 7 chase combine, 8 Watterson channel. */
+int  ria_ctx_set_timing(ria_ctx* ctx, int enable);
+int  ria_ctx_get_timing(ria_ctx* ctx, int kind, double* total_ms, int64_t* launches);
 /* number of kernels this library has launched on the context since creation */
 int64_t ria_ctx_launch_count(const ria_ctx* ctx);
 
@@ -191,6 +197,18 @@ int ria_ofdm_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg, int rate,
                             const float* samples, int64_t frame_stride, int32_t frame_len,
                             const float* cfo_hz, const float* phase, int64_t n_frames,
                             uint8_t* data, ria_frame_status* status, float* snr_db);
+
+/* ---- channel simulation on the device ------------------------------------------------------ */
+/* AWGN as SimulatedChannel::applyChannel (tools/cli_simulator.cpp:343-366): frame f of the batch is
+ * tx_pool[(first_frame_id + f) % pool_frames] plus white Gaussian noise whose standard deviation
+ * is sqrt(mean(s^2) / 10^(snr/10)) measured on that frame.  snr_db_dev ([n], may be NULL) overrides
+ * the scalar snr_db per frame.  Noise comes from a Philox4x32-10 counter keyed by
+ * (seed, first_frame_id + f, sample), so results are reproducible and independent of the sharding;
+ * parity with the reference's std::mt19937 stream is statistical only. */
+int ria_channel_awgn_batch_dev(ria_ctx* ctx, const float* tx_pool_dev, int32_t pool_frames,
+                               int32_t frame_len, const float* snr_db_dev, float snr_db,
+                               uint64_t seed, int64_t first_frame_id, int64_t n_frames,
+                               float* out_dev, int64_t out_stride);
 
 /* CRC-16/CCITT-FALSE as ControlFrame::calculateCRC (src/protocol/frame_v2.cpp:115-128); host. */
 uint16_t ria_crc16(const uint8_t* data, size_t len);

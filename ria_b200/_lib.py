@@ -30,6 +30,8 @@ _SIGNATURES = {
     "ria_ctx_synchronize": (_i32, [_vp]),
     "ria_last_error": (C.c_char_p, [_vp]),
     "ria_ctx_launch_count": (_i64, [_vp]),
+    "ria_ctx_set_timing": (_i32, [_vp, _i32]),
+    "ria_ctx_get_timing": (_i32, [_vp, _i32, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "ria_ldpc_params": (_i32, [_i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "ria_ldpc_get_matrix": (_i32, [_i32, _vp, _vp]),
     "ria_ldpc_decode_batch_dev": (_i32, [_vp, _i32, _i32, _f32, _vp, _i64, _vp, _i32, _vp, _vp]),
@@ -47,6 +49,7 @@ _SIGNATURES = {
                                       _vp, _vp, _vp]),
     "ria_ofdm_rx_frames_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _i64,
                                        _vp, _vp, _vp]),
+    "ria_channel_awgn_batch_dev": (_i32, [_vp, _vp, _i32, _i32, _vp, _f32, C.c_uint64, _i64, _i64, _vp, _i64]),
     "ria_crc16": (C.c_uint16, [_vp, C.c_size_t]),
     "ria_channel_interleaver_step": (_i32, [_i32, _i32]),
 }
@@ -98,6 +101,15 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self._L.ria_ctx_launch_count(self.handle))
+
+    def set_timing(self, enable: bool) -> None:
+        self.check(self._L.ria_ctx_set_timing(self.handle, int(enable)))
+
+    def get_timing(self, kind: int):
+        """(total_ms, launches) of one kernel kind since set_timing(True)."""
+        ms, n = C.c_double(0), _i64(0)
+        self.check(self._L.ria_ctx_get_timing(self.handle, int(kind), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def check(self, rc: int) -> None:
         if rc != 0:

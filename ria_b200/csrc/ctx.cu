@@ -34,6 +34,19 @@ int ensure_stage(ria_ctx* ctx, int which, size_t dev_bytes, size_t pin_bytes) {
     return RIA_OK;
 }
 
+void time_begin(ria_ctx* ctx, int kind) {
+    if (!ctx->timing) return;
+    ria_ctx::TimedLaunch t{kind, nullptr, nullptr};
+    if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) return;
+    cudaEventRecord(t.start, ctx->stream);
+    ctx->timed.push_back(t);
+}
+
+void time_end(ria_ctx* ctx) {
+    if (!ctx->timing || ctx->timed.empty()) return;
+    cudaEventRecord(ctx->timed.back().stop, ctx->stream);
+}
+
 int ensure_scratch(ria_ctx* ctx, size_t bytes) {
     if (bytes > ctx->scratch_bytes) {
         if (ctx->scratch) RIA_CUDA(ctx, cudaFree(ctx->scratch));
@@ -98,6 +111,7 @@ extern "C" int ria_ctx_destroy(ria_ctx* ctx) {
         if (t.chk_var) cudaFree(t.chk_var);
         if (t.var_slot) cudaFree(t.var_slot);
     }
+    for (auto& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
     for (auto* t : ctx->ofdm_tables) ria::ofdm_tables_free(t);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->work_counter) cudaFree(ctx->work_counter);
@@ -122,6 +136,32 @@ extern "C" int ria_ctx_synchronize(ria_ctx* ctx) {
     if (!ctx) return RIA_E_INVAL;
     RIA_CUDA(ctx, cudaSetDevice(ctx->device));
     RIA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RIA_OK;
+}
+
+extern "C" int ria_ctx_set_timing(ria_ctx* ctx, int enable) {
+    if (!ctx) return RIA_E_INVAL;
+    for (auto& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
+    ctx->timed.clear();
+    ctx->timing = enable != 0;
+    return RIA_OK;
+}
+
+extern "C" int ria_ctx_get_timing(ria_ctx* ctx, int kind, double* total_ms, int64_t* launches) {
+    if (!ctx || !total_ms || !launches) return RIA_E_INVAL;
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    double ms = 0.0;
+    int64_t n = 0;
+    for (auto& t : ctx->timed) {
+        if (t.kind != kind) continue;
+        RIA_CUDA(ctx, cudaEventSynchronize(t.stop));
+        float e = 0.f;
+        RIA_CUDA(ctx, cudaEventElapsedTime(&e, t.start, t.stop));
+        ms += e;
+        ++n;
+    }
+    *total_ms = ms;
+    *launches = n;
     return RIA_OK;
 }
 

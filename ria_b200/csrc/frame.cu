@@ -21,7 +21,7 @@ int ldpc_launch(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor, cons
 namespace {
 
 constexpr int kFrameBits = 4 * RIA_LDPC_N;     // FrameInterleaver::TOTAL_FRAME_BITS = 2592
-constexpr int kInfoStride = 64;                // per-codeword info bytes in the scratch buffer
+constexpr int kInfoStride = 72;                // per-codeword info bytes in the scratch buffer
 
 // LDPCCodec::getRecommendedIterations, src/fec/ldpc_codec.hpp:86-96
 int recommended_iterations(int rate) {
@@ -146,7 +146,9 @@ int frame_decode_impl(ria_ctx* ctx, int rate, int use_ci, int bits_per_symbol, c
     if (rc != RIA_OK) return rc;
     const int threads = 128;
     const unsigned blocks = static_cast<unsigned>((n_frames + threads - 1) / threads);
+    time_begin(ctx, KK_FRAME_STATUS);
     frame_status_kernel<<<blocks, threads, 0, ctx->stream>>>(s.info, s.ok, s.iters, n_frames, bpc, data_dev, status_dev);
+    time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return RIA_OK;

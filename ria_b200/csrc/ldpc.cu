@@ -296,9 +296,11 @@ int ria::ldpc_launch(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor,
     if (grid > want) grid = want;
     RIA_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int), ctx->stream));
     LdpcGather gather{frame_mode, soft_stride, step};
+    time_begin(ctx, KK_LDPC);
     kern<<<static_cast<unsigned>(grid), W * 32, smem, ctx->stream>>>(
         llr_dev, n_cw, gather, t->chk_var, t->var_slot, t->k, t->m, t->dv_max, max_iter, min_sum_factor,
         info_dev, info_stride, ok_dev, iters_dev, ctx->work_counter);
+    time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return RIA_OK;

@@ -932,7 +932,9 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
     long long grid = static_cast<long long>(ctx->sm_count) * per_sm;
     if (grid > n_frames) grid = n_frames;
     RIA_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), ctx->stream));
+    time_begin(ctx, KK_OFDM_DEMOD);
     ofdm_presynced_kernel<<<static_cast<unsigned>(grid), kThreads, smem, ctx->stream>>>(a);
+    time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return RIA_OK;

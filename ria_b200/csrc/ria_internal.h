@@ -60,6 +60,10 @@ struct ria_ctx {
     // scratch owned by the context for the fused chain entry points
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // optional per-kernel timing (CUDA events on the launching stream), see ria_ctx_set_timing
+    bool timing = false;
+    struct TimedLaunch { int kind; cudaEvent_t start, stop; };
+    std::vector<TimedLaunch> timed;
     // staging for *_host entry points (grown on demand)
     void* stage_dev[2] = {nullptr, nullptr};
     size_t stage_dev_bytes[2] = {0, 0};
@@ -76,6 +80,12 @@ int ldpc_tables_dev(ria_ctx* ctx, int rate, const LdpcCodeDev** out);
 int ofdm_tables_dev(ria_ctx* ctx, const ria_modem_config& cfg, int need_nco, const OfdmTablesDev** out);
 void ofdm_tables_free(OfdmTablesDev* t);
 int ensure_scratch(ria_ctx* ctx, size_t bytes);
+
+// kernel kinds for the timing hook / launch accounting
+enum KernelKind { KK_LDPC = 0, KK_OFDM_DEMOD = 1, KK_FRAME_STATUS = 2, KK_AWGN = 3, KK_MCDPSK = 4,
+                  KK_ZC_SYNC = 5, KK_CHIRP_SYNC = 6, KK_CHASE = 7, KK_WATTERSON = 8, KK_COUNT = 16 };
+void time_begin(ria_ctx* ctx, int kind);
+void time_end(ria_ctx* ctx);
 
 }  // namespace ria
 
