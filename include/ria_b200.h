@@ -143,6 +143,13 @@ int ria_ofdm_presynced_batch_dev(ria_ctx* ctx, const ria_modem_config* cfg,
                                  float* llr_dev, int32_t llr_stride, int32_t* n_llr_dev,
                                  float* snr_db_dev, float* cfo_out_dev, float* fading_dev);
 
+/* Same with HOST buffers (H2D -> kernel -> D2H inside the call). */
+int ria_ofdm_presynced_batch_host(ria_ctx* ctx, const ria_modem_config* cfg,
+                                  const float* samples, int64_t frame_stride, int32_t frame_len,
+                                  const float* cfo_hz, const float* phase, int64_t n_frames,
+                                  float* llr, int32_t llr_stride, int32_t* n_llr,
+                                  float* snr_db, float* cfo_out, float* fading);
+
 /* Debug/parity taps of the same kernel: frequency-domain bins of every symbol for the used
  * carriers ([n][n_symbols][num_carriers] interleaved re,im; logical carrier order) and the
  * channel estimate after the LTS ([n][num_carriers] re,im).  Either may be NULL. */

@@ -1,0 +1,337 @@
+// ria_b200_adapters.hpp -- C++ host adapters over the C ABI (ria_b200.h), header-only.
+//
+// They mirror the reference classes on the hot path with the same method names, argument meaning,
+// ownership and error behaviour, so that a maintainer can swap them in behind the reference's own
+// plugin seams:
+//
+//   ria::LDPCDecoder        <- ultra::LDPCDecoder              include/ultra/fec.hpp:48-81
+//   ria::LDPCCodec          <- ultra::fec::LDPCCodec / ICodec  src/fec/ldpc_codec.hpp:38-105
+//   ria::OFDMChirpRx        <- RX half of ultra::OFDMChirpWaveform (IWaveform)
+//                                                              src/waveform/ofdm_chirp_waveform.cpp:79-105, 391-485
+//   ria::decodeFixedFrame   <- first pass of ultra::protocol::v2::decodeFixedFrame
+//                                                              src/protocol/frame_v2.cpp:1335-1385
+//
+// Compile inside the reference tree with -DRIA_WITH_ULTRA to make LDPCCodec derive from
+// ultra::fec::ICodec (then it can be returned by CodecFactory::create).  Without that macro the
+// header depends on nothing but the C ABI and the standard library.
+//
+// Like the reference objects, an adapter instance is driven by one thread at a time.  Batch = 1
+// calls go through the *_host entry points (H2D, kernel, D2H inside the call); the batched entry
+// points of the C ABI are what a many-channel receiver should call directly.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <span>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "ria_b200.h"
+
+#ifdef RIA_WITH_ULTRA
+#include "fec/codec_interface.hpp"
+#include "ultra/fec.hpp"
+#endif
+
+namespace ria {
+
+using Bytes = std::vector<uint8_t>;
+
+// One shared context per process and device (created on first use).  ria_ctx_create fails when
+// no B200 is usable; the adapters then throw std::runtime_error -- there is no CPU fallback.
+class Context {
+public:
+    static Context& instance(int device = 0) {
+        static Context ctx(device);
+        return ctx;
+    }
+    ria_ctx* get() const { return ctx_; }
+    void check(int rc) const {
+        if (rc != RIA_OK) throw std::runtime_error(std::string("ria_b200: ") + ria_last_error(ctx_));
+    }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    ~Context() { ria_ctx_destroy(ctx_); }
+
+private:
+    explicit Context(int device) {
+        if (ria_ctx_create(device, &ctx_) != RIA_OK || !ctx_)
+            throw std::runtime_error("ria_b200: no usable B200 (ria_ctx_create failed); no CPU fallback");
+    }
+    ria_ctx* ctx_ = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// ultra::LDPCDecoder
+// ------------------------------------------------------------------------------------------------
+class LDPCDecoder {
+public:
+    explicit LDPCDecoder(int rate) { setRate(rate); }
+
+    // ldpc_decoder.cpp:268-282
+    Bytes decode(std::span<const uint8_t> coded_data) {
+        std::vector<float> llrs;
+        llrs.reserve(coded_data.size() * 8);
+        for (uint8_t byte : coded_data)
+            for (int b = 7; b >= 0; --b) llrs.push_back(((byte >> b) & 1) ? -6.0f : 6.0f);
+        return decodeSoft(llrs);
+    }
+
+    // ldpc_decoder.cpp:284-429: single block (<= 648 LLRs, zero padded) or bit-level
+    // concatenation of the k info bits of every 648-LLR block (+ a zero-padded partial block).
+    Bytes decodeSoft(std::span<const float> llrs) {
+        if (llrs.empty()) { last_success_ = false; return {}; }
+        const size_t n = RIA_LDPC_N;
+        const bool single = llrs.size() <= n;
+        const size_t full = llrs.size() / n, rem = llrs.size() - full * n;
+        const size_t blocks = single ? 1 : full + (rem ? 1 : 0);
+        std::vector<float> padded(blocks * n, 0.0f);
+        std::memcpy(padded.data(), llrs.data(), llrs.size() * sizeof(float));
+        const int stride = (k_ + 7) / 8;
+        std::vector<uint8_t> info(blocks * stride), ok(blocks);
+        std::vector<int32_t> iters(blocks);
+        Context& c = Context::instance();
+        c.check(ria_ldpc_decode_batch_host(c.get(), rate_, max_iter_, factor_, padded.data(),
+                                           static_cast<int64_t>(blocks), info.data(), stride, ok.data(), iters.data()));
+        last_iters_ = iters.back();
+        if (single) { last_success_ = ok[0] != 0; return info; }
+        // a trailing partial block goes through decodeBP, which overwrites the flag (:401)
+        if (rem) last_success_ = ok.back() != 0;
+        else { last_success_ = true; for (size_t b = 0; b < full; ++b) last_success_ = last_success_ && ok[b]; }
+        Bytes out;
+        uint8_t byte = 0;
+        int cnt = 0;
+        for (size_t b = 0; b < blocks; ++b)
+            for (int j = 0; j < k_; ++j) {
+                const uint8_t bit = (info[b * stride + (j >> 3)] >> (7 - (j & 7))) & 1;
+                byte = static_cast<uint8_t>((byte << 1) | bit);
+                if (++cnt == 8) { out.push_back(byte); byte = 0; cnt = 0; }
+            }
+        if (cnt > 0) out.push_back(static_cast<uint8_t>(byte << (8 - cnt)));
+        return out;
+    }
+
+    bool lastDecodeSuccess() const { return last_success_; }
+    int lastIterations() const { return last_iters_; }
+    void setRate(int rate) {
+        int k = 0;
+        if (ria_ldpc_params(rate, &k, nullptr, nullptr) != RIA_OK) throw std::invalid_argument("bad code rate");
+        rate_ = rate; k_ = k;
+    }
+    int getRate() const { return rate_; }
+    void setMaxIterations(int it) { max_iter_ = it; }
+    void setMinSumFactor(float f) { factor_ = f; }
+
+private:
+    int rate_ = RIA_R1_2, k_ = 324;
+    int max_iter_ = 50;        // Impl::max_iterations, ldpc_decoder.cpp:43
+    float factor_ = 0.75f;     // Impl::min_sum_factor, ldpc_decoder.cpp:44
+    bool last_success_ = false;
+    int last_iters_ = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// ultra::fec::LDPCCodec (decode side of ICodec)
+// ------------------------------------------------------------------------------------------------
+#ifdef RIA_WITH_ULTRA
+using DecodeResult = ultra::fec::DecodeResult;
+#else
+struct DecodeResult {
+    bool success = false;
+    Bytes data;
+    int iterations = 0;
+    float ber_estimate = 0.0f;
+};
+#endif
+
+class LDPCCodec
+#ifdef RIA_WITH_ULTRA
+    : public ultra::fec::ICodec
+#endif
+{
+public:
+    static constexpr size_t CODEWORD_BITS = 648;
+    static constexpr size_t CODEWORD_BYTES = 81;
+
+    // ldpc_codec.hpp:86-96
+    static int getRecommendedIterations(int rate) {
+        switch (rate) {
+            case RIA_R3_4: return 60;
+            case RIA_R2_3: return 70;
+            case RIA_R1_2: return 80;
+            case RIA_R1_3: return 60;
+            case RIA_R1_4: return 50;
+            default: return 50;
+        }
+    }
+
+    explicit LDPCCodec(int rate = RIA_R1_2)
+        : rate_(rate), max_iterations_(getRecommendedIterations(rate)), decoder_(rate) {
+        decoder_.setMaxIterations(max_iterations_);
+    }
+
+#ifdef RIA_WITH_ULTRA
+#define RIA_OVERRIDE override
+    explicit LDPCCodec(ultra::CodeRate rate) : LDPCCodec(static_cast<int>(rate)) {}
+    void setRate(ultra::CodeRate rate) override { setRate(static_cast<int>(rate)); }
+    ultra::CodeRate getRate() const override { return static_cast<ultra::CodeRate>(rate_); }
+    // TX stays on the CPU: the reference encoder is used as is
+    Bytes encode(const Bytes& data) override {
+        ultra::LDPCEncoder enc(static_cast<ultra::CodeRate>(rate_));
+        return enc.encode(ultra::ByteSpan(data.data(), data.size()));
+    }
+#else
+#define RIA_OVERRIDE
+#endif
+    std::string getName() const RIA_OVERRIDE { return "802.11n LDPC"; }
+    void setRate(int rate) {
+        rate_ = rate;
+        decoder_.setRate(rate);
+        const int rec = getRecommendedIterations(rate);
+        if (max_iterations_ != rec) { max_iterations_ = rec; decoder_.setMaxIterations(rec); }
+    }
+    int getRateValue() const { return rate_; }
+    void setMaxIterations(int it) RIA_OVERRIDE { max_iterations_ = it; decoder_.setMaxIterations(it); }
+    int getMaxIterations() const RIA_OVERRIDE { return max_iterations_; }
+
+    std::pair<bool, Bytes> decode(const std::vector<float>& soft_bits) RIA_OVERRIDE {
+        Bytes d = decoder_.decodeSoft(soft_bits);
+        return {decoder_.lastDecodeSuccess(), std::move(d)};
+    }
+    DecodeResult decodeExtended(const std::vector<float>& soft_bits) RIA_OVERRIDE {
+        DecodeResult r;
+        r.data = decoder_.decodeSoft(soft_bits);
+        r.success = decoder_.lastDecodeSuccess();
+        r.iterations = decoder_.lastIterations();
+        r.ber_estimate = r.success ? static_cast<float>(r.iterations) / (max_iterations_ * 10.0f) : 0.5f;
+        return r;
+    }
+    size_t getCodewordBits() const RIA_OVERRIDE { return CODEWORD_BITS; }
+    size_t getInfoBits() const RIA_OVERRIDE { int k = 0; ria_ldpc_params(rate_, &k, nullptr, nullptr); return static_cast<size_t>(k); }
+    size_t getParityBits() const RIA_OVERRIDE { return CODEWORD_BITS - getInfoBits(); }
+    size_t getCodewordBytes() const RIA_OVERRIDE { return CODEWORD_BYTES; }
+    size_t getDataBytes() const RIA_OVERRIDE { return getInfoBits() / 8; }
+    float getEffectiveRate() const RIA_OVERRIDE { return static_cast<float>(getInfoBits()) / static_cast<float>(CODEWORD_BITS); }
+#undef RIA_OVERRIDE
+
+private:
+    int rate_;
+    int max_iterations_;
+    LDPCDecoder decoder_;
+};
+
+// ------------------------------------------------------------------------------------------------
+// v2::decodeFixedFrame (first pass) for one frame
+// ------------------------------------------------------------------------------------------------
+struct CodewordStatus {
+    std::vector<bool> decoded;       // 4 entries
+    std::vector<Bytes> data;         // bytes_per_cw each (empty when the codeword failed)
+    ria_frame_status status{};       // header fields / CRC flags
+    bool allSuccess() const { for (bool b : decoded) if (!b) return false; return !decoded.empty(); }
+};
+
+// Batch = 1 convenience over a device round trip; a real receiver batches frames and calls
+// ria_frame_decode_batch_dev / ria_ofdm_rx_frames_host directly.
+inline CodewordStatus decodeFixedFrame(const ria_modem_config& cfg, int rate, bool use_channel_interleave,
+                                       std::span<const float> frame_samples, float cfo_hz = 0.0f,
+                                       float phase = 0.0f, float* snr_db = nullptr) {
+    int k = 0;
+    if (ria_ldpc_params(rate, &k, nullptr, nullptr) != RIA_OK) throw std::invalid_argument("bad code rate");
+    const int bpc = k / 8;
+    Bytes data(4 * bpc);
+    CodewordStatus st;
+    float snr = 0.f;
+    Context& c = Context::instance();
+    c.check(ria_ofdm_rx_frames_host(c.get(), &cfg, rate, use_channel_interleave ? 1 : 0, frame_samples.data(),
+                                    static_cast<int64_t>(frame_samples.size()), static_cast<int32_t>(frame_samples.size()),
+                                    &cfo_hz, &phase, 1, data.data(), &st.status, &snr));
+    if (snr_db) *snr_db = snr;
+    st.decoded.resize(4);
+    st.data.resize(4);
+    for (int i = 0; i < 4; ++i) {
+        st.decoded[i] = st.status.cw_ok[i] != 0;
+        if (st.decoded[i]) st.data[i].assign(data.begin() + i * bpc, data.begin() + (i + 1) * bpc);
+    }
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RX half of ultra::OFDMChirpWaveform (IWaveform): configure / setFrequencyOffset /
+// setAbsoluteTrainingPosition / process / getSoftBits / estimatedSNR / estimatedCFO /
+// getFadingIndex / reset with the reference's semantics (ofdm_chirp_waveform.cpp:79-105, 391-485)
+// ------------------------------------------------------------------------------------------------
+class OFDMChirpRx {
+public:
+    OFDMChirpRx() { ria_modem_config_for(RIA_DQPSK, RIA_R1_2, &config_); }
+    explicit OFDMChirpRx(const ria_modem_config& cfg) : config_(cfg) {}
+
+    void configure(int mod, int rate) {
+        switch (mod) {
+            case RIA_DBPSK: case RIA_DQPSK: case RIA_D8PSK: case RIA_QPSK: case RIA_BPSK:
+            case RIA_QAM16: case RIA_QAM32: case RIA_QAM64: break;
+            default: mod = RIA_DQPSK;                        // :81-87
+        }
+        ria_modem_config_for(mod, rate, &config_);
+    }
+    void setFrequencyOffset(float cfo_hz) { cfo_hz_ = cfo_hz; }
+    void setAbsoluteTrainingPosition(size_t pos) { abs_pos_ = pos; has_abs_pos_ = true; }
+    int getSamplesPerSymbol() const { return ria_ofdm_symbol_samples(&config_); }
+
+    bool process(std::span<const float> samples) {
+        if (static_cast<int>(samples.size()) < getSamplesPerSymbol()) return false;
+        const size_t ref = has_abs_pos_ ? abs_pos_ : training_start_;
+        // :404-413, evaluated in double like the reference expression
+        float ph = static_cast<float>(-2.0f * 3.14159265358979323846 * cfo_hz_ * ref / config_.sample_rate);
+        while (ph > 3.14159265358979323846) ph -= 2.0f * 3.14159265358979323846;
+        while (ph < -3.14159265358979323846) ph += 2.0f * 3.14159265358979323846;
+        const int n_sym = static_cast<int>(samples.size()) / getSamplesPerSymbol();
+        const int bits = ria_ofdm_data_carriers(&config_) * bitsPerCarrier();
+        const int stride = ((n_sym > 2 ? n_sym - 2 : 0) * bits + 3) & ~3;
+        std::vector<float> llr(static_cast<size_t>(stride > 4 ? stride : 4));
+        int32_t n_llr = 0;
+        float snr = 0, cfo = 0, fad = 0;
+        Context& c = Context::instance();
+        c.check(ria_ofdm_presynced_batch_host(c.get(), &config_, samples.data(), static_cast<int64_t>(samples.size()),
+                                              static_cast<int32_t>(samples.size()), &cfo_hz_, &ph, 1, llr.data(),
+                                              static_cast<int32_t>(llr.size()), &n_llr, &snr, &cfo, &fad));
+        fading_ = fad;
+        const bool ready = n_llr >= RIA_LDPC_N;
+        if (ready) {
+            llr.resize(static_cast<size_t>(n_llr));
+            soft_bits_ = std::move(llr);
+            last_snr_ = snr;
+            cfo_hz_ = last_cfo_ = cfo;                       // CFO feedback (:447-455)
+        }
+        return ready;
+    }
+    std::vector<float> getSoftBits() { return std::move(soft_bits_); }   // moves out (:470-472)
+    float estimatedSNR() const { return last_snr_; }
+    float estimatedCFO() const { return std::fabs(last_cfo_) > 0.1f ? last_cfo_ : cfo_hz_; }
+    float getFadingIndex() const { return fading_; }
+    void reset() { soft_bits_.clear(); has_abs_pos_ = false; abs_pos_ = 0; }   // CFO is kept (:474-485)
+    const ria_modem_config& config() const { return config_; }
+
+private:
+    int bitsPerCarrier() const {
+        switch (config_.modulation) {
+            case RIA_DQPSK: case RIA_QPSK: return 2;
+            case RIA_D8PSK: case RIA_QAM8: return 3;
+            case RIA_QAM16: return 4;
+            case RIA_QAM32: return 5;
+            case RIA_QAM64: return 6;
+            case RIA_QAM256: return 8;
+            default: return 1;
+        }
+    }
+    ria_modem_config config_{};
+    float cfo_hz_ = 0.0f, last_cfo_ = 0.0f, last_snr_ = 0.0f, fading_ = 0.0f;
+    size_t training_start_ = 0, abs_pos_ = 0;
+    bool has_abs_pos_ = false;
+    std::vector<float> soft_bits_;
+};
+
+}  // namespace ria

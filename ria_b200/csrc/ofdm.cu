@@ -40,7 +40,7 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int kFft = 1024;
-constexpr int kMaxSymLen = 1280;
+constexpr int kMaxSymLen = 1160;    // fft 1024 + CP <= 128 + guard <= 8
 constexpr int kTwCount = 1024;     // stage-major twiddle table (1022 used)
 
 // ------------------------------- complex helpers -------------------------------------------
@@ -344,7 +344,7 @@ __device__ void demap_qam32(float2 sym, float nv, float* out) {
     for (int b = 0; b < 5; ++b) out[b] = clip_llr(sf * (d1[b] - d0[b]));
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 8)
 ofdm_presynced_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -926,6 +926,8 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
 
     const size_t smem = sizeof(Smem);
     RIA_CUDA(ctx, cudaFuncSetAttribute(ofdm_presynced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RIA_CUDA(ctx, cudaFuncSetAttribute(ofdm_presynced_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     RIA_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ofdm_presynced_kernel, kThreads, smem));
     if (per_sm < 1) return set_error(ctx, RIA_E_UNSUPPORTED, "ofdm: kernel does not fit");
@@ -948,4 +950,48 @@ extern "C" int ria_ofdm_presynced_batch_dev(ria_ctx* ctx, const ria_modem_config
     return ria_ofdm_presynced_batch_taps_dev(ctx, cfg, samples_dev, frame_stride, frame_len, cfo_hz_dev, phase_dev,
                                              n_frames, llr_dev, llr_stride, n_llr_dev, snr_db_dev, cfo_out_dev,
                                              fading_dev, nullptr, nullptr);
+}
+
+extern "C" int ria_ofdm_presynced_batch_host(ria_ctx* ctx, const ria_modem_config* cfg,
+                                             const float* samples, int64_t frame_stride, int32_t frame_len,
+                                             const float* cfo_hz, const float* phase, int64_t n_frames,
+                                             float* llr, int32_t llr_stride, int32_t* n_llr,
+                                             float* snr_db, float* cfo_out, float* fading) {
+    using namespace ria;
+    if (!ctx || !cfg) return RIA_E_INVAL;
+    if (n_frames < 0 || frame_len < 0 || frame_stride < frame_len || llr_stride < 0) return set_error(ctx, RIA_E_INVAL, "ofdm: bad sizes");
+    if (n_frames == 0) return RIA_OK;
+    if (!samples || !llr || !n_llr) return set_error(ctx, RIA_E_INVAL, "ofdm: null buffer");
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t chunk = 4096;
+    const size_t in_b = static_cast<size_t>(chunk) * frame_len * 4;
+    const size_t llr_b = static_cast<size_t>(chunk) * llr_stride * 4;
+    const size_t aux_b = static_cast<size_t>(chunk) * 4 * 6;
+    int rc = ensure_stage(ctx, 0, in_b + llr_b + aux_b + 1024, 0);
+    if (rc != RIA_OK) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->stage_dev[0]);
+    float* d_samp = reinterpret_cast<float*>(base);
+    float* d_llr = reinterpret_cast<float*>(base + in_b);
+    float* d_aux = reinterpret_cast<float*>(base + in_b + llr_b);
+    float *d_cfo = d_aux, *d_ph = d_aux + chunk, *d_snr = d_aux + 2 * chunk, *d_co = d_aux + 3 * chunk, *d_fa = d_aux + 4 * chunk;
+    int32_t* d_nl = reinterpret_cast<int32_t*>(d_aux + 5 * chunk);
+    cudaStream_t s = ctx->stream;
+    for (int64_t off = 0; off < n_frames; off += chunk) {
+        const int64_t n = (n_frames - off < chunk) ? (n_frames - off) : chunk;
+        RIA_CUDA(ctx, cudaMemcpy2DAsync(d_samp, static_cast<size_t>(frame_len) * 4, samples + off * frame_stride,
+                                        static_cast<size_t>(frame_stride) * 4, static_cast<size_t>(frame_len) * 4,
+                                        static_cast<size_t>(n), cudaMemcpyHostToDevice, s));
+        if (cfo_hz) RIA_CUDA(ctx, cudaMemcpyAsync(d_cfo, cfo_hz + off, n * 4, cudaMemcpyHostToDevice, s));
+        if (phase) RIA_CUDA(ctx, cudaMemcpyAsync(d_ph, phase + off, n * 4, cudaMemcpyHostToDevice, s));
+        rc = ria_ofdm_presynced_batch_dev(ctx, cfg, d_samp, frame_len, frame_len, cfo_hz ? d_cfo : nullptr,
+                                          phase ? d_ph : nullptr, n, d_llr, llr_stride, d_nl, d_snr, d_co, d_fa);
+        if (rc != RIA_OK) return rc;
+        RIA_CUDA(ctx, cudaMemcpyAsync(llr + off * llr_stride, d_llr, static_cast<size_t>(n) * llr_stride * 4, cudaMemcpyDeviceToHost, s));
+        RIA_CUDA(ctx, cudaMemcpyAsync(n_llr + off, d_nl, n * 4, cudaMemcpyDeviceToHost, s));
+        if (snr_db) RIA_CUDA(ctx, cudaMemcpyAsync(snr_db + off, d_snr, n * 4, cudaMemcpyDeviceToHost, s));
+        if (cfo_out) RIA_CUDA(ctx, cudaMemcpyAsync(cfo_out + off, d_co, n * 4, cudaMemcpyDeviceToHost, s));
+        if (fading) RIA_CUDA(ctx, cudaMemcpyAsync(fading + off, d_fa, n * 4, cudaMemcpyDeviceToHost, s));
+        RIA_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    return RIA_OK;
 }
