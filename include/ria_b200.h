@@ -58,7 +58,7 @@ const char* ria_version(void);
 /* Per-kernel timing for bench.py: when enabled, every kernel launch is bracketed by CUDA events on
  * the context stream; get_timing sums the elapsed time of all launches of one kind since enable.
  * kinds: 0 LDPC, 1 OFDM demod, 2 frame status/CRC, 3 AWGN channel, 4 MC-DPSK demod, 5 ZC sync,
- * 6 chirp sync, 7 chase combine, 8 Watterson channel. */
+ * 6 chirp sync, 7 chase combine, 8 Watterson channel, 9 MC-DPSK CFO correction. */
 int  ria_ctx_set_timing(ria_ctx* ctx, int enable);
 int  ria_ctx_get_timing(ria_ctx* ctx, int kind, double* total_ms, int64_t* launches);
 /* number of kernels this library has launched on the context since creation */
@@ -204,6 +204,40 @@ int ria_ofdm_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg, int rate,
                             const float* samples, int64_t frame_stride, int32_t frame_len,
                             const float* cfo_hz, const float* phase, int64_t n_frames,
                             uint8_t* data, ria_frame_status* status, float* snr_db);
+
+/* ---- MC-DPSK receive path -------------------------------------------------------------------- */
+/* POD mirror of the RX-relevant fields of ultra::MultiCarrierDPSKConfig
+ * (src/psk/multi_carrier_dpsk.hpp:27-100).  Reference defaults: 48000, 8 carriers (the tools use
+ * 10), 500..2500 Hz, 512 samples per symbol, 8 training symbols. */
+typedef struct {
+    float    sample_rate;
+    uint32_t num_carriers;        /* 1..16                                          */
+    float    freq_low, freq_high;
+    uint32_t samples_per_symbol;  /* 512                                            */
+    uint32_t bits_per_symbol;     /* 1 = DBPSK, 2 = DQPSK                           */
+    uint32_t spreading;           /* SpreadingMode as a factor: 1, 2 or 4           */
+    uint32_t training_symbols;
+} ria_mcdpsk_config;
+
+/* soft bits one frame of frame_len samples yields (0 if it is shorter than training + ref) */
+int ria_mcdpsk_soft_bits_per_frame(const ria_mcdpsk_config* cfg, int32_t frame_len);
+
+/* Batched replacement for MCDPSKWaveform::process (src/waveform/mc_dpsk_waveform.cpp:294-338) =
+ * MultiCarrierDPSKDemodulator::setChirpDetected(cfo) + process (src/psk/multi_carrier_dpsk.hpp:
+ * 797-895): CFO correction by Hilbert transform + rotation when |cfo| > 0.1 Hz (:901-926),
+ * setReference (:507-518), demodulateSoft with 2x/4x coherent despreading (:520-736).
+ *   samples_dev  fp32, frame f at samples_dev + f*frame_stride, frame_len samples laid out
+ *                [training_symbols x 512][reference 512][data ...] (what process() is handed)
+ *   cfo_hz_dev   [n] CFO handed to setChirpDetected (NULL = 0: no correction pass at all)
+ *   phase_dev    [n] cfo_initial_phase_ (setCFOWithPhase), NULL = 0
+ *   llr_dev      [n][llr_stride] soft bits, symbol-major / carrier-minor (:683-698)
+ *   fading_dev   [n] getFadingIndex() (frequency CV + temporal CV), may be NULL
+ *   cfo_out_dev  [n] getEstimatedCFO() after the call, may be NULL */
+int ria_mcdpsk_process_batch_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg,
+                                 const float* samples_dev, int64_t frame_stride, int32_t frame_len,
+                                 const float* cfo_hz_dev, const float* phase_dev, int64_t n_frames,
+                                 float* llr_dev, int32_t llr_stride, int32_t* n_llr_dev,
+                                 float* fading_dev, float* cfo_out_dev);
 
 /* ---- channel simulation on the device ------------------------------------------------------ */
 /* AWGN as SimulatedChannel::applyChannel (tools/cli_simulator.cpp:343-366): frame f of the batch is

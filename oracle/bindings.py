@@ -65,6 +65,18 @@ class ModemConfig(C.Structure):
         return self.num_carriers - self.pilots()
 
 
+class McdpskConfig(C.Structure):
+    """Same layout as ria_mcdpsk_config (include/ria_b200.h)."""
+    _fields_ = [("sample_rate", C.c_float), ("num_carriers", C.c_uint32), ("freq_low", C.c_float),
+                ("freq_high", C.c_float), ("samples_per_symbol", C.c_uint32),
+                ("bits_per_symbol", C.c_uint32), ("spreading", C.c_uint32),
+                ("training_symbols", C.c_uint32)]
+
+    @classmethod
+    def make(cls, bits=1, spreading=4, carriers=10, training=8):
+        return cls(48000.0, carriers, 500.0, 2500.0, 512, bits, spreading, training)
+
+
 class FrameStatus(C.Structure):
     """Same layout as ria_frame_status (include/ria_b200.h)."""
     _fields_ = [("cw_ok", C.c_uint8 * 4), ("cw_iters", C.c_int32 * 4), ("all_ok", C.c_uint8),
@@ -175,6 +187,15 @@ class Ref:
         L.ref_make_data_frame.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _u8p, C.c_int, _u8p, C.c_int]
         L.ref_make_data_frame.restype = C.c_int
         self._demods = {}
+        mcp = C.POINTER(McdpskConfig)
+        L.ref_mcdpsk_tx_frame.argtypes = [mcp, _u8p, C.c_int, _f32p, C.c_int]
+        L.ref_mcdpsk_tx_frame.restype = C.c_int
+        L.ref_mcdpsk_demod_new.argtypes = [mcp]
+        L.ref_mcdpsk_demod_new.restype = C.c_void_p
+        L.ref_mcdpsk_demod_free.argtypes = [C.c_void_p]
+        L.ref_mcdpsk_process.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_float, _f32p, C.c_int,
+                                         C.POINTER(C.c_int), fp, fp]
+        L.ref_mcdpsk_process.restype = C.c_int
 
     @staticmethod
     def available() -> bool:
@@ -249,6 +270,29 @@ class Ref:
         bins = np.zeros((n_sym, cfg.num_carriers, 2), np.float32)
         self.lib.ref_ofdm_symbol_bins(self._demod(cfg), samples, n_sym, cfo_hz, phase, bins)
         return bins[..., 0] + 1j * bins[..., 1]
+
+    # ---- MC-DPSK ----
+    def mcdpsk_tx_frame(self, cfg: McdpskConfig, data) -> np.ndarray:
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        bits_sym = cfg.num_carriers * cfg.bits_per_symbol
+        cap = 512 * (cfg.training_symbols + 2 + (len(data) * 8 // bits_sym + 2) * cfg.spreading)
+        out = np.zeros(cap, np.float32)
+        n = self.lib.ref_mcdpsk_tx_frame(C.byref(cfg), data, len(data), out, cap)
+        assert n >= 0, n
+        return out[:n].copy()
+
+    def mcdpsk_process(self, cfg: McdpskConfig, samples, cfo_hz=0.0, phase=0.0):
+        key = ("mc", bytes(cfg))
+        if key not in self._demods:
+            self._demods[key] = self.lib.ref_mcdpsk_demod_new(C.byref(cfg))
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        cap = 16384
+        soft = np.zeros(cap, np.float32)
+        n_soft = C.c_int(0)
+        fad, cfo = C.c_float(0), C.c_float(0)
+        ready = self.lib.ref_mcdpsk_process(self._demods[key], samples, len(samples), cfo_hz, phase,
+                                            soft, cap, C.byref(n_soft), C.byref(fad), C.byref(cfo))
+        return dict(ready=bool(ready), soft=soft[: n_soft.value].copy(), fading=fad.value, cfo=cfo.value)
 
     # ---- fixed frame ----
     def encode_fixed_frame(self, data, rate, use_ci, bps) -> np.ndarray:

@@ -18,6 +18,8 @@
 #include "fec/frame_interleaver.hpp"
 #include "fec/ldpc_codec.hpp"
 #include "protocol/frame_v2.hpp"
+#include "psk/multi_carrier_dpsk.hpp"
+#include "fec/chase_cache.hpp"
 
 #include "ria_b200.h"                     // POD config / status structs shared with the product ABI
 
@@ -276,6 +278,62 @@ int ref_make_data_frame(const char* src, const char* dst, int seq, const uint8_t
     if (n > cap) return -n;
     std::memcpy(out, s.data(), s.size());
     return n;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// MC-DPSK  (src/psk/multi_carrier_dpsk.hpp)
+// ---------------------------------------------------------------------------------------------
+static MultiCarrierDPSKConfig to_mc(const ria_mcdpsk_config* c) {
+    MultiCarrierDPSKConfig m;
+    m.sample_rate = c->sample_rate;
+    m.num_carriers = static_cast<int>(c->num_carriers);
+    m.freq_low = c->freq_low;
+    m.freq_high = c->freq_high;
+    m.samples_per_symbol = static_cast<int>(c->samples_per_symbol);
+    m.bits_per_symbol = static_cast<int>(c->bits_per_symbol);
+    m.spreading_mode = c->spreading == 4 ? SpreadingMode::TIME_4X
+                     : c->spreading == 2 ? SpreadingMode::TIME_2X : SpreadingMode::NONE;
+    m.training_symbols = static_cast<int>(c->training_symbols);
+    return m;
+}
+
+// TX after the sync preamble: [training][reference][modulate(data)]
+// (MultiCarrierDPSKModulator::generateTrainingSequence / generateReferenceSymbol / modulate)
+int ref_mcdpsk_tx_frame(const ria_mcdpsk_config* c, const uint8_t* data, int len, float* out, int cap) {
+    MultiCarrierDPSKModulator mod(to_mc(c));
+    Samples tr = mod.generateTrainingSequence();
+    Samples rf = mod.generateReferenceSymbol();
+    Samples d = mod.modulate(Bytes(data, data + len));
+    int n = static_cast<int>(tr.size() + rf.size() + d.size());
+    if (n > cap) return -n;
+    std::memcpy(out, tr.data(), tr.size() * 4);
+    std::memcpy(out + tr.size(), rf.data(), rf.size() * 4);
+    std::memcpy(out + tr.size() + rf.size(), d.data(), d.size() * 4);
+    return n;
+}
+
+void* ref_mcdpsk_demod_new(const ria_mcdpsk_config* c) { return new MultiCarrierDPSKDemodulator(to_mc(c)); }
+void ref_mcdpsk_demod_free(void* h) { delete static_cast<MultiCarrierDPSKDemodulator*>(h); }
+
+// What MCDPSKWaveform::process does (mc_dpsk_waveform.cpp:294-338): setChirpDetected(cfo);
+// process(samples); getSoftBits().  `phase` mirrors setCFOWithPhase's initial phase.
+int ref_mcdpsk_process(void* h, const float* samples, int n, float cfo_hz, float phase,
+                       float* soft, int cap, int* n_soft, float* fading, float* cfo_out) {
+    auto* d = static_cast<MultiCarrierDPSKDemodulator*>(h);
+    d->reset();
+    d->setCFOWithPhase(cfo_hz, phase);
+    d->setChirpDetected(cfo_hz);
+    bool ready = d->process(SampleSpan(samples, static_cast<size_t>(n)));
+    *n_soft = 0;
+    if (ready) {
+        auto sb = d->getSoftBits();
+        *n_soft = static_cast<int>(sb.size());
+        if (*n_soft <= cap) std::memcpy(soft, sb.data(), sb.size() * 4);
+    }
+    if (fading) *fading = d->getFadingIndex();
+    if (cfo_out) *cfo_out = d->getEstimatedCFO();
+    return ready ? 1 : 0;
 }
 
 }  // extern "C"

@@ -7,7 +7,8 @@ There is no CPU fallback.
 from ._lib import Context, RiaError, LIB_PATH, exported_symbols, lib  # noqa: F401
 from . import fec  # noqa: F401
 from . import ofdm  # noqa: F401
+from . import mcdpsk  # noqa: F401
 from . import sim  # noqa: F401
 from . import txsynth  # noqa: F401
 
-__all__ = ["Context", "RiaError", "LIB_PATH", "exported_symbols", "lib", "fec", "ofdm", "sim", "txsynth"]
+__all__ = ["Context", "RiaError", "LIB_PATH", "exported_symbols", "lib", "fec", "ofdm", "mcdpsk", "sim", "txsynth"]

@@ -1,0 +1,67 @@
+// Exact evaluation of the reference's fp32 CFO correction-phase accumulator, 32 samples at a time.
+//
+// Both demodulators rotate every sample by e^{j phase} and then do
+//     phase += phase_inc;  if (phase > M_PI) phase -= 2.0f*M_PI;  else if (phase < -M_PI) phase += 2.0f*M_PI;
+// in fp32 with a double-promoted wrap (src/ofdm/channel_equalizer.cpp:132-144;
+// src/psk/multi_carrier_dpsk.hpp:913-921 uses two independent ifs, which is equivalent because
+// only one can fire).  The rounding of that accumulator is visible in the soft bits at the 1e-4
+// level over 10^4..10^5 samples, so it has to be reproduced exactly -- but not sequentially:
+// while phase_k stays inside one binade (same exponent, same sign, no wrap), fl(phase + inc) =
+// phase + S*ulp with the constant integer S = rint(inc / ulp), provided inc/ulp is not an exact
+// tie.  A warp therefore proposes phase_k = phase_0 + k*S*ulp for its 32 lanes (exact in double),
+// checks that the last value is still strictly inside the binade and the wrap range, and only
+// otherwise falls back to stepping the 32 samples one by one.  Crossings happen once every few
+// hundred to few thousand samples, so almost every block takes the closed form.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace ria {
+
+// one reference step
+__device__ __forceinline__ float cfo_phase_step(float ph, float inc) {
+    ph = __fadd_rn(ph, inc);
+    if (static_cast<double>(ph) > M_PI) ph = static_cast<float>(static_cast<double>(ph) - 2.0f * M_PI);
+    else if (static_cast<double>(ph) < -M_PI) ph = static_cast<float>(static_cast<double>(ph) + 2.0f * M_PI);
+    return ph;
+}
+
+// Warp-collective.  `base` = phase before sample 0 of the block (identical in all lanes).
+// Returns the phase before sample `lane` of the block; *next = phase before sample 32.
+__device__ __forceinline__ float cfo_phase_block32(float base, float inc, int lane, float* next) {
+    bool fast = false;
+    double step = 0.0;
+    const unsigned bits = __float_as_uint(base);
+    const int e = static_cast<int>((bits >> 23) & 0xFF);
+    if (e > 0 && e < 255 && inc != 0.0f && fabs(static_cast<double>(base)) <= M_PI) {
+        const double ulp = __longlong_as_double(static_cast<long long>(e - 127 - 23 + 1023) << 52);   // 2^(e-150)
+        const double q = static_cast<double>(inc) / ulp;        // exact (power-of-two divisor)
+        const double S = rint(q);
+        if (fabs(q - trunc(q)) != 0.5 && fabs(S) < 4194304.0) {
+            step = S * ulp;
+            const double last = static_cast<double>(base) + 32.0 * step;      // exact
+            const double lo = __longlong_as_double(static_cast<long long>(e - 127 + 1023) << 52);   // 2^(e-127)
+            const double mag = fabs(last);
+            // strictly inside the binade of `base`, same sign, and never beyond the wrap range
+            fast = (mag > lo) && (mag < 2.0 * lo) && ((last < 0.0) == (base < 0.0f)) && (mag <= M_PI);
+        }
+    }
+    if (fast) {
+        *next = static_cast<float>(static_cast<double>(base) + 32.0 * step);
+        return static_cast<float>(static_cast<double>(base) + static_cast<double>(lane) * step);
+    }
+    float ph = base, mine = base;
+#pragma unroll 1
+    for (int k = 0; k < 32; ++k) {
+        if (k == lane) mine = ph;
+        ph = cfo_phase_step(ph, inc);
+    }
+    *next = ph;
+    return mine;
+}
+
+}  // namespace ria

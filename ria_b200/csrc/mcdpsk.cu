@@ -1,0 +1,552 @@
+// Batched MC-DPSK receive path for sm_100a: optional CFO correction (Hilbert FIR + rotation),
+// per-(symbol, carrier) correlation demod, coherent 2x/4x despreading, differential decode and
+// the two-pass LLR scaling.
+//
+// Replaces, per frame, MCDPSKWaveform::process (src/waveform/mc_dpsk_waveform.cpp:294-338)
+//   = MultiCarrierDPSKDemodulator::setChirpDetected + process -> processGotChirp
+//     (src/psk/multi_carrier_dpsk.hpp:323-340, 797-895), which runs
+//       applyCFOCorrection   :901-926   (127-tap Hilbert, src/dsp/filters.cpp:266-317)
+//       setReference         :507-518
+//       demodulateOneSymbol  :931-946
+//       demodulateSoft       :520-736
+//   processTraining (:473-505) only refines cfo_hz_, which processGotChirp overwrites again when
+//   the chirp was detected externally (:857-862) -- it has no effect on any output and is skipped.
+//
+// Kernels
+//   mcdpsk_phase_scan_kernel  one warp per frame: phase of the fp32 CFO accumulator at every
+//                             32-sample block boundary (exact, cfo_phase.cuh)
+//   mcdpsk_cfo_kernel         Hilbert FIR + rotation -> corrected samples (HBM scratch)
+//   mcdpsk_demod_kernel       one CTA per frame: correlate, despread, differential phases, LLRs
+//
+// Float-order fidelity: every per-(symbol, carrier) correlation is accumulated over the 512
+// samples in the reference's order without FMA, the mixer phasors come from a host table built
+// with the reference's fp32 recurrence, and the ordered reductions of demodulateSoft are
+// evaluated in the reference's order.
+
+#include "cfo_phase.cuh"
+#include "ria_internal.h"
+
+#include <cmath>
+
+namespace ria {
+
+struct McdpskTablesDev {
+    bool ready = false;
+    ria_mcdpsk_config cfg{};
+    float2* mixer = nullptr;     // [carriers][sps] = polar(1, -phase_i)
+    float* hilbert = nullptr;    // 127 taps
+};
+
+namespace {
+
+constexpr int kMaxCar = 16;
+constexpr int kSps = 512;
+constexpr int kSpsPad = kSps + 1;
+constexpr int kGroup = 24;               // rx symbols correlated per pass (multiple of 1, 2 and 4)
+constexpr int kDemodThreads = 256;
+constexpr int kHilbertTaps = 127;
+constexpr int kHilbertDelay = 63;
+
+__device__ __forceinline__ float cabs_d(float2 a) {
+    const double x = a.x, y = a.y;
+    return static_cast<float>(sqrt(x * x + y * y));
+}
+__device__ __forceinline__ float atan2_rn(float y, float x) { return static_cast<float>(atan2(static_cast<double>(y), static_cast<double>(x))); }
+__device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }
+__device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b : a; }
+
+// ---------------------------------------------------------------------------------------------
+// CFO correction
+// ---------------------------------------------------------------------------------------------
+__global__ void mcdpsk_phase_scan_kernel(const float* __restrict__ cfo_hz, const float* __restrict__ phase0,
+                                         long long n_frames, int n_blocks, float sample_rate,
+                                         float* __restrict__ block_phase /*[n][n_blocks]*/) {
+    const long long f = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (f >= n_frames) return;
+    const float cfo = cfo_hz[f];
+    if (!(fabsf(cfo) > 0.1f)) return;
+    // phase_inc = -2.0f * M_PI * cfo_hz / sample_rate   (multi_carrier_dpsk.hpp:911)
+    const float inc = static_cast<float>(-2.0f * M_PI * static_cast<double>(cfo) / static_cast<double>(sample_rate));
+    float base = phase0 ? phase0[f] : 0.0f;
+    float* out = block_phase + f * n_blocks;
+    for (int b = 0; b < n_blocks; ++b) {
+        if (lane == 0) out[b] = base;
+        float next;
+        (void)cfo_phase_block32(base, inc, lane, &next);
+        base = next;
+    }
+}
+
+// One thread per sample; a CTA covers 1024 consecutive samples of one frame (+126 history).
+__global__ void __launch_bounds__(256)
+mcdpsk_cfo_kernel(const float* __restrict__ samples, long long frame_stride, int frame_len,
+                  const float* __restrict__ cfo_hz, const float* __restrict__ block_phase, int n_blocks,
+                  const float* __restrict__ taps_g, float sample_rate,
+                  float* __restrict__ out, long long out_stride) {
+    __shared__ float taps[kHilbertTaps + 1];
+    __shared__ float x[1024 + kHilbertTaps];
+    const long long f = blockIdx.y;
+    const int chunk0 = blockIdx.x * 1024;
+    const float cfo = cfo_hz[f];
+    const float* src = samples + f * frame_stride;
+    float* dst = out + f * out_stride;
+    const bool active = fabsf(cfo) > 0.1f && frame_len >= 128;      // :838, :903
+    if (!active) {
+        for (int i = threadIdx.x; i < 1024 && chunk0 + i < frame_len; i += 256) dst[chunk0 + i] = src[chunk0 + i];
+        return;
+    }
+    if (threadIdx.x < kHilbertTaps) taps[threadIdx.x] = taps_g[threadIdx.x];
+    for (int i = threadIdx.x; i < 1024 + kHilbertTaps - 1; i += 256) {
+        const int g = chunk0 - (kHilbertTaps - 1) + i;
+        x[i] = (g >= 0 && g < frame_len) ? src[g] : 0.0f;          // delay line starts at zero
+    }
+    __syncthreads();
+    const float inc = static_cast<float>(-2.0f * M_PI * static_cast<double>(cfo) / static_cast<double>(sample_rate));
+    const int lane = threadIdx.x & 31;
+    for (int r = 0; r < 4; ++r) {
+        const int li = r * 256 + threadIdx.x;          // local sample
+        const int gi = chunk0 + li;
+        const int blk = gi >> 5;
+        float nx;
+        const float ph = (blk < n_blocks) ? cfo_phase_block32(block_phase[f * n_blocks + blk], inc, lane, &nx) : 0.0f;
+        if (gi >= frame_len) continue;
+        // q = sum_k coeffs[k] * x[i - k], ascending k (filters.cpp:299-306); odd taps are exactly 0
+        float q = 0.0f;
+        const float* xp = x + li + (kHilbertTaps - 1);
+#pragma unroll 8
+        for (int k = 0; k < kHilbertTaps; k += 2) q = __fadd_rn(q, __fmul_rn(taps[k], xp[-k]));
+        const float re = xp[-kHilbertDelay];           // delayed input (filters.cpp:309-310)
+        double s, c;
+        sincos(static_cast<double>(ph), &s, &c);
+        const float cr = static_cast<float>(c), sr = static_cast<float>(s);
+        // real part of analytic * rotation (:916-917)
+        dst[gi] = __fsub_rn(__fmul_rn(re, cr), __fmul_rn(q, sr));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// demod
+// ---------------------------------------------------------------------------------------------
+struct DemodArgs {
+    const float* samples; long long frame_stride; int frame_len;
+    const float* cfo_hz; long long n_frames;
+    float* llr; int llr_stride; int* n_llr; float* fading; float* cfo_out;
+    float* scratch;            // per frame: mags[max_ds][C] | phases[max_ds][C] | errs[max_ds][C]
+    int max_ds;
+    const float2* mixer_g;
+    int carriers, bits, spread, training;
+    unsigned int* counter;
+};
+
+struct DemodSmem {
+    float2 mixer[kMaxCar * kSpsPad];
+    float sym[kGroup * kSpsPad];
+    float2 corr[kGroup * kMaxCar];
+    float2 prev[kMaxCar];
+    float car_sum[kMaxCar], car_sq[kMaxCar], rel[kMaxCar], car_mag[kMaxCar];
+    float scale;
+    int valid_symbols;
+    long long frame;
+};
+
+__global__ void __launch_bounds__(kDemodThreads)
+mcdpsk_demod_kernel(const DemodArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DemodSmem& sm = *reinterpret_cast<DemodSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int C = a.carriers;
+    for (int i = tid; i < C * kSps; i += kDemodThreads) {
+        const int c = i / kSps, k = i - c * kSps;
+        sm.mixer[c * kSpsPad + k] = a.mixer_g[i];
+    }
+    __syncthreads();
+
+    const int preamble = (a.training + 1) * kSps;
+    const int data_samples = a.frame_len - preamble;
+    const int n_rx = data_samples > 0 ? data_samples / kSps : 0;
+    int n_ds = n_rx / a.spread;
+    if (n_ds < 1) n_ds = 1;                                         // :527
+    const int n_out = n_ds * C * a.bits;
+
+    for (;;) {
+        if (tid == 0) sm.frame = static_cast<long long>(atomicAdd(a.counter, 1u));
+        __syncthreads();
+        const long long f = sm.frame;
+        __syncthreads();
+        if (f >= a.n_frames) break;
+        float* llr_out = a.llr + f * a.llr_stride;
+        if (a.frame_len <= preamble || n_ds > a.max_ds) {           // processGotChirp waits for more samples
+            if (tid == 0) { a.n_llr[f] = 0; if (a.fading) a.fading[f] = 0.0f; if (a.cfo_out) a.cfo_out[f] = a.cfo_hz ? a.cfo_hz[f] : 0.0f; }
+            for (int i = tid; i < a.llr_stride; i += kDemodThreads) llr_out[i] = 0.0f;
+            continue;
+        }
+        const float* frame = a.samples + f * a.frame_stride;
+        float* mags = a.scratch + f * (3LL * a.max_ds * kMaxCar);
+        float* phases = mags + a.max_ds * kMaxCar;
+        float* errs = phases + a.max_ds * kMaxCar;
+
+        // ---- setReference (:507-518): symbol right after the training ----
+        for (int i = tid; i < kSps; i += kDemodThreads) sm.sym[i] = frame[a.training * kSps + i];
+        __syncthreads();
+        if (tid < C) {
+            float2 acc = make_float2(0.f, 0.f);
+            const float2* mx = sm.mixer + tid * kSpsPad;
+            for (int i = 0; i < kSps; ++i) {
+                const float s = sm.sym[i];
+                acc.x = __fadd_rn(acc.x, __fmul_rn(mx[i].x, s));
+                acc.y = __fadd_rn(acc.y, __fmul_rn(mx[i].y, s));
+            }
+            float2 p = make_float2(__fdiv_rn(acc.x, static_cast<float>(kSps)), __fdiv_rn(acc.y, static_cast<float>(kSps)));
+            const float m = cabs_d(p);
+            if (m > 0.001f) { const float m2 = cabs_d(p); p = make_float2(__fdiv_rn(p.x, m2), __fdiv_rn(p.y, m2)); }
+            else p = make_float2(1.0f, 0.0f);
+            sm.prev[tid] = p;
+        }
+        __syncthreads();
+
+        // ---- demodulateSoft pass 1 (:548-602): correlate, despread, differential phase ----
+        for (int g0 = 0; g0 < n_ds * a.spread; g0 += kGroup) {
+            int g_n = n_rx - g0;                                   // rx symbols available in this group
+            if (g_n > kGroup) g_n = kGroup;
+            if (g_n < 0) g_n = 0;
+            for (int i = tid; i < g_n * kSps; i += kDemodThreads) {
+                const int s = i / kSps, k = i - s * kSps;
+                sm.sym[s * kSpsPad + k] = __ldcs(frame + preamble + (g0 + s) * kSps + k);
+            }
+            __syncthreads();
+            for (int p = tid; p < kGroup * C; p += kDemodThreads) {
+                const int s = p / C, c = p - s * C;
+                float2 acc = make_float2(0.f, 0.f);
+                if (s < g_n) {
+                    const float2* mx = sm.mixer + c * kSpsPad;
+                    const float* sy = sm.sym + s * kSpsPad;
+#pragma unroll 8
+                    for (int i = 0; i < kSps; ++i) {                // sum += samples[i] * mixer  (:940-943)
+                        const float v = sy[i];
+                        const float2 m = mx[i];
+                        acc.x = __fadd_rn(acc.x, __fmul_rn(m.x, v));
+                        acc.y = __fadd_rn(acc.y, __fmul_rn(m.y, v));
+                    }
+                    acc = make_float2(__fdiv_rn(acc.x, static_cast<float>(kSps)), __fdiv_rn(acc.y, static_cast<float>(kSps)));
+                }
+                sm.corr[s * kMaxCar + c] = acc;
+            }
+            __syncthreads();
+            // combine repetitions, then differential decode; data symbols of a group are
+            // chained through sm.prev, so one thread per carrier walks them in order
+            if (tid < C) {
+                const int c = tid;
+                float2 prev = sm.prev[c];
+                const int ds0 = g0 / a.spread;
+                const int ds_n = kGroup / a.spread;
+                for (int d = 0; d < ds_n && ds0 + d < n_ds; ++d) {
+                    float2 comb = make_float2(0.f, 0.f);
+                    for (int rep = 0; rep < a.spread; ++rep) {
+                        const int rx = (ds0 + d) * a.spread + rep;
+                        if (rx >= n_rx) break;
+                        const float2 cur = sm.corr[(d * a.spread + rep) * kMaxCar + c];
+                        comb.x = __fadd_rn(comb.x, cur.x); comb.y = __fadd_rn(comb.y, cur.y);
+                    }
+                    comb.x = __fdiv_rn(comb.x, static_cast<float>(a.spread));
+                    comb.y = __fdiv_rn(comb.y, static_cast<float>(a.spread));
+                    const float mag = cabs_d(comb);
+                    const float2 nrm = (mag > 0.0001f) ? make_float2(__fdiv_rn(comb.x, mag), __fdiv_rn(comb.y, mag))
+                                                       : make_float2(1.0f, 0.0f);
+                    // diff = normalized * conj(prev)
+                    const float2 diff = make_float2(__fsub_rn(__fmul_rn(nrm.x, prev.x), __fmul_rn(nrm.y, -prev.y)),
+                                                    __fadd_rn(__fmul_rn(nrm.x, -prev.y), __fmul_rn(nrm.y, prev.x)));
+                    prev = nrm;
+                    const float phase = atan2_rn(diff.y, diff.x);
+                    const float PI = static_cast<float>(M_PI);
+                    float err;
+                    if (a.bits == 2) {
+                        const float shifted = phase - PI / 4.0f;
+                        const float idx = roundf(shifted / (PI / 2.0f));
+                        const float ideal = idx * PI / 2.0f + PI / 4.0f;
+                        err = phase - ideal;
+                    } else {
+                        const float idx = roundf(phase / PI);
+                        const float ideal = idx * PI;
+                        err = phase - ideal;
+                    }
+                    while (err > PI) err -= 2.0f * PI;
+                    while (err < -PI) err += 2.0f * PI;
+                    const int o = (ds0 + d) * kMaxCar + c;
+                    mags[o] = mag; phases[o] = phase; errs[o] = err * err;
+                }
+                sm.prev[c] = prev;
+            }
+            __syncthreads();
+        }
+
+        // ---- ordered reductions (:541-570, 604-634, 636-698) ----
+        if (tid == 0) {
+            // noise_sum over (data symbol, carrier) in order
+            float noise_sum = 0.f;
+            for (int d = 0; d < n_ds; ++d) for (int c = 0; c < C; ++c) noise_sum += errs[d * kMaxCar + c];
+            const int noise_count = n_ds * C;
+            // silence detection on per-symbol total magnitude
+            int valid = n_ds;
+            if (n_ds >= 4) {
+                float ref_mag = 0.f;
+                for (int s = 0; s < 4; ++s) { float t = 0.f; for (int c = 0; c < C; ++c) t += mags[s * kMaxCar + c]; ref_mag += t; }
+                ref_mag /= 4.0f;
+                if (ref_mag > 0.001f) {
+                    const float thr = ref_mag * 0.2f;
+                    while (valid > 4) {
+                        float t = 0.f;
+                        for (int c = 0; c < C; ++c) t += mags[(valid - 1) * kMaxCar + c];
+                        if (t < thr) --valid; else break;
+                    }
+                }
+            }
+            sm.valid_symbols = valid;
+            float var = (noise_count > 0) ? noise_sum / noise_count : 0.5f;
+            var = std_max(0.01f, var);
+            float scale = 2.0f * sqrtf(1.0f / var);
+            sm.scale = std_min(scale, 20.0f);
+        }
+        __syncthreads();
+        if (tid < C) {       // per-carrier sums over the valid symbols, in symbol order
+            float s1 = 0.f, s2 = 0.f;
+            for (int d = 0; d < sm.valid_symbols; ++d) { const float m = mags[d * kMaxCar + tid]; s1 += m; s2 += m * m; }
+            sm.car_sum[tid] = s1; sm.car_sq[tid] = s2;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int valid = sm.valid_symbols;
+            for (int c = 0; c < C; ++c) sm.rel[c] = 1.0f;
+            if (a.bits == 1 && valid > 0) {
+                float gsum = 0.f; int gcnt = 0;
+                for (int c = 0; c < C; ++c) {
+                    const float mean = sm.car_sum[c] / valid;
+                    sm.car_mag[c] = mean;
+                    if (mean > 1e-4f) { gsum += mean; ++gcnt; }
+                }
+                const float gmean = (gcnt > 0) ? (gsum / gcnt) : 0.0f;
+                for (int c = 0; c < C; ++c) {
+                    const float mean = sm.car_mag[c];
+                    if (mean <= 1e-4f || gmean <= 1e-4f) { sm.rel[c] = 0.12f; continue; }
+                    const float mean_sq = sm.car_sq[c] / valid;
+                    const float var = std_max(0.0f, mean_sq - mean * mean);
+                    const float cv = sqrtf(var) / (mean + 1e-6f);
+                    const float ratio = mean / gmean;
+                    const float mag_w = std_max(0.10f, std_min(1.25f, ratio));
+                    const float stab = 1.0f / (1.0f + 1.5f * cv);
+                    float damp = 1.0f;
+                    if (ratio < 0.20f) damp = 0.25f; else if (ratio < 0.35f) damp = 0.50f;
+                    const float w = mag_w * stab * damp;
+                    sm.rel[c] = std_max(0.12f, std_min(1.25f, w));
+                }
+            }
+            // fading indices (:702-733, 403-432)
+            if (a.fading) {
+                float cm[kMaxCar];
+                for (int c = 0; c < C; ++c) cm[c] = (valid > 0) ? sm.car_sum[c] / valid : 0.0f;
+                float temporal = 0.0f;
+                if (valid >= 4) {
+                    float cvs = 0.f; int vc = 0;
+                    for (int c = 0; c < C; ++c) {
+                        const float mean = sm.car_sum[c] / valid;
+                        if (mean < 0.001f) continue;
+                        const float mean_sq = sm.car_sq[c] / valid;
+                        const float var = std_max(0.0f, mean_sq - mean * mean);
+                        cvs += sqrtf(var) / mean; ++vc;
+                    }
+                    temporal = (vc > 0) ? cvs / vc : 0.0f;
+                }
+                float sum = 0.f;
+                for (int c = 0; c < C; ++c) sum += cm[c];
+                const float mean = sum / C;
+                float freq_cv = 0.0f;
+                if (!(mean < 0.001f)) {
+                    float vs = 0.f;
+                    for (int c = 0; c < C; ++c) { const float d = cm[c] - mean; vs += d * d; }
+                    freq_cv = sqrtf(vs / C) / mean;
+                }
+                a.fading[f] = freq_cv + 1.0f * temporal;
+            }
+            a.n_llr[f] = n_out;
+            if (a.cfo_out) {
+                const float cfo = a.cfo_hz ? a.cfo_hz[f] : 0.0f;
+                // applyCFOCorrection zeroes cfo_hz_ once the correction is in the samples (:924)
+                a.cfo_out[f] = (fabsf(cfo) > 0.1f && a.frame_len >= 128) ? 0.0f : cfo;
+            }
+        }
+        __syncthreads();
+        // ---- pass 2: LLRs (:683-698) ----
+        for (int p = tid; p < n_ds * C; p += kDemodThreads) {
+            const int d = p / C, c = p - d * C;
+            const float phase = phases[d * kMaxCar + c];
+            const float cs = sm.scale * sm.rel[c];
+            if (a.bits == 2) {
+                const float sb0 = cs * static_cast<float>(sin(static_cast<double>(phase)));
+                const float sb1 = cs * static_cast<float>(sin(static_cast<double>(2.0f * phase)));
+                llr_out[p * 2] = std_max(-20.0f, std_min(20.0f, sb0));
+                llr_out[p * 2 + 1] = std_max(-20.0f, std_min(20.0f, sb1));
+            } else {
+                const float sb = cs * static_cast<float>(cos(static_cast<double>(phase)));
+                llr_out[p] = std_max(-20.0f, std_min(20.0f, sb));
+            }
+        }
+        for (int i = n_out + tid; i < a.llr_stride; i += kDemodThreads) llr_out[i] = 0.0f;
+        __syncthreads();
+    }
+}
+
+const char* mcdpsk_config_error(const ria_mcdpsk_config& c) {
+    if (c.samples_per_symbol != kSps) return "samples_per_symbol must be 512";
+    if (c.num_carriers < 1 || c.num_carriers > kMaxCar) return "num_carriers must be in [1, 16]";
+    if (c.bits_per_symbol != 1 && c.bits_per_symbol != 2) return "bits_per_symbol must be 1 (DBPSK) or 2 (DQPSK)";
+    if (c.spreading != 1 && c.spreading != 2 && c.spreading != 4) return "spreading must be 1, 2 or 4";
+    if (c.training_symbols > 64) return "bad training_symbols";
+    if (!(c.sample_rate > 0.0f)) return "sample_rate must be > 0";
+    return nullptr;
+}
+
+void build_tables(const ria_mcdpsk_config& cfg, std::vector<float2>& mixer, std::vector<float>& taps) {
+    // carrier frequencies (multi_carrier_dpsk.hpp:68-79) and mixer phasors (:931-946)
+    const int C = static_cast<int>(cfg.num_carriers);
+    mixer.resize(static_cast<size_t>(C) * kSps);
+    for (int c = 0; c < C; ++c) {
+        float freq;
+        if (C == 1) freq = (cfg.freq_low + cfg.freq_high) / 2.0f;
+        else { const float spacing = (cfg.freq_high - cfg.freq_low) / (C - 1); freq = cfg.freq_low + c * spacing; }
+        const float phase_inc = 2.0f * M_PI * freq / cfg.sample_rate;
+        float phase = 0.0f;
+        for (int i = 0; i < kSps; ++i) {
+            mixer[static_cast<size_t>(c) * kSps + i] = make_float2(1.0f * std::cos(-phase), 1.0f * std::sin(-phase));
+            phase += phase_inc;
+        }
+    }
+    // HilbertTransform(127) coefficients (filters.cpp:266-291)
+    taps.assign(kHilbertTaps, 0.0f);
+    const int M = (kHilbertTaps - 1) / 2;
+    for (int n = 0; n < kHilbertTaps; ++n) {
+        const int k = n - M;
+        float v;
+        if (k == 0) v = 0;
+        else if (k % 2 != 0) v = 2.0f / (M_PI * k);
+        else v = 0;
+        const float w = 2.0f * M_PI * n / (kHilbertTaps - 1);
+        v *= 0.42f - 0.5f * std::cos(w) + 0.08f * std::cos(2.0f * w);
+        taps[n] = v;
+    }
+}
+
+}  // namespace
+
+void mcdpsk_tables_free(McdpskTablesDev* t) {
+    if (!t) return;
+    if (t->mixer) cudaFree(t->mixer);
+    if (t->hilbert) cudaFree(t->hilbert);
+    delete t;
+}
+
+static int mcdpsk_tables_dev(ria_ctx* ctx, const ria_mcdpsk_config& cfg, const McdpskTablesDev** out) {
+    if (const char* e = mcdpsk_config_error(cfg)) return set_error(ctx, RIA_E_UNSUPPORTED, "mcdpsk: %s", e);
+    for (McdpskTablesDev* t : ctx->mcdpsk_tables)
+        if (std::memcmp(&t->cfg, &cfg, sizeof cfg) == 0) { *out = t; return RIA_OK; }
+    std::vector<float2> mixer;
+    std::vector<float> taps;
+    build_tables(cfg, mixer, taps);
+    McdpskTablesDev* t = new McdpskTablesDev();
+    t->cfg = cfg;
+    ctx->mcdpsk_tables.push_back(t);
+    RIA_CUDA(ctx, cudaMalloc(&t->mixer, mixer.size() * sizeof(float2)));
+    RIA_CUDA(ctx, cudaMalloc(&t->hilbert, taps.size() * sizeof(float)));
+    RIA_CUDA(ctx, cudaMemcpy(t->mixer, mixer.data(), mixer.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    RIA_CUDA(ctx, cudaMemcpy(t->hilbert, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    t->ready = true;
+    *out = t;
+    return RIA_OK;
+}
+
+}  // namespace ria
+
+extern "C" int ria_mcdpsk_soft_bits_per_frame(const ria_mcdpsk_config* cfg, int32_t frame_len) {
+    if (!cfg || ria::mcdpsk_config_error(*cfg)) return RIA_E_INVAL;
+    const int preamble = (static_cast<int>(cfg->training_symbols) + 1) * static_cast<int>(cfg->samples_per_symbol);
+    if (frame_len <= preamble) return 0;
+    const int n_rx = (frame_len - preamble) / static_cast<int>(cfg->samples_per_symbol);
+    int n_ds = n_rx / static_cast<int>(cfg->spreading);
+    if (n_ds < 1) n_ds = 1;
+    return n_ds * static_cast<int>(cfg->num_carriers) * static_cast<int>(cfg->bits_per_symbol);
+}
+
+extern "C" int ria_mcdpsk_process_batch_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg,
+                                            const float* samples_dev, int64_t frame_stride, int32_t frame_len,
+                                            const float* cfo_hz_dev, const float* phase_dev, int64_t n_frames,
+                                            float* llr_dev, int32_t llr_stride, int32_t* n_llr_dev,
+                                            float* fading_dev, float* cfo_out_dev) {
+    using namespace ria;
+    if (!ctx || !cfg) return RIA_E_INVAL;
+    if (n_frames < 0 || frame_len < 0 || frame_stride < frame_len) return set_error(ctx, RIA_E_INVAL, "mcdpsk: bad sizes");
+    if (n_frames == 0) return RIA_OK;
+    if (!samples_dev || !llr_dev || !n_llr_dev) return set_error(ctx, RIA_E_INVAL, "mcdpsk: null buffer");
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    const McdpskTablesDev* t = nullptr;
+    int rc = mcdpsk_tables_dev(ctx, *cfg, &t);
+    if (rc != RIA_OK) return rc;
+    const int n_out = ria_mcdpsk_soft_bits_per_frame(cfg, frame_len);
+    if (llr_stride < n_out) return set_error(ctx, RIA_E_INVAL, "mcdpsk: llr_stride %d < %d soft bits per frame", llr_stride, n_out);
+    const int C = static_cast<int>(cfg->num_carriers);
+    const int max_ds = n_out / (C * static_cast<int>(cfg->bits_per_symbol)) + 1;
+    const int n_blocks = (frame_len + 31) / 32;
+
+    // scratch: per-frame mags/phases/errs, then (only with a CFO vector) block phases + corrected samples
+    const size_t s_demod = static_cast<size_t>(n_frames) * 3 * max_ds * kMaxCar * sizeof(float);
+    const size_t s_phase = cfo_hz_dev ? static_cast<size_t>(n_frames) * n_blocks * sizeof(float) : 0;
+    const size_t corr_stride = (static_cast<size_t>(frame_len) + 3) & ~size_t(3);
+    const size_t s_corr = cfo_hz_dev ? static_cast<size_t>(n_frames) * corr_stride * sizeof(float) : 0;
+    const size_t a1 = (s_demod + 255) & ~size_t(255), a2 = (s_phase + 255) & ~size_t(255);
+    rc = ensure_scratch(ctx, a1 + a2 + s_corr + 256);
+    if (rc != RIA_OK) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->scratch);
+    float* d_scr = reinterpret_cast<float*>(base);
+    float* d_bph = reinterpret_cast<float*>(base + a1);
+    float* d_corr = reinterpret_cast<float*>(base + a1 + a2);
+
+    const float* demod_in = samples_dev;
+    long long demod_stride = frame_stride;
+    if (cfo_hz_dev) {
+        const unsigned scan_blocks = static_cast<unsigned>((n_frames * 32 + 127) / 128);
+        time_begin(ctx, KK_MCDPSK_CFO);
+        mcdpsk_phase_scan_kernel<<<scan_blocks, 128, 0, ctx->stream>>>(cfo_hz_dev, phase_dev, n_frames, n_blocks,
+                                                                      cfg->sample_rate, d_bph);
+        dim3 grid(static_cast<unsigned>((frame_len + 1023) / 1024), static_cast<unsigned>(n_frames));
+        if (n_frames > 65535) return set_error(ctx, RIA_E_INVAL, "mcdpsk: batch too large for one CFO launch (max 65535 frames)");
+        mcdpsk_cfo_kernel<<<grid, 256, 0, ctx->stream>>>(samples_dev, frame_stride, frame_len, cfo_hz_dev, d_bph, n_blocks,
+                                                         t->hilbert, cfg->sample_rate, d_corr, static_cast<long long>(corr_stride));
+        time_end(ctx);
+        RIA_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 2;
+        demod_in = d_corr;
+        demod_stride = static_cast<long long>(corr_stride);
+    }
+
+    DemodArgs a{};
+    a.samples = demod_in; a.frame_stride = demod_stride; a.frame_len = frame_len;
+    a.cfo_hz = cfo_hz_dev; a.n_frames = n_frames;
+    a.llr = llr_dev; a.llr_stride = llr_stride; a.n_llr = n_llr_dev; a.fading = fading_dev; a.cfo_out = cfo_out_dev;
+    a.scratch = d_scr; a.max_ds = max_ds; a.mixer_g = t->mixer;
+    a.carriers = C; a.bits = static_cast<int>(cfg->bits_per_symbol); a.spread = static_cast<int>(cfg->spreading);
+    a.training = static_cast<int>(cfg->training_symbols);
+    a.counter = ctx->work_counter + 2;
+    const size_t smem = sizeof(DemodSmem);
+    RIA_CUDA(ctx, cudaFuncSetAttribute(mcdpsk_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RIA_CUDA(ctx, cudaFuncSetAttribute(mcdpsk_demod_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    RIA_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mcdpsk_demod_kernel, kDemodThreads, smem));
+    if (per_sm < 1) return set_error(ctx, RIA_E_UNSUPPORTED, "mcdpsk: kernel does not fit");
+    long long grid = static_cast<long long>(ctx->sm_count) * per_sm;
+    if (grid > n_frames) grid = n_frames;
+    RIA_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), ctx->stream));
+    time_begin(ctx, KK_MCDPSK);
+    mcdpsk_demod_kernel<<<static_cast<unsigned>(grid), kDemodThreads, smem, ctx->stream>>>(a);
+    time_end(ctx);
+    RIA_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return RIA_OK;
+}

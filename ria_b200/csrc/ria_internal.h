@@ -33,6 +33,7 @@ const LdpcCodeHost& ldpc_code_host(int rate);   // cached, thread-safe; throws o
 bool ldpc_rate_valid(int rate);
 
 struct OfdmTablesDev;   // ofdm_tables.h
+struct McdpskTablesDev; // mcdpsk.cu
 
 struct LdpcCodeDev {
     bool ready = false;
@@ -57,6 +58,7 @@ struct ria_ctx {
     ria::LdpcCodeDev ldpc[8];
     unsigned int* work_counter = nullptr;   // device, dynamic tile schedulers (one slot per kernel)
     std::vector<ria::OfdmTablesDev*> ofdm_tables;
+    std::vector<ria::McdpskTablesDev*> mcdpsk_tables;
     // scratch owned by the context for the fused chain entry points
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -79,11 +81,12 @@ int ensure_stage(ria_ctx* ctx, int which, size_t dev_bytes, size_t pin_bytes);
 int ldpc_tables_dev(ria_ctx* ctx, int rate, const LdpcCodeDev** out);
 int ofdm_tables_dev(ria_ctx* ctx, const ria_modem_config& cfg, int need_nco, const OfdmTablesDev** out);
 void ofdm_tables_free(OfdmTablesDev* t);
+void mcdpsk_tables_free(McdpskTablesDev* t);
 int ensure_scratch(ria_ctx* ctx, size_t bytes);
 
 // kernel kinds for the timing hook / launch accounting
 enum KernelKind { KK_LDPC = 0, KK_OFDM_DEMOD = 1, KK_FRAME_STATUS = 2, KK_AWGN = 3, KK_MCDPSK = 4,
-                  KK_ZC_SYNC = 5, KK_CHIRP_SYNC = 6, KK_CHASE = 7, KK_WATTERSON = 8, KK_COUNT = 16 };
+                  KK_ZC_SYNC = 5, KK_CHIRP_SYNC = 6, KK_CHASE = 7, KK_WATTERSON = 8, KK_MCDPSK_CFO = 9, KK_COUNT = 16 };
 void time_begin(ria_ctx* ctx, int kind);
 void time_end(ria_ctx* ctx);
 
