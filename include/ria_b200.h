@@ -205,6 +205,45 @@ int ria_ofdm_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg, int rate,
                             const float* cfo_hz, const float* phase, int64_t n_frames,
                             uint8_t* data, ria_frame_status* status, float* snr_db);
 
+/* ---- synchronisation ------------------------------------------------------------------------- */
+/* sync::ZCConfig (src/sync/zc_sync.hpp:61-108) */
+typedef struct {
+    float   sample_rate;
+    int32_t sequence_length;     /* 127 */
+    int32_t upsample_factor;     /* 8   */
+    int32_t num_repetitions;     /* 2   */
+    float   carrier_freq;        /* 1500 */
+    float   gap_ms;              /* 10  */
+    int32_t root_ping, root_pong, root_data, root_control;   /* 1, 3, 5, 7 */
+} ria_zc_config;
+
+/* sync::ZCSyncResult (zc_sync.hpp:111-119) / sync::ChirpSync::DualChirpResult (chirp_sync.hpp:343-350) */
+typedef struct {
+    int32_t detected;
+    int32_t start_sample;        /* ZC: position + preamble length; chirp: CFO-corrected up-chirp start */
+    float   correlation;         /* ZC: best (combined) correlation; chirp: up-chirp correlation        */
+    float   cfo_hz;
+    float   snr_estimate;        /* ZC only (correlationToSNR); chirp: down-chirp correlation           */
+    int32_t root;                /* ZC: detected root, -1 if none; chirp: raw up-chirp position         */
+    int32_t frame_type;          /* ZC: ZCFrameType, 255 = unknown; chirp: raw down-chirp position      */
+    int32_t aux;                 /* chirp: CFO-corrected down-chirp start                               */
+} ria_sync_result;
+
+/* the configuration MCDPSKWaveform::initZCSync uses (src/waveform/mc_dpsk_waveform.cpp:50-64) */
+int ria_zc_config_default(ria_zc_config* cfg);
+
+/* Batched replacement for sync::ZCSync::detect(samples, threshold, false, root_mask, known_cfo_hz)
+ * (src/sync/zc_sync.hpp:192-391) as called by MCDPSKWaveform::detectDataSync
+ * (src/waveform/mc_dpsk_waveform.cpp:227-292).
+ *   samples_dev    fp32 search windows, window f at samples_dev + f*frame_stride, `window` samples
+ *   known_cfo_dev  [n] known CFO in Hz added to the down-conversion frequency (NULL = 0)
+ *   root_mask      bit 0 PING, 1 PONG, 2 DATA, 3 CONTROL (ZC_ROOT_MASK_*, zc_sync.hpp:34-41)
+ *   out_dev        [n] results; at most 65535 windows per call */
+int ria_zc_detect_batch_dev(ria_ctx* ctx, const ria_zc_config* cfg,
+                            const float* samples_dev, int64_t frame_stride, int32_t window,
+                            const float* known_cfo_dev, float threshold, uint32_t root_mask,
+                            int64_t n_frames, ria_sync_result* out_dev);
+
 /* ---- MC-DPSK receive path -------------------------------------------------------------------- */
 /* POD mirror of the RX-relevant fields of ultra::MultiCarrierDPSKConfig
  * (src/psk/multi_carrier_dpsk.hpp:27-100).  Reference defaults: 48000, 8 carriers (the tools use

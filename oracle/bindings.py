@@ -77,6 +77,25 @@ class McdpskConfig(C.Structure):
         return cls(48000.0, carriers, 500.0, 2500.0, 512, bits, spreading, training)
 
 
+class ZcConfig(C.Structure):
+    """Same layout as ria_zc_config (include/ria_b200.h)."""
+    _fields_ = [("sample_rate", C.c_float), ("sequence_length", C.c_int32), ("upsample_factor", C.c_int32),
+                ("num_repetitions", C.c_int32), ("carrier_freq", C.c_float), ("gap_ms", C.c_float),
+                ("root_ping", C.c_int32), ("root_pong", C.c_int32), ("root_data", C.c_int32),
+                ("root_control", C.c_int32)]
+
+    @classmethod
+    def default(cls):
+        return cls(48000.0, 127, 8, 2, 1500.0, 10.0, 1, 3, 5, 7)
+
+
+class SyncResult(C.Structure):
+    """Same layout as ria_sync_result (include/ria_b200.h)."""
+    _fields_ = [("detected", C.c_int32), ("start_sample", C.c_int32), ("correlation", C.c_float),
+                ("cfo_hz", C.c_float), ("snr_estimate", C.c_float), ("root", C.c_int32),
+                ("frame_type", C.c_int32), ("aux", C.c_int32)]
+
+
 class FrameStatus(C.Structure):
     """Same layout as ria_frame_status (include/ria_b200.h)."""
     _fields_ = [("cw_ok", C.c_uint8 * 4), ("cw_iters", C.c_int32 * 4), ("all_ok", C.c_uint8),
@@ -187,6 +206,13 @@ class Ref:
         L.ref_make_data_frame.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _u8p, C.c_int, _u8p, C.c_int]
         L.ref_make_data_frame.restype = C.c_int
         self._demods = {}
+        zcp = C.POINTER(ZcConfig)
+        L.ref_zc_preamble.argtypes = [zcp, C.c_int, _f32p, C.c_int]
+        L.ref_zc_preamble.restype = C.c_int
+        L.ref_zc_detect.argtypes = [zcp, _f32p, C.c_int, C.c_float, C.c_uint, C.c_float, C.POINTER(SyncResult)]
+        L.ref_chirp_generate.argtypes = [_f32p, C.c_int]
+        L.ref_chirp_generate.restype = C.c_int
+        L.ref_chirp_detect_dual.argtypes = [_f32p, C.c_int, C.c_float, C.POINTER(SyncResult)]
         mcp = C.POINTER(McdpskConfig)
         L.ref_mcdpsk_tx_frame.argtypes = [mcp, _u8p, C.c_int, _f32p, C.c_int]
         L.ref_mcdpsk_tx_frame.restype = C.c_int
@@ -270,6 +296,31 @@ class Ref:
         bins = np.zeros((n_sym, cfg.num_carriers, 2), np.float32)
         self.lib.ref_ofdm_symbol_bins(self._demod(cfg), samples, n_sym, cfo_hz, phase, bins)
         return bins[..., 0] + 1j * bins[..., 1]
+
+    # ---- sync ----
+    def zc_preamble(self, cfg: ZcConfig, frame_type: int) -> np.ndarray:
+        out = np.zeros(8192, np.float32)
+        n = self.lib.ref_zc_preamble(C.byref(cfg), frame_type, out, len(out))
+        assert n > 0
+        return out[:n].copy()
+
+    def zc_detect(self, cfg: ZcConfig, samples, threshold=0.3, root_mask=0xF, known_cfo=0.0) -> SyncResult:
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        r = SyncResult()
+        self.lib.ref_zc_detect(C.byref(cfg), samples, len(samples), threshold, root_mask, known_cfo, C.byref(r))
+        return r
+
+    def chirp_generate(self) -> np.ndarray:
+        out = np.zeros(60000, np.float32)
+        n = self.lib.ref_chirp_generate(out, len(out))
+        assert n > 0
+        return out[:n].copy()
+
+    def chirp_detect_dual(self, samples, threshold=0.15) -> SyncResult:
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        r = SyncResult()
+        self.lib.ref_chirp_detect_dual(samples, len(samples), threshold, C.byref(r))
+        return r
 
     # ---- MC-DPSK ----
     def mcdpsk_tx_frame(self, cfg: McdpskConfig, data) -> np.ndarray:

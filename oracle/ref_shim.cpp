@@ -20,6 +20,8 @@
 #include "protocol/frame_v2.hpp"
 #include "psk/multi_carrier_dpsk.hpp"
 #include "fec/chase_cache.hpp"
+#include "sync/zc_sync.hpp"
+#include "sync/chirp_sync.hpp"
 
 #include "ria_b200.h"                     // POD config / status structs shared with the product ABI
 
@@ -334,6 +336,66 @@ int ref_mcdpsk_process(void* h, const float* samples, int n, float cfo_hz, float
     if (fading) *fading = d->getFadingIndex();
     if (cfo_out) *cfo_out = d->getEstimatedCFO();
     return ready ? 1 : 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Sync  (src/sync/zc_sync.hpp, src/sync/chirp_sync.hpp)
+// ---------------------------------------------------------------------------------------------
+static sync::ZCConfig to_zc(const ria_zc_config* c) {
+    sync::ZCConfig z;
+    z.sample_rate = c->sample_rate; z.sequence_length = c->sequence_length; z.upsample_factor = c->upsample_factor;
+    z.num_repetitions = c->num_repetitions; z.carrier_freq = c->carrier_freq; z.gap_ms = c->gap_ms;
+    z.root_ping = c->root_ping; z.root_pong = c->root_pong; z.root_data = c->root_data; z.root_control = c->root_control;
+    return z;
+}
+
+int ref_zc_preamble(const ria_zc_config* c, int frame_type, float* out, int cap) {
+    sync::ZCSync zc(to_zc(c));
+    Samples p = zc.generatePreamble(static_cast<sync::ZCFrameType>(frame_type));
+    int n = static_cast<int>(p.size());
+    if (n > cap) return -n;
+    std::memcpy(out, p.data(), p.size() * 4);
+    return n;
+}
+
+void ref_zc_detect(const ria_zc_config* c, const float* samples, int n, float threshold, unsigned root_mask,
+                   float known_cfo, ria_sync_result* out) {
+    sync::ZCSync zc(to_zc(c));
+    auto r = zc.detect(SampleSpan(samples, static_cast<size_t>(n)), threshold, false,
+                       static_cast<uint8_t>(root_mask), known_cfo);
+    out->detected = r.detected ? 1 : 0;
+    out->start_sample = r.start_sample;
+    out->correlation = r.correlation;
+    out->cfo_hz = r.cfo_hz;
+    out->snr_estimate = r.snr_estimate;
+    out->root = r.root_detected;
+    out->frame_type = static_cast<int>(r.frame_type);
+    out->aux = 0;
+}
+
+static sync::ChirpSync& chirp_instance() {
+    static sync::ChirpSync cs{sync::ChirpConfig{}};    // the defaults both waveforms use
+    return cs;
+}
+
+int ref_chirp_generate(float* out, int cap) {
+    Samples p = chirp_instance().generate();
+    int n = static_cast<int>(p.size());
+    if (n > cap) return -n;
+    std::memcpy(out, p.data(), p.size() * 4);
+    return n;
+}
+
+void ref_chirp_detect_dual(const float* samples, int n, float threshold, ria_sync_result* out) {
+    auto r = chirp_instance().detectDualChirp(SampleSpan(samples, static_cast<size_t>(n)), threshold);
+    out->detected = r.success ? 1 : 0;
+    out->start_sample = r.up_chirp_start;
+    out->correlation = r.up_correlation;
+    out->cfo_hz = r.cfo_hz;
+    out->snr_estimate = r.down_correlation;
+    out->root = 0; out->frame_type = 0;
+    out->aux = r.down_chirp_start;
 }
 
 }  // extern "C"

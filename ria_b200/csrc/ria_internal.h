@@ -34,6 +34,8 @@ bool ldpc_rate_valid(int rate);
 
 struct OfdmTablesDev;   // ofdm_tables.h
 struct McdpskTablesDev; // mcdpsk.cu
+struct ZcTablesDev;     // zc_sync.cu
+struct ChirpTablesDev;  // chirp_sync.cu
 
 struct LdpcCodeDev {
     bool ready = false;
@@ -59,6 +61,8 @@ struct ria_ctx {
     unsigned int* work_counter = nullptr;   // device, dynamic tile schedulers (one slot per kernel)
     std::vector<ria::OfdmTablesDev*> ofdm_tables;
     std::vector<ria::McdpskTablesDev*> mcdpsk_tables;
+    std::vector<ria::ZcTablesDev*> zc_tables;
+    std::vector<ria::ChirpTablesDev*> chirp_tables;
     // scratch owned by the context for the fused chain entry points
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -82,6 +86,7 @@ int ldpc_tables_dev(ria_ctx* ctx, int rate, const LdpcCodeDev** out);
 int ofdm_tables_dev(ria_ctx* ctx, const ria_modem_config& cfg, int need_nco, const OfdmTablesDev** out);
 void ofdm_tables_free(OfdmTablesDev* t);
 void mcdpsk_tables_free(McdpskTablesDev* t);
+void zc_tables_free(ZcTablesDev* t);
 int ensure_scratch(ria_ctx* ctx, size_t bytes);
 
 // kernel kinds for the timing hook / launch accounting

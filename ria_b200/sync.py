@@ -1,0 +1,88 @@
+"""Host-side mirror of the reference synchronisers over the C ABI.
+
+  * ``ZCConfig`` / ``ZCSync.detect_batch``      <- sync::ZCSync::detect (src/sync/zc_sync.hpp:192-391)
+  * ``ChirpSync.detect_dual_batch``             <- sync::ChirpSync::detectDualChirp
+                                                   (src/sync/chirp_sync.hpp:352-512)
+Results come back as a structured numpy array with the fields of ``ria_sync_result``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ._lib import Context, RiaError, lib
+from .fec import default_context
+
+ZC_ROOT_MASK_PING, ZC_ROOT_MASK_PONG, ZC_ROOT_MASK_DATA, ZC_ROOT_MASK_CONTROL = 1, 2, 4, 8
+ZC_ROOT_MASK_ALL = 15
+ZC_DEFAULT_DETECT_THRESHOLD = 0.3
+
+SYNC_RESULT_DTYPE = np.dtype([("detected", np.int32), ("start_sample", np.int32), ("correlation", np.float32),
+                              ("cfo_hz", np.float32), ("snr_estimate", np.float32), ("root", np.int32),
+                              ("frame_type", np.int32), ("aux", np.int32)])
+
+
+class ZCConfig(C.Structure):
+    """ria_zc_config (include/ria_b200.h) = sync::ZCConfig."""
+    _fields_ = [("sample_rate", C.c_float), ("sequence_length", C.c_int32), ("upsample_factor", C.c_int32),
+                ("num_repetitions", C.c_int32), ("carrier_freq", C.c_float), ("gap_ms", C.c_float),
+                ("root_ping", C.c_int32), ("root_pong", C.c_int32), ("root_data", C.c_int32),
+                ("root_control", C.c_int32)]
+
+    @classmethod
+    def default(cls):
+        c = cls()
+        lib().ria_zc_config_default(C.addressof(c))
+        return c
+
+    def singleRepSamples(self) -> int:
+        return self.sequence_length * self.upsample_factor
+
+    def preambleSamples(self) -> int:
+        return self.singleRepSamples() * self.num_repetitions + int(np.float32(self.sample_rate) * np.float32(self.gap_ms) / np.float32(1000.0))
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _check_windows(samples):
+    if not (isinstance(samples, torch.Tensor) and samples.is_cuda and samples.dtype == torch.float32
+            and samples.dim() == 2):
+        raise RiaError("detect wants CUDA fp32 [n_windows, window] (no CPU fallback)")
+    return samples if samples.stride(1) == 1 else samples.contiguous()
+
+
+class ZCSync:
+    def __init__(self, config: Optional[ZCConfig] = None, ctx: Optional[Context] = None):
+        self.config = config or ZCConfig.default()
+        self._ctx = ctx
+
+    @property
+    def ctx(self) -> Context:
+        if self._ctx is None:
+            self._ctx = default_context()
+        return self._ctx
+
+    def detect_batch(self, samples: torch.Tensor, threshold: float = ZC_DEFAULT_DETECT_THRESHOLD,
+                     root_mask: int = ZC_ROOT_MASK_ALL, known_cfo_hz: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """-> uint8 tensor [n, 32]; ``results(t)`` views it with SYNC_RESULT_DTYPE."""
+        samples = _check_windows(samples)
+        n, window = samples.shape
+        out = torch.empty((n, SYNC_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=samples.device)
+        ctx = self.ctx
+        ctx.set_stream(torch.cuda.current_stream(samples.device))
+        for off in range(0, n, 32768):
+            m = min(32768, n - off)
+            ctx.check(lib().ria_zc_detect_batch_dev(
+                ctx.handle, C.addressof(self.config), _ptr(samples[off:]), samples.stride(0), window,
+                _ptr(known_cfo_hz[off:]) if known_cfo_hz is not None else C.c_void_p(0),
+                float(threshold), int(root_mask), m, _ptr(out[off:])))
+        return out
+
+
+def results(t: torch.Tensor) -> np.ndarray:
+    return t.cpu().numpy().view(SYNC_RESULT_DTYPE).reshape(-1)
