@@ -244,6 +244,28 @@ int ria_zc_detect_batch_dev(ria_ctx* ctx, const ria_zc_config* cfg,
                             const float* known_cfo_dev, float threshold, uint32_t root_mask,
                             int64_t n_frames, ria_sync_result* out_dev);
 
+/* sync::ChirpConfig (src/sync/chirp_sync.hpp:30-39); dual chirp always on */
+typedef struct {
+    float sample_rate;   /* 48000 */
+    float f_start;       /* 300   */
+    float f_end;         /* 2700  */
+    float duration_ms;   /* 500   */
+    float gap_ms;        /* 100   */
+} ria_chirp_config;
+
+int ria_chirp_config_default(ria_chirp_config* cfg);
+
+/* Batched replacement for sync::ChirpSync::detectDualChirp(samples, threshold)
+ * (src/sync/chirp_sync.hpp:352-512) -- what IWaveform::detectSync runs for both waveforms.
+ * Result fields: detected = success, start_sample = up_chirp_start (CFO-corrected),
+ * aux = down_chirp_start (CFO-corrected), correlation = up_correlation,
+ * snr_estimate = down_correlation, cfo_hz, root / frame_type = raw up / down peak positions.
+ * window <= 131072 samples, at most 65535 windows per call.  Windows whose down-chirp search
+ * slice is shorter than two chirps (the reference's time-domain fallback) report aux = -2. */
+int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_config* cfg,
+                                    const float* samples_dev, int64_t frame_stride, int32_t window,
+                                    float threshold, int64_t n_frames, ria_sync_result* out_dev);
+
 /* ---- MC-DPSK receive path -------------------------------------------------------------------- */
 /* POD mirror of the RX-relevant fields of ultra::MultiCarrierDPSKConfig
  * (src/psk/multi_carrier_dpsk.hpp:27-100).  Reference defaults: 48000, 8 carriers (the tools use

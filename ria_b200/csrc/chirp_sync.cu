@@ -1,0 +1,404 @@
+// Batched dual-chirp (up/down LFM) preamble detection with CFO estimation for sm_100a.
+//
+// Replaces sync::ChirpSync::detectDualChirp / detectChirpTemplateFFT (src/sync/chirp_sync.hpp:
+// 352-512, 627-712) as called by OFDMChirpWaveform::detectSync / MCDPSKWaveform::detectSync
+// (src/waveform/ofdm_chirp_waveform.cpp:163-205, mc_dpsk_waveform.cpp:177-224): matched filter
+// against the complex (cos + j sin) up- and down-chirp templates through a 131072-point FFT,
+// normalisation by the sliding signal energy from an fp32 prefix sum, first strict maximum, down
+// chirp searched in a window that starts half a chirp after the up-chirp peak, CFO from the
+// error of the gap between the two peaks, CFO-corrected positions.
+//
+// B200 mapping: the 2^17-point transform is three shared-memory stages 32 x 64 x 64 (four-step
+// decomposition, in place, digit-permuted spectrum); because forward and inverse use mirrored
+// stage orders no transpose or bit-reversal pass ever touches HBM, and the template spectra are
+// stored in the same permuted order.  One forward transform of the window serves both templates
+// (the reference transforms the down-chirp search slice separately; the correlation at a given
+// lag is the same sum, only fp32 rounding differs at the 1e-6 level, far below the peak margins).
+// The sliding energy uses the reference's sequential fp32 prefix sums, restarted at the start of
+// the down-chirp search slice exactly like the reference.
+//
+// Not built: the time-domain fallback of detectChirpTemplate (:745-817), which the reference
+// only takes when the down-chirp search slice is shorter than two chirps (window truncated right
+// after the up chirp).  Such windows report detected = 0 with aux = -2.
+
+#include "ria_internal.h"
+
+#include <cmath>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace ria {
+
+struct ChirpTablesDev {
+    ria_chirp_config cfg{};
+    float2* tw1 = nullptr;        // [A][B*C]  W_N^{ka * m}
+    float2* tw2 = nullptr;        // [B][C]    W_{BC}^{kb * c}
+    float2* tmpl_up = nullptr;    // conj(FFT(up template)), permuted layout
+    float2* tmpl_dn = nullptr;
+    float energy_up = 0.f, energy_dn = 0.f;
+    int chirp_len = 0, gap = 0;
+};
+
+namespace {
+
+constexpr int kA = 32, kB = 64, kC = 64;
+constexpr int kN = kA * kB * kC;          // 131072 = ChirpSync::FFT_SIZE (:565)
+constexpr int kT = 16;                    // transforms per tile
+constexpr int kFftThreads = 128;
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// One stage of the three-stage transform: T small DFTs of length L in shared memory
+// (radix-2 DIT), followed by a pointwise twiddle (or the final 1/N scale).
+//   mode 1: over a (L = 32), element stride B*C      forward: then * tw1     inverse: then * scale
+//   mode 2: over b (L = 64), element stride C        forward: then * tw2     inverse: then * conj(tw1)
+//   mode 3: over c (L = 64), contiguous              forward: nothing        inverse: then * conj(tw2)
+template <int L, int MODE>
+__global__ void __launch_bounds__(kFftThreads)
+fft_stage_kernel(float2* __restrict__ data, int inverse, const float2* __restrict__ tw1,
+                 const float2* __restrict__ tw2, float scale) {
+    __shared__ float2 buf[L][kT + 1];
+    __shared__ float2 wl[L / 2];
+    const int tid = threadIdx.x;
+    float2* x = data + static_cast<size_t>(blockIdx.y) * kN;
+    const int q = blockIdx.x;
+    if (tid < L / 2) {
+        double s, c;
+        sincospi(-2.0 * tid / L, &s, &c);
+        wl[tid] = make_float2(static_cast<float>(c), static_cast<float>(inverse ? -s : s));
+    }
+    constexpr int LOGL = (L == 64) ? 6 : 5;
+    // ---- load (bit-reversed rows) ----
+    for (int e = tid; e < L * kT; e += kFftThreads) {
+        int i, t; size_t idx;
+        if (MODE == 3) { i = e % L; t = e / L; idx = static_cast<size_t>(q * kT + t) * kC + i; }
+        else {
+            t = e % kT; i = e / kT;
+            if (MODE == 1) idx = static_cast<size_t>(i) * (kB * kC) + q * kT + t;
+            else { const int ka = q / (kC / kT), c0 = (q % (kC / kT)) * kT; idx = static_cast<size_t>(ka) * (kB * kC) + i * kC + c0 + t; }
+        }
+        const int ir = __brev(static_cast<unsigned>(i)) >> (32 - LOGL);
+        buf[ir][t] = x[idx];
+    }
+    __syncthreads();
+    // ---- radix-2 DIT stages ----
+    for (int len = 2; len <= L; len <<= 1) {
+        const int half = len >> 1, step = L / len;
+        for (int e = tid; e < (L / 2) * kT; e += kFftThreads) {
+            const int t = e % kT, bf = e / kT;
+            const int blk = bf / half, k = bf % half;
+            const int i0 = blk * len + k, i1 = i0 + half;
+            const float2 w = wl[k * step];
+            const float2 a = buf[i0][t], b = cmulf(w, buf[i1][t]);
+            buf[i0][t] = make_float2(a.x + b.x, a.y + b.y);
+            buf[i1][t] = make_float2(a.x - b.x, a.y - b.y);
+        }
+        __syncthreads();
+    }
+    // ---- pointwise factor + store ----
+    for (int e = tid; e < L * kT; e += kFftThreads) {
+        int i, t; size_t idx; float2 f = make_float2(1.0f, 0.0f); bool has_f = false;
+        if (MODE == 3) {
+            i = e % L; t = e / L;
+            const int row = q * kT + t;                       // row = ka*B + kb
+            idx = static_cast<size_t>(row) * kC + i;
+            if (inverse) { f = tw2[(row % kB) * kC + i]; f.y = -f.y; has_f = true; }
+        } else {
+            t = e % kT; i = e / kT;
+            if (MODE == 1) {
+                const int m = q * kT + t;
+                idx = static_cast<size_t>(i) * (kB * kC) + m;
+                if (!inverse) { f = tw1[static_cast<size_t>(i) * (kB * kC) + m]; has_f = true; }
+            } else {
+                const int ka = q / (kC / kT), c = (q % (kC / kT)) * kT + t;
+                idx = static_cast<size_t>(ka) * (kB * kC) + i * kC + c;
+                if (!inverse) { f = tw2[i * kC + c]; has_f = true; }
+                else { f = tw1[static_cast<size_t>(ka) * (kB * kC) + i * kC + c]; f.y = -f.y; has_f = true; }
+            }
+        }
+        float2 v = buf[i][t];
+        if (has_f) v = cmulf(v, f);
+        if (MODE == 1 && inverse) { v.x *= scale; v.y *= scale; }
+        x[idx] = v;
+    }
+}
+
+void fft_forward(float2* d, int batch, const ChirpTablesDev& t, cudaStream_t s) {
+    fft_stage_kernel<kA, 1><<<dim3(kB * kC / kT, batch), kFftThreads, 0, s>>>(d, 0, t.tw1, t.tw2, 1.0f);
+    fft_stage_kernel<kB, 2><<<dim3(kA * kC / kT, batch), kFftThreads, 0, s>>>(d, 0, t.tw1, t.tw2, 1.0f);
+    fft_stage_kernel<kC, 3><<<dim3(kA * kB / kT, batch), kFftThreads, 0, s>>>(d, 0, t.tw1, t.tw2, 1.0f);
+}
+void fft_inverse(float2* d, int batch, const ChirpTablesDev& t, cudaStream_t s) {
+    fft_stage_kernel<kC, 3><<<dim3(kA * kB / kT, batch), kFftThreads, 0, s>>>(d, 1, t.tw1, t.tw2, 1.0f);
+    fft_stage_kernel<kB, 2><<<dim3(kA * kC / kT, batch), kFftThreads, 0, s>>>(d, 1, t.tw1, t.tw2, 1.0f);
+    fft_stage_kernel<kA, 1><<<dim3(kB * kC / kT, batch), kFftThreads, 0, s>>>(d, 1, t.tw1, t.tw2, 1.0f / kN);
+}
+
+__global__ void chirp_twiddle_kernel(float2* tw1, float2* tw2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kN) {
+        const int ka = i / (kB * kC), m = i % (kB * kC);
+        double s, c;
+        sincospi(-2.0 * (static_cast<double>(ka) * m) / kN, &s, &c);
+        tw1[i] = make_float2(static_cast<float>(c), static_cast<float>(s));
+    }
+    if (i < kB * kC) {
+        const int kb = i / kC, cc = i % kC;
+        double s, c;
+        sincospi(-2.0 * (static_cast<double>(kb) * cc) / (kB * kC), &s, &c);
+        tw2[i] = make_float2(static_cast<float>(c), static_cast<float>(s));
+    }
+}
+
+__global__ void conj_kernel(float2* d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kN) d[i].y = -d[i].y;
+}
+
+// signal -> zero-padded complex (:647-650)
+__global__ void chirp_pack_kernel(const float* __restrict__ samples, long long frame_stride, int n_in,
+                                  float2* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kN) return;
+    const long long f = blockIdx.y;
+    out[static_cast<size_t>(f) * kN + i] = make_float2(i < n_in ? samples[f * frame_stride + i] : 0.0f, 0.0f);
+}
+
+// product with both template spectra (:656-659)
+__global__ void chirp_product_kernel(const float2* __restrict__ sig, const float2* __restrict__ tu,
+                                     const float2* __restrict__ td, float2* __restrict__ pu, float2* __restrict__ pd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kN) return;
+    const size_t o = static_cast<size_t>(blockIdx.y) * kN + i;
+    const float2 s = sig[o];
+    pu[o] = cmulf(s, tu[i]);
+    pd[o] = cmulf(s, td[i]);
+}
+
+__device__ __forceinline__ float cabs_d(float2 a) {
+    const double x = a.x, y = a.y;
+    return static_cast<float>(sqrt(x * x + y * y));
+}
+__device__ __forceinline__ void better(float& bv, int& bi, float v, int i) {
+    if (v > bv || (v == bv && v > 0.0f && (bi < 0 || i < bi))) { bv = v; bi = i; }
+}
+
+struct PeakArgs {
+    const float* samples; long long frame_stride; int window;
+    const float2* corr_up; const float2* corr_dn;
+    float* cumsum;                 // [n][window + 1] scratch
+    float threshold, energy_up, energy_dn;
+    int chirp_len, gap;
+    float sample_rate, f_start, f_end, duration_ms;
+    ria_sync_result* out;
+};
+
+// sequential fp32 prefix sum of s^2 over [start, start+len) (:666-669), by one thread
+__device__ void prefix_energy(const float* s, int start, int len, float* c) {
+    float acc = 0.0f;
+    c[0] = 0.0f;
+    for (int i = 0; i < len; ++i) { const float v = s[start + i]; acc = __fadd_rn(acc, __fmul_rn(v, v)); c[i + 1] = acc; }
+}
+
+// normalised peak over pos < search_len (:677-689); corr index offset `off`
+__device__ void peak_search(const float2* corr, int off, const float* c, int search_len, int chirp_len,
+                            float tmpl_energy, float* red_v, int* red_i, float* best, int* pos) {
+    const int tid = threadIdx.x;
+    float bv = 0.0f; int bi = -1;
+    for (int p = tid; p < search_len; p += blockDim.x) {
+        const float mag = cabs_d(corr[off + p]);
+        const float e = __fsub_rn(c[p + chirp_len], c[p]);
+        const float denom = sqrtf(__fmul_rn(e, tmpl_energy));
+        const float nc = (denom > 1e-10f) ? __fdiv_rn(mag, denom) : 0.0f;
+        better(bv, bi, nc, p);
+    }
+    red_v[tid] = bv; red_i[tid] = bi;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (tid < s) { float v = red_v[tid]; int i = red_i[tid]; better(v, i, red_v[tid + s], red_i[tid + s]); red_v[tid] = v; red_i[tid] = i; }
+        __syncthreads();
+    }
+    *best = red_v[0]; *pos = red_i[0];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+chirp_peak_kernel(const PeakArgs a) {
+    __shared__ float red_v[256];
+    __shared__ int red_i[256];
+    const long long f = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float* s = a.samples + f * a.frame_stride;
+    float* c = a.cumsum + f * (static_cast<long long>(a.window) + 1);
+    const float2* cu = a.corr_up + static_cast<size_t>(f) * kN;
+    const float2* cd = a.corr_dn + static_cast<size_t>(f) * kN;
+    const int CL = a.chirp_len;
+    const int n_in = min(a.window, kN);
+
+    ria_sync_result res;
+    res.detected = 0; res.start_sample = -1; res.correlation = 0.0f; res.cfo_hz = 0.0f;
+    res.snr_estimate = 0.0f; res.root = -1; res.frame_type = -1; res.aux = -1;
+
+    if (a.window >= 2 * CL + a.gap) {                       // :373-377
+        // ---- up chirp over the whole window ----
+        if (tid == 0) prefix_energy(s, 0, n_in, c);
+        __syncthreads();
+        float up_corr; int up_pos;
+        peak_search(cu, 0, c, n_in - CL, CL, a.energy_up, red_v, red_i, &up_corr, &up_pos);
+        res.correlation = up_corr;
+        if (up_pos >= 0 && !(up_corr < a.threshold)) {      // :708-712
+            res.root = up_pos;
+            // ---- down chirp search slice (:429-446) ----
+            const long long ds = static_cast<long long>(up_pos) + CL / 2;
+            const long long expected = static_cast<long long>(up_pos) + CL + a.gap;
+            long long de = max(expected + 10000 + CL, ds + 2LL * CL + 1000);
+            if (de > a.window) de = a.window;
+            if (ds < a.window) {
+                if (de <= ds + CL) { de = ds + 2LL * CL; if (de > a.window) de = a.window; }
+                const int dlen = static_cast<int>(de - ds);
+                if (dlen >= 2 * CL) {
+                    if (tid == 0) prefix_energy(s, static_cast<int>(ds), min(dlen, kN), c);
+                    __syncthreads();
+                    float dn_corr; int dn_rel;
+                    peak_search(cd, static_cast<int>(ds), c, min(dlen, kN) - CL, CL, a.energy_dn, red_v, red_i, &dn_corr, &dn_rel);
+                    if (dn_rel >= 0 && !(dn_corr < a.threshold)) {
+                        const int dn_pos = dn_rel + static_cast<int>(ds);
+                        res.snr_estimate = dn_corr;
+                        res.frame_type = dn_pos;
+                        // ---- CFO from the gap error (:462-490) ----
+                        const float T = a.duration_ms / 1000.0f;
+                        const float rate = (a.f_end - a.f_start) / T;
+                        const float c2s = a.sample_rate / rate;
+                        const int expected_gap = CL + a.gap;
+                        const float gap_error = static_cast<float>(dn_pos - up_pos - expected_gap);
+                        const float cfo = gap_error / (2.0f * c2s);
+                        res.cfo_hz = cfo;
+                        if (!(fabsf(cfo) > 100.0f)) {
+                            const float upc = cfo * c2s, dnc = -cfo * c2s;
+                            res.start_sample = static_cast<int>(roundf(up_pos + upc));
+                            res.aux = static_cast<int>(roundf(dn_pos + dnc));
+                            res.detected = 1;
+                        }
+                    }
+                } else if (dlen >= CL) {
+                    res.aux = -2;                            // reference would use the time-domain fallback
+                }
+            }
+        }
+    }
+    if (tid == 0) a.out[f] = res;
+}
+
+}  // namespace
+
+void chirp_tables_free(ChirpTablesDev* t) {
+    if (!t) return;
+    if (t->tw1) cudaFree(t->tw1);
+    if (t->tw2) cudaFree(t->tw2);
+    if (t->tmpl_up) cudaFree(t->tmpl_up);
+    if (t->tmpl_dn) cudaFree(t->tmpl_dn);
+    delete t;
+}
+
+static int chirp_tables_dev(ria_ctx* ctx, const ria_chirp_config& cfg, ChirpTablesDev** out) {
+    for (ChirpTablesDev* t : ctx->chirp_tables)
+        if (std::memcmp(&t->cfg, &cfg, sizeof cfg) == 0) { *out = t; return RIA_OK; }
+    // ChirpSync::generateTemplate (:874-900): sin/cos templates and their energies, host floats
+    const size_t chirp_len = static_cast<size_t>(cfg.sample_rate * cfg.duration_ms / 1000.0f);
+    if (chirp_len == 0 || 2 * chirp_len > kN) return set_error(ctx, RIA_E_UNSUPPORTED, "chirp: unsupported chirp length");
+    std::vector<float2> up(kN, make_float2(0.f, 0.f)), dn(kN, make_float2(0.f, 0.f));
+    float e_up = 0.f, e_dn = 0.f;
+    const float T = cfg.duration_ms / 1000.0f;
+    const float k = (cfg.f_end - cfg.f_start) / T;
+    for (size_t i = 0; i < chirp_len; ++i) {
+        const float t = static_cast<float>(i) / cfg.sample_rate;
+        const float pu = 2.0f * M_PI * (cfg.f_start * t + 0.5f * k * t * t);
+        const float pd = 2.0f * M_PI * (cfg.f_end * t - 0.5f * k * t * t);
+        up[i] = make_float2(std::cos(pu), std::sin(pu));
+        dn[i] = make_float2(std::cos(pd), std::sin(pd));
+        e_up += up[i].y * up[i].y;
+        e_dn += dn[i].y * dn[i].y;
+    }
+    ChirpTablesDev* t = new ChirpTablesDev();
+    t->cfg = cfg; t->chirp_len = static_cast<int>(chirp_len);
+    t->gap = static_cast<int>(static_cast<size_t>(cfg.sample_rate * cfg.gap_ms / 1000.0f));
+    t->energy_up = e_up; t->energy_dn = e_dn;
+    ctx->chirp_tables.push_back(t);
+    RIA_CUDA(ctx, cudaMalloc(&t->tw1, sizeof(float2) * kN));
+    RIA_CUDA(ctx, cudaMalloc(&t->tw2, sizeof(float2) * kB * kC));
+    RIA_CUDA(ctx, cudaMalloc(&t->tmpl_up, sizeof(float2) * kN));
+    RIA_CUDA(ctx, cudaMalloc(&t->tmpl_dn, sizeof(float2) * kN));
+    cudaStream_t s = ctx->stream;
+    chirp_twiddle_kernel<<<(kN + 255) / 256, 256, 0, s>>>(t->tw1, t->tw2);
+    RIA_CUDA(ctx, cudaMemcpyAsync(t->tmpl_up, up.data(), sizeof(float2) * kN, cudaMemcpyHostToDevice, s));
+    RIA_CUDA(ctx, cudaMemcpyAsync(t->tmpl_dn, dn.data(), sizeof(float2) * kN, cudaMemcpyHostToDevice, s));
+    RIA_CUDA(ctx, cudaStreamSynchronize(s));
+    // template spectra, conjugated (:586-611), kept in the permuted layout of the stage transform
+    fft_forward(t->tmpl_up, 1, *t, s);
+    fft_forward(t->tmpl_dn, 1, *t, s);
+    conj_kernel<<<(kN + 255) / 256, 256, 0, s>>>(t->tmpl_up);
+    conj_kernel<<<(kN + 255) / 256, 256, 0, s>>>(t->tmpl_dn);
+    RIA_CUDA(ctx, cudaGetLastError());
+    RIA_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->launches += 9;
+    *out = t;
+    return RIA_OK;
+}
+
+}  // namespace ria
+
+extern "C" int ria_chirp_config_default(ria_chirp_config* cfg) {
+    if (!cfg) return RIA_E_INVAL;
+    *cfg = ria_chirp_config{48000.0f, 300.0f, 2700.0f, 500.0f, 100.0f};     // ChirpConfig defaults (:30-39)
+    return RIA_OK;
+}
+
+extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_config* cfg,
+                                               const float* samples_dev, int64_t frame_stride, int32_t window,
+                                               float threshold, int64_t n_frames, ria_sync_result* out_dev) {
+    using namespace ria;
+    if (!ctx || !cfg) return RIA_E_INVAL;
+    if (n_frames < 0 || window < 0 || frame_stride < window) return set_error(ctx, RIA_E_INVAL, "chirp: bad sizes");
+    if (n_frames == 0) return RIA_OK;
+    if (!samples_dev || !out_dev) return set_error(ctx, RIA_E_INVAL, "chirp: null buffer");
+    if (n_frames > 65535) return set_error(ctx, RIA_E_INVAL, "chirp: at most 65535 windows per call");
+    if (window > 131072) return set_error(ctx, RIA_E_UNSUPPORTED, "chirp: window must be <= 131072 samples");
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    ChirpTablesDev* t = nullptr;
+    int rc = chirp_tables_dev(ctx, *cfg, &t);
+    if (rc != RIA_OK) return rc;
+    const int batch = static_cast<int>(n_frames);
+    const size_t s_c = static_cast<size_t>(batch) * kN * sizeof(float2);
+    const size_t s_cum = ((static_cast<size_t>(batch) * (static_cast<size_t>(window) + 1) * sizeof(float)) + 255) & ~size_t(255);
+    rc = ensure_scratch(ctx, 3 * s_c + s_cum + 256);
+    if (rc != RIA_OK) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->scratch);
+    float2* d_sig = reinterpret_cast<float2*>(base);
+    float2* d_pu = reinterpret_cast<float2*>(base + s_c);
+    float2* d_pd = reinterpret_cast<float2*>(base + 2 * s_c);
+    float* d_cum = reinterpret_cast<float*>(base + 3 * s_c);
+    cudaStream_t s = ctx->stream;
+    const int n_in = window < kN ? window : kN;
+    time_begin(ctx, KK_CHIRP_SYNC);
+    chirp_pack_kernel<<<dim3(kN / 256, batch), 256, 0, s>>>(samples_dev, frame_stride, n_in, d_sig);
+    fft_forward(d_sig, batch, *t, s);
+    chirp_product_kernel<<<dim3(kN / 256, batch), 256, 0, s>>>(d_sig, t->tmpl_up, t->tmpl_dn, d_pu, d_pd);
+    fft_inverse(d_pu, batch, *t, s);
+    fft_inverse(d_pd, batch, *t, s);
+    PeakArgs a{};
+    a.samples = samples_dev; a.frame_stride = frame_stride; a.window = window;
+    a.corr_up = d_pu; a.corr_dn = d_pd; a.cumsum = d_cum;
+    a.threshold = threshold; a.energy_up = t->energy_up; a.energy_dn = t->energy_dn;
+    a.chirp_len = t->chirp_len; a.gap = t->gap;
+    a.sample_rate = cfg->sample_rate; a.f_start = cfg->f_start; a.f_end = cfg->f_end; a.duration_ms = cfg->duration_ms;
+    a.out = out_dev;
+    chirp_peak_kernel<<<batch, 256, 0, s>>>(a);
+    time_end(ctx);
+    RIA_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 12;
+    return RIA_OK;
+}

@@ -87,6 +87,7 @@ int ofdm_tables_dev(ria_ctx* ctx, const ria_modem_config& cfg, int need_nco, con
 void ofdm_tables_free(OfdmTablesDev* t);
 void mcdpsk_tables_free(McdpskTablesDev* t);
 void zc_tables_free(ZcTablesDev* t);
+void chirp_tables_free(ChirpTablesDev* t);
 int ensure_scratch(ria_ctx* ctx, size_t bytes);
 
 // kernel kinds for the timing hook / launch accounting

@@ -86,3 +86,51 @@ class ZCSync:
 
 def results(t: torch.Tensor) -> np.ndarray:
     return t.cpu().numpy().view(SYNC_RESULT_DTYPE).reshape(-1)
+
+
+class ChirpConfig(C.Structure):
+    """ria_chirp_config (include/ria_b200.h) = sync::ChirpConfig with dual chirp."""
+    _fields_ = [("sample_rate", C.c_float), ("f_start", C.c_float), ("f_end", C.c_float),
+                ("duration_ms", C.c_float), ("gap_ms", C.c_float)]
+
+    @classmethod
+    def default(cls):
+        c = cls()
+        lib().ria_chirp_config_default(C.addressof(c))
+        return c
+
+    def getChirpSamples(self) -> int:
+        return int(np.float32(self.sample_rate) * np.float32(self.duration_ms) / np.float32(1000.0))
+
+    def getTotalSamples(self) -> int:
+        gap = int(np.float32(self.sample_rate) * np.float32(self.gap_ms) / np.float32(1000.0))
+        return 2 * self.getChirpSamples() + 2 * gap
+
+
+class ChirpSync:
+    def __init__(self, config: Optional[ChirpConfig] = None, ctx: Optional[Context] = None):
+        self.config = config or ChirpConfig.default()
+        self._ctx = ctx
+
+    @property
+    def ctx(self) -> Context:
+        if self._ctx is None:
+            self._ctx = default_context()
+        return self._ctx
+
+    def detect_dual_batch(self, samples: torch.Tensor, threshold: float = 0.15, max_batch: int = 256) -> torch.Tensor:
+        """detectDualChirp for every row of samples (CUDA fp32 [n, window <= 131072]).
+
+        Each window needs 3 MiB of scratch for the 131072-point spectra, so the batch is walked
+        in slices of ``max_batch`` windows."""
+        samples = _check_windows(samples)
+        n, window = samples.shape
+        out = torch.empty((n, SYNC_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=samples.device)
+        ctx = self.ctx
+        ctx.set_stream(torch.cuda.current_stream(samples.device))
+        for off in range(0, n, max_batch):
+            m = min(max_batch, n - off)
+            ctx.check(lib().ria_chirp_detect_dual_batch_dev(
+                ctx.handle, C.addressof(self.config), _ptr(samples[off:]), samples.stride(0), window,
+                float(threshold), m, _ptr(out[off:])))
+        return out
