@@ -50,7 +50,9 @@ typedef struct ria_ctx ria_ctx;
 /* ---- context ------------------------------------------------------------------------------ */
 int  ria_ctx_create(int device, ria_ctx** out);
 int  ria_ctx_destroy(ria_ctx* ctx);
-/* Bind the context to an existing cudaStream_t (e.g. torch's current stream); NULL = own stream. */
+/* Bind the context to an existing cudaStream_t (e.g. torch's current stream).  NULL is the legacy
+ * default stream (what torch uses unless told otherwise).  Until this is called the context issues
+ * its work on a private non-blocking stream. */
 int  ria_ctx_set_stream(ria_ctx* ctx, void* cuda_stream);
 int  ria_ctx_synchronize(ria_ctx* ctx);
 const char* ria_last_error(const ria_ctx* ctx);
@@ -260,8 +262,7 @@ int ria_chirp_config_default(ria_chirp_config* cfg);
  * Result fields: detected = success, start_sample = up_chirp_start (CFO-corrected),
  * aux = down_chirp_start (CFO-corrected), correlation = up_correlation,
  * snr_estimate = down_correlation, cfo_hz, root / frame_type = raw up / down peak positions.
- * window <= 131072 samples, at most 65535 windows per call.  Windows whose down-chirp search
- * slice is shorter than two chirps (the reference's time-domain fallback) report aux = -2. */
+ * window <= 131072 samples, at most 65535 windows per call. */
 int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_config* cfg,
                                     const float* samples_dev, int64_t frame_stride, int32_t window,
                                     float threshold, int64_t n_frames, ria_sync_result* out_dev);

@@ -17,9 +17,9 @@
 // The sliding energy uses the reference's sequential fp32 prefix sums, restarted at the start of
 // the down-chirp search slice exactly like the reference.
 //
-// Not built: the time-domain fallback of detectChirpTemplate (:745-817), which the reference
-// only takes when the down-chirp search slice is shorter than two chirps (window truncated right
-// after the up chirp).  Such windows report detected = 0 with aux = -2.
+// When the down-chirp search slice is shorter than two chirps (window truncated right after the
+// up chirp) the reference falls back to a time-domain coarse/fine/parabolic search
+// (detectChirpTemplate :745-817); td_detect reproduces it with the reference's sequential sums.
 
 #include "ria_internal.h"
 
@@ -37,6 +37,7 @@ struct ChirpTablesDev {
     float2* tw2 = nullptr;        // [B][C]    W_{BC}^{kb * c}
     float2* tmpl_up = nullptr;    // conj(FFT(up template)), permuted layout
     float2* tmpl_dn = nullptr;
+    float2* tmpl_dn_time = nullptr;   // (cos, sin) of the down-chirp template, time domain
     float energy_up = 0.f, energy_dn = 0.f;
     int chirp_len = 0, gap = 0;
 };
@@ -191,6 +192,7 @@ struct PeakArgs {
     const float* samples; long long frame_stride; int window;
     const float2* corr_up; const float2* corr_dn;
     float* cumsum;                 // [n][window + 1] scratch
+    const float2* tmpl_dn_time;
     float threshold, energy_up, energy_dn;
     int chirp_len, gap;
     float sample_rate, f_start, f_end, duration_ms;
@@ -224,6 +226,66 @@ __device__ void peak_search(const float2* corr, int off, const float* c, int sea
     }
     *best = red_v[0]; *pos = red_i[0];
     __syncthreads();
+}
+
+// computeComplexTemplateCorrelation (:823-846): sequential fp32 sums over the whole template
+__device__ float td_corr(const float* s, int offset, const float2* tmpl, int CL, float tmpl_energy) {
+    float ci = 0.0f, cq = 0.0f, en = 0.0f;
+    for (int i = 0; i < CL; ++i) {
+        const float v = s[offset + i];
+        const float2 t = tmpl[i];
+        ci = __fadd_rn(ci, __fmul_rn(v, t.x));
+        cq = __fadd_rn(cq, __fmul_rn(v, t.y));
+        en = __fadd_rn(en, __fmul_rn(v, v));
+    }
+    const float denom = sqrtf(__fmul_rn(en, tmpl_energy));
+    if (denom < 1e-10f) return 0.0f;
+    return __fdiv_rn(sqrtf(__fadd_rn(__fmul_rn(ci, ci), __fmul_rn(cq, cq))), denom);
+}
+
+// time-domain fallback of detectChirpTemplate (:745-817) on the slice s[0 .. len)
+__device__ void td_detect(const float* s, int len, const float2* tmpl, int CL, float tmpl_energy, float threshold,
+                          float* vals /*>= 640 floats of scratch*/, float* out_corr, int* out_pos) {
+    __shared__ float sh_best;
+    __shared__ int sh_pos;
+    const int tid = threadIdx.x;
+    const int search_len = len - CL;
+    const int n_coarse = (search_len + 47) / 48;
+    for (int k = tid; k < n_coarse; k += blockDim.x) vals[k] = td_corr(s, k * 48, tmpl, CL, tmpl_energy);
+    __syncthreads();
+    if (tid == 0) {
+        float best = 0.0f; int pos = -1;
+        for (int k = 0; k < n_coarse; ++k) if (vals[k] > best) { best = vals[k]; pos = k * 48; }
+        sh_best = best; sh_pos = pos;
+    }
+    __syncthreads();
+    float best = sh_best; int pos = sh_pos;
+    if (pos < 0 || best < threshold * 0.3f) { *out_corr = best; *out_pos = -1; return; }
+    const int fs = max(0, pos - 48), fe = min(search_len, pos + 48);
+    __syncthreads();
+    for (int k = tid; k <= fe - fs; k += blockDim.x) vals[k] = td_corr(s, fs + k, tmpl, CL, tmpl_energy);
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 0; k <= fe - fs; ++k) if (vals[k] > best) { best = vals[k]; pos = fs + k; }
+        sh_best = best; sh_pos = pos;
+    }
+    __syncthreads();
+    best = sh_best; pos = sh_pos;
+    __syncthreads();
+    if (pos > 0 && pos < search_len - 1) {
+        if (tid < 2) vals[tid] = td_corr(s, tid == 0 ? pos - 1 : pos + 1, tmpl, CL, tmpl_energy);
+        __syncthreads();
+        const float c0 = vals[0], c1 = best, c2 = vals[1];
+        const float denom = 2.0f * (c0 - 2.0f * c1 + c2);
+        if (fabsf(denom) > 1e-10f) {
+            float delta = (c0 - c2) / denom;
+            delta = fmaxf(-1.0f, fminf(1.0f, delta));
+            pos = static_cast<int>(roundf(pos + delta));
+        }
+        __syncthreads();
+    }
+    *out_corr = best;
+    *out_pos = (best >= threshold) ? pos : -1;
 }
 
 __global__ void __launch_bounds__(256)
@@ -260,12 +322,18 @@ chirp_peak_kernel(const PeakArgs a) {
             if (ds < a.window) {
                 if (de <= ds + CL) { de = ds + 2LL * CL; if (de > a.window) de = a.window; }
                 const int dlen = static_cast<int>(de - ds);
-                if (dlen >= 2 * CL) {
-                    if (tid == 0) prefix_energy(s, static_cast<int>(ds), min(dlen, kN), c);
-                    __syncthreads();
+                if (dlen >= CL) {
                     float dn_corr; int dn_rel;
-                    peak_search(cd, static_cast<int>(ds), c, min(dlen, kN) - CL, CL, a.energy_dn, red_v, red_i, &dn_corr, &dn_rel);
-                    if (dn_rel >= 0 && !(dn_corr < a.threshold)) {
+                    if (dlen >= 2 * CL) {
+                        if (tid == 0) prefix_energy(s, static_cast<int>(ds), min(dlen, kN), c);
+                        __syncthreads();
+                        peak_search(cd, static_cast<int>(ds), c, min(dlen, kN) - CL, CL, a.energy_dn, red_v, red_i, &dn_corr, &dn_rel);
+                        if (dn_corr < a.threshold) dn_rel = -1;
+                    } else {
+                        // slice shorter than two chirps: the reference correlates in the time domain
+                        td_detect(s + ds, dlen, a.tmpl_dn_time, CL, a.energy_dn, a.threshold, c, &dn_corr, &dn_rel);
+                    }
+                    if (dn_rel >= 0) {
                         const int dn_pos = dn_rel + static_cast<int>(ds);
                         res.snr_estimate = dn_corr;
                         res.frame_type = dn_pos;
@@ -284,8 +352,6 @@ chirp_peak_kernel(const PeakArgs a) {
                             res.detected = 1;
                         }
                     }
-                } else if (dlen >= CL) {
-                    res.aux = -2;                            // reference would use the time-domain fallback
                 }
             }
         }
@@ -301,6 +367,7 @@ void chirp_tables_free(ChirpTablesDev* t) {
     if (t->tw2) cudaFree(t->tw2);
     if (t->tmpl_up) cudaFree(t->tmpl_up);
     if (t->tmpl_dn) cudaFree(t->tmpl_dn);
+    if (t->tmpl_dn_time) cudaFree(t->tmpl_dn_time);
     delete t;
 }
 
@@ -332,10 +399,12 @@ static int chirp_tables_dev(ria_ctx* ctx, const ria_chirp_config& cfg, ChirpTabl
     RIA_CUDA(ctx, cudaMalloc(&t->tw2, sizeof(float2) * kB * kC));
     RIA_CUDA(ctx, cudaMalloc(&t->tmpl_up, sizeof(float2) * kN));
     RIA_CUDA(ctx, cudaMalloc(&t->tmpl_dn, sizeof(float2) * kN));
+    RIA_CUDA(ctx, cudaMalloc(&t->tmpl_dn_time, sizeof(float2) * chirp_len));
     cudaStream_t s = ctx->stream;
     chirp_twiddle_kernel<<<(kN + 255) / 256, 256, 0, s>>>(t->tw1, t->tw2);
     RIA_CUDA(ctx, cudaMemcpyAsync(t->tmpl_up, up.data(), sizeof(float2) * kN, cudaMemcpyHostToDevice, s));
     RIA_CUDA(ctx, cudaMemcpyAsync(t->tmpl_dn, dn.data(), sizeof(float2) * kN, cudaMemcpyHostToDevice, s));
+    RIA_CUDA(ctx, cudaMemcpyAsync(t->tmpl_dn_time, dn.data(), sizeof(float2) * chirp_len, cudaMemcpyHostToDevice, s));
     RIA_CUDA(ctx, cudaStreamSynchronize(s));
     // template spectra, conjugated (:586-611), kept in the permuted layout of the stage transform
     fft_forward(t->tmpl_up, 1, *t, s);
@@ -391,7 +460,7 @@ extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_con
     fft_inverse(d_pd, batch, *t, s);
     PeakArgs a{};
     a.samples = samples_dev; a.frame_stride = frame_stride; a.window = window;
-    a.corr_up = d_pu; a.corr_dn = d_pd; a.cumsum = d_cum;
+    a.corr_up = d_pu; a.corr_dn = d_pd; a.cumsum = d_cum; a.tmpl_dn_time = t->tmpl_dn_time;
     a.threshold = threshold; a.energy_up = t->energy_up; a.energy_dn = t->energy_dn;
     a.chirp_len = t->chirp_len; a.gap = t->gap;
     a.sample_rate = cfg->sample_rate; a.f_start = cfg->f_start; a.f_end = cfg->f_end; a.duration_ms = cfg->duration_ms;

@@ -131,7 +131,7 @@ extern "C" int ria_ctx_destroy(ria_ctx* ctx) {
 
 extern "C" int ria_ctx_set_stream(ria_ctx* ctx, void* cuda_stream) {
     if (!ctx) return RIA_E_INVAL;
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);     // NULL = the legacy default stream, like torch's default
     return RIA_OK;
 }
 
