@@ -301,6 +301,36 @@ int ria_mcdpsk_process_batch_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg,
                                  float* llr_dev, int32_t llr_stride, int32_t* n_llr_dev,
                                  float* fading_dev, float* cfo_out_dev);
 
+/* ---- HARQ chase combining ---------------------------------------------------------------------- */
+/* Arithmetic of fec::ChaseCache::store (src/fec/chase_cache.cpp:27-88) on cache slots resident in
+ * HBM: item i with slot_dev[i] >= 0 either overwrites (first_dev[i] != 0: first reception) or
+ * accumulates (`existing[j] += soft[j]`, :81) its 648 LLRs into acc_dev[slot][648].  A slot may
+ * appear at most once per call, so the accumulation order is the reception order.  The cache
+ * policy (keys, <= 4 combines, LRU, TTL) is host logic (ria_b200.fec.ChaseCache). */
+int ria_chase_combine_batch_dev(ria_ctx* ctx, float* acc_dev, const int32_t* slot_dev,
+                                const uint8_t* first_dev, const float* llr_dev, int64_t llr_stride,
+                                int64_t n);
+
+/* ---- waveform / rate selection (host logic) ---------------------------------------------------- */
+#define RIA_WAVEFORM_OFDM_COX   0   /* protocol::WaveformMode, src/protocol/frame_v2.hpp */
+#define RIA_WAVEFORM_OTFS_EQ    1
+#define RIA_WAVEFORM_OTFS_RAW   2
+#define RIA_WAVEFORM_MFSK       3
+#define RIA_WAVEFORM_MC_DPSK    4
+#define RIA_WAVEFORM_OFDM_CHIRP 5
+typedef struct {
+    int32_t waveform;                 /* RIA_WAVEFORM_*                      */
+    int32_t modulation;               /* ria_modulation                      */
+    int32_t rate;                     /* ria_code_rate                       */
+    float   estimated_throughput_bps;
+    int32_t num_carriers;
+    int32_t spreading;                /* 1, 2 or 4                           */
+} ria_waveform_recommendation;
+/* protocol::recommendWaveformAndRate (src/protocol/waveform_selection.hpp:112-222) */
+int ria_recommend_waveform(float snr_db, float fading_index, ria_waveform_recommendation* rec);
+/* protocol::recommendDataMode (waveform_selection.hpp:250-314); estimated_throughput_bps unset */
+int ria_recommend_data_mode(float snr_db, int waveform, float fading_index, ria_waveform_recommendation* rec);
+
 /* ---- channel simulation on the device ------------------------------------------------------ */
 /* AWGN as SimulatedChannel::applyChannel (tools/cli_simulator.cpp:343-366): frame f of the batch is
  * tx_pool[(first_frame_id + f) % pool_frames] plus white Gaussian noise whose standard deviation
@@ -312,6 +342,31 @@ int ria_channel_awgn_batch_dev(ria_ctx* ctx, const float* tx_pool_dev, int32_t p
                                int32_t frame_len, const float* snr_db_dev, float snr_db,
                                uint64_t seed, int64_t first_frame_id, int64_t n_frames,
                                float* out_dev, int64_t out_stride);
+
+/* sim::WattersonChannel::Config (src/sim/hf_channel.hpp:33-47), fields that shape the output */
+typedef struct {
+    float    snr_db;
+    float    delay_spread_ms;
+    float    doppler_spread_hz;
+    float    path1_gain, path2_gain;     /* 0.707 each */
+    uint32_t sample_rate;
+    uint32_t fading_enabled, multipath_enabled, noise_enabled;
+    uint32_t stationary_start;           /* 1: draw the initial tap state from the stationary
+                                            distribution (frames are independent draws of a
+                                            long-running channel); 0: start at (1,0) like a freshly
+                                            constructed WattersonChannel (:68-69)                 */
+} ria_watterson_config;
+/* itu_r_f1487 presets (hf_channel.hpp:411-488): 0 AWGN, 1 Good, 2 Moderate, 3 Poor, 4 Flutter */
+int ria_watterson_preset(int condition, float snr_db, ria_watterson_config* cfg);
+/* WattersonChannel::process for a batch (hf_channel.hpp:107-177, 267-284): frame f of the batch is
+ * tx_pool[(first_frame_id + f) % pool_frames] through two Rayleigh taps (first-order IIR-shaped
+ * complex Gaussians), a delay of delay_spread_ms on the second path and AWGN scaled to the rms of
+ * the non-silent input samples.  The CFO stage of the class (applyCFO) is not part of this call.
+ * Philox-keyed like ria_channel_awgn_batch_dev; parity with the reference is statistical. */
+int ria_channel_watterson_batch_dev(ria_ctx* ctx, const ria_watterson_config* cfg,
+                                    const float* tx_pool_dev, int32_t pool_frames, int32_t frame_len,
+                                    const float* snr_db_dev, uint64_t seed, int64_t first_frame_id,
+                                    int64_t n_frames, float* out_dev, int64_t out_stride);
 
 /* CRC-16/CCITT-FALSE as ControlFrame::calculateCRC (src/protocol/frame_v2.cpp:115-128); host. */
 uint16_t ria_crc16(const uint8_t* data, size_t len);

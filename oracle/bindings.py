@@ -96,6 +96,19 @@ class SyncResult(C.Structure):
                 ("frame_type", C.c_int32), ("aux", C.c_int32)]
 
 
+class WattersonConfig(C.Structure):
+    """Same layout as ria_watterson_config."""
+    _fields_ = [("snr_db", C.c_float), ("delay_spread_ms", C.c_float), ("doppler_spread_hz", C.c_float),
+                ("path1_gain", C.c_float), ("path2_gain", C.c_float), ("sample_rate", C.c_uint32),
+                ("fading_enabled", C.c_uint32), ("multipath_enabled", C.c_uint32),
+                ("noise_enabled", C.c_uint32), ("stationary_start", C.c_uint32)]
+
+
+class WaveformRecommendation(C.Structure):
+    _fields_ = [("waveform", C.c_int32), ("modulation", C.c_int32), ("rate", C.c_int32),
+                ("estimated_throughput_bps", C.c_float), ("num_carriers", C.c_int32), ("spreading", C.c_int32)]
+
+
 class FrameStatus(C.Structure):
     """Same layout as ria_frame_status (include/ria_b200.h)."""
     _fields_ = [("cw_ok", C.c_uint8 * 4), ("cw_iters", C.c_int32 * 4), ("all_ok", C.c_uint8),
@@ -206,6 +219,11 @@ class Ref:
         L.ref_make_data_frame.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _u8p, C.c_int, _u8p, C.c_int]
         L.ref_make_data_frame.restype = C.c_int
         self._demods = {}
+        L.ref_watterson_process.argtypes = [C.POINTER(WattersonConfig), C.c_uint, _f32p, C.c_int, _f32p]
+        L.ref_recommend_waveform.argtypes = [C.c_float, C.c_float, C.POINTER(WaveformRecommendation)]
+        L.ref_recommend_data_mode.argtypes = [C.c_float, C.c_int, C.c_float, C.POINTER(WaveformRecommendation)]
+        L.ref_chase_combine.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int)]
+        L.ref_chase_combine.restype = C.c_int
         zcp = C.POINTER(ZcConfig)
         L.ref_zc_preamble.argtypes = [zcp, C.c_int, _f32p, C.c_int]
         L.ref_zc_preamble.restype = C.c_int
@@ -296,6 +314,30 @@ class Ref:
         bins = np.zeros((n_sym, cfg.num_carriers, 2), np.float32)
         self.lib.ref_ofdm_symbol_bins(self._demod(cfg), samples, n_sym, cfo_hz, phase, bins)
         return bins[..., 0] + 1j * bins[..., 1]
+
+    # ---- channel / chase / selection ----
+    def watterson_process(self, cfg: WattersonConfig, seed: int, x) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.zeros_like(x)
+        self.lib.ref_watterson_process(C.byref(cfg), seed, x, len(x), out)
+        return out
+
+    def recommend_waveform(self, snr_db, fading) -> WaveformRecommendation:
+        r = WaveformRecommendation()
+        self.lib.ref_recommend_waveform(snr_db, fading, C.byref(r))
+        return r
+
+    def recommend_data_mode(self, snr_db, waveform, fading) -> WaveformRecommendation:
+        r = WaveformRecommendation()
+        self.lib.ref_recommend_data_mode(snr_db, waveform, fading, C.byref(r))
+        return r
+
+    def chase_combine(self, soft, cw_index=1, total_cw=4):
+        soft = np.ascontiguousarray(soft, dtype=np.float32).reshape(-1, 648)
+        out = np.zeros(648, np.float32)
+        cnt = C.c_int(0)
+        stored = self.lib.ref_chase_combine(soft, soft.shape[0], cw_index, total_cw, out, C.byref(cnt))
+        return out, stored, cnt.value
 
     # ---- sync ----
     def zc_preamble(self, cfg: ZcConfig, frame_type: int) -> np.ndarray:

@@ -22,6 +22,8 @@
 #include "fec/chase_cache.hpp"
 #include "sync/zc_sync.hpp"
 #include "sync/chirp_sync.hpp"
+#include "sim/hf_channel.hpp"
+#include "protocol/waveform_selection.hpp"
 
 #include "ria_b200.h"                     // POD config / status structs shared with the product ABI
 
@@ -396,6 +398,52 @@ void ref_chirp_detect_dual(const float* samples, int n, float threshold, ria_syn
     out->snr_estimate = r.down_correlation;
     out->root = 0; out->frame_type = 0;
     out->aux = r.down_chirp_start;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Channel, chase cache, waveform selection
+// ---------------------------------------------------------------------------------------------
+void ref_watterson_process(const ria_watterson_config* c, unsigned seed, const float* in, int n, float* out) {
+    sim::WattersonChannel::Config cfg;
+    cfg.snr_db = c->snr_db; cfg.delay_spread_ms = c->delay_spread_ms; cfg.doppler_spread_hz = c->doppler_spread_hz;
+    cfg.path1_gain = c->path1_gain; cfg.path2_gain = c->path2_gain; cfg.sample_rate = c->sample_rate;
+    cfg.fading_enabled = c->fading_enabled != 0; cfg.multipath_enabled = c->multipath_enabled != 0;
+    cfg.noise_enabled = c->noise_enabled != 0; cfg.cfo_enabled = false;
+    sim::WattersonChannel ch(cfg, seed);
+    Samples o = ch.process(SampleSpan(in, static_cast<size_t>(n)));
+    std::memcpy(out, o.data(), o.size() * 4);
+}
+
+void ref_recommend_waveform(float snr_db, float fading, ria_waveform_recommendation* out) {
+    auto r = protocol::recommendWaveformAndRate(snr_db, fading);
+    out->waveform = static_cast<int>(r.waveform); out->modulation = static_cast<int>(r.modulation);
+    out->rate = static_cast<int>(r.rate); out->estimated_throughput_bps = r.estimated_throughput_bps;
+    out->num_carriers = r.num_carriers;
+    out->spreading = r.spreading == SpreadingMode::TIME_4X ? 4 : r.spreading == SpreadingMode::TIME_2X ? 2 : 1;
+}
+
+void ref_recommend_data_mode(float snr_db, int waveform, float fading, ria_waveform_recommendation* out) {
+    Modulation mod = Modulation::DQPSK; CodeRate rate = CodeRate::R1_4; int nc = 10; SpreadingMode sp = SpreadingMode::NONE;
+    protocol::recommendDataMode(snr_db, static_cast<protocol::WaveformMode>(waveform), mod, rate, fading, &nc, &sp);
+    out->waveform = waveform; out->modulation = static_cast<int>(mod); out->rate = static_cast<int>(rate);
+    out->estimated_throughput_bps = 0.0f; out->num_carriers = nc;
+    out->spreading = sp == SpreadingMode::TIME_4X ? 4 : sp == SpreadingMode::TIME_2X ? 2 : 1;
+}
+
+// fec::ChaseCache: store the receptions in order, return the combined soft bits of one codeword
+int ref_chase_combine(const float* soft, int n_receptions, int cw_index, int total_cw, float* out, int* count) {
+    fec::ChaseCache cache;
+    fec::ChaseCacheKey key{1, 0x123456, 0x654321};
+    int stored = 0;
+    for (int r = 0; r < n_receptions; ++r) {
+        std::vector<float> v(soft + r * 648, soft + (r + 1) * 648);
+        stored += cache.store(key, cw_index, v, total_cw, protocol::v2::FrameType::DATA) ? 1 : 0;
+    }
+    auto c = cache.getCombined(key, cw_index);
+    *count = cache.getCombineCount(key, cw_index);
+    if (c) std::memcpy(out, c->data(), 648 * 4);
+    return stored;
 }
 
 }  // extern "C"

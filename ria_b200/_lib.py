@@ -58,7 +58,12 @@ _SIGNATURES = {
     "ria_mcdpsk_soft_bits_per_frame": (_i32, [_vp, _i32]),
     "ria_mcdpsk_process_batch_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64,
                                             _vp, _i32, _vp, _vp, _vp]),
+    "ria_chase_combine_batch_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64]),
+    "ria_recommend_waveform": (_i32, [_f32, _f32, _vp]),
+    "ria_recommend_data_mode": (_i32, [_f32, _i32, _f32, _vp]),
     "ria_channel_awgn_batch_dev": (_i32, [_vp, _vp, _i32, _i32, _vp, _f32, C.c_uint64, _i64, _i64, _vp, _i64]),
+    "ria_watterson_preset": (_i32, [_i32, _f32, _vp]),
+    "ria_channel_watterson_batch_dev": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, C.c_uint64, _i64, _i64, _vp, _i64]),
     "ria_crc16": (C.c_uint16, [_vp, C.c_size_t]),
     "ria_channel_interleaver_step": (_i32, [_i32, _i32]),
 }

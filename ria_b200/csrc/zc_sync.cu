@@ -127,7 +127,6 @@ zc_finish_kernel(const FinishArgs a) {
     __shared__ float2 fine_corr[160];
     __shared__ float2 aux_sum[3];
     __shared__ float aux_en[3];
-    __shared__ int s_ctl[4];
     const long long f = blockIdx.x;
     const int tid = threadIdx.x;
     const float2* bb = a.bb + f * a.bb_stride;

@@ -245,3 +245,126 @@ class LDPCCodec:
     @property
     def decoder(self) -> LDPCDecoder:
         return self._decoder
+
+
+class ChaseCache:
+    """fec::ChaseCache (src/fec/chase_cache.{hpp,cpp}) with the soft bits resident in HBM.
+
+    The policy is the reference's host logic: key = (seq, src_hash, dst_hash), at most
+    MAX_COMBINES (4) receptions per codeword, ``max_entries`` entries with LRU eviction, TTL.
+    ``store_batch`` performs one reception round for many (key, cw_index) items with one kernel
+    (ria_chase_combine_batch_dev); a (key, cw) pair may appear once per round."""
+
+    MAX_COMBINES = 4
+    LDPC_BLOCK_SIZE = 648
+
+    def __init__(self, max_entries: int = 16, entry_ttl_s: float = 30.0, max_cw: int = 16,
+                 ctx: Optional[Context] = None, device=None):
+        import time as _time
+        self._time = _time
+        self.max_entries, self.ttl, self.max_cw = int(max_entries), float(entry_ttl_s), int(max_cw)
+        self._ctx = ctx
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.acc = torch.zeros((self.max_entries * self.max_cw, LDPC_N), dtype=torch.float32, device=self.device)
+        self.entries = {}          # key -> dict(slot, total_cw, counts[], decoded[], created, last)
+        self.free = list(range(self.max_entries))
+        self.enabled = True
+        self.stats = dict(stores=0, combines=0, cache_hits=0, cache_misses=0, entries_evicted=0,
+                          entries_expired=0, recoveries=0)
+
+    @property
+    def ctx(self) -> Context:
+        if self._ctx is None:
+            self._ctx = default_context()
+        return self._ctx
+
+    def _prune(self):
+        now = self._time.monotonic()
+        for k in [k for k, e in self.entries.items() if now - e["created"] > self.ttl]:
+            self.free.append(self.entries.pop(k)["slot"])
+            self.stats["entries_expired"] += 1
+
+    def _evict(self):
+        while len(self.entries) >= self.max_entries:
+            k = min(self.entries, key=lambda q: self.entries[q]["last"])
+            self.free.append(self.entries.pop(k)["slot"])
+            self.stats["entries_evicted"] += 1
+
+    def store_batch(self, keys, cw_indices, total_cws, soft: torch.Tensor):
+        """One reception round: item i stores soft[i] (CUDA fp32 [n, >=648]) under keys[i] /
+        cw_indices[i].  Returns a list of bools like ChaseCache::store."""
+        n = len(keys)
+        assert soft.is_cuda and soft.dtype == torch.float32 and soft.shape[0] == n and soft.shape[1] >= LDPC_N
+        slots = np.full(n, -1, np.int32)
+        first = np.zeros(n, np.uint8)
+        ok = [False] * n
+        seen = set()
+        for i, (key, cw, total) in enumerate(zip(keys, cw_indices, total_cws)):
+            if not self.enabled or cw < 0 or cw >= total or total <= 0 or total > self.max_cw or (key, cw) in seen:
+                continue
+            self.stats["stores"] += 1
+            self._prune()
+            e = self.entries.get(key)
+            now = self._time.monotonic()
+            if e is None:
+                self._evict()
+                e = dict(slot=self.free.pop(), total_cw=total, counts=[0] * total, decoded=[False] * total,
+                         created=now, last=now)
+                self.entries[key] = e
+            e["last"] = now
+            if cw >= e["total_cw"] or e["decoded"][cw] or e["counts"][cw] >= self.MAX_COMBINES:
+                continue
+            slots[i] = e["slot"] * self.max_cw + cw
+            first[i] = 1 if e["counts"][cw] == 0 else 0
+            if e["counts"][cw] > 0:
+                self.stats["combines"] += 1
+            e["counts"][cw] += 1
+            seen.add((key, cw))
+            ok[i] = True
+        if n:
+            ctx = self.ctx
+            ctx.set_stream(torch.cuda.current_stream(self.device))
+            d_slots = torch.from_numpy(slots).to(self.device)
+            d_first = torch.from_numpy(first).to(self.device)
+            if soft.stride(1) != 1:
+                soft = soft.contiguous()
+            ctx.check(lib().ria_chase_combine_batch_dev(
+                ctx.handle, self.acc.data_ptr(), d_slots.data_ptr(), d_first.data_ptr(), soft.data_ptr(),
+                soft.stride(0), n))
+        return ok
+
+    def store(self, key, cw_index: int, soft_bits, total_cw: int) -> bool:
+        soft = torch.as_tensor(np.asarray(soft_bits, np.float32)).to(self.device).reshape(1, -1)
+        if soft.shape[1] != LDPC_N:
+            return False
+        return self.store_batch([key], [cw_index], [total_cw], soft)[0]
+
+    def getCombined(self, key, cw_index: int):
+        e = self.entries.get(key)
+        if (not self.enabled or e is None or cw_index < 0 or cw_index >= e["total_cw"]
+                or e["counts"][cw_index] == 0 or e["decoded"][cw_index]):
+            self.stats["cache_misses"] += 1
+            return None
+        self.stats["cache_hits"] += 1
+        return self.acc[e["slot"] * self.max_cw + cw_index]
+
+    def getCombineCount(self, key, cw_index: int) -> int:
+        e = self.entries.get(key)
+        return e["counts"][cw_index] if e is not None and 0 <= cw_index < e["total_cw"] else 0
+
+    def markDecoded(self, key, cw_index: int) -> None:
+        e = self.entries.get(key)
+        if e is None:
+            return
+        if 0 <= cw_index < e["total_cw"]:
+            e["decoded"][cw_index] = True
+        if all(e["decoded"]):
+            self.free.append(self.entries.pop(key)["slot"])
+
+    def size(self) -> int:
+        return len(self.entries)
+
+    def clear(self) -> None:
+        for e in self.entries.values():
+            self.free.append(e["slot"])
+        self.entries.clear()
