@@ -60,7 +60,7 @@ const char* ria_version(void);
 /* Per-kernel timing for bench.py: when enabled, every kernel launch is bracketed by CUDA events on
  * the context stream; get_timing sums the elapsed time of all launches of one kind since enable.
  * kinds: 0 LDPC, 1 OFDM demod, 2 frame status/CRC, 3 AWGN channel, 4 MC-DPSK demod, 5 ZC sync,
- * 6 chirp sync, 7 chase combine, 8 Watterson channel, 9 MC-DPSK CFO correction. */
+ * 6 chirp sync, 7 chase combine, 8 Watterson channel, 9 MC-DPSK CFO correction, 10 OFDM data sync. */
 int  ria_ctx_set_timing(ria_ctx* ctx, int enable);
 int  ria_ctx_get_timing(ria_ctx* ctx, int kind, double* total_ms, int64_t* launches);
 /* number of kernels this library has launched on the context since creation */
@@ -266,6 +266,15 @@ int ria_chirp_config_default(ria_chirp_config* cfg);
 int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_config* cfg,
                                     const float* samples_dev, int64_t frame_stride, int32_t window,
                                     float threshold, int64_t n_frames, ria_sync_result* out_dev);
+
+/* Batched replacement for OFDMChirpWaveform::detectDataSync(samples, result, known_cfo_hz, threshold)
+ * (src/waveform/ofdm_chirp_waveform.cpp:207-384): light (training-only) preamble detection for
+ * connected-mode frames.  Result fields: detected, start_sample = first LTS sample, correlation,
+ * cfo_hz = known CFO, aux = 1 when the burst-interleave marker (negated first LTS) is seen. */
+int ria_ofdm_data_sync_batch_dev(ria_ctx* ctx, const ria_modem_config* cfg,
+                                 const float* samples_dev, int64_t frame_stride, int32_t window,
+                                 const float* known_cfo_dev, float threshold, int64_t n_frames,
+                                 ria_sync_result* out_dev);
 
 /* ---- MC-DPSK receive path -------------------------------------------------------------------- */
 /* POD mirror of the RX-relevant fields of ultra::MultiCarrierDPSKConfig

@@ -224,6 +224,7 @@ class Ref:
         L.ref_recommend_data_mode.argtypes = [C.c_float, C.c_int, C.c_float, C.POINTER(WaveformRecommendation)]
         L.ref_chase_combine.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int)]
         L.ref_chase_combine.restype = C.c_int
+        L.ref_ofdm_data_sync.argtypes = [C.POINTER(ModemConfig), _f32p, C.c_int, C.c_float, C.c_float, C.POINTER(SyncResult)]
         zcp = C.POINTER(ZcConfig)
         L.ref_zc_preamble.argtypes = [zcp, C.c_int, _f32p, C.c_int]
         L.ref_zc_preamble.restype = C.c_int
@@ -340,6 +341,12 @@ class Ref:
         return out, stored, cnt.value
 
     # ---- sync ----
+    def ofdm_data_sync(self, cfg: ModemConfig, samples, known_cfo=0.0, threshold=0.3) -> SyncResult:
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        r = SyncResult()
+        self.lib.ref_ofdm_data_sync(C.byref(cfg), samples, len(samples), known_cfo, threshold, C.byref(r))
+        return r
+
     def zc_preamble(self, cfg: ZcConfig, frame_type: int) -> np.ndarray:
         out = np.zeros(8192, np.float32)
         n = self.lib.ref_zc_preamble(C.byref(cfg), frame_type, out, len(out))

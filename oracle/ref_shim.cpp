@@ -23,6 +23,7 @@
 #include "sync/zc_sync.hpp"
 #include "sync/chirp_sync.hpp"
 #include "sim/hf_channel.hpp"
+#include "waveform/ofdm_chirp_waveform.hpp"
 #include "protocol/waveform_selection.hpp"
 
 #include "ria_b200.h"                     // POD config / status structs shared with the product ABI
@@ -444,6 +445,21 @@ int ref_chase_combine(const float* soft, int n_receptions, int cw_index, int tot
     *count = cache.getCombineCount(key, cw_index);
     if (c) std::memcpy(out, c->data(), 648 * 4);
     return stored;
+}
+
+
+// OFDMChirpWaveform::detectDataSync (src/waveform/ofdm_chirp_waveform.cpp:207-384)
+void ref_ofdm_data_sync(const ria_modem_config* c, const float* samples, int n, float known_cfo, float threshold,
+                        ria_sync_result* out) {
+    OFDMChirpWaveform wf(to_cfg(c));
+    SyncResult r;
+    bool det = wf.detectDataSync(SampleSpan(samples, static_cast<size_t>(n)), r, known_cfo, threshold);
+    out->detected = det ? 1 : 0;
+    out->start_sample = r.start_sample;
+    out->correlation = r.correlation;
+    out->cfo_hz = r.cfo_hz;
+    out->snr_estimate = 0.0f; out->root = 0; out->frame_type = 0;
+    out->aux = wf.wasBurstInterleaved() ? 1 : 0;
 }
 
 }  // extern "C"

@@ -53,6 +53,7 @@ _SIGNATURES = {
                                        _vp, _vp, _vp]),
     "ria_zc_config_default": (_i32, [_vp]),
     "ria_zc_detect_batch_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _f32, C.c_uint32, _i64, _vp]),
+    "ria_ofdm_data_sync_batch_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _f32, _i64, _vp]),
     "ria_chirp_config_default": (_i32, [_vp]),
     "ria_chirp_detect_dual_batch_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _f32, _i64, _vp]),
     "ria_mcdpsk_soft_bits_per_frame": (_i32, [_vp, _i32]),

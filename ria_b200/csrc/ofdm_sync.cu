@@ -1,0 +1,232 @@
+// Batched OFDM light (training-only) preamble detection for connected-mode DATA frames.
+//
+// Replaces OFDMChirpWaveform::detectDataSync (src/waveform/ofdm_chirp_waveform.cpp:207-384):
+// energy gate on the first 100 ms, 65-tap Blackman Hilbert FIR (src/dsp/filters.cpp:266-317),
+// Schmidl-Cox style lag-one-symbol autocorrelation of the analytic signal on a step-8 grid with
+// early exit at the first correlation above 0.95, +-4 sample refinement, burst-interleave marker
+// from the sign of Re(P e^{-j phi_cfo}).
+//
+// The search is sequential in the reference only through its early exit; here every candidate
+// offset is evaluated in parallel (each with the reference's in-order fp32 sums) and the scan
+// semantics (running best, first > 0.95 stops) are applied afterwards by one thread, which gives
+// the identical offset.
+
+#include "ria_internal.h"
+
+#include <cmath>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace ria {
+namespace {
+
+constexpr int kTaps = 65;
+constexpr int kDelay = 32;
+constexpr int kThreads = 256;
+constexpr int kMaxCand = 2048;
+
+__device__ __forceinline__ float cabs_d(float2 a) {
+    const double x = a.x, y = a.y;
+    return static_cast<float>(sqrt(x * x + y * y));
+}
+
+struct SyncArgs {
+    const float* samples; long long frame_stride; int window;
+    const float* known_cfo; float threshold; int sym; float sample_rate;
+    const float* taps_g;
+    float2* analytic; long long an_stride;      // scratch [n][window]
+    float* cand; long long cand_stride;         // scratch [n][4 * kMaxCand]: corr, P.re, P.im
+    ria_sync_result* out;
+};
+
+// P = sum conj(s1) s2, energies, in order (:283-295)
+__device__ __forceinline__ void lag_corr(const float2* an, int offset, int sym, float* corr, float2* P_out) {
+    float2 P = make_float2(0.f, 0.f);
+    float e1 = 0.f, e2 = 0.f;
+    for (int n = 0; n < sym; ++n) {
+        const float2 s1 = an[offset + n], s2 = an[offset + n + sym];
+        // conj(s1) * s2
+        const float re = __fsub_rn(__fmul_rn(s1.x, s2.x), __fmul_rn(-s1.y, s2.y));
+        const float im = __fadd_rn(__fmul_rn(s1.x, s2.y), __fmul_rn(-s1.y, s2.x));
+        P.x = __fadd_rn(P.x, re); P.y = __fadd_rn(P.y, im);
+        e1 = __fadd_rn(e1, __fadd_rn(__fmul_rn(s1.x, s1.x), __fmul_rn(s1.y, s1.y)));
+        e2 = __fadd_rn(e2, __fadd_rn(__fmul_rn(s2.x, s2.x), __fmul_rn(s2.y, s2.y)));
+    }
+    const float denom = __fadd_rn(sqrtf(__fmul_rn(e1, e2)), 1e-10f);
+    *corr = __fdiv_rn(cabs_d(P), denom);
+    *P_out = P;
+}
+
+__global__ void __launch_bounds__(kThreads)
+ofdm_data_sync_kernel(const SyncArgs a) {
+    __shared__ float taps[kTaps + 3];
+    __shared__ int s_i[kThreads];
+    __shared__ float s_f[4];
+    __shared__ int s_n[4];
+    const long long f = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float* x = a.samples + f * a.frame_stride;
+    float2* an = a.analytic + f * a.an_stride;
+    float* cand = a.cand + f * a.cand_stride;
+    const int N = a.window, sym = a.sym;
+    const float known = a.known_cfo ? a.known_cfo[f] : 0.0f;
+
+    ria_sync_result res;
+    res.detected = 0; res.start_sample = -1; res.correlation = 0.0f; res.cfo_hz = known;
+    res.snr_estimate = 0.0f; res.root = 0; res.frame_type = 0; res.aux = 0;
+    if (N < sym * 3) { if (tid == 0) a.out[f] = res; return; }      // :222-224
+
+    if (tid < kTaps) taps[tid] = a.taps_g[tid];
+    // ---- energy gate (:232-260) ----
+    if (tid == 0) {
+        const int ns = min(N / 4, 4800);
+        float nf = 0.0f;
+        for (int i = 0; i < ns; ++i) nf = __fadd_rn(nf, __fmul_rn(x[i], x[i]));
+        nf = sqrtf(nf / ns);
+        s_f[0] = nf;
+        s_f[1] = nf * 3.0f + 0.01f;
+    }
+    __syncthreads();
+    const bool in_noise = s_f[0] < 0.05f;
+    int signal_start = 0;
+    if (in_noise) {
+        const float thr = s_f[1];
+        int first = 0x7fffffff;
+        const int lim = N - sym * 2;
+        for (int i = tid; i < lim && i < first; i += kThreads) {
+            float e = 0.0f;
+            for (int j = 0; j < 64; ++j) if (i + j < N) e = __fadd_rn(e, __fmul_rn(x[i + j], x[i + j]));
+            e = sqrtf(e / 64);
+            if (e > thr) { first = i; break; }
+        }
+        s_i[tid] = first;
+        __syncthreads();
+        for (int s = kThreads / 2; s > 0; s >>= 1) { if (tid < s) s_i[tid] = min(s_i[tid], s_i[tid + s]); __syncthreads(); }
+        signal_start = (s_i[0] == 0x7fffffff) ? 0 : s_i[0];
+        __syncthreads();
+    }
+    const int search_window = sym * 4;
+    const int actual = in_noise ? search_window : max(search_window, sym * 8);
+    const int search_end = min(signal_start + actual, N - sym * 2);
+
+    // ---- analytic signal over the span the search touches (:266-270, filters.cpp:293-317) ----
+    const int an_lo = max(0, signal_start - 4), an_hi = min(N, search_end + 2 * sym + 8);
+    for (int i = an_lo + tid; i < an_hi; i += kThreads) {
+        float q = 0.0f;
+        for (int k = 1; k < kTaps; k += 2) {                       // even taps are exactly zero
+            const int j = i - k;
+            const float v = (j >= 0) ? x[j] : 0.0f;
+            q = __fadd_rn(q, __fmul_rn(taps[k], v));
+        }
+        an[i] = make_float2(i >= kDelay ? x[i - kDelay] : 0.0f, q);
+    }
+    __syncthreads();
+
+    // ---- coarse candidates, all in parallel (:283-312) ----
+    int n_cand = (search_end > signal_start) ? (search_end - signal_start + 7) / 8 : 0;
+    if (n_cand > kMaxCand) n_cand = kMaxCand;
+    for (int c = tid; c < n_cand; c += kThreads) {
+        float corr; float2 P;
+        lag_corr(an, signal_start + 8 * c, sym, &corr, &P);
+        cand[c] = corr; cand[kMaxCand + c] = P.x; cand[2 * kMaxCand + c] = P.y;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float best = 0.0f; int bo = 0; float2 bp = make_float2(0.f, 0.f);
+        for (int c = 0; c < n_cand; ++c) {
+            const float corr = cand[c];
+            if (corr > best) { best = corr; bo = signal_start + 8 * c; bp = make_float2(cand[kMaxCand + c], cand[2 * kMaxCand + c]); }
+            if (corr > 0.95f) break;                                 // first high-confidence peak
+        }
+        s_f[2] = best; s_n[0] = bo; s_f[0] = bp.x; s_f[1] = bp.y;
+    }
+    __syncthreads();
+    float best_corr = s_f[2]; int best_offset = s_n[0]; float2 best_p = make_float2(s_f[0], s_f[1]);
+    __syncthreads();
+    // ---- +-4 refinement (:318-350) ----
+    if (best_corr > a.threshold) {
+        const int r0 = max(signal_start, best_offset - 4), r1 = min(search_end, best_offset + 5);
+        if (tid < r1 - r0 && r0 + tid != best_offset) {
+            float corr; float2 P;
+            lag_corr(an, r0 + tid, sym, &corr, &P);
+            cand[tid] = corr; cand[kMaxCand + tid] = P.x; cand[2 * kMaxCand + tid] = P.y;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int o = r0; o < r1; ++o) {
+                if (o == best_offset) continue;
+                const float corr = cand[o - r0];
+                if (corr > best_corr) { best_corr = corr; best_offset = o; best_p = make_float2(cand[kMaxCand + o - r0], cand[2 * kMaxCand + o - r0]); }
+            }
+        }
+    }
+    if (tid == 0) {
+        res.correlation = best_corr;
+        if (best_corr > a.threshold) {
+            res.detected = 1;
+            res.start_sample = best_offset;
+            // burst-interleave marker (:366-372)
+            const float cfo_phase = static_cast<float>(2.0f * M_PI * static_cast<double>(known) * sym / static_cast<double>(a.sample_rate));
+            double s, c;
+            sincos(static_cast<double>(-cfo_phase), &s, &c);
+            const float re = __fsub_rn(__fmul_rn(best_p.x, static_cast<float>(c)), __fmul_rn(best_p.y, static_cast<float>(s)));
+            res.aux = (re < 0.0f) ? 1 : 0;
+        }
+        a.out[f] = res;
+    }
+}
+
+}  // namespace
+}  // namespace ria
+
+extern "C" int ria_ofdm_data_sync_batch_dev(ria_ctx* ctx, const ria_modem_config* cfg,
+                                            const float* samples_dev, int64_t frame_stride, int32_t window,
+                                            const float* known_cfo_dev, float threshold, int64_t n_frames,
+                                            ria_sync_result* out_dev) {
+    using namespace ria;
+    if (!ctx || !cfg) return RIA_E_INVAL;
+    if (n_frames < 0 || window < 0 || frame_stride < window) return set_error(ctx, RIA_E_INVAL, "data sync: bad sizes");
+    if (n_frames == 0) return RIA_OK;
+    if (!samples_dev || !out_dev) return set_error(ctx, RIA_E_INVAL, "data sync: null buffer");
+    const int sym = ria_ofdm_symbol_samples(cfg);
+    if (sym <= 0 || sym > 4096) return set_error(ctx, RIA_E_UNSUPPORTED, "data sync: unsupported symbol length");
+    if ((sym * 8 + 7) / 8 > kMaxCand) return set_error(ctx, RIA_E_UNSUPPORTED, "data sync: search window too large");
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    // HilbertTransform(65) coefficients (filters.cpp:266-291), host floats
+    if (!ctx->hilbert65) {
+        float taps[kTaps];
+        const int M = (kTaps - 1) / 2;
+        for (int n = 0; n < kTaps; ++n) {
+            const int k = n - M;
+            float v;
+            if (k == 0) v = 0;
+            else if (k % 2 != 0) v = 2.0f / (M_PI * k);
+            else v = 0;
+            const float w = 2.0f * M_PI * n / (kTaps - 1);
+            v *= 0.42f - 0.5f * std::cos(w) + 0.08f * std::cos(2.0f * w);
+            taps[n] = v;
+        }
+        RIA_CUDA(ctx, cudaMalloc(&ctx->hilbert65, sizeof taps));
+        RIA_CUDA(ctx, cudaMemcpy(ctx->hilbert65, taps, sizeof taps, cudaMemcpyHostToDevice));
+    }
+    const size_t an_stride = (static_cast<size_t>(window) + 1) & ~size_t(1);
+    const size_t s_an = (static_cast<size_t>(n_frames) * an_stride * sizeof(float2) + 255) & ~size_t(255);
+    const size_t cand_stride = 3 * kMaxCand;
+    int rc = ensure_scratch(ctx, s_an + static_cast<size_t>(n_frames) * cand_stride * sizeof(float) + 256);
+    if (rc != RIA_OK) return rc;
+    SyncArgs a{};
+    a.samples = samples_dev; a.frame_stride = frame_stride; a.window = window;
+    a.known_cfo = known_cfo_dev; a.threshold = threshold; a.sym = sym; a.sample_rate = static_cast<float>(cfg->sample_rate);
+    a.taps_g = ctx->hilbert65;
+    a.analytic = static_cast<float2*>(ctx->scratch); a.an_stride = static_cast<long long>(an_stride);
+    a.cand = reinterpret_cast<float*>(static_cast<unsigned char*>(ctx->scratch) + s_an); a.cand_stride = static_cast<long long>(cand_stride);
+    a.out = out_dev;
+    time_begin(ctx, KK_OFDM_SYNC);
+    ofdm_data_sync_kernel<<<static_cast<unsigned>(n_frames), kThreads, 0, ctx->stream>>>(a);
+    time_end(ctx);
+    RIA_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return RIA_OK;
+}

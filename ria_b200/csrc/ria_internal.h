@@ -63,6 +63,7 @@ struct ria_ctx {
     std::vector<ria::McdpskTablesDev*> mcdpsk_tables;
     std::vector<ria::ZcTablesDev*> zc_tables;
     std::vector<ria::ChirpTablesDev*> chirp_tables;
+    float* hilbert65 = nullptr;             // 65-tap Hilbert FIR (OFDM data sync)
     // scratch owned by the context for the fused chain entry points
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -92,7 +93,7 @@ int ensure_scratch(ria_ctx* ctx, size_t bytes);
 
 // kernel kinds for the timing hook / launch accounting
 enum KernelKind { KK_LDPC = 0, KK_OFDM_DEMOD = 1, KK_FRAME_STATUS = 2, KK_AWGN = 3, KK_MCDPSK = 4,
-                  KK_ZC_SYNC = 5, KK_CHIRP_SYNC = 6, KK_CHASE = 7, KK_WATTERSON = 8, KK_MCDPSK_CFO = 9, KK_COUNT = 16 };
+                  KK_ZC_SYNC = 5, KK_CHIRP_SYNC = 6, KK_CHASE = 7, KK_WATTERSON = 8, KK_MCDPSK_CFO = 9, KK_OFDM_SYNC = 10, KK_COUNT = 16 };
 void time_begin(ria_ctx* ctx, int kind);
 void time_end(ria_ctx* ctx);
 

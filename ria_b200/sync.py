@@ -134,3 +134,18 @@ class ChirpSync:
                 ctx.handle, C.addressof(self.config), _ptr(samples[off:]), samples.stride(0), window,
                 float(threshold), m, _ptr(out[off:])))
         return out
+
+
+def ofdm_data_sync_batch(config, samples: torch.Tensor, known_cfo_hz: Optional[torch.Tensor] = None,
+                         threshold: float = 0.3, ctx: Optional[Context] = None) -> torch.Tensor:
+    """OFDMChirpWaveform::detectDataSync for every row of samples (CUDA fp32 [n, window]);
+    ``config`` is a ria_b200.ofdm.ModemConfig."""
+    samples = _check_windows(samples)
+    n, window = samples.shape
+    out = torch.empty((n, SYNC_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=samples.device)
+    ctx = ctx or default_context()
+    ctx.set_stream(torch.cuda.current_stream(samples.device))
+    ctx.check(lib().ria_ofdm_data_sync_batch_dev(
+        ctx.handle, C.addressof(config), _ptr(samples), samples.stride(0), window,
+        _ptr(known_cfo_hz), float(threshold), n, _ptr(out)))
+    return out

@@ -71,7 +71,8 @@ def test_watterson_statistics_vs_reference(ctx, ref):
         # delayed copies; both implementations agree within sampling error
         assert abs(p_gpu.mean() - p_ref.mean()) < 0.25 * p_ref.mean(), (name, p_gpu.mean(), p_ref.mean())
         if cond != 4:      # slow fading: frame powers vary a lot between frames in both
-            assert p_gpu.std() > 0.3 * p_gpu.mean() and p_ref.std() > 0.3 * p_ref.mean()
+            assert p_gpu.std() > 0.15 * p_gpu.mean() and p_ref.std() > 0.15 * p_ref.mean()
+            assert abs(p_gpu.std() / p_gpu.mean() - p_ref.std() / p_ref.mean()) < 0.2
     # noise level: AWGN preset at 10 dB on a constant-envelope tone
     cfg = sim.WattersonConfig.preset(0, 10.0)
     out = sim.watterson_batch(cfg, pool, 64, seed=1, ctx=ctx)
