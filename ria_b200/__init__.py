@@ -10,7 +10,8 @@ from . import ofdm  # noqa: F401
 from . import mcdpsk  # noqa: F401
 from . import sim  # noqa: F401
 from . import sync  # noqa: F401
+from . import dist  # noqa: F401
 from . import selection  # noqa: F401
 from . import txsynth  # noqa: F401
 
-__all__ = ["Context", "RiaError", "LIB_PATH", "exported_symbols", "lib", "fec", "ofdm", "mcdpsk", "sim", "sync", "selection", "txsynth"]
+__all__ = ["Context", "RiaError", "LIB_PATH", "exported_symbols", "lib", "fec", "ofdm", "mcdpsk", "sim", "sync", "dist", "selection", "txsynth"]
