@@ -32,6 +32,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 KK_LDPC, KK_OFDM_DEMOD, KK_FRAME_STATUS, KK_AWGN = 0, 1, 2, 3
+KK_OFDM_FFT, KK_OFDM_CARRIER, KK_OFDM_PHASE = 11, 12, 13
 
 
 # ---------------------------------------------------------------------------------------------
@@ -181,13 +182,19 @@ class OfdmQam64Workload:
     def samples_per_step(self):
         return float(self.n) * self.frame_len
 
-    # dominant kernel = OFDM demod: algorithmic bytes per frame = samples in + LLRs out
-    dominant_kind = KK_OFDM_DEMOD
-    dominant_name = "ofdm_presynced_kernel"
-
-    def dominant_bytes_per_launch(self):
-        n_llr = 10 * 44 * 6
-        return self.n * (self.frame_len * 4 + n_llr * 4)
+    def kernels(self):
+        """kind -> (kernel name, ALGORITHMIC bytes per step); DESIGN.md section 3 derives the figures.
+        Per frame: 12 symbols x 1120 samples in, 12 x 59 complex bins between the stages, 10 x 44 x 6
+        soft bits out of the demodulator, 4 x 61 info bytes + flags out of the decoder."""
+        n_sym, nc, n_llr = 12, 59, 10 * 44 * 6
+        samples, bins, llr = self.frame_len * 4, n_sym * nc * 8, n_llr * 4
+        return {
+            KK_OFDM_FFT: ("ofdm_fft_kernel", self.n * (samples + bins)),
+            KK_OFDM_CARRIER: ("ofdm_carrier_kernel", self.n * (bins + llr)),
+            KK_OFDM_DEMOD: ("ofdm_presynced_kernel (residual-CFO re-run frames only)", 0),
+            KK_LDPC: ("ldpc_decode_kernel", self.n * (llr + 4 * (61 + 5))),
+            KK_FRAME_STATUS: ("frame_status_kernel", self.n * (4 * 72 + 4 * 5 + 40)),
+        }
 
     def counters(self):
         """[frames, frames_ok (4/4 cw + header + frame CRC), cw_fail, frames_payload_wrong, sum_iters]"""
@@ -305,8 +312,6 @@ class LdpcWorkload:
     MAX_ITER = {0: 50, 2: 80, 3: 70, 4: 60}
     FACTOR = 0.9375
     CW_PER_FRAME = 4
-    dominant_kind = KK_LDPC
-    dominant_name = "ldpc_decode_kernel"
 
     def __init__(self, n_cw: int):
         self.n_cw = n_cw
@@ -374,9 +379,10 @@ class LdpcWorkload:
     def samples_per_step(self):
         return 0.0
 
-    def dominant_bytes_per_launch(self):
+    def kernels(self):
         from ria_b200 import fec
-        return sum(self.n_cw * (648 * 4 + (fec.code_params(r)[0] + 7) // 8 + 5) for r in self.RATES) / len(self.RATES)
+        return {KK_LDPC: ("ldpc_decode_kernel",
+                          sum(self.n_cw * (648 * 4 + (fec.code_params(r)[0] + 7) // 8 + 5) for r in self.RATES))}
 
     def counters(self):
         torch = self.torch
@@ -546,7 +552,7 @@ def main():
         barrier()
         ms = ev0.elapsed_time(ev1)
         launches = ctx.launch_count - l0
-        kern_ms = {k: ctx.get_timing(k) for k in (KK_LDPC, KK_OFDM_DEMOD, KK_FRAME_STATUS)}
+        kern_ms = {k: ctx.get_timing(k) for k in wl.kernels()}
         ctx.set_timing(False)
         clocks = sampler.stop() if rank == 0 else None
 
@@ -576,9 +582,13 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        dom_ms, dom_n = kern_ms[wl.dominant_kind]
+        kinfo = wl.kernels()
+        dom_kind = max(kern_ms, key=lambda k: kern_ms[k][0])          # most device time in the step
+        dom_name, dom_bytes_step = kinfo[dom_kind]
+        dom_ms, dom_n = kern_ms[dom_kind]
         kern_s = dom_ms / max(1, dom_n) * 1e-3
-        achieved = wl.dominant_bytes_per_launch() / kern_s / 1e9
+        bytes_per_launch = dom_bytes_step * args.steps / max(1, dom_n)
+        achieved = bytes_per_launch / kern_s / 1e9
         step_ms_local = ms / args.steps
         line = {
             "metric": wl.metric, "value": value, "unit": wl.unit,
@@ -589,14 +599,17 @@ def main():
             "counters": wl.counter_dict(cnt.cpu().numpy()),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": wl.dominant_name, "kernel_ms_per_launch": kern_s * 1e3,
-                         "algorithmic_bytes_per_launch": wl.dominant_bytes_per_launch(),
-                         "note": "see DESIGN.md: this kernel is FP32-issue / shared-memory bound, "
-                                 "not HBM bound; the HBM fraction is what the contract asks for"},
-            "kernel_share_of_step": {
-                "ldpc_decode_kernel": kern_ms[KK_LDPC][0] / args.steps / step_ms_local,
-                "ofdm_presynced_kernel": kern_ms[KK_OFDM_DEMOD][0] / args.steps / step_ms_local,
-                "frame_status_kernel": kern_ms[KK_FRAME_STATUS][0] / args.steps / step_ms_local},
+                         "kernel": dom_name, "kernel_ms_per_launch": kern_s * 1e3,
+                         "launches_per_step": dom_n / args.steps,
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "note": "dominant kernel = most device time in the step; see DESIGN.md section 3 "
+                                 "for the per-frame byte counts and what bounds each kernel"},
+            "kernels": {kinfo[k][0]: {"share_of_step": kern_ms[k][0] / args.steps / step_ms_local,
+                                      "ms_per_step": kern_ms[k][0] / args.steps,
+                                      "launches_per_step": kern_ms[k][1] / args.steps,
+                                      "algorithmic_gb_per_s": (kinfo[k][1] * args.steps / (kern_ms[k][0] * 1e-3) / 1e9
+                                                               if kern_ms[k][0] > 0 else None)}
+                        for k in kern_ms},
             "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "batch": getattr(wl, "e2e_n", args.e2e_batch),
                     "api": "ria_ofdm_rx_frames_host / ria_ldpc_decode_batch_host (pinned host buffers)"},

@@ -64,4 +64,27 @@ __device__ __forceinline__ float cfo_phase_block32(float base, float inc, int la
     return mine;
 }
 
+// Per-thread variant: phase before sample k (0 <= k < 32) of a block whose first sample sees
+// `base`.  Same closed form, checked over the k steps actually taken.
+__device__ __forceinline__ float cfo_phase_at(float base, float inc, int k) {
+    const unsigned bits = __float_as_uint(base);
+    const int e = static_cast<int>((bits >> 23) & 0xFF);
+    if (e > 0 && e < 255 && inc != 0.0f && fabs(static_cast<double>(base)) <= M_PI) {
+        const double ulp = __longlong_as_double(static_cast<long long>(e - 127 - 23 + 1023) << 52);   // 2^(e-150)
+        const double q = static_cast<double>(inc) / ulp;
+        const double S = rint(q);
+        if (fabs(q - trunc(q)) != 0.5 && fabs(S) < 4194304.0) {
+            const double last = static_cast<double>(base) + static_cast<double>(k) * (S * ulp);       // exact
+            const double lo = __longlong_as_double(static_cast<long long>(e - 127 + 1023) << 52);     // 2^(e-127)
+            const double mag = fabs(last);
+            if ((mag > lo) && (mag < 2.0 * lo) && ((last < 0.0) == (base < 0.0f)) && (mag <= M_PI))
+                return static_cast<float>(last);
+        }
+    }
+    float ph = base;
+#pragma unroll 1
+    for (int i = 0; i < k; ++i) ph = cfo_phase_step(ph, inc);
+    return ph;
+}
+
 }  // namespace ria

@@ -11,24 +11,37 @@
 //       Impl::equalize / hardDecision             channel_equalizer.cpp:1168-1451
 //       Impl::demodulateSymbol + soft_demap::*    demodulator.cpp:208-508, soft_demap.hpp:22-263
 //
-// Mapping (B200): one CTA of 128 threads per frame (persistent CTAs, atomic frame counter);
-// the symbols of a frame are inherently sequential (channel estimate, EMA and differential
-// reference carry over), so parallelism is frames x (samples | carriers) inside a symbol.
-//   * samples are read from HBM exactly once, coalesced, straight into the FFT registers
-//     (thread t owns samples t + 128 q, which is precisely the radix-2 DIT bit-reversed group it
-//     needs for the first three stages); the cyclic prefix is never loaded;
-//   * the FFT performs the reference's radix-2 DIT butterflies in the reference's order with
-//     the reference's twiddle values, three stages per pass in registers, exchanging through
-//     an XOR-swizzled shared-memory tile (conflict-free for every pass), so every used bin is
-//     bit-identical to the reference FFT;  the last stage is evaluated only for the carriers;
-//   * the 59 carriers are handled by threads 0..63; reductions whose fp32 summation order is
-//     observable (they feed thresholds) are done in the reference's order.
+// Mapping (B200).  The only sequential dependence between the symbols of a frame is the
+// per-carrier equaliser state; the FFTs are independent (unless the LTS finds a residual CFO,
+// see below).  The batch therefore runs as a short pipeline of kernels over chunks of frames:
+//   ofdm_phase_scan_kernel  (only when a CFO is given) one warp per frame: value of the fp32
+//                           CFO phase accumulator at every 32nd sample, exact (cfo_phase.cuh);
+//   ofdm_fft_kernel         128-thread CTAs, work item = (symbol index, 16 frames): the mixer
+//                           phasors of that symbol are staged once in shared memory, then every
+//                           frame's samples are read from HBM exactly once (coalesced, CP never
+//                           loaded, next frame prefetched into registers), mixed and transformed
+//                           with the reference's radix-2 DIT butterflies in the reference's
+//                           order -- three stages per pass in registers, exchanged through an
+//                           XOR-swizzled shared-memory tile (conflict-free for every pass).  The
+//                           last four stages are evaluated only for the <= 63 used bins (output
+//                           pruning: 7 half-butterflies per thread instead of 12 + 1 full ones).
+//                           Every used bin is bit-identical to the reference FFT.
+//   ofdm_carrier_kernel     one warp per frame, two carriers per lane, no block barriers: LTS
+//                           estimate, then the data symbols in order (pilot tracking, MMSE,
+//                           LLRs).  Reductions whose fp32 summation order is observable (they
+//                           feed thresholds) are done in the reference's order by lane 0.
+//   ofdm_presynced_kernel   the monolithic per-frame kernel (FFT + carriers in one CTA); runs
+//                           only for the frames whose LTS reports a residual CFO in (0.3, 5) Hz:
+//                           the reference then re-mixes the whole frame with the corrected CFO
+//                           (channel_equalizer.cpp:304-382), which the carrier kernel cannot do.
 // Float-order fidelity: compiled with --fmad=false; complex multiply/divide/abs follow what
 // libstdc++/libgcc do on x86-64 (division and abs go through double, see cdiv/cabs below).
 
 #include "ofdm_tables.h"
+#include "cfo_phase.cuh"
 
 #include <cfloat>
+#include <cstdlib>
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -41,7 +54,9 @@ namespace {
 constexpr int kThreads = 128;
 constexpr int kFft = 1024;
 constexpr int kMaxSymLen = 1160;    // fft 1024 + CP <= 128 + guard <= 8
-constexpr int kTwCount = 1024;     // stage-major twiddle table (1022 used)
+constexpr int kTwCount = 1024;      // stage-major twiddle table (1022 used)
+constexpr int kFftGroup = 16;       // frames per (symbol, group) work item of the FFT kernel
+constexpr int kCarWarps = 4;        // frames per CTA of the carrier kernel
 
 // ------------------------------- complex helpers -------------------------------------------
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -92,7 +107,7 @@ __device__ __forceinline__ float clip_llr(float llr) {
     return c;
 }
 
-// ------------------------------- shared memory layout --------------------------------------
+// ------------------------------- per-frame equaliser state ---------------------------------
 struct FrameScalars {
     float cfo_hz, cfo_phase, phase_start;
     float noise_var, snr_lin, slope;
@@ -109,12 +124,7 @@ struct FrameScalars {
     int have_dd;
 };
 
-struct Smem {
-    float2 tw[kTwCount];
-    float re[kFft];
-    float im[kFft];
-    float cph[kMaxSymLen];
-    OfdmCarrierTable car;
+struct CarState {
     float2 bin[kMaxCarriers];
     float2 H[kMaxCarriers];
     float2 hps[2][kMaxCarriers];
@@ -135,24 +145,7 @@ struct Smem {
     FrameScalars s;
 };
 
-// XOR-swizzled 32x32 transpose: conflict-free for all four FFT passes (see DESIGN.md).
-__device__ __forceinline__ int fft_addr(int j) { return ((j & 31) << 5) | (((j >> 5) ^ j) & 31); }
-// stage-major twiddle table: tw_L[k] = W[k * (1024 / L)], k < L/2, stored at offset L/2 - 2
-__device__ __forceinline__ int tw_off(int L) { return (L >> 1) - 2; }
-
-// one radix-2 DIT butterfly exactly as fft.cpp:115-119:  t = w * b;  b = a - t;  a = a + t
-__device__ __forceinline__ void bfly(float2& a, float2& b, float2 w) {
-    const float2 t = cmul(w, b);
-    b = csub(a, t);
-    a = cadd(a, t);
-}
-// k = 0: w = (1, -0); multiplying by it is value-exact, so the product is skipped
-__device__ __forceinline__ void bfly0(float2& a, float2& b) {
-    const float2 t = b;
-    b = csub(a, t);
-    a = cadd(a, t);
-}
-
+// what every stage needs to know about the batch
 struct KernelArgs {
     const float* samples; long long frame_stride; int frame_len;
     const float* cfo_hz; const float* phase; long long n_frames;
@@ -162,118 +155,20 @@ struct KernelArgs {
     const float2* tw_g; const float2* nco_g; const OfdmCarrierTable* car_g;
     int cp, sym_len, modulation, differential, bits_per_carrier, sample_rate;
     unsigned int* counter;
+    // staged pipeline
+    float2* bins;                 // [frame][symbol][carrier] carrier bins written by the FFT kernel
+    long long bins_frame0;        // frame index bins[0] belongs to
+    const float* block_phase;     // [frame - bins_frame0][block] CFO accumulator at sample 32*block
+    int n_blocks;
+    int pruned;                   // all used bins have distinct residues mod 64
+    int* rerun_list;              // frames the carrier kernel hands to the monolithic kernel
+    unsigned int* rerun_count;
+    long long frame_begin, frame_end;   // chunk of the batch this launch covers
 };
 
-// Mix + CFO-correct + FFT one symbol (absolute symbol index `sym` inside the frame) and leave
-// the carrier bins in sm.bin[c].  channel_equalizer.cpp:99-187 + fft.cpp:96-128.
-__device__ void fft_symbol(Smem& sm, const KernelArgs& a, const float* __restrict__ frame, int sym) {
-    const int tid = threadIdx.x;
-    const int base = sym * a.sym_len;
-    const bool cfo_on = fabsf(sm.s.cfo_hz) > 0.01f;
-
-    if (cfo_on) {
-        // freq_correction_phase is an fp32 accumulator with a double-promoted wrap
-        // (channel_equalizer.cpp:103, 132-144); its rounding is part of the result, so the scan
-        // is done sequentially, once per symbol, by one thread.
-        if (tid == 0) {
-            const float inc = static_cast<float>(-2.0f * M_PI * static_cast<double>(sm.s.cfo_hz) /
-                                                 static_cast<double>(static_cast<unsigned>(a.sample_rate)));
-            float ph = sm.s.cfo_phase;
-            for (int i = 0; i < a.sym_len; ++i) {
-                sm.cph[i] = ph;
-                ph = __fadd_rn(ph, inc);
-                if (static_cast<double>(ph) > M_PI) ph = static_cast<float>(static_cast<double>(ph) - 2.0f * M_PI);
-                else if (static_cast<double>(ph) < -M_PI) ph = static_cast<float>(static_cast<double>(ph) + 2.0f * M_PI);
-            }
-            sm.s.cfo_phase = ph;
-        }
-        __syncthreads();
-    }
-
-    // ---- load + mix: v[t] = baseband sample (tid + 128 * brev3(t)) of the FFT window ----
-    float2 v[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const int q = ((t & 1) << 2) | (t & 2) | ((t & 4) >> 2);      // brev3
-        const int i = a.cp + tid + 128 * q;                           // index inside the symbol
-        const float s = __ldcs(frame + base + i);
-        const float2 osc = __ldg(a.nco_g + base + i);
-        // samples[i] * conj(osc)  ->  (osc.re * s, (-osc.im) * s)
-        float2 m = make_float2(__fmul_rn(osc.x, s), __fmul_rn(-osc.y, s));
-        if (cfo_on) m = cmul(m, cexpj(sm.cph[i]));
-        v[t] = m;
-    }
-    // ---- pass 1: stages L = 2, 4, 8 on data[8g .. 8g+7], g = brev7(tid) ----
-    bfly0(v[0], v[1]); bfly0(v[2], v[3]); bfly0(v[4], v[5]); bfly0(v[6], v[7]);
-    {
-        const float2 w1 = sm.tw[tw_off(4) + 1];
-        bfly0(v[0], v[2]); bfly(v[1], v[3], w1);
-        bfly0(v[4], v[6]); bfly(v[5], v[7], w1);
-        const float2 x1 = sm.tw[tw_off(8) + 1], x2 = sm.tw[tw_off(8) + 2], x3 = sm.tw[tw_off(8) + 3];
-        bfly0(v[0], v[4]); bfly(v[1], v[5], x1); bfly(v[2], v[6], x2); bfly(v[3], v[7], x3);
-    }
-    {
-        const int g = __brev(static_cast<unsigned>(tid)) >> 25;      // brev7
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int ad = fft_addr((g << 3) | t);
-            sm.re[ad] = v[t].x; sm.im[ad] = v[t].y;
-        }
-    }
-    __syncthreads();
-    const int lane = tid & 31, warp = tid >> 5;
-    // ---- pass 2: stages L = 16, 32, 64; thread owns bits j5..j3 ----
-    {
-        const int lo = (warp << 1) | (lane & 1);                      // j2 j1 j0
-        const int hi = lane >> 1;                                     // j9..j6
-        const int jb = (hi << 6) | lo;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 3)); v[u] = make_float2(sm.re[ad], sm.im[ad]); }
-        const float2 w16 = sm.tw[tw_off(16) + lo];
-        if (lo == 0) { bfly0(v[0], v[1]); bfly0(v[2], v[3]); bfly0(v[4], v[5]); bfly0(v[6], v[7]); }
-        else { bfly(v[0], v[1], w16); bfly(v[2], v[3], w16); bfly(v[4], v[5], w16); bfly(v[6], v[7], w16); }
-        const float2 w32a = sm.tw[tw_off(32) + lo], w32b = sm.tw[tw_off(32) + 8 + lo];
-        if (lo == 0) { bfly0(v[0], v[2]); bfly0(v[4], v[6]); } else { bfly(v[0], v[2], w32a); bfly(v[4], v[6], w32a); }
-        bfly(v[1], v[3], w32b); bfly(v[5], v[7], w32b);
-        if (lo == 0) bfly0(v[0], v[4]); else bfly(v[0], v[4], sm.tw[tw_off(64) + lo]);
-        bfly(v[1], v[5], sm.tw[tw_off(64) + 8 + lo]);
-        bfly(v[2], v[6], sm.tw[tw_off(64) + 16 + lo]);
-        bfly(v[3], v[7], sm.tw[tw_off(64) + 24 + lo]);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 3)); sm.re[ad] = v[u].x; sm.im[ad] = v[u].y; }
-    }
-    __syncthreads();
-    // ---- pass 3: stages L = 128, 256, 512; thread owns bits j8..j6 ----
-    {
-        const int lo6 = ((warp & 1) << 5) | lane;                     // j5..j0
-        const int jb = ((warp >> 1) << 9) | lo6;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 6)); v[u] = make_float2(sm.re[ad], sm.im[ad]); }
-        const float2 w128 = sm.tw[tw_off(128) + lo6];
-        if (lo6 == 0) { bfly0(v[0], v[1]); bfly0(v[2], v[3]); bfly0(v[4], v[5]); bfly0(v[6], v[7]); }
-        else { bfly(v[0], v[1], w128); bfly(v[2], v[3], w128); bfly(v[4], v[5], w128); bfly(v[6], v[7], w128); }
-        const float2 w256a = sm.tw[tw_off(256) + lo6], w256b = sm.tw[tw_off(256) + 64 + lo6];
-        if (lo6 == 0) { bfly0(v[0], v[2]); bfly0(v[4], v[6]); } else { bfly(v[0], v[2], w256a); bfly(v[4], v[6], w256a); }
-        bfly(v[1], v[3], w256b); bfly(v[5], v[7], w256b);
-        if (lo6 == 0) bfly0(v[0], v[4]); else bfly(v[0], v[4], sm.tw[tw_off(512) + lo6]);
-        bfly(v[1], v[5], sm.tw[tw_off(512) + 64 + lo6]);
-        bfly(v[2], v[6], sm.tw[tw_off(512) + 128 + lo6]);
-        bfly(v[3], v[7], sm.tw[tw_off(512) + 192 + lo6]);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 6)); sm.re[ad] = v[u].x; sm.im[ad] = v[u].y; }
-    }
-    __syncthreads();
-    // ---- pass 4: stage L = 1024, only for the carriers ----
-    if (tid < sm.car.num_carriers) {
-        const int f = sm.car.fft_idx[tid];
-        const int k = f & 511;
-        const int a0 = fft_addr(k), a1 = fft_addr(k + 512);
-        float2 x0 = make_float2(sm.re[a0], sm.im[a0]);
-        float2 x1 = make_float2(sm.re[a1], sm.im[a1]);
-        if (k == 0) bfly0(x0, x1); else bfly(x0, x1, sm.tw[tw_off(1024) + k]);
-        sm.bin[tid] = (f < 512) ? x0 : x1;
-    }
-    __syncthreads();
+// Group of G threads working on one frame: a CTA (G = 128) or a warp (G = 32).
+template <int G> __device__ __forceinline__ void gsync() {
+    if (G == 32) __syncwarp(); else __syncthreads();
 }
 
 // hardDecision, channel_equalizer.cpp:1168-1230
@@ -344,10 +239,705 @@ __device__ void demap_qam32(float2 sym, float nv, float* out) {
     for (int b = 0; b < 5; ++b) out[b] = clip_llr(sf * (d1[b] - d0[b]));
 }
 
+// =============================== carrier-domain processing =================================
+// Everything below works on cs.bin[] (the carrier bins of the current symbol) with a group of
+// G threads, g = index inside the group.  It is shared by the warp-per-frame carrier kernel
+// (G = 32) and the monolithic kernel (G = 128).
+
+template <int G>
+__device__ __forceinline__ void frame_reset(CarState& cs, const KernelArgs& a, long long f, int g) {
+    // demodulator.cpp:1264-1300
+    if (g == 0) {
+        cs.s.cfo_hz = a.cfo_hz ? a.cfo_hz[f] : 0.0f;
+        cs.s.cfo_phase = a.phase ? a.phase[f] : 0.0f;
+        cs.s.phase_start = cs.s.cfo_phase;
+        cs.s.noise_var = 0.1f;
+        cs.s.snr_lin = 1.0f;
+        cs.s.slope = 0.0f;
+        cs.s.cpc = make_float2(1.0f, 0.0f);
+        cs.s.cpc_init = 0;
+        cs.s.snr_count = 0;
+        cs.s.rerun = 0;
+        cs.s.have_prev_pilot = 0;
+        cs.s.have_dd = 0;
+    }
+    for (int c = g; c < kMaxCarriers; c += G) cs.H[c] = make_float2(1.0f, 0.0f);
+    gsync<G>();
+}
+
+// frames too short to hold the two training symbols: processPresynced returns false without output
+template <int G>
+__device__ __forceinline__ void frame_too_short(const KernelArgs& a, long long f, int g) {
+    if (g == 0) {
+        a.n_llr[f] = 0;
+        if (a.snr_db) a.snr_db[f] = 0.0f;
+        if (a.cfo_out) a.cfo_out[f] = a.cfo_hz ? a.cfo_hz[f] : 0.0f;
+        if (a.fading) a.fading[f] = 0.0f;
+    }
+    float* llr_out = a.llr + f * a.llr_stride;
+    for (int i = g; i < a.llr_stride; i += G) llr_out[i] = 0.0f;
+}
+
+// H_s = rx / tx on LTS symbol s (channel_equalizer.cpp:264, 278)
+template <int G>
+__device__ __forceinline__ void lts_symbol(CarState& cs, const OfdmCarrierTable& car, int s, int g) {
+    const int nc = car.num_carriers;
+    for (int c = g; c < nc; c += G) {
+        const int sub = car.sub_idx[c];
+        const float2 tx = car.is_pilot[c] ? make_float2(car.pilot_sign[sub], 0.0f) : car.tx_data[sub];
+        cs.hps[s][c] = cdiv(cs.bin[c], tx);
+    }
+    gsync<G>();
+}
+
+// residual CFO from the phase rotation between the two LTS symbols (:304-382).  Returns true when
+// the reference re-runs the LTS with the corrected CFO; cs.s.cfo_hz / cfo_phase are then updated.
+template <int G>
+__device__ __forceinline__ bool lts_residual(CarState& cs, const OfdmCarrierTable& car, const KernelArgs& a, int g) {
+    const int nd = car.n_data;
+    for (int i = g; i < nd; i += G) {
+        const int c = car.data_car[i];
+        const float2 h0 = cs.hps[0][c], h1 = cs.hps[1][c];
+        int ok = 0;
+        if (cabs(h0) > 0.01f && cabs(h1) > 0.01f) {
+            const float2 diff = cmul(h1, cconj(h0));
+            const float mag = cabs(diff);
+            if (mag > 1e-6f) { cs.tmpc[i] = cdivf(diff, mag); ok = 1; }
+        }
+        cs.flag[i] = ok;
+    }
+    gsync<G>();
+    if (g == 0) {
+        float2 sum = make_float2(0.f, 0.f);
+        int valid = 0;
+        for (int i = 0; i < nd; ++i) if (cs.flag[i]) { sum = cadd(sum, cs.tmpc[i]); ++valid; }
+        int rerun = 0;
+        if (valid > 10) {
+            const float avg_phase = atan2_rn(sum.y, sum.x);
+            const float symbol_duration = static_cast<float>(a.sym_len) / static_cast<float>(static_cast<unsigned>(a.sample_rate));
+            const float residual = static_cast<float>(static_cast<double>(avg_phase) /
+                                                      (2.0f * M_PI * static_cast<double>(symbol_duration)));
+            if (fabsf(residual) > 0.3f && fabsf(residual) < 5.0f) {
+                cs.s.cfo_hz = __fadd_rn(cs.s.cfo_hz, residual);
+                cs.s.cfo_phase = cs.s.phase_start;            // :341
+                rerun = 1;
+            }
+        }
+        cs.s.rerun = rerun;
+    }
+    gsync<G>();
+    return cs.s.rerun != 0;
+}
+
+// channel estimate := last LTS symbol, phase slope, noise variance / SNR (:387-485, :642)
+template <int G>
+__device__ __forceinline__ void lts_finish(CarState& cs, const OfdmCarrierTable& car, const KernelArgs& a, long long f, int g) {
+    const int nc = car.num_carriers, nd = car.n_data;
+    for (int c = g; c < nc; c += G) cs.H[c] = cs.hps[1][c];
+    gsync<G>();
+    // phase slope across adjacent carriers (:412-437)
+    for (int c = g; c < nc - 1; c += G) {
+        const float2 h0 = cs.H[c], h1 = cs.H[c + 1];
+        int ok = 0;
+        if (cabs(h0) > 0.01f && cabs(h1) > 0.01f) {
+            const float2 diff = cmul(h1, cconj(h0));
+            const float mag = cabs(diff);
+            if (mag > 1e-6f) { cs.tmpc[c] = cdivf(diff, mag); ok = 1; }
+        }
+        cs.flag[c] = ok;
+    }
+    gsync<G>();
+    if (g == 0) {
+        float2 sum = make_float2(0.f, 0.f);
+        int cnt = 0;
+        for (int i = 0; i < nc - 1; ++i) if (cs.flag[i]) { sum = cadd(sum, cs.tmpc[i]); ++cnt; }
+        if (cnt > 0) cs.s.slope = carg(cdivf(sum, static_cast<float>(cnt)));
+    }
+    gsync<G>();
+    // noise variance / SNR from the two LTS estimates (:457-485)
+    for (int i = g; i < nd; i += G) {
+        const int c = car.data_car[i];
+        const float2 h0 = cs.hps[0][c], h1 = cs.hps[1][c];
+        int ok = 0;
+        if (cabs(h0) > 1e-6f && cabs(h1) > 1e-6f) {
+            cs.tmpf[i] = cnorm(csub(h1, h0));
+            cs.tmpg[i] = __fdiv_rn(__fadd_rn(cnorm(h0), cnorm(h1)), 2.0f);
+            ok = 1;
+        }
+        cs.flag[i] = ok;
+    }
+    gsync<G>();
+    if (g == 0) {
+        float noise_sum = 0.f, signal_sum = 0.f;
+        int cnt = 0;
+        for (int i = 0; i < nd; ++i) if (cs.flag[i]) { noise_sum += cs.tmpf[i]; signal_sum += cs.tmpg[i]; ++cnt; }
+        if (cnt > 0) {
+            const float nvar = noise_sum / (4.0f * cnt);
+            const float sp = signal_sum / cnt;
+            float snr = sp / std_max(nvar, 1e-10f);
+            snr = std_max(3.16f, std_min(10000.0f, snr));
+            cs.s.noise_var = nvar;
+            cs.s.snr_lin = snr;
+        }
+        cs.s.snr_count = 2;                                       // :642
+    }
+    if (a.h_lts_tap)
+        for (int c = g; c < nc; c += G) reinterpret_cast<float2*>(a.h_lts_tap)[f * nc + c] = cs.H[c];
+    gsync<G>();
+}
+
+// One data symbol: updateChannelEstimate + equalize + demodulateSymbol on cs.bin[].
+// `sd` = index of the data symbol (0 = first after the LTS), llr_out = soft bits of the frame.
+template <int G>
+__device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable& car, const KernelArgs& a,
+                                            float* __restrict__ llr_out, int sd, int g) {
+    const int nc = car.num_carriers, nd = car.n_data, np = car.n_pilot;
+    const int mod = a.modulation;
+    const bool differential = a.differential != 0;
+    const int bpc = a.bits_per_carrier;
+    const int llr_per_sym = nd * bpc;
+    const bool first = (sd == 0);                             // soft_bits.empty()
+
+    // ----------------- updateChannelEstimate (channel_equalizer.cpp:645-1043) -----------------
+    if (np > 0) {
+        float alpha;
+        if (first) alpha = 1.0f; else if (differential) alpha = 0.5f; else alpha = 0.9f;
+        for (int i = g; i < np; i += G) {
+            const int c = car.pilot_car[i];
+            cs.pil_ls[i] = cdiv(cs.bin[c], make_float2(car.pilot_sign[i], 0.0f));   // :687
+        }
+        gsync<G>();
+        if (differential) {
+            // carrier phase recovery on the first symbol that yields a usable average (:699-714)
+            if (g == 0 && !cs.s.cpc_init) {
+                float2 h_sum = make_float2(0.f, 0.f);
+                for (int i = 0; i < np; ++i) h_sum = cadd(h_sum, cs.pil_ls[i]);
+                const float2 h_avg = cdivf(h_sum, static_cast<float>(np));
+                const float avg_mag = cabs(h_avg);
+                if (avg_mag > 0.01f) { cs.s.cpc = cdivf(cconj(h_avg), avg_mag); cs.s.cpc_init = 1; }
+            }
+            gsync<G>();
+            for (int i = g; i < np; i += G) cs.pil_ls[i] = cmul(cs.pil_ls[i], cs.s.cpc);
+            gsync<G>();
+        } else {
+            // CPE: common phase of pilot LS vs current H, applied to every carrier (:720-756)
+            for (int i = g; i < np; i += G) {
+                const int c = car.pilot_car[i];
+                const float2 h_old = cs.H[c];
+                const float h_old_mag = cabs(h_old);
+                int ok = 0;
+                if (h_old_mag > 0.01f) {
+                    const float2 ratio = cmul(cs.pil_ls[i], cconj(h_old));
+                    const float mag = cabs(ratio);
+                    if (mag > 1e-6f) { cs.tmpc[i] = cscale(cdivf(ratio, mag), h_old_mag); cs.tmpf[i] = h_old_mag; ok = 1; }
+                }
+                cs.flag[i] = ok;
+            }
+            gsync<G>();
+            if (g == 0) {
+                float2 cpe_sum = make_float2(0.f, 0.f);
+                float w = 0.f;
+                for (int i = 0; i < np; ++i) if (cs.flag[i]) { cpe_sum = cadd(cpe_sum, cs.tmpc[i]); w += cs.tmpf[i]; }
+                int apply = 0;
+                if (w > 0.01f) {
+                    const float ph = carg(cpe_sum);
+                    if (fabsf(ph) > 0.001f) { cs.s.cpe = cexpj(ph); apply = 1; }
+                }
+                cs.s.apply_cpe = apply;
+            }
+            gsync<G>();
+            if (cs.s.apply_cpe)
+                for (int c = g; c < nc; c += G) cs.H[c] = cmul(cs.H[c], cs.s.cpe);
+            gsync<G>();
+        }
+        // pilot power, temporal noise count, smoothed update at the pilots (:778-820)
+        if (g == 0) {
+            float sp = 0.f;
+            for (int i = 0; i < np; ++i) sp += cnorm(cs.pil_ls[i]);
+            cs.s.signal_power = sp / static_cast<float>(np);
+            int ncount = 0;
+            float npow = 0.f;
+            if (cs.s.have_prev_pilot)
+                for (int i = 0; i < np; ++i) {
+                    const float2 ph = cs.prev_pilot[i], ch = cs.pil_ls[i];
+                    if (cnorm(ph) > 1e-6f && cnorm(ch) > 1e-6f) { npow += cnorm(csub(ch, ph)); ++ncount; }
+                }
+            if (ncount == 0) { npow = cs.s.signal_power / 31.6f; ncount = 1; }
+            // the SNR EMA only looks at (noise_count > 1) and (noise_power_sum > 0) (:1025-1040)
+            cs.s.noise_count = (npow > 0.0f) ? ncount : 0;
+        }
+        gsync<G>();
+        for (int i = g; i < np; i += G) {
+            const int c = car.pilot_car[i];
+            const float2 h_old = cs.H[c];
+            const float2 ls = cs.pil_ls[i];
+            if (differential) {
+                const float new_mag = alpha * cabs(ls) + (1.0f - alpha) * cabs(h_old);
+                const float2 e = cexpj(carg(h_old));
+                cs.H[c] = make_float2(new_mag * e.x, new_mag * e.y);              // std::polar
+            } else {
+                cs.H[c] = cadd(cscale(ls, alpha), cscale(h_old, 1.0f - alpha));
+            }
+            cs.prev_pilot[i] = ls;                                                // :882
+        }
+        gsync<G>();
+        // interpolation to the data carriers (:885-957)
+        if (!differential) {
+            for (int i = g; i < np; i += G) {
+                const int c = car.pilot_car[i];
+                const float ph = -cs.s.slope * static_cast<float>(car.car_k[c]);
+                cs.desloped[i] = cmul(cs.H[c], cexpj(ph));
+            }
+            gsync<G>();
+            for (int i = g; i < nd; i += G) {
+                const int c = car.data_car[i];
+                const int lo = car.interp_lo[i], hi = car.interp_hi[i];
+                const float al = car.interp_alpha[i];
+                float2 ih = make_float2(0.f, 0.f);
+                if (lo >= 0 && hi >= 0) ih = cadd(cscale(cs.desloped[lo], 1.0f - al), cscale(cs.desloped[hi], al));
+                else if (lo >= 0) ih = cs.desloped[lo];
+                else if (hi >= 0) ih = cs.desloped[hi];
+                const float ph = cs.s.slope * static_cast<float>(car.car_k[c]);
+                float2 h = cmul(ih, cexpj(ph));
+                // decision-directed phase refinement from the previous symbol (:964-975)
+                if (cs.s.have_dd && cs.s.snr_count >= 3) {
+                    const float corr = cs.dd[i];
+                    if (fabsf(corr) > 0.001f) h = cmul(h, cexpj(corr * 0.3f));
+                }
+                cs.H[c] = h;
+            }
+        } else {
+            for (int i = g; i < nd; i += G) {
+                const int c = car.data_car[i];
+                const int lo = car.interp_lo[i], hi = car.interp_hi[i];
+                const float al = car.interp_alpha[i];
+                float im = 0.0f;
+                if (lo >= 0 && hi >= 0) {
+                    const float m1 = cabs(cs.H[car.pilot_car[lo]]), m2 = cabs(cs.H[car.pilot_car[hi]]);
+                    im = (1.0f - al) * m1 + al * m2;
+                } else if (lo >= 0) im = cabs(cs.H[car.pilot_car[lo]]);
+                else if (hi >= 0) im = cabs(cs.H[car.pilot_car[hi]]);
+                const float2 e = cexpj(carg(cs.H[c]));
+                cs.H[c] = make_float2(im * e.x, im * e.y);
+            }
+        }
+        gsync<G>();     // every thread has read snr_count / have_dd before thread 0 moves them on
+        if (g == 0) {
+            if (!differential && cs.s.noise_count > 1) {          // :1035-1039
+                float inst = cs.s.signal_power / std_max(cs.s.noise_var, 1e-6f);
+                inst = std_max(0.1f, std_min(10000.0f, inst));
+                cs.s.snr_lin = 0.3f * inst + (1.0f - 0.3f) * cs.s.snr_lin;
+            }
+            cs.s.snr_count += 1;
+            cs.s.have_prev_pilot = 1;
+        }
+        gsync<G>();
+    }
+
+    // ----------------------- equalize (channel_equalizer.cpp:1259-1451) -----------------------
+    for (int i = g; i < nd; i += G) cs.hpow[i] = cnorm(cs.H[car.data_car[i]]);
+    gsync<G>();
+    if (g == 0) {
+        float s = 0.f;
+        for (int i = 0; i < nd; ++i) s += cs.hpow[i];
+        cs.s.avg_h_power = s / static_cast<float>(nd);
+    }
+    gsync<G>();
+    const bool dd_mod = !differential && (mod == RIA_QPSK || mod == RIA_BPSK || mod == RIA_QAM16 ||
+                                          mod == RIA_QAM32 || mod == RIA_QAM64);
+    for (int i = g; i < nd; i += G) {
+        const int c = car.data_car[i];
+        const float2 rx = cs.bin[c], h = cs.H[c];
+        const float h_power = cs.hpow[i];
+        const float fade_threshold = 0.25f * cs.s.avg_h_power;
+        float2 e;
+        float nvv;
+        if (differential) {
+            float snv = cs.s.noise_var;
+            if (snv < 1e-6f) snv = cs.s.avg_h_power / 31.6f;
+            const float den = h_power + snv;
+            if (den < 1e-10f) { e = make_float2(0.f, 0.f); nvv = 100.0f; }
+            else { e = cdivf(cmul(rx, cconj(h)), den); nvv = snv / (h_power + snv); }
+            if (h_power < fade_threshold) nvv = 100.0f;
+            nvv = std_max(1e-6f, std_min(100.0f, nvv));
+        } else {
+            const float den = h_power + cs.s.noise_var;
+            if (den < 1e-10f) { e = make_float2(0.f, 0.f); nvv = 100.0f; }
+            else {
+                e = cdivf(cmul(cconj(h), rx), den);
+                nvv = cs.s.noise_var / den;
+                nvv = std_max(1e-6f, std_min(100.0f, nvv));
+            }
+            if (h_power < fade_threshold) nvv = 100.0f;
+            // decision-directed phase error for the next symbol (:1413-1448)
+            if (dd_mod && cs.s.snr_count >= 2) {
+                float mag_thr = 0.3f, ph_thr = 0.61f;
+                if (mod == RIA_QAM16) { mag_thr = 0.25f; ph_thr = 0.44f; }
+                else if (mod == RIA_QAM32 || mod == RIA_QAM64) { mag_thr = 0.20f; ph_thr = 0.35f; }
+                float ddv = 0.0f;
+                if (!(cabs(e) < mag_thr)) {
+                    const float2 dec = hard_decision(e, mod);
+                    const float perr = carg(cmul(e, cconj(dec)));
+                    if (fabsf(perr) < ph_thr) ddv = -perr;
+                }
+                cs.dd[i] = ddv;
+            }
+        }
+        cs.eq[i] = e;
+        cs.cnv[i] = nvv;
+    }
+    if (g == 0 && dd_mod && cs.s.snr_count >= 2) cs.s.have_dd = 1;
+    gsync<G>();
+
+    // ----------------------- demodulateSymbol (demodulator.cpp:208-508) -----------------------
+    for (int i = g; i < nd; i += G) {
+        const float2 sym = cs.eq[i];
+        // per-carrier |eq| EMA / variance (:240-254)
+        const float mag = cabs(sym);
+        float ema, var;
+        if (first) { ema = mag; var = 0.0f; }
+        else {
+            ema = cs.ema[i]; var = cs.var[i];
+            const float delta = mag - ema;
+            ema += 0.3f * delta;
+            var += 0.3f * (delta * delta - var);
+        }
+        cs.ema[i] = ema; cs.var[i] = var;
+        float nv = cs.cnv[i] * ce_margin(mod);
+        {
+            const float mean_sq = ema * ema + 1e-6f;
+            const float norm_var = var / mean_sq;
+            nv *= (1.0f + 10.0f * norm_var);
+        }
+        float* out = llr_out + sd * llr_per_sym + i * bpc;
+        switch (mod) {
+            case RIA_DBPSK: {                                 // demapDBPSK, soft_demap.hpp:172-193
+                const float2 prev = first ? make_float2(1.0f, 0.0f) : cs.prev_eq[i];
+                const float2 diff = cmul(sym, cconj(prev));
+                const float pd = atan2_rn(diff.y, diff.x);
+                const float sp = mag * cabs(prev);
+                float l = 0.0f;
+                if (!(sp < 1e-6f)) {
+                    const float dnv = 2.0f * nv;
+                    const float conf = 2.0f * sp / dnv;
+                    l = clip_llr(conf * cos_rn(pd));
+                }
+                out[0] = l;
+                cs.prev_eq[i] = sym;
+                break;
+            }
+            case RIA_DQPSK: {                                 // demapDQPSK, soft_demap.hpp:199-235
+                const float2 prev = first ? make_float2(1.0f, 0.0f) : cs.prev_eq[i];
+                const float2 diff = cmul(sym, cconj(prev));
+                const float dmag = cabs(diff);
+                float l0 = 0.0f, l1 = 0.0f;
+                if (!(dmag < 1e-6f)) {
+                    const float dnv = 2.0f * nv;
+                    const float sp = mag * cabs(prev);
+                    const float snr = sp / dnv;
+                    const float scale = 2.0f * sqrtf(snr);
+                    const float pi = 3.14159265358979f;
+                    const float ph = atan2_rn(diff.y, diff.x);
+                    l0 = clip_llr(scale * sin_rn(ph + pi / 4));
+                    l1 = clip_llr(scale * (fabsf(diff.x) - fabsf(diff.y)) / dmag);
+                }
+                out[0] = l0; out[1] = l1;
+                cs.prev_eq[i] = sym;
+                break;
+            }
+            case RIA_BPSK:                                    // soft_demap.hpp:37-39
+                out[0] = clip_llr(-2.0f * sym.x / nv);
+                break;
+            case RIA_QPSK: {                                  // soft_demap.hpp:42-45
+                const float scale = -2.0f * 0.7071067811865476f / nv;
+                out[0] = clip_llr(sym.x * scale); out[1] = clip_llr(sym.y * scale);
+                break;
+            }
+            case RIA_QAM16: {                                 // soft_demap.hpp:49-64
+                const float scale = 2.0f / nv, T = 0.6324555320336759f;
+                out[0] = clip_llr(-scale * sym.x);
+                out[1] = clip_llr(scale * (fabsf(sym.x) - T));
+                out[2] = clip_llr(-scale * sym.y);
+                out[3] = clip_llr(scale * (fabsf(sym.y) - T));
+                break;
+            }
+            case RIA_QAM32: {
+                float l[5];
+                demap_qam32(sym, nv, l);
+#pragma unroll
+                for (int b = 0; b < 5; ++b) out[b] = l[b];
+                break;
+            }
+            case RIA_QAM64: {                                 // soft_demap.hpp:125-142
+                const float scale = 2.0f / nv, D2 = 0.3086067f, D4 = 0.6172134f;
+                const float I = sym.x, Q = sym.y;
+                out[0] = clip_llr(-scale * I);
+                out[1] = clip_llr(scale * (fabsf(I) - D4));
+                out[2] = clip_llr(scale * (fabsf(fabsf(I) - D4) - D2));
+                out[3] = clip_llr(-scale * Q);
+                out[4] = clip_llr(scale * (fabsf(Q) - D4));
+                out[5] = clip_llr(scale * (fabsf(fabsf(Q) - D4) - D2));
+                break;
+            }
+            case RIA_QAM256: {                                // soft_demap.hpp:145-164
+                const float scale = 2.0f / nv, D2 = 0.1290994f, D4 = 0.2581989f, D8 = 0.5163978f;
+                const float I = sym.x, Q = sym.y;
+                out[0] = clip_llr(-scale * I);
+                out[1] = clip_llr(scale * (fabsf(I) - D8));
+                out[2] = clip_llr(scale * (fabsf(fabsf(I) - D8) - D4));
+                out[3] = clip_llr(scale * (fabsf(fabsf(fabsf(I) - D8) - D4) - D2));
+                out[4] = clip_llr(-scale * Q);
+                out[5] = clip_llr(scale * (fabsf(Q) - D8));
+                out[6] = clip_llr(scale * (fabsf(fabsf(Q) - D8) - D4));
+                out[7] = clip_llr(scale * (fabsf(fabsf(fabsf(Q) - D8) - D4) - D2));
+                break;
+            }
+            default: break;
+        }
+    }
+    gsync<G>();
+}
+
+// per-frame outputs: soft-bit count, zero padding, SNR, CFO, fading index
+template <int G>
+__device__ __forceinline__ void frame_outputs(CarState& cs, const OfdmCarrierTable& car, const KernelArgs& a,
+                                              long long f, int n_data_sym, int g) {
+    const int nd = car.n_data;
+    const int n_llr = (n_data_sym > 0 ? n_data_sym : 0) * nd * a.bits_per_carrier;
+    float* llr_out = a.llr + f * a.llr_stride;
+    for (int i = n_llr + g; i < a.llr_stride; i += G) llr_out[i] = 0.0f;
+    for (int i = g; i < nd; i += G) cs.tmpf[i] = cabs(cs.H[car.data_car[i]]);
+    gsync<G>();
+    if (g == 0) {
+        a.n_llr[f] = n_llr;
+        if (a.snr_db) a.snr_db[f] = 10.0f * log10f(cs.s.snr_lin);                  // getEstimatedSNR
+        if (a.cfo_out) a.cfo_out[f] = cs.s.cfo_hz;                                 // getFrequencyOffset
+        if (a.fading) {                                                            // getFadingIndex, :1168-1199
+            float sum = 0.f;
+            for (int i = 0; i < nd; ++i) sum += cs.tmpf[i];
+            const float mean = sum / static_cast<float>(nd);
+            float fi = 0.0f;
+            if (!(mean < 0.001f)) {
+                float vs = 0.f;
+                for (int i = 0; i < nd; ++i) { const float d = cs.tmpf[i] - mean; vs += d * d; }
+                fi = sqrtf(vs / static_cast<float>(nd)) / mean;
+            }
+            a.fading[f] = fi;
+        }
+    }
+    gsync<G>();
+}
+
+// ======================================= FFT ================================================
+// XOR-swizzled 32x32 transpose: conflict-free for all four FFT passes (see DESIGN.md).
+__device__ __forceinline__ int fft_addr(int j) { return ((j & 31) << 5) | (((j >> 5) ^ j) & 31); }
+// stage-major twiddle table: tw_L[k] = W[k * (1024 / L)], k < L/2, stored at offset L/2 - 2
+__device__ __forceinline__ int tw_off(int L) { return (L >> 1) - 2; }
+
+// one radix-2 DIT butterfly exactly as fft.cpp:115-119:  t = w * b;  b = a - t;  a = a + t
+__device__ __forceinline__ void bfly(float2& a, float2& b, float2 w) {
+    const float2 t = cmul(w, b);
+    b = csub(a, t);
+    a = cadd(a, t);
+}
+// k = 0: w = (1, -0); multiplying by it is value-exact, so the product is skipped
+__device__ __forceinline__ void bfly0(float2& a, float2& b) {
+    const float2 t = b;
+    b = csub(a, t);
+    a = cadd(a, t);
+}
+// one output of a butterfly: a + t (upper half of the block) or a - t (lower half).  a - t and
+// a + (-t) are the same IEEE operation, so the sign is folded into t.
+__device__ __forceinline__ float2 bfly_half(float2 a, float2 b, float2 w, unsigned neg) {
+    float2 t = cmul(w, b);
+    t.x = __uint_as_float(__float_as_uint(t.x) ^ neg);
+    t.y = __uint_as_float(__float_as_uint(t.y) ^ neg);
+    return cadd(a, t);
+}
+
+struct FftTile {
+    float re[kFft];
+    float im[kFft];
+};
+
+// passes 1 and 2 (stages L = 2 .. 64) on the 8 mixed samples each thread holds; v[t] = baseband
+// sample (tid + 128 * brev3(t)) of the FFT window.  Leaves the stage-64 result in the tile.
+__device__ __forceinline__ void fft_stages_2_to_64(FftTile& ft, const float2* __restrict__ tw, float2 (&v)[8], int tid) {
+    // ---- pass 1: stages L = 2, 4, 8 on data[8g .. 8g+7], g = brev7(tid) ----
+    bfly0(v[0], v[1]); bfly0(v[2], v[3]); bfly0(v[4], v[5]); bfly0(v[6], v[7]);
+    {
+        const float2 w1 = tw[tw_off(4) + 1];
+        bfly0(v[0], v[2]); bfly(v[1], v[3], w1);
+        bfly0(v[4], v[6]); bfly(v[5], v[7], w1);
+        const float2 x1 = tw[tw_off(8) + 1], x2 = tw[tw_off(8) + 2], x3 = tw[tw_off(8) + 3];
+        bfly0(v[0], v[4]); bfly(v[1], v[5], x1); bfly(v[2], v[6], x2); bfly(v[3], v[7], x3);
+    }
+    {
+        const int g = __brev(static_cast<unsigned>(tid)) >> 25;      // brev7
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int ad = fft_addr((g << 3) | t);
+            ft.re[ad] = v[t].x; ft.im[ad] = v[t].y;
+        }
+    }
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    // ---- pass 2: stages L = 16, 32, 64; thread owns bits j5..j3 ----
+    {
+        const int lo = (warp << 1) | (lane & 1);                      // j2 j1 j0
+        const int hi = lane >> 1;                                     // j9..j6
+        const int jb = (hi << 6) | lo;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 3)); v[u] = make_float2(ft.re[ad], ft.im[ad]); }
+        const float2 w16 = tw[tw_off(16) + lo];
+        if (lo == 0) { bfly0(v[0], v[1]); bfly0(v[2], v[3]); bfly0(v[4], v[5]); bfly0(v[6], v[7]); }
+        else { bfly(v[0], v[1], w16); bfly(v[2], v[3], w16); bfly(v[4], v[5], w16); bfly(v[6], v[7], w16); }
+        const float2 w32a = tw[tw_off(32) + lo], w32b = tw[tw_off(32) + 8 + lo];
+        if (lo == 0) { bfly0(v[0], v[2]); bfly0(v[4], v[6]); } else { bfly(v[0], v[2], w32a); bfly(v[4], v[6], w32a); }
+        bfly(v[1], v[3], w32b); bfly(v[5], v[7], w32b);
+        if (lo == 0) bfly0(v[0], v[4]); else bfly(v[0], v[4], tw[tw_off(64) + lo]);
+        bfly(v[1], v[5], tw[tw_off(64) + 8 + lo]);
+        bfly(v[2], v[6], tw[tw_off(64) + 16 + lo]);
+        bfly(v[3], v[7], tw[tw_off(64) + 24 + lo]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 3)); ft.re[ad] = v[u].x; ft.im[ad] = v[u].y; }
+    }
+    __syncthreads();
+}
+
+// pass 3 (stages L = 128, 256, 512, all bins) and pass 4 (stage 1024, carriers only): the
+// general path, used by the monolithic kernel and when the bins do not allow pruning.
+__device__ __forceinline__ void fft_stages_128_to_1024_full(FftTile& ft, const float2* __restrict__ tw,
+                                                            const OfdmCarrierTable& car, float2* __restrict__ bin_out,
+                                                            int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    float2 v[8];
+    {
+        const int lo6 = ((warp & 1) << 5) | lane;                     // j5..j0
+        const int jb = ((warp >> 1) << 9) | lo6;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 6)); v[u] = make_float2(ft.re[ad], ft.im[ad]); }
+        const float2 w128 = tw[tw_off(128) + lo6];
+        if (lo6 == 0) { bfly0(v[0], v[1]); bfly0(v[2], v[3]); bfly0(v[4], v[5]); bfly0(v[6], v[7]); }
+        else { bfly(v[0], v[1], w128); bfly(v[2], v[3], w128); bfly(v[4], v[5], w128); bfly(v[6], v[7], w128); }
+        const float2 w256a = tw[tw_off(256) + lo6], w256b = tw[tw_off(256) + 64 + lo6];
+        if (lo6 == 0) { bfly0(v[0], v[2]); bfly0(v[4], v[6]); } else { bfly(v[0], v[2], w256a); bfly(v[4], v[6], w256a); }
+        bfly(v[1], v[3], w256b); bfly(v[5], v[7], w256b);
+        if (lo6 == 0) bfly0(v[0], v[4]); else bfly(v[0], v[4], tw[tw_off(512) + lo6]);
+        bfly(v[1], v[5], tw[tw_off(512) + 64 + lo6]);
+        bfly(v[2], v[6], tw[tw_off(512) + 128 + lo6]);
+        bfly(v[3], v[7], tw[tw_off(512) + 192 + lo6]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 6)); ft.re[ad] = v[u].x; ft.im[ad] = v[u].y; }
+    }
+    __syncthreads();
+    if (tid < car.num_carriers) {
+        const int f = car.fft_idx[tid];
+        const int k = f & 511;
+        const int a0 = fft_addr(k), a1 = fft_addr(k + 512);
+        float2 x0 = make_float2(ft.re[a0], ft.im[a0]);
+        float2 x1 = make_float2(ft.re[a1], ft.im[a1]);
+        if (k == 0) bfly0(x0, x1); else bfly(x0, x1, tw[tw_off(1024) + k]);
+        bin_out[tid] = (f < 512) ? x0 : x1;
+    }
+    __syncthreads();
+}
+
+// Per-thread constants of the pruned last four stages.  Thread (j9 = warp >> 1, r = j5..j0)
+// follows the one bin k with k mod 64 == r (if any) through stages 128..512 of its half, and the
+// j9 = 0 thread finishes stage 1024.
+struct PrunedPlan {
+    int carrier;            // logical carrier of bin k, -1 = residue unused
+    float2 w128, w256, w512, w1024;
+    unsigned n128, n256, n512, n1024;     // sign masks: bit (log2 L - 1) of k selects a - t
+};
+
+__device__ __forceinline__ PrunedPlan make_pruned_plan(const float2* __restrict__ tw, const short* res_car,
+                                                       const short* res_k, int r) {
+    PrunedPlan p;
+    p.carrier = res_car[r];
+    const int k = p.carrier >= 0 ? res_k[r] : r;
+    p.w128 = tw[tw_off(128) + (k & 63)];
+    p.w256 = tw[tw_off(256) + (k & 127)];
+    p.w512 = tw[tw_off(512) + (k & 255)];
+    p.w1024 = tw[tw_off(1024) + (k & 511)];
+    p.n128 = (k & 64) ? 0x80000000u : 0u;
+    p.n256 = (k & 128) ? 0x80000000u : 0u;
+    p.n512 = (k & 256) ? 0x80000000u : 0u;
+    p.n1024 = (k & 512) ? 0x80000000u : 0u;
+    return p;
+}
+
+__device__ __forceinline__ void fft_stages_128_to_1024_pruned(FftTile& ft, float2* xch, const PrunedPlan& p,
+                                                              float2* __restrict__ bin_out, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int r = ((warp & 1) << 5) | lane;
+    const int j9 = warp >> 1;
+    float2 x = make_float2(0.f, 0.f);
+    if (p.carrier >= 0) {
+        const int jb = (j9 << 9) | r;
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 6)); v[u] = make_float2(ft.re[ad], ft.im[ad]); }
+        const float2 y0 = bfly_half(v[0], v[1], p.w128, p.n128);
+        const float2 y1 = bfly_half(v[2], v[3], p.w128, p.n128);
+        const float2 y2 = bfly_half(v[4], v[5], p.w128, p.n128);
+        const float2 y3 = bfly_half(v[6], v[7], p.w128, p.n128);
+        const float2 z0 = bfly_half(y0, y1, p.w256, p.n256);
+        const float2 z1 = bfly_half(y2, y3, p.w256, p.n256);
+        x = bfly_half(z0, z1, p.w512, p.n512);
+        if (j9) xch[r] = x;
+    }
+    __syncthreads();
+    if (p.carrier >= 0 && j9 == 0) bin_out[p.carrier] = bfly_half(x, xch[r], p.w1024, p.n1024);
+}
+
+// mixer + CFO phase increment exactly as channel_equalizer.cpp:103
+__device__ __forceinline__ float cfo_phase_inc(float cfo_hz, int sample_rate) {
+    return static_cast<float>(-2.0f * M_PI * static_cast<double>(cfo_hz) /
+                              static_cast<double>(static_cast<unsigned>(sample_rate)));
+}
+
+// ------------------------------- stage 0: CFO phase scan -----------------------------------
+// One warp per frame: value of the fp32 phase accumulator (channel_equalizer.cpp:132-144) before
+// every 32nd sample of the frame.  Frames without a usable CFO are skipped (never read).
+__global__ void ofdm_phase_scan_kernel(const float* __restrict__ cfo_hz, const float* __restrict__ phase0,
+                                       long long frame_begin, long long n_local, int n_blocks, int sample_rate,
+                                       float* __restrict__ block_phase /*[n_local][n_blocks]*/) {
+    const long long w = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_local) return;
+    const long long f = frame_begin + w;
+    const float cfo = cfo_hz[f];
+    if (!(fabsf(cfo) > 0.01f)) return;
+    const float inc = cfo_phase_inc(cfo, sample_rate);
+    float base = phase0 ? phase0[f] : 0.0f;
+    float* out = block_phase + w * n_blocks;
+    for (int b = 0; b < n_blocks; ++b) {
+        if (lane == 0) out[b] = base;
+        float next;
+        (void)cfo_phase_block32(base, inc, lane, &next);
+        base = next;
+    }
+}
+
+// ------------------------------- stage 1: mix + FFT ----------------------------------------
+struct FftSmem {
+    float2 tw[kTwCount];
+    float2 nco[kFft];           // conj(mixer phasor) over the FFT window of the current symbol
+    FftTile ft;
+    float2 xch[64];
+    OfdmCarrierTable car;
+    short res_car[64];
+    short res_k[64];
+};
+
+template <bool PRUNED>
 __global__ void __launch_bounds__(kThreads, 8)
-ofdm_presynced_kernel(const KernelArgs a) {
+ofdm_fft_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    FftSmem& sm = *reinterpret_cast<FftSmem*>(smem_raw);
+    __shared__ unsigned int item_sh;
     const int tid = threadIdx.x;
 
     for (int i = tid; i < kTwCount; i += kThreads) sm.tw[i] = a.tw_g[i];
@@ -356,488 +946,262 @@ ofdm_presynced_kernel(const KernelArgs a) {
         int* dst = reinterpret_cast<int*>(&sm.car);
         for (int i = tid; i < static_cast<int>(sizeof(OfdmCarrierTable) / 4); i += kThreads) dst[i] = src[i];
     }
-    __shared__ long long frame_sh;
+    if (tid < 64) { sm.res_car[tid] = -1; sm.res_k[tid] = 0; }
     __syncthreads();
+    const int nc = sm.car.num_carriers;
+    if (tid < nc) {
+        const int k = sm.car.fft_idx[tid];
+        sm.res_car[k & 63] = static_cast<short>(tid);
+        sm.res_k[k & 63] = static_cast<short>(k);
+    }
+    __syncthreads();
+    PrunedPlan plan;
+    if (PRUNED) plan = make_pruned_plan(sm.tw, sm.res_car, sm.res_k, (((tid >> 5) & 1) << 5) | (tid & 31));
 
-    const int nc = sm.car.num_carriers, nd = sm.car.n_data, np = sm.car.n_pilot;
-    const int mod = a.modulation;
-    const bool differential = a.differential != 0;
-    const int bpc = a.bits_per_carrier;
-    const int n_sym_total = a.frame_len / a.sym_len;
-    const int n_data_sym = n_sym_total - 2;
-    const int llr_per_sym = nd * bpc;
+    const int n_sym = a.frame_len / a.sym_len;
+    const long long n_local = a.frame_end - a.frame_begin;
+    const unsigned n_groups = static_cast<unsigned>((n_local + kFftGroup - 1) / kFftGroup);
+    const unsigned n_items = n_groups * static_cast<unsigned>(n_sym);
+    int cur_sym = -1;
 
     for (;;) {
-        if (tid == 0) frame_sh = static_cast<long long>(atomicAdd(a.counter, 1u));
+        if (tid == 0) item_sh = atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const unsigned item = item_sh;
+        __syncthreads();
+        if (item >= n_items) break;
+        const int s = static_cast<int>(item / n_groups);
+        const unsigned grp = item % n_groups;
+        const int win = s * a.sym_len + a.cp;               // first sample of the FFT window
+        if (s != cur_sym) {
+            const float2* src = a.nco_g + win;
+            for (int i = tid; i < kFft; i += kThreads) { const float2 o = __ldg(src + i); sm.nco[i] = make_float2(o.x, -o.y); }
+            cur_sym = s;
+            __syncthreads();
+        }
+        const long long f0 = a.frame_begin + static_cast<long long>(grp) * kFftGroup;
+        const long long f1 = (f0 + kFftGroup < a.frame_end) ? f0 + kFftGroup : a.frame_end;
+
+        float nxt[8];
+        {
+            const float* p = a.samples + f0 * a.frame_stride + win + tid;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) nxt[q] = __ldcs(p + 128 * q);
+        }
+        for (long long f = f0; f < f1; ++f) {
+            // ---- mix: v[t] = baseband sample (tid + 128 * brev3(t)) of the FFT window ----
+            float2 v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int q = ((t & 1) << 2) | (t & 2) | ((t & 4) >> 2);      // brev3
+                const float2 osc = sm.nco[tid + 128 * q];
+                // samples[i] * conj(osc)  ->  (osc.re * s, (-osc.im) * s)
+                v[t] = make_float2(__fmul_rn(osc.x, nxt[q]), __fmul_rn(osc.y, nxt[q]));
+            }
+            if (f + 1 < f1) {
+                const float* p = a.samples + (f + 1) * a.frame_stride + win + tid;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) nxt[q] = __ldcs(p + 128 * q);
+            }
+            if (a.cfo_hz) {
+                const float cfo = a.cfo_hz[f];
+                if (fabsf(cfo) > 0.01f) {
+                    const float inc = cfo_phase_inc(cfo, a.sample_rate);
+                    const float* bp = a.block_phase + (f - a.frame_begin) * a.n_blocks;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int q = ((t & 1) << 2) | (t & 2) | ((t & 4) >> 2);
+                        const int n = win + tid + 128 * q;
+                        const float ph = cfo_phase_at(bp[n >> 5], inc, n & 31);
+                        v[t] = cmul(v[t], cexpj(ph));
+                    }
+                }
+            }
+            fft_stages_2_to_64(sm.ft, sm.tw, v, tid);
+            float2* out = a.bins + ((f - a.bins_frame0) * n_sym + s) * nc;
+            if (PRUNED) fft_stages_128_to_1024_pruned(sm.ft, sm.xch, plan, out, tid);
+            else        fft_stages_128_to_1024_full(sm.ft, sm.tw, sm.car, out, tid);
+        }
+    }
+}
+
+// ------------------------------- stage 2: carriers -----------------------------------------
+struct CarSmem {
+    OfdmCarrierTable car;
+    CarState cs[kCarWarps];
+};
+
+__global__ void __launch_bounds__(kCarWarps * 32)
+ofdm_carrier_kernel(const KernelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CarSmem& sm = *reinterpret_cast<CarSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const int* src = reinterpret_cast<const int*>(a.car_g);
+        int* dst = reinterpret_cast<int*>(&sm.car);
+        for (int i = tid; i < static_cast<int>(sizeof(OfdmCarrierTable) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const OfdmCarrierTable& car = sm.car;
+    CarState& cs = sm.cs[warp];
+    const int nc = car.num_carriers;
+    const int n_sym = a.frame_len / a.sym_len;
+    const int n_data_sym = n_sym - 2;
+    const int llr_per_sym = car.n_data * a.bits_per_carrier;
+    (void)llr_per_sym;
+
+    for (;;) {
+        long long f = 0;
+        if (lane == 0) f = a.frame_begin + static_cast<long long>(atomicAdd(a.counter, 1u));
+        f = __shfl_sync(0xffffffffu, f, 0);
+        if (f >= a.frame_end) break;
+        if (n_sym < 2) { frame_too_short<32>(a, f, lane); continue; }
+        const float2* fb = a.bins + (f - a.bins_frame0) * n_sym * nc;
+
+        frame_reset<32>(cs, a, f, lane);
+        // ---- LTS: estimateChannelFromLTS (channel_equalizer.cpp:193-643) ----
+        for (int s = 0; s < 2; ++s) {
+            for (int c = lane; c < nc; c += 32) cs.bin[c] = fb[s * nc + c];
+            __syncwarp();
+            lts_symbol<32>(cs, car, s, lane);
+        }
+        if (lts_residual<32>(cs, car, a, lane)) {
+            // the reference now re-mixes the frame with the corrected CFO: hand it over
+            if (lane == 0) a.rerun_list[atomicAdd(a.rerun_count, 1u)] = static_cast<int>(f - a.frame_begin);
+            continue;
+        }
+        lts_finish<32>(cs, car, a, f, lane);
+        // ---- data symbols (demodulator.cpp:1361-1382) ----
+        float* llr_out = a.llr + f * a.llr_stride;
+        float2 nb0 = make_float2(0.f, 0.f), nb1 = nb0;
+        if (n_data_sym > 0) {
+            if (lane < nc) nb0 = fb[2 * nc + lane];
+            if (lane + 32 < nc) nb1 = fb[2 * nc + lane + 32];
+        }
+        for (int sd = 0; sd < n_data_sym; ++sd) {
+            if (lane < nc) cs.bin[lane] = nb0;
+            if (lane + 32 < nc) cs.bin[lane + 32] = nb1;
+            __syncwarp();
+            if (sd + 1 < n_data_sym) {          // prefetch the next symbol's bins
+                if (lane < nc) nb0 = fb[(3 + sd) * nc + lane];
+                if (lane + 32 < nc) nb1 = fb[(3 + sd) * nc + lane + 32];
+            }
+            data_symbol<32>(cs, car, a, llr_out, sd, lane);
+        }
+        frame_outputs<32>(cs, car, a, f, n_data_sym, lane);
+    }
+}
+
+// ------------------------------- monolithic kernel -----------------------------------------
+// FFT + carriers of one frame in one CTA.  Serves the frames the carrier kernel handed over
+// (residual CFO re-run); `rerun_list == nullptr` runs every frame of [frame_begin, frame_end).
+struct MonoSmem {
+    float2 tw[kTwCount];
+    FftTile ft;
+    float cph[kMaxSymLen];
+    OfdmCarrierTable car;
+    CarState cs;
+};
+
+// Mix + CFO-correct + FFT one symbol (absolute symbol index `sym` inside the frame) and leave
+// the carrier bins in sm.cs.bin[c].  channel_equalizer.cpp:99-187 + fft.cpp:96-128.
+__device__ void mono_fft_symbol(MonoSmem& sm, const KernelArgs& a, const float* __restrict__ frame, int sym) {
+    const int tid = threadIdx.x;
+    const int base = sym * a.sym_len;
+    const bool cfo_on = fabsf(sm.cs.s.cfo_hz) > 0.01f;
+
+    if (cfo_on) {
+        // freq_correction_phase is an fp32 accumulator with a double-promoted wrap
+        // (channel_equalizer.cpp:103, 132-144); its rounding is part of the result
+        if (tid < 32) {
+            const float inc = cfo_phase_inc(sm.cs.s.cfo_hz, a.sample_rate);
+            float ph0 = sm.cs.s.cfo_phase;
+            for (int b = 0; b < a.sym_len; b += 32) {
+                float next;
+                const float mine = cfo_phase_block32(ph0, inc, tid, &next);
+                if (b + tid < a.sym_len) sm.cph[b + tid] = mine;
+                if (b + 32 <= a.sym_len) ph0 = next;
+                else ph0 = __shfl_sync(0xffffffffu, mine, a.sym_len - b);     // ragged tail: phase before sample sym_len
+            }
+            if (tid == 0) sm.cs.s.cfo_phase = ph0;
+        }
+        __syncthreads();
+    }
+
+    float2 v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int q = ((t & 1) << 2) | (t & 2) | ((t & 4) >> 2);      // brev3
+        const int i = a.cp + tid + 128 * q;                           // index inside the symbol
+        const float s = __ldcs(frame + base + i);
+        const float2 osc = __ldg(a.nco_g + base + i);
+        // samples[i] * conj(osc)  ->  (osc.re * s, (-osc.im) * s)
+        float2 m = make_float2(__fmul_rn(osc.x, s), __fmul_rn(-osc.y, s));
+        if (cfo_on) m = cmul(m, cexpj(sm.cph[i]));
+        v[t] = m;
+    }
+    fft_stages_2_to_64(sm.ft, sm.tw, v, tid);
+    fft_stages_128_to_1024_full(sm.ft, sm.tw, sm.car, sm.cs.bin, tid);
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+ofdm_presynced_kernel(const KernelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MonoSmem& sm = *reinterpret_cast<MonoSmem*>(smem_raw);
+    __shared__ long long frame_sh;
+    const int tid = threadIdx.x;
+    if (a.rerun_list && *a.rerun_count == 0) return;          // the usual case: nothing handed over
+
+    for (int i = tid; i < kTwCount; i += kThreads) sm.tw[i] = a.tw_g[i];
+    {
+        const int* src = reinterpret_cast<const int*>(a.car_g);
+        int* dst = reinterpret_cast<int*>(&sm.car);
+        for (int i = tid; i < static_cast<int>(sizeof(OfdmCarrierTable) / 4); i += kThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    const OfdmCarrierTable& car = sm.car;
+    CarState& cs = sm.cs;
+    const int nc = car.num_carriers;
+    const int n_sym = a.frame_len / a.sym_len;
+    const int n_data_sym = n_sym - 2;
+
+    for (;;) {
+        if (tid == 0) {
+            const unsigned i = atomicAdd(a.counter, 1u);
+            long long f = -1;
+            if (a.rerun_list) { if (i < *a.rerun_count) f = a.frame_begin + a.rerun_list[i]; }
+            else if (a.frame_begin + i < a.frame_end) f = a.frame_begin + i;
+            frame_sh = f;
+        }
         __syncthreads();
         const long long f = frame_sh;
         __syncthreads();
-        if (f >= a.n_frames) break;
+        if (f < 0) break;
         const float* frame = a.samples + f * a.frame_stride;
-        float* llr_out = a.llr + f * a.llr_stride;
+        if (n_sym < 2) { frame_too_short<kThreads>(a, f, tid); continue; }
 
-        if (n_sym_total < 2) {       // processPresynced returns false without output
-            if (tid == 0) {
-                a.n_llr[f] = 0;
-                if (a.snr_db) a.snr_db[f] = 0.0f;
-                if (a.cfo_out) a.cfo_out[f] = a.cfo_hz ? a.cfo_hz[f] : 0.0f;
-                if (a.fading) a.fading[f] = 0.0f;
-            }
-            for (int i = tid; i < a.llr_stride; i += kThreads) llr_out[i] = 0.0f;
-            continue;
-        }
-
-        // ---- state reset (demodulator.cpp:1264-1300) ----
-        if (tid == 0) {
-            sm.s.cfo_hz = a.cfo_hz ? a.cfo_hz[f] : 0.0f;
-            sm.s.cfo_phase = a.phase ? a.phase[f] : 0.0f;
-            sm.s.phase_start = sm.s.cfo_phase;
-            sm.s.noise_var = 0.1f;
-            sm.s.snr_lin = 1.0f;
-            sm.s.slope = 0.0f;
-            sm.s.cpc = make_float2(1.0f, 0.0f);
-            sm.s.cpc_init = 0;
-            sm.s.snr_count = 0;
-            sm.s.rerun = 0;
-            sm.s.have_prev_pilot = 0;
-            sm.s.have_dd = 0;
-        }
-        if (tid < kMaxCarriers) sm.H[tid] = make_float2(1.0f, 0.0f);
-        __syncthreads();
-
-        // =============== LTS: estimateChannelFromLTS (channel_equalizer.cpp:193-643) ===============
+        frame_reset<kThreads>(cs, a, f, tid);
+        // ---- LTS: estimateChannelFromLTS (channel_equalizer.cpp:193-643) ----
         for (int pass = 0; pass < 2; ++pass) {
             for (int s = 0; s < 2; ++s) {
-                fft_symbol(sm, a, frame, s);
-                if (tid < nc) {
-                    const int sub = sm.car.sub_idx[tid];
-                    const float2 tx = sm.car.is_pilot[tid] ? make_float2(sm.car.pilot_sign[sub], 0.0f)
-                                                           : sm.car.tx_data[sub];
-                    sm.hps[s][tid] = cdiv(sm.bin[tid], tx);          // H = rx / tx  (:264, :278)
-                    if (a.bins_tap)
-                        reinterpret_cast<float2*>(a.bins_tap)[(f * n_sym_total + s) * nc + tid] = sm.bin[tid];
-                }
-                __syncthreads();
+                mono_fft_symbol(sm, a, frame, s);
+                if (a.bins_tap && tid < nc)
+                    reinterpret_cast<float2*>(a.bins_tap)[(f * n_sym + s) * nc + tid] = cs.bin[tid];
+                lts_symbol<kThreads>(cs, car, s, tid);
             }
             if (pass == 1) break;
-            // residual CFO from the phase rotation between the two LTS symbols (:304-382)
-            if (tid < nd) {
-                const int c = sm.car.data_car[tid];
-                const float2 h0 = sm.hps[0][c], h1 = sm.hps[1][c];
-                int ok = 0;
-                if (cabs(h0) > 0.01f && cabs(h1) > 0.01f) {
-                    const float2 diff = cmul(h1, cconj(h0));
-                    const float mag = cabs(diff);
-                    if (mag > 1e-6f) { sm.tmpc[tid] = cdivf(diff, mag); ok = 1; }
-                }
-                sm.flag[tid] = ok;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                float2 sum = make_float2(0.f, 0.f);
-                int valid = 0;
-                for (int i = 0; i < nd; ++i) if (sm.flag[i]) { sum = cadd(sum, sm.tmpc[i]); ++valid; }
-                int rerun = 0;
-                if (valid > 10) {
-                    const float avg_phase = atan2_rn(sum.y, sum.x);
-                    const float symbol_duration = static_cast<float>(a.sym_len) / static_cast<float>(static_cast<unsigned>(a.sample_rate));
-                    const float residual = static_cast<float>(static_cast<double>(avg_phase) /
-                                                              (2.0f * M_PI * static_cast<double>(symbol_duration)));
-                    if (fabsf(residual) > 0.3f && fabsf(residual) < 5.0f) {
-                        sm.s.cfo_hz = __fadd_rn(sm.s.cfo_hz, residual);
-                        sm.s.cfo_phase = sm.s.phase_start;            // :341
-                        rerun = 1;
-                    }
-                }
-                sm.s.rerun = rerun;
-            }
-            __syncthreads();
-            if (!sm.s.rerun) break;
+            if (!lts_residual<kThreads>(cs, car, a, tid)) break;
         }
-        // channel estimate := last LTS symbol (:387-404)
-        if (tid < nc) {
-            sm.H[tid] = sm.hps[1][tid];
-        }
-        __syncthreads();
-        // phase slope across adjacent carriers (:412-437)
-        if (tid < nc - 1) {
-            const float2 h0 = sm.H[tid], h1 = sm.H[tid + 1];
-            int ok = 0;
-            if (cabs(h0) > 0.01f && cabs(h1) > 0.01f) {
-                const float2 diff = cmul(h1, cconj(h0));
-                const float mag = cabs(diff);
-                if (mag > 1e-6f) { sm.tmpc[tid] = cdivf(diff, mag); ok = 1; }
-            }
-            sm.flag[tid] = ok;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            float2 sum = make_float2(0.f, 0.f);
-            int cnt = 0;
-            for (int i = 0; i < nc - 1; ++i) if (sm.flag[i]) { sum = cadd(sum, sm.tmpc[i]); ++cnt; }
-            if (cnt > 0) sm.s.slope = carg(cdivf(sum, static_cast<float>(cnt)));
-        }
-        __syncthreads();
-        // noise variance / SNR from the two LTS estimates (:457-485)
-        if (tid < nd) {
-            const int c = sm.car.data_car[tid];
-            const float2 h0 = sm.hps[0][c], h1 = sm.hps[1][c];
-            int ok = 0;
-            if (cabs(h0) > 1e-6f && cabs(h1) > 1e-6f) {
-                sm.tmpf[tid] = cnorm(csub(h1, h0));
-                sm.tmpg[tid] = __fdiv_rn(__fadd_rn(cnorm(h0), cnorm(h1)), 2.0f);
-                ok = 1;
-            }
-            sm.flag[tid] = ok;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            float noise_sum = 0.f, signal_sum = 0.f;
-            int cnt = 0;
-            for (int i = 0; i < nd; ++i) if (sm.flag[i]) { noise_sum += sm.tmpf[i]; signal_sum += sm.tmpg[i]; ++cnt; }
-            if (cnt > 0) {
-                const float nvar = noise_sum / (4.0f * cnt);
-                const float sp = signal_sum / cnt;
-                float snr = sp / std_max(nvar, 1e-10f);
-                snr = std_max(3.16f, std_min(10000.0f, snr));
-                sm.s.noise_var = nvar;
-                sm.s.snr_lin = snr;
-            }
-            sm.s.snr_count = 2;                                       // :642
-        }
-        if (a.h_lts_tap && tid < nc) reinterpret_cast<float2*>(a.h_lts_tap)[f * nc + tid] = sm.H[tid];
-        __syncthreads();
-
-        // ======================= data symbols (demodulator.cpp:1361-1382) =======================
+        lts_finish<kThreads>(cs, car, a, f, tid);
+        // ---- data symbols (demodulator.cpp:1361-1382) ----
+        float* llr_out = a.llr + f * a.llr_stride;
         for (int sd = 0; sd < n_data_sym; ++sd) {
-            fft_symbol(sm, a, frame, 2 + sd);
+            mono_fft_symbol(sm, a, frame, 2 + sd);
             if (a.bins_tap && tid < nc)
-                reinterpret_cast<float2*>(a.bins_tap)[(f * n_sym_total + 2 + sd) * nc + tid] = sm.bin[tid];
-            const bool first = (sd == 0);                             // soft_bits.empty()
-
-            // ----------------- updateChannelEstimate (channel_equalizer.cpp:645-1043) -----------------
-            if (np > 0) {
-                float alpha;
-                if (first) alpha = 1.0f; else if (differential) alpha = 0.5f; else alpha = 0.9f;
-                if (tid < np) {
-                    const int c = sm.car.pilot_car[tid];
-                    sm.pil_ls[tid] = cdiv(sm.bin[c], make_float2(sm.car.pilot_sign[tid], 0.0f));   // :687
-                }
-                __syncthreads();
-                if (differential) {
-                    // carrier phase recovery on the first symbol that yields a usable average (:699-714)
-                    if (tid == 0 && !sm.s.cpc_init) {
-                        float2 h_sum = make_float2(0.f, 0.f);
-                        for (int i = 0; i < np; ++i) h_sum = cadd(h_sum, sm.pil_ls[i]);
-                        const float2 h_avg = cdivf(h_sum, static_cast<float>(np));
-                        const float avg_mag = cabs(h_avg);
-                        if (avg_mag > 0.01f) { sm.s.cpc = cdivf(cconj(h_avg), avg_mag); sm.s.cpc_init = 1; }
-                    }
-                    __syncthreads();
-                    if (tid < np) sm.pil_ls[tid] = cmul(sm.pil_ls[tid], sm.s.cpc);
-                    __syncthreads();
-                } else {
-                    // CPE: common phase of pilot LS vs current H, applied to every carrier (:720-756)
-                    if (tid < np) {
-                        const int c = sm.car.pilot_car[tid];
-                        const float2 h_old = sm.H[c];
-                        const float h_old_mag = cabs(h_old);
-                        int ok = 0;
-                        if (h_old_mag > 0.01f) {
-                            const float2 ratio = cmul(sm.pil_ls[tid], cconj(h_old));
-                            const float mag = cabs(ratio);
-                            if (mag > 1e-6f) { sm.tmpc[tid] = cscale(cdivf(ratio, mag), h_old_mag); sm.tmpf[tid] = h_old_mag; ok = 1; }
-                        }
-                        sm.flag[tid] = ok;
-                    }
-                    __syncthreads();
-                    if (tid == 0) {
-                        float2 cpe_sum = make_float2(0.f, 0.f);
-                        float w = 0.f;
-                        for (int i = 0; i < np; ++i) if (sm.flag[i]) { cpe_sum = cadd(cpe_sum, sm.tmpc[i]); w += sm.tmpf[i]; }
-                        int apply = 0;
-                        if (w > 0.01f) {
-                            const float ph = carg(cpe_sum);
-                            if (fabsf(ph) > 0.001f) { sm.s.cpe = cexpj(ph); apply = 1; }
-                        }
-                        sm.s.apply_cpe = apply;
-                    }
-                    __syncthreads();
-                    if (sm.s.apply_cpe && tid < nc) sm.H[tid] = cmul(sm.H[tid], sm.s.cpe);
-                    __syncthreads();
-                }
-                // pilot power, temporal noise count, smoothed update at the pilots (:778-820)
-                if (tid == 0) {
-                    float sp = 0.f;
-                    for (int i = 0; i < np; ++i) sp += cnorm(sm.pil_ls[i]);
-                    sm.s.signal_power = sp / static_cast<float>(np);
-                    int ncount = 0;
-                    float npow = 0.f;
-                    if (sm.s.have_prev_pilot)
-                        for (int i = 0; i < np; ++i) {
-                            const float2 ph = sm.prev_pilot[i], ch = sm.pil_ls[i];
-                            if (cnorm(ph) > 1e-6f && cnorm(ch) > 1e-6f) { npow += cnorm(csub(ch, ph)); ++ncount; }
-                        }
-                    if (ncount == 0) { npow = sm.s.signal_power / 31.6f; ncount = 1; }
-                    // the SNR EMA only looks at (noise_count > 1) and (noise_power_sum > 0) (:1025-1040)
-                    sm.s.noise_count = (npow > 0.0f) ? ncount : 0;
-                }
-                __syncthreads();
-                if (tid < np) {
-                    const int c = sm.car.pilot_car[tid];
-                    const float2 h_old = sm.H[c];
-                    const float2 ls = sm.pil_ls[tid];
-                    if (differential) {
-                        const float new_mag = alpha * cabs(ls) + (1.0f - alpha) * cabs(h_old);
-                        const float2 e = cexpj(carg(h_old));
-                        sm.H[c] = make_float2(new_mag * e.x, new_mag * e.y);              // std::polar
-                    } else {
-                        sm.H[c] = cadd(cscale(ls, alpha), cscale(h_old, 1.0f - alpha));
-                    }
-                    sm.prev_pilot[tid] = ls;                                              // :882
-                }
-                __syncthreads();
-                // interpolation to the data carriers (:885-957)
-                if (!differential) {
-                    if (tid < np) {
-                        const int c = sm.car.pilot_car[tid];
-                        const float ph = -sm.s.slope * static_cast<float>(sm.car.car_k[c]);
-                        sm.desloped[tid] = cmul(sm.H[c], cexpj(ph));
-                    }
-                    __syncthreads();
-                    if (tid < nd) {
-                        const int c = sm.car.data_car[tid];
-                        const int lo = sm.car.interp_lo[tid], hi = sm.car.interp_hi[tid];
-                        const float al = sm.car.interp_alpha[tid];
-                        float2 ih = make_float2(0.f, 0.f);
-                        if (lo >= 0 && hi >= 0) ih = cadd(cscale(sm.desloped[lo], 1.0f - al), cscale(sm.desloped[hi], al));
-                        else if (lo >= 0) ih = sm.desloped[lo];
-                        else if (hi >= 0) ih = sm.desloped[hi];
-                        const float ph = sm.s.slope * static_cast<float>(sm.car.car_k[c]);
-                        float2 h = cmul(ih, cexpj(ph));
-                        // decision-directed phase refinement from the previous symbol (:964-975)
-                        if (sm.s.have_dd && sm.s.snr_count >= 3) {
-                            const float corr = sm.dd[tid];
-                            if (fabsf(corr) > 0.001f) h = cmul(h, cexpj(corr * 0.3f));
-                        }
-                        sm.H[c] = h;
-                    }
-                } else {
-                    if (tid < nd) {
-                        const int c = sm.car.data_car[tid];
-                        const int lo = sm.car.interp_lo[tid], hi = sm.car.interp_hi[tid];
-                        const float al = sm.car.interp_alpha[tid];
-                        float im = 0.0f;
-                        if (lo >= 0 && hi >= 0) {
-                            const float m1 = cabs(sm.H[sm.car.pilot_car[lo]]), m2 = cabs(sm.H[sm.car.pilot_car[hi]]);
-                            im = (1.0f - al) * m1 + al * m2;
-                        } else if (lo >= 0) im = cabs(sm.H[sm.car.pilot_car[lo]]);
-                        else if (hi >= 0) im = cabs(sm.H[sm.car.pilot_car[hi]]);
-                        const float2 e = cexpj(carg(sm.H[c]));
-                        sm.H[c] = make_float2(im * e.x, im * e.y);
-                    }
-                }
-                if (tid == 0) {
-                    if (!differential && sm.s.noise_count > 1) {          // :1035-1039
-                        float inst = sm.s.signal_power / std_max(sm.s.noise_var, 1e-6f);
-                        inst = std_max(0.1f, std_min(10000.0f, inst));
-                        sm.s.snr_lin = 0.3f * inst + (1.0f - 0.3f) * sm.s.snr_lin;
-                    }
-                    sm.s.snr_count += 1;
-                    sm.s.have_prev_pilot = 1;
-                }
-                __syncthreads();
-            }
-
-            // ----------------------- equalize (channel_equalizer.cpp:1259-1451) -----------------------
-            if (tid < nd) sm.hpow[tid] = cnorm(sm.H[sm.car.data_car[tid]]);
-            __syncthreads();
-            if (tid == 0) {
-                float s = 0.f;
-                for (int i = 0; i < nd; ++i) s += sm.hpow[i];
-                sm.s.avg_h_power = s / static_cast<float>(nd);
-            }
-            __syncthreads();
-            if (tid < nd) {
-                const int c = sm.car.data_car[tid];
-                const float2 rx = sm.bin[c], h = sm.H[c];
-                const float h_power = sm.hpow[tid];
-                const float fade_threshold = 0.25f * sm.s.avg_h_power;
-                float2 e;
-                float nvv;
-                if (differential) {
-                    float snv = sm.s.noise_var;
-                    if (snv < 1e-6f) snv = sm.s.avg_h_power / 31.6f;
-                    const float den = h_power + snv;
-                    if (den < 1e-10f) { e = make_float2(0.f, 0.f); nvv = 100.0f; }
-                    else { e = cdivf(cmul(rx, cconj(h)), den); nvv = snv / (h_power + snv); }
-                    if (h_power < fade_threshold) nvv = 100.0f;
-                    nvv = std_max(1e-6f, std_min(100.0f, nvv));
-                } else {
-                    const float den = h_power + sm.s.noise_var;
-                    if (den < 1e-10f) { e = make_float2(0.f, 0.f); nvv = 100.0f; }
-                    else {
-                        e = cdivf(cmul(cconj(h), rx), den);
-                        nvv = sm.s.noise_var / den;
-                        nvv = std_max(1e-6f, std_min(100.0f, nvv));
-                    }
-                    if (h_power < fade_threshold) nvv = 100.0f;
-                    // decision-directed phase error for the next symbol (:1413-1448)
-                    const bool dd_mod = (mod == RIA_QPSK || mod == RIA_BPSK || mod == RIA_QAM16 ||
-                                         mod == RIA_QAM32 || mod == RIA_QAM64);
-                    if (dd_mod && sm.s.snr_count >= 2) {
-                        float mag_thr = 0.3f, ph_thr = 0.61f;
-                        if (mod == RIA_QAM16) { mag_thr = 0.25f; ph_thr = 0.44f; }
-                        else if (mod == RIA_QAM32 || mod == RIA_QAM64) { mag_thr = 0.20f; ph_thr = 0.35f; }
-                        float ddv = 0.0f;
-                        if (!(cabs(e) < mag_thr)) {
-                            const float2 dec = hard_decision(e, mod);
-                            const float perr = carg(cmul(e, cconj(dec)));
-                            if (fabsf(perr) < ph_thr) ddv = -perr;
-                        }
-                        sm.dd[tid] = ddv;
-                    }
-                }
-                sm.eq[tid] = e;
-                sm.cnv[tid] = nvv;
-            }
-            if (tid == 0 && !differential && sm.s.snr_count >= 2 &&
-                (mod == RIA_QPSK || mod == RIA_BPSK || mod == RIA_QAM16 || mod == RIA_QAM32 || mod == RIA_QAM64))
-                sm.s.have_dd = 1;
-            __syncthreads();
-
-            // ----------------------- demodulateSymbol (demodulator.cpp:208-508) -----------------------
-            if (tid < nd) {
-                const float2 sym = sm.eq[tid];
-                // per-carrier |eq| EMA / variance (:240-254)
-                const float mag = cabs(sym);
-                float ema, var;
-                if (first) { ema = mag; var = 0.0f; }
-                else {
-                    ema = sm.ema[tid]; var = sm.var[tid];
-                    const float delta = mag - ema;
-                    ema += 0.3f * delta;
-                    var += 0.3f * (delta * delta - var);
-                }
-                sm.ema[tid] = ema; sm.var[tid] = var;
-                float nv = sm.cnv[tid] * ce_margin(mod);
-                {
-                    const float mean_sq = ema * ema + 1e-6f;
-                    const float norm_var = var / mean_sq;
-                    nv *= (1.0f + 10.0f * norm_var);
-                }
-                float* out = llr_out + sd * llr_per_sym + tid * bpc;
-                switch (mod) {
-                    case RIA_DBPSK: {                                 // demapDBPSK, soft_demap.hpp:172-193
-                        const float2 prev = first ? make_float2(1.0f, 0.0f) : sm.prev_eq[tid];
-                        const float2 diff = cmul(sym, cconj(prev));
-                        const float pd = atan2_rn(diff.y, diff.x);
-                        const float sp = mag * cabs(prev);
-                        float l = 0.0f;
-                        if (!(sp < 1e-6f)) {
-                            const float dnv = 2.0f * nv;
-                            const float conf = 2.0f * sp / dnv;
-                            l = clip_llr(conf * cos_rn(pd));
-                        }
-                        out[0] = l;
-                        sm.prev_eq[tid] = sym;
-                        break;
-                    }
-                    case RIA_DQPSK: {                                 // demapDQPSK, soft_demap.hpp:199-235
-                        const float2 prev = first ? make_float2(1.0f, 0.0f) : sm.prev_eq[tid];
-                        const float2 diff = cmul(sym, cconj(prev));
-                        const float dmag = cabs(diff);
-                        float l0 = 0.0f, l1 = 0.0f;
-                        if (!(dmag < 1e-6f)) {
-                            const float dnv = 2.0f * nv;
-                            const float sp = mag * cabs(prev);
-                            const float snr = sp / dnv;
-                            const float scale = 2.0f * sqrtf(snr);
-                            const float pi = 3.14159265358979f;
-                            const float ph = atan2_rn(diff.y, diff.x);
-                            l0 = clip_llr(scale * sin_rn(ph + pi / 4));
-                            l1 = clip_llr(scale * (fabsf(diff.x) - fabsf(diff.y)) / dmag);
-                        }
-                        out[0] = l0; out[1] = l1;
-                        sm.prev_eq[tid] = sym;
-                        break;
-                    }
-                    case RIA_BPSK:                                    // soft_demap.hpp:37-39
-                        out[0] = clip_llr(-2.0f * sym.x / nv);
-                        break;
-                    case RIA_QPSK: {                                  // soft_demap.hpp:42-45
-                        const float scale = -2.0f * 0.7071067811865476f / nv;
-                        out[0] = clip_llr(sym.x * scale); out[1] = clip_llr(sym.y * scale);
-                        break;
-                    }
-                    case RIA_QAM16: {                                 // soft_demap.hpp:49-64
-                        const float scale = 2.0f / nv, T = 0.6324555320336759f;
-                        out[0] = clip_llr(-scale * sym.x);
-                        out[1] = clip_llr(scale * (fabsf(sym.x) - T));
-                        out[2] = clip_llr(-scale * sym.y);
-                        out[3] = clip_llr(scale * (fabsf(sym.y) - T));
-                        break;
-                    }
-                    case RIA_QAM32: {
-                        float l[5];
-                        demap_qam32(sym, nv, l);
-#pragma unroll
-                        for (int b = 0; b < 5; ++b) out[b] = l[b];
-                        break;
-                    }
-                    case RIA_QAM64: {                                 // soft_demap.hpp:125-142
-                        const float scale = 2.0f / nv, D2 = 0.3086067f, D4 = 0.6172134f;
-                        const float I = sym.x, Q = sym.y;
-                        out[0] = clip_llr(-scale * I);
-                        out[1] = clip_llr(scale * (fabsf(I) - D4));
-                        out[2] = clip_llr(scale * (fabsf(fabsf(I) - D4) - D2));
-                        out[3] = clip_llr(-scale * Q);
-                        out[4] = clip_llr(scale * (fabsf(Q) - D4));
-                        out[5] = clip_llr(scale * (fabsf(fabsf(Q) - D4) - D2));
-                        break;
-                    }
-                    case RIA_QAM256: {                                // soft_demap.hpp:145-164
-                        const float scale = 2.0f / nv, D2 = 0.1290994f, D4 = 0.2581989f, D8 = 0.5163978f;
-                        const float I = sym.x, Q = sym.y;
-                        out[0] = clip_llr(-scale * I);
-                        out[1] = clip_llr(scale * (fabsf(I) - D8));
-                        out[2] = clip_llr(scale * (fabsf(fabsf(I) - D8) - D4));
-                        out[3] = clip_llr(scale * (fabsf(fabsf(fabsf(I) - D8) - D4) - D2));
-                        out[4] = clip_llr(-scale * Q);
-                        out[5] = clip_llr(scale * (fabsf(Q) - D8));
-                        out[6] = clip_llr(scale * (fabsf(fabsf(Q) - D8) - D4));
-                        out[7] = clip_llr(scale * (fabsf(fabsf(fabsf(Q) - D8) - D4) - D2));
-                        break;
-                    }
-                    default: break;
-                }
-            }
-            __syncthreads();
+                reinterpret_cast<float2*>(a.bins_tap)[(f * n_sym + 2 + sd) * nc + tid] = cs.bin[tid];
+            data_symbol<kThreads>(cs, car, a, llr_out, sd, tid);
         }
-
-        // ---- per-frame outputs ----
-        const int n_llr = (n_data_sym > 0 ? n_data_sym : 0) * llr_per_sym;
-        for (int i = n_llr + tid; i < a.llr_stride; i += kThreads) llr_out[i] = 0.0f;
-        if (tid < nd) sm.tmpf[tid] = cabs(sm.H[sm.car.data_car[tid]]);
-        __syncthreads();
-        if (tid == 0) {
-            a.n_llr[f] = n_llr;
-            if (a.snr_db) a.snr_db[f] = 10.0f * log10f(sm.s.snr_lin);                  // getEstimatedSNR
-            if (a.cfo_out) a.cfo_out[f] = sm.s.cfo_hz;                                 // getFrequencyOffset
-            if (a.fading) {                                                            // getFadingIndex, :1168-1199
-                float sum = 0.f;
-                for (int i = 0; i < nd; ++i) sum += sm.tmpf[i];
-                const float mean = sum / static_cast<float>(nd);
-                float fi = 0.0f;
-                if (!(mean < 0.001f)) {
-                    float vs = 0.f;
-                    for (int i = 0; i < nd; ++i) { const float d = sm.tmpf[i] - mean; vs += d * d; }
-                    fi = sqrtf(vs / static_cast<float>(nd)) / mean;
-                }
-                a.fading[f] = fi;
-            }
-        }
-        __syncthreads();
+        frame_outputs<kThreads>(cs, car, a, f, n_data_sym, tid);
     }
 }
 
@@ -846,6 +1210,36 @@ void build_stage_twiddles(const std::vector<float2>& W, std::vector<float2>& out
     out.assign(kTwCount, make_float2(0.f, 0.f));
     for (int L = 4; L <= kFft; L <<= 1)
         for (int k = 0; k < L / 2; ++k) out[(L >> 1) - 2 + k] = W[static_cast<size_t>(k) * (kFft / L)];
+}
+
+// output pruning needs every used bin to have its own residue mod 64
+bool bins_allow_pruning(const OfdmCarrierTable& car) {
+    bool seen[64] = {};
+    for (int c = 0; c < car.num_carriers; ++c) {
+        const int r = car.fft_idx[c] & 63;
+        if (seen[r]) return false;
+        seen[r] = true;
+    }
+    return true;
+}
+
+int ensure_ofdm_scratch(ria_ctx* ctx, size_t bytes) {
+    if (bytes > ctx->ofdm_scratch_bytes) {
+        if (ctx->ofdm_scratch) RIA_CUDA(ctx, cudaFree(ctx->ofdm_scratch));
+        ctx->ofdm_scratch = nullptr; ctx->ofdm_scratch_bytes = 0;
+        RIA_CUDA(ctx, cudaMalloc(&ctx->ofdm_scratch, bytes));
+        ctx->ofdm_scratch_bytes = bytes;
+    }
+    return RIA_OK;
+}
+
+template <typename K>
+int blocks_per_sm(ria_ctx* ctx, K kernel, int threads, size_t smem, int* out) {
+    RIA_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RIA_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    RIA_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kernel, threads, smem));
+    if (*out < 1) return set_error(ctx, RIA_E_UNSUPPORTED, "ofdm: kernel does not fit on this device");
+    return RIA_OK;
 }
 
 }  // namespace
@@ -908,6 +1302,7 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
     if (rc != RIA_OK) return rc;
     const int n_sym = frame_len / t->sym_len;
     const int nd = t->car_host.n_data;
+    const int nc = t->car_host.num_carriers;
     const int bpc = ofdm_bits_per_carrier(cfg->modulation);
     const int n_llr = (n_sym > 2 ? n_sym - 2 : 0) * nd * bpc;
     if (llr_stride < n_llr) return set_error(ctx, RIA_E_INVAL, "ofdm: llr_stride %d < %d soft bits per frame", llr_stride, n_llr);
@@ -922,23 +1317,96 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
     a.cp = t->cp; a.sym_len = t->sym_len; a.modulation = static_cast<int>(cfg->modulation);
     a.differential = ofdm_is_differential(cfg->modulation) ? 1 : 0;
     a.bits_per_carrier = bpc; a.sample_rate = static_cast<int>(cfg->sample_rate);
-    a.counter = ctx->work_counter + 1;
+    a.pruned = bins_allow_pruning(t->car_host) ? 1 : 0;
+    cudaStream_t st = ctx->stream;
 
-    const size_t smem = sizeof(Smem);
-    RIA_CUDA(ctx, cudaFuncSetAttribute(ofdm_presynced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    RIA_CUDA(ctx, cudaFuncSetAttribute(ofdm_presynced_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       cudaSharedmemCarveoutMaxShared));
-    int per_sm = 0;
-    RIA_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ofdm_presynced_kernel, kThreads, smem));
-    if (per_sm < 1) return set_error(ctx, RIA_E_UNSUPPORTED, "ofdm: kernel does not fit");
-    long long grid = static_cast<long long>(ctx->sm_count) * per_sm;
-    if (grid > n_frames) grid = n_frames;
-    RIA_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), ctx->stream));
-    time_begin(ctx, KK_OFDM_DEMOD);
-    ofdm_presynced_kernel<<<static_cast<unsigned>(grid), kThreads, smem, ctx->stream>>>(a);
-    time_end(ctx);
-    RIA_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 1;
+    int mono_per_sm = 0;
+    rc = blocks_per_sm(ctx, ofdm_presynced_kernel, kThreads, sizeof(MonoSmem), &mono_per_sm);
+    if (rc != RIA_OK) return rc;
+
+    // RIA_OFDM_MONOLITHIC=1: every frame through the one-CTA-per-frame kernel (A/B testing)
+    const char* mono_env = std::getenv("RIA_OFDM_MONOLITHIC");
+    if (n_sym < 2 || (mono_env && mono_env[0] == '1')) {
+        a.frame_begin = 0; a.frame_end = n_frames;
+        a.counter = ctx->work_counter + 1;
+        long long grid = static_cast<long long>(ctx->sm_count) * mono_per_sm;
+        if (grid > n_frames) grid = n_frames;
+        RIA_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
+        time_begin(ctx, KK_OFDM_DEMOD);
+        ofdm_presynced_kernel<<<static_cast<unsigned>(grid), kThreads, sizeof(MonoSmem), st>>>(a);
+        time_end(ctx);
+        RIA_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        return RIA_OK;
+    }
+
+    int fft_per_sm = 0, car_per_sm = 0;
+    if (a.pruned) rc = blocks_per_sm(ctx, ofdm_fft_kernel<true>, kThreads, sizeof(FftSmem), &fft_per_sm);
+    else          rc = blocks_per_sm(ctx, ofdm_fft_kernel<false>, kThreads, sizeof(FftSmem), &fft_per_sm);
+    if (rc != RIA_OK) return rc;
+    rc = blocks_per_sm(ctx, ofdm_carrier_kernel, kCarWarps * 32, sizeof(CarSmem), &car_per_sm);
+    if (rc != RIA_OK) return rc;
+
+    // chunk of frames whose carrier bins live in scratch between the stages
+    const int64_t chunk = n_frames < 65536 ? n_frames : 65536;
+    const int n_blocks = (n_sym * t->sym_len + 31) / 32;
+    const size_t bins_b = bins_dev ? 0 : static_cast<size_t>(chunk) * n_sym * nc * sizeof(float2);
+    const size_t phase_b = cfo_hz_dev ? static_cast<size_t>(chunk) * n_blocks * sizeof(float) : 0;
+    const size_t list_b = static_cast<size_t>(chunk) * sizeof(int);
+    rc = ensure_ofdm_scratch(ctx, bins_b + phase_b + list_b + 256);
+    if (rc != RIA_OK) return rc;
+    unsigned char* sp = static_cast<unsigned char*>(ctx->ofdm_scratch);
+    float2* bins_scratch = reinterpret_cast<float2*>(sp);
+    float* block_phase = reinterpret_cast<float*>(sp + bins_b);
+    a.rerun_list = reinterpret_cast<int*>(sp + bins_b + phase_b);
+    a.block_phase = block_phase;
+    a.n_blocks = n_blocks;
+    unsigned int* ctr = ctx->work_counter + 8;      // [0] fft items, [1] carrier frames, [2] rerun count, [3] rerun work
+    a.rerun_count = ctr + 2;
+
+    for (int64_t off = 0; off < n_frames; off += chunk) {
+        const int64_t n = (n_frames - off < chunk) ? (n_frames - off) : chunk;
+        a.frame_begin = off; a.frame_end = off + n;
+        if (bins_dev) { a.bins = reinterpret_cast<float2*>(bins_dev); a.bins_frame0 = 0; }
+        else          { a.bins = bins_scratch; a.bins_frame0 = off; }
+        RIA_CUDA(ctx, cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), st));
+        if (cfo_hz_dev) {
+            time_begin(ctx, KK_OFDM_PHASE);
+            ofdm_phase_scan_kernel<<<static_cast<unsigned>((n + 3) / 4), 128, 0, st>>>(
+                cfo_hz_dev, phase_dev, off, n, n_blocks, a.sample_rate, block_phase);
+            time_end(ctx);
+            ctx->launches += 1;
+        }
+        {
+            const long long items = ((n + kFftGroup - 1) / kFftGroup) * n_sym;
+            long long grid = static_cast<long long>(ctx->sm_count) * fft_per_sm;
+            if (grid > items) grid = items;
+            a.counter = ctr + 0;
+            time_begin(ctx, KK_OFDM_FFT);
+            if (a.pruned) ofdm_fft_kernel<true><<<static_cast<unsigned>(grid), kThreads, sizeof(FftSmem), st>>>(a);
+            else          ofdm_fft_kernel<false><<<static_cast<unsigned>(grid), kThreads, sizeof(FftSmem), st>>>(a);
+            time_end(ctx);
+        }
+        {
+            long long grid = static_cast<long long>(ctx->sm_count) * car_per_sm;
+            const long long need = (n + kCarWarps - 1) / kCarWarps;
+            if (grid > need) grid = need;
+            a.counter = ctr + 1;
+            time_begin(ctx, KK_OFDM_CARRIER);
+            ofdm_carrier_kernel<<<static_cast<unsigned>(grid), kCarWarps * 32, sizeof(CarSmem), st>>>(a);
+            time_end(ctx);
+        }
+        {
+            long long grid = static_cast<long long>(ctx->sm_count) * mono_per_sm;
+            if (grid > n) grid = n;
+            a.counter = ctr + 3;
+            time_begin(ctx, KK_OFDM_DEMOD);
+            ofdm_presynced_kernel<<<static_cast<unsigned>(grid), kThreads, sizeof(MonoSmem), st>>>(a);
+            time_end(ctx);
+        }
+        RIA_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 3;
+    }
     return RIA_OK;
 }
 

@@ -67,6 +67,8 @@ struct ria_ctx {
     // scratch owned by the context for the fused chain entry points
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    void* ofdm_scratch = nullptr;           // carrier bins / CFO phases between the OFDM stages
+    size_t ofdm_scratch_bytes = 0;
     // optional per-kernel timing (CUDA events on the launching stream), see ria_ctx_set_timing
     bool timing = false;
     struct TimedLaunch { int kind; cudaEvent_t start, stop; };
@@ -93,7 +95,8 @@ int ensure_scratch(ria_ctx* ctx, size_t bytes);
 
 // kernel kinds for the timing hook / launch accounting
 enum KernelKind { KK_LDPC = 0, KK_OFDM_DEMOD = 1, KK_FRAME_STATUS = 2, KK_AWGN = 3, KK_MCDPSK = 4,
-                  KK_ZC_SYNC = 5, KK_CHIRP_SYNC = 6, KK_CHASE = 7, KK_WATTERSON = 8, KK_MCDPSK_CFO = 9, KK_OFDM_SYNC = 10, KK_COUNT = 16 };
+                  KK_ZC_SYNC = 5, KK_CHIRP_SYNC = 6, KK_CHASE = 7, KK_WATTERSON = 8, KK_MCDPSK_CFO = 9, KK_OFDM_SYNC = 10,
+                  KK_OFDM_FFT = 11, KK_OFDM_CARRIER = 12, KK_OFDM_PHASE = 13, KK_COUNT = 16 };
 void time_begin(ria_ctx* ctx, int kind);
 void time_end(ria_ctx* ctx);
 
