@@ -729,35 +729,60 @@ __device__ __forceinline__ void frame_outputs(CarState& cs, const OfdmCarrierTab
 }
 
 // ======================================= FFT ================================================
-// XOR-swizzled 32x32 transpose: conflict-free for all four FFT passes.
-__device__ __forceinline__ int fft_addr(int j) { return ((j & 31) << 5) | (((j >> 5) ^ j) & 31); }
+// The 1024-point tile lives in shared memory as float2, element j at fft_addr(j): j with the
+// rotated bits j9..j6 XORed into j3..j0.  For each pass the 16 lanes of every half-warp then hit
+// 16 different bank pairs, so all 64-bit loads/stores are conflict-free.
+__device__ __forceinline__ int fft_addr(int j) { return j ^ (((j >> 5) & 14) | ((j >> 9) & 1)); }
 // stage-major twiddle table: tw_L[k] = W[k * (1024 / L)], k < L/2, stored at offset L/2 - 2
 __device__ __forceinline__ int tw_off(int L) { return (L >> 1) - 2; }
 
+// Blackwell packed fp32 (FADD2 / FMUL2): two IEEE round-to-nearest operations per issue slot.
+// ptxas contracts a packed multiply that feeds a packed add into FFMA2 even under --fmad=false,
+// so products always go through a scalar add (tests/test_abi_cpu.py checks the SASS for FFMA).
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 mul2s(float s, float2 b) {            // (s * b.x, s * b.y)
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%2}; mov.b64 rb, {%3,%4}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(s), "f"(b.x), "f"(b.y));
+    return r;
+}
+// same products and the same sums as cmul(w, b)
+__device__ __forceinline__ float2 cmul_p(float2 w, float2 b) {
+    const float2 m = mul2s(w.x, b), n = mul2s(w.y, b);
+    return make_float2(__fsub_rn(m.x, n.y), __fadd_rn(m.y, n.x));
+}
+
 // one radix-2 DIT butterfly exactly as fft.cpp:115-119:  t = w * b;  b = a - t;  a = a + t
 __device__ __forceinline__ void bfly(float2& a, float2& b, float2 w) {
-    const float2 t = cmul(w, b);
-    b = csub(a, t);
-    a = cadd(a, t);
+    const float2 t = cmul_p(w, b);
+    b = sub2(a, t);
+    a = add2(a, t);
 }
 // k = 0: w = (1, -0); multiplying by it is value-exact, so the product is skipped
 __device__ __forceinline__ void bfly0(float2& a, float2& b) {
     const float2 t = b;
-    b = csub(a, t);
-    a = cadd(a, t);
+    b = sub2(a, t);
+    a = add2(a, t);
 }
-// one output of a butterfly: a + t (upper half of the block) or a - t (lower half).  a - t and
-// a + (-t) are the same IEEE operation, so the sign is folded into t.
-__device__ __forceinline__ float2 bfly_half(float2 a, float2 b, float2 w, unsigned neg) {
-    float2 t = cmul(w, b);
-    t.x = __uint_as_float(__float_as_uint(t.x) ^ neg);
-    t.y = __uint_as_float(__float_as_uint(t.y) ^ neg);
-    return cadd(a, t);
+// one output of a butterfly: a + t (upper half of the block) or a - t (lower half).  a - t is
+// a + (-w) * b exactly, so the sign is folded into the twiddle.
+__device__ __forceinline__ float2 bfly_half(float2 a, float2 b, float2 w_signed) {
+    return add2(a, cmul_p(w_signed, b));
 }
 
 struct FftTile {
-    float re[kFft];
-    float im[kFft];
+    float2 x[kFft];
 };
 
 // passes 1 and 2 (stages L = 2 .. 64) on the 8 mixed samples each thread holds; v[t] = baseband
@@ -775,10 +800,7 @@ __device__ __forceinline__ void fft_stages_2_to_64(FftTile& ft, const float2* __
     {
         const int g = __brev(static_cast<unsigned>(tid)) >> 25;      // brev7
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int ad = fft_addr((g << 3) | t);
-            ft.re[ad] = v[t].x; ft.im[ad] = v[t].y;
-        }
+        for (int t = 0; t < 8; ++t) ft.x[fft_addr((g << 3) | t)] = v[t];
     }
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5;
@@ -788,19 +810,18 @@ __device__ __forceinline__ void fft_stages_2_to_64(FftTile& ft, const float2* __
         const int hi = lane >> 1;                                     // j9..j6
         const int jb = (hi << 6) | lo;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 3)); v[u] = make_float2(ft.re[ad], ft.im[ad]); }
+        for (int u = 0; u < 8; ++u) v[u] = ft.x[fft_addr(jb | (u << 3))];
         const float2 w16 = tw[tw_off(16) + lo];
-        if (lo == 0) { bfly0(v[0], v[1]); bfly0(v[2], v[3]); bfly0(v[4], v[5]); bfly0(v[6], v[7]); }
-        else { bfly(v[0], v[1], w16); bfly(v[2], v[3], w16); bfly(v[4], v[5], w16); bfly(v[6], v[7], w16); }
+        bfly(v[0], v[1], w16); bfly(v[2], v[3], w16); bfly(v[4], v[5], w16); bfly(v[6], v[7], w16);
         const float2 w32a = tw[tw_off(32) + lo], w32b = tw[tw_off(32) + 8 + lo];
-        if (lo == 0) { bfly0(v[0], v[2]); bfly0(v[4], v[6]); } else { bfly(v[0], v[2], w32a); bfly(v[4], v[6], w32a); }
+        bfly(v[0], v[2], w32a); bfly(v[4], v[6], w32a);
         bfly(v[1], v[3], w32b); bfly(v[5], v[7], w32b);
-        if (lo == 0) bfly0(v[0], v[4]); else bfly(v[0], v[4], tw[tw_off(64) + lo]);
+        bfly(v[0], v[4], tw[tw_off(64) + lo]);
         bfly(v[1], v[5], tw[tw_off(64) + 8 + lo]);
         bfly(v[2], v[6], tw[tw_off(64) + 16 + lo]);
         bfly(v[3], v[7], tw[tw_off(64) + 24 + lo]);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 3)); ft.re[ad] = v[u].x; ft.im[ad] = v[u].y; }
+        for (int u = 0; u < 8; ++u) ft.x[fft_addr(jb | (u << 3))] = v[u];
     }
     __syncthreads();
 }
@@ -816,28 +837,26 @@ __device__ __forceinline__ void fft_stages_128_to_1024_full(FftTile& ft, const f
         const int lo6 = ((warp & 1) << 5) | lane;                     // j5..j0
         const int jb = ((warp >> 1) << 9) | lo6;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 6)); v[u] = make_float2(ft.re[ad], ft.im[ad]); }
+        for (int u = 0; u < 8; ++u) v[u] = ft.x[fft_addr(jb | (u << 6))];
         const float2 w128 = tw[tw_off(128) + lo6];
-        if (lo6 == 0) { bfly0(v[0], v[1]); bfly0(v[2], v[3]); bfly0(v[4], v[5]); bfly0(v[6], v[7]); }
-        else { bfly(v[0], v[1], w128); bfly(v[2], v[3], w128); bfly(v[4], v[5], w128); bfly(v[6], v[7], w128); }
+        bfly(v[0], v[1], w128); bfly(v[2], v[3], w128); bfly(v[4], v[5], w128); bfly(v[6], v[7], w128);
         const float2 w256a = tw[tw_off(256) + lo6], w256b = tw[tw_off(256) + 64 + lo6];
-        if (lo6 == 0) { bfly0(v[0], v[2]); bfly0(v[4], v[6]); } else { bfly(v[0], v[2], w256a); bfly(v[4], v[6], w256a); }
+        bfly(v[0], v[2], w256a); bfly(v[4], v[6], w256a);
         bfly(v[1], v[3], w256b); bfly(v[5], v[7], w256b);
-        if (lo6 == 0) bfly0(v[0], v[4]); else bfly(v[0], v[4], tw[tw_off(512) + lo6]);
+        bfly(v[0], v[4], tw[tw_off(512) + lo6]);
         bfly(v[1], v[5], tw[tw_off(512) + 64 + lo6]);
         bfly(v[2], v[6], tw[tw_off(512) + 128 + lo6]);
         bfly(v[3], v[7], tw[tw_off(512) + 192 + lo6]);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 6)); ft.re[ad] = v[u].x; ft.im[ad] = v[u].y; }
+        for (int u = 0; u < 8; ++u) ft.x[fft_addr(jb | (u << 6))] = v[u];
     }
     __syncthreads();
     if (tid < car.num_carriers) {
         const int f = car.fft_idx[tid];
         const int k = f & 511;
-        const int a0 = fft_addr(k), a1 = fft_addr(k + 512);
-        float2 x0 = make_float2(ft.re[a0], ft.im[a0]);
-        float2 x1 = make_float2(ft.re[a1], ft.im[a1]);
-        if (k == 0) bfly0(x0, x1); else bfly(x0, x1, tw[tw_off(1024) + k]);
+        float2 x0 = ft.x[fft_addr(k)];
+        float2 x1 = ft.x[fft_addr(k + 512)];
+        bfly(x0, x1, tw[tw_off(1024) + k]);
         bin_out[tid] = (f < 512) ? x0 : x1;
     }
     __syncthreads();
@@ -845,26 +864,24 @@ __device__ __forceinline__ void fft_stages_128_to_1024_full(FftTile& ft, const f
 
 // Per-thread constants of the pruned last four stages.  Thread (j9 = warp >> 1, r = j5..j0)
 // follows the one bin k with k mod 64 == r (if any) through stages 128..512 of its half, and the
-// j9 = 0 thread finishes stage 1024.
+// j9 = 0 thread finishes stage 1024.  Bit log2(L/2) of k selects the a - t output of stage L;
+// the twiddles carry that sign.
 struct PrunedPlan {
     int carrier;            // logical carrier of bin k, -1 = residue unused
     float2 w128, w256, w512, w1024;
-    unsigned n128, n256, n512, n1024;     // sign masks: bit (log2 L - 1) of k selects a - t
 };
+
+__device__ __forceinline__ float2 signed_tw(float2 w, bool neg) { return neg ? make_float2(-w.x, -w.y) : w; }
 
 __device__ __forceinline__ PrunedPlan make_pruned_plan(const float2* __restrict__ tw, const short* res_car,
                                                        const short* res_k, int r) {
     PrunedPlan p;
     p.carrier = res_car[r];
     const int k = p.carrier >= 0 ? res_k[r] : r;
-    p.w128 = tw[tw_off(128) + (k & 63)];
-    p.w256 = tw[tw_off(256) + (k & 127)];
-    p.w512 = tw[tw_off(512) + (k & 255)];
-    p.w1024 = tw[tw_off(1024) + (k & 511)];
-    p.n128 = (k & 64) ? 0x80000000u : 0u;
-    p.n256 = (k & 128) ? 0x80000000u : 0u;
-    p.n512 = (k & 256) ? 0x80000000u : 0u;
-    p.n1024 = (k & 512) ? 0x80000000u : 0u;
+    p.w128 = signed_tw(tw[tw_off(128) + (k & 63)], k & 64);
+    p.w256 = signed_tw(tw[tw_off(256) + (k & 127)], k & 128);
+    p.w512 = signed_tw(tw[tw_off(512) + (k & 255)], k & 256);
+    p.w1024 = signed_tw(tw[tw_off(1024) + (k & 511)], k & 512);
     return p;
 }
 
@@ -878,18 +895,18 @@ __device__ __forceinline__ void fft_stages_128_to_1024_pruned(FftTile& ft, float
         const int jb = (j9 << 9) | r;
         float2 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int ad = fft_addr(jb | (u << 6)); v[u] = make_float2(ft.re[ad], ft.im[ad]); }
-        const float2 y0 = bfly_half(v[0], v[1], p.w128, p.n128);
-        const float2 y1 = bfly_half(v[2], v[3], p.w128, p.n128);
-        const float2 y2 = bfly_half(v[4], v[5], p.w128, p.n128);
-        const float2 y3 = bfly_half(v[6], v[7], p.w128, p.n128);
-        const float2 z0 = bfly_half(y0, y1, p.w256, p.n256);
-        const float2 z1 = bfly_half(y2, y3, p.w256, p.n256);
-        x = bfly_half(z0, z1, p.w512, p.n512);
+        for (int u = 0; u < 8; ++u) v[u] = ft.x[fft_addr(jb | (u << 6))];
+        const float2 y0 = bfly_half(v[0], v[1], p.w128);
+        const float2 y1 = bfly_half(v[2], v[3], p.w128);
+        const float2 y2 = bfly_half(v[4], v[5], p.w128);
+        const float2 y3 = bfly_half(v[6], v[7], p.w128);
+        const float2 z0 = bfly_half(y0, y1, p.w256);
+        const float2 z1 = bfly_half(y2, y3, p.w256);
+        x = bfly_half(z0, z1, p.w512);
         if (j9) xch[r] = x;
     }
     __syncthreads();
-    if (p.carrier >= 0 && j9 == 0) bin_out[p.carrier] = bfly_half(x, xch[r], p.w1024, p.n1024);
+    if (p.carrier >= 0 && j9 == 0) bin_out[p.carrier] = bfly_half(x, xch[r], p.w1024);
 }
 
 // mixer + CFO phase increment exactly as channel_equalizer.cpp:103
