@@ -39,6 +39,7 @@
 
 #include "ofdm_tables.h"
 #include "cfo_phase.cuh"
+#include "rn_math.h"
 
 #include <cfloat>
 #include <cstdlib>
@@ -84,18 +85,16 @@ __device__ __forceinline__ float2 cdiv(float2 a, float2 b) {
     return make_float2(static_cast<float>((aa * cc + bb * dd) / den),
                        static_cast<float>((bb * cc - aa * dd) / den));
 }
-// Transcendentals: the reference calls glibc's float cosf/sinf/atan2f, which are (almost always)
-// correctly rounded; CUDA's float versions are 1-2 ulp.  Those ulps are amplified by the QAM
-// demapper's 2/noise_var scale into LLR differences above the 1e-4 contract, so the device
-// evaluates them in double and rounds once (B200 has half-rate FP64, this is affordable).
-__device__ __forceinline__ float atan2_rn(float y, float x) { return static_cast<float>(atan2(static_cast<double>(y), static_cast<double>(x))); }
-__device__ __forceinline__ float sin_rn(float x) { return static_cast<float>(sin(static_cast<double>(x))); }
-__device__ __forceinline__ float cos_rn(float x) { return static_cast<float>(cos(static_cast<double>(x))); }
+// Transcendentals: the reference calls glibc's float atan2f / sinf / cosf, which are not correctly
+// rounded; rn_math.h restates the algorithms glibc runs so the device returns the same bits.
+__device__ __forceinline__ float atan2_rn(float y, float x) { return glibc_atan2f(y, x); }
+__device__ __forceinline__ float sin_rn(float x) { return glibc_sinf(x); }
+__device__ __forceinline__ float cos_rn(float x) { return glibc_cosf(x); }
 __device__ __forceinline__ float carg(float2 a) { return atan2_rn(a.y, a.x); }
 __device__ __forceinline__ float2 cexpj(float th) {
-    double s, c;
-    sincos(static_cast<double>(th), &s, &c);
-    return make_float2(static_cast<float>(c), static_cast<float>(s));
+    float s, c;
+    glibc_sincosf(th, &s, &c);
+    return make_float2(c, s);
 }
 __device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }   // std::max(a,b)
 __device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b : a; }   // std::min(a,b)
@@ -388,13 +387,21 @@ __device__ __forceinline__ void lts_finish(CarState& cs, const OfdmCarrierTable&
 
 // One data symbol: updateChannelEstimate + equalize + demodulateSymbol on cs.bin[].
 // `sd` = index of the data symbol (0 = first after the LTS), llr_out = soft bits of the frame.
-template <int G>
+// MOD >= 0 fixes the modulation at compile time (the carrier kernel is instantiated per modulation
+// so that each instance only carries its own demapper); MOD < 0 reads it from the arguments.
+__host__ __device__ constexpr bool mod_is_differential(int m) { return m == RIA_DBPSK || m == RIA_DQPSK || m == RIA_D8PSK; }
+__host__ __device__ constexpr int mod_bits(int m) {
+    return m == RIA_DBPSK || m == RIA_BPSK ? 1 : m == RIA_DQPSK || m == RIA_QPSK ? 2 : m == RIA_D8PSK || m == RIA_QAM8 ? 3
+         : m == RIA_QAM16 ? 4 : m == RIA_QAM32 ? 5 : m == RIA_QAM64 ? 6 : m == RIA_QAM256 ? 8 : 0;
+}
+
+template <int G, int MOD>
 __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable& car, const KernelArgs& a,
                                             float* __restrict__ llr_out, int sd, int g) {
     const int nc = car.num_carriers, nd = car.n_data, np = car.n_pilot;
-    const int mod = a.modulation;
-    const bool differential = a.differential != 0;
-    const int bpc = a.bits_per_carrier;
+    const int mod = (MOD >= 0) ? MOD : a.modulation;
+    const bool differential = (MOD >= 0) ? mod_is_differential(MOD) : (a.differential != 0);
+    const int bpc = (MOD >= 0) ? mod_bits(MOD) : a.bits_per_carrier;
     const int llr_per_sym = nd * bpc;
     const bool first = (sd == 0);                             // soft_bits.empty()
 
@@ -404,7 +411,9 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
         if (first) alpha = 1.0f; else if (differential) alpha = 0.5f; else alpha = 0.9f;
         for (int i = g; i < np; i += G) {
             const int c = car.pilot_car[i];
-            cs.pil_ls[i] = cdiv(cs.bin[c], make_float2(car.pilot_sign[i], 0.0f));   // :687
+            // rx / (+-1, 0) (:687): libgcc's complex division by a unit real is a sign change
+            const float2 rx = cs.bin[c];
+            cs.pil_ls[i] = (car.pilot_sign[i] < 0.0f) ? make_float2(-rx.x, -rx.y) : rx;
         }
         gsync<G>();
         if (differential) {
@@ -1048,6 +1057,7 @@ struct CarSmem {
     CarState cs[kCarWarps];
 };
 
+template <int MOD>
 __global__ void __launch_bounds__(kCarWarps * 32)
 ofdm_carrier_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1064,8 +1074,6 @@ ofdm_carrier_kernel(const KernelArgs a) {
     const int nc = car.num_carriers;
     const int n_sym = a.frame_len / a.sym_len;
     const int n_data_sym = n_sym - 2;
-    const int llr_per_sym = car.n_data * a.bits_per_carrier;
-    (void)llr_per_sym;
 
     for (;;) {
         long long f = 0;
@@ -1103,7 +1111,7 @@ ofdm_carrier_kernel(const KernelArgs a) {
                 if (lane < nc) nb0 = fb[(3 + sd) * nc + lane];
                 if (lane + 32 < nc) nb1 = fb[(3 + sd) * nc + lane + 32];
             }
-            data_symbol<32>(cs, car, a, llr_out, sd, lane);
+            data_symbol<32, MOD>(cs, car, a, llr_out, sd, lane);
         }
         frame_outputs<32>(cs, car, a, f, n_data_sym, lane);
     }
@@ -1216,7 +1224,7 @@ ofdm_presynced_kernel(const KernelArgs a) {
             mono_fft_symbol(sm, a, frame, 2 + sd);
             if (a.bins_tap && tid < nc)
                 reinterpret_cast<float2*>(a.bins_tap)[(f * n_sym + 2 + sd) * nc + tid] = cs.bin[tid];
-            data_symbol<kThreads>(cs, car, a, llr_out, sd, tid);
+            data_symbol<kThreads, -1>(cs, car, a, llr_out, sd, tid);
         }
         frame_outputs<kThreads>(cs, car, a, f, n_data_sym, tid);
     }
@@ -1361,7 +1369,19 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
     if (a.pruned) rc = blocks_per_sm(ctx, ofdm_fft_kernel<true>, kThreads, sizeof(FftSmem), &fft_per_sm);
     else          rc = blocks_per_sm(ctx, ofdm_fft_kernel<false>, kThreads, sizeof(FftSmem), &fft_per_sm);
     if (rc != RIA_OK) return rc;
-    rc = blocks_per_sm(ctx, ofdm_carrier_kernel, kCarWarps * 32, sizeof(CarSmem), &car_per_sm);
+    void (*carrier_kernel)(const KernelArgs) = nullptr;
+    switch (cfg->modulation) {
+        case RIA_DBPSK:  carrier_kernel = ofdm_carrier_kernel<RIA_DBPSK>; break;
+        case RIA_DQPSK:  carrier_kernel = ofdm_carrier_kernel<RIA_DQPSK>; break;
+        case RIA_BPSK:   carrier_kernel = ofdm_carrier_kernel<RIA_BPSK>; break;
+        case RIA_QPSK:   carrier_kernel = ofdm_carrier_kernel<RIA_QPSK>; break;
+        case RIA_QAM16:  carrier_kernel = ofdm_carrier_kernel<RIA_QAM16>; break;
+        case RIA_QAM32:  carrier_kernel = ofdm_carrier_kernel<RIA_QAM32>; break;
+        case RIA_QAM64:  carrier_kernel = ofdm_carrier_kernel<RIA_QAM64>; break;
+        case RIA_QAM256: carrier_kernel = ofdm_carrier_kernel<RIA_QAM256>; break;
+        default: return set_error(ctx, RIA_E_UNSUPPORTED, "ofdm: modulation %u has no demapper", cfg->modulation);
+    }
+    rc = blocks_per_sm(ctx, carrier_kernel, kCarWarps * 32, sizeof(CarSmem), &car_per_sm);
     if (rc != RIA_OK) return rc;
 
     // chunk of frames whose carrier bins live in scratch between the stages
@@ -1410,7 +1430,7 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
             if (grid > need) grid = need;
             a.counter = ctr + 1;
             time_begin(ctx, KK_OFDM_CARRIER);
-            ofdm_carrier_kernel<<<static_cast<unsigned>(grid), kCarWarps * 32, sizeof(CarSmem), st>>>(a);
+            carrier_kernel<<<static_cast<unsigned>(grid), kCarWarps * 32, sizeof(CarSmem), st>>>(a);
             time_end(ctx);
         }
         {

@@ -1,0 +1,286 @@
+// glibc's float transcendentals, restated so that the device returns the same bits as the host.
+//
+// The reference calls std::atan2 / std::arg / std::sin / std::cos / std::polar / std::exp on
+// floats, i.e. glibc's atan2f, sinf, cosf and sincosf.  Neither is correctly rounded (atan2f is
+// off by one ulp in ~14 % of calls, sinf/cosf in ~1 %), and CUDA's own float versions differ from
+// them by 1-2 ulp -- which the QAM demapper's 2/noise_var scale amplifies past the 1e-4 soft-bit
+// contract.  So the algorithms glibc 2.39 (x86-64) runs are restated here operation by operation:
+//   glibc_atan2f / glibc_atanf   sysdeps/ieee754/flt-32/e_atan2f.c, s_atanf.c (fdlibm, pure fp32,
+//                                no FMA: x86-64 glibc has no FMA variant of these);
+//   glibc_sinf / glibc_cosf / glibc_sincosf
+//                                sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c, sincosf.h (ARM
+//                                optimized-routines: double polynomial, the x86-64 ifunc picks
+//                                the FMA build on every CPU with FMA3, so a + b*c is one fma).
+// glibc is not part of /root/reference; the restatement is pinned bit-for-bit against the
+// container's libm on 2 x 10^7 arguments per function (tests/test_rn_math_cpu.py), and the same
+// source compiles for the device.  Arguments outside the fast paths (|x| >= 120 for sin/cos) go
+// to a correctly rounded double evaluation; the modem never produces them.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define RN_HD __host__ __device__ __forceinline__
+#else
+#define RN_HD static inline
+#endif
+
+RN_HD uint32_t rn_fbits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+RN_HD float rn_ffrom(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+// fp32 a*b + c with two roundings, whatever the compiler's contraction setting
+RN_HD float rn_mad(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(__fmul_rn(a, b), c);
+#else
+    volatile float p = a * b;
+    return p + c;
+#endif
+}
+RN_HD float rn_mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+RN_HD float rn_add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+RN_HD float rn_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// atanf / atan2f (fdlibm)
+// ------------------------------------------------------------------------------------------
+RN_HD float glibc_atanf(float x) {
+    const float hi0 = 4.6364760399e-01f, hi1 = 7.8539812565e-01f, hi2 = 9.8279368877e-01f, hi3 = 1.5707962513e+00f;
+    const float lo0 = 5.0121582440e-09f, lo1 = 3.7748947079e-08f, lo2 = 3.4473217170e-08f, lo3 = 7.5497894159e-08f;
+    const float aT0 = 3.3333334327e-01f, aT1 = -2.0000000298e-01f, aT2 = 1.4285714924e-01f, aT3 = -1.1111110449e-01f,
+                aT4 = 9.0908870101e-02f, aT5 = -7.6918758452e-02f, aT6 = 6.6610731184e-02f, aT7 = -5.8335702866e-02f,
+                aT8 = 4.9768779427e-02f, aT9 = -3.6531571299e-02f, aT10 = 1.6285819933e-02f;
+    const int32_t hx = static_cast<int32_t>(rn_fbits(x));
+    const int32_t ix = hx & 0x7fffffff;
+    int id;
+    float hi = 0.0f, lo = 0.0f;
+    if (ix >= 0x4c000000) {                      // |x| >= 2^25
+        if (ix > 0x7f800000) return rn_add(x, x);
+        return (hx > 0) ? rn_add(hi3, lo3) : rn_add(-hi3, -lo3);
+    }
+    if (ix < 0x3ee00000) {                       // |x| < 0.4375
+        if (ix < 0x31000000) return x;           // |x| < 2^-29
+        id = -1;
+    } else {
+        x = fabsf(x);
+        if (ix < 0x3f980000) {                   // |x| < 1.1875
+            if (ix < 0x3f300000) { id = 0; hi = hi0; lo = lo0; x = rn_div(rn_add(rn_mul(2.0f, x), -1.0f), rn_add(2.0f, x)); }
+            else                 { id = 1; hi = hi1; lo = lo1; x = rn_div(rn_add(x, -1.0f), rn_add(x, 1.0f)); }
+        } else {
+            if (ix < 0x401c0000) { id = 2; hi = hi2; lo = lo2; x = rn_div(rn_add(x, -1.5f), rn_mad(1.5f, x, 1.0f)); }
+            else                 { id = 3; hi = hi3; lo = lo3; x = rn_div(-1.0f, x); }
+        }
+    }
+    const float z = rn_mul(x, x);
+    const float w = rn_mul(z, z);
+    // break sum from i=0 to 10 aT[i] z^(i+1) into odd and even poly
+    const float s1 = rn_mul(z, rn_mad(w, rn_mad(w, rn_mad(w, rn_mad(w, rn_mad(w, aT10, aT8), aT6), aT4), aT2), aT0));
+    const float s2 = rn_mul(w, rn_mad(w, rn_mad(w, rn_mad(w, rn_mad(w, aT9, aT7), aT5), aT3), aT1));
+    const float xs = rn_mul(x, rn_add(s1, s2));
+    if (id < 0) return rn_add(x, -xs);
+    const float zz = rn_add(hi, -rn_add(rn_add(xs, -lo), -x));
+    return (hx < 0) ? -zz : zz;
+}
+
+RN_HD float glibc_atan2f(float y, float x) {
+    const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f,
+                pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+    const int32_t hx = static_cast<int32_t>(rn_fbits(x)), hy = static_cast<int32_t>(rn_fbits(y));
+    const int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+    if (ix > 0x7f800000 || iy > 0x7f800000) return rn_add(x, y);           // NaN
+    if (hx == 0x3f800000) return glibc_atanf(y);                          // x = 1.0
+    const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);                     // 2*sign(x) + sign(y)
+    if (iy == 0) {
+        switch (m) { case 0: case 1: return y; case 2: return rn_add(pi, tiny); default: return rn_add(-pi, -tiny); }
+    }
+    if (ix == 0) return (hy < 0) ? rn_add(-pi_o_2, -tiny) : rn_add(pi_o_2, tiny);
+    if (ix == 0x7f800000) {
+        if (iy == 0x7f800000) {
+            switch (m) {
+                case 0: return rn_add(pi_o_4, tiny);
+                case 1: return rn_add(-pi_o_4, -tiny);
+                case 2: return rn_add(rn_mul(3.0f, pi_o_4), tiny);
+                default: return rn_add(rn_mul(-3.0f, pi_o_4), -tiny);
+            }
+        }
+        switch (m) { case 0: return 0.0f; case 1: return -0.0f; case 2: return rn_add(pi, tiny); default: return rn_add(-pi, -tiny); }
+    }
+    if (iy == 0x7f800000) return (hy < 0) ? rn_add(-pi_o_2, -tiny) : rn_add(pi_o_2, tiny);
+    const int32_t k = (iy - ix) >> 23;
+    float z;
+    if (k > 60) z = rn_add(pi_o_2, rn_mul(0.5f, pi_lo));                   // |y/x| > 2^60
+    else if (hx < 0 && k < -60) z = 0.0f;                                  // |y|/x < -2^60
+    else z = glibc_atanf(fabsf(rn_div(y, x)));
+    switch (m) {
+        case 0: return z;
+        case 1: return rn_ffrom(rn_fbits(z) ^ 0x80000000u);
+        case 2: return rn_add(pi, -rn_add(z, -pi_lo));
+        default: return rn_add(rn_add(z, -pi_lo), -pi);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// sinf / cosf / sincosf (ARM optimized-routines as built by glibc with FMA)
+// ------------------------------------------------------------------------------------------
+// correctly rounded fallback for |x| >= 120: Cody-Waite by pi/2 in double + Taylor polynomials
+RN_HD void rn_sincos_d(double x, double* s_out, double* c_out) {
+    if (!(fabs(x) < 1.0e5)) { *s_out = sin(x); *c_out = cos(x); return; }
+    const double n = rint(x * 0.63661977236758138243);
+    double r = fma(-n, 1.57079632679489655800e+00, x);
+    r = fma(-n, 6.12323399573676603587e-17, r);
+    const double r2 = r * r;
+    double sp = -7.6471637318198164759e-13;
+    sp = fma(sp, r2, 1.6059043836821614599e-10);
+    sp = fma(sp, r2, -2.5052108385441718775e-08);
+    sp = fma(sp, r2, 2.7557319223985890653e-06);
+    sp = fma(sp, r2, -1.9841269841269841270e-04);
+    sp = fma(sp, r2, 8.3333333333333333333e-03);
+    sp = fma(sp, r2, -1.6666666666666666667e-01);
+    const double s = fma(sp * r2, r, r);
+    double cp = 4.7794773323873852974e-14;
+    cp = fma(cp, r2, -1.1470745597729724714e-11);
+    cp = fma(cp, r2, 2.0876756987868098979e-09);
+    cp = fma(cp, r2, -2.7557319223985890653e-07);
+    cp = fma(cp, r2, 2.4801587301587301587e-05);
+    cp = fma(cp, r2, -1.3888888888888888889e-03);
+    cp = fma(cp, r2, 4.1666666666666666667e-02);
+    const double c = fma(cp * r2, r2, fma(-0.5, r2, 1.0));
+    const int q = static_cast<int>(n) & 3;
+    const double ss = (q & 1) ? c : s;
+    const double cc = (q & 1) ? s : c;
+    *s_out = (q & 2) ? -ss : ss;
+    *c_out = ((q + 1) & 2) ? -cc : cc;
+}
+
+// sincosf.h: __sincosf_table[0]; table[1] is the same with c0..c4 negated (flip = -1)
+#define RN_SC_C0 0x1p0
+#define RN_SC_C1 -0x1.ffffffd0c621cp-2
+#define RN_SC_C2 0x1.55553e1068f19p-5
+#define RN_SC_C3 -0x1.6c087e89a359dp-10
+#define RN_SC_C4 0x1.99343027bf8c3p-16
+#define RN_SC_S1 -0x1.555545995a603p-3
+#define RN_SC_S2 0x1.1107605230bc4p-7
+#define RN_SC_S3 -0x1.994eb3774cf24p-13
+#define RN_SC_HPI_INV 0x1.45F306DC9C883p+23
+#define RN_SC_HPI 0x1.921FB54442D18p0
+
+RN_HD uint32_t rn_abstop12(float x) { return (rn_fbits(x) >> 20) & 0x7ff; }
+
+// sine polynomial of sincosf_poly / sinf_poly
+RN_HD double rn_sc_sin(double x, double x2) {
+    const double x3 = x * x2;
+    const double s1 = fma(x2, RN_SC_S3, RN_SC_S2);
+    const double x5 = x3 * x2;
+    const double s = fma(x3, RN_SC_S1, x);
+    return fma(x5, s1, s);
+}
+// cosine polynomial; flip = +1 for table[0], -1 for table[1] (negated coefficients)
+RN_HD double rn_sc_cos(double x2, double flip) {
+    const double x4 = x2 * x2;
+    const double c2 = fma(x2, flip * RN_SC_C4, flip * RN_SC_C3);
+    const double c1 = fma(x2, flip * RN_SC_C1, flip * RN_SC_C0);
+    const double x6 = x4 * x2;
+    const double c = fma(x4, flip * RN_SC_C2, c1);
+    return fma(x6, c2, c);
+}
+// reduce_fast: n = round(x / (pi/2)), returns x - n pi/2
+RN_HD double rn_sc_reduce(double x, int* np) {
+    const double r = x * RN_SC_HPI_INV;
+    const int n = (static_cast<int32_t>(r) + 0x800000) >> 24;
+    *np = n;
+    return fma(-static_cast<double>(n), RN_SC_HPI, x);
+}
+
+RN_HD void glibc_sincosf(float y, float* sinp, float* cosp) {
+    double x = static_cast<double>(y);
+    if (rn_abstop12(y) < rn_abstop12(0x1.921FB6p-1f)) {                     // |y| < pi/4
+        const double x2 = x * x;
+        if (rn_abstop12(y) < rn_abstop12(0x1p-12f)) { *sinp = y; *cosp = 1.0f; return; }
+        *sinp = static_cast<float>(rn_sc_sin(x, x2));
+        *cosp = static_cast<float>(rn_sc_cos(x2, 1.0));
+    } else if (rn_abstop12(y) < rn_abstop12(120.0f)) {
+        int n;
+        x = rn_sc_reduce(x, &n);
+        // sign[n & 3] = {1, -1, -1, 1}; table[1] (n & 2) negates the cosine polynomial
+        const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+        const double flip = (n & 2) ? -1.0 : 1.0;
+        const double x2 = x * x;
+        const float ps = static_cast<float>(rn_sc_sin(x * s, x2));
+        const float pc = static_cast<float>(rn_sc_cos(x2, flip));
+        if (n & 1) { *sinp = pc; *cosp = ps; } else { *sinp = ps; *cosp = pc; }
+    } else {
+        double sd, cd;
+        rn_sincos_d(x, &sd, &cd);
+        *sinp = static_cast<float>(sd);
+        *cosp = static_cast<float>(cd);
+    }
+}
+
+RN_HD float glibc_sinf(float y) {
+    double x = static_cast<double>(y);
+    if (rn_abstop12(y) < rn_abstop12(0x1.921FB6p-1f)) {
+        if (rn_abstop12(y) < rn_abstop12(0x1p-12f)) return y;
+        return static_cast<float>(rn_sc_sin(x, x * x));
+    }
+    if (rn_abstop12(y) < rn_abstop12(120.0f)) {
+        int n;
+        x = rn_sc_reduce(x, &n);
+        const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+        const double flip = (n & 2) ? -1.0 : 1.0;
+        return static_cast<float>((n & 1) ? rn_sc_cos(x * x, flip) : rn_sc_sin(x * s, x * x));
+    }
+    double sd, cd;
+    rn_sincos_d(x, &sd, &cd);
+    return static_cast<float>(sd);
+}
+
+RN_HD float glibc_cosf(float y) {
+    double x = static_cast<double>(y);
+    if (rn_abstop12(y) < rn_abstop12(0x1.921FB6p-1f)) {
+        if (rn_abstop12(y) < rn_abstop12(0x1p-12f)) return 1.0f;
+        return static_cast<float>(rn_sc_cos(x * x, 1.0));
+    }
+    if (rn_abstop12(y) < rn_abstop12(120.0f)) {
+        int n;
+        x = rn_sc_reduce(x, &n);
+        // cosf: sign[(n + 1) & 3], table[1] when (n + 1) & 2, polynomial selected by n ^ 1
+        const int m = n + 1;
+        const double s = ((m & 3) == 1 || (m & 3) == 2) ? -1.0 : 1.0;
+        const double flip = (m & 2) ? -1.0 : 1.0;
+        return static_cast<float>(((n ^ 1) & 1) ? rn_sc_cos(x * x, flip) : rn_sc_sin(x * s, x * x));
+    }
+    double sd, cd;
+    rn_sincos_d(x, &sd, &cd);
+    return static_cast<float>(cd);
+}

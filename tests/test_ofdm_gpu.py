@@ -36,8 +36,12 @@ def _compare(ref, cfg, frames, out, cfos, phases, exact_bins):
         n = int(out["n_llr"][i])
         assert n == len(r["soft"]), (n, len(r["soft"]))
         got = out["llr"][i, :n]
-        ok = llr_close(got, r["soft"])
-        assert ok.all(), (i, np.abs(got - r["soft"]).max(), got[~ok][:5], r["soft"][~ok][:5])
+        # The contract is 1e-4 relative (llr_close); since the device restates glibc's atan2f /
+        # sinf / cosf bit for bit (csrc/rn_math.h) the soft bits are in fact IDENTICAL to the
+        # reference's, with and without CFO correction, so that is what is asserted.
+        assert llr_close(got, r["soft"]).all(), (i, np.abs(got - r["soft"]).max())
+        same = got.view(np.uint32) == r["soft"].view(np.uint32)
+        assert same.all(), (i, int((~same).sum()), got[~same][:5], r["soft"][~same][:5])
         worst = max(worst, float(np.abs(got - r["soft"]).max()))
         assert abs(out["snr_db"][i] - r["snr_db"]) <= 1e-3 * max(1.0, abs(r["snr_db"]))
         assert abs(out["cfo"][i] - r["cfo"]) <= 1e-4 * max(1.0, abs(r["cfo"]))
