@@ -73,13 +73,13 @@ __device__ __forceinline__ float2 cdivf(float2 a, float s) { return make_float2(
 __device__ __forceinline__ float cnorm(float2 a) { return __fadd_rn(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y)); }
 // std::abs(std::complex<float>) = hypotf; glibc evaluates it in double and rounds once
 // (verified bit-exact against the reference toolchain on 2M random inputs).
-__device__ __forceinline__ float cabs(float2 a) {
+__device__ __noinline__ float cabs(float2 a) {
     const double x = a.x, y = a.y;
     return static_cast<float>(sqrt(x * x + y * y));
 }
 // complex<float> / complex<float> = libgcc __divsc3: plain formula evaluated in double
 // (verified bit-exact against the reference toolchain on 2M random inputs).
-__device__ __forceinline__ float2 cdiv(float2 a, float2 b) {
+__device__ __noinline__ float2 cdiv(float2 a, float2 b) {
     const double aa = a.x, bb = a.y, cc = b.x, dd = b.y;
     const double den = cc * cc + dd * dd;
     return make_float2(static_cast<float>((aa * cc + bb * dd) / den),
@@ -87,11 +87,12 @@ __device__ __forceinline__ float2 cdiv(float2 a, float2 b) {
 }
 // Transcendentals: the reference calls glibc's float atan2f / sinf / cosf, which are not correctly
 // rounded; rn_math.h restates the algorithms glibc runs so the device returns the same bits.
-__device__ __forceinline__ float atan2_rn(float y, float x) { return glibc_atan2f(y, x); }
+// (real calls: one copy of each in the instruction cache instead of one per call site)
+__device__ __noinline__ float atan2_rn(float y, float x) { return glibc_atan2f(y, x); }
 __device__ __forceinline__ float sin_rn(float x) { return glibc_sinf(x); }
 __device__ __forceinline__ float cos_rn(float x) { return glibc_cosf(x); }
 __device__ __forceinline__ float carg(float2 a) { return atan2_rn(a.y, a.x); }
-__device__ __forceinline__ float2 cexpj(float th) {
+__device__ __noinline__ float2 cexpj(float th) {
     float s, c;
     glibc_sincosf(th, &s, &c);
     return make_float2(c, s);
@@ -123,7 +124,7 @@ struct FrameScalars {
     int have_dd;
 };
 
-struct CarState {
+struct alignas(16) CarState {
     float2 bin[kMaxCarriers];
     float2 H[kMaxCarriers];
     float2 hps[2][kMaxCarriers];
@@ -238,6 +239,53 @@ __device__ void demap_qam32(float2 sym, float nv, float* out) {
     for (int b = 0; b < 5; ++b) out[b] = clip_llr(sf * (d1[b] - d0[b]));
 }
 
+// fp32 sum of a[0..n) in index order (the order is observable).  One lane walks the chain;
+// loads come four at a time.
+__device__ __forceinline__ float ordered_sum(const float* a, int n) {
+    float s = 0.f;
+    int i = 0;
+#pragma unroll 2
+    for (; i + 4 <= n; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(a + i);
+        s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
+    }
+#pragma unroll 1
+    for (; i < n; ++i) s = __fadd_rn(s, a[i]);
+    return s;
+}
+__device__ __forceinline__ int count_flags(const int* a, int n) {
+    int s = 0, i = 0;
+#pragma unroll 1
+    for (; i + 4 <= n; i += 4) { const int4 v = *reinterpret_cast<const int4*>(a + i); s += v.x + v.y + v.z + v.w; }
+#pragma unroll 1
+    for (; i < n; ++i) s += a[i];
+    return s;
+}
+__device__ __forceinline__ float2 ordered_csum(const float2* a, int n) {
+    float2 s = make_float2(0.f, 0.f);
+    int i = 0;
+#pragma unroll 1
+    for (; i + 2 <= n; i += 2) {
+        const float4 v = *reinterpret_cast<const float4*>(a + i);
+        s.x = __fadd_rn(s.x, v.x); s.y = __fadd_rn(s.y, v.y);
+        s.x = __fadd_rn(s.x, v.z); s.y = __fadd_rn(s.y, v.w);
+    }
+#pragma unroll 1
+    for (; i < n; ++i) s = cadd(s, a[i]);
+    return s;
+}
+// Several ordered sums of the same length at once: lane j < n_rows walks row j (rows are
+// kMaxCarriers floats apart), so k sums cost one pass instead of k.  Result of row j in lane j.
+__device__ __forceinline__ float ordered_sum_rows(const float* rows, int n_rows, int n, int lane) {
+    float s = 0.f;
+    if (lane < n_rows) {
+        const float* a = rows + lane * kMaxCarriers;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) s = __fadd_rn(s, a[i]);
+    }
+    return s;
+}
+
 // =============================== carrier-domain processing =================================
 // Everything below works on cs.bin[] (the carrier bins of the current symbol) with a group of
 // G threads, g = index inside the group.  It is shared by the warp-per-frame carrier kernel
@@ -260,6 +308,7 @@ __device__ __forceinline__ void frame_reset(CarState& cs, const KernelArgs& a, l
         cs.s.have_prev_pilot = 0;
         cs.s.have_dd = 0;
     }
+    #pragma unroll 1
     for (int c = g; c < kMaxCarriers; c += G) cs.H[c] = make_float2(1.0f, 0.0f);
     gsync<G>();
 }
@@ -274,6 +323,7 @@ __device__ __forceinline__ void frame_too_short(const KernelArgs& a, long long f
         if (a.fading) a.fading[f] = 0.0f;
     }
     float* llr_out = a.llr + f * a.llr_stride;
+    #pragma unroll 1
     for (int i = g; i < a.llr_stride; i += G) llr_out[i] = 0.0f;
 }
 
@@ -281,6 +331,7 @@ __device__ __forceinline__ void frame_too_short(const KernelArgs& a, long long f
 template <int G>
 __device__ __forceinline__ void lts_symbol(CarState& cs, const OfdmCarrierTable& car, int s, int g) {
     const int nc = car.num_carriers;
+    #pragma unroll 1
     for (int c = g; c < nc; c += G) {
         const int sub = car.sub_idx[c];
         const float2 tx = car.is_pilot[c] ? make_float2(car.pilot_sign[sub], 0.0f) : car.tx_data[sub];
@@ -294,6 +345,7 @@ __device__ __forceinline__ void lts_symbol(CarState& cs, const OfdmCarrierTable&
 template <int G>
 __device__ __forceinline__ bool lts_residual(CarState& cs, const OfdmCarrierTable& car, const KernelArgs& a, int g) {
     const int nd = car.n_data;
+    #pragma unroll 1
     for (int i = g; i < nd; i += G) {
         const int c = car.data_car[i];
         const float2 h0 = cs.hps[0][c], h1 = cs.hps[1][c];
@@ -303,13 +355,13 @@ __device__ __forceinline__ bool lts_residual(CarState& cs, const OfdmCarrierTabl
             const float mag = cabs(diff);
             if (mag > 1e-6f) { cs.tmpc[i] = cdivf(diff, mag); ok = 1; }
         }
+        if (!ok) cs.tmpc[i] = make_float2(0.f, 0.f);       // adding zero leaves the ordered sum unchanged
         cs.flag[i] = ok;
     }
     gsync<G>();
     if (g == 0) {
-        float2 sum = make_float2(0.f, 0.f);
-        int valid = 0;
-        for (int i = 0; i < nd; ++i) if (cs.flag[i]) { sum = cadd(sum, cs.tmpc[i]); ++valid; }
+        const float2 sum = ordered_csum(cs.tmpc, nd);
+        const int valid = count_flags(cs.flag, nd);
         int rerun = 0;
         if (valid > 10) {
             const float avg_phase = atan2_rn(sum.y, sum.x);
@@ -332,9 +384,11 @@ __device__ __forceinline__ bool lts_residual(CarState& cs, const OfdmCarrierTabl
 template <int G>
 __device__ __forceinline__ void lts_finish(CarState& cs, const OfdmCarrierTable& car, const KernelArgs& a, long long f, int g) {
     const int nc = car.num_carriers, nd = car.n_data;
+    #pragma unroll 1
     for (int c = g; c < nc; c += G) cs.H[c] = cs.hps[1][c];
     gsync<G>();
     // phase slope across adjacent carriers (:412-437)
+    #pragma unroll 1
     for (int c = g; c < nc - 1; c += G) {
         const float2 h0 = cs.H[c], h1 = cs.H[c + 1];
         int ok = 0;
@@ -343,17 +397,18 @@ __device__ __forceinline__ void lts_finish(CarState& cs, const OfdmCarrierTable&
             const float mag = cabs(diff);
             if (mag > 1e-6f) { cs.tmpc[c] = cdivf(diff, mag); ok = 1; }
         }
+        if (!ok) cs.tmpc[c] = make_float2(0.f, 0.f);
         cs.flag[c] = ok;
     }
     gsync<G>();
     if (g == 0) {
-        float2 sum = make_float2(0.f, 0.f);
-        int cnt = 0;
-        for (int i = 0; i < nc - 1; ++i) if (cs.flag[i]) { sum = cadd(sum, cs.tmpc[i]); ++cnt; }
+        const float2 sum = ordered_csum(cs.tmpc, nc - 1);
+        const int cnt = count_flags(cs.flag, nc - 1);
         if (cnt > 0) cs.s.slope = carg(cdivf(sum, static_cast<float>(cnt)));
     }
     gsync<G>();
     // noise variance / SNR from the two LTS estimates (:457-485)
+    #pragma unroll 1
     for (int i = g; i < nd; i += G) {
         const int c = car.data_car[i];
         const float2 h0 = cs.hps[0][c], h1 = cs.hps[1][c];
@@ -362,14 +417,13 @@ __device__ __forceinline__ void lts_finish(CarState& cs, const OfdmCarrierTable&
             cs.tmpf[i] = cnorm(csub(h1, h0));
             cs.tmpg[i] = __fdiv_rn(__fadd_rn(cnorm(h0), cnorm(h1)), 2.0f);
             ok = 1;
-        }
+        } else { cs.tmpf[i] = 0.f; cs.tmpg[i] = 0.f; }
         cs.flag[i] = ok;
     }
     gsync<G>();
     if (g == 0) {
-        float noise_sum = 0.f, signal_sum = 0.f;
-        int cnt = 0;
-        for (int i = 0; i < nd; ++i) if (cs.flag[i]) { noise_sum += cs.tmpf[i]; signal_sum += cs.tmpg[i]; ++cnt; }
+        const float noise_sum = ordered_sum(cs.tmpf, nd), signal_sum = ordered_sum(cs.tmpg, nd);
+        const int cnt = count_flags(cs.flag, nd);
         if (cnt > 0) {
             const float nvar = noise_sum / (4.0f * cnt);
             const float sp = signal_sum / cnt;
@@ -381,7 +435,20 @@ __device__ __forceinline__ void lts_finish(CarState& cs, const OfdmCarrierTable&
         cs.s.snr_count = 2;                                       // :642
     }
     if (a.h_lts_tap)
+        #pragma unroll 1
         for (int c = g; c < nc; c += G) reinterpret_cast<float2*>(a.h_lts_tap)[f * nc + c] = cs.H[c];
+    gsync<G>();
+    // The de-slope / re-slope phasors of the pilot interpolation (:897, :935) depend only on the
+    // LTS slope and the carrier number: evaluate them once per frame.  hps[] is dead from here on.
+    {
+        const int np = car.n_pilot;
+        float2* rot_p = cs.hps[0];
+        float2* rot_d = cs.hps[1];
+        #pragma unroll 1
+        for (int i = g; i < np; i += G) rot_p[i] = cexpj(-cs.s.slope * static_cast<float>(car.car_k[car.pilot_car[i]]));
+        #pragma unroll 1
+        for (int i = g; i < nd; i += G) rot_d[i] = cexpj(cs.s.slope * static_cast<float>(car.car_k[car.data_car[i]]));
+    }
     gsync<G>();
 }
 
@@ -409,6 +476,7 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
     if (np > 0) {
         float alpha;
         if (first) alpha = 1.0f; else if (differential) alpha = 0.5f; else alpha = 0.9f;
+        #pragma unroll 1
         for (int i = g; i < np; i += G) {
             const int c = car.pilot_car[i];
             // rx / (+-1, 0) (:687): libgcc's complex division by a unit real is a sign change
@@ -419,17 +487,18 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
         if (differential) {
             // carrier phase recovery on the first symbol that yields a usable average (:699-714)
             if (g == 0 && !cs.s.cpc_init) {
-                float2 h_sum = make_float2(0.f, 0.f);
-                for (int i = 0; i < np; ++i) h_sum = cadd(h_sum, cs.pil_ls[i]);
+                const float2 h_sum = ordered_csum(cs.pil_ls, np);
                 const float2 h_avg = cdivf(h_sum, static_cast<float>(np));
                 const float avg_mag = cabs(h_avg);
                 if (avg_mag > 0.01f) { cs.s.cpc = cdivf(cconj(h_avg), avg_mag); cs.s.cpc_init = 1; }
             }
             gsync<G>();
+            #pragma unroll 1
             for (int i = g; i < np; i += G) cs.pil_ls[i] = cmul(cs.pil_ls[i], cs.s.cpc);
             gsync<G>();
         } else {
             // CPE: common phase of pilot LS vs current H, applied to every carrier (:720-756)
+            #pragma unroll 1
             for (int i = g; i < np; i += G) {
                 const int c = car.pilot_car[i];
                 const float2 h_old = cs.H[c];
@@ -440,13 +509,12 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
                     const float mag = cabs(ratio);
                     if (mag > 1e-6f) { cs.tmpc[i] = cscale(cdivf(ratio, mag), h_old_mag); cs.tmpf[i] = h_old_mag; ok = 1; }
                 }
-                cs.flag[i] = ok;
+                if (!ok) { cs.tmpc[i] = make_float2(0.f, 0.f); cs.tmpf[i] = 0.f; }
             }
             gsync<G>();
             if (g == 0) {
-                float2 cpe_sum = make_float2(0.f, 0.f);
-                float w = 0.f;
-                for (int i = 0; i < np; ++i) if (cs.flag[i]) { cpe_sum = cadd(cpe_sum, cs.tmpc[i]); w += cs.tmpf[i]; }
+                const float2 cpe_sum = ordered_csum(cs.tmpc, np);
+                const float w = ordered_sum(cs.tmpf, np);
                 int apply = 0;
                 if (w > 0.01f) {
                     const float ph = carg(cpe_sum);
@@ -456,26 +524,35 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
             }
             gsync<G>();
             if (cs.s.apply_cpe)
+                #pragma unroll 1
                 for (int c = g; c < nc; c += G) cs.H[c] = cmul(cs.H[c], cs.s.cpe);
             gsync<G>();
         }
         // pilot power, temporal noise count, smoothed update at the pilots (:778-820)
+        #pragma unroll 1
+        for (int i = g; i < np; i += G) {
+            const float2 ch = cs.pil_ls[i];
+            cs.tmpg[i] = cnorm(ch);
+            float term = 0.f;
+            int ok = 0;
+            if (cs.s.have_prev_pilot) {
+                const float2 ph = cs.prev_pilot[i];
+                if (cnorm(ph) > 1e-6f && cnorm(ch) > 1e-6f) { term = cnorm(csub(ch, ph)); ok = 1; }
+            }
+            cs.tmpf[i] = term;
+            cs.flag[i] = ok;
+        }
+        gsync<G>();
         if (g == 0) {
-            float sp = 0.f;
-            for (int i = 0; i < np; ++i) sp += cnorm(cs.pil_ls[i]);
-            cs.s.signal_power = sp / static_cast<float>(np);
-            int ncount = 0;
-            float npow = 0.f;
-            if (cs.s.have_prev_pilot)
-                for (int i = 0; i < np; ++i) {
-                    const float2 ph = cs.prev_pilot[i], ch = cs.pil_ls[i];
-                    if (cnorm(ph) > 1e-6f && cnorm(ch) > 1e-6f) { npow += cnorm(csub(ch, ph)); ++ncount; }
-                }
+            cs.s.signal_power = ordered_sum(cs.tmpg, np) / static_cast<float>(np);
+            int ncount = count_flags(cs.flag, np);
+            float npow = ordered_sum(cs.tmpf, np);
             if (ncount == 0) { npow = cs.s.signal_power / 31.6f; ncount = 1; }
             // the SNR EMA only looks at (noise_count > 1) and (noise_power_sum > 0) (:1025-1040)
             cs.s.noise_count = (npow > 0.0f) ? ncount : 0;
         }
         gsync<G>();
+        #pragma unroll 1
         for (int i = g; i < np; i += G) {
             const int c = car.pilot_car[i];
             const float2 h_old = cs.H[c];
@@ -492,12 +569,12 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
         gsync<G>();
         // interpolation to the data carriers (:885-957)
         if (!differential) {
+            #pragma unroll 1
             for (int i = g; i < np; i += G) {
-                const int c = car.pilot_car[i];
-                const float ph = -cs.s.slope * static_cast<float>(car.car_k[c]);
-                cs.desloped[i] = cmul(cs.H[c], cexpj(ph));
+                cs.desloped[i] = cmul(cs.H[car.pilot_car[i]], cs.hps[0][i]);
             }
             gsync<G>();
+            #pragma unroll 1
             for (int i = g; i < nd; i += G) {
                 const int c = car.data_car[i];
                 const int lo = car.interp_lo[i], hi = car.interp_hi[i];
@@ -506,8 +583,7 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
                 if (lo >= 0 && hi >= 0) ih = cadd(cscale(cs.desloped[lo], 1.0f - al), cscale(cs.desloped[hi], al));
                 else if (lo >= 0) ih = cs.desloped[lo];
                 else if (hi >= 0) ih = cs.desloped[hi];
-                const float ph = cs.s.slope * static_cast<float>(car.car_k[c]);
-                float2 h = cmul(ih, cexpj(ph));
+                float2 h = cmul(ih, cs.hps[1][i]);
                 // decision-directed phase refinement from the previous symbol (:964-975)
                 if (cs.s.have_dd && cs.s.snr_count >= 3) {
                     const float corr = cs.dd[i];
@@ -516,6 +592,7 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
                 cs.H[c] = h;
             }
         } else {
+            #pragma unroll 1
             for (int i = g; i < nd; i += G) {
                 const int c = car.data_car[i];
                 const int lo = car.interp_lo[i], hi = car.interp_hi[i];
@@ -544,16 +621,16 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
     }
 
     // ----------------------- equalize (channel_equalizer.cpp:1259-1451) -----------------------
+    #pragma unroll 1
     for (int i = g; i < nd; i += G) cs.hpow[i] = cnorm(cs.H[car.data_car[i]]);
     gsync<G>();
     if (g == 0) {
-        float s = 0.f;
-        for (int i = 0; i < nd; ++i) s += cs.hpow[i];
-        cs.s.avg_h_power = s / static_cast<float>(nd);
+        cs.s.avg_h_power = ordered_sum(cs.hpow, nd) / static_cast<float>(nd);
     }
     gsync<G>();
     const bool dd_mod = !differential && (mod == RIA_QPSK || mod == RIA_BPSK || mod == RIA_QAM16 ||
                                           mod == RIA_QAM32 || mod == RIA_QAM64);
+    #pragma unroll 1
     for (int i = g; i < nd; i += G) {
         const int c = car.data_car[i];
         const float2 rx = cs.bin[c], h = cs.H[c];
@@ -599,6 +676,7 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
     gsync<G>();
 
     // ----------------------- demodulateSymbol (demodulator.cpp:208-508) -----------------------
+    #pragma unroll 1
     for (int i = g; i < nd; i += G) {
         const float2 sym = cs.eq[i];
         // per-carrier |eq| EMA / variance (:240-254)
@@ -714,7 +792,9 @@ __device__ __forceinline__ void frame_outputs(CarState& cs, const OfdmCarrierTab
     const int nd = car.n_data;
     const int n_llr = (n_data_sym > 0 ? n_data_sym : 0) * nd * a.bits_per_carrier;
     float* llr_out = a.llr + f * a.llr_stride;
+    #pragma unroll 1
     for (int i = n_llr + g; i < a.llr_stride; i += G) llr_out[i] = 0.0f;
+    #pragma unroll 1
     for (int i = g; i < nd; i += G) cs.tmpf[i] = cabs(cs.H[car.data_car[i]]);
     gsync<G>();
     if (g == 0) {
