@@ -89,6 +89,8 @@ extern "C" int ria_ctx_create(int device, ria_ctx** out) {
         return RIA_E_UNSUPPORTED;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)

@@ -36,7 +36,7 @@ namespace ria {
 namespace {
 
 constexpr int kN = RIA_LDPC_N;
-constexpr int kWarpsPerCta = 8;
+constexpr int kMaxWarpsPerCta = 16;
 
 __device__ __forceinline__ float clamp50(float x) {
     // std::max(-50.0f, std::min(50.0f, x)) with libstdc++ semantics (NaN -> 50)
@@ -48,6 +48,8 @@ struct LdpcGather {
     int frame_mode;     // 0: llr_g is [n_cw][648];  1: llr_g is [n_frames][soft_stride], n_cw = 4 n_frames
     int soft_stride;
     int step;           // ChannelInterleaver step, 0 = no channel interleaving
+    int inv_step;       // step^-1 mod 648 (0 = none: scalar gather), used by the coalesced load
+    int vec_ok;         // rows are 16-byte aligned: one float4 per interleaver position
 };
 
 struct CheckIn {
@@ -82,8 +84,7 @@ __device__ __forceinline__ void check_update(const CheckIn& in, float factor, fl
     }
 }
 
-template <int W>
-__global__ void __launch_bounds__(W * 32)
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32)
 ldpc_decode_kernel(const float* __restrict__ llr_g, long long n_cw, const LdpcGather gather,
                    const uint16_t* __restrict__ chk_var_g, const uint16_t* __restrict__ var_slot_g,
                    int k, int m, int dv_max, int max_iter, float factor,
@@ -134,9 +135,27 @@ ldpc_decode_kernel(const float* __restrict__ llr_g, long long n_cw, const LdpcGa
             const long long fr = cw >> 2;
             const int c = static_cast<int>(cw & 3);
             const float* src = llr_g + fr * gather.soft_stride;
-            for (int p = lane; p < kN; p += 32) {
-                const int b = gather.step ? (p * gather.step) % kN : p;
-                llr[p] = __ldg(src + 4 * b + ((c + b) & 3));
+            if (gather.vec_ok && (gather.step == 0 || gather.inv_step != 0)) {
+                // Walk the frame in memory order: position b holds the four codewords' bit b as one
+                // float4 (coalesced, and the four warps of a frame hit the same lines); this warp
+                // keeps component (c + b) & 3 and scatters it to p = b * step^-1 mod 648.
+                const float4* src4 = reinterpret_cast<const float4*>(src);
+                const int inv = gather.step ? gather.inv_step : 1;
+                int p = (lane * inv) % kN;
+                const int dp = (32 * inv) % kN;
+                for (int b = lane; b < kN; b += 32) {
+                    const float4 v = __ldg(src4 + b);
+                    const int sel = (c + b) & 3;
+                    const float lo = (sel & 1) ? v.y : v.x, hi = (sel & 1) ? v.w : v.z;
+                    llr[p] = (sel & 2) ? hi : lo;
+                    p += dp;
+                    if (p >= kN) p -= kN;
+                }
+            } else {
+                for (int p = lane; p < kN; p += 32) {
+                    const int b = gather.step ? (p * gather.step) % kN : p;
+                    llr[p] = __ldg(src + 4 * b + ((c + b) & 3));
+                }
             }
         }
         __syncwarp();
@@ -150,44 +169,68 @@ ldpc_decode_kernel(const float* __restrict__ llr_g, long long n_cw, const LdpcGa
         int iters = max_iter;
         bool success = false;
         // it == max_iter is a parity-only pass over the totals of the last iteration.
+        // The parity of iteration it-1 is seen at the start of pass `it`.  For it <= 3 -- where
+        // clean frames converge -- it is a separate cheap pass, so a converged codeword does not
+        // pay for a check update it will discard; later passes fold it into the update.
         for (int it = 0; it <= max_iter; ++it) {
+            const bool fused_parity = it > 3;
+            if (it >= 1 && !fused_parity) {
+                bool bad = false;
+                for (int i = lane; i < m; i += 32) {
+                    const uint4 vi = chk_var[i];
+                    const int cnt = vi.w >> 16;
+                    const unsigned idx[6] = {vi.x & 0xFFFFu, vi.x >> 16, vi.y & 0xFFFFu,
+                                             vi.y >> 16,     vi.z & 0xFFFFu, vi.z >> 16};
+                    unsigned par = (reinterpret_cast<const float*>(msg + m + i)[3] < 0.0f) ? 1u : 0u;
+#pragma unroll
+                    for (int d = 0; d < 6; ++d)
+                        if (d < cnt) par ^= (tot[idx[d]] < 0.0f) ? 1u : 0u;
+                    bad |= (par != 0);
+                }
+                if (!__any_sync(0xffffffffu, bad)) { success = true; iters = it - 1; break; }
+                if (it == max_iter) break;
+            }
             // ================= phase A: checks =================
             bool bad = false;
-            for (int i = lane; i < m; i += 32) {
-                const uint4 vi = chk_var[i];
-                const float4 c_lo = msg[i];
-                const float4 c_hi = msg[m + i];
-                const int cnt = vi.w >> 16;
-                const unsigned idx[6] = {vi.x & 0xFFFFu, vi.x >> 16, vi.y & 0xFFFFu,
-                                         vi.y >> 16,     vi.z & 0xFFFFu, vi.z >> 16};
-                const float cold[7] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z};
-                CheckIn in;
-                in.cnt = cnt;
-                unsigned par = 0;
+            if (it < max_iter || fused_parity) {
+                for (int i = lane; i < m; i += 32) {
+                    const uint4 vi = chk_var[i];
+                    const float4 c_lo = msg[i];
+                    const float4 c_hi = msg[m + i];
+                    const int cnt = vi.w >> 16;
+                    const unsigned idx[6] = {vi.x & 0xFFFFu, vi.x >> 16, vi.y & 0xFFFFu,
+                                             vi.y >> 16,     vi.z & 0xFFFFu, vi.z >> 16};
+                    const float cold[7] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z};
+                    CheckIn in;
+                    in.cnt = cnt;
+                    unsigned par = 0;
 #pragma unroll
-                for (int d = 0; d < 6; ++d) {
-                    float T = 0.0f;
-                    if (d < cnt) T = tot[idx[d]];
-                    par ^= (d < cnt && T < 0.0f) ? 1u : 0u;
-                    in.v[d] = (it == 0) ? T : clamp50(__fsub_rn(T, cold[d]));
-                }
-                {
-                    const float T = c_hi.w;                     // parity variable's total
-                    par ^= (T < 0.0f) ? 1u : 0u;
-                    in.v[6] = (it == 0) ? T : clamp50(__fsub_rn(T, cold[6]));
-                }
-                bad |= (par != 0);
-                if (it < max_iter) {
-                    float out[7];
-                    check_update(in, factor, out);
-                    const float tp = __fadd_rn(llr[k + i], out[6]);
-                    msg[i] = make_float4(out[0], out[1], out[2], out[3]);
-                    msg[m + i] = make_float4(out[4], out[5], out[6], tp);
+                    for (int d = 0; d < 6; ++d) {
+                        float T = 0.0f;
+                        if (d < cnt) T = tot[idx[d]];
+                        par ^= (d < cnt && T < 0.0f) ? 1u : 0u;
+                        in.v[d] = (it == 0) ? T : clamp50(__fsub_rn(T, cold[d]));
+                    }
+                    {
+                        const float T = c_hi.w;                     // parity variable's total
+                        par ^= (T < 0.0f) ? 1u : 0u;
+                        in.v[6] = (it == 0) ? T : clamp50(__fsub_rn(T, cold[6]));
+                    }
+                    bad |= (par != 0);
+                    if (it < max_iter) {
+                        float out[7];
+                        check_update(in, factor, out);
+                        const float tp = __fadd_rn(llr[k + i], out[6]);
+                        msg[i] = make_float4(out[0], out[1], out[2], out[3]);
+                        msg[m + i] = make_float4(out[4], out[5], out[6], tp);
+                    }
                 }
             }
-            // totals examined in this pass belong to iteration it-1
-            const bool any_bad = __any_sync(0xffffffffu, bad);
-            if (it > 0 && !any_bad) { success = true; iters = it - 1; break; }
+            if (fused_parity) {
+                // totals examined in this pass belong to iteration it-1
+                const bool any_bad = __any_sync(0xffffffffu, bad);
+                if (!any_bad) { success = true; iters = it - 1; break; }
+            }
             if (it == max_iter) break;
             __syncwarp();
             // ================= phase B: info variables =================
@@ -205,15 +248,13 @@ ldpc_decode_kernel(const float* __restrict__ llr_g, long long n_cw, const LdpcGa
         }
 
         // ---- outputs: pack info hard bits MSB-first (ldpc_decoder.cpp:240-257) ----
-        for (int b = lane; b < info_stride; b += 32) {     // bytes past ceil(k/8) are zeroed
-            unsigned byte = 0;
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const int j = b * 8 + t;
-                const unsigned bit = (j < k && tot[j] < 0.0f) ? 1u : 0u;
-                byte = (byte << 1) | bit;
-            }
-            info_g[cw * info_stride + b] = static_cast<uint8_t>(byte);
+        // one ballot per 32 variables; bit-reversed it reads as 4 output bytes, MSB = lowest index
+        for (int r = 0; 4 * r < info_stride; ++r) {        // bytes past ceil(k/8) come out as zero
+            const int j = 32 * r + lane;
+            const bool bit = (j < k) && (tot[j] < 0.0f);
+            const unsigned word = __brev(__ballot_sync(0xffffffffu, bit));
+            if (lane < 4 && 4 * r + lane < info_stride)
+                info_g[cw * info_stride + 4 * r + lane] = static_cast<uint8_t>(word >> (24 - 8 * lane));
         }
         if (lane == 0) {
             ok_g[cw] = success ? 1 : 0;
@@ -284,10 +325,20 @@ int ria::ldpc_launch(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor,
     if (rc != RIA_OK) return rc;
     if (info_stride < (t->k + 7) / 8) return set_error(ctx, RIA_E_INVAL, "ldpc: info_stride too small");
 
-    constexpr int W = kWarpsPerCta;
+    // warps (= codewords) per CTA: whatever keeps the most codewords resident per SM
+    auto kern = ldpc_decode_kernel;
+    int W = 0, best_warps = 0;
+    for (int w = 4; w <= kMaxWarpsPerCta; ++w) {
+        const size_t need = ldpc_smem_bytes(t->k, t->m, t->dv_max, w) + 1024;      // + per-CTA reservation
+        if (need > ctx->smem_optin + 1024) break;
+        const int ctas = static_cast<int>(ctx->smem_per_sm / need);
+        const int warps = ctas * w > 48 ? 48 : ctas * w;
+        if (warps > best_warps) { best_warps = warps; W = w; }
+    }
+    if (W == 0) return set_error(ctx, RIA_E_UNSUPPORTED, "ldpc: kernel does not fit in shared memory");
     const size_t smem = ldpc_smem_bytes(t->k, t->m, t->dv_max, W);
-    auto kern = ldpc_decode_kernel<W>;
     RIA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RIA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int ctas_per_sm = 0;
     RIA_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, W * 32, smem));
     if (ctas_per_sm < 1) return set_error(ctx, RIA_E_UNSUPPORTED, "ldpc: kernel does not fit (smem %zu)", smem);
@@ -295,7 +346,11 @@ int ria::ldpc_launch(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor,
     long long grid = static_cast<long long>(ctx->sm_count) * ctas_per_sm;
     if (grid > want) grid = want;
     RIA_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int), ctx->stream));
-    LdpcGather gather{frame_mode, soft_stride, step};
+    int inv_step = 0;
+    if (step > 0)
+        for (int x = 1; x < kN; ++x) if ((static_cast<long long>(x) * step) % kN == 1) { inv_step = x; break; }
+    const int vec_ok = frame_mode && (soft_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(llr_dev) & 15) == 0);
+    LdpcGather gather{frame_mode, soft_stride, step, inv_step, vec_ok};
     time_begin(ctx, KK_LDPC);
     kern<<<static_cast<unsigned>(grid), W * 32, smem, ctx->stream>>>(
         llr_dev, n_cw, gather, t->chk_var, t->var_slot, t->k, t->m, t->dv_max, max_iter, min_sum_factor,

@@ -274,17 +274,6 @@ __device__ __forceinline__ float2 ordered_csum(const float2* a, int n) {
     for (; i < n; ++i) s = cadd(s, a[i]);
     return s;
 }
-// Several ordered sums of the same length at once: lane j < n_rows walks row j (rows are
-// kMaxCarriers floats apart), so k sums cost one pass instead of k.  Result of row j in lane j.
-__device__ __forceinline__ float ordered_sum_rows(const float* rows, int n_rows, int n, int lane) {
-    float s = 0.f;
-    if (lane < n_rows) {
-        const float* a = rows + lane * kMaxCarriers;
-#pragma unroll 1
-        for (int i = 0; i < n; ++i) s = __fadd_rn(s, a[i]);
-    }
-    return s;
-}
 
 // =============================== carrier-domain processing =================================
 // Everything below works on cs.bin[] (the carrier bins of the current symbol) with a group of

@@ -52,6 +52,8 @@ struct LdpcCodeDev {
 struct ria_ctx {
     int device = 0;
     int sm_count = 0;
+    size_t smem_per_sm = 0;                 // shared memory per SM / opt-in maximum per CTA
+    size_t smem_optin = 0;
     cudaStream_t stream = nullptr;      // stream all work is issued on
     cudaStream_t own_stream = nullptr;  // created by us (destroyed with the ctx)
     cudaStream_t copy_stream = nullptr; // H2D/D2H staging for *_host entry points
