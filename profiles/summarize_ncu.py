@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Condense an `ncu --set full` report into the few numbers DESIGN.md argues with.
+
+usage: python profiles/summarize_ncu.py gpurun_out/<name>.ncu-rep > profiles/<name>.summary.txt
+"""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__inst_issued.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+]
+STALLS = "smsp__average_warps_issue_stalled_"
+
+
+def main():
+    rep = sys.argv[1]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        print(f"== {name}")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"  {k:72s} {r[i]} {units[i]}")
+        stalls = [(float(r[i]), h[len(STALLS):-len('_per_issue_active.ratio')]) for i, h in enumerate(hdr)
+                  if h.startswith(STALLS) and h.endswith("_per_issue_active.ratio") and r[i] not in ("", "n/a")]
+        print("  warp stall cycles per issued instruction: " +
+              ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:7]))
+
+
+if __name__ == "__main__":
+    main()

@@ -67,3 +67,18 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cpp", ".h", ".cuh", ".hpp")) or fn == "Makefile":
                 text = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "oracle" not in text.replace("test oracle", ""), f"{fn} mentions oracle/"
+
+
+def test_no_packed_fma_contraction_in_sass():
+    """The FFT butterflies use Blackwell's packed fp32 instructions (FADD2 / FMUL2).  ptxas fuses a
+    packed multiply that feeds a packed add into FFMA2 even with --fmad=false, which would change
+    the rounding of every butterfly; the kernels route products through scalar adds instead.
+    Guard it: the library must contain packed adds/multiplies and no FFMA2 at all."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ria_b200", "libria_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], check=True, capture_output=True, text=True).stdout
+    assert "FADD2" in sass and "FMUL2" in sass
+    assert "FFMA2" not in sass
