@@ -59,26 +59,30 @@ struct CheckIn {
 
 // c2v for all 7 slots of one check from its v2c values.  Unused info slots (d >= cnt) are
 // neutral: magnitude FLT_MAX, positive sign.
+// ldpc_decoder.cpp:186-203 keeps (min1, min_idx, min2) with strict `<` updates and sends min2 to
+// min_idx, min1 to everyone else.  Selecting by VALUE (|v_d| == min1 ? min2 : min1) is the same
+// function: when the minimum is tied the strict updates leave min2 == min1, so every tied edge
+// gets that value either way.  That turns the index bookkeeping into three min/max per edge.
 __device__ __forceinline__ void check_update(const CheckIn& in, float factor, float (&out)[7]) {
     float m1 = FLT_MAX, m2 = FLT_MAX;
-    int arg = -1;
+    float a[7];
     unsigned neg = 0;
 #pragma unroll
     for (int d = 0; d < 7; ++d) {
         const bool used = (d == 6) || (d < in.cnt);
-        float a = fabsf(in.v[d]);
-        a = (a < FLT_MAX) ? a : FLT_MAX;            // `abs_msg < min_abs` never admits inf/NaN
-        a = used ? a : FLT_MAX;
+        float x = fminf(fabsf(in.v[d]), FLT_MAX);   // `abs_msg < min_abs` never admits inf/NaN
+        x = used ? x : FLT_MAX;
+        a[d] = x;
         if (used && in.v[d] < 0.0f) neg ^= (1u << d) | 0x80u;   // bit 7 = running product
-        if (a < m1) { m2 = m1; m1 = a; arg = d; }
-        else if (a < m2) { m2 = a; }
+        m2 = fminf(m2, fmaxf(m1, x));
+        m1 = fminf(m1, x);
     }
     const float s1 = __fmul_rn(m1, factor);
     const float s2 = __fmul_rn(m2, factor);
     const unsigned all_neg = (neg >> 7) & 1u;
 #pragma unroll
     for (int d = 0; d < 7; ++d) {
-        const float mag = (d == arg) ? s2 : s1;
+        const float mag = (a[d] == m1) ? s2 : s1;
         const unsigned sgn = all_neg ^ ((neg >> d) & 1u);
         out[d] = sgn ? -mag : mag;
     }

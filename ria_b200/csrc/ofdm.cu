@@ -124,21 +124,19 @@ struct FrameScalars {
     int have_dd;
 };
 
+constexpr int kMaxPilots = 32;      // pilot_spacing >= 2 (checked by ofdm_config_error)
+
 struct alignas(16) CarState {
     float2 bin[kMaxCarriers];
     float2 H[kMaxCarriers];
-    float2 hps[2][kMaxCarriers];
+    float2 hps[2][kMaxCarriers];        // LTS estimates; after the LTS: de-slope / re-slope phasors
     float2 tmpc[kMaxCarriers];
     float tmpf[kMaxCarriers];
-    float tmpg[kMaxCarriers];
+    float tmpg[kMaxCarriers];           // also |H|^2 of the data carriers during equalisation
     int   flag[kMaxCarriers];
-    float2 pil_ls[kMaxCarriers];
-    float2 prev_pilot[kMaxCarriers];
-    float2 desloped[kMaxCarriers];
-    float2 eq[kMaxCarriers];
-    float2 prev_eq[kMaxCarriers];
-    float cnv[kMaxCarriers];
-    float hpow[kMaxCarriers];
+    float2 pil_ls[kMaxPilots];
+    float2 prev_pilot[kMaxPilots];
+    float2 prev_eq[kMaxCarriers];       // differential reference; coherent: de-sloped pilot estimates
     float ema[kMaxCarriers];
     float var[kMaxCarriers];
     float dd[kMaxCarriers];
@@ -560,7 +558,7 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
         if (!differential) {
             #pragma unroll 1
             for (int i = g; i < np; i += G) {
-                cs.desloped[i] = cmul(cs.H[car.pilot_car[i]], cs.hps[0][i]);
+                cs.prev_eq[i] = cmul(cs.H[car.pilot_car[i]], cs.hps[0][i]);
             }
             gsync<G>();
             #pragma unroll 1
@@ -569,9 +567,9 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
                 const int lo = car.interp_lo[i], hi = car.interp_hi[i];
                 const float al = car.interp_alpha[i];
                 float2 ih = make_float2(0.f, 0.f);
-                if (lo >= 0 && hi >= 0) ih = cadd(cscale(cs.desloped[lo], 1.0f - al), cscale(cs.desloped[hi], al));
-                else if (lo >= 0) ih = cs.desloped[lo];
-                else if (hi >= 0) ih = cs.desloped[hi];
+                if (lo >= 0 && hi >= 0) ih = cadd(cscale(cs.prev_eq[lo], 1.0f - al), cscale(cs.prev_eq[hi], al));
+                else if (lo >= 0) ih = cs.prev_eq[lo];
+                else if (hi >= 0) ih = cs.prev_eq[hi];
                 float2 h = cmul(ih, cs.hps[1][i]);
                 // decision-directed phase refinement from the previous symbol (:964-975)
                 if (cs.s.have_dd && cs.s.snr_count >= 3) {
@@ -611,10 +609,10 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
 
     // ----------------------- equalize (channel_equalizer.cpp:1259-1451) -----------------------
     #pragma unroll 1
-    for (int i = g; i < nd; i += G) cs.hpow[i] = cnorm(cs.H[car.data_car[i]]);
+    for (int i = g; i < nd; i += G) cs.tmpg[i] = cnorm(cs.H[car.data_car[i]]);
     gsync<G>();
     if (g == 0) {
-        cs.s.avg_h_power = ordered_sum(cs.hpow, nd) / static_cast<float>(nd);
+        cs.s.avg_h_power = ordered_sum(cs.tmpg, nd) / static_cast<float>(nd);
     }
     gsync<G>();
     const bool dd_mod = !differential && (mod == RIA_QPSK || mod == RIA_BPSK || mod == RIA_QAM16 ||
@@ -623,7 +621,7 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
     for (int i = g; i < nd; i += G) {
         const int c = car.data_car[i];
         const float2 rx = cs.bin[c], h = cs.H[c];
-        const float h_power = cs.hpow[i];
+        const float h_power = cs.tmpg[i];
         const float fade_threshold = 0.25f * cs.s.avg_h_power;
         float2 e;
         float nvv;
@@ -658,16 +656,9 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
                 cs.dd[i] = ddv;
             }
         }
-        cs.eq[i] = e;
-        cs.cnv[i] = nvv;
-    }
-    if (g == 0 && dd_mod && cs.s.snr_count >= 2) cs.s.have_dd = 1;
-    gsync<G>();
-
-    // ----------------------- demodulateSymbol (demodulator.cpp:208-508) -----------------------
-    #pragma unroll 1
-    for (int i = g; i < nd; i += G) {
-        const float2 sym = cs.eq[i];
+        // ----------------------- demodulateSymbol (demodulator.cpp:208-508) -----------------------
+        // (same carrier, same thread: the equalised symbol and its noise variance stay in registers)
+        const float2 sym = e;
         // per-carrier |eq| EMA / variance (:240-254)
         const float mag = cabs(sym);
         float ema, var;
@@ -679,7 +670,7 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
             var += 0.3f * (delta * delta - var);
         }
         cs.ema[i] = ema; cs.var[i] = var;
-        float nv = cs.cnv[i] * ce_margin(mod);
+        float nv = nvv * ce_margin(mod);
         {
             const float mean_sq = ema * ema + 1e-6f;
             const float norm_var = var / mean_sq;
@@ -771,6 +762,8 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
             default: break;
         }
     }
+    gsync<G>();      // everybody has read snr_count / have_dd of this symbol
+    if (g == 0 && dd_mod && cs.s.snr_count >= 2) cs.s.have_dd = 1;
     gsync<G>();
 }
 

@@ -61,6 +61,8 @@ const char* ofdm_config_error(const ria_modem_config& c) {
     if (c.sample_rate == 0) return "sample_rate must be > 0";
     if (c.training_symbols != 2) return "training_symbols must be 2 (the reference waveform always sends 2 LTS)";
     if (c.use_pilots && c.pilot_spacing == 0) return "pilot_spacing must be > 0";
+    if (c.use_pilots && (c.num_carriers + c.pilot_spacing - 1) / c.pilot_spacing > 32)
+        return "more than 32 pilot carriers (pilot_spacing must be >= 2)";
     switch (c.modulation) {
         case RIA_DBPSK: case RIA_BPSK: case RIA_DQPSK: case RIA_QPSK:
         case RIA_QAM16: case RIA_QAM32: case RIA_QAM64: case RIA_QAM256: break;
