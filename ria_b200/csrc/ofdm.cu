@@ -42,6 +42,7 @@
 #include "rn_math.h"
 
 #include <cfloat>
+#include <cstddef>
 #include <cstdlib>
 
 #ifndef M_PI
@@ -142,6 +143,9 @@ struct alignas(16) CarState {
     float dd[kMaxCarriers];
     FrameScalars s;
 };
+static_assert(offsetof(CarState, tmpf) == offsetof(CarState, tmpc) + 4 * kMaxPilots * sizeof(float) &&
+              offsetof(CarState, tmpg) == offsetof(CarState, tmpf) + 2 * kMaxPilots * sizeof(float),
+              "the reduction rows are laid over tmpc | tmpf | tmpg");
 
 // what every stage needs to know about the batch
 struct KernelArgs {
@@ -270,6 +274,18 @@ __device__ __forceinline__ float2 ordered_csum(const float2* a, int n) {
     }
 #pragma unroll 1
     for (; i < n; ++i) s = cadd(s, a[i]);
+    return s;
+}
+
+// Several ordered sums of the same length at once: lane r < n_rows walks row r (rows are
+// kMaxPilots floats apart), so k sums cost one pass instead of k.  Result of row r in lane r.
+__device__ __forceinline__ float ordered_sum_rows(const float* rows, int n_rows, int n, int lane) {
+    float s = 0.f;
+    if (lane < n_rows) {
+        const float* a = rows + lane * kMaxPilots;
+#pragma unroll 2
+        for (int i = 0; i < n; ++i) s = __fadd_rn(s, a[i]);
+    }
     return s;
 }
 
@@ -463,15 +479,20 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
     if (np > 0) {
         float alpha;
         if (first) alpha = 1.0f; else if (differential) alpha = 0.5f; else alpha = 0.9f;
-        #pragma unroll 1
-        for (int i = g; i < np; i += G) {
-            const int c = car.pilot_car[i];
-            // rx / (+-1, 0) (:687): libgcc's complex division by a unit real is a sign change
-            const float2 rx = cs.bin[c];
-            cs.pil_ls[i] = (car.pilot_sign[i] < 0.0f) ? make_float2(-rx.x, -rx.y) : rx;
-        }
-        gsync<G>();
+        // Reduction rows (kMaxPilots floats each, laid over tmpc/tmpf/tmpg): 0,1 = CPE sum re/im,
+        // 2 = CPE weight, 3 = pilot power, 4 = temporal noise power.  Lane r of the first warp
+        // walks row r in index order, so the five ordered sums cost one pass.
+        float* red = reinterpret_cast<float*>(cs.tmpc);
+        float cpe_x = 0.f, cpe_y = 0.f, cpe_w = 0.f;
         if (differential) {
+            #pragma unroll 1
+            for (int i = g; i < np; i += G) {
+                const int c = car.pilot_car[i];
+                // rx / (+-1, 0) (:687): libgcc's complex division by a unit real is a sign change
+                const float2 rx = cs.bin[c];
+                cs.pil_ls[i] = (car.pilot_sign[i] < 0.0f) ? make_float2(-rx.x, -rx.y) : rx;
+            }
+            gsync<G>();
             // carrier phase recovery on the first symbol that yields a usable average (:699-714)
             if (g == 0 && !cs.s.cpc_init) {
                 const float2 h_sum = ordered_csum(cs.pil_ls, np);
@@ -481,64 +502,84 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
             }
             gsync<G>();
             #pragma unroll 1
-            for (int i = g; i < np; i += G) cs.pil_ls[i] = cmul(cs.pil_ls[i], cs.s.cpc);
-            gsync<G>();
+            for (int i = g; i < np; i += G) {
+                const float2 ch = cmul(cs.pil_ls[i], cs.s.cpc);
+                cs.pil_ls[i] = ch;
+                float term = 0.f;
+                int ok = 0;
+                if (cs.s.have_prev_pilot) {
+                    const float2 ph = cs.prev_pilot[i];
+                    if (cnorm(ph) > 1e-6f && cnorm(ch) > 1e-6f) { term = cnorm(csub(ch, ph)); ok = 1; }
+                }
+                red[3 * kMaxPilots + i] = cnorm(ch);
+                red[4 * kMaxPilots + i] = term;
+                cs.flag[i] = ok;
+            }
         } else {
-            // CPE: common phase of pilot LS vs current H, applied to every carrier (:720-756)
+            // LS estimate at the pilots, CPE terms (common phase of pilot LS vs current H, :720-756),
+            // pilot power and temporal noise terms (:778-800) in one pass over the pilots
             #pragma unroll 1
             for (int i = g; i < np; i += G) {
                 const int c = car.pilot_car[i];
+                const float2 rx = cs.bin[c];
+                const float2 ls = (car.pilot_sign[i] < 0.0f) ? make_float2(-rx.x, -rx.y) : rx;   // rx / (+-1, 0), :687
+                cs.pil_ls[i] = ls;
                 const float2 h_old = cs.H[c];
                 const float h_old_mag = cabs(h_old);
-                int ok = 0;
+                float2 t = make_float2(0.f, 0.f);      // adding zero leaves the ordered sums unchanged
+                float w = 0.f;
                 if (h_old_mag > 0.01f) {
-                    const float2 ratio = cmul(cs.pil_ls[i], cconj(h_old));
+                    const float2 ratio = cmul(ls, cconj(h_old));
                     const float mag = cabs(ratio);
-                    if (mag > 1e-6f) { cs.tmpc[i] = cscale(cdivf(ratio, mag), h_old_mag); cs.tmpf[i] = h_old_mag; ok = 1; }
+                    if (mag > 1e-6f) { t = cscale(cdivf(ratio, mag), h_old_mag); w = h_old_mag; }
                 }
-                if (!ok) { cs.tmpc[i] = make_float2(0.f, 0.f); cs.tmpf[i] = 0.f; }
+                float term = 0.f;
+                int ok = 0;
+                if (cs.s.have_prev_pilot) {
+                    const float2 ph = cs.prev_pilot[i];
+                    if (cnorm(ph) > 1e-6f && cnorm(ls) > 1e-6f) { term = cnorm(csub(ls, ph)); ok = 1; }
+                }
+                red[0 * kMaxPilots + i] = t.x;
+                red[1 * kMaxPilots + i] = t.y;
+                red[2 * kMaxPilots + i] = w;
+                red[3 * kMaxPilots + i] = cnorm(ls);
+                red[4 * kMaxPilots + i] = term;
+                cs.flag[i] = ok;
             }
-            gsync<G>();
+        }
+        gsync<G>();
+        if (g < 32) {       // the group's first warp (all of it)
+            const float rs = ordered_sum_rows(red, 5, np, g);
+            cpe_x = __shfl_sync(0xffffffffu, rs, 0);
+            cpe_y = __shfl_sync(0xffffffffu, rs, 1);
+            cpe_w = __shfl_sync(0xffffffffu, rs, 2);
+            const float sp = __shfl_sync(0xffffffffu, rs, 3);
+            float npow = __shfl_sync(0xffffffffu, rs, 4);
             if (g == 0) {
-                const float2 cpe_sum = ordered_csum(cs.tmpc, np);
-                const float w = ordered_sum(cs.tmpf, np);
-                int apply = 0;
-                if (w > 0.01f) {
-                    const float ph = carg(cpe_sum);
-                    if (fabsf(ph) > 0.001f) { cs.s.cpe = cexpj(ph); apply = 1; }
+                // pilot power and temporal noise count (:778-800)
+                cs.s.signal_power = sp / static_cast<float>(np);
+                int ncount = count_flags(cs.flag, np);
+                if (ncount == 0) { npow = cs.s.signal_power / 31.6f; ncount = 1; }
+                // the SNR EMA only looks at (noise_count > 1) and (noise_power_sum > 0) (:1025-1040)
+                cs.s.noise_count = (npow > 0.0f) ? ncount : 0;
+                if (!differential) {
+                    int apply = 0;
+                    if (cpe_w > 0.01f) {
+                        const float ph = atan2_rn(cpe_y, cpe_x);
+                        if (fabsf(ph) > 0.001f) { cs.s.cpe = cexpj(ph); apply = 1; }
+                    }
+                    cs.s.apply_cpe = apply;
                 }
-                cs.s.apply_cpe = apply;
             }
-            gsync<G>();
+        }
+        gsync<G>();
+        if (!differential) {
             if (cs.s.apply_cpe)
                 #pragma unroll 1
                 for (int c = g; c < nc; c += G) cs.H[c] = cmul(cs.H[c], cs.s.cpe);
             gsync<G>();
         }
-        // pilot power, temporal noise count, smoothed update at the pilots (:778-820)
-        #pragma unroll 1
-        for (int i = g; i < np; i += G) {
-            const float2 ch = cs.pil_ls[i];
-            cs.tmpg[i] = cnorm(ch);
-            float term = 0.f;
-            int ok = 0;
-            if (cs.s.have_prev_pilot) {
-                const float2 ph = cs.prev_pilot[i];
-                if (cnorm(ph) > 1e-6f && cnorm(ch) > 1e-6f) { term = cnorm(csub(ch, ph)); ok = 1; }
-            }
-            cs.tmpf[i] = term;
-            cs.flag[i] = ok;
-        }
-        gsync<G>();
-        if (g == 0) {
-            cs.s.signal_power = ordered_sum(cs.tmpg, np) / static_cast<float>(np);
-            int ncount = count_flags(cs.flag, np);
-            float npow = ordered_sum(cs.tmpf, np);
-            if (ncount == 0) { npow = cs.s.signal_power / 31.6f; ncount = 1; }
-            // the SNR EMA only looks at (noise_count > 1) and (noise_power_sum > 0) (:1025-1040)
-            cs.s.noise_count = (npow > 0.0f) ? ncount : 0;
-        }
-        gsync<G>();
+        // smoothed update at the pilots (:801-820)
         #pragma unroll 1
         for (int i = g; i < np; i += G) {
             const int c = car.pilot_car[i];
