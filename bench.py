@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 
 KK_LDPC, KK_OFDM_DEMOD, KK_FRAME_STATUS, KK_AWGN = 0, 1, 2, 3
 KK_OFDM_FFT, KK_OFDM_CARRIER, KK_OFDM_PHASE = 11, 12, 13
+KK_MCDPSK, KK_CHIRP_SYNC, KK_CHASE, KK_MCDPSK_CFO = 4, 6, 7, 9
 
 
 # ---------------------------------------------------------------------------------------------
@@ -296,6 +297,187 @@ def cpu_baseline_ofdm(wl, frames_per_core):
 
 
 # ---------------------------------------------------------------------------------------------
+# workload: chirp-acquired MC-DPSK 4x spread with HARQ chase combining (BASELINE.json configs[2])
+# ---------------------------------------------------------------------------------------------
+
+class McdpskC3Workload:
+    """Every frame is received twice (HARQ): per reception the channel is simulated on the device
+    (AWGN at -8 dB over the whole transmission), the dual chirp is searched in the first 120 000
+    samples of the row (streaming_decoder.cpp:408-411), the frame is demodulated at the detected
+    training start with the detected CFO, its soft bits are chase-combined with the previous
+    reception and the LDPC R1/4 codeword is decoded.  A step is both receptions of all frames."""
+    name = "mcdpsk_dbpsk_10car_4x_awgn-8dB_chirp_chase"
+    metric = "decoded_frames_per_s"
+    unit = "frames/s"
+    dtype = "f32"
+    RATE, MAX_ITER, FACTOR, SNR_DB, POOL, LEAD, TAIL, WINDOW = 0, 50, 0.9375, -8.0, 64, 2000, 800, 120000
+
+    def __init__(self, n_frames: int):
+        self.n = n_frames
+        self._pool = None
+        self.row_len = self.frame_len = 0
+
+    def cfg(self):
+        from ria_b200 import mcdpsk
+        return mcdpsk.MultiCarrierDPSKConfig.level4_dbpsk(mcdpsk.SPREAD_4X)
+
+    def pool_host(self, seed=31):
+        if self._pool is None:
+            from ria_b200 import txsynth
+            rng = np.random.default_rng(seed)
+            pre = txsynth.chirp_preamble()
+            rows, sent = [], []
+            for _ in range(self.POOL):
+                data = rng.integers(0, 256, size=20, dtype=np.uint8)
+                info_bits = np.concatenate([np.unpackbits(data), np.zeros(2, np.uint8)])       # k = 162
+                cw = np.packbits(txsynth.ldpc_encode_bits(info_bits, self.RATE))
+                body = txsynth.mcdpsk_modulate_frame(self.cfg(), cw.tobytes())
+                self.frame_len = len(body)
+                rows.append(np.concatenate([np.zeros(self.LEAD, np.float32), pre, body, np.zeros(self.TAIL, np.float32)]))
+                sent.append(data)
+            self._pool = (np.stack(rows), np.stack(sent))
+            self.row_len = self._pool[0].shape[1]
+        return self._pool
+
+    def describe(self):
+        self.pool_host()
+        return {"workload": self.name, "frames_per_gpu": self.n, "receptions_per_frame": 2,
+                "row_samples": self.row_len, "frame_samples": self.frame_len, "modulation": "DBPSK",
+                "carriers": 10, "spreading": 4, "code_rate": "R1/4",
+                "channel": f"AWGN {self.SNR_DB} dB over the whole transmission, generated on the device "
+                           f"(Philox) inside the timed step, {self.POOL} distinct TX frames",
+                "chain": "per reception: AWGN -> dual-chirp sync (131072-pt FFT matched filter) -> Hilbert CFO "
+                         "correction -> 10-carrier correlation demod + 4x despreading -> chase combine -> "
+                         "LDPC R1/4 (0.9375, 50 it)",
+                "l2": "one reception of the batch (78 GB at 100k frames) exceeds the 126 MB L2; no flush needed"}
+
+    def setup(self, ctx, device, rank, world):
+        import torch
+        from ria_b200 import mcdpsk
+        self.torch, self.ctx, self.device = torch, ctx, device
+        pool, sent = self.pool_host()
+        self.pool_dev = torch.from_numpy(pool).to(device)
+        self.sent_dev = torch.from_numpy(sent).to(device)
+        self.first_id = rank * self.n
+        self.rows = torch.empty((self.n, self.row_len), dtype=torch.float32, device=device)
+        self.acc = torch.empty((self.n, 648), dtype=torch.float32, device=device)
+        self.chain = mcdpsk.McdpskRxChain(self.cfg(), self.RATE, self.MAX_ITER, self.FACTOR, 0.15, ctx)
+        self.out = None
+        self.first_ok = None
+        self.epoch = 0
+        torch.cuda.synchronize()
+
+    def step(self):
+        from ria_b200 import sim
+        for rec in (0, 1):
+            sim.awgn_batch(self.pool_dev, self.n, self.SNR_DB, seed=9000 + 2 * self.epoch + rec,
+                           first_frame_id=self.first_id, out=self.rows, ctx=self.ctx)
+            self.out = self.chain.process_batch(self.rows, self.frame_len, self.WINDOW, self.acc, rec == 0, self.out)
+            if rec == 0:
+                self.first_ok = self.out["ok"].clone()
+        self.epoch += 1
+
+    def units_per_step(self):
+        return float(self.n)
+
+    def samples_per_step(self):
+        return 2.0 * self.n * self.row_len
+
+    def kernels(self):
+        """kind -> (kernel names, ALGORITHMIC bytes per step); two receptions per frame."""
+        n2 = 2 * self.n
+        row, body, win = self.row_len * 4, self.frame_len * 4, self.WINDOW * 4
+        return {
+            KK_AWGN: ("awgn_kernel", n2 * 2 * row),
+            KK_CHIRP_SYNC: ("chirp_* (pack, 3-stage FFT x3, product, peak)", n2 * win),
+            KK_MCDPSK_CFO: ("mcdpsk_phase_scan_kernel + mcdpsk_cfo_kernel", n2 * 2 * body),
+            KK_MCDPSK: ("mcdpsk_demod_kernel", n2 * (body + 652 * 4)),
+            KK_CHASE: ("chase_combine_kernel", n2 * 3 * 648 * 4),
+            KK_LDPC: ("ldpc_decode_kernel", n2 * (648 * 4 + 24 + 5)),
+        }
+
+    def counters(self):
+        """[frames, ok after the first reception, ok after chase combining, decoded-but-wrong payload, sum iters]"""
+        torch = self.torch
+        ok2 = self.out["ok"].bool()
+        want = self.sent_dev[(torch.arange(self.n, device=self.device) + self.first_id) % self.POOL]
+        wrong = (self.out["info"][:, :20] != want).any(dim=1) & ok2
+        return torch.stack([torch.tensor(self.n, device=self.device), self.first_ok.sum(), ok2.sum(), wrong.sum(),
+                            self.out["iters"].sum()]).to(torch.int64)
+
+    def counter_dict(self, c):
+        return {"frames": int(c[0]), "frames_ok_first_reception": int(c[1]), "frames_ok_after_chase_combining": int(c[2]),
+                "decoded_but_wrong_payload": int(c[3]), "mean_ldpc_iters_second_pass": float(c[4]) / max(1, int(c[0]))}
+
+    def setup_e2e(self, n_e2e):
+        torch = self.torch
+        self.e2e_n = n_e2e = min(n_e2e, self.n, 2048)
+        pin = torch.empty((n_e2e, self.row_len), dtype=torch.float32, pin_memory=True)
+        pin.copy_(self.rows[:n_e2e])
+        torch.cuda.synchronize()
+        self._pin = pin
+
+    def step_e2e(self):
+        return self.chain.process_batch_host(self._pin, self.frame_len, self.WINDOW)
+
+    def e2e_units(self):
+        return float(self.e2e_n)
+
+    def e2e_bytes(self):
+        return (self.e2e_n * self.row_len * 4, self.e2e_n * (24 + 1 + 4 + 32))
+
+
+def _cpu_mcdpsk_worker(args):
+    """One process per core: reference detectDualChirp + MC-DPSK process + LDPC on its own rows."""
+    _, n_frames, seed, _ = args
+    from oracle.bindings import McdpskConfig, Ref
+    wl = McdpskC3Workload(n_frames)
+    ref = Ref()
+    pool, _ = wl.pool_host()
+    cfg = McdpskConfig.from_buffer_copy(bytes(wl.cfg()))
+    rng = np.random.default_rng(seed)
+    rows = []
+    for i in range(n_frames):
+        tx = pool[i % len(pool)]
+        p = float(np.mean(tx.astype(np.float64) ** 2))
+        rows.append((tx + rng.standard_normal(len(tx)).astype(np.float32) *
+                     np.float32(np.sqrt(p / 10 ** (wl.SNR_DB / 10)))).astype(np.float32))
+    ok = 0
+    t0 = time.perf_counter()
+    for rx in rows:
+        s = ref.chirp_detect_dual(rx[:wl.WINDOW], 0.15)
+        if not s.detected:
+            continue
+        start = int(s.aux) + 28800
+        r = ref.mcdpsk_process(cfg, rx[start:start + wl.frame_len], float(s.cfo_hz))
+        if len(r["soft"]) >= 648:
+            _, okk, _ = ref.ldpc_decode_batch(wl.RATE, r["soft"][:648], wl.MAX_ITER, wl.FACTOR, 24)
+            ok += int(okk[0])
+    return time.perf_counter() - t0, ok
+
+
+def cpu_baseline_mcdpsk(wl, frames_per_core):
+    import multiprocessing as mp
+    from oracle.bindings import Ref
+    if not Ref.available():
+        return {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference",
+                "sample": "oracle/_ref/libria_ref.so not present"}
+    cores = host_cores()
+    wl.pool_host()
+    jobs = [("mcdpsk_c3", frames_per_core, 2000 + 13 * c, "reference") for c in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_mcdpsk_worker, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    rate = sum(frames_per_core / b for b, _ in res)
+    ok = sum(o for _, o in res)
+    return {"value": rate, "unit": "frames/s", "cores": cores, "kind": "reference",
+            "sample": f"{frames_per_core} single receptions per core x {cores} cores ({ok}/{frames_per_core * cores} "
+                      f"decoded), reference detectDualChirp + MC-DPSK process + LDPC decodeSoft, one process per "
+                      f"core, {wall:.1f} s wall; the GPU figure counts TWO receptions per frame"}
+
+
+# ---------------------------------------------------------------------------------------------
 # workload: batched LDPC decode (BASELINE.json configs[1])
 # ---------------------------------------------------------------------------------------------
 
@@ -456,6 +638,8 @@ def cpu_baseline_ldpc(wl, per_rate_per_core):
 
 
 def make_workload(args):
+    if args.workload == "mcdpsk":
+        return McdpskC3Workload(args.batch or 100_000), cpu_baseline_mcdpsk, args.cpu_sample or 16
     if args.workload == "ldpc":
         return LdpcWorkload(args.batch or (1 << 20)), cpu_baseline_ldpc, args.cpu_sample or 4096
     return OfdmQam64Workload(args.batch or (1 << 20)), cpu_baseline_ofdm, args.cpu_sample or 6000
@@ -473,7 +657,7 @@ def run_reference(args):
         return
     import ria_b200  # noqa: F401  (host-side input synthesis only; no GPU work on this arm)
     wl, cpu_fn, sample = make_workload(args)
-    if isinstance(wl, OfdmQam64Workload):
+    if hasattr(wl, "pool_host"):
         wl.pool_host()                      # built once here, inherited by the forked workers
     for _ in range(args.warmup):
         cpu_fn(wl, max(16, sample // 16))
@@ -499,7 +683,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ria_b200", choices=["ria_b200", "reference"])
-    ap.add_argument("--workload", default="ofdm_qam64", choices=["ofdm_qam64", "ldpc"])
+    ap.add_argument("--workload", default="ofdm_qam64", choices=["ofdm_qam64", "ldpc", "mcdpsk"])
     ap.add_argument("--batch", type=int, default=0, help="frames (or codewords per rate) per GPU")
     ap.add_argument("--e2e-batch", type=int, default=1 << 16)
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames (codewords per rate) per core")
@@ -612,7 +796,7 @@ def main():
                         for k in kern_ms},
             "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "batch": getattr(wl, "e2e_n", args.e2e_batch),
-                    "api": "ria_ofdm_rx_frames_host / ria_ldpc_decode_batch_host (pinned host buffers)"},
+                    "api": "ria_ofdm_rx_frames_host / ria_mcdpsk_rx_frames_host / ria_ldpc_decode_batch_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

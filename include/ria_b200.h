@@ -310,6 +310,43 @@ int ria_mcdpsk_process_batch_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg,
                                  float* llr_dev, int32_t llr_stride, int32_t* n_llr_dev,
                                  float* fading_dev, float* cfo_out_dev);
 
+/* Same, for frames that sit somewhere inside their row: frame f starts at
+ * samples_dev + f*frame_stride + start_dev[f] (what the streaming decoder does with
+ * SyncResult::start_sample, src/gui/modem/streaming_decoder.cpp:1700-1760).  start_dev == NULL
+ * means 0.  A frame whose [start, start + frame_len) leaves the row reports 0 soft bits. */
+int ria_mcdpsk_process_batch_at_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg,
+                                    const float* samples_dev, int64_t frame_stride, int32_t frame_len,
+                                    const int32_t* start_dev,
+                                    const float* cfo_hz_dev, const float* phase_dev, int64_t n_frames,
+                                    float* llr_dev, int32_t llr_stride, int32_t* n_llr_dev,
+                                    float* fading_dev, float* cfo_out_dev);
+
+/* Whole receive chain for chirp-acquired MC-DPSK frames (one LDPC codeword per frame), one call:
+ * MCDPSKWaveform::detectSync (dual chirp, src/waveform/mc_dpsk_waveform.cpp:176-224) on the first
+ * sync_window samples of every row -> MCDPSKWaveform::process at the detected training start with
+ * the detected CFO (:294-338) -> fec::ChaseCache::store arithmetic into acc_dev[f][648]
+ * (first_reception != 0 overwrites, otherwise adds; src/fec/chase_cache.cpp:75-85) ->
+ * LDPCDecoder::decodeSoft on the combined soft bits.
+ *   samples_dev  fp32 rows [n][row_stride]; a row holds [noise][chirp preamble][training][ref][data]
+ *   frame_len    samples handed to process() from the training start (training + reference + data)
+ *   sync_dev     [n] what detectDualChirp returned (aux = down-chirp start)
+ * An undetected frame contributes all-zero soft bits and fails to decode. */
+int ria_mcdpsk_rx_frames_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg, const ria_chirp_config* chirp,
+                             const float* samples_dev, int64_t row_stride, int32_t sync_window,
+                             int32_t frame_len, float threshold, int64_t n_frames,
+                             int rate, int max_iter, float min_sum_factor,
+                             float* acc_dev, int first_reception,
+                             uint8_t* info_dev, int32_t info_stride, uint8_t* ok_dev, int32_t* iters_dev,
+                             ria_sync_result* sync_dev);
+
+/* Same with HOST buffers (single reception, no cache): chunked H2D -> chain -> D2H inside the call. */
+int ria_mcdpsk_rx_frames_host(ria_ctx* ctx, const ria_mcdpsk_config* cfg, const ria_chirp_config* chirp,
+                              const float* samples, int64_t row_stride, int32_t sync_window,
+                              int32_t frame_len, float threshold, int64_t n_frames,
+                              int rate, int max_iter, float min_sum_factor,
+                              uint8_t* info, int32_t info_stride, uint8_t* ok, int32_t* iters,
+                              ria_sync_result* sync);
+
 /* ---- HARQ chase combining ---------------------------------------------------------------------- */
 /* Arithmetic of fec::ChaseCache::store (src/fec/chase_cache.cpp:27-88) on cache slots resident in
  * HBM: item i with slot_dev[i] >= 0 either overwrites (first_dev[i] != 0: first reception) or

@@ -199,11 +199,56 @@ struct PeakArgs {
     ria_sync_result* out;
 };
 
-// sequential fp32 prefix sum of s^2 over [start, start+len) (:666-669), by one thread
-__device__ void prefix_energy(const float* s, int start, int len, float* c) {
-    float acc = 0.0f;
-    c[0] = 0.0f;
-    for (int i = 0; i < len; ++i) { const float v = s[start + i]; acc = __fadd_rn(acc, __fmul_rn(v, v)); c[i + 1] = acc; }
+// Sequential fp32 prefix sum of s^2 over [start, start+len) (:666-669).  The order of the adds is
+// part of the result, so one thread walks the chain -- but only the chain.  Three shared tiles
+// rotate through load -> chain -> store: while thread 0 adds through tile k (4-cycle dependent
+// FADDs, operands prefetched, no memory latency on the chain), the other warps square and stage
+// tile k+1 from global memory and write the prefix values of tile k-1 back, all coalesced.
+// Block-collective; ends with a barrier.
+constexpr int kPrefixTile = 2048;
+__device__ __forceinline__ void prefix_chain(float* tile, int n, float& acc) {
+    float4* t4 = reinterpret_cast<float4*>(tile);
+    const int n8 = n >> 3;
+    float4 a = t4[0], b = t4[1];
+    for (int j = 0; j < n8; ++j) {
+        float4 na = a, nb = b;
+        if (j + 1 < n8) { na = t4[2 * j + 2]; nb = t4[2 * j + 3]; }
+        acc = __fadd_rn(acc, a.x); a.x = acc; acc = __fadd_rn(acc, a.y); a.y = acc;
+        acc = __fadd_rn(acc, a.z); a.z = acc; acc = __fadd_rn(acc, a.w); a.w = acc;
+        acc = __fadd_rn(acc, b.x); b.x = acc; acc = __fadd_rn(acc, b.y); b.y = acc;
+        acc = __fadd_rn(acc, b.z); b.z = acc; acc = __fadd_rn(acc, b.w); b.w = acc;
+        t4[2 * j] = a; t4[2 * j + 1] = b;
+        a = na; b = nb;
+    }
+    for (int i = n8 << 3; i < n; ++i) { acc = __fadd_rn(acc, tile[i]); tile[i] = acc; }
+}
+
+__device__ void prefix_energy(const float* __restrict__ s, int start, int len, float* __restrict__ c,
+                              float (*tiles)[kPrefixTile]) {
+    const int tid = threadIdx.x;
+    const int n_tiles = (len + kPrefixTile - 1) / kPrefixTile;
+    float acc = 0.0f;                                   // only thread 0's copy is meaningful
+    if (tid == 0) c[0] = 0.0f;
+    // phase k: helpers load tile k, thread 0 chains tile k-1, helpers store tile k-2
+    for (int k = 0; k < n_tiles + 2; ++k) {
+        if (tid == 0) {
+            const int t = k - 1;
+            if (t >= 0 && t < n_tiles) prefix_chain(tiles[t % 3], min(kPrefixTile, len - t * kPrefixTile), acc);
+        } else {
+            if (k < n_tiles) {
+                const int base = k * kPrefixTile, n = min(kPrefixTile, len - base);
+                float* tl = tiles[k % 3];
+                for (int i = tid - 1; i < n; i += blockDim.x - 1) { const float v = s[start + base + i]; tl[i] = __fmul_rn(v, v); }
+            }
+            const int t = k - 2;
+            if (t >= 0) {
+                const int base = t * kPrefixTile, n = min(kPrefixTile, len - base);
+                const float* tl = tiles[t % 3];
+                for (int i = tid - 1; i < n; i += blockDim.x - 1) c[base + 1 + i] = tl[i];
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // normalised peak over pos < search_len (:677-689); corr index offset `off`
@@ -288,10 +333,11 @@ __device__ void td_detect(const float* s, int len, const float2* tmpl, int CL, f
     *out_pos = (best >= threshold) ? pos : -1;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 7)      // 7 x 148 = 1036 >= one 1024-window slice in a single wave
 chirp_peak_kernel(const PeakArgs a) {
     __shared__ float red_v[256];
     __shared__ int red_i[256];
+    __shared__ __align__(16) float tile[3][kPrefixTile];
     const long long f = blockIdx.x;
     const int tid = threadIdx.x;
     const float* s = a.samples + f * a.frame_stride;
@@ -307,8 +353,7 @@ chirp_peak_kernel(const PeakArgs a) {
 
     if (a.window >= 2 * CL + a.gap) {                       // :373-377
         // ---- up chirp over the whole window ----
-        if (tid == 0) prefix_energy(s, 0, n_in, c);
-        __syncthreads();
+        prefix_energy(s, 0, n_in, c, tile);
         float up_corr; int up_pos;
         peak_search(cu, 0, c, n_in - CL, CL, a.energy_up, red_v, red_i, &up_corr, &up_pos);
         res.correlation = up_corr;
@@ -325,8 +370,7 @@ chirp_peak_kernel(const PeakArgs a) {
                 if (dlen >= CL) {
                     float dn_corr; int dn_rel;
                     if (dlen >= 2 * CL) {
-                        if (tid == 0) prefix_energy(s, static_cast<int>(ds), min(dlen, kN), c);
-                        __syncthreads();
+                        prefix_energy(s, static_cast<int>(ds), min(dlen, kN), c, tile);
                         peak_search(cd, static_cast<int>(ds), c, min(dlen, kN) - CL, CL, a.energy_dn, red_v, red_i, &dn_corr, &dn_rel);
                         if (dn_corr < a.threshold) dn_rel = -1;
                     } else {

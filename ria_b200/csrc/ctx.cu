@@ -120,6 +120,7 @@ extern "C" int ria_ctx_destroy(ria_ctx* ctx) {
     for (auto* t : ctx->chirp_tables) ria::chirp_tables_free(t);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->ofdm_scratch) cudaFree(ctx->ofdm_scratch);
+    if (ctx->chain_scratch) cudaFree(ctx->chain_scratch);
     if (ctx->hilbert65) cudaFree(ctx->hilbert65);
     if (ctx->work_counter) cudaFree(ctx->work_counter);
     for (int i = 0; i < 2; ++i) {

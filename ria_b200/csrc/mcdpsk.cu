@@ -59,17 +59,18 @@ __device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b 
 // CFO correction
 // ---------------------------------------------------------------------------------------------
 __global__ void mcdpsk_phase_scan_kernel(const float* __restrict__ cfo_hz, const float* __restrict__ phase0,
-                                         long long n_frames, int n_blocks, float sample_rate,
+                                         long long frame0, long long n_frames, int n_blocks, float sample_rate,
                                          float* __restrict__ block_phase /*[n][n_blocks]*/) {
-    const long long f = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const long long fl = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (f >= n_frames) return;
+    if (fl >= n_frames) return;
+    const long long f = frame0 + fl;
     const float cfo = cfo_hz[f];
     if (!(fabsf(cfo) > 0.1f)) return;
     // phase_inc = -2.0f * M_PI * cfo_hz / sample_rate   (multi_carrier_dpsk.hpp:911)
     const float inc = static_cast<float>(-2.0f * M_PI * static_cast<double>(cfo) / static_cast<double>(sample_rate));
     float base = phase0 ? phase0[f] : 0.0f;
-    float* out = block_phase + f * n_blocks;
+    float* out = block_phase + fl * n_blocks;
     for (int b = 0; b < n_blocks; ++b) {
         if (lane == 0) out[b] = base;
         float next;
@@ -81,21 +82,22 @@ __global__ void mcdpsk_phase_scan_kernel(const float* __restrict__ cfo_hz, const
 // One thread per sample; a CTA covers 1024 consecutive samples of one frame (+126 history).
 __global__ void __launch_bounds__(256)
 mcdpsk_cfo_kernel(const float* __restrict__ samples, long long frame_stride, int frame_len,
+                  const int* __restrict__ start, long long frame0,
                   const float* __restrict__ cfo_hz, const float* __restrict__ block_phase, int n_blocks,
                   const float* __restrict__ taps_g, float sample_rate,
                   float* __restrict__ out, long long out_stride) {
     __shared__ float taps[kHilbertTaps + 1];
     __shared__ float x[1024 + kHilbertTaps];
-    const long long f = blockIdx.y;
+    const long long fl = blockIdx.y;                 // frame inside the chunk
+    const long long f = frame0 + fl;
     const int chunk0 = blockIdx.x * 1024;
     const float cfo = cfo_hz[f];
-    const float* src = samples + f * frame_stride;
-    float* dst = out + f * out_stride;
+    const int st = start ? start[f] : 0;
+    if (st < 0 || static_cast<long long>(st) + frame_len > frame_stride) return;   // demod reports 0 soft bits
+    const float* src = samples + f * frame_stride + st;
+    float* dst = out + fl * out_stride;
     const bool active = fabsf(cfo) > 0.1f && frame_len >= 128;      // :838, :903
-    if (!active) {
-        for (int i = threadIdx.x; i < 1024 && chunk0 + i < frame_len; i += 256) dst[chunk0 + i] = src[chunk0 + i];
-        return;
-    }
+    if (!active) return;                       // the demodulator reads such frames straight from the input
     if (threadIdx.x < kHilbertTaps) taps[threadIdx.x] = taps_g[threadIdx.x];
     for (int i = threadIdx.x; i < 1024 + kHilbertTaps - 1; i += 256) {
         const int g = chunk0 - (kHilbertTaps - 1) + i;
@@ -109,7 +111,7 @@ mcdpsk_cfo_kernel(const float* __restrict__ samples, long long frame_stride, int
         const int gi = chunk0 + li;
         const int blk = gi >> 5;
         float nx;
-        const float ph = (blk < n_blocks) ? cfo_phase_block32(block_phase[f * n_blocks + blk], inc, lane, &nx) : 0.0f;
+        const float ph = (blk < n_blocks) ? cfo_phase_block32(block_phase[fl * n_blocks + blk], inc, lane, &nx) : 0.0f;
         if (gi >= frame_len) continue;
         // q = sum_k coeffs[k] * x[i - k], ascending k (filters.cpp:299-306); odd taps are exactly 0
         float q = 0.0f;
@@ -130,6 +132,11 @@ mcdpsk_cfo_kernel(const float* __restrict__ samples, long long frame_stride, int
 // ---------------------------------------------------------------------------------------------
 struct DemodArgs {
     const float* samples; long long frame_stride; int frame_len;
+    const int* start;          // per-frame first sample inside its row (nullptr = 0), only for uncorrected input
+    long long row_len;         // samples available per row (start + frame_len must fit)
+    long long frame0;          // first frame of this chunk
+    const float* corrected;    // chunk-local CFO-corrected samples (frames with |cfo| > 0.1 Hz), or nullptr
+    long long corrected_stride;
     const float* cfo_hz; long long n_frames;
     float* llr; int llr_stride; int* n_llr; float* fading; float* cfo_out;
     float* scratch;            // per frame: mags[max_ds][C] | phases[max_ds][C] | errs[max_ds][C]
@@ -172,17 +179,21 @@ mcdpsk_demod_kernel(const DemodArgs a) {
     for (;;) {
         if (tid == 0) sm.frame = static_cast<long long>(atomicAdd(a.counter, 1u));
         __syncthreads();
-        const long long f = sm.frame;
+        const long long fl = sm.frame;
         __syncthreads();
-        if (f >= a.n_frames) break;
+        if (fl >= a.n_frames) break;
+        const long long f = a.frame0 + fl;
         float* llr_out = a.llr + f * a.llr_stride;
-        if (a.frame_len <= preamble || n_ds > a.max_ds) {           // processGotChirp waits for more samples
+        const int st = a.start ? a.start[f] : 0;
+        const bool in_row = st >= 0 && static_cast<long long>(st) + a.frame_len <= a.row_len;
+        if (a.frame_len <= preamble || n_ds > a.max_ds || !in_row) {   // processGotChirp waits for more samples
             if (tid == 0) { a.n_llr[f] = 0; if (a.fading) a.fading[f] = 0.0f; if (a.cfo_out) a.cfo_out[f] = a.cfo_hz ? a.cfo_hz[f] : 0.0f; }
             for (int i = tid; i < a.llr_stride; i += kDemodThreads) llr_out[i] = 0.0f;
             continue;
         }
-        const float* frame = a.samples + f * a.frame_stride;
-        float* mags = a.scratch + f * (3LL * a.max_ds * kMaxCar);
+        const bool corrected = a.corrected && fabsf(a.cfo_hz[f]) > 0.1f && a.frame_len >= 128;      // :838, :903
+        const float* frame = corrected ? a.corrected + fl * a.corrected_stride : a.samples + f * a.frame_stride + st;
+        float* mags = a.scratch + fl * (3LL * a.max_ds * kMaxCar);
         float* phases = mags + a.max_ds * kMaxCar;
         float* errs = phases + a.max_ds * kMaxCar;
 
@@ -475,11 +486,12 @@ extern "C" int ria_mcdpsk_soft_bits_per_frame(const ria_mcdpsk_config* cfg, int3
     return n_ds * static_cast<int>(cfg->num_carriers) * static_cast<int>(cfg->bits_per_symbol);
 }
 
-extern "C" int ria_mcdpsk_process_batch_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg,
-                                            const float* samples_dev, int64_t frame_stride, int32_t frame_len,
-                                            const float* cfo_hz_dev, const float* phase_dev, int64_t n_frames,
-                                            float* llr_dev, int32_t llr_stride, int32_t* n_llr_dev,
-                                            float* fading_dev, float* cfo_out_dev) {
+extern "C" int ria_mcdpsk_process_batch_at_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg,
+                                               const float* samples_dev, int64_t frame_stride, int32_t frame_len,
+                                               const int32_t* start_dev,
+                                               const float* cfo_hz_dev, const float* phase_dev, int64_t n_frames,
+                                               float* llr_dev, int32_t llr_stride, int32_t* n_llr_dev,
+                                               float* fading_dev, float* cfo_out_dev) {
     using namespace ria;
     if (!ctx || !cfg) return RIA_E_INVAL;
     if (n_frames < 0 || frame_len < 0 || frame_stride < frame_len) return set_error(ctx, RIA_E_INVAL, "mcdpsk: bad sizes");
@@ -495,11 +507,18 @@ extern "C" int ria_mcdpsk_process_batch_dev(ria_ctx* ctx, const ria_mcdpsk_confi
     const int max_ds = n_out / (C * static_cast<int>(cfg->bits_per_symbol)) + 1;
     const int n_blocks = (frame_len + 31) / 32;
 
-    // scratch: per-frame mags/phases/errs, then (only with a CFO vector) block phases + corrected samples
-    const size_t s_demod = static_cast<size_t>(n_frames) * 3 * max_ds * kMaxCar * sizeof(float);
-    const size_t s_phase = cfo_hz_dev ? static_cast<size_t>(n_frames) * n_blocks * sizeof(float) : 0;
+    // Frames go through in chunks so that the scratch (per-frame mags/phases/errs and, with a CFO
+    // vector, block phases + corrected samples) stays bounded for 10^5-frame batches.
     const size_t corr_stride = (static_cast<size_t>(frame_len) + 3) & ~size_t(3);
-    const size_t s_corr = cfo_hz_dev ? static_cast<size_t>(n_frames) * corr_stride * sizeof(float) : 0;
+    const size_t per_frame = static_cast<size_t>(3) * max_ds * kMaxCar * sizeof(float) +
+                             (cfo_hz_dev ? (static_cast<size_t>(n_blocks) + corr_stride) * sizeof(float) : 0);
+    int64_t chunk = static_cast<int64_t>((size_t(3) << 30) / (per_frame ? per_frame : 1));     // <= 3 GiB of scratch
+    if (chunk > 65535) chunk = 65535;
+    if (chunk > n_frames) chunk = n_frames;
+    if (chunk < 1) chunk = 1;
+    const size_t s_demod = static_cast<size_t>(chunk) * 3 * max_ds * kMaxCar * sizeof(float);
+    const size_t s_phase = cfo_hz_dev ? static_cast<size_t>(chunk) * n_blocks * sizeof(float) : 0;
+    const size_t s_corr = cfo_hz_dev ? static_cast<size_t>(chunk) * corr_stride * sizeof(float) : 0;
     const size_t a1 = (s_demod + 255) & ~size_t(255), a2 = (s_phase + 255) & ~size_t(255);
     rc = ensure_scratch(ctx, a1 + a2 + s_corr + 256);
     if (rc != RIA_OK) return rc;
@@ -508,45 +527,55 @@ extern "C" int ria_mcdpsk_process_batch_dev(ria_ctx* ctx, const ria_mcdpsk_confi
     float* d_bph = reinterpret_cast<float*>(base + a1);
     float* d_corr = reinterpret_cast<float*>(base + a1 + a2);
 
-    const float* demod_in = samples_dev;
-    long long demod_stride = frame_stride;
-    if (cfo_hz_dev) {
-        const unsigned scan_blocks = static_cast<unsigned>((n_frames * 32 + 127) / 128);
-        time_begin(ctx, KK_MCDPSK_CFO);
-        mcdpsk_phase_scan_kernel<<<scan_blocks, 128, 0, ctx->stream>>>(cfo_hz_dev, phase_dev, n_frames, n_blocks,
-                                                                      cfg->sample_rate, d_bph);
-        dim3 grid(static_cast<unsigned>((frame_len + 1023) / 1024), static_cast<unsigned>(n_frames));
-        if (n_frames > 65535) return set_error(ctx, RIA_E_INVAL, "mcdpsk: batch too large for one CFO launch (max 65535 frames)");
-        mcdpsk_cfo_kernel<<<grid, 256, 0, ctx->stream>>>(samples_dev, frame_stride, frame_len, cfo_hz_dev, d_bph, n_blocks,
-                                                         t->hilbert, cfg->sample_rate, d_corr, static_cast<long long>(corr_stride));
-        time_end(ctx);
-        RIA_CUDA(ctx, cudaGetLastError());
-        ctx->launches += 2;
-        demod_in = d_corr;
-        demod_stride = static_cast<long long>(corr_stride);
-    }
-
-    DemodArgs a{};
-    a.samples = demod_in; a.frame_stride = demod_stride; a.frame_len = frame_len;
-    a.cfo_hz = cfo_hz_dev; a.n_frames = n_frames;
-    a.llr = llr_dev; a.llr_stride = llr_stride; a.n_llr = n_llr_dev; a.fading = fading_dev; a.cfo_out = cfo_out_dev;
-    a.scratch = d_scr; a.max_ds = max_ds; a.mixer_g = t->mixer;
-    a.carriers = C; a.bits = static_cast<int>(cfg->bits_per_symbol); a.spread = static_cast<int>(cfg->spreading);
-    a.training = static_cast<int>(cfg->training_symbols);
-    a.counter = ctx->work_counter + 2;
     const size_t smem = sizeof(DemodSmem);
     RIA_CUDA(ctx, cudaFuncSetAttribute(mcdpsk_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     RIA_CUDA(ctx, cudaFuncSetAttribute(mcdpsk_demod_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     RIA_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mcdpsk_demod_kernel, kDemodThreads, smem));
     if (per_sm < 1) return set_error(ctx, RIA_E_UNSUPPORTED, "mcdpsk: kernel does not fit");
-    long long grid = static_cast<long long>(ctx->sm_count) * per_sm;
-    if (grid > n_frames) grid = n_frames;
-    RIA_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), ctx->stream));
-    time_begin(ctx, KK_MCDPSK);
-    mcdpsk_demod_kernel<<<static_cast<unsigned>(grid), kDemodThreads, smem, ctx->stream>>>(a);
-    time_end(ctx);
-    RIA_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 1;
+
+    for (int64_t off = 0; off < n_frames; off += chunk) {
+        const int64_t n = (n_frames - off < chunk) ? (n_frames - off) : chunk;
+        DemodArgs a{};
+        a.samples = samples_dev; a.frame_stride = frame_stride; a.frame_len = frame_len;
+        a.start = start_dev; a.row_len = frame_stride; a.frame0 = off; a.corrected = nullptr; a.corrected_stride = 0;
+        if (cfo_hz_dev) {
+            const unsigned scan_blocks = static_cast<unsigned>((n * 32 + 127) / 128);
+            time_begin(ctx, KK_MCDPSK_CFO);
+            mcdpsk_phase_scan_kernel<<<scan_blocks, 128, 0, ctx->stream>>>(cfo_hz_dev, phase_dev, off, n, n_blocks,
+                                                                          cfg->sample_rate, d_bph);
+            dim3 grid(static_cast<unsigned>((frame_len + 1023) / 1024), static_cast<unsigned>(n));
+            mcdpsk_cfo_kernel<<<grid, 256, 0, ctx->stream>>>(samples_dev, frame_stride, frame_len, start_dev, off,
+                                                             cfo_hz_dev, d_bph, n_blocks, t->hilbert, cfg->sample_rate,
+                                                             d_corr, static_cast<long long>(corr_stride));
+            time_end(ctx);
+            RIA_CUDA(ctx, cudaGetLastError());
+            ctx->launches += 2;
+            a.corrected = d_corr; a.corrected_stride = static_cast<long long>(corr_stride);
+        }
+        a.cfo_hz = cfo_hz_dev; a.n_frames = n;
+        a.llr = llr_dev; a.llr_stride = llr_stride; a.n_llr = n_llr_dev; a.fading = fading_dev; a.cfo_out = cfo_out_dev;
+        a.scratch = d_scr; a.max_ds = max_ds; a.mixer_g = t->mixer;
+        a.carriers = C; a.bits = static_cast<int>(cfg->bits_per_symbol); a.spread = static_cast<int>(cfg->spreading);
+        a.training = static_cast<int>(cfg->training_symbols);
+        a.counter = ctx->work_counter + 2;
+        long long grid = static_cast<long long>(ctx->sm_count) * per_sm;
+        if (grid > n) grid = n;
+        RIA_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), ctx->stream));
+        time_begin(ctx, KK_MCDPSK);
+        mcdpsk_demod_kernel<<<static_cast<unsigned>(grid), kDemodThreads, smem, ctx->stream>>>(a);
+        time_end(ctx);
+        RIA_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
     return RIA_OK;
+}
+
+extern "C" int ria_mcdpsk_process_batch_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg,
+                                            const float* samples_dev, int64_t frame_stride, int32_t frame_len,
+                                            const float* cfo_hz_dev, const float* phase_dev, int64_t n_frames,
+                                            float* llr_dev, int32_t llr_stride, int32_t* n_llr_dev,
+                                            float* fading_dev, float* cfo_out_dev) {
+    return ria_mcdpsk_process_batch_at_dev(ctx, cfg, samples_dev, frame_stride, frame_len, nullptr, cfo_hz_dev, phase_dev,
+                                           n_frames, llr_dev, llr_stride, n_llr_dev, fading_dev, cfo_out_dev);
 }

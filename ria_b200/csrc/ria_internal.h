@@ -69,6 +69,8 @@ struct ria_ctx {
     // scratch owned by the context for the fused chain entry points
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    void* chain_scratch = nullptr;          // buffers between the stages of the MC-DPSK chain
+    size_t chain_scratch_bytes = 0;
     void* ofdm_scratch = nullptr;           // carrier bins / CFO phases between the OFDM stages
     size_t ofdm_scratch_bytes = 0;
     // optional per-kernel timing (CUDA events on the launching stream), see ria_ctx_set_timing

@@ -85,3 +85,76 @@ class MCDPSKDemodulator:
             _ptr(cfo_hz), _ptr(phase), n, _ptr(out["llr"]), stride, _ptr(out["n_llr"]),
             _ptr(out["fading"]), _ptr(out["cfo"])))
         return out
+
+
+class McdpskRxChain:
+    """Chirp-acquired MC-DPSK frames, one codeword per frame (BASELINE configs[2]):
+    MCDPSKWaveform::detectSync -> process -> ChaseCache combining -> LDPCDecoder::decodeSoft,
+    all on the device through ``ria_mcdpsk_rx_frames_dev`` / ``_host``."""
+
+    def __init__(self, config: MultiCarrierDPSKConfig, rate: int, max_iter: int = 50, min_sum_factor: float = 0.9375,
+                 threshold: float = 0.15, ctx: Optional[Context] = None):
+        from .sync import ChirpConfig
+        self.config = config
+        self.chirp = ChirpConfig.default()
+        self.rate, self.max_iter, self.factor, self.threshold = int(rate), int(max_iter), float(min_sum_factor), float(threshold)
+        self._ctx = ctx
+        from . import fec
+        self.info_bytes = (fec.code_params(self.rate)[0] + 7) // 8
+
+    @property
+    def ctx(self) -> Context:
+        if self._ctx is None:
+            self._ctx = default_context()
+        return self._ctx
+
+    def process_batch(self, rows: torch.Tensor, frame_len: int, sync_window: int, acc: Optional[torch.Tensor] = None,
+                      first_reception: bool = True, out=None):
+        """rows: CUDA fp32 [n, row_len].  acc: CUDA fp32 [n, 648] chase accumulators (created when None).
+
+        Returns dict(info u8 [n, info_stride], ok u8 [n], iters i32 [n], sync u8 [n, 32], acc)."""
+        from .sync import SYNC_RESULT_DTYPE
+        if not (isinstance(rows, torch.Tensor) and rows.is_cuda and rows.dtype == torch.float32 and rows.dim() == 2):
+            raise RiaError("process_batch wants CUDA fp32 [n_frames, row_len] (no CPU fallback)")
+        if rows.stride(1) != 1:
+            rows = rows.contiguous()
+        n = rows.shape[0]
+        dev = rows.device
+        info_stride = (self.info_bytes + 3) & ~3
+        if acc is None:
+            acc = torch.empty((n, 648), dtype=torch.float32, device=dev)
+        if out is None:
+            out = dict(info=torch.empty((n, info_stride), dtype=torch.uint8, device=dev),
+                       ok=torch.empty((n,), dtype=torch.uint8, device=dev),
+                       iters=torch.empty((n,), dtype=torch.int32, device=dev),
+                       sync=torch.empty((n, SYNC_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev))
+        out["acc"] = acc
+        ctx = self.ctx
+        ctx.set_stream(torch.cuda.current_stream(dev))
+        ctx.check(lib().ria_mcdpsk_rx_frames_dev(
+            ctx.handle, C.addressof(self.config), C.addressof(self.chirp), _ptr(rows), rows.stride(0),
+            int(sync_window), int(frame_len), self.threshold, n, self.rate, self.max_iter, self.factor,
+            _ptr(acc), int(bool(first_reception)), _ptr(out["info"]), out["info"].stride(0), _ptr(out["ok"]),
+            _ptr(out["iters"]), _ptr(out["sync"])))
+        return out
+
+    def process_batch_host(self, rows, frame_len: int, sync_window: int):
+        """rows: host fp32 array or (pinned) CPU tensor [n, row_len]; H2D, chain and D2H happen inside the call."""
+        import numpy as np
+        from .sync import SYNC_RESULT_DTYPE
+        t = rows if isinstance(rows, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32))
+        if t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+            raise RiaError("process_batch_host wants a contiguous host fp32 [n_frames, row_len]")
+        n = t.shape[0]
+        info_stride = (self.info_bytes + 3) & ~3
+        info = np.empty((n, info_stride), np.uint8)
+        ok = np.empty(n, np.uint8)
+        iters = np.empty(n, np.int32)
+        sync = np.empty(n, SYNC_RESULT_DTYPE)
+        ctx = self.ctx
+        ctx.check(lib().ria_mcdpsk_rx_frames_host(
+            ctx.handle, C.addressof(self.config), C.addressof(self.chirp), C.c_void_p(t.data_ptr()), t.stride(0),
+            int(sync_window), int(frame_len), self.threshold, n, self.rate, self.max_iter, self.factor,
+            info.ctypes.data_as(C.c_void_p), info_stride, ok.ctypes.data_as(C.c_void_p),
+            iters.ctypes.data_as(C.c_void_p), sync.ctypes.data_as(C.c_void_p)))
+        return dict(info=info, ok=ok, iters=iters, sync=sync)

@@ -240,3 +240,110 @@ def make_frame_pool(cfg: ModemConfig, rate: int, n_frames: int, seed: int = 1,
         frames.append(ofdm_modulate_frame(cfg, bits))
         raw.append(fr)
     return np.stack(frames), raw
+
+
+# ---------------------------------------------------------------------------------------------
+# Preambles and the MC-DPSK modulator (inputs of the C3 bench workload and of the sync tests)
+# ---------------------------------------------------------------------------------------------
+F32 = np.float32
+
+
+def zc_preamble(root: int = 5, sample_rate: float = 48000.0, sequence_length: int = 127, upsample: int = 8,
+                repetitions: int = 2, carrier_freq: float = 1500.0, gap_ms: float = 10.0) -> np.ndarray:
+    """sync::ZCSync::generatePreambleForRoot (src/sync/zc_sync.hpp:133-190): linearly interpolated
+    Zadoff-Chu chips on a 1500 Hz carrier, peak-normalised to 0.8, followed by a silent gap.
+    Root 5 = DATA frames (mc_dpsk_waveform.cpp:57-61)."""
+    n = np.arange(sequence_length, dtype=np.float64)
+    if sequence_length % 2 == 0:
+        phase = (-np.pi * root * n * n / sequence_length).astype(F32)
+    else:
+        phase = (-np.pi * root * n * (n + 1) / sequence_length).astype(F32)
+    zc = (np.cos(phase).astype(F32) + 1j * np.sin(phase).astype(F32)).astype(np.complex64)
+    rep_len = sequence_length * upsample
+    i = np.arange(rep_len)
+    chip_pos = (i.astype(F32) / F32(upsample)).astype(F32)
+    chip_idx = chip_pos.astype(np.int64)
+    frac = (chip_pos - chip_idx.astype(F32)).astype(F32)
+    nxt = np.minimum(chip_idx + 1, sequence_length - 1)
+    interp = np.where(chip_idx < sequence_length - 1,
+                      zc[chip_idx] * (F32(1.0) - frac) + zc[nxt] * frac, zc[chip_idx]).astype(np.complex64)
+    gi = (np.arange(repetitions)[:, None] * rep_len + i[None, :]).reshape(-1)
+    t = (gi.astype(F32) / F32(sample_rate)).astype(F32)
+    cph = (F32(2.0) * F32(np.pi) * F32(carrier_freq) * t).astype(F32)
+    it = np.tile(interp, repetitions)
+    s = (it.real * np.cos(cph).astype(F32) - it.imag * np.sin(cph).astype(F32)).astype(F32)
+    peak = np.abs(s).max()
+    if peak > 0:
+        s = (s * F32(F32(0.8) / peak)).astype(F32)
+    gap = int(F32(sample_rate) * F32(gap_ms) / F32(1000.0))
+    return np.concatenate([s, np.zeros(gap, F32)])
+
+
+def chirp_preamble(sample_rate: float = 48000.0, f_start: float = 300.0, f_end: float = 2700.0,
+                   duration_ms: float = 500.0, gap_ms: float = 100.0, amplitude: float = 0.5) -> np.ndarray:
+    """sync::ChirpSync::generate, dual chirp (src/sync/chirp_sync.hpp:61-108): [up][gap][down][gap]."""
+    n = int(F32(sample_rate) * F32(duration_ms) / F32(1000.0))
+    gap = int(F32(sample_rate) * F32(gap_ms) / F32(1000.0))
+    T = F32(duration_ms) / F32(1000.0)
+    k = F32((F32(f_end) - F32(f_start)) / T)
+    t = (np.arange(n).astype(F32) / F32(sample_rate)).astype(F32)
+    up = (F32(2.0) * F32(np.pi) * (F32(f_start) * t + F32(0.5) * k * t * t)).astype(F32)
+    dn = (F32(2.0) * F32(np.pi) * (F32(f_end) * t - F32(0.5) * k * t * t)).astype(F32)
+    out = np.zeros(2 * n + 2 * gap, F32)
+    out[:n] = F32(amplitude) * np.sin(up).astype(F32)
+    out[n + gap: 2 * n + gap] = F32(amplitude) * np.sin(dn).astype(F32)
+    return out
+
+
+def _mcdpsk_carrier_table(cfg) -> np.ndarray:
+    """e^{j 2 pi f_c i / fs}, i < samples_per_symbol, per carrier (multi_carrier_dpsk.hpp:68-79, 155-160)."""
+    C, sps = int(cfg.num_carriers), int(cfg.samples_per_symbol)
+    if C == 1:
+        freqs = np.array([(F32(cfg.freq_low) + F32(cfg.freq_high)) / F32(2.0)], F32)
+    else:
+        spacing = F32((F32(cfg.freq_high) - F32(cfg.freq_low)) / F32(C - 1))
+        freqs = (F32(cfg.freq_low) + np.arange(C).astype(F32) * spacing).astype(F32)
+    inc = (F32(2.0) * F32(np.pi) * freqs / F32(cfg.sample_rate)).astype(F32)
+    t = (np.arange(sps).astype(F32)[None, :] * inc[:, None]).astype(F32)
+    return (np.cos(t).astype(F32) + 1j * np.sin(t).astype(F32)).astype(np.complex64)
+
+
+def mcdpsk_modulate_frame(cfg, data: bytes) -> np.ndarray:
+    """[training][reference][data] as MultiCarrierDPSKModulator emits them
+    (src/psk/multi_carrier_dpsk.hpp:141-275): every carrier restarts at phase 0 each symbol, the
+    symbol is the mean over carriers of Re(sym_c * e^{j w_c i}), data symbols are repeated
+    `spreading` times, DBPSK 0 -> 0, 1 -> pi; DQPSK 00/01/11/10 -> +45/+135/-135/-45 degrees."""
+    C, sps, bps = int(cfg.num_carriers), int(cfg.samples_per_symbol), int(cfg.bits_per_symbol)
+    spread, n_train = int(cfg.spreading), int(cfg.training_symbols)
+    car = _mcdpsk_carrier_table(cfg)                               # [C][sps]
+
+    def symbol(vals: np.ndarray) -> np.ndarray:
+        out = np.zeros(sps, F32)
+        for c in range(C):                                          # accumulation order of the reference
+            out = (out + ((vals[c] * car[c]).real.astype(F32) / F32(C)).astype(F32)).astype(F32)
+        return out
+
+    parts = []
+    for sym in range(n_train):
+        ph = (np.arange(C) * sym).astype(F32) * F32(np.pi) / F32(2.0)
+        parts.append(symbol((np.cos(ph).astype(F32) + 1j * np.sin(ph).astype(F32)).astype(np.complex64)))
+    prev = np.ones(C, np.complex64)
+    parts.append(symbol(prev))
+    bits = np.unpackbits(np.frombuffer(bytes(data), np.uint8))
+    per_sym = C * bps
+    n_ds = (len(bits) + per_sym - 1) // per_sym
+    bits = np.concatenate([bits, np.zeros(n_ds * per_sym - len(bits), np.uint8)])
+    dq = np.array([np.pi / 4, 3 * np.pi / 4, -3 * np.pi / 4, -np.pi / 4], F32)
+    for d in range(n_ds):
+        b = bits[d * per_sym:(d + 1) * per_sym].reshape(C, bps)
+        if bps == 2:
+            change = dq[b[:, 0] * 2 + b[:, 1]]
+        else:
+            change = np.where(b[:, 0] == 1, F32(np.pi), F32(0.0)).astype(F32)
+        diff = (np.cos(change).astype(F32) + 1j * np.sin(change).astype(F32)).astype(np.complex64)
+        cur = (prev * diff).astype(np.complex64)
+        cur = (cur / np.abs(cur).astype(F32)).astype(np.complex64)
+        prev = cur
+        s = symbol(cur)
+        parts.extend([s] * spread)
+    return np.concatenate(parts)

@@ -140,3 +140,71 @@ def test_c3_chain_with_ldpc(ctx, ref, port):
         assert np.array_equal(info[i].cpu().numpy(), w_info[0])
         n_ok += int(w_ok[0] and bytes(w_info[0][:20]) == sent[i].tobytes())
     assert n_ok >= 10        # README.md:343: 4x spreading is verified at -8 dB
+
+
+def test_chirp_acquired_chain_matches_reference(ctx, ref, port):
+    """ria_mcdpsk_rx_frames_dev / _host (chirp sync -> process at the detected offset with the
+    detected CFO -> chase combining -> LDPC R1/4) against the reference run stage by stage on the
+    same rows: training start exact, payload bits / success flag / iteration count exact for the
+    first reception and for the chase-combined second reception."""
+    import torch
+    from ria_b200 import mcdpsk, txsynth
+    from ria_b200.sync import SYNC_RESULT_DTYPE
+    cfg = McdpskConfig.make(1, 4, 10)
+    rcfg = mcdpsk.MultiCarrierDPSKConfig.from_buffer_copy(bytes(cfg))
+    rng = np.random.default_rng(21)
+    pre = txsynth.chirp_preamble()
+    frame_len = None
+    rows1, rows2, sent = [], [], []
+    lead = 1500
+    for i in range(10):
+        data = rng.integers(0, 256, size=20, dtype=np.uint8)
+        cw = port.ldpc_encode(R1_4, data)[:81]
+        body = txsynth.mcdpsk_modulate_frame(rcfg, cw.tobytes())
+        frame_len = len(body)
+        cfo = float(rng.uniform(-20, 20)) if i % 2 else 0.0
+        tx = np.concatenate([np.zeros(lead + 37 * i, np.float32), pre, body, np.zeros(1200 - 37 * i, np.float32)])
+        tx = apply_cfo(tx, cfo) if cfo else tx
+        rows1.append(awgn(tx, -9.0, rng))
+        rows2.append(awgn(tx, -9.0, rng))
+        sent.append(data)
+    row_len = len(rows1[0])
+    window = 120000
+    chain = mcdpsk.McdpskRxChain(rcfg, R1_4, 50, 0.9375, 0.15, ctx)
+    r1 = chain.process_batch(torch.from_numpy(np.stack(rows1)).cuda(), frame_len, window, None, True)
+    torch.cuda.synchronize()
+    first = {k: v.cpu().numpy().copy() for k, v in r1.items()}
+    r2 = chain.process_batch(torch.from_numpy(np.stack(rows2)).cuda(), frame_len, window, r1["acc"], False)
+    torch.cuda.synchronize()
+    second = {k: v.cpu().numpy().copy() for k, v in r2.items()}
+    host = chain.process_batch_host(np.stack(rows1), frame_len, window)
+
+    after_down = 24000 + 4800
+    combined_better = 0
+    for i in range(len(rows1)):
+        soft = []
+        for rows, got in ((rows1, first), (rows2, second)):
+            rx = rows[i]
+            s = ref.chirp_detect_dual(rx[:window], 0.15)
+            g = got["sync"].view(SYNC_RESULT_DTYPE)[i, 0] if got["sync"].ndim == 2 else got["sync"][i]
+            assert bool(g["detected"]) == bool(s.detected)
+            assert s.detected, "test frames are meant to be detectable"
+            assert int(g["aux"]) == int(s.aux) and int(g["start_sample"]) == int(s.start_sample)
+            assert abs(float(g["cfo_hz"]) - float(s.cfo_hz)) <= 1e-3 + 1e-4 * abs(s.cfo_hz)
+            start = int(s.aux) + after_down
+            # the reference demodulator is driven with the CFO the device reported, so that the two
+            # chains see identical inputs from here on
+            r = ref.mcdpsk_process(cfg, rx[start:start + frame_len], float(g["cfo_hz"]))
+            soft.append(r["soft"][:648].astype(np.float32))
+        w1 = ref.ldpc_decode_batch(R1_4, soft[0], 50, 0.9375, 24)
+        w2 = ref.ldpc_decode_batch(R1_4, (soft[0] + soft[1]).astype(np.float32), 50, 0.9375, 24)
+        for w, got in ((w1, first), (w2, second)):
+            # soft bits agree within 1e-4, so success / iterations match unless a decode sits on the edge
+            assert got["ok"][i] == w[1][0] and got["iters"][i] == w[2][0], (i, got["ok"][i], w[1][0], got["iters"][i], w[2][0])
+            assert np.array_equal(got["info"][i, :21], w[0][0][:21])
+        assert host["ok"][i] == first["ok"][i] and host["iters"][i] == first["iters"][i]
+        assert np.array_equal(host["info"][i], first["info"][i])
+        combined_better += int(second["ok"][i]) - int(first["ok"][i])
+        if second["ok"][i]:
+            assert bytes(second["info"][i, :20]) == sent[i].tobytes()
+    assert combined_better >= 0 and second["ok"].sum() >= 8
