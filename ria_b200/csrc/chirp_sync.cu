@@ -48,6 +48,7 @@ constexpr int kA = 32, kB = 64, kC = 64;
 constexpr int kN = kA * kB * kC;          // 131072 = ChirpSync::FFT_SIZE (:565)
 constexpr int kT = 16;                    // transforms per tile
 constexpr int kFftThreads = 128;
+constexpr int kTilesPerCta = 8;
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -66,13 +67,17 @@ fft_stage_kernel(float2* __restrict__ data, int inverse, const float2* __restric
     __shared__ float2 wl[L / 2];
     const int tid = threadIdx.x;
     float2* x = data + static_cast<size_t>(blockIdx.y) * kN;
-    const int q = blockIdx.x;
     if (tid < L / 2) {
         double s, c;
         sincospi(-2.0 * tid / L, &s, &c);
         wl[tid] = make_float2(static_cast<float>(c), static_cast<float>(inverse ? -s : s));
     }
     constexpr int LOGL = (L == 64) ? 6 : 5;
+    // kTilesPerCta tiles per CTA: the small-DFT twiddles are set up once and the grid stays at a
+    // few hundred thousand CTAs per launch instead of several million
+    for (int qq = 0; qq < kTilesPerCta; ++qq) {
+    const int q = blockIdx.x * kTilesPerCta + qq;
+    __syncthreads();
     // ---- load (bit-reversed rows) ----
     for (int e = tid; e < L * kT; e += kFftThreads) {
         int i, t; size_t idx;
@@ -126,17 +131,18 @@ fft_stage_kernel(float2* __restrict__ data, int inverse, const float2* __restric
         if (MODE == 1 && inverse) { v.x *= scale; v.y *= scale; }
         x[idx] = v;
     }
+    }
 }
 
 void fft_forward(float2* d, int batch, const ChirpTablesDev& t, cudaStream_t s) {
-    fft_stage_kernel<kA, 1><<<dim3(kB * kC / kT, batch), kFftThreads, 0, s>>>(d, 0, t.tw1, t.tw2, 1.0f);
-    fft_stage_kernel<kB, 2><<<dim3(kA * kC / kT, batch), kFftThreads, 0, s>>>(d, 0, t.tw1, t.tw2, 1.0f);
-    fft_stage_kernel<kC, 3><<<dim3(kA * kB / kT, batch), kFftThreads, 0, s>>>(d, 0, t.tw1, t.tw2, 1.0f);
+    fft_stage_kernel<kA, 1><<<dim3(kB * kC / kT / kTilesPerCta, batch), kFftThreads, 0, s>>>(d, 0, t.tw1, t.tw2, 1.0f);
+    fft_stage_kernel<kB, 2><<<dim3(kA * kC / kT / kTilesPerCta, batch), kFftThreads, 0, s>>>(d, 0, t.tw1, t.tw2, 1.0f);
+    fft_stage_kernel<kC, 3><<<dim3(kA * kB / kT / kTilesPerCta, batch), kFftThreads, 0, s>>>(d, 0, t.tw1, t.tw2, 1.0f);
 }
 void fft_inverse(float2* d, int batch, const ChirpTablesDev& t, cudaStream_t s) {
-    fft_stage_kernel<kC, 3><<<dim3(kA * kB / kT, batch), kFftThreads, 0, s>>>(d, 1, t.tw1, t.tw2, 1.0f);
-    fft_stage_kernel<kB, 2><<<dim3(kA * kC / kT, batch), kFftThreads, 0, s>>>(d, 1, t.tw1, t.tw2, 1.0f);
-    fft_stage_kernel<kA, 1><<<dim3(kB * kC / kT, batch), kFftThreads, 0, s>>>(d, 1, t.tw1, t.tw2, 1.0f / kN);
+    fft_stage_kernel<kC, 3><<<dim3(kA * kB / kT / kTilesPerCta, batch), kFftThreads, 0, s>>>(d, 1, t.tw1, t.tw2, 1.0f);
+    fft_stage_kernel<kB, 2><<<dim3(kA * kC / kT / kTilesPerCta, batch), kFftThreads, 0, s>>>(d, 1, t.tw1, t.tw2, 1.0f);
+    fft_stage_kernel<kA, 1><<<dim3(kB * kC / kT / kTilesPerCta, batch), kFftThreads, 0, s>>>(d, 1, t.tw1, t.tw2, 1.0f / kN);
 }
 
 __global__ void chirp_twiddle_kernel(float2* tw1, float2* tw2) {
