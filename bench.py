@@ -389,7 +389,7 @@ class McdpskC3Workload:
         row, body, win = self.row_len * 4, self.frame_len * 4, self.WINDOW * 4
         return {
             KK_AWGN: ("awgn_kernel", n2 * 2 * row),
-            KK_CHIRP_SYNC: ("chirp_* (pack, 3-stage FFT x3, product, peak)", n2 * win),
+            KK_CHIRP_SYNC: ("chirp_* (3 x 3-stage 131072-pt FFT with fused real load / template products, peak)", n2 * win),
             KK_MCDPSK_CFO: ("mcdpsk_phase_scan_kernel + mcdpsk_cfo_kernel", n2 * 2 * body),
             KK_MCDPSK: ("mcdpsk_demod_kernel", n2 * (body + 652 * 4)),
             KK_CHASE: ("chase_combine_kernel", n2 * 3 * 648 * 4),

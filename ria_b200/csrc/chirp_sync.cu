@@ -46,103 +46,188 @@ namespace {
 
 constexpr int kA = 32, kB = 64, kC = 64;
 constexpr int kN = kA * kB * kC;          // 131072 = ChirpSync::FFT_SIZE (:565)
-constexpr int kT = 16;                    // transforms per tile
 constexpr int kFftThreads = 128;
-constexpr int kTilesPerCta = 8;
+constexpr int kTilesPerCta = 4;
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// One stage of the three-stage transform: T small DFTs of length L in shared memory
-// (radix-2 DIT), followed by a pointwise twiddle (or the final 1/N scale).
+// ---------------------------------------------------------------------------------------------
+// One stage of the three-stage transform: a tile of small DFTs (length 32 or 64) evaluated as
+// radix-8 x radix-4/8 in registers with one exchange through shared memory, followed by the
+// pointwise twiddle of the four-step decomposition (or the final 1/N scale).
 //   mode 1: over a (L = 32), element stride B*C      forward: then * tw1     inverse: then * scale
 //   mode 2: over b (L = 64), element stride C        forward: then * tw2     inverse: then * conj(tw1)
 //   mode 3: over c (L = 64), contiguous              forward: nothing        inverse: then * conj(tw2)
-template <int L, int MODE>
+// Forward mode 1 can read the real input window directly (zero-padded, :647-650) and forward
+// mode 3 can write the two template products (:656-659) instead of the spectrum, so neither the
+// packed complex signal nor the bare spectrum ever exists in HBM.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -j (forward) / +j (inverse)
+template <bool INV> __device__ __forceinline__ float2 mul_mj(float2 a) {
+    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+// 8-point DFT, natural order in and out (decimation in frequency, outputs un-bit-reversed)
+template <bool INV>
+__device__ __forceinline__ void dft8(float2 (&a)[8]) {
+    const float h = 0.70710678118654752440f;
+    float2 b[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { b[i] = cadd2(a[i], a[i + 4]); b[i + 4] = csub2(a[i], a[i + 4]); }
+    // twiddles W8^i on the lower half: 1, (1 -+ j)/sqrt2, -+j, (-1 -+ j)/sqrt2
+    {
+        const float2 t5 = b[5], t7 = b[7];
+        b[5] = INV ? make_float2(h * (t5.x - t5.y), h * (t5.x + t5.y)) : make_float2(h * (t5.x + t5.y), h * (t5.y - t5.x));
+        b[6] = mul_mj<INV>(b[6]);
+        b[7] = INV ? make_float2(-h * (t7.x + t7.y), h * (t7.x - t7.y)) : make_float2(h * (t7.y - t7.x), -h * (t7.x + t7.y));
+    }
+    float2 c[8];
+#pragma unroll
+    for (int g = 0; g < 8; g += 4) {
+        c[g] = cadd2(b[g], b[g + 2]);     c[g + 2] = csub2(b[g], b[g + 2]);
+        c[g + 1] = cadd2(b[g + 1], b[g + 3]); c[g + 3] = mul_mj<INV>(csub2(b[g + 1], b[g + 3]));
+    }
+    float2 d[8];
+#pragma unroll
+    for (int g = 0; g < 8; g += 2) { d[g] = cadd2(c[g], c[g + 1]); d[g + 1] = csub2(c[g], c[g + 1]); }
+    a[0] = d[0]; a[4] = d[1]; a[2] = d[2]; a[6] = d[3]; a[1] = d[4]; a[5] = d[5]; a[3] = d[6]; a[7] = d[7];
+}
+template <bool INV>
+__device__ __forceinline__ void dft4(float2 (&a)[4]) {
+    const float2 s0 = cadd2(a[0], a[2]), d0 = csub2(a[0], a[2]);
+    const float2 s1 = cadd2(a[1], a[3]), d1 = mul_mj<INV>(csub2(a[1], a[3]));
+    a[0] = cadd2(s0, s1); a[2] = csub2(s0, s1); a[1] = cadd2(d0, d1); a[3] = csub2(d0, d1);
+}
+
+struct StageArgs {
+    float2* data;                 // [batch][kN] in place
+    const float* real_in;         // forward mode 1: real input rows instead of data (may be null)
+    long long real_stride; int n_in;
+    float2* prod_up; float2* prod_dn;            // forward mode 3: write v * tu, v * td instead of v
+    const float2* tmpl_up; const float2* tmpl_dn;
+    const float2* tw1; const float2* tw2;
+    float scale;
+};
+
+template <int MODE, bool INV>
 __global__ void __launch_bounds__(kFftThreads)
-fft_stage_kernel(float2* __restrict__ data, int inverse, const float2* __restrict__ tw1,
-                 const float2* __restrict__ tw2, float scale) {
-    __shared__ float2 buf[L][kT + 1];
-    __shared__ float2 wl[L / 2];
+fft_stage_kernel(const StageArgs a) {
+    constexpr int L = (MODE == 1) ? kA : 64;
+    constexpr int R2 = L / 8;                         // second radix: 4 or 8
+    constexpr int T = (MODE == 1) ? 32 : 16;          // transforms per tile
+    constexpr int kRow = (MODE == 3) ? 72 : 0;        // mode 3: per-transform row of 8 x 9
+    __shared__ float2 buf[(MODE == 3) ? T * kRow : L * T];
+    __shared__ float2 wl[L];                          // w_L^m, conjugated for the inverse
     const int tid = threadIdx.x;
-    float2* x = data + static_cast<size_t>(blockIdx.y) * kN;
-    if (tid < L / 2) {
+    const size_t f = blockIdx.y;
+    float2* x = a.data + f * kN;
+    if (tid < L) {
         double s, c;
         sincospi(-2.0 * tid / L, &s, &c);
-        wl[tid] = make_float2(static_cast<float>(c), static_cast<float>(inverse ? -s : s));
+        wl[tid] = make_float2(static_cast<float>(c), static_cast<float>(INV ? -s : s));
     }
-    constexpr int LOGL = (L == 64) ? 6 : 5;
-    // kTilesPerCta tiles per CTA: the small-DFT twiddles are set up once and the grid stays at a
-    // few hundred thousand CTAs per launch instead of several million
+    __syncthreads();
+
     for (int qq = 0; qq < kTilesPerCta; ++qq) {
-    const int q = blockIdx.x * kTilesPerCta + qq;
-    __syncthreads();
-    // ---- load (bit-reversed rows) ----
-    for (int e = tid; e < L * kT; e += kFftThreads) {
-        int i, t; size_t idx;
-        if (MODE == 3) { i = e % L; t = e / L; idx = static_cast<size_t>(q * kT + t) * kC + i; }
-        else {
-            t = e % kT; i = e / kT;
-            if (MODE == 1) idx = static_cast<size_t>(i) * (kB * kC) + q * kT + t;
-            else { const int ka = q / (kC / kT), c0 = (q % (kC / kT)) * kT; idx = static_cast<size_t>(ka) * (kB * kC) + i * kC + c0 + t; }
+        const int q = blockIdx.x * kTilesPerCta + qq;
+        // element (i, t) of the tile lives at x[elem0 + i * istride + t * tstride]
+        size_t elem0; int istride, tstride;
+        if (MODE == 1) { elem0 = static_cast<size_t>(q) * T; istride = kB * kC; tstride = 1; }
+        else if (MODE == 2) {
+            const int ka = q / (kC / T), c0 = (q % (kC / T)) * T;
+            elem0 = static_cast<size_t>(ka) * (kB * kC) + c0; istride = kC; tstride = 1;
+        } else { elem0 = static_cast<size_t>(q) * T * kC; istride = 1; tstride = kC; }
+
+        // ---- pass 1: radix 8 over n1 (n = R2 * n1 + n2), twiddle w_L^(n2 k1) ----
+        {
+            int n2, t;
+            if (MODE == 3) { n2 = tid & 7; t = tid >> 3; } else { t = tid % T; n2 = tid / T; }
+            float2 v[8];
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) {
+                const size_t idx = elem0 + static_cast<size_t>(R2 * n1 + n2) * istride + static_cast<size_t>(t) * tstride;
+                if (MODE == 1 && !INV && a.real_in) v[n1] = make_float2(idx < static_cast<size_t>(a.n_in) ? a.real_in[f * a.real_stride + idx] : 0.0f, 0.0f);
+                else v[n1] = x[idx];
+            }
+            dft8<INV>(v);
+#pragma unroll
+            for (int k1 = 0; k1 < 8; ++k1) {
+                const float2 w = wl[n2 * k1];                      // n2 * k1 < L
+                const float2 y = (k1 == 0) ? v[0] : cmulf(v[k1], w);
+                if (MODE == 3) buf[t * kRow + k1 * 9 + n2] = y;
+                else buf[(k1 * R2 + n2) * T + t] = y;
+            }
         }
-        const int ir = __brev(static_cast<unsigned>(i)) >> (32 - LOGL);
-        buf[ir][t] = x[idx];
-    }
-    __syncthreads();
-    // ---- radix-2 DIT stages ----
-    for (int len = 2; len <= L; len <<= 1) {
-        const int half = len >> 1, step = L / len;
-        for (int e = tid; e < (L / 2) * kT; e += kFftThreads) {
-            const int t = e % kT, bf = e / kT;
-            const int blk = bf / half, k = bf % half;
-            const int i0 = blk * len + k, i1 = i0 + half;
-            const float2 w = wl[k * step];
-            const float2 a = buf[i0][t], b = cmulf(w, buf[i1][t]);
-            buf[i0][t] = make_float2(a.x + b.x, a.y + b.y);
-            buf[i1][t] = make_float2(a.x - b.x, a.y - b.y);
+        __syncthreads();
+        // ---- pass 2: radix R2 over n2 -> X[k1 + 8 k2], pointwise factor, store ----
+        for (int task = tid; task < 8 * T; task += kFftThreads) {
+            int k1, t;
+            if (MODE == 3) { k1 = task & 7; t = task >> 3; } else { t = task % T; k1 = task / T; }
+            float2 v[R2];
+#pragma unroll
+            for (int n2 = 0; n2 < R2; ++n2) v[n2] = (MODE == 3) ? buf[t * kRow + k1 * 9 + n2] : buf[(k1 * R2 + n2) * T + t];
+            if (R2 == 8) dft8<INV>(reinterpret_cast<float2 (&)[8]>(v)); else dft4<INV>(reinterpret_cast<float2 (&)[4]>(v));
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) {
+                const int i = k1 + 8 * k2;
+                const size_t idx = elem0 + static_cast<size_t>(i) * istride + static_cast<size_t>(t) * tstride;
+                float2 val = v[k2];
+                if (MODE == 1) {
+                    if (!INV) val = cmulf(val, a.tw1[idx]);
+                    else { val.x *= a.scale; val.y *= a.scale; }
+                } else if (MODE == 2) {
+                    const int c = static_cast<int>(idx % kC);
+                    if (!INV) val = cmulf(val, a.tw2[i * kC + c]);
+                    else { float2 w = a.tw1[idx]; w.y = -w.y; val = cmulf(val, w); }
+                } else if (INV) {
+                    const int row = static_cast<int>(idx / kC);               // row = ka*B + kb
+                    float2 w = a.tw2[(row % kB) * kC + i]; w.y = -w.y;
+                    val = cmulf(val, w);
+                }
+                if (MODE == 3 && !INV && a.prod_up) {
+                    a.prod_up[f * kN + idx] = cmulf(val, a.tmpl_up[idx]);
+                    a.prod_dn[f * kN + idx] = cmulf(val, a.tmpl_dn[idx]);
+                } else x[idx] = val;
+            }
         }
         __syncthreads();
     }
-    // ---- pointwise factor + store ----
-    for (int e = tid; e < L * kT; e += kFftThreads) {
-        int i, t; size_t idx; float2 f = make_float2(1.0f, 0.0f); bool has_f = false;
-        if (MODE == 3) {
-            i = e % L; t = e / L;
-            const int row = q * kT + t;                       // row = ka*B + kb
-            idx = static_cast<size_t>(row) * kC + i;
-            if (inverse) { f = tw2[(row % kB) * kC + i]; f.y = -f.y; has_f = true; }
-        } else {
-            t = e % kT; i = e / kT;
-            if (MODE == 1) {
-                const int m = q * kT + t;
-                idx = static_cast<size_t>(i) * (kB * kC) + m;
-                if (!inverse) { f = tw1[static_cast<size_t>(i) * (kB * kC) + m]; has_f = true; }
-            } else {
-                const int ka = q / (kC / kT), c = (q % (kC / kT)) * kT + t;
-                idx = static_cast<size_t>(ka) * (kB * kC) + i * kC + c;
-                if (!inverse) { f = tw2[i * kC + c]; has_f = true; }
-                else { f = tw1[static_cast<size_t>(ka) * (kB * kC) + i * kC + c]; f.y = -f.y; has_f = true; }
-            }
-        }
-        float2 v = buf[i][t];
-        if (has_f) v = cmulf(v, f);
-        if (MODE == 1 && inverse) { v.x *= scale; v.y *= scale; }
-        x[idx] = v;
-    }
-    }
 }
 
+template <bool INV>
+void fft_stages(const StageArgs& a, int batch, cudaStream_t s) {
+    const dim3 g1(kB * kC / 32 / kTilesPerCta, batch), g2(kA * kC / 16 / kTilesPerCta, batch), g3(kA * kB / 16 / kTilesPerCta, batch);
+    if (!INV) {
+        fft_stage_kernel<1, false><<<g1, kFftThreads, 0, s>>>(a);
+        fft_stage_kernel<2, false><<<g2, kFftThreads, 0, s>>>(a);
+        fft_stage_kernel<3, false><<<g3, kFftThreads, 0, s>>>(a);
+    } else {
+        fft_stage_kernel<3, true><<<g3, kFftThreads, 0, s>>>(a);
+        fft_stage_kernel<2, true><<<g2, kFftThreads, 0, s>>>(a);
+        fft_stage_kernel<1, true><<<g1, kFftThreads, 0, s>>>(a);
+    }
+}
 void fft_forward(float2* d, int batch, const ChirpTablesDev& t, cudaStream_t s) {
-    fft_stage_kernel<kA, 1><<<dim3(kB * kC / kT / kTilesPerCta, batch), kFftThreads, 0, s>>>(d, 0, t.tw1, t.tw2, 1.0f);
-    fft_stage_kernel<kB, 2><<<dim3(kA * kC / kT / kTilesPerCta, batch), kFftThreads, 0, s>>>(d, 0, t.tw1, t.tw2, 1.0f);
-    fft_stage_kernel<kC, 3><<<dim3(kA * kB / kT / kTilesPerCta, batch), kFftThreads, 0, s>>>(d, 0, t.tw1, t.tw2, 1.0f);
+    StageArgs a{};
+    a.data = d; a.tw1 = t.tw1; a.tw2 = t.tw2; a.scale = 1.0f;
+    fft_stages<false>(a, batch, s);
 }
 void fft_inverse(float2* d, int batch, const ChirpTablesDev& t, cudaStream_t s) {
-    fft_stage_kernel<kC, 3><<<dim3(kA * kB / kT / kTilesPerCta, batch), kFftThreads, 0, s>>>(d, 1, t.tw1, t.tw2, 1.0f);
-    fft_stage_kernel<kB, 2><<<dim3(kA * kC / kT / kTilesPerCta, batch), kFftThreads, 0, s>>>(d, 1, t.tw1, t.tw2, 1.0f);
-    fft_stage_kernel<kA, 1><<<dim3(kB * kC / kT / kTilesPerCta, batch), kFftThreads, 0, s>>>(d, 1, t.tw1, t.tw2, 1.0f / kN);
+    StageArgs a{};
+    a.data = d; a.tw1 = t.tw1; a.tw2 = t.tw2; a.scale = 1.0f / kN;
+    fft_stages<true>(a, batch, s);
+}
+// forward transform of real rows with the two template products as output
+void fft_forward_real_to_products(const float* samples, long long stride, int n_in, float2* work, float2* pu, float2* pd,
+                                  int batch, const ChirpTablesDev& t, cudaStream_t s) {
+    StageArgs a{};
+    a.data = work; a.real_in = samples; a.real_stride = stride; a.n_in = n_in;
+    a.prod_up = pu; a.prod_dn = pd; a.tmpl_up = t.tmpl_up; a.tmpl_dn = t.tmpl_dn;
+    a.tw1 = t.tw1; a.tw2 = t.tw2; a.scale = 1.0f;
+    fft_stages<false>(a, batch, s);
 }
 
 __global__ void chirp_twiddle_kernel(float2* tw1, float2* tw2) {
@@ -164,26 +249,6 @@ __global__ void chirp_twiddle_kernel(float2* tw1, float2* tw2) {
 __global__ void conj_kernel(float2* d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < kN) d[i].y = -d[i].y;
-}
-
-// signal -> zero-padded complex (:647-650)
-__global__ void chirp_pack_kernel(const float* __restrict__ samples, long long frame_stride, int n_in,
-                                  float2* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= kN) return;
-    const long long f = blockIdx.y;
-    out[static_cast<size_t>(f) * kN + i] = make_float2(i < n_in ? samples[f * frame_stride + i] : 0.0f, 0.0f);
-}
-
-// product with both template spectra (:656-659)
-__global__ void chirp_product_kernel(const float2* __restrict__ sig, const float2* __restrict__ tu,
-                                     const float2* __restrict__ td, float2* __restrict__ pu, float2* __restrict__ pd) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= kN) return;
-    const size_t o = static_cast<size_t>(blockIdx.y) * kN + i;
-    const float2 s = sig[o];
-    pu[o] = cmulf(s, tu[i]);
-    pd[o] = cmulf(s, td[i]);
 }
 
 __device__ __forceinline__ float cabs_d(float2 a) {
@@ -503,9 +568,7 @@ extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_con
     cudaStream_t s = ctx->stream;
     const int n_in = window < kN ? window : kN;
     time_begin(ctx, KK_CHIRP_SYNC);
-    chirp_pack_kernel<<<dim3(kN / 256, batch), 256, 0, s>>>(samples_dev, frame_stride, n_in, d_sig);
-    fft_forward(d_sig, batch, *t, s);
-    chirp_product_kernel<<<dim3(kN / 256, batch), 256, 0, s>>>(d_sig, t->tmpl_up, t->tmpl_dn, d_pu, d_pd);
+    fft_forward_real_to_products(samples_dev, frame_stride, n_in, d_sig, d_pu, d_pd, batch, *t, s);
     fft_inverse(d_pu, batch, *t, s);
     fft_inverse(d_pd, batch, *t, s);
     PeakArgs a{};
@@ -518,6 +581,6 @@ extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_con
     chirp_peak_kernel<<<batch, 256, 0, s>>>(a);
     time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 12;
+    ctx->launches += 10;
     return RIA_OK;
 }

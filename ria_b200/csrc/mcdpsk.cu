@@ -41,7 +41,8 @@ namespace {
 
 constexpr int kMaxCar = 16;
 constexpr int kSps = 512;
-constexpr int kSpsPad = kSps + 1;
+constexpr int kSymPad = kSps + 4;           // floats per staged symbol row: 16-byte aligned, bank shift 4 per row
+constexpr int kMixPad = kSps + 2;           // float2 per mixer row: 16-byte aligned, bank shift 4 per row
 constexpr int kGroup = 24;               // rx symbols correlated per pass (multiple of 1, 2 and 4)
 constexpr int kDemodThreads = 256;
 constexpr int kHilbertTaps = 127;
@@ -146,16 +147,48 @@ struct DemodArgs {
     unsigned int* counter;
 };
 
+// Shared memory of the demodulator: the mixer table only takes the rows of the carriers in use,
+// so that two CTAs fit on an SM for the 10-carrier modes.
 struct DemodSmem {
-    float2 mixer[kMaxCar * kSpsPad];
-    float sym[kGroup * kSpsPad];
+    float sym[kGroup * kSymPad];
     float2 corr[kGroup * kMaxCar];
     float2 prev[kMaxCar];
     float car_sum[kMaxCar], car_sq[kMaxCar], rel[kMaxCar], car_mag[kMaxCar];
     float scale;
     int valid_symbols;
     long long frame;
+    float2 mixer[1];           // [carriers][kMixPad], allocated with the launch
 };
+static size_t demod_smem_bytes(int carriers) {
+    return sizeof(DemodSmem) + static_cast<size_t>(carriers) * kMixPad * sizeof(float2);
+}
+
+// Packed fp32 multiply (Blackwell FMUL2): (s * m.x, s * m.y) in one issue slot.  The products go
+// through scalar adds, because ptxas would contract a packed multiply feeding a packed add into
+// FFMA2 (see ofdm.cu); the sums are the reference's `sum += samples[i] * mixer` (:940-943).
+__device__ __forceinline__ float2 mul2s(float s, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%2}; mov.b64 rb, {%3,%4}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(s), "f"(b.x), "f"(b.y));
+    return r;
+}
+// 512-term complex correlation of one staged symbol with one carrier's mixer row, in sample order
+__device__ __forceinline__ float2 correlate(const float* __restrict__ sy, const float2* __restrict__ mx) {
+    float2 acc = make_float2(0.f, 0.f);
+    const float4* sy4 = reinterpret_cast<const float4*>(sy);
+    const float4* mx4 = reinterpret_cast<const float4*>(mx);
+#pragma unroll 4
+    for (int i = 0; i < kSps / 4; ++i) {
+        const float4 v = sy4[i];
+        const float4 m01 = mx4[2 * i], m23 = mx4[2 * i + 1];
+        float2 p;
+        p = mul2s(v.x, make_float2(m01.x, m01.y)); acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
+        p = mul2s(v.y, make_float2(m01.z, m01.w)); acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
+        p = mul2s(v.z, make_float2(m23.x, m23.y)); acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
+        p = mul2s(v.w, make_float2(m23.z, m23.w)); acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
+    }
+    return acc;
+}
 
 __global__ void __launch_bounds__(kDemodThreads)
 mcdpsk_demod_kernel(const DemodArgs a) {
@@ -165,7 +198,7 @@ mcdpsk_demod_kernel(const DemodArgs a) {
     const int C = a.carriers;
     for (int i = tid; i < C * kSps; i += kDemodThreads) {
         const int c = i / kSps, k = i - c * kSps;
-        sm.mixer[c * kSpsPad + k] = a.mixer_g[i];
+        sm.mixer[c * kMixPad + k] = a.mixer_g[i];
     }
     __syncthreads();
 
@@ -201,13 +234,7 @@ mcdpsk_demod_kernel(const DemodArgs a) {
         for (int i = tid; i < kSps; i += kDemodThreads) sm.sym[i] = frame[a.training * kSps + i];
         __syncthreads();
         if (tid < C) {
-            float2 acc = make_float2(0.f, 0.f);
-            const float2* mx = sm.mixer + tid * kSpsPad;
-            for (int i = 0; i < kSps; ++i) {
-                const float s = sm.sym[i];
-                acc.x = __fadd_rn(acc.x, __fmul_rn(mx[i].x, s));
-                acc.y = __fadd_rn(acc.y, __fmul_rn(mx[i].y, s));
-            }
+            const float2 acc = correlate(sm.sym, sm.mixer + tid * kMixPad);
             float2 p = make_float2(__fdiv_rn(acc.x, static_cast<float>(kSps)), __fdiv_rn(acc.y, static_cast<float>(kSps)));
             const float m = cabs_d(p);
             if (m > 0.001f) { const float m2 = cabs_d(p); p = make_float2(__fdiv_rn(p.x, m2), __fdiv_rn(p.y, m2)); }
@@ -223,22 +250,14 @@ mcdpsk_demod_kernel(const DemodArgs a) {
             if (g_n < 0) g_n = 0;
             for (int i = tid; i < g_n * kSps; i += kDemodThreads) {
                 const int s = i / kSps, k = i - s * kSps;
-                sm.sym[s * kSpsPad + k] = __ldcs(frame + preamble + (g0 + s) * kSps + k);
+                sm.sym[s * kSymPad + k] = __ldcs(frame + preamble + (g0 + s) * kSps + k);
             }
             __syncthreads();
             for (int p = tid; p < kGroup * C; p += kDemodThreads) {
                 const int s = p / C, c = p - s * C;
                 float2 acc = make_float2(0.f, 0.f);
                 if (s < g_n) {
-                    const float2* mx = sm.mixer + c * kSpsPad;
-                    const float* sy = sm.sym + s * kSpsPad;
-#pragma unroll 8
-                    for (int i = 0; i < kSps; ++i) {                // sum += samples[i] * mixer  (:940-943)
-                        const float v = sy[i];
-                        const float2 m = mx[i];
-                        acc.x = __fadd_rn(acc.x, __fmul_rn(m.x, v));
-                        acc.y = __fadd_rn(acc.y, __fmul_rn(m.y, v));
-                    }
+                    acc = correlate(sm.sym + s * kSymPad, sm.mixer + c * kMixPad);     // sum += samples[i] * mixer  (:940-943)
                     acc = make_float2(__fdiv_rn(acc.x, static_cast<float>(kSps)), __fdiv_rn(acc.y, static_cast<float>(kSps)));
                 }
                 sm.corr[s * kMaxCar + c] = acc;
@@ -527,7 +546,7 @@ extern "C" int ria_mcdpsk_process_batch_at_dev(ria_ctx* ctx, const ria_mcdpsk_co
     float* d_bph = reinterpret_cast<float*>(base + a1);
     float* d_corr = reinterpret_cast<float*>(base + a1 + a2);
 
-    const size_t smem = sizeof(DemodSmem);
+    const size_t smem = demod_smem_bytes(C);
     RIA_CUDA(ctx, cudaFuncSetAttribute(mcdpsk_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     RIA_CUDA(ctx, cudaFuncSetAttribute(mcdpsk_demod_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
