@@ -64,6 +64,53 @@ __device__ __forceinline__ float cfo_phase_block32(float base, float inc, int la
     return mine;
 }
 
+// Closed-form parameters of one 32-sample block: returns true and the exact per-sample step
+// (S * ulp, representable in fp32) when all 32 phases of the block follow base + k * step.
+__device__ __forceinline__ bool cfo_block_step(float base, float inc, double* step_out) {
+    const unsigned bits = __float_as_uint(base);
+    const int e = static_cast<int>((bits >> 23) & 0xFF);
+    if (e > 0 && e < 255 && inc != 0.0f && fabs(static_cast<double>(base)) <= M_PI) {
+        const double ulp = __longlong_as_double(static_cast<long long>(e - 127 - 23 + 1023) << 52);   // 2^(e-150)
+        const double q = static_cast<double>(inc) / ulp;
+        const double S = rint(q);
+        if (fabs(q - trunc(q)) != 0.5 && fabs(S) < 4194304.0) {
+            const double step = S * ulp;
+            const double last = static_cast<double>(base) + 32.0 * step;      // exact
+            const double lo = __longlong_as_double(static_cast<long long>(e - 127 + 1023) << 52);   // 2^(e-127)
+            const double mag = fabs(last);
+            if ((mag > lo) && (mag < 2.0 * lo) && ((last < 0.0) == (base < 0.0f)) && (mag <= M_PI)) {
+                *step_out = step;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+// How many whole 32-sample blocks, starting at `base`, follow the closed form base + k * step:
+// the phase after the last of them must still be strictly inside base's binade, on the same side
+// of zero and inside the wrap range (the sequence is monotone, so the end point decides).
+// Requires cfo_block_step(base, inc, &step) == true, hence the result is >= 1.
+__device__ __forceinline__ int cfo_closed_form_blocks(float base, double step, int max_blocks) {
+    const int e = static_cast<int>((__float_as_uint(base) >> 23) & 0xFF);
+    const double lo = __longlong_as_double(static_cast<long long>(e - 127 + 1023) << 52);     // 2^(e-127)
+    const double b = fabs(static_cast<double>(base));
+    const double d = 32.0 * fabs(step);
+    const bool outward = (step < 0.0) == (base < 0.0f);          // |phase| grows
+    const double hi = fmin(2.0 * lo, M_PI);
+    // outward: b + m d < 2 lo and <= pi;  inward: b - m d > lo
+    double room = outward ? (hi - b) : (b - lo);
+    int m = static_cast<int>(fmin(floor(room / d), static_cast<double>(max_blocks)));
+    if (m < 1) m = 1;
+    for (;;) {                                                   // settle the strict inequalities exactly
+        const double last = outward ? b + m * d : b - m * d;
+        const bool ok = (last > lo) && (last < 2.0 * lo) && (last <= M_PI);
+        if (ok || m == 1) break;
+        --m;
+    }
+    return m;
+}
+
 // Per-thread variant: phase before sample k (0 <= k < 32) of a block whose first sample sees
 // `base`.  Same closed form, checked over the k steps actually taken.
 __device__ __forceinline__ float cfo_phase_at(float base, float inc, int k) {

@@ -160,11 +160,13 @@ struct KernelArgs {
     // staged pipeline
     float2* bins;                 // [frame][symbol][carrier] carrier bins written by the FFT kernel
     long long bins_frame0;        // frame index bins[0] belongs to
-    const float* block_phase;     // [frame - bins_frame0][block] CFO accumulator at sample 32*block
+    const float2* block_phase;    // [frame - frame_begin][block] {CFO accumulator at sample 32*block, per-sample step or NaN}
     int n_blocks;
     int pruned;                   // all used bins have distinct residues mod 64
-    int* rerun_list;              // frames the carrier kernel hands to the monolithic kernel
+    int* rerun_list;              // chunk-local ids of the frames whose LTS asks for the residual-CFO re-run
     unsigned int* rerun_count;
+    float* rerun_cfo;             // [chunk] corrected CFO of those frames (input CFO + LTS residual)
+    int second_pass;              // this launch re-runs the listed frames with rerun_cfo
     long long frame_begin, frame_end;   // chunk of the batch this launch covers
 };
 
@@ -298,7 +300,7 @@ template <int G>
 __device__ __forceinline__ void frame_reset(CarState& cs, const KernelArgs& a, long long f, int g) {
     // demodulator.cpp:1264-1300
     if (g == 0) {
-        cs.s.cfo_hz = a.cfo_hz ? a.cfo_hz[f] : 0.0f;
+        cs.s.cfo_hz = a.second_pass ? a.rerun_cfo[f - a.frame_begin] : (a.cfo_hz ? a.cfo_hz[f] : 0.0f);
         cs.s.cfo_phase = a.phase ? a.phase[f] : 0.0f;
         cs.s.phase_start = cs.s.cfo_phase;
         cs.s.noise_var = 0.1f;
@@ -1032,21 +1034,45 @@ __device__ __forceinline__ float cfo_phase_inc(float cfo_hz, int sample_rate) {
 // every 32nd sample of the frame.  Frames without a usable CFO are skipped (never read).
 __global__ void ofdm_phase_scan_kernel(const float* __restrict__ cfo_hz, const float* __restrict__ phase0,
                                        long long frame_begin, long long n_local, int n_blocks, int sample_rate,
-                                       float* __restrict__ block_phase /*[n_local][n_blocks]*/) {
-    const long long w = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+                                       float2* __restrict__ block_phase /*[n_local][n_blocks]*/,
+                                       const int* __restrict__ list, const unsigned int* __restrict__ list_count,
+                                       const float* __restrict__ list_cfo) {
+    long long w = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= n_local) return;
+    float cfo;
+    if (list) {                                   // second pass: the listed frames with their corrected CFO
+        if (w >= static_cast<long long>(*list_count)) return;
+        w = list[w];
+        cfo = list_cfo[w];
+    } else {
+        if (w >= n_local || !cfo_hz) return;
+        cfo = cfo_hz[frame_begin + w];
+    }
     const long long f = frame_begin + w;
-    const float cfo = cfo_hz[f];
     if (!(fabsf(cfo) > 0.01f)) return;
     const float inc = cfo_phase_inc(cfo, sample_rate);
     float base = phase0 ? phase0[f] : 0.0f;
-    float* out = block_phase + w * n_blocks;
-    for (int b = 0; b < n_blocks; ++b) {
-        if (lane == 0) out[b] = base;
-        float next;
-        (void)cfo_phase_block32(base, inc, lane, &next);
-        base = next;
+    float2* out = block_phase + w * n_blocks;
+    // {phase before the block's first sample, exact per-sample step}: the FFT stage then has
+    // phase_k = fl(base + k * step); step = NaN marks a block that has to be stepped (binade
+    // crossing, wrap or tie).  Between two such events the closed form holds for a whole stretch
+    // of blocks, which the lanes fill in parallel.
+    int b = 0;
+    while (b < n_blocks) {
+        double step = 0.0;
+        if (!cfo_block_step(base, inc, &step)) {
+            if (lane == 0) out[b] = make_float2(base, __int_as_float(0x7fc00000));
+#pragma unroll 1
+            for (int k = 0; k < 32; ++k) base = cfo_phase_step(base, inc);
+            ++b;
+            continue;
+        }
+        const int m = cfo_closed_form_blocks(base, step, n_blocks - b);
+        const float stepf = static_cast<float>(step);
+        for (int j = lane; j < m; j += 32)
+            out[b + j] = make_float2(static_cast<float>(static_cast<double>(base) + (32.0 * j) * step), stepf);
+        base = static_cast<float>(static_cast<double>(base) + (32.0 * m) * step);
+        b += m;
     }
 }
 
@@ -1068,6 +1094,7 @@ ofdm_fft_kernel(const KernelArgs a) {
     FftSmem& sm = *reinterpret_cast<FftSmem*>(smem_raw);
     __shared__ unsigned int item_sh;
     const int tid = threadIdx.x;
+    if (a.second_pass && *a.rerun_count == 0) return;          // the usual case: nothing to re-run
 
     for (int i = tid; i < kTwCount; i += kThreads) sm.tw[i] = a.tw_g[i];
     {
@@ -1088,7 +1115,8 @@ ofdm_fft_kernel(const KernelArgs a) {
     if (PRUNED) plan = make_pruned_plan(sm.tw, sm.res_car, sm.res_k, (((tid >> 5) & 1) << 5) | (tid & 31));
 
     const int n_sym = a.frame_len / a.sym_len;
-    const long long n_local = a.frame_end - a.frame_begin;
+    // first pass: every frame of the chunk; second pass: the frames the carrier stage listed
+    const long long n_local = a.second_pass ? static_cast<long long>(*a.rerun_count) : a.frame_end - a.frame_begin;
     const unsigned n_groups = static_cast<unsigned>((n_local + kFftGroup - 1) / kFftGroup);
     const unsigned n_items = n_groups * static_cast<unsigned>(n_sym);
     int cur_sym = -1;
@@ -1108,16 +1136,18 @@ ofdm_fft_kernel(const KernelArgs a) {
             cur_sym = s;
             __syncthreads();
         }
-        const long long f0 = a.frame_begin + static_cast<long long>(grp) * kFftGroup;
-        const long long f1 = (f0 + kFftGroup < a.frame_end) ? f0 + kFftGroup : a.frame_end;
+        const long long i0 = static_cast<long long>(grp) * kFftGroup;
+        const long long i1 = (i0 + kFftGroup < n_local) ? i0 + kFftGroup : n_local;
+        auto frame_of = [&](long long i) -> long long { return a.frame_begin + (a.second_pass ? a.rerun_list[i] : i); };
 
         float nxt[8];
         {
-            const float* p = a.samples + f0 * a.frame_stride + win + tid;
+            const float* p = a.samples + frame_of(i0) * a.frame_stride + win + tid;
 #pragma unroll
             for (int q = 0; q < 8; ++q) nxt[q] = __ldcs(p + 128 * q);
         }
-        for (long long f = f0; f < f1; ++f) {
+        for (long long i = i0; i < i1; ++i) {
+            const long long f = frame_of(i);
             // ---- mix: v[t] = baseband sample (tid + 128 * brev3(t)) of the FFT window ----
             float2 v[8];
 #pragma unroll
@@ -1127,22 +1157,31 @@ ofdm_fft_kernel(const KernelArgs a) {
                 // samples[i] * conj(osc)  ->  (osc.re * s, (-osc.im) * s)
                 v[t] = make_float2(__fmul_rn(osc.x, nxt[q]), __fmul_rn(osc.y, nxt[q]));
             }
-            if (f + 1 < f1) {
-                const float* p = a.samples + (f + 1) * a.frame_stride + win + tid;
+            if (i + 1 < i1) {
+                const float* p = a.samples + frame_of(i + 1) * a.frame_stride + win + tid;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) nxt[q] = __ldcs(p + 128 * q);
             }
-            if (a.cfo_hz) {
-                const float cfo = a.cfo_hz[f];
+            if (a.cfo_hz || a.second_pass) {
+                const float cfo = a.second_pass ? a.rerun_cfo[f - a.frame_begin] : a.cfo_hz[f];
                 if (fabsf(cfo) > 0.01f) {
                     const float inc = cfo_phase_inc(cfo, a.sample_rate);
-                    const float* bp = a.block_phase + (f - a.frame_begin) * a.n_blocks;
+                    const float2* bp = a.block_phase + (f - a.frame_begin) * a.n_blocks;
 #pragma unroll
                     for (int t = 0; t < 8; ++t) {
                         const int q = ((t & 1) << 2) | (t & 2) | ((t & 4) >> 2);
                         const int n = win + tid + 128 * q;
-                        const float ph = cfo_phase_at(bp[n >> 5], inc, n & 31);
-                        v[t] = cmul(v[t], cexpj(ph));
+                        const float2 blk = __ldg(bp + (n >> 5));
+                        float ph;
+                        if (blk.y == blk.y) ph = static_cast<float>(static_cast<double>(blk.x) + static_cast<double>(n & 31) * static_cast<double>(blk.y));
+                        else {
+                            ph = blk.x;
+#pragma unroll 1
+                            for (int k = 0; k < (n & 31); ++k) ph = cfo_phase_step(ph, inc);
+                        }
+                        float sn, cs;
+                        glibc_sincosf(ph, &sn, &cs);
+                        v[t] = cmul(v[t], make_float2(cs, sn));
                     }
                 }
             }
@@ -1166,6 +1205,7 @@ ofdm_carrier_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CarSmem& sm = *reinterpret_cast<CarSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (a.second_pass && *a.rerun_count == 0) return;
     {
         const int* src = reinterpret_cast<const int*>(a.car_g);
         int* dst = reinterpret_cast<int*>(&sm.car);
@@ -1179,10 +1219,14 @@ ofdm_carrier_kernel(const KernelArgs a) {
     const int n_data_sym = n_sym - 2;
 
     for (;;) {
-        long long f = 0;
-        if (lane == 0) f = a.frame_begin + static_cast<long long>(atomicAdd(a.counter, 1u));
+        long long f = -1;
+        if (lane == 0) {
+            const long long i = static_cast<long long>(atomicAdd(a.counter, 1u));
+            if (a.second_pass) { if (i < static_cast<long long>(*a.rerun_count)) f = a.frame_begin + a.rerun_list[i]; }
+            else if (a.frame_begin + i < a.frame_end) f = a.frame_begin + i;
+        }
         f = __shfl_sync(0xffffffffu, f, 0);
-        if (f >= a.frame_end) break;
+        if (f < 0) break;
         if (n_sym < 2) { frame_too_short<32>(a, f, lane); continue; }
         const float2* fb = a.bins + (f - a.bins_frame0) * n_sym * nc;
 
@@ -1193,9 +1237,15 @@ ofdm_carrier_kernel(const KernelArgs a) {
             __syncwarp();
             lts_symbol<32>(cs, car, s, lane);
         }
-        if (lts_residual<32>(cs, car, a, lane)) {
-            // the reference now re-mixes the frame with the corrected CFO: hand it over
-            if (lane == 0) a.rerun_list[atomicAdd(a.rerun_count, 1u)] = static_cast<int>(f - a.frame_begin);
+        // The reference checks the residual CFO only on its first LTS pass (:304-382); when it asks
+        // for a re-run the whole frame is mixed again with the corrected CFO, so the frame goes
+        // back to the phase-scan / FFT stages and returns here as a second-pass frame.
+        if (!a.second_pass && lts_residual<32>(cs, car, a, lane)) {
+            if (lane == 0) {
+                const int fl = static_cast<int>(f - a.frame_begin);
+                a.rerun_cfo[fl] = cs.s.cfo_hz;
+                a.rerun_list[atomicAdd(a.rerun_count, 1u)] = fl;
+            }
             continue;
         }
         lts_finish<32>(cs, car, a, f, lane);
@@ -1491,17 +1541,19 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
     const int64_t chunk = n_frames < 65536 ? n_frames : 65536;
     const int n_blocks = (n_sym * t->sym_len + 31) / 32;
     const size_t bins_b = bins_dev ? 0 : static_cast<size_t>(chunk) * n_sym * nc * sizeof(float2);
-    const size_t phase_b = cfo_hz_dev ? static_cast<size_t>(chunk) * n_blocks * sizeof(float) : 0;
+    const size_t phase_b = static_cast<size_t>(chunk) * n_blocks * sizeof(float2);
     const size_t list_b = static_cast<size_t>(chunk) * sizeof(int);
-    rc = ensure_ofdm_scratch(ctx, bins_b + phase_b + list_b + 256);
+    rc = ensure_ofdm_scratch(ctx, bins_b + phase_b + 2 * list_b + 256);
     if (rc != RIA_OK) return rc;
     unsigned char* sp = static_cast<unsigned char*>(ctx->ofdm_scratch);
     float2* bins_scratch = reinterpret_cast<float2*>(sp);
-    float* block_phase = reinterpret_cast<float*>(sp + bins_b);
+    float2* block_phase = reinterpret_cast<float2*>(sp + bins_b);
     a.rerun_list = reinterpret_cast<int*>(sp + bins_b + phase_b);
+    a.rerun_cfo = reinterpret_cast<float*>(sp + bins_b + phase_b + list_b);
     a.block_phase = block_phase;
     a.n_blocks = n_blocks;
-    unsigned int* ctr = ctx->work_counter + 8;      // [0] fft items, [1] carrier frames, [2] rerun count, [3] rerun work
+    // [0] fft items, [1] carrier frames, [2] re-run count, [3] fft items and [4] carrier frames of the second pass
+    unsigned int* ctr = ctx->work_counter + 8;
     a.rerun_count = ctr + 2;
 
     for (int64_t off = 0; off < n_frames; off += chunk) {
@@ -1509,43 +1561,36 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
         a.frame_begin = off; a.frame_end = off + n;
         if (bins_dev) { a.bins = reinterpret_cast<float2*>(bins_dev); a.bins_frame0 = 0; }
         else          { a.bins = bins_scratch; a.bins_frame0 = off; }
-        RIA_CUDA(ctx, cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), st));
-        if (cfo_hz_dev) {
-            time_begin(ctx, KK_OFDM_PHASE);
-            ofdm_phase_scan_kernel<<<static_cast<unsigned>((n + 3) / 4), 128, 0, st>>>(
-                cfo_hz_dev, phase_dev, off, n, n_blocks, a.sample_rate, block_phase);
-            time_end(ctx);
-            ctx->launches += 1;
-        }
-        {
-            const long long items = ((n + kFftGroup - 1) / kFftGroup) * n_sym;
-            long long grid = static_cast<long long>(ctx->sm_count) * fft_per_sm;
-            if (grid > items) grid = items;
-            a.counter = ctr + 0;
+        RIA_CUDA(ctx, cudaMemsetAsync(ctr, 0, 5 * sizeof(unsigned int), st));
+        const long long items = ((n + kFftGroup - 1) / kFftGroup) * n_sym;
+        long long fft_grid = static_cast<long long>(ctx->sm_count) * fft_per_sm;
+        if (fft_grid > items) fft_grid = items;
+        long long car_grid = static_cast<long long>(ctx->sm_count) * car_per_sm;
+        if (car_grid > (n + kCarWarps - 1) / kCarWarps) car_grid = (n + kCarWarps - 1) / kCarWarps;
+        // pass 0: every frame with the CFO it was handed; pass 1: the frames whose LTS asked for
+        // the residual-CFO re-run, with the corrected CFO (kernels exit at once when there are none)
+        for (int pass = 0; pass < 2; ++pass) {
+            a.second_pass = pass;
+            if (pass == 1 || cfo_hz_dev) {
+                time_begin(ctx, KK_OFDM_PHASE);
+                ofdm_phase_scan_kernel<<<static_cast<unsigned>((n + 3) / 4), 128, 0, st>>>(
+                    cfo_hz_dev, phase_dev, off, n, n_blocks, a.sample_rate, block_phase,
+                    pass ? a.rerun_list : nullptr, a.rerun_count, a.rerun_cfo);
+                time_end(ctx);
+                ctx->launches += 1;
+            }
+            a.counter = ctr + (pass ? 3 : 0);
             time_begin(ctx, KK_OFDM_FFT);
-            if (a.pruned) ofdm_fft_kernel<true><<<static_cast<unsigned>(grid), kThreads, sizeof(FftSmem), st>>>(a);
-            else          ofdm_fft_kernel<false><<<static_cast<unsigned>(grid), kThreads, sizeof(FftSmem), st>>>(a);
+            if (a.pruned) ofdm_fft_kernel<true><<<static_cast<unsigned>(fft_grid), kThreads, sizeof(FftSmem), st>>>(a);
+            else          ofdm_fft_kernel<false><<<static_cast<unsigned>(fft_grid), kThreads, sizeof(FftSmem), st>>>(a);
             time_end(ctx);
-        }
-        {
-            long long grid = static_cast<long long>(ctx->sm_count) * car_per_sm;
-            const long long need = (n + kCarWarps - 1) / kCarWarps;
-            if (grid > need) grid = need;
-            a.counter = ctr + 1;
+            a.counter = ctr + (pass ? 4 : 1);
             time_begin(ctx, KK_OFDM_CARRIER);
-            carrier_kernel<<<static_cast<unsigned>(grid), kCarWarps * 32, sizeof(CarSmem), st>>>(a);
+            carrier_kernel<<<static_cast<unsigned>(car_grid), kCarWarps * 32, sizeof(CarSmem), st>>>(a);
             time_end(ctx);
-        }
-        {
-            long long grid = static_cast<long long>(ctx->sm_count) * mono_per_sm;
-            if (grid > n) grid = n;
-            a.counter = ctr + 3;
-            time_begin(ctx, KK_OFDM_DEMOD);
-            ofdm_presynced_kernel<<<static_cast<unsigned>(grid), kThreads, sizeof(MonoSmem), st>>>(a);
-            time_end(ctx);
+            ctx->launches += 2;
         }
         RIA_CUDA(ctx, cudaGetLastError());
-        ctx->launches += 3;
     }
     return RIA_OK;
 }
