@@ -111,6 +111,37 @@ __device__ __forceinline__ int cfo_closed_form_blocks(float base, double step, i
     return m;
 }
 
+// Warp-collective scan of one frame: out[b] = {phase before sample 32 b, exact per-sample step of
+// that block, or NaN when the block has to be stepped (binade crossing, wrap, tie)}.  Between two
+// such events the closed form holds for a whole stretch of blocks, which the lanes fill in parallel.
+// A consumer evaluates phase_k = fl(base + k * step), k < 32 (cfo_block_phase below).
+__device__ __forceinline__ void cfo_scan_frame(float base, float inc, int n_blocks, float2* __restrict__ out, int lane) {
+    int b = 0;
+    while (b < n_blocks) {
+        double step = 0.0;
+        if (!cfo_block_step(base, inc, &step)) {
+            if (lane == 0) out[b] = make_float2(base, __int_as_float(0x7fc00000));
+#pragma unroll 1
+            for (int k = 0; k < 32; ++k) base = cfo_phase_step(base, inc);
+            ++b;
+            continue;
+        }
+        const int m = cfo_closed_form_blocks(base, step, n_blocks - b);
+        const float stepf = static_cast<float>(step);
+        for (int j = lane; j < m; j += 32)
+            out[b + j] = make_float2(static_cast<float>(static_cast<double>(base) + (32.0 * j) * step), stepf);
+        base = static_cast<float>(static_cast<double>(base) + (32.0 * m) * step);
+        b += m;
+    }
+}
+__device__ __forceinline__ float cfo_block_phase(float2 blk, float inc, int k) {
+    if (blk.y == blk.y) return static_cast<float>(static_cast<double>(blk.x) + static_cast<double>(k) * static_cast<double>(blk.y));
+    float ph = blk.x;
+#pragma unroll 1
+    for (int i = 0; i < k; ++i) ph = cfo_phase_step(ph, inc);
+    return ph;
+}
+
 // Per-thread variant: phase before sample k (0 <= k < 32) of a block whose first sample sees
 // `base`.  Same closed form, checked over the k steps actually taken.
 __device__ __forceinline__ float cfo_phase_at(float base, float inc, int k) {

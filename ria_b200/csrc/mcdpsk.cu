@@ -24,6 +24,7 @@
 // evaluated in the reference's order.
 
 #include "cfo_phase.cuh"
+#include "rn_math.h"
 #include "ria_internal.h"
 
 #include <cmath>
@@ -52,7 +53,8 @@ __device__ __forceinline__ float cabs_d(float2 a) {
     const double x = a.x, y = a.y;
     return static_cast<float>(sqrt(x * x + y * y));
 }
-__device__ __forceinline__ float atan2_rn(float y, float x) { return static_cast<float>(atan2(static_cast<double>(y), static_cast<double>(x))); }
+// std::arg / std::sin / std::cos on floats are glibc's atan2f / sinf / cosf: restated bit for bit in rn_math.h
+__device__ __noinline__ float atan2_rn(float y, float x) { return glibc_atan2f(y, x); }
 __device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }
 __device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b : a; }
 
@@ -61,7 +63,7 @@ __device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b 
 // ---------------------------------------------------------------------------------------------
 __global__ void mcdpsk_phase_scan_kernel(const float* __restrict__ cfo_hz, const float* __restrict__ phase0,
                                          long long frame0, long long n_frames, int n_blocks, float sample_rate,
-                                         float* __restrict__ block_phase /*[n][n_blocks]*/) {
+                                         float2* __restrict__ block_phase /*[n][n_blocks]*/) {
     const long long fl = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (fl >= n_frames) return;
@@ -70,25 +72,26 @@ __global__ void mcdpsk_phase_scan_kernel(const float* __restrict__ cfo_hz, const
     if (!(fabsf(cfo) > 0.1f)) return;
     // phase_inc = -2.0f * M_PI * cfo_hz / sample_rate   (multi_carrier_dpsk.hpp:911)
     const float inc = static_cast<float>(-2.0f * M_PI * static_cast<double>(cfo) / static_cast<double>(sample_rate));
-    float base = phase0 ? phase0[f] : 0.0f;
-    float* out = block_phase + fl * n_blocks;
-    for (int b = 0; b < n_blocks; ++b) {
-        if (lane == 0) out[b] = base;
-        float next;
-        (void)cfo_phase_block32(base, inc, lane, &next);
-        base = next;
-    }
+    cfo_scan_frame(phase0 ? phase0[f] : 0.0f, inc, n_blocks, block_phase + fl * n_blocks, lane);
 }
 
-// One thread per sample; a CTA covers 1024 consecutive samples of one frame (+126 history).
-__global__ void __launch_bounds__(256)
+// HilbertTransform(127) taps (filters.cpp:266-291); only the even-indexed taps are non-zero.  In
+// constant memory every tap is an immediate operand of its multiply once the loop is unrolled.
+__constant__ float c_hilbert[kHilbertTaps + 1];
+
+// A CTA covers 1024 consecutive samples of one frame (+126 samples of history); each thread
+// produces four consecutive outputs.  q_i = sum_k coeffs[k] * x[i - k] in ascending k
+// (filters.cpp:299-306) -- the odd taps are exactly zero and add nothing -- so the four chains
+// run side by side: every tap needs one new pair of inputs (the window slides by two) and one
+// broadcast load of the tap; the adds stay ordered.
+__global__ void __launch_bounds__(256, 4)
 mcdpsk_cfo_kernel(const float* __restrict__ samples, long long frame_stride, int frame_len,
                   const int* __restrict__ start, long long frame0,
-                  const float* __restrict__ cfo_hz, const float* __restrict__ block_phase, int n_blocks,
-                  const float* __restrict__ taps_g, float sample_rate,
-                  float* __restrict__ out, long long out_stride) {
+                  const float* __restrict__ cfo_hz, const float2* __restrict__ block_phase, int n_blocks,
+                  float sample_rate, float* __restrict__ out, long long out_stride) {
+    constexpr int kHist = kHilbertTaps - 1;          // 126
+    __shared__ __align__(16) float x[1024 + kHist + 2];
     __shared__ float taps[kHilbertTaps + 1];
-    __shared__ float x[1024 + kHilbertTaps];
     const long long fl = blockIdx.y;                 // frame inside the chunk
     const long long f = frame0 + fl;
     const int chunk0 = blockIdx.x * 1024;
@@ -99,32 +102,39 @@ mcdpsk_cfo_kernel(const float* __restrict__ samples, long long frame_stride, int
     float* dst = out + fl * out_stride;
     const bool active = fabsf(cfo) > 0.1f && frame_len >= 128;      // :838, :903
     if (!active) return;                       // the demodulator reads such frames straight from the input
-    if (threadIdx.x < kHilbertTaps) taps[threadIdx.x] = taps_g[threadIdx.x];
-    for (int i = threadIdx.x; i < 1024 + kHilbertTaps - 1; i += 256) {
-        const int g = chunk0 - (kHilbertTaps - 1) + i;
+    if (threadIdx.x < kHilbertTaps) taps[threadIdx.x] = c_hilbert[threadIdx.x];
+    for (int i = threadIdx.x; i < 1024 + kHist; i += 256) {
+        const int g = chunk0 - kHist + i;
         x[i] = (g >= 0 && g < frame_len) ? src[g] : 0.0f;          // delay line starts at zero
     }
     __syncthreads();
     const float inc = static_cast<float>(-2.0f * M_PI * static_cast<double>(cfo) / static_cast<double>(sample_rate));
-    const int lane = threadIdx.x & 31;
-    for (int r = 0; r < 4; ++r) {
-        const int li = r * 256 + threadIdx.x;          // local sample
-        const int gi = chunk0 + li;
-        const int blk = gi >> 5;
-        float nx;
-        const float ph = (blk < n_blocks) ? cfo_phase_block32(block_phase[fl * n_blocks + blk], inc, lane, &nx) : 0.0f;
-        if (gi >= frame_len) continue;
-        // q = sum_k coeffs[k] * x[i - k], ascending k (filters.cpp:299-306); odd taps are exactly 0
-        float q = 0.0f;
-        const float* xp = x + li + (kHilbertTaps - 1);
-#pragma unroll 8
-        for (int k = 0; k < kHilbertTaps; k += 2) q = __fadd_rn(q, __fmul_rn(taps[k], xp[-k]));
-        const float re = xp[-kHilbertDelay];           // delayed input (filters.cpp:309-310)
-        double s, c;
-        sincos(static_cast<double>(ph), &s, &c);
-        const float cr = static_cast<float>(c), sr = static_cast<float>(s);
+    const int li = 4 * threadIdx.x;                  // first of this thread's four local samples
+    const int gi = chunk0 + li;
+    if (gi >= frame_len) return;
+    // window w = x[i - k .. i - k + 3] for the current tap k, i = li (index in x: + kHist)
+    const float* xp = x + li + kHist;
+    float2 w01 = *reinterpret_cast<const float2*>(xp), w23 = *reinterpret_cast<const float2*>(xp + 2);
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kHilbertTaps; k += 2) {
+        const float c = taps[k];                           // one broadcast load per tap
+        q0 = __fadd_rn(q0, __fmul_rn(c, w01.x)); q1 = __fadd_rn(q1, __fmul_rn(c, w01.y));
+        q2 = __fadd_rn(q2, __fmul_rn(c, w23.x)); q3 = __fadd_rn(q3, __fmul_rn(c, w23.y));
+        if (k + 2 < kHilbertTaps) { w23 = w01; w01 = *reinterpret_cast<const float2*>(xp - k - 2); }
+    }
+    const float q[4] = {q0, q1, q2, q3};
+    const float2* bp = block_phase + fl * n_blocks;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int g = gi + j;
+        if (g >= frame_len) break;
+        const float re = xp[j - kHilbertDelay];            // delayed input (filters.cpp:309-310)
+        const float ph = cfo_block_phase(bp[g >> 5], inc, g & 31);
+        float sr, cr;
+        glibc_sincosf_uniform(ph, &sr, &cr);               // Complex(std::cos(phase), std::sin(phase)), :913
         // real part of analytic * rotation (:916-917)
-        dst[gi] = __fsub_rn(__fmul_rn(re, cr), __fmul_rn(q, sr));
+        dst[g] = __fsub_rn(__fmul_rn(re, cr), __fmul_rn(q[j], sr));
     }
 }
 
@@ -411,12 +421,12 @@ mcdpsk_demod_kernel(const DemodArgs a) {
             const float phase = phases[d * kMaxCar + c];
             const float cs = sm.scale * sm.rel[c];
             if (a.bits == 2) {
-                const float sb0 = cs * static_cast<float>(sin(static_cast<double>(phase)));
-                const float sb1 = cs * static_cast<float>(sin(static_cast<double>(2.0f * phase)));
+                const float sb0 = cs * glibc_sinf(phase);
+                const float sb1 = cs * glibc_sinf(2.0f * phase);
                 llr_out[p * 2] = std_max(-20.0f, std_min(20.0f, sb0));
                 llr_out[p * 2 + 1] = std_max(-20.0f, std_min(20.0f, sb1));
             } else {
-                const float sb = cs * static_cast<float>(cos(static_cast<double>(phase)));
+                const float sb = cs * glibc_cosf(phase);
                 llr_out[p] = std_max(-20.0f, std_min(20.0f, sb));
             }
         }
@@ -488,6 +498,7 @@ static int mcdpsk_tables_dev(ria_ctx* ctx, const ria_mcdpsk_config& cfg, const M
     RIA_CUDA(ctx, cudaMalloc(&t->hilbert, taps.size() * sizeof(float)));
     RIA_CUDA(ctx, cudaMemcpy(t->mixer, mixer.data(), mixer.size() * sizeof(float2), cudaMemcpyHostToDevice));
     RIA_CUDA(ctx, cudaMemcpy(t->hilbert, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    RIA_CUDA(ctx, cudaMemcpyToSymbol(c_hilbert, taps.data(), taps.size() * sizeof(float)));
     t->ready = true;
     *out = t;
     return RIA_OK;
@@ -530,20 +541,20 @@ extern "C" int ria_mcdpsk_process_batch_at_dev(ria_ctx* ctx, const ria_mcdpsk_co
     // vector, block phases + corrected samples) stays bounded for 10^5-frame batches.
     const size_t corr_stride = (static_cast<size_t>(frame_len) + 3) & ~size_t(3);
     const size_t per_frame = static_cast<size_t>(3) * max_ds * kMaxCar * sizeof(float) +
-                             (cfo_hz_dev ? (static_cast<size_t>(n_blocks) + corr_stride) * sizeof(float) : 0);
+                             (cfo_hz_dev ? (2 * static_cast<size_t>(n_blocks) + corr_stride) * sizeof(float) : 0);
     int64_t chunk = static_cast<int64_t>((size_t(3) << 30) / (per_frame ? per_frame : 1));     // <= 3 GiB of scratch
     if (chunk > 65535) chunk = 65535;
     if (chunk > n_frames) chunk = n_frames;
     if (chunk < 1) chunk = 1;
     const size_t s_demod = static_cast<size_t>(chunk) * 3 * max_ds * kMaxCar * sizeof(float);
-    const size_t s_phase = cfo_hz_dev ? static_cast<size_t>(chunk) * n_blocks * sizeof(float) : 0;
+    const size_t s_phase = cfo_hz_dev ? static_cast<size_t>(chunk) * n_blocks * sizeof(float2) : 0;
     const size_t s_corr = cfo_hz_dev ? static_cast<size_t>(chunk) * corr_stride * sizeof(float) : 0;
     const size_t a1 = (s_demod + 255) & ~size_t(255), a2 = (s_phase + 255) & ~size_t(255);
     rc = ensure_scratch(ctx, a1 + a2 + s_corr + 256);
     if (rc != RIA_OK) return rc;
     unsigned char* base = static_cast<unsigned char*>(ctx->scratch);
     float* d_scr = reinterpret_cast<float*>(base);
-    float* d_bph = reinterpret_cast<float*>(base + a1);
+    float2* d_bph = reinterpret_cast<float2*>(base + a1);
     float* d_corr = reinterpret_cast<float*>(base + a1 + a2);
 
     const size_t smem = demod_smem_bytes(C);
@@ -565,7 +576,7 @@ extern "C" int ria_mcdpsk_process_batch_at_dev(ria_ctx* ctx, const ria_mcdpsk_co
                                                                           cfg->sample_rate, d_bph);
             dim3 grid(static_cast<unsigned>((frame_len + 1023) / 1024), static_cast<unsigned>(n));
             mcdpsk_cfo_kernel<<<grid, 256, 0, ctx->stream>>>(samples_dev, frame_stride, frame_len, start_dev, off,
-                                                             cfo_hz_dev, d_bph, n_blocks, t->hilbert, cfg->sample_rate,
+                                                             cfo_hz_dev, d_bph, n_blocks, cfg->sample_rate,
                                                              d_corr, static_cast<long long>(corr_stride));
             time_end(ctx);
             RIA_CUDA(ctx, cudaGetLastError());

@@ -1053,27 +1053,7 @@ __global__ void ofdm_phase_scan_kernel(const float* __restrict__ cfo_hz, const f
     const float inc = cfo_phase_inc(cfo, sample_rate);
     float base = phase0 ? phase0[f] : 0.0f;
     float2* out = block_phase + w * n_blocks;
-    // {phase before the block's first sample, exact per-sample step}: the FFT stage then has
-    // phase_k = fl(base + k * step); step = NaN marks a block that has to be stepped (binade
-    // crossing, wrap or tie).  Between two such events the closed form holds for a whole stretch
-    // of blocks, which the lanes fill in parallel.
-    int b = 0;
-    while (b < n_blocks) {
-        double step = 0.0;
-        if (!cfo_block_step(base, inc, &step)) {
-            if (lane == 0) out[b] = make_float2(base, __int_as_float(0x7fc00000));
-#pragma unroll 1
-            for (int k = 0; k < 32; ++k) base = cfo_phase_step(base, inc);
-            ++b;
-            continue;
-        }
-        const int m = cfo_closed_form_blocks(base, step, n_blocks - b);
-        const float stepf = static_cast<float>(step);
-        for (int j = lane; j < m; j += 32)
-            out[b + j] = make_float2(static_cast<float>(static_cast<double>(base) + (32.0 * j) * step), stepf);
-        base = static_cast<float>(static_cast<double>(base) + (32.0 * m) * step);
-        b += m;
-    }
+    cfo_scan_frame(base, inc, n_blocks, out, lane);
 }
 
 // ------------------------------- stage 1: mix + FFT ----------------------------------------
@@ -1171,16 +1151,9 @@ ofdm_fft_kernel(const KernelArgs a) {
                     for (int t = 0; t < 8; ++t) {
                         const int q = ((t & 1) << 2) | (t & 2) | ((t & 4) >> 2);
                         const int n = win + tid + 128 * q;
-                        const float2 blk = __ldg(bp + (n >> 5));
-                        float ph;
-                        if (blk.y == blk.y) ph = static_cast<float>(static_cast<double>(blk.x) + static_cast<double>(n & 31) * static_cast<double>(blk.y));
-                        else {
-                            ph = blk.x;
-#pragma unroll 1
-                            for (int k = 0; k < (n & 31); ++k) ph = cfo_phase_step(ph, inc);
-                        }
+                        const float ph = cfo_block_phase(__ldg(bp + (n >> 5)), inc, n & 31);
                         float sn, cs;
-                        glibc_sincosf(ph, &sn, &cs);
+                        glibc_sincosf_uniform(ph, &sn, &cs);
                         v[t] = cmul(v[t], make_float2(cs, sn));
                     }
                 }

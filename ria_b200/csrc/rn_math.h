@@ -247,6 +247,22 @@ RN_HD void glibc_sincosf(float y, float* sinp, float* cosp) {
     }
 }
 
+// Same results as glibc_sincosf for |y| < 120 without the |y| < pi/4 fork: reduce_fast returns
+// n = 0 and x unchanged there, and below 2^-12 the polynomials round to (y, 1) by themselves, so
+// one straight-line path serves all lanes of a warp.  (|y| >= 120 goes to glibc_sincosf.)
+RN_HD void glibc_sincosf_uniform(float y, float* sinp, float* cosp) {
+    if (!(rn_abstop12(y) < rn_abstop12(120.0f))) { glibc_sincosf(y, sinp, cosp); return; }
+    int n;
+    const double x = rn_sc_reduce(static_cast<double>(y), &n);
+    const double s = ((n + 1) & 2) ? -1.0 : 1.0;                       // sign[n & 3] = {1, -1, -1, 1}
+    const double flip = (n & 2) ? -1.0 : 1.0;
+    const double x2 = x * x;
+    const float ps = static_cast<float>(rn_sc_sin(x * s, x2));
+    const float pc = static_cast<float>(rn_sc_cos(x2, flip));
+    *sinp = (n & 1) ? pc : ps;
+    *cosp = (n & 1) ? ps : pc;
+}
+
 RN_HD float glibc_sinf(float y) {
     double x = static_cast<double>(y);
     if (rn_abstop12(y) < rn_abstop12(0x1.921FB6p-1f)) {

@@ -24,6 +24,8 @@ int main(int argc, char** argv) {
         float rs, rc;
         sincosf(x, &rs, &rc);
         bad_sincos += (rn_fbits(s) != rn_fbits(rs)) + (rn_fbits(c) != rn_fbits(rc));
+        glibc_sincosf_uniform(x, &s, &c);
+        bad_sincos += (rn_fbits(s) != rn_fbits(rs)) + (rn_fbits(c) != rn_fbits(rc));
         bad_sin += rn_fbits(glibc_sinf(x)) != rn_fbits(sinf(x));
         bad_cos += rn_fbits(glibc_cosf(x)) != rn_fbits(cosf(x));
     }
