@@ -12,6 +12,7 @@
 // the identical offset.
 
 #include "ria_internal.h"
+#include "rn_math.h"
 
 #include <cmath>
 
@@ -169,9 +170,9 @@ ofdm_data_sync_kernel(const SyncArgs a) {
             res.start_sample = best_offset;
             // burst-interleave marker (:366-372)
             const float cfo_phase = static_cast<float>(2.0f * M_PI * static_cast<double>(known) * sym / static_cast<double>(a.sample_rate));
-            double s, c;
-            sincos(static_cast<double>(-cfo_phase), &s, &c);
-            const float re = __fsub_rn(__fmul_rn(best_p.x, static_cast<float>(c)), __fmul_rn(best_p.y, static_cast<float>(s)));
+            float s, c;
+            glibc_sincosf(-cfo_phase, &s, &c);                  // std::cos / std::sin of a float = glibc, restated
+            const float re = __fsub_rn(__fmul_rn(best_p.x, c), __fmul_rn(best_p.y, s));
             res.aux = (re < 0.0f) ? 1 : 0;
         }
         a.out[f] = res;

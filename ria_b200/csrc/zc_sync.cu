@@ -18,6 +18,7 @@
 //                        combining, CFO, best root
 
 #include "ria_internal.h"
+#include "rn_math.h"
 
 #include <cmath>
 
@@ -210,7 +211,7 @@ zc_finish_kernel(const FinishArgs a) {
                     const float2 x = aux_sum[2], y = aux_sum[1];                          // corr2 * conj(corr1)
                     const float re = __fsub_rn(__fmul_rn(x.x, y.x), __fmul_rn(x.y, -y.y));
                     const float im = __fadd_rn(__fmul_rn(x.x, -y.y), __fmul_rn(x.y, y.x));
-                    const float phase_diff = static_cast<float>(atan2(static_cast<double>(im), static_cast<double>(re)));
+                    const float phase_diff = glibc_atan2f(im, re);                        // std::arg (:351) = glibc atan2f, restated
                     const float rep_duration = static_cast<float>(R) / a.sample_rate;
                     best_cfo = static_cast<float>(static_cast<double>(phase_diff) / (2.0f * M_PI * static_cast<double>(rep_duration)));
                 }
