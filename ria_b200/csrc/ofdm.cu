@@ -668,6 +668,7 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
         const float fade_threshold = 0.25f * cs.s.avg_h_power;
         float2 e;
         float nvv;
+        float e_mag = -1.0f;          // |e|, evaluated at most once (DD gate here, |eq| EMA below)
         if (differential) {
             float snv = cs.s.noise_var;
             if (snv < 1e-6f) snv = cs.s.avg_h_power / 31.6f;
@@ -691,7 +692,8 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
                 if (mod == RIA_QAM16) { mag_thr = 0.25f; ph_thr = 0.44f; }
                 else if (mod == RIA_QAM32 || mod == RIA_QAM64) { mag_thr = 0.20f; ph_thr = 0.35f; }
                 float ddv = 0.0f;
-                if (!(cabs(e) < mag_thr)) {
+                e_mag = cabs(e);
+                if (!(e_mag < mag_thr)) {
                     const float2 dec = hard_decision(e, mod);
                     const float perr = carg(cmul(e, cconj(dec)));
                     if (fabsf(perr) < ph_thr) ddv = -perr;
@@ -703,7 +705,7 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
         // (same carrier, same thread: the equalised symbol and its noise variance stay in registers)
         const float2 sym = e;
         // per-carrier |eq| EMA / variance (:240-254)
-        const float mag = cabs(sym);
+        const float mag = (e_mag >= 0.0f) ? e_mag : cabs(sym);
         float ema, var;
         if (first) { ema = mag; var = 0.0f; }
         else {
@@ -1067,14 +1069,19 @@ struct FftSmem {
     short res_k[64];
 };
 
-template <bool PRUNED>
+// MODE 0: first pass, no CFO vector; 1: first pass with the CFO handed in; 2: second pass (listed
+// frames, corrected CFO).  Separate instances keep the rotation code and the list indirection out
+// of the plain transform (no spills at 64 registers).
+template <bool PRUNED, int MODE>
 __global__ void __launch_bounds__(kThreads, 8)
 ofdm_fft_kernel(const KernelArgs a) {
+    constexpr bool kSecond = (MODE == 2);
+    constexpr bool kCfo = (MODE != 0);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FftSmem& sm = *reinterpret_cast<FftSmem*>(smem_raw);
     __shared__ unsigned int item_sh;
     const int tid = threadIdx.x;
-    if (a.second_pass && *a.rerun_count == 0) return;          // the usual case: nothing to re-run
+    if (kSecond && *a.rerun_count == 0) return;               // the usual case: nothing to re-run
 
     for (int i = tid; i < kTwCount; i += kThreads) sm.tw[i] = a.tw_g[i];
     {
@@ -1096,7 +1103,7 @@ ofdm_fft_kernel(const KernelArgs a) {
 
     const int n_sym = a.frame_len / a.sym_len;
     // first pass: every frame of the chunk; second pass: the frames the carrier stage listed
-    const long long n_local = a.second_pass ? static_cast<long long>(*a.rerun_count) : a.frame_end - a.frame_begin;
+    const long long n_local = kSecond ? static_cast<long long>(*a.rerun_count) : a.frame_end - a.frame_begin;
     const unsigned n_groups = static_cast<unsigned>((n_local + kFftGroup - 1) / kFftGroup);
     const unsigned n_items = n_groups * static_cast<unsigned>(n_sym);
     int cur_sym = -1;
@@ -1118,7 +1125,7 @@ ofdm_fft_kernel(const KernelArgs a) {
         }
         const long long i0 = static_cast<long long>(grp) * kFftGroup;
         const long long i1 = (i0 + kFftGroup < n_local) ? i0 + kFftGroup : n_local;
-        auto frame_of = [&](long long i) -> long long { return a.frame_begin + (a.second_pass ? a.rerun_list[i] : i); };
+        auto frame_of = [&](long long i) -> long long { return a.frame_begin + (kSecond ? a.rerun_list[i] : i); };
 
         float nxt[8];
         {
@@ -1142,8 +1149,8 @@ ofdm_fft_kernel(const KernelArgs a) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) nxt[q] = __ldcs(p + 128 * q);
             }
-            if (a.cfo_hz || a.second_pass) {
-                const float cfo = a.second_pass ? a.rerun_cfo[f - a.frame_begin] : a.cfo_hz[f];
+            if (kCfo) {
+                const float cfo = kSecond ? a.rerun_cfo[f - a.frame_begin] : a.cfo_hz[f];
                 if (fabsf(cfo) > 0.01f) {
                     const float inc = cfo_phase_inc(cfo, a.sample_rate);
                     const float2* bp = a.block_phase + (f - a.frame_begin) * a.n_blocks;
@@ -1492,9 +1499,15 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
     }
 
     int fft_per_sm = 0, car_per_sm = 0;
-    if (a.pruned) rc = blocks_per_sm(ctx, ofdm_fft_kernel<true>, kThreads, sizeof(FftSmem), &fft_per_sm);
-    else          rc = blocks_per_sm(ctx, ofdm_fft_kernel<false>, kThreads, sizeof(FftSmem), &fft_per_sm);
-    if (rc != RIA_OK) return rc;
+    void (*fft_kernels[3])(const KernelArgs);
+    if (a.pruned) { fft_kernels[0] = ofdm_fft_kernel<true, 0>; fft_kernels[1] = ofdm_fft_kernel<true, 1>; fft_kernels[2] = ofdm_fft_kernel<true, 2>; }
+    else          { fft_kernels[0] = ofdm_fft_kernel<false, 0>; fft_kernels[1] = ofdm_fft_kernel<false, 1>; fft_kernels[2] = ofdm_fft_kernel<false, 2>; }
+    for (int m = 0; m < 3; ++m) {
+        int per = 0;
+        rc = blocks_per_sm(ctx, fft_kernels[m], kThreads, sizeof(FftSmem), &per);
+        if (rc != RIA_OK) return rc;
+        if (m == 0 || per < fft_per_sm) fft_per_sm = per;
+    }
     void (*carrier_kernel)(const KernelArgs) = nullptr;
     switch (cfg->modulation) {
         case RIA_DBPSK:  carrier_kernel = ofdm_carrier_kernel<RIA_DBPSK>; break;
@@ -1554,8 +1567,7 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
             }
             a.counter = ctr + (pass ? 3 : 0);
             time_begin(ctx, KK_OFDM_FFT);
-            if (a.pruned) ofdm_fft_kernel<true><<<static_cast<unsigned>(fft_grid), kThreads, sizeof(FftSmem), st>>>(a);
-            else          ofdm_fft_kernel<false><<<static_cast<unsigned>(fft_grid), kThreads, sizeof(FftSmem), st>>>(a);
+            fft_kernels[pass ? 2 : (cfo_hz_dev ? 1 : 0)]<<<static_cast<unsigned>(fft_grid), kThreads, sizeof(FftSmem), st>>>(a);
             time_end(ctx);
             a.counter = ctr + (pass ? 4 : 1);
             time_begin(ctx, KK_OFDM_CARRIER);
