@@ -154,6 +154,7 @@ def test_golden_fixtures(ctx):
             n = int(out["n_llr"][i])
             assert n == want.shape[1]
             assert llr_close(out["llr"][i, :n], want[i]).all()
+            assert np.array_equal(out["llr"][i, :n].view(np.uint32), want[i].astype(np.float32).view(np.uint32))
             assert abs(out["snr_db"][i] - g[f"{name}_snr"][i]) < 1e-3 * max(1, abs(g[f"{name}_snr"][i]))
             assert abs(out["cfo"][i] - g[f"{name}_cfo_out"][i]) < 1e-4 * max(1, abs(g[f"{name}_cfo_out"][i]))
 
