@@ -329,23 +329,30 @@ int ria::ldpc_launch(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor,
     if (rc != RIA_OK) return rc;
     if (info_stride < (t->k + 7) / 8) return set_error(ctx, RIA_E_INVAL, "ldpc: info_stride too small");
 
-    // warps (= codewords) per CTA: whatever keeps the most codewords resident per SM
+    // warps (= codewords) per CTA: whatever keeps the most codewords resident per SM (settled once per rate)
     auto kern = ldpc_decode_kernel;
-    int W = 0, best_warps = 0;
-    for (int w = 4; w <= kMaxWarpsPerCta; ++w) {
-        const size_t need = ldpc_smem_bytes(t->k, t->m, t->dv_max, w) + 1024;      // + per-CTA reservation
-        if (need > ctx->smem_optin + 1024) break;
-        const int ctas = static_cast<int>(ctx->smem_per_sm / need);
-        const int warps = ctas * w > 48 ? 48 : ctas * w;
-        if (warps > best_warps) { best_warps = warps; W = w; }
+    LdpcCodeDev* tm = &ctx->ldpc[rate];
+    if (tm->launch_warps == 0) {
+        int W = 0, best_warps = 0;
+        for (int w = 4; w <= kMaxWarpsPerCta; ++w) {
+            const size_t need = ldpc_smem_bytes(t->k, t->m, t->dv_max, w) + 1024;      // + per-CTA reservation
+            if (need > ctx->smem_optin + 1024) break;
+            const int ctas = static_cast<int>(ctx->smem_per_sm / need);
+            const int warps = ctas * w > 48 ? 48 : ctas * w;
+            if (warps > best_warps) { best_warps = warps; W = w; }
+        }
+        if (W == 0) return set_error(ctx, RIA_E_UNSUPPORTED, "ldpc: kernel does not fit in shared memory");
+        const size_t smem = ldpc_smem_bytes(t->k, t->m, t->dv_max, W);
+        // one attribute for all rates: the largest opt-in size
+        RIA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+        RIA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int ctas_per_sm = 0;
+        RIA_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, W * 32, smem));
+        if (ctas_per_sm < 1) return set_error(ctx, RIA_E_UNSUPPORTED, "ldpc: kernel does not fit (smem %zu)", smem);
+        tm->launch_warps = W; tm->launch_ctas_per_sm = ctas_per_sm; tm->launch_smem = smem;
     }
-    if (W == 0) return set_error(ctx, RIA_E_UNSUPPORTED, "ldpc: kernel does not fit in shared memory");
-    const size_t smem = ldpc_smem_bytes(t->k, t->m, t->dv_max, W);
-    RIA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    RIA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int ctas_per_sm = 0;
-    RIA_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, W * 32, smem));
-    if (ctas_per_sm < 1) return set_error(ctx, RIA_E_UNSUPPORTED, "ldpc: kernel does not fit (smem %zu)", smem);
+    const int W = tm->launch_warps, ctas_per_sm = tm->launch_ctas_per_sm;
+    const size_t smem = tm->launch_smem;
     long long want = (n_cw + W - 1) / W;
     long long grid = static_cast<long long>(ctx->sm_count) * ctas_per_sm;
     if (grid > want) grid = want;

@@ -1393,10 +1393,14 @@ int ensure_ofdm_scratch(ria_ctx* ctx, size_t bytes) {
 
 template <typename K>
 int blocks_per_sm(ria_ctx* ctx, K kernel, int threads, size_t smem, int* out) {
+    const void* key = reinterpret_cast<const void*>(kernel);
+    auto hit = ctx->occ_cache.find(key);
+    if (hit != ctx->occ_cache.end()) { *out = hit->second; return RIA_OK; }
     RIA_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     RIA_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     RIA_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kernel, threads, smem));
     if (*out < 1) return set_error(ctx, RIA_E_UNSUPPORTED, "ofdm: kernel does not fit on this device");
+    ctx->occ_cache[key] = *out;
     return RIA_OK;
 }
 

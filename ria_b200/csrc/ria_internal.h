@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "ria_b200.h"
@@ -42,6 +43,8 @@ struct LdpcCodeDev {
     int k = 0, m = 0, dv_max = 0;
     uint16_t* chk_var = nullptr;
     uint16_t* var_slot = nullptr;
+    int launch_warps = 0, launch_ctas_per_sm = 0;     // launch shape, settled on first use
+    size_t launch_smem = 0;
 };
 
 }  // namespace ria
@@ -69,6 +72,7 @@ struct ria_ctx {
     // scratch owned by the context for the fused chain entry points
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    std::unordered_map<const void*, int> occ_cache;   // kernel -> resident CTAs per SM (attributes set once)
     void* chain_scratch = nullptr;          // buffers between the stages of the MC-DPSK chain
     size_t chain_scratch_bytes = 0;
     void* ofdm_scratch = nullptr;           // carrier bins / CFO phases between the OFDM stages
