@@ -637,6 +637,17 @@ def cpu_baseline_ldpc(wl, per_rate_per_core):
                       f"({cores * per_core_cw} codewords), {wall:.1f} s wall, {max(busy):.1f} s max busy"}
 
 
+def measured_traffic(workload, kernel_name, frames_per_launch):
+    """DRAM bytes per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum from the
+    committed ncu --set full capture (profiles/r1_traffic.json, bytes per frame) x frames per launch."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)
+        return t[workload][kernel_name]["dram_bytes_per_frame"] * frames_per_launch
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def make_workload(args):
     if args.workload == "mcdpsk":
         return McdpskC3Workload(args.batch or 100_000), cpu_baseline_mcdpsk, args.cpu_sample or 16
@@ -773,6 +784,7 @@ def main():
         kern_s = dom_ms / max(1, dom_n) * 1e-3
         bytes_per_launch = dom_bytes_step * args.steps / max(1, dom_n)
         achieved = bytes_per_launch / kern_s / 1e9
+        traffic = measured_traffic(args.workload, dom_name, wl.units_per_step() * args.steps / max(1, dom_n))
         step_ms_local = ms / args.steps
         line = {
             "metric": wl.metric, "value": value, "unit": wl.unit,
@@ -782,7 +794,10 @@ def main():
             "rx_msamples_per_s": wl.samples_per_step() * world / (ms_per_step * 1e-3) / 1e6,
             "counters": wl.counter_dict(cnt.cpu().numpy()),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": ("profiles/r1_traffic.json: dram bytes per frame of this kernel from one "
+                                            "ncu --set full capture x frames per launch" if traffic else None),
+                         "peak_source": peak_src,
                          "kernel": dom_name, "kernel_ms_per_launch": kern_s * 1e3,
                          "launches_per_step": dom_n / args.steps,
                          "algorithmic_bytes_per_launch": bytes_per_launch,

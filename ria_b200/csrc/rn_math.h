@@ -300,3 +300,41 @@ RN_HD float glibc_cosf(float y) {
     rn_sincos_d(x, &sd, &cd);
     return static_cast<float>(cd);
 }
+
+// ------------------------------------------------------------------------------------------
+// logf (ARM optimized-routines, glibc sysdeps/ieee754/flt-32/e_logf.c + e_logf_data.c)
+// ------------------------------------------------------------------------------------------
+// libstdc++'s std::normal_distribution<float> (Marsaglia polar) calls std::log(float) == logf;
+// the LDPC retry ladder of v2::decodeFixedFrame perturbs soft bits with it
+// (src/protocol/frame_v2.cpp:1389-1546), so the perturbation is only reproducible with glibc's
+// logf.  The table and polynomial below are __logf_data of the container's libm (2.39), read out
+// of the binary; the restatement matches libm on every normal float in (0, 1] -- the only
+// arguments the polar method produces -- with or without FMA contraction (tests/rn_math_check.cpp).
+// Only positive normal arguments are handled (r2 in (0, 1]); others return NaN.
+RN_HD float glibc_logf(float x) {
+    static const double tab[32] = {
+        0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2, 0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2,
+        0x1.49539f0f010b0p+0, -0x1.01eae7f513a67p-2, 0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3,
+        0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3, 0x1.25e227b0b8ea0p+0, -0x1.1aa2bc79c8100p-3,
+        0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4, 0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4,
+        0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5, 0x1.0000000000000p+0, 0x0.0p+0,
+        0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5,  0x1.ca4b31f026aa0p-1, 0x1.c5e53aa362eb4p-4,
+        0x1.b2036576afce6p-1, 0x1.526e57720db08p-3,  0x1.9c2d163a1aa2dp-1, 0x1.bc2860d224770p-3,
+        0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2,  0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2};
+    const uint32_t ix = rn_fbits(x);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) return rn_ffrom(0x7fc00000u);
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = static_cast<int>((tmp >> 19) & 15u);
+    const int k = static_cast<int32_t>(tmp) >> 23;
+    const uint32_t iz = ix - (tmp & (0x1ffu << 23));
+    const double invc = tab[2 * i], logc = tab[2 * i + 1];
+    const double z = static_cast<double>(rn_ffrom(iz));
+    const double r = fma(z, invc, -1.0);
+    const double y0 = fma(static_cast<double>(k), 0x1.62e42fefa39efp-1, logc);
+    const double r2 = r * r;
+    double y = fma(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
+    y = fma(-0x1.00ea348b88334p-2, r2, y);
+    y = fma(y, r2, y0 + r);
+    return static_cast<float>(y);
+}

@@ -60,7 +60,13 @@ int main(int argc, char** argv) {
             ++special_bad; fprintf(stderr, "sincos(%g)\n", x);
         }
     }
-    printf("n %ld bad_sin %ld bad_cos %ld bad_sincos %ld bad_atan2 %ld bad_large %ld special_bad %d\n",
-           n, bad_sin, bad_cos, bad_sincos, bad_atan2, bad_large, special_bad);
+    // logf on (0, 1]: every 61st normal float plus the neighbourhood of 1 (the polar method's r2)
+    long bad_log = 0;
+    for (uint32_t u = 0x00800000u; u <= 0x3f800000u; u += (u > 0x3f7f0000u ? 1u : 61u)) {
+        const float x = rn_ffrom(u);
+        bad_log += rn_fbits(glibc_logf(x)) != rn_fbits(logf(x));
+    }
+    printf("n %ld bad_sin %ld bad_cos %ld bad_sincos %ld bad_atan2 %ld bad_large %ld special_bad %d bad_log %ld\n",
+           n, bad_sin, bad_cos, bad_sincos, bad_atan2, bad_large, special_bad, bad_log);
     return 0;
 }

@@ -14,5 +14,5 @@ def test_restated_glibc_functions_match_libm_bitwise(tmp_path):
     out = subprocess.run([str(exe), "3000000"], check=True, capture_output=True, text=True).stdout.split()
     res = {out[i]: int(out[i + 1]) for i in range(0, len(out), 2)}
     assert res["n"] == 3000000
-    for k in ("bad_sin", "bad_cos", "bad_sincos", "bad_atan2", "bad_large", "special_bad"):
+    for k in ("bad_sin", "bad_cos", "bad_sincos", "bad_atan2", "bad_large", "special_bad", "bad_log"):
         assert res[k] == 0, res
