@@ -60,8 +60,20 @@ const char* ria_version(void);
 /* Per-kernel timing for bench.py: when enabled, every kernel launch is bracketed by CUDA events on
  * the context stream; get_timing sums the elapsed time of all launches of one kind since enable.
  * kinds: 0 LDPC, 1 OFDM demod, 2 frame status/CRC, 3 AWGN channel, 4 MC-DPSK demod, 5 ZC sync,
- * 6 chirp sync, 7 chase combine, 8 Watterson channel, 9 MC-DPSK CFO correction, 10 OFDM data sync. */
+ * 6 chirp sync, 7 chase combine, 8 Watterson channel, 9 MC-DPSK CFO correction, 10 OFDM data sync,
+ * 11 OFDM FFT stage, 12 OFDM carrier stage, 13 OFDM CFO phase scan, 14 LDPC retry ladder. */
 int  ria_ctx_set_timing(ria_ctx* ctx, int enable);
+/* Decode options of the frame entry points (ria_frame_decode_batch_dev, ria_ofdm_rx_frames_dev/_host):
+ *   RIA_DECODE_RETRY_LADDER  run the LDPC retry ladder of v2::decodeFixedFrame
+ *                            (src/protocol/frame_v2.cpp:1389-1546: 4 min-sum factors, then 34 seeded
+ *                            soft-bit perturbations) on every codeword whose first decode failed,
+ *                            including the reference's carry-over of the decoder's min-sum factor to
+ *                            the following codewords of the frame.
+ * Default 0 = first pass only (:1335-1385).  The CRC-guided false-positive repair (:1558-1916) is
+ * not part of either mode (second half). */
+#define RIA_DECODE_RETRY_LADDER 1
+int  ria_ctx_set_decode_flags(ria_ctx* ctx, int flags);
+int  ria_ctx_get_decode_flags(const ria_ctx* ctx);
 int  ria_ctx_get_timing(ria_ctx* ctx, int kind, double* total_ms, int64_t* launches);
 /* number of kernels this library has launched on the context since creation */
 int64_t ria_ctx_launch_count(const ria_ctx* ctx);
@@ -94,6 +106,21 @@ int ria_ldpc_decode_batch_dev(ria_ctx* ctx, int rate, int max_iter, float min_su
 int ria_ldpc_decode_batch_host(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor,
                                const float* llr, int64_t n_cw,
                                uint8_t* info, int info_stride, uint8_t* ok, int32_t* iters);
+
+/* Batched robustDecodeSingleCW (src/gui/modem/streaming_decoder.cpp:1028-1058): decodeSoft with
+ * factor 0.9375 and LDPCCodec::getRecommendedIterations(rate); codewords that fail are retried with
+ * the min-sum factors 0.875, 0.75, 0.625, 0.5 in that order (first success wins).
+ *   attempt_dev  optional [n_cw]: 0 = first decode succeeded, 1..4 = retry that succeeded, 255 = all failed
+ *   iters_dev    iterations of the decode that produced the result (first decode when all failed) */
+int ria_ldpc_robust_decode_batch_dev(ria_ctx* ctx, int rate, const float* llr_dev, int64_t n_cw,
+                                     uint8_t* info_dev, int info_stride,
+                                     uint8_t* ok_dev, int32_t* iters_dev, uint8_t* attempt_dev);
+
+/* The soft bits that attempt `attempt` (1..38) of the decodeFixedFrame retry ladder hands to the
+ * decoder (src/protocol/frame_v2.cpp:1409-1542): attempts 1-4 the soft bits themselves, 5-38 the
+ * clipped / scaled / hard-limited soft bits plus std::normal_distribution<float> noise drawn from
+ * std::mt19937(hash(first 16 soft bits) + f(attempt)).  llr_dev / out_dev: [n_cw][648]. */
+int ria_ldpc_ladder_perturb_dev(ria_ctx* ctx, const float* llr_dev, int64_t n_cw, int attempt, float* out_dev);
 
 
 /* ---- OFDM presynced receive chain ---------------------------------------------------------- */
@@ -175,7 +202,9 @@ typedef struct {
     uint32_t src_hash;
     uint32_t dst_hash;
     uint8_t  total_cw;
-    uint8_t  pad[3];
+    uint8_t  ladder_cw_mask;     /* bit c: codeword c failed its first decode and the retry ladder recovered it */
+    uint8_t  ladder_max_attempt; /* highest ladder attempt (1..38, frame_v2.cpp:1409-1542) a recovered codeword needed */
+    uint8_t  pad[1];
 } ria_frame_status;
 
 /* Batched first pass of v2::decodeFixedFrame (src/protocol/frame_v2.cpp:1335-1385, 1548-1556):
@@ -183,8 +212,8 @@ typedef struct {
  * ChannelInterleaver::deinterleave (src/fec/ldpc_decoder.cpp:552-625) with
  * bits_per_symbol, 4 x LDPCDecoder::decodeSoft(factor 0.9375, getRecommendedIterations(rate)),
  * take bytes_per_cw bytes per codeword, then v2::parseHeader + frame CRC
- * (src/protocol/frame_v2.cpp:115-128, 1195-1253, 555-600).  The retry ladder (:1389-1546) is
- * NOT run.
+ * (src/protocol/frame_v2.cpp:115-128, 1195-1253, 555-600).  The retry ladder (:1389-1546) runs when
+ * the context has RIA_DECODE_RETRY_LADDER set (ria_ctx_set_decode_flags).
  *   soft_dev   [n][soft_stride] >= 2592 soft bits per frame (soft_stride >= 2592)
  *   data_dev   [n][4*bytes_per_cw] reassembled info bytes (codewords that failed are zeros)
  *   status_dev [n] */

@@ -114,7 +114,8 @@ class FrameStatus(C.Structure):
     _fields_ = [("cw_ok", C.c_uint8 * 4), ("cw_iters", C.c_int32 * 4), ("all_ok", C.c_uint8),
                 ("header_valid", C.c_uint8), ("frame_crc_ok", C.c_uint8), ("type", C.c_uint8),
                 ("seq", C.c_uint16), ("payload_len", C.c_uint16), ("src_hash", C.c_uint32),
-                ("dst_hash", C.c_uint32), ("total_cw", C.c_uint8), ("pad", C.c_uint8 * 3)]
+                ("dst_hash", C.c_uint32), ("total_cw", C.c_uint8), ("ladder_cw_mask", C.c_uint8),
+                ("ladder_max_attempt", C.c_uint8), ("pad", C.c_uint8 * 1)]
 
 
 # ultra::Modulation (include/ultra/types.hpp:27-39)
@@ -213,6 +214,7 @@ class Ref:
         L.ref_encode_fixed_frame.restype = C.c_int
         L.ref_frame_decode_first_pass.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _u8p, _u8p, _i32p]
         L.ref_decode_fixed_frame_full.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _u8p]
+        L.ref_ladder_perturb.argtypes = [_f32p, C.c_int, C.c_uint, C.c_float, C.c_int, _f32p]
         L.ref_parse_header.argtypes = [_u8p, C.c_int, C.POINTER(FrameStatus)]
         L.ref_crc16.argtypes = [_u8p, C.c_int]
         L.ref_crc16.restype = C.c_uint16
@@ -417,6 +419,13 @@ class Ref:
         ok = np.zeros(4, np.uint8)
         self.lib.ref_decode_fixed_frame_full(soft, soft.size, rate, int(use_ci), bps, data, ok)
         return data, ok
+
+    def ladder_perturb(self, llr, seed: int, sigma: float, kind: int) -> np.ndarray:
+        """std::mt19937(seed) + std::normal_distribution<float>(0, sigma) perturbation (frame_v2.cpp:1426-1542)."""
+        llr = np.ascontiguousarray(llr, dtype=np.float32)
+        out = np.empty_like(llr)
+        self.lib.ref_ladder_perturb(llr, llr.size, seed & 0xFFFFFFFF, sigma, kind, out)
+        return out
 
     def parse_header(self, data) -> FrameStatus:
         data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))

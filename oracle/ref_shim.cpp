@@ -31,6 +31,7 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <random>
 #include <vector>
 
 using namespace ultra;
@@ -248,6 +249,28 @@ void ref_decode_fixed_frame_full(const float* soft, int n_soft, int rate, int us
         ok[c] = st.decoded[c] ? 1 : 0;
         std::memset(data + c * bpc, 0, bpc);
         if (st.decoded[c] && st.data[c].size() >= bpc) std::memcpy(data + c * bpc, st.data[c].data(), bpc);
+    }
+}
+
+// The soft-bit perturbation of one retry-ladder attempt, stated with the SAME library objects the
+// reference uses (std::mt19937 + std::normal_distribution<float> of this libstdc++; the ladder itself
+// is inline in decodeFixedFrame, frame_v2.cpp:1389-1546, and cannot be called separately).  Test
+// helper for ria_ldpc_ladder_perturb_dev; the end-to-end check is ref_decode_fixed_frame_full.
+//   kind: 1 add, 2 clip 10, 3 scale 0.5, 4 clip 6, 5 hard, 6 scale 0.25
+void ref_ladder_perturb(const float* in, int n, unsigned seed, float sigma, int kind, float* out) {
+    std::mt19937 rng(seed);
+    std::normal_distribution<float> noise(0.0f, sigma);
+    for (int i = 0; i < n; ++i) {
+        float llr = in[i];
+        switch (kind) {
+            case 2: llr = std::max(-10.0f, std::min(10.0f, llr)); llr += noise(rng); break;
+            case 3: llr = llr * 0.5f + noise(rng); break;
+            case 4: llr = std::max(-6.0f, std::min(6.0f, llr)); llr += noise(rng); break;
+            case 5: llr = (llr >= 0) ? 1.0f : -1.0f; llr += noise(rng); break;
+            case 6: llr = llr * 0.25f + noise(rng); break;
+            default: llr += noise(rng); break;
+        }
+        out[i] = llr;
     }
 }
 

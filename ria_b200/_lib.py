@@ -13,6 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libria_b200.so")
 
 
+DECODE_RETRY_LADDER = 1        # RIA_DECODE_RETRY_LADDER (include/ria_b200.h)
+
+
 class RiaError(RuntimeError):
     pass
 
@@ -31,11 +34,15 @@ _SIGNATURES = {
     "ria_last_error": (C.c_char_p, [_vp]),
     "ria_ctx_launch_count": (_i64, [_vp]),
     "ria_ctx_set_timing": (_i32, [_vp, _i32]),
+    "ria_ctx_set_decode_flags": (_i32, [_vp, _i32]),
+    "ria_ctx_get_decode_flags": (_i32, [_vp]),
     "ria_ctx_get_timing": (_i32, [_vp, _i32, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "ria_ldpc_params": (_i32, [_i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "ria_ldpc_get_matrix": (_i32, [_i32, _vp, _vp]),
     "ria_ldpc_decode_batch_dev": (_i32, [_vp, _i32, _i32, _f32, _vp, _i64, _vp, _i32, _vp, _vp]),
     "ria_ldpc_decode_batch_host": (_i32, [_vp, _i32, _i32, _f32, _vp, _i64, _vp, _i32, _vp, _vp]),
+    "ria_ldpc_robust_decode_batch_dev": (_i32, [_vp, _i32, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
+    "ria_ldpc_ladder_perturb_dev": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "ria_modem_config_for": (_i32, [_i32, _i32, _vp]),
     "ria_ofdm_symbol_samples": (_i32, [_vp]),
     "ria_ofdm_data_carriers": (_i32, [_vp]),
@@ -122,6 +129,13 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self._L.ria_ctx_launch_count(self.handle))
+
+    def set_decode_flags(self, flags: int) -> None:
+        """RIA_DECODE_RETRY_LADDER (1): frame entry points run v2::decodeFixedFrame's retry ladder."""
+        self.check(self._L.ria_ctx_set_decode_flags(self.handle, int(flags)))
+
+    def get_decode_flags(self) -> int:
+        return int(self._L.ria_ctx_get_decode_flags(self.handle))
 
     def set_timing(self, enable: bool) -> None:
         self.check(self._L.ria_ctx_set_timing(self.handle, int(enable)))

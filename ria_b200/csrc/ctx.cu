@@ -147,6 +147,15 @@ extern "C" int ria_ctx_synchronize(ria_ctx* ctx) {
     return RIA_OK;
 }
 
+extern "C" int ria_ctx_set_decode_flags(ria_ctx* ctx, int flags) {
+    if (!ctx) return RIA_E_INVAL;
+    if (flags & ~RIA_DECODE_RETRY_LADDER) return ria::set_error(ctx, RIA_E_INVAL, "ctx: unknown decode flags 0x%x", flags);
+    ctx->decode_flags = flags;
+    return RIA_OK;
+}
+
+extern "C" int ria_ctx_get_decode_flags(const ria_ctx* ctx) { return ctx ? ctx->decode_flags : 0; }
+
 extern "C" int ria_ctx_set_timing(ria_ctx* ctx, int enable) {
     if (!ctx) return RIA_E_INVAL;
     for (auto& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }

@@ -14,17 +14,15 @@
 
 namespace ria {
 
-int ldpc_launch(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor, const float* llr_dev, int64_t n_cw,
-                int frame_mode, int soft_stride, int step,
-                uint8_t* info_dev, int info_stride, uint8_t* ok_dev, int32_t* iters_dev);
-
 namespace {
 
 constexpr int kFrameBits = 4 * RIA_LDPC_N;     // FrameInterleaver::TOTAL_FRAME_BITS = 2592
 constexpr int kInfoStride = 72;                // per-codeword info bytes in the scratch buffer
 
+}  // namespace
+
 // LDPCCodec::getRecommendedIterations, src/fec/ldpc_codec.hpp:86-96
-int recommended_iterations(int rate) {
+int recommended_ldpc_iterations(int rate) {
     switch (rate) {
         case RIA_R3_4: return 60;
         case RIA_R2_3: return 70;
@@ -34,6 +32,9 @@ int recommended_iterations(int rate) {
         default: return 50;
     }
 }
+
+namespace {
+int recommended_iterations(int rate) { return recommended_ldpc_iterations(rate); }
 
 __device__ __forceinline__ uint16_t crc16_dev(const uint8_t* d, int len) {
     uint16_t crc = 0xFFFF;
@@ -53,7 +54,8 @@ __device__ __forceinline__ bool is_control_frame(uint8_t t) {
 // One thread per frame: reassemble the 4 x bytes_per_cw info bytes (failed codewords stay zero,
 // CodewordStatus::data is only filled on success), parse the header and check the CRCs.
 __global__ void frame_status_kernel(const uint8_t* __restrict__ info, const uint8_t* __restrict__ ok,
-                                    const int32_t* __restrict__ iters, long long n_frames, int bpc,
+                                    const int32_t* __restrict__ iters, const uint8_t* __restrict__ attempt,
+                                    long long n_frames, int bpc,
                                     uint8_t* __restrict__ data, ria_frame_status* __restrict__ status) {
     const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (f >= n_frames) return;
@@ -66,6 +68,10 @@ __global__ void frame_status_kernel(const uint8_t* __restrict__ info, const uint
         st.cw_ok[c] = ok[cw];
         st.cw_iters[c] = iters[cw];
         all = all && ok[cw];
+        if (attempt && ok[cw] && attempt[cw] >= 1 && attempt[cw] <= 38) {
+            st.ladder_cw_mask |= static_cast<uint8_t>(1u << c);
+            if (attempt[cw] > st.ladder_max_attempt) st.ladder_max_attempt = attempt[cw];
+        }
         for (int b = 0; b < bpc; ++b) out[c * bpc + b] = ok[cw] ? info[cw * kInfoStride + b] : 0;
     }
     st.all_ok = all ? 1 : 0;
@@ -112,6 +118,7 @@ int bytes_per_codeword(int rate) {
 // scratch layout for n frames: info [4n][64] | ok [4n] | iters [4n] (+ llr [n][llr_stride] for the chain)
 struct Scratch {
     uint8_t* info; uint8_t* ok; int32_t* iters; float* llr; int32_t* n_llr;
+    uint8_t* attempt; int* fail_list;           // retry ladder only
 };
 
 int carve_scratch(ria_ctx* ctx, int64_t n_frames, int llr_stride, Scratch& s) {
@@ -123,11 +130,16 @@ int carve_scratch(ria_ctx* ctx, int64_t n_frames, int llr_stride, Scratch& s) {
     const size_t o_it = take(n_cw * 4);
     const size_t o_llr = take(static_cast<size_t>(n_frames) * llr_stride * 4);
     const size_t o_nl = take(static_cast<size_t>(n_frames) * 4);
+    const bool ladder = (ctx->decode_flags & RIA_DECODE_RETRY_LADDER) != 0;
+    const size_t o_at = take(ladder ? n_cw : 0);
+    const size_t o_fl = take(ladder ? static_cast<size_t>(n_frames) * 4 : 0);
     int rc = ensure_scratch(ctx, off);
     if (rc != RIA_OK) return rc;
     unsigned char* b = static_cast<unsigned char*>(ctx->scratch);
     s.info = b + o_info; s.ok = b + o_ok; s.iters = reinterpret_cast<int32_t*>(b + o_it);
     s.llr = reinterpret_cast<float*>(b + o_llr); s.n_llr = reinterpret_cast<int32_t*>(b + o_nl);
+    s.attempt = ladder ? b + o_at : nullptr;
+    s.fail_list = ladder ? reinterpret_cast<int*>(b + o_fl) : nullptr;
     return RIA_OK;
 }
 
@@ -144,10 +156,16 @@ int frame_decode_impl(ria_ctx* ctx, int rate, int use_ci, int bits_per_symbol, c
     int rc = ldpc_launch(ctx, rate, recommended_iterations(rate), 0.9375f, soft_dev, n_frames * 4,
                          1, soft_stride, step, s.info, kInfoStride, s.ok, s.iters);
     if (rc != RIA_OK) return rc;
+    if (s.fail_list) {
+        // retry ladder (frame_v2.cpp:1389-1546) on the frames with a failed codeword
+        rc = ldpc_retry_launch(ctx, rate, recommended_iterations(rate), soft_dev, n_frames, 1, soft_stride, step,
+                               s.info, kInfoStride, s.ok, s.iters, s.attempt, s.fail_list);
+        if (rc != RIA_OK) return rc;
+    }
     const int threads = 128;
     const unsigned blocks = static_cast<unsigned>((n_frames + threads - 1) / threads);
     time_begin(ctx, KK_FRAME_STATUS);
-    frame_status_kernel<<<blocks, threads, 0, ctx->stream>>>(s.info, s.ok, s.iters, n_frames, bpc, data_dev, status_dev);
+    frame_status_kernel<<<blocks, threads, 0, ctx->stream>>>(s.info, s.ok, s.iters, s.attempt, n_frames, bpc, data_dev, status_dev);
     time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

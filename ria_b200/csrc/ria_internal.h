@@ -62,6 +62,7 @@ struct ria_ctx {
     cudaStream_t copy_stream = nullptr; // H2D/D2H staging for *_host entry points
     std::string last_error;
     int64_t launches = 0;
+    int decode_flags = 0;                   // RIA_DECODE_* (ria_ctx_set_decode_flags)
     ria::LdpcCodeDev ldpc[8];
     unsigned int* work_counter = nullptr;   // device, dynamic tile schedulers (one slot per kernel)
     std::vector<ria::OfdmTablesDev*> ofdm_tables;
@@ -100,11 +101,19 @@ void mcdpsk_tables_free(McdpskTablesDev* t);
 void zc_tables_free(ZcTablesDev* t);
 void chirp_tables_free(ChirpTablesDev* t);
 int ensure_scratch(ria_ctx* ctx, size_t bytes);
+int recommended_ldpc_iterations(int rate);          // LDPCCodec::getRecommendedIterations (frame.cu)
+// ldpc.cu / ldpc_retry.cu
+int ldpc_launch(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor, const float* llr_dev, int64_t n_cw,
+                int frame_mode, int soft_stride, int step,
+                uint8_t* info_dev, int info_stride, uint8_t* ok_dev, int32_t* iters_dev);
+int ldpc_retry_launch(ria_ctx* ctx, int rate, int max_iter, const float* llr_dev, int64_t n_units, int frame_mode,
+                      int soft_stride, int step, uint8_t* info_dev, int info_stride, uint8_t* ok_dev,
+                      int32_t* iters_dev, uint8_t* attempt_dev, int* list_scratch);
 
 // kernel kinds for the timing hook / launch accounting
 enum KernelKind { KK_LDPC = 0, KK_OFDM_DEMOD = 1, KK_FRAME_STATUS = 2, KK_AWGN = 3, KK_MCDPSK = 4,
                   KK_ZC_SYNC = 5, KK_CHIRP_SYNC = 6, KK_CHASE = 7, KK_WATTERSON = 8, KK_MCDPSK_CFO = 9, KK_OFDM_SYNC = 10,
-                  KK_OFDM_FFT = 11, KK_OFDM_CARRIER = 12, KK_OFDM_PHASE = 13, KK_COUNT = 16 };
+                  KK_OFDM_FFT = 11, KK_OFDM_CARRIER = 12, KK_OFDM_PHASE = 13, KK_LDPC_RETRY = 14, KK_COUNT = 16 };
 void time_begin(ria_ctx* ctx, int kind);
 void time_end(ria_ctx* ctx);
 

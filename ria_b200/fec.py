@@ -123,6 +123,29 @@ class LDPCDecoder:
             info.data_ptr(), stride, ok.data_ptr(), iters.data_ptr()))
         return info, ok, iters
 
+    def robust_decode_batch(self, llr: torch.Tensor, info_stride: Optional[int] = None):
+        """Batched robustDecodeSingleCW (src/gui/modem/streaming_decoder.cpp:1028-1058): factor 0.9375 and
+        the recommended iterations, then the factors 0.875/0.75/0.625/0.5 on the codewords that failed.
+        -> (info, ok, iters, attempt); attempt 0 = first decode, 1..4 = retry, 255 = all failed."""
+        if not (isinstance(llr, torch.Tensor) and llr.is_cuda):
+            raise RiaError("robust_decode_batch wants a CUDA tensor (no CPU fallback)")
+        if llr.dtype != torch.float32 or llr.dim() != 2 or llr.shape[1] != LDPC_N:
+            raise ValueError("llr must be fp32 [n_cw, 648]")
+        llr = llr.contiguous()
+        k, _, _ = code_params(self._rate)
+        stride = int(info_stride) if info_stride else (k + 7) // 8
+        n = llr.shape[0]
+        info = torch.empty((n, stride), dtype=torch.uint8, device=llr.device)
+        ok = torch.empty((n,), dtype=torch.uint8, device=llr.device)
+        iters = torch.empty((n,), dtype=torch.int32, device=llr.device)
+        attempt = torch.empty((n,), dtype=torch.uint8, device=llr.device)
+        ctx = self.ctx
+        ctx.set_stream(torch.cuda.current_stream(llr.device))
+        ctx.check(lib().ria_ldpc_robust_decode_batch_dev(
+            ctx.handle, self._rate, llr.data_ptr(), n, info.data_ptr(), stride, ok.data_ptr(), iters.data_ptr(),
+            attempt.data_ptr()))
+        return info, ok, iters, attempt
+
     def decode_batch_host(self, llr: np.ndarray, info_stride: Optional[int] = None):
         """Host buffers in, host buffers out (H2D/D2H inside the C call)."""
         llr = np.ascontiguousarray(llr, dtype=np.float32).reshape(-1, LDPC_N)
@@ -167,6 +190,20 @@ class LDPCDecoder:
         """Hard-bit entry (ldpc_decoder.cpp:268-282): bit -> -6/+6 LLR."""
         bits = np.unpackbits(np.frombuffer(bytes(coded), dtype=np.uint8))
         return self.decodeSoft(np.where(bits == 1, -6.0, 6.0).astype(np.float32))
+
+
+def ladder_perturb_batch(llr: torch.Tensor, attempt: int, ctx: Optional[Context] = None) -> torch.Tensor:
+    """Soft bits that attempt `attempt` (1..38) of decodeFixedFrame's retry ladder decodes
+    (src/protocol/frame_v2.cpp:1409-1542).  llr: CUDA fp32 [n_cw, 648]."""
+    if not (isinstance(llr, torch.Tensor) and llr.is_cuda and llr.dtype == torch.float32 and llr.dim() == 2
+            and llr.shape[1] == LDPC_N):
+        raise ValueError("llr must be a CUDA fp32 [n_cw, 648] tensor")
+    llr = llr.contiguous()
+    out = torch.empty_like(llr)
+    ctx = ctx or default_context()
+    ctx.set_stream(torch.cuda.current_stream(llr.device))
+    ctx.check(lib().ria_ldpc_ladder_perturb_dev(ctx.handle, llr.data_ptr(), llr.shape[0], int(attempt), out.data_ptr()))
+    return out
 
 
 @dataclass

@@ -21,7 +21,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from ._lib import Context, RiaError, lib
+from ._lib import Context, RiaError, lib, DECODE_RETRY_LADDER
 from .fec import code_params, default_context
 
 # ultra::Modulation (include/ultra/types.hpp:27-39)
@@ -76,13 +76,15 @@ class FrameStatus(C.Structure):
     _fields_ = [("cw_ok", C.c_uint8 * 4), ("cw_iters", C.c_int32 * 4), ("all_ok", C.c_uint8),
                 ("header_valid", C.c_uint8), ("frame_crc_ok", C.c_uint8), ("type", C.c_uint8),
                 ("seq", C.c_uint16), ("payload_len", C.c_uint16), ("src_hash", C.c_uint32),
-                ("dst_hash", C.c_uint32), ("total_cw", C.c_uint8), ("pad", C.c_uint8 * 3)]
+                ("dst_hash", C.c_uint32), ("total_cw", C.c_uint8), ("ladder_cw_mask", C.c_uint8),
+                ("ladder_max_attempt", C.c_uint8), ("pad", C.c_uint8 * 1)]
 
 
 FRAME_STATUS_DTYPE = np.dtype([
     ("cw_ok", np.uint8, 4), ("cw_iters", np.int32, 4), ("all_ok", np.uint8), ("header_valid", np.uint8),
     ("frame_crc_ok", np.uint8), ("type", np.uint8), ("seq", np.uint16), ("payload_len", np.uint16),
-    ("src_hash", np.uint32), ("dst_hash", np.uint32), ("total_cw", np.uint8), ("pad", np.uint8, 3)],
+    ("src_hash", np.uint32), ("dst_hash", np.uint32), ("total_cw", np.uint8), ("ladder_cw_mask", np.uint8),
+    ("ladder_max_attempt", np.uint8), ("pad", np.uint8, 1)],
     align=True)
 assert FRAME_STATUS_DTYPE.itemsize == C.sizeof(FrameStatus)
 
@@ -162,8 +164,10 @@ class OFDMDemodulator:
 
 
 def decode_fixed_frame_batch(soft: torch.Tensor, rate: int, use_channel_interleave: bool,
-                             bits_per_symbol: int, ctx: Optional[Context] = None):
-    """First pass of v2::decodeFixedFrame for a batch: soft CUDA fp32 [n, >=2592].
+                             bits_per_symbol: int, ctx: Optional[Context] = None, retry_ladder: Optional[bool] = None):
+    """v2::decodeFixedFrame for a batch: soft CUDA fp32 [n, >=2592].  First pass only, or with the
+    LDPC retry ladder (frame_v2.cpp:1389-1546) when retry_ladder is True (None: the context's
+    decode flags decide).
 
     Returns (data u8 [n, 4*bytes_per_cw], status structured array on the device as uint8 tensor
     viewable with FRAME_STATUS_DTYPE after .cpu().numpy())."""
@@ -177,9 +181,15 @@ def decode_fixed_frame_batch(soft: torch.Tensor, rate: int, use_channel_interlea
     data = torch.empty((n, 4 * bpc), dtype=torch.uint8, device=soft.device)
     status = torch.empty((n, FRAME_STATUS_DTYPE.itemsize), dtype=torch.uint8, device=soft.device)
     ctx.set_stream(torch.cuda.current_stream(soft.device))
-    ctx.check(lib().ria_frame_decode_batch_dev(
-        ctx.handle, int(rate), int(bool(use_channel_interleave)), int(bits_per_symbol),
-        _ptr(soft), soft.stride(0), n, _ptr(data), _ptr(status)))
+    saved = ctx.get_decode_flags()
+    if retry_ladder is not None:
+        ctx.set_decode_flags((saved | DECODE_RETRY_LADDER) if retry_ladder else (saved & ~DECODE_RETRY_LADDER))
+    try:
+        ctx.check(lib().ria_frame_decode_batch_dev(
+            ctx.handle, int(rate), int(bool(use_channel_interleave)), int(bits_per_symbol),
+            _ptr(soft), soft.stride(0), n, _ptr(data), _ptr(status)))
+    finally:
+        ctx.set_decode_flags(saved)
     return data, status
 
 

@@ -1,0 +1,137 @@
+"""GPU parity of the LDPC retry ladder: v2::decodeFixedFrame phases 0-6
+(src/protocol/frame_v2.cpp:1389-1546) and robustDecodeSingleCW
+(src/gui/modem/streaming_decoder.cpp:1028-1058) against the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.bindings import (R1_4, R1_2, R2_3, R3_4, BYTES_PER_CW, awgn_llrs, unpack_bits)
+
+pytestmark = pytest.mark.gpu
+
+MAX_ITER = {R1_4: 50, R1_2: 80, R2_3: 70, R3_4: 60}
+
+# frame_v2.cpp:1409-1542: (kind of ref_ladder_perturb, sigma, seed offset from the data hash) per attempt 5..38
+LADDER = ([(1, s, r * 997 + r * 31) for r, s in enumerate(
+              [0.3, 0.7, 0.3, 1.0, 0.5, 1.5, 0.3, 2.0, 0.5, 0.7, 1.0, 2.5, 0.3, 1.5, 0.5])] +
+          [(2, s, (r + 15) * 997 + 12345) for r, s in enumerate([0.3, 0.8, 1.5, 2.5, 4.0])] +
+          [(3, s, (r + 20) * 997 + 54321) for r, s in enumerate([0.5, 1.5, 3.0])] +
+          [(4, s, (r + 23) * 997 + 99999) for r, s in enumerate([0.5, 1.5, 3.0])] +
+          [(5, s, (r + 26) * 997 + 33333) for r, s in enumerate([0.0, 0.2, 0.5, 1.0, 1.5])] +
+          [(6, s, (r + 31) * 997 + 77777) for r, s in enumerate([0.3, 1.0, 2.0])])
+
+
+def data_hash(cw_bits: np.ndarray) -> int:
+    """frame_v2.cpp:1391-1396"""
+    h = 0
+    for u in cw_bits[:16].astype(np.float32).view(np.uint32):
+        h ^= (int(u) + 0x9e3779b9 + ((h << 6) & 0xFFFFFFFF) + (h >> 2)) & 0xFFFFFFFF
+    return h
+
+
+def test_ladder_perturbation_is_libstdcxx_exact(ctx, ref):
+    """Every perturbing attempt (5..38): the soft bits handed to the decoder are the same bits as
+    std::mt19937 + std::normal_distribution<float> produce on the host."""
+    from ria_b200 import fec
+    rng = np.random.default_rng(7)
+    llr = (rng.standard_normal((24, 648)) * 6.0).astype(np.float32)
+    llr[3] *= 4.0                      # exercises the +-10 / +-6 clips
+    llr[5, :40] = 0.0                  # llr >= 0 -> +1 in the hard-decision phase
+    d = torch.from_numpy(llr).cuda()
+    for attempt in range(1, 39):
+        got = fec.ladder_perturb_batch(d, attempt, ctx).cpu().numpy()
+        if attempt <= 4:
+            assert np.array_equal(got.view(np.uint32), llr.view(np.uint32))
+            continue
+        kind, sigma, off = LADDER[attempt - 5]
+        for i in range(len(llr)):
+            want = ref.ladder_perturb(llr[i], data_hash(llr[i]) + off, sigma, kind)
+            assert np.array_equal(got[i].view(np.uint32), want.view(np.uint32)), (attempt, i, np.abs(got[i] - want).max())
+
+
+@pytest.mark.parametrize("rate,esn0", [(R1_4, -1.2), (R1_2, 2.2), (R2_3, 3.8), (R3_4, 4.6)])
+def test_robust_decode_single_cw(ctx, ref, port, rate, esn0):
+    from ria_b200 import fec
+    rng = np.random.default_rng(100 + rate)
+    k = fec.code_params(rate)[0]
+    nb = (k + 7) // 8
+    n = 192
+    cws = np.stack([unpack_bits(port.ldpc_encode(rate, rng.integers(0, 256, size=k // 8, dtype=np.uint8))[:81])
+                    for _ in range(n)])
+    llr = awgn_llrs(cws, esn0, rng)
+    dec = fec.LDPCDecoder(rate, ctx)
+    info, ok, iters, attempt = [t.cpu().numpy() for t in dec.robust_decode_batch(torch.from_numpy(llr).cuda())]
+    n_retry_ok = 0
+    for i in range(n):
+        w_ok, w_info, w_it, w_at = False, None, None, 255
+        first_it = None
+        for a, factor in enumerate([0.9375, 0.875, 0.75, 0.625, 0.5]):
+            b, s, it = ref.ldpc_decode_soft(rate, llr[i], MAX_ITER[rate], factor)
+            if a == 0:
+                first_it = it
+            if s:
+                w_ok, w_info, w_it, w_at = True, b, it, a
+                break
+        assert bool(ok[i]) == w_ok, i
+        if w_ok:
+            assert attempt[i] == w_at and iters[i] == w_it, (i, attempt[i], w_at, iters[i], w_it)
+            assert bytes(info[i, :nb]) == bytes(w_info[:nb]), i
+            n_retry_ok += w_at > 0
+        else:
+            assert attempt[i] == 255 and iters[i] == first_it
+    assert int((attempt != 0).sum()) > 5, "operating point does not exercise the retries"
+    print(f"rate {rate}: {int((attempt != 0).sum())} first-decode failures, {n_retry_ok} recovered by a retry")
+
+
+def _frames(ref, rate, n, esn0, rng, bps):
+    bpc = BYTES_PER_CW[rate]
+    soft = np.empty((n, 2592), np.float32)
+    for i in range(n):
+        payload = rng.integers(0, 256, size=4 * bpc - 19 - int(rng.integers(0, 8)), dtype=np.uint8)
+        frame = ref.make_data_frame("K1ABC", "W2XYZ", i & 0xFFFF, payload)
+        coded = ref.encode_fixed_frame(frame, rate, True, bps)
+        soft[i] = awgn_llrs(np.unpackbits(coded)[:2592], esn0, rng)
+    return soft
+
+
+@pytest.mark.parametrize("rate,esn0,bps", [(R1_2, 1.75, 106), (R3_4, 4.9, 264), (R1_4, -1.0, 53), (R2_3, 3.6, 176)])
+def test_decode_fixed_frame_with_ladder_matches_reference(ctx, ref, rate, esn0, bps):
+    """Whole frames through the reference's complete decodeFixedFrame vs the first pass + ladder
+    on the device.  Frames in which all four codewords decode but the frame CRC fails go on to the
+    reference's CRC-guided repair (:1558-1916), which is not built: they are counted, not compared."""
+    from ria_b200 import ofdm
+    rng = np.random.default_rng(300 + rate)
+    n = 96
+    soft = _frames(ref, rate, n, esn0, rng, bps)
+    data, status = ofdm.decode_fixed_frame_batch(torch.from_numpy(soft).cuda(), rate, True, bps, ctx, retry_ladder=True)
+    data1, status1 = ofdm.decode_fixed_frame_batch(torch.from_numpy(soft).cuda(), rate, True, bps, ctx, retry_ladder=False)
+    data, st, st1 = data.cpu().numpy(), ofdm.status_array(status), ofdm.status_array(status1)
+    bpc = BYTES_PER_CW[rate]
+    skipped = compared = recovered = carried = 0
+    for i in range(n):
+        if st["all_ok"][i] and not (st["header_valid"][i] and st["frame_crc_ok"][i]):
+            skipped += 1
+            continue
+        w_data, w_ok = ref.decode_fixed_frame_full(soft[i], rate, True, bps)
+        assert np.array_equal(st["cw_ok"][i], w_ok), (i, st["cw_ok"][i], w_ok, st["ladder_cw_mask"][i])
+        assert np.array_equal(data[i], w_data), i
+        compared += 1
+        recovered += bin(int(st["ladder_cw_mask"][i])).count("1")
+        # a codeword the first pass decoded but the frame walk had to decode again with the carried factor
+        carried += int(((st1["cw_ok"][i] == 1) & (st["cw_iters"][i] != st1["cw_iters"][i])).sum())
+    first_fail = int((st1["cw_ok"] == 0).sum())
+    assert first_fail > 10, "operating point does not exercise the ladder"
+    assert int((st["ladder_cw_mask"] != 0).sum()) > 0          # the ladder recovered something (compared or not)
+    assert compared >= 10, (compared, skipped)
+    print(f"rate {rate}: {first_fail} first-pass failures, {recovered} recovered by the ladder, "
+          f"{carried} codewords re-decoded with the carried factor, {skipped} frames skipped (false positives)")
+
+
+def test_ladder_off_is_first_pass_and_flag_roundtrip(ctx):
+    import ria_b200
+    assert ctx.get_decode_flags() == 0
+    ctx.set_decode_flags(ria_b200.DECODE_RETRY_LADDER)
+    assert ctx.get_decode_flags() == ria_b200.DECODE_RETRY_LADDER
+    ctx.set_decode_flags(0)
+    with pytest.raises(ria_b200.RiaError):
+        ctx.set_decode_flags(64)
