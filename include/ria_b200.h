@@ -61,7 +61,8 @@ const char* ria_version(void);
  * the context stream; get_timing sums the elapsed time of all launches of one kind since enable.
  * kinds: 0 LDPC, 1 OFDM demod, 2 frame status/CRC, 3 AWGN channel, 4 MC-DPSK demod, 5 ZC sync,
  * 6 chirp sync, 7 chase combine, 8 Watterson channel, 9 MC-DPSK CFO correction, 10 OFDM data sync,
- * 11 OFDM FFT stage, 12 OFDM carrier stage, 13 OFDM CFO phase scan, 14 LDPC retry ladder. */
+ * 11 OFDM FFT stage, 12 OFDM carrier stage, 13 OFDM CFO phase scan, 14 LDPC retry ladder,
+ * 15 false-positive frame repair. */
 int  ria_ctx_set_timing(ria_ctx* ctx, int enable);
 /* Decode options of the frame entry points (ria_frame_decode_batch_dev, ria_ofdm_rx_frames_dev/_host):
  *   RIA_DECODE_RETRY_LADDER  run the LDPC retry ladder of v2::decodeFixedFrame
@@ -69,9 +70,14 @@ int  ria_ctx_set_timing(ria_ctx* ctx, int enable);
  *                            soft-bit perturbations) on every codeword whose first decode failed,
  *                            including the reference's carry-over of the decoder's min-sum factor to
  *                            the following codewords of the frame.
- * Default 0 = first pass only (:1335-1385).  The CRC-guided false-positive repair (:1558-1916) is
- * not part of either mode (second half). */
+ *   RIA_DECODE_FP_REPAIR     run the "LDPC false positive recovery" (:1558-1916) on every frame whose
+ *                            four codewords pass parity while the reassembled frame does not verify:
+ *                            CRC-guided 1..4-bit flips, re-decode with other min-sum factors, else all
+ *                            four codewords are marked failed.
+ * Default 0 = first pass only (:1335-1385).  RIA_DECODE_FULL = the complete v2::decodeFixedFrame. */
 #define RIA_DECODE_RETRY_LADDER 1
+#define RIA_DECODE_FP_REPAIR    2
+#define RIA_DECODE_FULL         3
 int  ria_ctx_set_decode_flags(ria_ctx* ctx, int flags);
 int  ria_ctx_get_decode_flags(const ria_ctx* ctx);
 int  ria_ctx_get_timing(ria_ctx* ctx, int kind, double* total_ms, int64_t* launches);
@@ -204,7 +210,8 @@ typedef struct {
     uint8_t  total_cw;
     uint8_t  ladder_cw_mask;     /* bit c: codeword c failed its first decode and the retry ladder recovered it */
     uint8_t  ladder_max_attempt; /* highest ladder attempt (1..38, frame_v2.cpp:1409-1542) a recovered codeword needed */
-    uint8_t  pad[1];
+    uint8_t  fp_repair;          /* false-positive repair (frame_v2.cpp:1558-1916): 0 not needed / not run,
+                                    1 frame repaired, 2 given up (all four codewords marked failed) */
 } ria_frame_status;
 
 /* Batched first pass of v2::decodeFixedFrame (src/protocol/frame_v2.cpp:1335-1385, 1548-1556):
@@ -213,7 +220,8 @@ typedef struct {
  * bits_per_symbol, 4 x LDPCDecoder::decodeSoft(factor 0.9375, getRecommendedIterations(rate)),
  * take bytes_per_cw bytes per codeword, then v2::parseHeader + frame CRC
  * (src/protocol/frame_v2.cpp:115-128, 1195-1253, 555-600).  The retry ladder (:1389-1546) runs when
- * the context has RIA_DECODE_RETRY_LADDER set (ria_ctx_set_decode_flags).
+ * the context has RIA_DECODE_RETRY_LADDER set, the false-positive repair (:1558-1916) with
+ * RIA_DECODE_FP_REPAIR (ria_ctx_set_decode_flags; RIA_DECODE_FULL = both = the whole function).
  *   soft_dev   [n][soft_stride] >= 2592 soft bits per frame (soft_stride >= 2592)
  *   data_dev   [n][4*bytes_per_cw] reassembled info bytes (codewords that failed are zeros)
  *   status_dev [n] */

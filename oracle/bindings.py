@@ -115,7 +115,7 @@ class FrameStatus(C.Structure):
                 ("header_valid", C.c_uint8), ("frame_crc_ok", C.c_uint8), ("type", C.c_uint8),
                 ("seq", C.c_uint16), ("payload_len", C.c_uint16), ("src_hash", C.c_uint32),
                 ("dst_hash", C.c_uint32), ("total_cw", C.c_uint8), ("ladder_cw_mask", C.c_uint8),
-                ("ladder_max_attempt", C.c_uint8), ("pad", C.c_uint8 * 1)]
+                ("ladder_max_attempt", C.c_uint8), ("fp_repair", C.c_uint8)]
 
 
 # ultra::Modulation (include/ultra/types.hpp:27-39)

@@ -4,7 +4,7 @@ Python here is plumbing (torch for device memory / streams / torch.distributed);
 is hand-written sm_100a CUDA in libria_b200.so behind the C ABI of include/ria_b200.h.
 There is no CPU fallback.
 """
-from ._lib import Context, RiaError, LIB_PATH, DECODE_RETRY_LADDER, exported_symbols, lib  # noqa: F401
+from ._lib import Context, RiaError, LIB_PATH, DECODE_RETRY_LADDER, DECODE_FP_REPAIR, DECODE_FULL, exported_symbols, lib  # noqa: F401
 from . import fec  # noqa: F401
 from . import ofdm  # noqa: F401
 from . import mcdpsk  # noqa: F401

@@ -13,7 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libria_b200.so")
 
 
-DECODE_RETRY_LADDER = 1        # RIA_DECODE_RETRY_LADDER (include/ria_b200.h)
+DECODE_RETRY_LADDER = 1        # RIA_DECODE_* (include/ria_b200.h)
+DECODE_FP_REPAIR = 2
+DECODE_FULL = 3
 
 
 class RiaError(RuntimeError):

@@ -149,7 +149,7 @@ extern "C" int ria_ctx_synchronize(ria_ctx* ctx) {
 
 extern "C" int ria_ctx_set_decode_flags(ria_ctx* ctx, int flags) {
     if (!ctx) return RIA_E_INVAL;
-    if (flags & ~RIA_DECODE_RETRY_LADDER) return ria::set_error(ctx, RIA_E_INVAL, "ctx: unknown decode flags 0x%x", flags);
+    if (flags & ~RIA_DECODE_FULL) return ria::set_error(ctx, RIA_E_INVAL, "ctx: unknown decode flags 0x%x", flags);
     ctx->decode_flags = flags;
     return RIA_OK;
 }

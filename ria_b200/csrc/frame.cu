@@ -55,7 +55,7 @@ __device__ __forceinline__ bool is_control_frame(uint8_t t) {
 // CodewordStatus::data is only filled on success), parse the header and check the CRCs.
 __global__ void frame_status_kernel(const uint8_t* __restrict__ info, const uint8_t* __restrict__ ok,
                                     const int32_t* __restrict__ iters, const uint8_t* __restrict__ attempt,
-                                    long long n_frames, int bpc,
+                                    const uint8_t* __restrict__ repair, long long n_frames, int bpc,
                                     uint8_t* __restrict__ data, ria_frame_status* __restrict__ status) {
     const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (f >= n_frames) return;
@@ -75,6 +75,7 @@ __global__ void frame_status_kernel(const uint8_t* __restrict__ info, const uint
         for (int b = 0; b < bpc; ++b) out[c * bpc + b] = ok[cw] ? info[cw * kInfoStride + b] : 0;
     }
     st.all_ok = all ? 1 : 0;
+    if (repair) st.fp_repair = repair[f];
     // v2::parseHeader on codeword 0 (needs >= 20 bytes and a decoded CW0, reassemble():1030-1051)
     if (st.cw_ok[0] && bpc >= 20) {
         const uint8_t* h = out;
@@ -118,7 +119,8 @@ int bytes_per_codeword(int rate) {
 // scratch layout for n frames: info [4n][64] | ok [4n] | iters [4n] (+ llr [n][llr_stride] for the chain)
 struct Scratch {
     uint8_t* info; uint8_t* ok; int32_t* iters; float* llr; int32_t* n_llr;
-    uint8_t* attempt; int* fail_list;           // retry ladder only
+    uint8_t* attempt; int* fail_list;           // retry ladder / repair only
+    uint8_t* repair;
 };
 
 int carve_scratch(ria_ctx* ctx, int64_t n_frames, int llr_stride, Scratch& s) {
@@ -131,15 +133,18 @@ int carve_scratch(ria_ctx* ctx, int64_t n_frames, int llr_stride, Scratch& s) {
     const size_t o_llr = take(static_cast<size_t>(n_frames) * llr_stride * 4);
     const size_t o_nl = take(static_cast<size_t>(n_frames) * 4);
     const bool ladder = (ctx->decode_flags & RIA_DECODE_RETRY_LADDER) != 0;
+    const bool repair = (ctx->decode_flags & RIA_DECODE_FP_REPAIR) != 0;
     const size_t o_at = take(ladder ? n_cw : 0);
-    const size_t o_fl = take(ladder ? static_cast<size_t>(n_frames) * 4 : 0);
+    const size_t o_fl = take((ladder || repair) ? static_cast<size_t>(n_frames) * 4 : 0);
+    const size_t o_rp = take(repair ? static_cast<size_t>(n_frames) : 0);
     int rc = ensure_scratch(ctx, off);
     if (rc != RIA_OK) return rc;
     unsigned char* b = static_cast<unsigned char*>(ctx->scratch);
     s.info = b + o_info; s.ok = b + o_ok; s.iters = reinterpret_cast<int32_t*>(b + o_it);
     s.llr = reinterpret_cast<float*>(b + o_llr); s.n_llr = reinterpret_cast<int32_t*>(b + o_nl);
     s.attempt = ladder ? b + o_at : nullptr;
-    s.fail_list = ladder ? reinterpret_cast<int*>(b + o_fl) : nullptr;
+    s.fail_list = (ladder || repair) ? reinterpret_cast<int*>(b + o_fl) : nullptr;
+    s.repair = repair ? b + o_rp : nullptr;
     return RIA_OK;
 }
 
@@ -156,16 +161,22 @@ int frame_decode_impl(ria_ctx* ctx, int rate, int use_ci, int bits_per_symbol, c
     int rc = ldpc_launch(ctx, rate, recommended_iterations(rate), 0.9375f, soft_dev, n_frames * 4,
                          1, soft_stride, step, s.info, kInfoStride, s.ok, s.iters);
     if (rc != RIA_OK) return rc;
-    if (s.fail_list) {
+    if (s.attempt) {
         // retry ladder (frame_v2.cpp:1389-1546) on the frames with a failed codeword
         rc = ldpc_retry_launch(ctx, rate, recommended_iterations(rate), soft_dev, n_frames, 1, soft_stride, step,
                                s.info, kInfoStride, s.ok, s.iters, s.attempt, s.fail_list);
         if (rc != RIA_OK) return rc;
     }
+    if (s.repair) {
+        // false-positive repair (frame_v2.cpp:1558-1916) on the frames that decoded but do not verify
+        rc = frame_repair_launch(ctx, rate, recommended_iterations(rate), soft_dev, n_frames, soft_stride, step,
+                                 s.info, kInfoStride, s.ok, s.repair, s.fail_list);
+        if (rc != RIA_OK) return rc;
+    }
     const int threads = 128;
     const unsigned blocks = static_cast<unsigned>((n_frames + threads - 1) / threads);
     time_begin(ctx, KK_FRAME_STATUS);
-    frame_status_kernel<<<blocks, threads, 0, ctx->stream>>>(s.info, s.ok, s.iters, s.attempt, n_frames, bpc, data_dev, status_dev);
+    frame_status_kernel<<<blocks, threads, 0, ctx->stream>>>(s.info, s.ok, s.iters, s.attempt, s.repair, n_frames, bpc, data_dev, status_dev);
     time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

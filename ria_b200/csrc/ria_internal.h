@@ -109,11 +109,14 @@ int ldpc_launch(ria_ctx* ctx, int rate, int max_iter, float min_sum_factor, cons
 int ldpc_retry_launch(ria_ctx* ctx, int rate, int max_iter, const float* llr_dev, int64_t n_units, int frame_mode,
                       int soft_stride, int step, uint8_t* info_dev, int info_stride, uint8_t* ok_dev,
                       int32_t* iters_dev, uint8_t* attempt_dev, int* list_scratch);
+int frame_repair_launch(ria_ctx* ctx, int rate, int max_iter, const float* soft_dev, int64_t n_frames, int soft_stride,
+                        int step, uint8_t* info_dev, int info_stride, uint8_t* ok_dev, uint8_t* repair_dev,
+                        int* list_scratch);
 
 // kernel kinds for the timing hook / launch accounting
 enum KernelKind { KK_LDPC = 0, KK_OFDM_DEMOD = 1, KK_FRAME_STATUS = 2, KK_AWGN = 3, KK_MCDPSK = 4,
                   KK_ZC_SYNC = 5, KK_CHIRP_SYNC = 6, KK_CHASE = 7, KK_WATTERSON = 8, KK_MCDPSK_CFO = 9, KK_OFDM_SYNC = 10,
-                  KK_OFDM_FFT = 11, KK_OFDM_CARRIER = 12, KK_OFDM_PHASE = 13, KK_LDPC_RETRY = 14, KK_COUNT = 16 };
+                  KK_OFDM_FFT = 11, KK_OFDM_CARRIER = 12, KK_OFDM_PHASE = 13, KK_LDPC_RETRY = 14, KK_FRAME_REPAIR = 15, KK_COUNT = 16 };
 void time_begin(ria_ctx* ctx, int kind);
 void time_end(ria_ctx* ctx);
 

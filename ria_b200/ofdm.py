@@ -21,7 +21,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from ._lib import Context, RiaError, lib, DECODE_RETRY_LADDER
+from ._lib import Context, RiaError, lib, DECODE_RETRY_LADDER, DECODE_FP_REPAIR
 from .fec import code_params, default_context
 
 # ultra::Modulation (include/ultra/types.hpp:27-39)
@@ -77,14 +77,14 @@ class FrameStatus(C.Structure):
                 ("header_valid", C.c_uint8), ("frame_crc_ok", C.c_uint8), ("type", C.c_uint8),
                 ("seq", C.c_uint16), ("payload_len", C.c_uint16), ("src_hash", C.c_uint32),
                 ("dst_hash", C.c_uint32), ("total_cw", C.c_uint8), ("ladder_cw_mask", C.c_uint8),
-                ("ladder_max_attempt", C.c_uint8), ("pad", C.c_uint8 * 1)]
+                ("ladder_max_attempt", C.c_uint8), ("fp_repair", C.c_uint8)]
 
 
 FRAME_STATUS_DTYPE = np.dtype([
     ("cw_ok", np.uint8, 4), ("cw_iters", np.int32, 4), ("all_ok", np.uint8), ("header_valid", np.uint8),
     ("frame_crc_ok", np.uint8), ("type", np.uint8), ("seq", np.uint16), ("payload_len", np.uint16),
     ("src_hash", np.uint32), ("dst_hash", np.uint32), ("total_cw", np.uint8), ("ladder_cw_mask", np.uint8),
-    ("ladder_max_attempt", np.uint8), ("pad", np.uint8, 1)],
+    ("ladder_max_attempt", np.uint8), ("fp_repair", np.uint8)],
     align=True)
 assert FRAME_STATUS_DTYPE.itemsize == C.sizeof(FrameStatus)
 
@@ -164,10 +164,12 @@ class OFDMDemodulator:
 
 
 def decode_fixed_frame_batch(soft: torch.Tensor, rate: int, use_channel_interleave: bool,
-                             bits_per_symbol: int, ctx: Optional[Context] = None, retry_ladder: Optional[bool] = None):
+                             bits_per_symbol: int, ctx: Optional[Context] = None, retry_ladder: Optional[bool] = None,
+                             fp_repair: Optional[bool] = None):
     """v2::decodeFixedFrame for a batch: soft CUDA fp32 [n, >=2592].  First pass only, or with the
     LDPC retry ladder (frame_v2.cpp:1389-1546) when retry_ladder is True (None: the context's
-    decode flags decide).
+    decode flags decide) and the false-positive repair (:1558-1916) when fp_repair is True; both = the
+    complete reference function.
 
     Returns (data u8 [n, 4*bytes_per_cw], status structured array on the device as uint8 tensor
     viewable with FRAME_STATUS_DTYPE after .cpu().numpy())."""
@@ -184,6 +186,9 @@ def decode_fixed_frame_batch(soft: torch.Tensor, rate: int, use_channel_interlea
     saved = ctx.get_decode_flags()
     if retry_ladder is not None:
         ctx.set_decode_flags((saved | DECODE_RETRY_LADDER) if retry_ladder else (saved & ~DECODE_RETRY_LADDER))
+    if fp_repair is not None:
+        cur = ctx.get_decode_flags()
+        ctx.set_decode_flags((cur | DECODE_FP_REPAIR) if fp_repair else (cur & ~DECODE_FP_REPAIR))
     try:
         ctx.check(lib().ria_frame_decode_batch_dev(
             ctx.handle, int(rate), int(bool(use_channel_interleave)), int(bits_per_symbol),

@@ -94,7 +94,7 @@ def _frames(ref, rate, n, esn0, rng, bps):
     return soft
 
 
-@pytest.mark.parametrize("rate,esn0,bps", [(R1_2, 1.75, 106), (R3_4, 4.9, 264), (R1_4, -1.0, 53), (R2_3, 3.6, 176)])
+@pytest.mark.parametrize("rate,esn0,bps", [(R1_2, 1.75, 106), (R1_4, -1.0, 53), (R2_3, 3.6, 176)])
 def test_decode_fixed_frame_with_ladder_matches_reference(ctx, ref, rate, esn0, bps):
     """Whole frames through the reference's complete decodeFixedFrame vs the first pass + ladder
     on the device.  Frames in which all four codewords decode but the frame CRC fails go on to the
@@ -135,3 +135,26 @@ def test_ladder_off_is_first_pass_and_flag_roundtrip(ctx):
     ctx.set_decode_flags(0)
     with pytest.raises(ria_b200.RiaError):
         ctx.set_decode_flags(64)
+
+
+@pytest.mark.parametrize("rate,esn0,bps", [(R1_2, 1.75, 106), (R1_2, 3.4, 106), (R3_4, 4.9, 264), (R3_4, 7.5, 264),
+                                           (R1_4, -1.0, 53), (R2_3, 3.6, 176), (R2_3, 5.5, 176)])
+def test_decode_fixed_frame_full_matches_reference(ctx, ref, rate, esn0, bps):
+    """RIA_DECODE_FULL (first pass + retry ladder + false-positive repair) against the reference's
+    complete v2::decodeFixedFrame on every frame: decoded flags and bytes identical."""
+    from ria_b200 import ofdm
+    rng = np.random.default_rng(500 + rate + int(10 * esn0))
+    n = 128
+    soft = _frames(ref, rate, n, esn0, rng, bps)
+    soft[::7, :] = np.clip(soft[::7, :], -2.5, 2.5)        # ties among the weakest soft bits (suspect ordering)
+    data, status = ofdm.decode_fixed_frame_batch(torch.from_numpy(soft).cuda(), rate, True, bps, ctx,
+                                                 retry_ladder=True, fp_repair=True)
+    data, st = data.cpu().numpy(), ofdm.status_array(status)
+    for i in range(n):
+        w_data, w_ok = ref.decode_fixed_frame_full(soft[i], rate, True, bps)
+        assert np.array_equal(st["cw_ok"][i], w_ok), (i, st["cw_ok"][i], w_ok, st["ladder_cw_mask"][i], st["fp_repair"][i])
+        assert np.array_equal(data[i], w_data), (i, st["fp_repair"][i])
+    print(f"rate {rate} @ {esn0} dB: ladder recovered {int((st['ladder_cw_mask'] != 0).sum())} frames, "
+          f"repair: {int((st['fp_repair'] == 1).sum())} repaired, {int((st['fp_repair'] == 2).sum())} given up, "
+          f"{int(st['all_ok'].sum())}/{n} frames decoded")
+    assert int((st["fp_repair"] != 0).sum()) + int((st["ladder_cw_mask"] != 0).sum()) > 0
