@@ -241,7 +241,10 @@ class OfdmQam64Workload:
 
     def e2e_bytes(self):
         from ria_b200 import ofdm
-        return (self.e2e_n * self.frame_len * 4,
+        # ria_ofdm_rx_frames_host copies only the 1024-sample FFT window of each 1120-sample symbol (the
+        # cyclic prefix is never read by the demodulator): 12 x 1024 x 4 B per frame cross PCIe
+        sym_copied = 1024 if os.environ.get("RIA_H2D_FULL_SYMBOLS") != "1" else 1120
+        return (self.e2e_n * (self.frame_len // 1120) * sym_copied * 4,
                 self.e2e_n * (240 + ofdm.FRAME_STATUS_DTYPE.itemsize + 4))
 
 

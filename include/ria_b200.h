@@ -229,6 +229,13 @@ int ria_frame_decode_batch_dev(ria_ctx* ctx, int rate, int use_channel_interleav
                                int bits_per_symbol, const float* soft_dev, int32_t soft_stride,
                                int64_t n_frames, uint8_t* data_dev, ria_frame_status* status_dev);
 
+/* Same with HOST buffers (soft [n][soft_stride], data [n][4*bytes_per_cw], status [n]): H2D, kernels and
+ * D2H inside the call.  With RIA_DECODE_FULL this is v2::decodeFixedFrame(interleaved_soft, rate,
+ * use_channel_deinterleave, bits_per_symbol) for n frames. */
+int ria_frame_decode_batch_host(ria_ctx* ctx, int rate, int use_channel_interleave,
+                                int bits_per_symbol, const float* soft, int32_t soft_stride,
+                                int64_t n_frames, uint8_t* data, ria_frame_status* status);
+
 /* Whole receive chain for OFDM data frames: presynced demod -> frame decode, one call.
  * Device buffers; llr scratch is owned by the context. */
 int ria_ofdm_rx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg, int rate,

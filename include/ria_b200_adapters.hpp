@@ -8,8 +8,9 @@
 //   ria::LDPCCodec          <- ultra::fec::LDPCCodec / ICodec  src/fec/ldpc_codec.hpp:38-105
 //   ria::OFDMChirpRx        <- RX half of ultra::OFDMChirpWaveform (IWaveform)
 //                                                              src/waveform/ofdm_chirp_waveform.cpp:79-105, 391-485
-//   ria::decodeFixedFrame   <- first pass of ultra::protocol::v2::decodeFixedFrame
-//                                                              src/protocol/frame_v2.cpp:1335-1385
+//   ria::decodeFixedFrame   <- ultra::protocol::v2::decodeFixedFrame (soft bits in: the complete function with
+//                              retry ladder and false-positive repair; samples in: demod + first pass)
+//                                                              src/protocol/frame_v2.cpp:1335-1920
 //
 // Compile inside the reference tree with -DRIA_WITH_ULTRA to make LDPCCodec derive from
 // ultra::fec::ICodec (then it can be returned by CodecFactory::create).  Without that macro the
@@ -233,6 +234,34 @@ struct CodewordStatus {
     ria_frame_status status{};       // header fields / CRC flags
     bool allSuccess() const { for (bool b : decoded) if (!b) return false; return !decoded.empty(); }
 };
+
+// v2::decodeFixedFrame(interleaved_soft, rate, use_channel_deinterleave, bits_per_symbol)
+// (frame_v2.cpp:1335-1920), same arguments and result: first pass, retry ladder (:1389-1546) and
+// false-positive repair (:1558-1916).  Fewer than 2592 soft bits -> all four codewords failed (:1343-1345).
+inline CodewordStatus decodeFixedFrame(const std::vector<float>& interleaved_soft, int rate,
+                                       bool use_channel_deinterleave = false, size_t bits_per_symbol = 0) {
+    int k = 0;
+    if (ria_ldpc_params(rate, &k, nullptr, nullptr) != RIA_OK) throw std::invalid_argument("bad code rate");
+    const int bpc = k / 8;
+    CodewordStatus st;
+    st.decoded.assign(4, false);
+    st.data.resize(4);
+    if (interleaved_soft.size() < 2592) return st;
+    Bytes data(4 * bpc);
+    Context& c = Context::instance();
+    const int saved = ria_ctx_get_decode_flags(c.get());
+    c.check(ria_ctx_set_decode_flags(c.get(), RIA_DECODE_FULL));
+    const int rc = ria_frame_decode_batch_host(c.get(), rate, use_channel_deinterleave ? 1 : 0,
+                                               static_cast<int>(bits_per_symbol), interleaved_soft.data(),
+                                               static_cast<int32_t>(interleaved_soft.size()), 1, data.data(), &st.status);
+    ria_ctx_set_decode_flags(c.get(), saved);
+    c.check(rc);
+    for (int i = 0; i < 4; ++i) {
+        st.decoded[i] = st.status.cw_ok[i] != 0;
+        if (st.decoded[i]) st.data[i].assign(data.begin() + i * bpc, data.begin() + (i + 1) * bpc);
+    }
+    return st;
+}
 
 // Batch = 1 convenience over a device round trip; a real receiver batches frames and calls
 // ria_frame_decode_batch_dev / ria_ofdm_rx_frames_host directly.

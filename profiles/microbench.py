@@ -107,6 +107,27 @@ def main():
             del s, llr
             torch.cuda.empty_cache()
 
+        # ---- complete decodeFixedFrame (first pass / + retry ladder / + false-positive repair) on degraded frames ----
+        for mod, rate, snr, label in ((ofdm.QPSK, 2, 1.0, "QPSK R1/2 AWGN 1 dB"), (ofdm.QAM64, 4, 18.5, "QAM64 R3/4 AWGN 18.5 dB")):
+            cfg = ofdm.ModemConfig.high_throughput(mod) if mod == ofdm.QAM64 else ofdm.ModemConfig.for_waveform(mod, rate)
+            pool, _ = txsynth.make_frame_pool(cfg, rate, 8, seed=5)
+            n = 16384
+            rx = sim.awgn_batch(torch.from_numpy(pool).to(dev), n, snr, seed=2, ctx=ctx)
+            out = ofdm.OFDMDemodulator(cfg, ctx).process_presynced_batch(rx)
+            soft = out["llr"]
+            bps = cfg.getDataCarriers() * ofdm.getBitsPerSymbol(mod)
+            for flags, what in ((0, "first pass"), (1, "+ retry ladder"), (3, "+ ladder + false-positive repair (RIA_DECODE_FULL)")):
+                ctx.set_decode_flags(flags)
+                _, st = ofdm.decode_fixed_frame_batch(soft, rate, True, bps, ctx)
+                ms = timed(lambda: ofdm.decode_fixed_frame_batch(soft, rate, True, bps, ctx), reps=3, warm=1)
+                sa = ofdm.status_array(st)
+                good = int((sa["all_ok"] & sa["header_valid"] & sa["frame_crc_ok"]).sum())
+                add(f"ria_frame_decode_batch_dev  {label}, {what}: {good}/{n} frames valid, "
+                    f"{int((sa['ladder_cw_mask'] != 0).sum())} by ladder, {int((sa['fp_repair'] == 1).sum())} repaired", n, ms, 2592 * 4 + 4 * 61 + 40)
+            ctx.set_decode_flags(0)
+            del rx, out, soft
+            torch.cuda.empty_cache()
+
         # ---- MC-DPSK demodulator ----
         for bits, spread, label in ((1, 4, "DBPSK x4 (configs[2])"), (1, 1, "DBPSK x1"), (2, 1, "DQPSK x1")):
             cfg = mcdpsk.MultiCarrierDPSKConfig.default(bits, spread, 10)

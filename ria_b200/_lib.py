@@ -56,6 +56,7 @@ _SIGNATURES = {
     "ria_ofdm_presynced_batch_taps_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64,
                                                  _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ria_frame_decode_batch_dev": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _vp]),
+    "ria_frame_decode_batch_host": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _vp]),
     "ria_ofdm_rx_frames_dev": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _i64,
                                       _vp, _vp, _vp]),
     "ria_ofdm_rx_frames_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _i64,

@@ -10,6 +10,8 @@
 // :115-128 (CRC-16/CCITT-FALSE), :1195-1253 (parseHeader), :555-600 (frame CRC),
 // src/protocol/frame_v2.hpp:222-228 (isControlFrame), :676-692 (bytes per codeword).
 
+#include <cstdlib>
+
 #include "ofdm_tables.h"
 
 namespace ria {
@@ -203,6 +205,43 @@ extern "C" int ria_frame_decode_batch_dev(ria_ctx* ctx, int rate, int use_channe
                              s, data_dev, status_dev);
 }
 
+extern "C" int ria_frame_decode_batch_host(ria_ctx* ctx, int rate, int use_channel_interleave,
+                                           int bits_per_symbol, const float* soft, int32_t soft_stride,
+                                           int64_t n_frames, uint8_t* data, ria_frame_status* status) {
+    using namespace ria;
+    if (!ctx) return RIA_E_INVAL;
+    if (n_frames < 0) return set_error(ctx, RIA_E_INVAL, "frame: negative size");
+    if (n_frames == 0) return RIA_OK;
+    if (!soft || !data || !status) return set_error(ctx, RIA_E_INVAL, "frame: null buffer");
+    if (soft_stride < kFrameBits) return set_error(ctx, RIA_E_INVAL, "frame: need >= 2592 soft bits per frame");
+    const int bpc = bytes_per_codeword(rate);
+    if (bpc < 0) return set_error(ctx, RIA_E_INVAL, "frame: bad rate %d", rate);
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t chunk = 65536;
+    const int32_t dstride = (kFrameBits + 3) & ~3;
+    const size_t in_b = static_cast<size_t>(chunk) * dstride * sizeof(float);
+    const size_t out_b = static_cast<size_t>(chunk) * (4 * bpc + sizeof(ria_frame_status));
+    int rc = ensure_stage(ctx, 0, in_b + out_b + 512, 0);
+    if (rc != RIA_OK) return rc;
+    cudaStream_t s = ctx->stream;
+    unsigned char* base = static_cast<unsigned char*>(ctx->stage_dev[0]);
+    float* d_soft = reinterpret_cast<float*>(base);
+    ria_frame_status* d_st = reinterpret_cast<ria_frame_status*>(base + in_b);
+    uint8_t* d_data = reinterpret_cast<uint8_t*>(d_st + chunk);
+    for (int64_t off = 0; off < n_frames; off += chunk) {
+        const int64_t n = (n_frames - off < chunk) ? (n_frames - off) : chunk;
+        RIA_CUDA(ctx, cudaMemcpy2DAsync(d_soft, static_cast<size_t>(dstride) * 4, soft + off * soft_stride,
+                                        static_cast<size_t>(soft_stride) * 4, static_cast<size_t>(kFrameBits) * 4,
+                                        static_cast<size_t>(n), cudaMemcpyHostToDevice, s));
+        rc = ria_frame_decode_batch_dev(ctx, rate, use_channel_interleave, bits_per_symbol, d_soft, dstride, n, d_data, d_st);
+        if (rc != RIA_OK) return rc;
+        RIA_CUDA(ctx, cudaMemcpyAsync(data + off * 4 * bpc, d_data, static_cast<size_t>(n) * 4 * bpc, cudaMemcpyDeviceToHost, s));
+        RIA_CUDA(ctx, cudaMemcpyAsync(status + off, d_st, static_cast<size_t>(n) * sizeof(ria_frame_status), cudaMemcpyDeviceToHost, s));
+        RIA_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    return RIA_OK;
+}
+
 extern "C" int ria_ofdm_rx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg, int rate,
                                       int use_channel_interleave,
                                       const float* samples_dev, int64_t frame_stride, int32_t frame_len,
@@ -256,6 +295,9 @@ extern "C" int ria_ofdm_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg
         if (rc != RIA_OK) return rc;
     }
     cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+    if (const char* err = ofdm_config_error(*cfg)) return set_error(ctx, RIA_E_UNSUPPORTED, "ofdm: %s", err);
+    const int sym = ofdm_symbol_samples(*cfg), cp = ofdm_cyclic_prefix(*cfg);
+    static const bool skip_cp = [] { const char* e = std::getenv("RIA_H2D_FULL_SYMBOLS"); return !(e && e[0] == '1'); }();
     // stage_ev[0..1]: "compute of buffer b finished"  stage_ev[2..3]: "H2D of buffer b finished"
     int buf = 0;
     for (int64_t off = 0; off < n_frames; off += chunk, buf ^= 1) {
@@ -269,7 +311,14 @@ extern "C" int ria_ofdm_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg
         uint8_t* d_data = reinterpret_cast<uint8_t*>(d_snr + chunk);
         // buffer reuse: wait until the kernels + D2H that used it two chunks ago are done
         RIA_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->stage_ev[buf], 0));
-        if (frame_stride == frame_len) {
+        if (frame_stride == frame_len && frame_len % sym == 0 && skip_cp) {
+            // Only the FFT window of each symbol is ever read by the demodulator (the cyclic prefix and the
+            // guard are skipped by the kernels), so only the windows cross PCIe: one 2-D copy whose rows are
+            // the symbols of the chunk (pitch = symbol, width = FFT size, starting at the prefix length).
+            RIA_CUDA(ctx, cudaMemcpy2DAsync(d_samp + cp, static_cast<size_t>(sym) * 4, samples + off * frame_stride + cp,
+                                            static_cast<size_t>(sym) * 4, static_cast<size_t>(cfg->fft_size) * 4,
+                                            static_cast<size_t>(n) * (frame_len / sym), cudaMemcpyHostToDevice, cs));
+        } else if (frame_stride == frame_len) {
             RIA_CUDA(ctx, cudaMemcpyAsync(d_samp, samples + off * frame_stride, static_cast<size_t>(n) * frame_len * sizeof(float),
                                           cudaMemcpyHostToDevice, cs));
         } else {

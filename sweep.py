@@ -100,6 +100,8 @@ def run_sweep(args):
     if world > 1:
         rdist.init("nccl", device)
     ctx = ria_b200.Context(local)
+    if not getattr(args, "first_pass_only", False):
+        ctx.set_decode_flags(ria_b200.DECODE_FULL)      # the reference's complete decodeFixedFrame (ladder + repair)
     lo, n_local = rdist.shard_range(args.frames, rank, world)
     cache = ModeCache(ctx, device)
     results = []
@@ -142,6 +144,8 @@ def main():
     ap.add_argument("--snr-max", type=float, default=30.0)
     ap.add_argument("--snr-step", type=float, default=2.0)
     ap.add_argument("--quiet", action="store_true")
+    ap.add_argument("--first-pass-only", action="store_true",
+                    help="skip decodeFixedFrame's retry ladder and false-positive repair")
     run_sweep(ap.parse_args())
 
 
