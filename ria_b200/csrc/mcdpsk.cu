@@ -43,7 +43,6 @@ namespace {
 constexpr int kMaxCar = 16;
 constexpr int kSps = 512;
 constexpr int kSymPad = kSps + 4;           // floats per staged symbol row: 16-byte aligned, bank shift 4 per row
-constexpr int kMixPad = kSps + 2;           // float2 per mixer row: 16-byte aligned, bank shift 4 per row
 constexpr int kGroup = 24;               // rx symbols correlated per pass (multiple of 1, 2 and 4)
 constexpr int kDemodThreads = 256;
 constexpr int kHilbertTaps = 127;
@@ -152,6 +151,9 @@ struct DemodArgs {
     float* llr; int llr_stride; int* n_llr; float* fading; float* cfo_out;
     float* scratch;            // per frame: mags[max_ds][C] | phases[max_ds][C] | errs[max_ds][C]
     int max_ds;
+    int stats_smem_off;        // > 0: the three per-frame arrays live in shared memory at this byte offset
+                               // (the ordered reductions below walk them serially: from global memory that
+                               // walk, not the correlations, was most of the kernel's time)
     const float2* mixer_g;
     int carriers, bits, spread, training;
     unsigned int* counter;
@@ -162,15 +164,16 @@ struct DemodArgs {
 struct DemodSmem {
     float sym[kGroup * kSymPad];
     float2 corr[kGroup * kMaxCar];
+    float2 nrm[kGroup * kMaxCar];      // normalised data symbols of the current group
     float2 prev[kMaxCar];
     float car_sum[kMaxCar], car_sq[kMaxCar], rel[kMaxCar], car_mag[kMaxCar];
     float scale;
     int valid_symbols;
     long long frame;
-    float2 mixer[1];           // [carriers][kMixPad], allocated with the launch
+    float2 mixer[1];           // [kSps][carriers] (sample-major, see correlate), allocated with the launch
 };
 static size_t demod_smem_bytes(int carriers) {
-    return sizeof(DemodSmem) + static_cast<size_t>(carriers) * kMixPad * sizeof(float2);
+    return sizeof(DemodSmem) + static_cast<size_t>(carriers) * kSps * sizeof(float2);
 }
 
 // Packed fp32 multiply (Blackwell FMUL2): (s * m.x, s * m.y) in one issue slot.  The products go
@@ -182,20 +185,26 @@ __device__ __forceinline__ float2 mul2s(float s, float2 b) {
         : "=f"(r.x), "=f"(r.y) : "f"(s), "f"(b.x), "f"(b.y));
     return r;
 }
-// 512-term complex correlation of one staged symbol with one carrier's mixer row, in sample order
-__device__ __forceinline__ float2 correlate(const float* __restrict__ sy, const float2* __restrict__ mx) {
+// 512-term complex correlation of one staged symbol with one carrier's mixer phasors, in sample
+// order.  The kernel is bound by shared-memory wavefronts, not by issue slots: with one mixer row
+// per carrier a warp's 128-bit phasor load touched ten rows and cost ~6 wavefronts (ncu), and
+// there are twice as many phasor loads as sample loads.  The table is therefore sample-major,
+// [sample][carrier]: at a given step every lane of the warp reads the same sample index, so a
+// 64-bit phasor load covers one contiguous 8*C-byte span (one wavefront), and the sample loads are
+// broadcasts.  Per four samples and warp: 4 + ~2 wavefronts instead of ~14.
+__device__ __forceinline__ float2 correlate(const float* __restrict__ sy, const float2* __restrict__ mx, int C) {
     float2 acc = make_float2(0.f, 0.f);
     const float4* sy4 = reinterpret_cast<const float4*>(sy);
-    const float4* mx4 = reinterpret_cast<const float4*>(mx);
 #pragma unroll 4
     for (int i = 0; i < kSps / 4; ++i) {
         const float4 v = sy4[i];
-        const float4 m01 = mx4[2 * i], m23 = mx4[2 * i + 1];
+        const float2 m0 = mx[0], m1 = mx[C], m2 = mx[2 * C], m3 = mx[3 * C];
+        mx += 4 * C;
         float2 p;
-        p = mul2s(v.x, make_float2(m01.x, m01.y)); acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
-        p = mul2s(v.y, make_float2(m01.z, m01.w)); acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
-        p = mul2s(v.z, make_float2(m23.x, m23.y)); acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
-        p = mul2s(v.w, make_float2(m23.z, m23.w)); acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
+        p = mul2s(v.x, m0); acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
+        p = mul2s(v.y, m1); acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
+        p = mul2s(v.z, m2); acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
+        p = mul2s(v.w, m3); acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y);
     }
     return acc;
 }
@@ -208,7 +217,7 @@ mcdpsk_demod_kernel(const DemodArgs a) {
     const int C = a.carriers;
     for (int i = tid; i < C * kSps; i += kDemodThreads) {
         const int c = i / kSps, k = i - c * kSps;
-        sm.mixer[c * kMixPad + k] = a.mixer_g[i];
+        sm.mixer[k * C + c] = a.mixer_g[i];
     }
     __syncthreads();
 
@@ -236,7 +245,8 @@ mcdpsk_demod_kernel(const DemodArgs a) {
         }
         const bool corrected = a.corrected && fabsf(a.cfo_hz[f]) > 0.1f && a.frame_len >= 128;      // :838, :903
         const float* frame = corrected ? a.corrected + fl * a.corrected_stride : a.samples + f * a.frame_stride + st;
-        float* mags = a.scratch + fl * (3LL * a.max_ds * kMaxCar);
+        float* mags = a.stats_smem_off ? reinterpret_cast<float*>(smem_raw + a.stats_smem_off)
+                                       : a.scratch + fl * (3LL * a.max_ds * kMaxCar);
         float* phases = mags + a.max_ds * kMaxCar;
         float* errs = phases + a.max_ds * kMaxCar;
 
@@ -244,7 +254,7 @@ mcdpsk_demod_kernel(const DemodArgs a) {
         for (int i = tid; i < kSps; i += kDemodThreads) sm.sym[i] = frame[a.training * kSps + i];
         __syncthreads();
         if (tid < C) {
-            const float2 acc = correlate(sm.sym, sm.mixer + tid * kMixPad);
+            const float2 acc = correlate(sm.sym, sm.mixer + tid, C);
             float2 p = make_float2(__fdiv_rn(acc.x, static_cast<float>(kSps)), __fdiv_rn(acc.y, static_cast<float>(kSps)));
             const float m = cabs_d(p);
             if (m > 0.001f) { const float m2 = cabs_d(p); p = make_float2(__fdiv_rn(p.x, m2), __fdiv_rn(p.y, m2)); }
@@ -267,56 +277,63 @@ mcdpsk_demod_kernel(const DemodArgs a) {
                 const int s = p / C, c = p - s * C;
                 float2 acc = make_float2(0.f, 0.f);
                 if (s < g_n) {
-                    acc = correlate(sm.sym + s * kSymPad, sm.mixer + c * kMixPad);     // sum += samples[i] * mixer  (:940-943)
+                    acc = correlate(sm.sym + s * kSymPad, sm.mixer + c, C);     // sum += samples[i] * mixer  (:940-943)
                     acc = make_float2(__fdiv_rn(acc.x, static_cast<float>(kSps)), __fdiv_rn(acc.y, static_cast<float>(kSps)));
                 }
                 sm.corr[s * kMaxCar + c] = acc;
             }
             __syncthreads();
-            // combine repetitions, then differential decode; data symbols of a group are
-            // chained through sm.prev, so one thread per carrier walks them in order
-            if (tid < C) {
-                const int c = tid;
-                float2 prev = sm.prev[c];
-                const int ds0 = g0 / a.spread;
-                const int ds_n = kGroup / a.spread;
-                for (int d = 0; d < ds_n && ds0 + d < n_ds; ++d) {
-                    float2 comb = make_float2(0.f, 0.f);
-                    for (int rep = 0; rep < a.spread; ++rep) {
-                        const int rx = (ds0 + d) * a.spread + rep;
-                        if (rx >= n_rx) break;
-                        const float2 cur = sm.corr[(d * a.spread + rep) * kMaxCar + c];
-                        comb.x = __fadd_rn(comb.x, cur.x); comb.y = __fadd_rn(comb.y, cur.y);
-                    }
-                    comb.x = __fdiv_rn(comb.x, static_cast<float>(a.spread));
-                    comb.y = __fdiv_rn(comb.y, static_cast<float>(a.spread));
-                    const float mag = cabs_d(comb);
-                    const float2 nrm = (mag > 0.0001f) ? make_float2(__fdiv_rn(comb.x, mag), __fdiv_rn(comb.y, mag))
-                                                       : make_float2(1.0f, 0.0f);
-                    // diff = normalized * conj(prev)
-                    const float2 diff = make_float2(__fsub_rn(__fmul_rn(nrm.x, prev.x), __fmul_rn(nrm.y, -prev.y)),
-                                                    __fadd_rn(__fmul_rn(nrm.x, -prev.y), __fmul_rn(nrm.y, prev.x)));
-                    prev = nrm;
-                    const float phase = atan2_rn(diff.y, diff.x);
-                    const float PI = static_cast<float>(M_PI);
-                    float err;
-                    if (a.bits == 2) {
-                        const float shifted = phase - PI / 4.0f;
-                        const float idx = roundf(shifted / (PI / 2.0f));
-                        const float ideal = idx * PI / 2.0f + PI / 4.0f;
-                        err = phase - ideal;
-                    } else {
-                        const float idx = roundf(phase / PI);
-                        const float ideal = idx * PI;
-                        err = phase - ideal;
-                    }
-                    while (err > PI) err -= 2.0f * PI;
-                    while (err < -PI) err += 2.0f * PI;
-                    const int o = (ds0 + d) * kMaxCar + c;
-                    mags[o] = mag; phases[o] = phase; errs[o] = err * err;
+            // combine repetitions, normalise, differential decode.  The chain through `prev` is not a
+            // recurrence -- prev is just the previous symbol's normalised value -- so every (data symbol,
+            // carrier) of the group is evaluated by its own thread: first the normalised symbols, then the
+            // differences against the neighbour (the group's first symbol against sm.prev).
+            const int ds0 = g0 / a.spread;
+            int ds_n = kGroup / a.spread;
+            if (ds_n > n_ds - ds0) ds_n = n_ds - ds0;
+            for (int p = tid; p < ds_n * C; p += kDemodThreads) {
+                const int d = p / C, c = p - d * C;
+                float2 comb = make_float2(0.f, 0.f);
+                for (int rep = 0; rep < a.spread; ++rep) {
+                    const int rx = (ds0 + d) * a.spread + rep;
+                    if (rx >= n_rx) break;
+                    const float2 cur = sm.corr[(d * a.spread + rep) * kMaxCar + c];
+                    comb.x = __fadd_rn(comb.x, cur.x); comb.y = __fadd_rn(comb.y, cur.y);
                 }
-                sm.prev[c] = prev;
+                comb.x = __fdiv_rn(comb.x, static_cast<float>(a.spread));
+                comb.y = __fdiv_rn(comb.y, static_cast<float>(a.spread));
+                const float mag = cabs_d(comb);
+                sm.nrm[d * kMaxCar + c] = (mag > 0.0001f) ? make_float2(__fdiv_rn(comb.x, mag), __fdiv_rn(comb.y, mag))
+                                                          : make_float2(1.0f, 0.0f);
+                mags[(ds0 + d) * kMaxCar + c] = mag;
             }
+            __syncthreads();
+            for (int p = tid; p < ds_n * C; p += kDemodThreads) {
+                const int d = p / C, c = p - d * C;
+                const float2 nrm = sm.nrm[d * kMaxCar + c];
+                const float2 prev = (d == 0) ? sm.prev[c] : sm.nrm[(d - 1) * kMaxCar + c];
+                // diff = normalized * conj(prev)
+                const float2 diff = make_float2(__fsub_rn(__fmul_rn(nrm.x, prev.x), __fmul_rn(nrm.y, -prev.y)),
+                                                __fadd_rn(__fmul_rn(nrm.x, -prev.y), __fmul_rn(nrm.y, prev.x)));
+                const float phase = atan2_rn(diff.y, diff.x);
+                const float PI = static_cast<float>(M_PI);
+                float err;
+                if (a.bits == 2) {
+                    const float shifted = phase - PI / 4.0f;
+                    const float idx = roundf(shifted / (PI / 2.0f));
+                    const float ideal = idx * PI / 2.0f + PI / 4.0f;
+                    err = phase - ideal;
+                } else {
+                    const float idx = roundf(phase / PI);
+                    const float ideal = idx * PI;
+                    err = phase - ideal;
+                }
+                while (err > PI) err -= 2.0f * PI;
+                while (err < -PI) err += 2.0f * PI;
+                const int o = (ds0 + d) * kMaxCar + c;
+                phases[o] = phase; errs[o] = err * err;
+            }
+            __syncthreads();
+            if (tid < C && ds_n > 0) sm.prev[tid] = sm.nrm[(ds_n - 1) * kMaxCar + tid];
             __syncthreads();
         }
 
@@ -557,7 +574,17 @@ extern "C" int ria_mcdpsk_process_batch_at_dev(ria_ctx* ctx, const ria_mcdpsk_co
     float2* d_bph = reinterpret_cast<float2*>(base + a1);
     float* d_corr = reinterpret_cast<float*>(base + a1 + a2);
 
-    const size_t smem = demod_smem_bytes(C);
+    size_t smem = demod_smem_bytes(C);
+    int stats_smem_off = 0;
+    {
+        // per-frame mags / phases / errs in shared memory when two CTAs still fit on an SM
+        const size_t off = (smem + 15) & ~size_t(15);
+        const size_t with_stats = off + static_cast<size_t>(3) * max_ds * kMaxCar * sizeof(float);
+        if (2 * (with_stats + 1024) <= ctx->smem_per_sm && with_stats <= ctx->smem_optin) {
+            stats_smem_off = static_cast<int>(off);
+            smem = with_stats;
+        }
+    }
     RIA_CUDA(ctx, cudaFuncSetAttribute(mcdpsk_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     RIA_CUDA(ctx, cudaFuncSetAttribute(mcdpsk_demod_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
@@ -585,7 +612,7 @@ extern "C" int ria_mcdpsk_process_batch_at_dev(ria_ctx* ctx, const ria_mcdpsk_co
         }
         a.cfo_hz = cfo_hz_dev; a.n_frames = n;
         a.llr = llr_dev; a.llr_stride = llr_stride; a.n_llr = n_llr_dev; a.fading = fading_dev; a.cfo_out = cfo_out_dev;
-        a.scratch = d_scr; a.max_ds = max_ds; a.mixer_g = t->mixer;
+        a.scratch = d_scr; a.max_ds = max_ds; a.mixer_g = t->mixer; a.stats_smem_off = stats_smem_off;
         a.carriers = C; a.bits = static_cast<int>(cfg->bits_per_symbol); a.spread = static_cast<int>(cfg->spreading);
         a.training = static_cast<int>(cfg->training_symbols);
         a.counter = ctx->work_counter + 2;
