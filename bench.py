@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 
 KK_LDPC, KK_OFDM_DEMOD, KK_FRAME_STATUS, KK_AWGN = 0, 1, 2, 3
 KK_OFDM_FFT, KK_OFDM_CARRIER, KK_OFDM_PHASE = 11, 12, 13
+KK_LDPC_RETRY, KK_FRAME_REPAIR = 14, 15
 KK_MCDPSK, KK_CHIRP_SYNC, KK_CHASE, KK_MCDPSK_CFO = 4, 6, 7, 9
 
 
@@ -149,7 +150,8 @@ class OfdmQam64Workload:
                 "channel": f"AWGN {self.SNR_DB} dB, generated on the device (Philox), "
                            f"{self.POOL} distinct TX frames x per-frame noise",
                 "chain": "mix+CFO+CP+FFT1024+LTS/pilot est+MMSE+QAM64 LLR -> frame/channel "
-                         "de-interleave -> 4x LDPC R3/4 (0.9375, 60 it) -> header+CRC16",
+                         "de-interleave -> complete v2::decodeFixedFrame (4x LDPC R3/4 0.9375/60 it, retry ladder and "
+                         "false-positive repair armed: RIA_DECODE_FULL) -> header+CRC16",
                 "l2": "input batch (53.8 GB at 1M frames) exceeds the 126 MB L2; no flush needed"}
 
     def setup(self, ctx, device, rank, world):
@@ -167,6 +169,8 @@ class OfdmQam64Workload:
         self.first_id = rank * self.n                       # global frame ids: sharding-independent noise
         self.samples = sim.awgn_batch(self.pool_dev, self.n, self.SNR_DB, seed=2026,
                                       first_frame_id=self.first_id, ctx=ctx)
+        import ria_b200
+        ctx.set_decode_flags(ria_b200.DECODE_FULL)          # the reference's complete decodeFixedFrame
         self.chain = ofdm.OfdmRxChain(self.cfg(), self.RATE, True, ctx)
         self.out = None
         torch.cuda.synchronize()
@@ -195,6 +199,9 @@ class OfdmQam64Workload:
             KK_OFDM_DEMOD: ("ofdm_presynced_kernel (residual-CFO re-run frames only)", 0),
             KK_LDPC: ("ldpc_decode_kernel", self.n * (llr + 4 * (61 + 5))),
             KK_FRAME_STATUS: ("frame_status_kernel", self.n * (4 * 72 + 4 * 5 + 40)),
+            KK_LDPC_RETRY: ("ldpc_fail_list_kernel + ldpc_retry_kernel (retry ladder, failed frames only)", self.n * 4),
+            KK_FRAME_REPAIR: ("frame_repair_list_kernel + frame_repair_kernel (false-positive repair, invalid frames only)",
+                              self.n * (4 + 4 * 60)),
         }
 
     def counters(self):
@@ -250,7 +257,8 @@ class OfdmQam64Workload:
 
 def _cpu_ofdm_worker(args):
     """One process per core: make its own received frames (untimed), then time the reference's
-    processPresynced + first-pass decodeFixedFrame + parseHeader on them."""
+    processPresynced + the complete v2::decodeFixedFrame (first pass, retry ladder, false-positive repair) +
+    parseHeader on them."""
     _, n_frames, seed, kind = args
     from oracle.bindings import ModemConfig, Ref
     wl = OfdmQam64Workload(n_frames)
@@ -269,7 +277,7 @@ def _cpu_ofdm_worker(args):
     t0 = time.perf_counter()
     for rx in frames:
         r = ref.ofdm_process_presynced(cfg, rx, 0.0, 0.0)
-        data, cw_ok, _ = ref.frame_decode_first_pass(r["soft"], wl.RATE, True, bps)
+        data, cw_ok = ref.decode_fixed_frame_full(r["soft"], wl.RATE, True, bps)
         st = ref.parse_header(data)
         ok += int(cw_ok.all() and st.frame_crc_ok)
     return time.perf_counter() - t0, ok
@@ -295,7 +303,7 @@ def cpu_baseline_ofdm(wl, frames_per_core):
     return {"value": rate, "unit": "frames/s", "cores": cores, "kind": "reference",
             "sample": f"{frames_per_core} frames per core x {cores} cores "
                       f"({ok}/{frames_per_core * cores} decoded with valid CRC), reference "
-                      f"processPresynced + first-pass decodeFixedFrame + parseHeader, one process "
+                      f"processPresynced + complete decodeFixedFrame + parseHeader, one process "
                       f"per core, {wall:.1f} s wall, {max(b for b, _ in res):.1f} s max busy"}
 
 

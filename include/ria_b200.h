@@ -251,6 +251,15 @@ int ria_ofdm_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg, int rate,
                             const float* cfo_hz, const float* phase, int64_t n_frames,
                             uint8_t* data, ria_frame_status* status, float* snr_db);
 
+/* Batched fec::BurstInterleaver::deinterleave (src/fec/burst_interleaver.cpp:39-78), applied by
+ * StreamingDecoder::finalizeBurstGroup (src/gui/modem/streaming_decoder.cpp:3209-3216) to the soft bits of
+ * a burst group before decodeFrame.  physical_dev [n_groups][group_size][in_stride] -> logical_dev
+ * [n_groups][group_size][out_stride], 2592 soft bits per frame; group_size < 2 copies (:43).  Soft bits past
+ * 2592 in a row are not touched.  Strides multiples of 4, buffers 16-byte aligned, not in place. */
+int ria_burst_deinterleave_batch_dev(ria_ctx* ctx, const float* physical_dev, int32_t in_stride,
+                                     int32_t group_size, int64_t n_groups,
+                                     float* logical_dev, int32_t out_stride);
+
 /* ---- synchronisation ------------------------------------------------------------------------- */
 /* sync::ZCConfig (src/sync/zc_sync.hpp:61-108) */
 typedef struct {

@@ -214,6 +214,7 @@ class Ref:
         L.ref_encode_fixed_frame.restype = C.c_int
         L.ref_frame_decode_first_pass.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _u8p, _u8p, _i32p]
         L.ref_decode_fixed_frame_full.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _u8p]
+        L.ref_burst_deinterleave.argtypes = [_f32p, C.c_int, _f32p]
         L.ref_ladder_perturb.argtypes = [_f32p, C.c_int, C.c_uint, C.c_float, C.c_int, _f32p]
         L.ref_parse_header.argtypes = [_u8p, C.c_int, C.POINTER(FrameStatus)]
         L.ref_crc16.argtypes = [_u8p, C.c_int]
@@ -419,6 +420,13 @@ class Ref:
         ok = np.zeros(4, np.uint8)
         self.lib.ref_decode_fixed_frame_full(soft, soft.size, rate, int(use_ci), bps, data, ok)
         return data, ok
+
+    def burst_deinterleave(self, physical) -> np.ndarray:
+        """fec::BurstInterleaver::deinterleave on [n, 2592] soft bits."""
+        physical = np.ascontiguousarray(physical, dtype=np.float32)
+        out = np.empty_like(physical)
+        self.lib.ref_burst_deinterleave(physical, physical.shape[0], out)
+        return out
 
     def ladder_perturb(self, llr, seed: int, sigma: float, kind: int) -> np.ndarray:
         """std::mt19937(seed) + std::normal_distribution<float>(0, sigma) perturbation (frame_v2.cpp:1426-1542)."""

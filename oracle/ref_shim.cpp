@@ -32,6 +32,7 @@
 #include <cstring>
 #include <memory>
 #include <random>
+#include "fec/burst_interleaver.hpp"
 #include <vector>
 
 using namespace ultra;
@@ -272,6 +273,14 @@ void ref_ladder_perturb(const float* in, int n, unsigned seed, float sigma, int 
         }
         out[i] = llr;
     }
+}
+
+// fec::BurstInterleaver::deinterleave (src/fec/burst_interleaver.cpp:39-78): phys / out are [n][2592]
+void ref_burst_deinterleave(const float* phys, int n, float* out) {
+    std::vector<std::vector<float>> p(n);
+    for (int i = 0; i < n; ++i) p[i].assign(phys + i * 2592, phys + (i + 1) * 2592);
+    auto l = fec::BurstInterleaver::deinterleave(p);
+    for (int i = 0; i < n; ++i) std::memcpy(out + i * 2592, l[i].data(), 2592 * sizeof(float));
 }
 
 // v2::parseHeader (frame_v2.cpp:1195-1253) + DataFrame::deserialize frame CRC (:555-600)

@@ -108,7 +108,7 @@ def main():
             torch.cuda.empty_cache()
 
         # ---- complete decodeFixedFrame (first pass / + retry ladder / + false-positive repair) on degraded frames ----
-        for mod, rate, snr, label in ((ofdm.QPSK, 2, 1.0, "QPSK R1/2 AWGN 1 dB"), (ofdm.QAM64, 4, 18.5, "QAM64 R3/4 AWGN 18.5 dB")):
+        for mod, rate, snr, label in ((ofdm.QPSK, 2, -9.0, "QPSK R1/2 AWGN -9 dB"), (ofdm.QAM64, 4, 18.5, "QAM64 R3/4 AWGN 18.5 dB")):
             cfg = ofdm.ModemConfig.high_throughput(mod) if mod == ofdm.QAM64 else ofdm.ModemConfig.for_waveform(mod, rate)
             pool, _ = txsynth.make_frame_pool(cfg, rate, 8, seed=5)
             n = 16384

@@ -61,6 +61,7 @@ _SIGNATURES = {
                                       _vp, _vp, _vp]),
     "ria_ofdm_rx_frames_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _i64,
                                        _vp, _vp, _vp]),
+    "ria_burst_deinterleave_batch_dev": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _i32]),
     "ria_zc_config_default": (_i32, [_vp]),
     "ria_zc_detect_batch_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _f32, C.c_uint32, _i64, _vp]),
     "ria_ofdm_data_sync_batch_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _f32, _i64, _vp]),

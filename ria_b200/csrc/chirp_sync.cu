@@ -277,7 +277,7 @@ struct PeakArgs {
 // FADDs, operands prefetched, no memory latency on the chain), the other warps square and stage
 // tile k+1 from global memory and write the prefix values of tile k-1 back, all coalesced.
 // Block-collective; ends with a barrier.
-constexpr int kPrefixTile = 2048;
+constexpr int kPrefixTile = 1024;
 __device__ __forceinline__ void prefix_chain(float* tile, int n, float& acc) {
     float4* t4 = reinterpret_cast<float4*>(tile);
     const int n8 = n >> 3;
@@ -405,7 +405,11 @@ __device__ void td_detect(const float* s, int len, const float2* tmpl, int CL, f
     *out_pos = (best >= threshold) ? pos : -1;
 }
 
-__global__ void __launch_bounds__(256, 7)      // 7 x 148 = 1036 >= one 1024-window slice in a single wave
+// The kernel's time is the latency of the serial prefix chains (~170 k dependent FADDs per window), so what
+// matters is how many windows are in flight: 128-thread CTAs with 1024-element tiles fit 14 per SM,
+// 14 x 148 = 2072 >= one 2048-window slice in a single wave.
+constexpr int kPeakThreads = 128;
+__global__ void __launch_bounds__(kPeakThreads, 14)
 chirp_peak_kernel(const PeakArgs a) {
     __shared__ float red_v[256];
     __shared__ int red_i[256];
@@ -590,7 +594,7 @@ extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_con
         a.chirp_len = t->chirp_len; a.gap = t->gap;
         a.sample_rate = cfg->sample_rate; a.f_start = cfg->f_start; a.f_end = cfg->f_end; a.duration_ms = cfg->duration_ms;
         a.out = out_dev + off;
-        chirp_peak_kernel<<<batch, 256, 0, s>>>(a);
+        chirp_peak_kernel<<<batch, kPeakThreads, 0, s>>>(a);
         ctx->launches += 10;
     }
     time_end(ctx);

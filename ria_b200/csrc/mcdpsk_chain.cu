@@ -78,7 +78,7 @@ extern "C" int ria_mcdpsk_rx_frames_dev(ria_ctx* ctx, const ria_mcdpsk_config* c
     unsigned char* d_first = base + b_llr + 3 * b_i;
 
     // ---- acquisition: dual chirp, slices bounded by the 3 MiB of spectra each window needs ----
-    const int64_t slice = 1024;
+    const int64_t slice = 2048;      // one wave of the peak kernel (14 CTAs x 148 SMs); 7 GB of spectra
     for (int64_t off = 0; off < n_frames; off += slice) {
         const int64_t n = (n_frames - off < slice) ? (n_frames - off) : slice;
         rc = ria_chirp_detect_dual_batch_dev(ctx, chirp, samples_dev + off * row_stride, row_stride, sync_window,

@@ -192,6 +192,22 @@ class LDPCDecoder:
         return self.decodeSoft(np.where(bits == 1, -6.0, 6.0).astype(np.float32))
 
 
+def burst_deinterleave_batch(physical: torch.Tensor, ctx: Optional[Context] = None) -> torch.Tensor:
+    """fec::BurstInterleaver::deinterleave (src/fec/burst_interleaver.cpp:39-78) for a batch of burst
+    groups: physical CUDA fp32 [n_groups, N, >= 2592] -> logical [n_groups, N, 2592]."""
+    if not (isinstance(physical, torch.Tensor) and physical.is_cuda and physical.dtype == torch.float32 and physical.dim() == 3):
+        raise ValueError("physical must be a CUDA fp32 [n_groups, N, >= 2592] tensor")
+    if physical.shape[2] < 2592:
+        raise ValueError("BurstInterleaver::deinterleave: soft bits size mismatch")
+    physical = physical.contiguous()
+    g, n, stride = physical.shape
+    out = torch.empty((g, n, 2592), dtype=torch.float32, device=physical.device)
+    ctx = ctx or default_context()
+    ctx.set_stream(torch.cuda.current_stream(physical.device))
+    ctx.check(lib().ria_burst_deinterleave_batch_dev(ctx.handle, physical.data_ptr(), stride, n, g, out.data_ptr(), 2592))
+    return out
+
+
 def ladder_perturb_batch(llr: torch.Tensor, attempt: int, ctx: Optional[Context] = None) -> torch.Tensor:
     """Soft bits that attempt `attempt` (1..38) of decodeFixedFrame's retry ladder decodes
     (src/protocol/frame_v2.cpp:1409-1542).  llr: CUDA fp32 [n_cw, 648]."""

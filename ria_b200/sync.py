@@ -118,7 +118,7 @@ class ChirpSync:
             self._ctx = default_context()
         return self._ctx
 
-    def detect_dual_batch(self, samples: torch.Tensor, threshold: float = 0.15, max_batch: int = 256) -> torch.Tensor:
+    def detect_dual_batch(self, samples: torch.Tensor, threshold: float = 0.15, max_batch: int = 2048) -> torch.Tensor:
         """detectDualChirp for every row of samples (CUDA fp32 [n, window <= 131072]).
 
         Each window needs 3 MiB of scratch for the 131072-point spectra, so the batch is walked

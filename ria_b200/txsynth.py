@@ -227,15 +227,23 @@ def ofdm_modulate_frame(cfg: ModemConfig, coded_bits: np.ndarray, output_scale: 
 
 def make_frame_pool(cfg: ModemConfig, rate: int, n_frames: int, seed: int = 1,
                     use_channel_interleave: bool = True):
-    """n_frames distinct clean TX frames -> (samples fp32 [n, frame_len], frame bytes list)."""
+    """n_frames distinct clean TX frames -> (samples fp32 [n, frame_len], frame bytes list).
+
+    Payloads are re-drawn until none of the codeword chunks 1..3 of the frame starts with 0xD5: the
+    reference's CodewordStatus::reassemble (src/protocol/frame_v2.cpp:974) takes such a chunk for a
+    DATA_CW_MARKER, and its complete decodeFixedFrame then drops the frame however clean the channel
+    (tests/test_ldpc_retry_gpu.py pins that behaviour); a throughput workload should not contain them."""
     rng = np.random.default_rng(seed)
     k, _, _ = fec.code_params(rate)
     bpc = k // 8
     bps = cfg.getDataCarriers() * getBitsPerSymbol(cfg.modulation)
     frames, raw = [], []
     for i in range(n_frames):
-        payload = rng.integers(0, 256, size=4 * bpc - 19, dtype=np.uint8).tobytes()
-        fr = make_data_frame("K1ABC", "W2XYZ", i & 0xFFFF, payload)
+        while True:
+            payload = rng.integers(0, 256, size=4 * bpc - 19, dtype=np.uint8).tobytes()
+            fr = make_data_frame("K1ABC", "W2XYZ", i & 0xFFFF, payload)
+            if all(fr[c * bpc] != 0xD5 for c in (1, 2, 3) if c * bpc < len(fr)):
+                break
         bits = encode_fixed_frame_bits(fr, rate, use_channel_interleave, bps)
         frames.append(ofdm_modulate_frame(cfg, bits))
         raw.append(fr)

@@ -85,8 +85,41 @@ def ofdm_golden(ref, out_dir):
     print("ofdm_golden.npz written")
 
 
+def frame_golden(ref, out_dir):
+    """Complete v2::decodeFixedFrame (first pass + retry ladder + false-positive repair) on degraded
+    frames, plus the burst de-interleaver: soft bits in, the reference's decoded flags / bytes out."""
+    from oracle.bindings import BYTES_PER_CW
+    rng = np.random.default_rng(20261019)
+    out = {}
+    for name, rate, esn0, bps in (("r14", R1_4, -1.0, 53), ("r12", R1_2, 2.6, 106), ("r23", R2_3, 4.6, 176), ("r34", R3_4, 7.0, 264)):
+        bpc = BYTES_PER_CW[rate]
+        n = 20
+        soft = np.empty((n, 2592), np.float16)
+        data = np.empty((n, 4 * bpc), np.uint8)
+        ok = np.empty((n, 4), np.uint8)
+        for i in range(n):
+            payload = rng.integers(0, 256, size=4 * bpc - 19 - int(rng.integers(0, 8)), dtype=np.uint8)
+            if i == 3:
+                payload[bpc - 17] = 0xD5                     # DATA_CW_MARKER quirk of reassemble() (frame_v2.cpp:974)
+            frame = ref.make_data_frame("K1ABC", "W2XYZ", i, payload)
+            coded = ref.encode_fixed_frame(frame, rate, True, bps)
+            llr = awgn_llrs(np.unpackbits(coded)[:2592], esn0 + (i % 4) * 0.5, rng)
+            soft[i] = llr.astype(np.float16)                 # stored as fp16 (exactly representable inputs keep the file small)
+            data[i], ok[i] = ref.decode_fixed_frame_full(soft[i].astype(np.float32), rate, True, bps)
+        out[f"{name}_soft"], out[f"{name}_data"], out[f"{name}_ok"] = soft, data, ok
+        out[f"{name}_rate"], out[f"{name}_bps"] = np.int32(rate), np.int32(bps)
+        print(name, "frames decoded by the reference:", int(ok.all(axis=1).sum()), "of", n)
+    phys = rng.standard_normal((4, 2592)).astype(np.float16)
+    out["burst_physical"] = phys
+    out["burst_logical"] = ref.burst_deinterleave(phys.astype(np.float32)).astype(np.float16)
+    np.savez_compressed(os.path.join(out_dir, "frame_golden.npz"), **out)
+    print("frame_golden.npz written")
+
+
 if __name__ == "__main__":
     ref = Ref()
+    if "frame" in sys.argv[1:] or len(sys.argv) == 1:
+        frame_golden(ref, HERE)
     if "ldpc" in sys.argv[1:] or len(sys.argv) == 1:
         ldpc_golden(ref, HERE)
     if "ofdm" in sys.argv[1:] or len(sys.argv) == 1:

@@ -158,3 +158,21 @@ def test_decode_fixed_frame_full_matches_reference(ctx, ref, rate, esn0, bps):
           f"repair: {int((st['fp_repair'] == 1).sum())} repaired, {int((st['fp_repair'] == 2).sum())} given up, "
           f"{int(st['all_ok'].sum())}/{n} frames decoded")
     assert int((st["fp_repair"] != 0).sum()) + int((st["ladder_cw_mask"] != 0).sum()) > 0
+
+
+def test_decode_fixed_frame_full_against_committed_golden(ctx):
+    """tests/golden/frame_golden.npz: outputs of the unmodified reference's complete decodeFixedFrame and
+    BurstInterleaver::deinterleave on seeded soft bits (tests/golden/make_golden.py); no reference needed."""
+    import os
+    from ria_b200 import fec, ofdm
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frame_golden.npz"))
+    for name in ("r14", "r12", "r23", "r34"):
+        soft = g[f"{name}_soft"].astype(np.float32)
+        rate, bps = int(g[f"{name}_rate"]), int(g[f"{name}_bps"])
+        data, status = ofdm.decode_fixed_frame_batch(torch.from_numpy(soft).cuda(), rate, True, bps, ctx,
+                                                     retry_ladder=True, fp_repair=True)
+        st = ofdm.status_array(status)
+        assert np.array_equal(st["cw_ok"], g[f"{name}_ok"]), name
+        assert np.array_equal(data.cpu().numpy(), g[f"{name}_data"]), name
+    phys = torch.from_numpy(g["burst_physical"].astype(np.float32)[None]).cuda()
+    assert np.array_equal(fec.burst_deinterleave_batch(phys, ctx).cpu().numpy()[0], g["burst_logical"].astype(np.float32))
