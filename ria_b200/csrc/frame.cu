@@ -38,15 +38,21 @@ int recommended_ldpc_iterations(int rate) {
 namespace {
 int recommended_iterations(int rate) { return recommended_ldpc_iterations(rate); }
 
-__device__ __forceinline__ uint16_t crc16_dev(const uint8_t* d, int len) {
-    uint16_t crc = 0xFFFF;
-    for (int i = 0; i < len; ++i) {
-        crc ^= static_cast<uint16_t>(static_cast<uint16_t>(d[i]) << 8);
+// CRC-16/CCITT-FALSE (frame_v2.cpp:115-128), one table lookup per byte; the 256-entry table is built
+// in shared memory by the CTA (entry b = the register after byte b from a zero start).
+__device__ __forceinline__ void crc16_build_table(uint16_t* tab) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+        unsigned r = static_cast<unsigned>(b) << 8;
 #pragma unroll
-        for (int b = 0; b < 8; ++b)
-            crc = (crc & 0x8000) ? static_cast<uint16_t>((crc << 1) ^ 0x1021) : static_cast<uint16_t>(crc << 1);
+        for (int i = 0; i < 8; ++i) r = ((r & 0x8000u) ? ((r << 1) ^ 0x1021u) : (r << 1)) & 0xFFFFu;
+        tab[b] = static_cast<uint16_t>(r);
     }
-    return crc;
+    __syncthreads();
+}
+__device__ __forceinline__ uint16_t crc16_dev(const uint16_t* __restrict__ tab, const uint8_t* d, int len) {
+    unsigned crc = 0xFFFFu;
+    for (int i = 0; i < len; ++i) crc = ((crc << 8) & 0xFFFFu) ^ tab[((crc >> 8) ^ d[i]) & 0xFFu];
+    return static_cast<uint16_t>(crc);
 }
 
 __device__ __forceinline__ bool is_control_frame(uint8_t t) {
@@ -59,6 +65,8 @@ __global__ void frame_status_kernel(const uint8_t* __restrict__ info, const uint
                                     const int32_t* __restrict__ iters, const uint8_t* __restrict__ attempt,
                                     const uint8_t* __restrict__ repair, long long n_frames, int bpc,
                                     uint8_t* __restrict__ data, ria_frame_status* __restrict__ status) {
+    __shared__ uint16_t crc_tab[256];
+    crc16_build_table(crc_tab);
     const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (f >= n_frames) return;
     uint8_t* out = data + f * 4 * bpc;
@@ -89,12 +97,12 @@ __global__ void frame_status_kernel(const uint8_t* __restrict__ info, const uint
             st.dst_hash = (static_cast<uint32_t>(h[9]) << 16) | (static_cast<uint32_t>(h[10]) << 8) | h[11];
             if (is_control_frame(st.type)) {
                 const uint16_t rx = static_cast<uint16_t>((h[18] << 8) | h[19]);
-                if (rx == crc16_dev(h, 18)) { st.header_valid = 1; st.total_cw = 1; st.payload_len = 0; }
+                if (rx == crc16_dev(crc_tab, h, 18)) { st.header_valid = 1; st.total_cw = 1; st.payload_len = 0; }
             } else {
                 st.total_cw = h[12];
                 st.payload_len = static_cast<uint16_t>((h[13] << 8) | h[14]);
                 const uint16_t rx = static_cast<uint16_t>((h[15] << 8) | h[16]);
-                if (rx == crc16_dev(h, 15)) st.header_valid = 1;
+                if (rx == crc16_dev(crc_tab, h, 15)) st.header_valid = 1;
                 // frame CRC over header + payload (DataFrame::deserialize :590-596); needs every
                 // codeword that carries part of the frame
                 const int expected = 17 + st.payload_len + 2;
@@ -103,7 +111,7 @@ __global__ void frame_status_kernel(const uint8_t* __restrict__ info, const uint
                     for (int c = 0; c < 4; ++c) if (c * bpc < expected && !st.cw_ok[c]) have = false;
                     if (have) {
                         const uint16_t frx = static_cast<uint16_t>((h[expected - 2] << 8) | h[expected - 1]);
-                        st.frame_crc_ok = (frx == crc16_dev(h, expected - 2)) ? 1 : 0;
+                        st.frame_crc_ok = (frx == crc16_dev(crc_tab, h, expected - 2)) ? 1 : 0;
                     }
                 }
             }

@@ -65,6 +65,10 @@ ldpc_decode_kernel(const float* __restrict__ llr_g, long long n_cw, const LdpcGa
     }
     __syncthreads();
 
+    // The clean-codeword shortcut (ldpc_core.cuh) costs one parity pass; at an operating point where the
+    // channel hard decisions are rarely a codeword it is switched off after 16 tries with < 25 % hits
+    // (warp-uniform, results do not depend on it).
+    int sc_tries = 0, sc_hits = 0;
     for (;;) {
         long long cw;
         {
@@ -74,8 +78,11 @@ ldpc_decode_kernel(const float* __restrict__ llr_g, long long n_cw, const LdpcGa
         }
         if (cw >= n_cw) break;
         ldpc_core::gather_codeword(llr_g, cw, gather, llr, lane);
-        bool success; int iters;
-        ldpc_core::decode_codeword(llr, tot, msg, chk_var, var_slot, k, m, dv_max, max_iter, factor, lane, success, iters);
+        bool success, took; int iters;
+        const bool try_sc = sc_tries < 16 || 4 * sc_hits >= sc_tries;
+        ldpc_core::decode_codeword(llr, tot, msg, chk_var, var_slot, k, m, dv_max, max_iter, factor, lane, success, iters,
+                                   try_sc, &took);
+        if (try_sc) { ++sc_tries; sc_hits += took ? 1 : 0; }
         ldpc_core::pack_info(tot, k, info_g + cw * info_stride, info_stride, lane);
         if (lane == 0) {
             ok_g[cw] = success ? 1 : 0;

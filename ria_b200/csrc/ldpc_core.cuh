@@ -119,9 +119,37 @@ struct DecodeSmem {
 // parity).  On return tot[] / msg slot 7 hold the totals the hard decision is taken from.
 __device__ __forceinline__ void decode_codeword(float* llr, float* tot, float4* msg, const uint4* chk_var,
                                                 const uint16_t* var_slot, int k, int m, int dv_max,
-                                                int max_iter, float factor, int lane, bool& success, int& iters) {
+                                                int max_iter, float factor, int lane, bool& success, int& iters,
+                                                bool try_shortcut = false, bool* took_shortcut = nullptr) {
     __syncwarp();
     for (int j = lane; j < k; j += 32) tot[j] = llr[j];
+    // Clean codeword shortcut.  If the channel hard decisions already satisfy every check, each
+    // check-to-variable message of the first iteration carries the sign of "the other bits' parity",
+    // which is the variable's own sign, so no total changes sign: the reference stops after its first
+    // iteration with exactly these bits and reports 0 iterations (ldpc_decoder.cpp:226-238).  The first
+    // check / variable update is skipped; the result (bits, success, count) is the same.  max_iter = 0
+    // runs no iteration and never succeeds (:170), so the shortcut needs max_iter >= 1.
+    if (took_shortcut) *took_shortcut = false;
+    if (try_shortcut && max_iter >= 1) {
+        bool bad = false;
+        for (int i = lane; i < m; i += 32) {
+            const uint4 vi = chk_var[i];
+            const int cnt = vi.w >> 16;
+            const unsigned idx[6] = {vi.x & 0xFFFFu, vi.x >> 16, vi.y & 0xFFFFu,
+                                     vi.y >> 16,     vi.z & 0xFFFFu, vi.z >> 16};
+            unsigned par = (llr[k + i] < 0.0f) ? 1u : 0u;
+#pragma unroll
+            for (int d = 0; d < 6; ++d)
+                if (d < cnt) par ^= (llr[idx[d]] < 0.0f) ? 1u : 0u;
+            bad |= (par != 0);
+        }
+        if (!__any_sync(0xffffffffu, bad)) {
+            success = true; iters = 0;
+            if (took_shortcut) *took_shortcut = true;
+            __syncwarp();
+            return;
+        }
+    }
     for (int i = lane; i < m; i += 32) {
         msg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         msg[m + i] = make_float4(0.f, 0.f, 0.f, llr[k + i]);   // slot 7 = parity total
