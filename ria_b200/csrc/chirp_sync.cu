@@ -198,6 +198,93 @@ fft_stage_kernel(const StageArgs a) {
     }
 }
 
+// Forward stage 3, the two template products and inverse stage 3 in one kernel.  Forward and inverse use
+// mirrored stage orders, so the innermost pair works on the same tiles (16 rows of 64 contiguous bins):
+// the products never leave the SM, which removes one write and one read of both 1 MB product spectra
+// (4 of ~18 MB of HBM traffic per window) and two launches.  Output: prod_up / prod_dn hold the result
+// of inverse stage 3, ready for inverse stages 2 and 1.
+__global__ void __launch_bounds__(kFftThreads)
+fft_stage3_fused_kernel(const StageArgs a) {
+    constexpr int L = 64, T = 16, kRow = 72;
+    __shared__ float2 buf[T * kRow];
+    __shared__ float2 pu[T * kRow];                    // products, natural order inside a row
+    __shared__ float2 pd[T * kRow];
+    __shared__ float2 wl[L];                           // w_64^m (forward); the inverse uses the conjugate
+    const int tid = threadIdx.x;
+    const size_t f = blockIdx.y;
+    const float2* x = a.data + f * kN;
+    if (tid < L) {
+        double s, c;
+        sincospi(-2.0 * tid / L, &s, &c);
+        wl[tid] = make_float2(static_cast<float>(c), static_cast<float>(s));
+    }
+    __syncthreads();
+    for (int qq = 0; qq < kTilesPerCta; ++qq) {
+        const int q = blockIdx.x * kTilesPerCta + qq;
+        const size_t elem0 = static_cast<size_t>(q) * T * kC;
+        const int n2 = tid & 7, t = tid >> 3;          // pass-1 role
+        const int k1 = tid & 7;                        // pass-2 role (same t)
+        // ---- forward pass 1 ----
+        {
+            float2 v[8];
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) v[n1] = x[elem0 + static_cast<size_t>(8 * n1 + n2) + static_cast<size_t>(t) * kC];
+            dft8<false>(v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) buf[t * kRow + k * 9 + n2] = (k == 0) ? v[0] : cmulf(v[k], wl[n2 * k]);
+        }
+        __syncthreads();
+        // ---- forward pass 2 + template products ----
+        {
+            float2 v[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) v[m] = buf[t * kRow + k1 * 9 + m];
+            dft8<false>(v);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) {
+                const int i = k1 + 8 * k2;
+                const size_t idx = elem0 + static_cast<size_t>(i) + static_cast<size_t>(t) * kC;
+                pu[t * kRow + i] = cmulf(v[k2], a.tmpl_up[idx]);
+                pd[t * kRow + i] = cmulf(v[k2], a.tmpl_dn[idx]);
+            }
+        }
+        __syncthreads();
+        // ---- inverse stage 3 on both products ----
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+            const float2* prod = which ? pd : pu;
+            float2* out = (which ? a.prod_dn : a.prod_up) + f * kN;
+            {
+                float2 v[8];
+#pragma unroll
+                for (int n1 = 0; n1 < 8; ++n1) v[n1] = prod[t * kRow + 8 * n1 + n2];
+                dft8<true>(v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float2 w = wl[n2 * k]; w.y = -w.y;
+                    buf[t * kRow + k * 9 + n2] = (k == 0) ? v[0] : cmulf(v[k], w);
+                }
+            }
+            __syncthreads();
+            {
+                float2 v[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = buf[t * kRow + k1 * 9 + m];
+                dft8<true>(v);
+#pragma unroll
+                for (int k2 = 0; k2 < 8; ++k2) {
+                    const int i = k1 + 8 * k2;
+                    const size_t idx = elem0 + static_cast<size_t>(i) + static_cast<size_t>(t) * kC;
+                    const int row = static_cast<int>(idx / kC);                // row = ka*B + kb
+                    float2 w = a.tw2[(row % kB) * kC + i]; w.y = -w.y;
+                    out[idx] = cmulf(v[k2], w);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 template <bool INV>
 void fft_stages(const StageArgs& a, int batch, cudaStream_t s) {
     const dim3 g1(kB * kC / 32 / kTilesPerCta, batch), g2(kA * kC / 16 / kTilesPerCta, batch), g3(kA * kB / 16 / kTilesPerCta, batch);
@@ -221,6 +308,27 @@ void fft_inverse(float2* d, int batch, const ChirpTablesDev& t, cudaStream_t s) 
     a.data = d; a.tw1 = t.tw1; a.tw2 = t.tw2; a.scale = 1.0f / kN;
     fft_stages<true>(a, batch, s);
 }
+// forward transform of real rows -> template products -> inverse stage 3 (fused), then inverse stages 2, 1:
+// leaves the two correlations in pu / pd
+void chirp_correlate(const float* samples, long long stride, int n_in, float2* work, float2* pu, float2* pd,
+                     int batch, const ChirpTablesDev& t, cudaStream_t s) {
+    StageArgs a{};
+    a.data = work; a.real_in = samples; a.real_stride = stride; a.n_in = n_in;
+    a.prod_up = nullptr; a.prod_dn = nullptr; a.tmpl_up = t.tmpl_up; a.tmpl_dn = t.tmpl_dn;
+    a.tw1 = t.tw1; a.tw2 = t.tw2; a.scale = 1.0f;
+    const dim3 g1(kB * kC / 32 / kTilesPerCta, batch), g2(kA * kC / 16 / kTilesPerCta, batch), g3(kA * kB / 16 / kTilesPerCta, batch);
+    fft_stage_kernel<1, false><<<g1, kFftThreads, 0, s>>>(a);
+    fft_stage_kernel<2, false><<<g2, kFftThreads, 0, s>>>(a);
+    a.prod_up = pu; a.prod_dn = pd;
+    fft_stage3_fused_kernel<<<g3, kFftThreads, 0, s>>>(a);
+    for (float2* d : {pu, pd}) {
+        StageArgs b{};
+        b.data = d; b.tw1 = t.tw1; b.tw2 = t.tw2; b.scale = 1.0f / kN;
+        fft_stage_kernel<2, true><<<g2, kFftThreads, 0, s>>>(b);
+        fft_stage_kernel<1, true><<<g1, kFftThreads, 0, s>>>(b);
+    }
+}
+
 // forward transform of real rows with the two template products as output
 void fft_forward_real_to_products(const float* samples, long long stride, int n_in, float2* work, float2* pu, float2* pd,
                                   int batch, const ChirpTablesDev& t, cudaStream_t s) {
@@ -584,9 +692,14 @@ extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_con
     for (int64_t off = 0; off < n_frames; off += sub) {
         const int batch = static_cast<int>(n_frames - off < sub ? n_frames - off : sub);
         const float* in = samples_dev + off * frame_stride;
-        fft_forward_real_to_products(in, frame_stride, n_in, d_sig, d_pu, d_pd, batch, *t, s);
-        fft_inverse(d_pu, batch, *t, s);
-        fft_inverse(d_pd, batch, *t, s);
+        static const bool unfused = [] { const char* e = std::getenv("RIA_CHIRP_UNFUSED"); return e && e[0] == '1'; }();
+        if (unfused) {
+            fft_forward_real_to_products(in, frame_stride, n_in, d_sig, d_pu, d_pd, batch, *t, s);
+            fft_inverse(d_pu, batch, *t, s);
+            fft_inverse(d_pd, batch, *t, s);
+        } else {
+            chirp_correlate(in, frame_stride, n_in, d_sig, d_pu, d_pd, batch, *t, s);
+        }
         PeakArgs a{};
         a.samples = in; a.frame_stride = frame_stride; a.window = window;
         a.corr_up = d_pu; a.corr_dn = d_pd; a.cumsum = d_cum; a.tmpl_dn_time = t->tmpl_dn_time;
@@ -595,7 +708,7 @@ extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_con
         a.sample_rate = cfg->sample_rate; a.f_start = cfg->f_start; a.f_end = cfg->f_end; a.duration_ms = cfg->duration_ms;
         a.out = out_dev + off;
         chirp_peak_kernel<<<batch, kPeakThreads, 0, s>>>(a);
-        ctx->launches += 10;
+        ctx->launches += unfused ? 10 : 8;
     }
     time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());
