@@ -251,6 +251,27 @@ int ria_ofdm_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg, int rate,
                             const float* cfo_hz, const float* phase, int64_t n_frames,
                             uint8_t* data, ria_frame_status* status, float* snr_db);
 
+/* ---- transmit synthesis on the device ---------------------------------- */
+/* Batched v2::encodeFixedFrame (src/protocol/frame_v2.cpp:1285-1328): frames_dev [n][frame_stride] bytes
+ * (frame_len valid, zero padded / truncated to 4 x bytes_per_cw) -> coded_dev [n][324] bytes: LDPC encode
+ * (src/fec/ldpc_encoder.cpp:193-257), ChannelInterleaver::interleave when use_channel_interleave
+ * (src/fec/ldpc_decoder.cpp:600-615, step from bits_per_symbol), FrameInterleaver::interleave. */
+int ria_encode_fixed_frame_batch_dev(ria_ctx* ctx, int rate, int use_channel_interleave, int bits_per_symbol,
+                                     const uint8_t* frames_dev, int64_t frame_stride, int32_t frame_len,
+                                     int64_t n_frames, uint8_t* coded_dev);
+
+/* Samples of one transmitted frame: (training_symbols + ceil(8 coded_len / bits per OFDM symbol)) symbols. */
+int ria_ofdm_tx_frame_samples(const ria_modem_config* cfg, int32_t coded_len);
+
+/* Batched OFDMModulator::generateTrainingSymbols(cfg->training_symbols) + modulate(coded, cfg->modulation)
+ * (src/ofdm/modulator.cpp:528-582, 348-477): what OFDMChirpWaveform transmits after the chirp and what
+ * IWaveform::process is handed on the receive side.  Sample-identical to the reference (same radix-2
+ * inverse transform, mixer phasors and operation order).  coded_dev [n][coded_stride] bytes,
+ * samples_dev [n][out_stride] fp32 with out_stride >= ria_ofdm_tx_frame_samples(). */
+int ria_ofdm_tx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg,
+                           const uint8_t* coded_dev, int64_t coded_stride, int32_t coded_len,
+                           int64_t n_frames, float* samples_dev, int64_t out_stride);
+
 /* Batched fec::BurstInterleaver::deinterleave (src/fec/burst_interleaver.cpp:39-78), applied by
  * StreamingDecoder::finalizeBurstGroup (src/gui/modem/streaming_decoder.cpp:3209-3216) to the soft bits of
  * a burst group before decodeFrame.  physical_dev [n_groups][group_size][in_stride] -> logical_dev

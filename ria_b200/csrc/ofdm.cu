@@ -1409,6 +1409,7 @@ int blocks_per_sm(ria_ctx* ctx, K kernel, int threads, size_t smem, int* out) {
 void ofdm_tables_free(OfdmTablesDev* t) {
     if (!t) return;
     if (t->twiddle) cudaFree(t->twiddle);
+    if (t->twiddle_nat) cudaFree(t->twiddle_nat);
     if (t->nco) cudaFree(t->nco);
     if (t->car) cudaFree(t->car);
     delete t;
@@ -1428,10 +1429,13 @@ int ofdm_tables_dev(ria_ctx* ctx, const ria_modem_config& cfg, int need_nco, con
         std::vector<float2> tw;
         build_stage_twiddles(h.twiddle, tw);
         if (hit->twiddle) cudaFree(hit->twiddle);
+        if (hit->twiddle_nat) cudaFree(hit->twiddle_nat);
         if (hit->nco) cudaFree(hit->nco);
         if (hit->car) cudaFree(hit->car);
-        hit->twiddle = nullptr; hit->nco = nullptr; hit->car = nullptr; hit->ready = false;
+        hit->twiddle = nullptr; hit->twiddle_nat = nullptr; hit->nco = nullptr; hit->car = nullptr; hit->ready = false;
         RIA_CUDA(ctx, cudaMalloc(&hit->twiddle, tw.size() * sizeof(float2)));
+        RIA_CUDA(ctx, cudaMalloc(&hit->twiddle_nat, h.twiddle.size() * sizeof(float2)));
+        RIA_CUDA(ctx, cudaMemcpy(hit->twiddle_nat, h.twiddle.data(), h.twiddle.size() * sizeof(float2), cudaMemcpyHostToDevice));
         RIA_CUDA(ctx, cudaMalloc(&hit->nco, h.nco.size() * sizeof(float2)));
         RIA_CUDA(ctx, cudaMalloc(&hit->car, sizeof(OfdmCarrierTable)));
         RIA_CUDA(ctx, cudaMemcpy(hit->twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));

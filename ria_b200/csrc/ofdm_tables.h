@@ -46,7 +46,8 @@ struct OfdmTablesDev {
     bool ready = false;
     ria_modem_config cfg{};
     int cp = 0, sym_len = 0, nco_len = 0;
-    float2* twiddle = nullptr;
+    float2* twiddle = nullptr;       // stage-major (receive FFT kernel)
+    float2* twiddle_nat = nullptr;   // natural order W[k], k < fft_size/2 (transmit IFFT)
     float2* nco = nullptr;
     OfdmCarrierTable* car = nullptr;
     OfdmCarrierTable car_host{};

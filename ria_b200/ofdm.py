@@ -198,6 +198,41 @@ def decode_fixed_frame_batch(soft: torch.Tensor, rate: int, use_channel_interlea
     return data, status
 
 
+def encode_fixed_frame_batch(frames: torch.Tensor, rate: int, use_channel_interleave: bool, bits_per_symbol: int,
+                             ctx: Optional[Context] = None) -> torch.Tensor:
+    """v2::encodeFixedFrame for a batch on the device: frames CUDA u8 [n, <= 4*bytes_per_cw] -> coded u8 [n, 324]
+    (src/protocol/frame_v2.cpp:1285-1328)."""
+    if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 2):
+        raise RiaError("encode_fixed_frame_batch wants a CUDA uint8 [n, frame_len] tensor")
+    frames = frames.contiguous()
+    ctx = ctx or default_context()
+    n, flen = frames.shape
+    coded = torch.empty((n, 324), dtype=torch.uint8, device=frames.device)
+    ctx.set_stream(torch.cuda.current_stream(frames.device))
+    ctx.check(lib().ria_encode_fixed_frame_batch_dev(ctx.handle, int(rate), int(bool(use_channel_interleave)),
+                                                      int(bits_per_symbol), _ptr(frames), frames.stride(0), flen, n, _ptr(coded)))
+    return coded
+
+
+def ofdm_tx_frames(config: ModemConfig, coded: torch.Tensor, ctx: Optional[Context] = None) -> torch.Tensor:
+    """OFDMModulator::generateTrainingSymbols + modulate for a batch on the device
+    (src/ofdm/modulator.cpp:528-582, 348-477): coded CUDA u8 [n, coded_len] -> samples fp32 [n, frame_len],
+    sample-identical to the reference transmitter."""
+    if not (isinstance(coded, torch.Tensor) and coded.is_cuda and coded.dtype == torch.uint8 and coded.dim() == 2):
+        raise RiaError("ofdm_tx_frames wants a CUDA uint8 [n, coded_len] tensor")
+    coded = coded.contiguous()
+    ctx = ctx or default_context()
+    n, clen = coded.shape
+    flen = lib().ria_ofdm_tx_frame_samples(C.addressof(config), clen)
+    if flen <= 0:
+        raise RiaError("ofdm_tx_frames: unsupported configuration")
+    out = torch.empty((n, flen), dtype=torch.float32, device=coded.device)
+    ctx.set_stream(torch.cuda.current_stream(coded.device))
+    ctx.check(lib().ria_ofdm_tx_frames_dev(ctx.handle, C.addressof(config), _ptr(coded), coded.stride(0), clen, n,
+                                           _ptr(out), out.stride(0)))
+    return out
+
+
 def status_array(status: torch.Tensor) -> np.ndarray:
     return status.cpu().numpy().view(FRAME_STATUS_DTYPE).reshape(-1)
 
