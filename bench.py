@@ -147,8 +147,8 @@ class OfdmQam64Workload:
         return {"workload": self.name, "frames_per_gpu": self.n, "frame_samples": self.frame_len,
                 "modulation": "QAM64", "code_rate": "R3/4", "fft": 1024, "cp": L - 1024,
                 "carriers": 59, "pilots": c.getPilotCarriers(), "data_carriers": c.getDataCarriers(),
-                "channel": f"AWGN {self.SNR_DB} dB, generated on the device (Philox), "
-                           f"{self.POOL} distinct TX frames x per-frame noise",
+                "channel": f"AWGN {self.SNR_DB} dB generated on the device (Philox); every frame has its own payload, "
+                           "encodeFixedFrame + OFDM TX on the device (sample-identical to the reference transmitter)",
                 "chain": "mix+CFO+CP+FFT1024+LTS/pilot est+MMSE+QAM64 LLR -> frame/channel "
                          "de-interleave -> complete v2::decodeFixedFrame (4x LDPC R3/4 0.9375/60 it, retry ladder and "
                          "false-positive repair armed: RIA_DECODE_FULL) -> header+CRC16",
@@ -158,17 +158,37 @@ class OfdmQam64Workload:
         import torch
         from ria_b200 import ofdm, sim
         self.torch, self.ctx = torch, ctx
-        pool, raw = self.pool_host()
-        self.pool_dev = torch.from_numpy(pool).to(device)
-        bpc4 = 4 * 60
-        sent = np.zeros((self.POOL, bpc4), np.uint8)
-        for i, fr in enumerate(raw):
-            sent[i, : len(fr)] = np.frombuffer(fr, np.uint8)
-        self.sent_dev = torch.from_numpy(sent).to(device)
-        self.sent_len = len(raw[0])
-        self.first_id = rank * self.n                       # global frame ids: sharding-independent noise
-        self.samples = sim.awgn_batch(self.pool_dev, self.n, self.SNR_DB, seed=2026,
-                                      first_frame_id=self.first_id, ctx=ctx)
+        # Every frame is its own transmission: payload bytes (host RNG) -> v2 data frame (header, CRCs) ->
+        # encodeFixedFrame, OFDM training + modulate and the AWGN channel on the device
+        # (ria_encode_fixed_frame_batch_dev / ria_ofdm_tx_frames_dev are byte- / sample-identical to the
+        # reference transmitter, tests/test_tx_gpu.py).  Generated in chunks so that only one chunk of clean
+        # TX samples exists next to the resident RX batch.
+        from ria_b200 import txsynth
+        bpc = 60
+        self.first_id = rank * self.n                       # global frame ids: sharding-independent payloads and noise
+        cfg = self.cfg()
+        bps = cfg.getDataCarriers() * 6
+        self.samples = torch.empty((self.n, self.frame_len), dtype=torch.float32, device=device)
+        self.sent_len = 4 * bpc - 2
+        self.sent_dev = torch.empty((self.n, self.sent_len), dtype=torch.uint8, device=device)
+        chunk = 65536
+        for off in range(0, self.n, chunk):
+            m = min(chunk, self.n - off)
+            rng = np.random.default_rng([2026, self.first_id + off])
+            frames = txsynth.make_data_frames("K1ABC", "W2XYZ", self.first_id + off,
+                                              rng.integers(0, 256, size=(m, 4 * bpc - 19 - 2), dtype=np.uint8), bpc)
+            fr_dev = torch.from_numpy(frames).to(device)
+            self.sent_dev[off:off + m] = fr_dev
+            coded = ofdm.encode_fixed_frame_batch(fr_dev, self.RATE, True, bps, ctx)
+            tx = ofdm.ofdm_tx_frames(cfg, coded, ctx)
+            assert tx.shape[1] == self.frame_len
+            # the channel takes TX row (global id % pool rows) and keys its noise by the global id: with the
+            # chunk as the pool, rotate it so that frame i of the chunk sits in row (gid + i) % m
+            gid = self.first_id + off
+            if gid % m:
+                tx = torch.roll(tx, shifts=gid % m, dims=0)
+            sim.awgn_batch(tx, m, self.SNR_DB, seed=2026, first_frame_id=gid, out=self.samples[off:off + m], ctx=ctx)
+            del tx, coded, fr_dev
         import ria_b200
         ctx.set_decode_flags(ria_b200.DECODE_FULL)          # the reference's complete decodeFixedFrame
         self.chain = ofdm.OfdmRxChain(self.cfg(), self.RATE, True, ctx)
@@ -215,9 +235,7 @@ class OfdmQam64Workload:
         cw_ok = st[:, off["cw_ok"]:off["cw_ok"] + 4]
         iters = st[:, off["cw_iters"]:off["cw_iters"] + 16].contiguous().view(torch.int32)
         ok = (st[:, off["all_ok"]] == 1) & (st[:, off["header_valid"]] == 1) & (st[:, off["frame_crc_ok"]] == 1)
-        ids = (torch.arange(self.n, device=data.device) + self.first_id) % self.POOL
-        want = self.sent_dev[ids][:, : self.sent_len]
-        wrong = (data[:, : self.sent_len] != want).any(dim=1) & ok
+        wrong = (data[:, : self.sent_len] != self.sent_dev).any(dim=1) & ok
         c = torch.zeros(5, dtype=torch.int64, device=data.device)
         c[0] = self.n
         c[1] = ok.sum()

@@ -42,6 +42,49 @@ def make_data_frame(src: str, dst: str, seq: int, payload: bytes, ftype: int = 0
     return body + bytes([f >> 8, f & 0xFF])
 
 
+def _crc16_rows(rows: np.ndarray) -> np.ndarray:
+    """CRC-16/CCITT-FALSE of every row of a uint8 [n, len] array (table driven, vectorised over rows)."""
+    tab = np.zeros(256, np.uint16)
+    for b in range(256):
+        r = b << 8
+        for _ in range(8):
+            r = ((r << 1) ^ 0x1021) & 0xFFFF if r & 0x8000 else (r << 1) & 0xFFFF
+        tab[b] = r
+    crc = np.full(rows.shape[0], 0xFFFF, np.uint16)
+    for j in range(rows.shape[1]):
+        crc = ((crc << 8) & 0xFFFF).astype(np.uint16) ^ tab[((crc >> 8) ^ rows[:, j]) & 0xFF]
+    return crc
+
+
+def make_data_frames(src: str, dst: str, seq0: int, payloads: np.ndarray, bytes_per_cw: int = 0) -> np.ndarray:
+    """make_data_frame for every row of payloads (uint8 [n, len]) -> frames uint8 [n, 17 + len + 2], seq = seq0 + row.
+    With bytes_per_cw > 0 a payload byte that would make a codeword chunk 1..3 start with 0xD5 is changed to
+    0xD4 first (see make_frame_pool: the reference drops such frames)."""
+    payloads = np.ascontiguousarray(payloads, np.uint8)
+    n, ln = payloads.shape
+    out = np.zeros((n, 17 + ln + 2), np.uint8)
+    sh, dh = hash_callsign(src), hash_callsign(dst)
+    seq = (seq0 + np.arange(n)) & 0xFFFF
+    total_cw = (((17 + ln + 2) * 8 + 161) // 162) & 0xFF
+    out[:, 0], out[:, 1], out[:, 2], out[:, 3] = 0x55, 0x4C, 0x30, 0x01
+    out[:, 4], out[:, 5] = seq >> 8, seq & 0xFF
+    out[:, 6:9] = [(sh >> 16) & 0xFF, (sh >> 8) & 0xFF, sh & 0xFF]
+    out[:, 9:12] = [(dh >> 16) & 0xFF, (dh >> 8) & 0xFF, dh & 0xFF]
+    out[:, 12], out[:, 13], out[:, 14] = total_cw, (ln >> 8) & 0xFF, ln & 0xFF
+    h = _crc16_rows(out[:, :15])
+    out[:, 15], out[:, 16] = h >> 8, h & 0xFF
+    out[:, 17:17 + ln] = payloads
+    if bytes_per_cw:
+        for c in (1, 2, 3):
+            pos = c * bytes_per_cw
+            if 17 <= pos < 17 + ln:
+                col = out[:, pos]
+                col[col == 0xD5] = 0xD4
+    f = _crc16_rows(out[:, :17 + ln])
+    out[:, 17 + ln], out[:, 18 + ln] = f >> 8, f & 0xFF
+    return out
+
+
 _H_CACHE = {}
 
 
