@@ -422,6 +422,18 @@ int ria_mcdpsk_rx_frames_host(ria_ctx* ctx, const ria_mcdpsk_config* cfg, const 
                               ria_sync_result* sync);
 
 /* ---- HARQ chase combining ---------------------------------------------------------------------- */
+/* ---- MC-DPSK transmit synthesis on the device ---------------------------- */
+/* Samples of one MC-DPSK frame body: (training_symbols + 1 + data symbols x spreading) x samples_per_symbol. */
+int ria_mcdpsk_tx_frame_samples(const ria_mcdpsk_config* cfg, int32_t data_len);
+
+/* Batched MultiCarrierDPSKModulator::generateTrainingSequence + generateReferenceSymbol + modulate(data)
+ * (src/psk/multi_carrier_dpsk.hpp:141-275): the frame body a transmitter sends after the sync preamble and
+ * IWaveform::process is handed.  Sample-identical to the reference.  data_dev [n][data_stride] bytes (one
+ * LDPC codeword = 81 bytes in the reference's use), samples_dev [n][out_stride] fp32. */
+int ria_mcdpsk_tx_frames_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg,
+                             const uint8_t* data_dev, int64_t data_stride, int32_t data_len,
+                             int64_t n_frames, float* samples_dev, int64_t out_stride);
+
 /* Arithmetic of fec::ChaseCache::store (src/fec/chase_cache.cpp:27-88) on cache slots resident in
  * HBM: item i with slot_dev[i] >= 0 either overwrites (first_dev[i] != 0: first reception) or
  * accumulates (`existing[j] += soft[j]`, :81) its 648 LLRs into acc_dev[slot][648].  A slot may

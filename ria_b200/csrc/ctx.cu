@@ -118,6 +118,7 @@ extern "C" int ria_ctx_destroy(ria_ctx* ctx) {
     for (auto* t : ctx->mcdpsk_tables) ria::mcdpsk_tables_free(t);
     for (auto* t : ctx->zc_tables) ria::zc_tables_free(t);
     for (auto* t : ctx->chirp_tables) ria::chirp_tables_free(t);
+    for (auto* t : ctx->mcdpsk_tx_tables) ria::mcdpsk_tx_tables_free(t);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->ofdm_scratch) cudaFree(ctx->ofdm_scratch);
     if (ctx->chain_scratch) cudaFree(ctx->chain_scratch);

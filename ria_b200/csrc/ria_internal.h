@@ -37,6 +37,7 @@ struct OfdmTablesDev;   // ofdm_tables.h
 struct McdpskTablesDev; // mcdpsk.cu
 struct ZcTablesDev;     // zc_sync.cu
 struct ChirpTablesDev;  // chirp_sync.cu
+struct McdpskTxTablesDev;  // mcdpsk_tx.cu
 
 struct LdpcCodeDev {
     bool ready = false;
@@ -69,6 +70,7 @@ struct ria_ctx {
     std::vector<ria::McdpskTablesDev*> mcdpsk_tables;
     std::vector<ria::ZcTablesDev*> zc_tables;
     std::vector<ria::ChirpTablesDev*> chirp_tables;
+    std::vector<ria::McdpskTxTablesDev*> mcdpsk_tx_tables;
     float* hilbert65 = nullptr;             // 65-tap Hilbert FIR (OFDM data sync)
     // scratch owned by the context for the fused chain entry points
     void* scratch = nullptr;
@@ -100,6 +102,7 @@ void ofdm_tables_free(OfdmTablesDev* t);
 void mcdpsk_tables_free(McdpskTablesDev* t);
 void zc_tables_free(ZcTablesDev* t);
 void chirp_tables_free(ChirpTablesDev* t);
+void mcdpsk_tx_tables_free(McdpskTxTablesDev* t);
 int ensure_scratch(ria_ctx* ctx, size_t bytes);
 int recommended_ldpc_iterations(int rate);          // LDPCCodec::getRecommendedIterations (frame.cu)
 // ldpc.cu / ldpc_retry.cu

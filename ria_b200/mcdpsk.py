@@ -158,3 +158,22 @@ class McdpskRxChain:
             info.ctypes.data_as(C.c_void_p), info_stride, ok.ctypes.data_as(C.c_void_p),
             iters.ctypes.data_as(C.c_void_p), sync.ctypes.data_as(C.c_void_p)))
         return dict(info=info, ok=ok, iters=iters, sync=sync)
+
+
+def mcdpsk_tx_frames(config: "MultiCarrierDPSKConfig", data: torch.Tensor, ctx: Optional[Context] = None) -> torch.Tensor:
+    """MultiCarrierDPSKModulator training + reference + modulate(data) for a batch on the device
+    (src/psk/multi_carrier_dpsk.hpp:141-275): data CUDA u8 [n, len] -> samples fp32 [n, frame_len],
+    sample-identical to the reference transmitter."""
+    if not (isinstance(data, torch.Tensor) and data.is_cuda and data.dtype == torch.uint8 and data.dim() == 2):
+        raise RiaError("mcdpsk_tx_frames wants a CUDA uint8 [n, len] tensor")
+    data = data.contiguous()
+    ctx = ctx or default_context()
+    n, ln = data.shape
+    flen = lib().ria_mcdpsk_tx_frame_samples(C.addressof(config), ln)
+    if flen <= 0:
+        raise RiaError("mcdpsk_tx_frames: unsupported configuration")
+    out = torch.empty((n, flen), dtype=torch.float32, device=data.device)
+    ctx.set_stream(torch.cuda.current_stream(data.device))
+    ctx.check(lib().ria_mcdpsk_tx_frames_dev(ctx.handle, C.addressof(config), data.data_ptr(), data.stride(0), ln, n,
+                                             out.data_ptr(), out.stride(0)))
+    return out

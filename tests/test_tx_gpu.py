@@ -59,3 +59,19 @@ def test_device_tx_chain_decodes_and_matches_host_payload(ctx, ref):
     st = ofdm.status_array(status)
     assert st["all_ok"].all() and st["frame_crc_ok"].all()
     assert np.array_equal(data.cpu().numpy()[:, :frames.shape[1]], frames)
+
+
+@pytest.mark.parametrize("bits,spreading,carriers", [(1, 4, 10), (1, 2, 10), (1, 1, 10), (2, 1, 10), (2, 1, 5), (1, 4, 8)])
+def test_mcdpsk_tx_is_sample_identical(ctx, ref, bits, spreading, carriers):
+    """MultiCarrierDPSKModulator training + reference + modulate(data) on the device vs the reference."""
+    from oracle.bindings import McdpskConfig
+    from ria_b200 import mcdpsk
+    cfg_o = McdpskConfig.make(bits, spreading, carriers)
+    cfg = mcdpsk.MultiCarrierDPSKConfig.from_buffer_copy(bytes(cfg_o))
+    rng = np.random.default_rng(bits * 100 + spreading * 10 + carriers)
+    data = rng.integers(0, 256, size=(5, 81), dtype=np.uint8)
+    got = mcdpsk.mcdpsk_tx_frames(cfg, torch.from_numpy(data).cuda(), ctx).cpu().numpy()
+    for i in range(len(data)):
+        want = ref.mcdpsk_tx_frame(cfg_o, data[i])
+        assert got.shape[1] == len(want), (got.shape, len(want))
+        assert np.array_equal(got[i].view(np.uint32), want.view(np.uint32)), (i, float(np.abs(got[i] - want).max()))
