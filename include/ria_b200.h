@@ -422,6 +422,14 @@ int ria_mcdpsk_rx_frames_host(ria_ctx* ctx, const ria_mcdpsk_config* cfg, const 
                               ria_sync_result* sync);
 
 /* ---- HARQ chase combining ---------------------------------------------------------------------- */
+/* Sync preambles of the reference transmitter, evaluated on the host with the reference's expressions
+ * (they do not depend on the payload; a batch needs each once).  Return the number of samples written, or
+ * minus the required capacity.
+ *   ria_zc_preamble_host     sync::ZCSync::generatePreambleForRoot (src/sync/zc_sync.hpp:133-190)
+ *   ria_chirp_generate_host  sync::ChirpSync::generate, dual chirp (src/sync/chirp_sync.hpp:61-108) */
+int ria_zc_preamble_host(const ria_zc_config* cfg, int root, float* out, int cap);
+int ria_chirp_generate_host(const ria_chirp_config* cfg, float* out, int cap);
+
 /* ---- MC-DPSK transmit synthesis on the device ---------------------------- */
 /* Samples of one MC-DPSK frame body: (training_symbols + 1 + data symbols x spreading) x samples_per_symbol. */
 int ria_mcdpsk_tx_frame_samples(const ria_mcdpsk_config* cfg, int32_t data_len);

@@ -149,3 +149,25 @@ def ofdm_data_sync_batch(config, samples: torch.Tensor, known_cfo_hz: Optional[t
         ctx.handle, C.addressof(config), _ptr(samples), samples.stride(0), window,
         _ptr(known_cfo_hz), float(threshold), n, _ptr(out)))
     return out
+
+
+def zc_preamble_host(config: Optional[ZCConfig] = None, root: int = 5) -> np.ndarray:
+    """sync::ZCSync::generatePreambleForRoot (src/sync/zc_sync.hpp:133-190), the reference's samples
+    (host evaluation; root 5 = DATA frames)."""
+    config = config or ZCConfig.default()
+    n = -lib().ria_zc_preamble_host(C.addressof(config), int(root), None, 0)
+    out = np.empty(n, np.float32)
+    got = lib().ria_zc_preamble_host(C.addressof(config), int(root), out.ctypes.data, n)
+    assert got == n
+    return out
+
+
+def chirp_generate_host(config: Optional[ChirpConfig] = None) -> np.ndarray:
+    """sync::ChirpSync::generate (src/sync/chirp_sync.hpp:61-108): [up chirp][gap][down chirp][gap], the
+    reference's samples (host evaluation)."""
+    config = config or ChirpConfig.default()
+    n = -lib().ria_chirp_generate_host(C.addressof(config), None, 0)
+    out = np.empty(n, np.float32)
+    got = lib().ria_chirp_generate_host(C.addressof(config), out.ctypes.data, n)
+    assert got == n
+    return out

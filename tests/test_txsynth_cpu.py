@@ -28,3 +28,19 @@ def test_txsynth_decodes_under_reference(ria_lib, ref, mod, spacing, rate):
         data, ok, _ = ref.frame_decode_first_pass(r["soft"], rate, True, bps)
         assert ok.all() and bytes(data[: len(fr)]) == fr
         assert ref.parse_header(data).frame_crc_ok == 1
+
+
+def test_host_preambles_are_the_reference_samples(ref, ria_lib):
+    """ria_zc_preamble_host / ria_chirp_generate_host (SURVEY 8f rank 2) vs ZCSync::generatePreamble and
+    ChirpSync::generate of the unmodified reference: bit-identical."""
+    from oracle.bindings import ZcConfig
+    from ria_b200 import sync
+    zc = ZcConfig.default()
+    for frame_type, root in ((0, zc.root_ping), (1, zc.root_pong), (2, zc.root_data), (3, zc.root_control)):
+        want = ref.zc_preamble(zc, frame_type)
+        got = sync.zc_preamble_host(sync.ZCConfig.default(), root)
+        assert len(got) == len(want)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), frame_type
+    want = ref.chirp_generate()
+    got = sync.chirp_generate_host()
+    assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
