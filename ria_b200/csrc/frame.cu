@@ -59,12 +59,116 @@ __device__ __forceinline__ bool is_control_frame(uint8_t t) {
     return t == 0x10 || t == 0x11 || t == 0x16 || t == 0x17 || t == 0x20 || t == 0x21 || t == 0x15 || t == 0x40;
 }
 
-// One thread per frame: reassemble the 4 x bytes_per_cw info bytes (failed codewords stay zero,
-// CodewordStatus::data is only filled on success), parse the header and check the CRCs.
-__global__ void frame_status_kernel(const uint8_t* __restrict__ info, const uint8_t* __restrict__ ok,
-                                    const int32_t* __restrict__ iters, const uint8_t* __restrict__ attempt,
-                                    const uint8_t* __restrict__ repair, long long n_frames, int bpc,
-                                    uint8_t* __restrict__ data, ria_frame_status* __restrict__ status) {
+// Header fields and CRC flags of one reassembled frame `h` (4 x bpc bytes, failed codewords zeroed):
+// v2::parseHeader on codeword 0 (needs >= 20 bytes and a decoded CW0, reassemble():1030-1051) and the
+// frame CRC of DataFrame::deserialize (:590-596).
+__device__ __forceinline__ void parse_frame(const uint16_t* __restrict__ crc_tab, const uint8_t* h, int bpc, ria_frame_status& st) {
+    if (!(st.cw_ok[0] && bpc >= 20)) return;
+    const uint16_t magic = static_cast<uint16_t>((h[0] << 8) | h[1]);
+    if (magic != 0x554C) return;
+    st.type = h[2];
+    st.seq = static_cast<uint16_t>((h[4] << 8) | h[5]);
+    st.src_hash = (static_cast<uint32_t>(h[6]) << 16) | (static_cast<uint32_t>(h[7]) << 8) | h[8];
+    st.dst_hash = (static_cast<uint32_t>(h[9]) << 16) | (static_cast<uint32_t>(h[10]) << 8) | h[11];
+    if (is_control_frame(st.type)) {
+        const uint16_t rx = static_cast<uint16_t>((h[18] << 8) | h[19]);
+        if (rx == crc16_dev(crc_tab, h, 18)) { st.header_valid = 1; st.total_cw = 1; st.payload_len = 0; }
+        return;
+    }
+    st.total_cw = h[12];
+    st.payload_len = static_cast<uint16_t>((h[13] << 8) | h[14]);
+    const uint16_t rx = static_cast<uint16_t>((h[15] << 8) | h[16]);
+    if (rx == crc16_dev(crc_tab, h, 15)) st.header_valid = 1;
+    // needs every codeword that carries part of the frame
+    const int expected = 17 + st.payload_len + 2;
+    if (st.header_valid && expected <= 4 * bpc) {
+        bool have = true;
+        for (int c = 0; c < 4; ++c) if (c * bpc < expected && !st.cw_ok[c]) have = false;
+        if (have) {
+            const uint16_t frx = static_cast<uint16_t>((h[expected - 2] << 8) | h[expected - 1]);
+            st.frame_crc_ok = (frx == crc16_dev(crc_tab, h, expected - 2)) ? 1 : 0;
+        }
+    }
+}
+
+// Reassemble the 4 x bytes_per_cw info bytes (failed codewords stay zero, CodewordStatus::data is only
+// filled on success), parse the header and check the CRCs.  Byte work over 288 B in / 280 B out per
+// frame: a warp takes 32 consecutive frames, moves their bytes through padded shared-memory rows with
+// coalesced 32-bit accesses (rows of 73 / 61 / 11 words: every lane on its own bank), and each lane
+// parses its frame out of shared memory.  (One thread per frame straight on global memory was LSU-bound:
+// 32 scattered byte accesses per instruction.)
+constexpr int kStatusWarps = 2;
+constexpr int kInWords = kInfoStride;             // 4 x 72 B = 72 words per frame
+constexpr int kInRow = kInWords + 1, kOutRow = 61, kStRow = 11;
+static_assert(sizeof(ria_frame_status) == 40, "status rows are copied as 10 words");
+
+__global__ void __launch_bounds__(kStatusWarps * 32)
+frame_status_kernel(const uint8_t* __restrict__ info, const uint8_t* __restrict__ ok,
+                    const int32_t* __restrict__ iters, const uint8_t* __restrict__ attempt,
+                    const uint8_t* __restrict__ repair, long long n_frames, int bpc,
+                    uint8_t* __restrict__ data, ria_frame_status* __restrict__ status) {
+    __shared__ uint16_t crc_tab[256];
+    __shared__ uint32_t in_rows[kStatusWarps][32 * kInRow];
+    __shared__ uint32_t out_rows[kStatusWarps][32 * kOutRow];
+    __shared__ uint32_t st_rows[kStatusWarps][32 * kStRow];
+    crc16_build_table(crc_tab);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long f0 = (blockIdx.x * static_cast<long long>(kStatusWarps) + warp) * 32;
+    if (f0 >= n_frames) return;
+    const int nv = static_cast<int>(n_frames - f0 < 32 ? n_frames - f0 : 32);
+    uint32_t* in = in_rows[warp];
+    uint32_t* outw = out_rows[warp];
+    uint32_t* stw = st_rows[warp];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(info + f0 * 4 * kInfoStride);
+        for (int g = lane; g < nv * kInWords; g += 32) in[(g / kInWords) * kInRow + (g % kInWords)] = __ldcs(src + g);
+    }
+    __syncwarp();
+    if (lane < nv) {
+        const long long f = f0 + lane;
+        const uint8_t* row = reinterpret_cast<const uint8_t*>(in + lane * kInRow);
+        uint8_t* h = reinterpret_cast<uint8_t*>(outw + lane * kOutRow);
+        ria_frame_status st;
+        memset(&st, 0, sizeof st);
+        const uchar4 okv = reinterpret_cast<const uchar4*>(ok)[f];
+        const int4 itv = reinterpret_cast<const int4*>(iters)[f];
+        const uint8_t oks[4] = {okv.x, okv.y, okv.z, okv.w};
+        const int its[4] = {itv.x, itv.y, itv.z, itv.w};
+        uchar4 atv = make_uchar4(0, 0, 0, 0);
+        if (attempt) atv = reinterpret_cast<const uchar4*>(attempt)[f];
+        const uint8_t ats[4] = {atv.x, atv.y, atv.z, atv.w};
+        bool all = true;
+        for (int c = 0; c < 4; ++c) {
+            st.cw_ok[c] = oks[c];
+            st.cw_iters[c] = its[c];
+            all = all && oks[c];
+            if (attempt && oks[c] && ats[c] >= 1 && ats[c] <= 38) {
+                st.ladder_cw_mask |= static_cast<uint8_t>(1u << c);
+                if (ats[c] > st.ladder_max_attempt) st.ladder_max_attempt = ats[c];
+            }
+            for (int b = 0; b < bpc; ++b) h[c * bpc + b] = oks[c] ? row[c * kInfoStride + b] : 0;
+        }
+        st.all_ok = all ? 1 : 0;
+        if (repair) st.fp_repair = repair[f];
+        parse_frame(crc_tab, h, bpc, st);
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(&st);
+#pragma unroll
+        for (int w = 0; w < 10; ++w) stw[lane * kStRow + w] = sw[w];
+    }
+    __syncwarp();
+    {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(data + f0 * 4 * bpc);       // 4 * bpc bytes = bpc words per frame
+        for (int g = lane; g < nv * bpc; g += 32) __stcs(dst + g, outw[(g / bpc) * kOutRow + (g % bpc)]);
+        uint32_t* sd = reinterpret_cast<uint32_t*>(status + f0);
+        for (int g = lane; g < nv * 10; g += 32) sd[g] = stw[(g / 10) * kStRow + (g % 10)];
+    }
+}
+
+// the same with one thread per frame on global memory: for caller buffers that are not 4-byte aligned
+__global__ void frame_status_bytes_kernel(const uint8_t* __restrict__ info, const uint8_t* __restrict__ ok,
+                                          const int32_t* __restrict__ iters, const uint8_t* __restrict__ attempt,
+                                          const uint8_t* __restrict__ repair, long long n_frames, int bpc,
+                                          uint8_t* __restrict__ data, ria_frame_status* __restrict__ status) {
     __shared__ uint16_t crc_tab[256];
     crc16_build_table(crc_tab);
     const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -86,37 +190,7 @@ __global__ void frame_status_kernel(const uint8_t* __restrict__ info, const uint
     }
     st.all_ok = all ? 1 : 0;
     if (repair) st.fp_repair = repair[f];
-    // v2::parseHeader on codeword 0 (needs >= 20 bytes and a decoded CW0, reassemble():1030-1051)
-    if (st.cw_ok[0] && bpc >= 20) {
-        const uint8_t* h = out;
-        const uint16_t magic = static_cast<uint16_t>((h[0] << 8) | h[1]);
-        if (magic == 0x554C) {
-            st.type = h[2];
-            st.seq = static_cast<uint16_t>((h[4] << 8) | h[5]);
-            st.src_hash = (static_cast<uint32_t>(h[6]) << 16) | (static_cast<uint32_t>(h[7]) << 8) | h[8];
-            st.dst_hash = (static_cast<uint32_t>(h[9]) << 16) | (static_cast<uint32_t>(h[10]) << 8) | h[11];
-            if (is_control_frame(st.type)) {
-                const uint16_t rx = static_cast<uint16_t>((h[18] << 8) | h[19]);
-                if (rx == crc16_dev(crc_tab, h, 18)) { st.header_valid = 1; st.total_cw = 1; st.payload_len = 0; }
-            } else {
-                st.total_cw = h[12];
-                st.payload_len = static_cast<uint16_t>((h[13] << 8) | h[14]);
-                const uint16_t rx = static_cast<uint16_t>((h[15] << 8) | h[16]);
-                if (rx == crc16_dev(crc_tab, h, 15)) st.header_valid = 1;
-                // frame CRC over header + payload (DataFrame::deserialize :590-596); needs every
-                // codeword that carries part of the frame
-                const int expected = 17 + st.payload_len + 2;
-                if (st.header_valid && expected <= 4 * bpc) {
-                    bool have = true;
-                    for (int c = 0; c < 4; ++c) if (c * bpc < expected && !st.cw_ok[c]) have = false;
-                    if (have) {
-                        const uint16_t frx = static_cast<uint16_t>((h[expected - 2] << 8) | h[expected - 1]);
-                        st.frame_crc_ok = (frx == crc16_dev(crc_tab, h, expected - 2)) ? 1 : 0;
-                    }
-                }
-            }
-        }
-    }
+    parse_frame(crc_tab, out, bpc, st);
     status[f] = st;
 }
 
@@ -183,10 +257,17 @@ int frame_decode_impl(ria_ctx* ctx, int rate, int use_ci, int bits_per_symbol, c
                                  s.info, kInfoStride, s.ok, s.repair, s.fail_list);
         if (rc != RIA_OK) return rc;
     }
-    const int threads = 128;
-    const unsigned blocks = static_cast<unsigned>((n_frames + threads - 1) / threads);
     time_begin(ctx, KK_FRAME_STATUS);
-    frame_status_kernel<<<blocks, threads, 0, ctx->stream>>>(s.info, s.ok, s.iters, s.attempt, s.repair, n_frames, bpc, data_dev, status_dev);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(data_dev) | reinterpret_cast<uintptr_t>(status_dev)) & 3) == 0 && bpc <= 60;
+    if (aligned) {
+        const int per_cta = kStatusWarps * 32;
+        const unsigned blocks = static_cast<unsigned>((n_frames + per_cta - 1) / per_cta);
+        frame_status_kernel<<<blocks, per_cta, 0, ctx->stream>>>(s.info, s.ok, s.iters, s.attempt, s.repair, n_frames, bpc, data_dev, status_dev);
+    } else {
+        const int threads = 128;
+        const unsigned blocks = static_cast<unsigned>((n_frames + threads - 1) / threads);
+        frame_status_bytes_kernel<<<blocks, threads, 0, ctx->stream>>>(s.info, s.ok, s.iters, s.attempt, s.repair, n_frames, bpc, data_dev, status_dev);
+    }
     time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
