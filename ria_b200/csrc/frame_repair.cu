@@ -130,7 +130,7 @@ frame_repair_kernel(const RepairArgs a) {
 }
 
 // frames whose four codewords all decoded but whose reassembled frame does not verify (:1565-1578)
-__global__ void frame_repair_list_kernel(const uint8_t* __restrict__ info, int info_stride, const uint8_t* __restrict__ ok,
+__global__ void frame_repair_list_bytes_kernel(const uint8_t* __restrict__ info, int info_stride, const uint8_t* __restrict__ ok,
                                          long long n_frames, int bpc, int* __restrict__ list, unsigned* __restrict__ list_len) {
     const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (f >= n_frames) return;
@@ -143,6 +143,36 @@ __global__ void frame_repair_list_kernel(const uint8_t* __restrict__ info, int i
         fr.cw[c] = cw[c];
         for (int b = 0; b < bpc; ++b) cw[c][b] = info[(f * 4 + c) * info_stride + b];
     }
+    fr.bpc = bpc;
+    if (!ria_repair::frame_valid(fr, tmp)) list[atomicAdd(list_len, 1u)] = static_cast<int>(f);
+}
+
+
+// The same for the usual 72-byte codeword stride: a warp takes 32 consecutive frames, stages their
+// 288 info bytes through padded shared rows with coalesced 32-bit loads, and every lane checks its frame
+// out of shared memory.
+constexpr int kListWarps = 2;
+__global__ void __launch_bounds__(kListWarps * 32)
+frame_repair_list_kernel(const uint8_t* __restrict__ info, const uint8_t* __restrict__ ok,
+                         long long n_frames, int bpc, int* __restrict__ list, unsigned* __restrict__ list_len) {
+    constexpr int kWords = 72, kRow = 73;
+    __shared__ uint32_t rows[kListWarps][32 * kRow];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long f0 = (blockIdx.x * static_cast<long long>(kListWarps) + warp) * 32;
+    if (f0 >= n_frames) return;
+    const int nv = static_cast<int>(n_frames - f0 < 32 ? n_frames - f0 : 32);
+    uint32_t* in = rows[warp];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(info + f0 * 4 * 72);
+    for (int g = lane; g < nv * kWords; g += 32) in[(g / kWords) * kRow + (g % kWords)] = src[g];
+    __syncwarp();
+    if (lane >= nv) return;
+    const long long f = f0 + lane;
+    const uchar4 o = reinterpret_cast<const uchar4*>(ok)[f];
+    if (!(o.x && o.y && o.z && o.w)) return;
+    uint8_t tmp[ria_repair::kMaxFrameBytes];
+    ria_repair::Frame fr;
+    uint8_t* row = reinterpret_cast<uint8_t*>(in + lane * kRow);
+    for (int c = 0; c < 4; ++c) fr.cw[c] = row + c * 72;
     fr.bpc = bpc;
     if (!ria_repair::frame_valid(fr, tmp)) list[atomicAdd(list_len, 1u)] = static_cast<int>(f);
 }
@@ -184,7 +214,12 @@ int frame_repair_launch(ria_ctx* ctx, int rate, int max_iter, const float* soft_
     const int threads = 128;
     const unsigned blocks = static_cast<unsigned>((n_frames + threads - 1) / threads);
     time_begin(ctx, KK_FRAME_REPAIR);
-    frame_repair_list_kernel<<<blocks, threads, 0, s>>>(info_dev, info_stride, ok_dev, n_frames, bpc, list_scratch, list_len);
+    if (info_stride == 72 && (reinterpret_cast<uintptr_t>(info_dev) & 3) == 0) {
+        const unsigned lb = static_cast<unsigned>((n_frames + kListWarps * 32 - 1) / (kListWarps * 32));
+        frame_repair_list_kernel<<<lb, kListWarps * 32, 0, s>>>(info_dev, ok_dev, n_frames, bpc, list_scratch, list_len);
+    } else {
+        frame_repair_list_bytes_kernel<<<blocks, threads, 0, s>>>(info_dev, info_stride, ok_dev, n_frames, bpc, list_scratch, list_len);
+    }
     long long grid = static_cast<long long>(ctx->sm_count) * ctas_per_sm;
     const long long want = (n_frames + kRepairWarps - 1) / kRepairWarps;
     if (grid > want) grid = want;
