@@ -75,3 +75,35 @@ def test_mcdpsk_tx_is_sample_identical(ctx, ref, bits, spreading, carriers):
         want = ref.mcdpsk_tx_frame(cfg_o, data[i])
         assert got.shape[1] == len(want), (got.shape, len(want))
         assert np.array_equal(got[i].view(np.uint32), want.view(np.uint32)), (i, float(np.abs(got[i] - want).max()))
+
+
+def test_new_entry_points_reject_bad_arguments_and_accept_empty_batches(ctx):
+    """Error behaviour of the round-1 additions: negative status + message, never a crash; n = 0 is a no-op."""
+    import ctypes as C
+    import ria_b200
+    from ria_b200 import ofdm, mcdpsk
+    L = ria_b200.lib()
+    h = ctx.handle
+    cfg = ofdm.ModemConfig.high_throughput(ofdm.QAM64)
+    buf = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(1 << 16, dtype=torch.float32, device="cuda")
+    # empty batches
+    assert L.ria_encode_fixed_frame_batch_dev(h, 4, 1, 264, buf.data_ptr(), 240, 240, 0, buf.data_ptr()) == 0
+    assert L.ria_ofdm_tx_frames_dev(h, C.addressof(cfg), buf.data_ptr(), 324, 324, 0, out.data_ptr(), 13440) == 0
+    assert L.ria_burst_deinterleave_batch_dev(h, out.data_ptr(), 2592, 4, 0, out.data_ptr(), 2592) == 0
+    assert L.ria_ldpc_robust_decode_batch_dev(h, 4, out.data_ptr(), 0, buf.data_ptr(), 61, buf.data_ptr(), out.data_ptr(), None) == 0
+    # bad arguments -> negative status and a message
+    assert L.ria_encode_fixed_frame_batch_dev(h, 99, 1, 264, buf.data_ptr(), 240, 240, 1, buf.data_ptr()) < 0
+    assert L.ria_encode_fixed_frame_batch_dev(h, 4, 1, 0, buf.data_ptr(), 240, 240, 1, buf.data_ptr()) < 0      # bits_per_symbol
+    assert L.ria_ofdm_tx_frames_dev(h, C.addressof(cfg), buf.data_ptr(), 324, 324, 1, out.data_ptr(), 100) < 0   # out_stride too small
+    assert b"out_stride" in L.ria_last_error(h)
+    assert L.ria_burst_deinterleave_batch_dev(h, out.data_ptr(), 2000, 4, 1, out.data_ptr() + 65536, 2592) < 0    # short rows
+    assert L.ria_burst_deinterleave_batch_dev(h, out.data_ptr(), 2592, 4, 1, out.data_ptr(), 2592) < 0            # in place
+    assert L.ria_ldpc_ladder_perturb_dev(h, out.data_ptr(), 1, 39, out.data_ptr()) < 0                            # attempt range
+    mc = mcdpsk.MultiCarrierDPSKConfig.default(1, 4, 10)
+    assert L.ria_mcdpsk_tx_frames_dev(h, C.addressof(mc), buf.data_ptr(), 81, 81, 1, out.data_ptr(), 10) < 0
+    assert L.ria_mcdpsk_tx_frame_samples(C.addressof(mc), 81) == (8 + 1 + 65 * 4) * 512
+    assert L.ria_ofdm_tx_frame_samples(C.addressof(cfg), 324) == 13440
+    with pytest.raises(ria_b200.RiaError):
+        ctx.set_decode_flags(8)
+    assert ctx.get_decode_flags() == 0
