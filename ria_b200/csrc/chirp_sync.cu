@@ -103,6 +103,12 @@ __device__ __forceinline__ void dft4(float2 (&a)[4]) {
     a[0] = cadd2(s0, s1); a[2] = csub2(s0, s1); a[1] = cadd2(d0, d1); a[3] = csub2(d0, d1);
 }
 
+// std::abs(std::complex<float>) = hypotf: the sum of squares in double, rounded once (:683)
+__device__ __forceinline__ float cabs_d(float2 a) {
+    const double x = a.x, y = a.y;
+    return static_cast<float>(sqrt(x * x + y * y));
+}
+
 struct StageArgs {
     float2* data;                 // [batch][kN] in place
     const float* real_in;         // forward mode 1: real input rows instead of data (may be null)
@@ -111,6 +117,8 @@ struct StageArgs {
     const float2* tmpl_up; const float2* tmpl_dn;
     const float2* tw1; const float2* tw2;
     float scale;
+    float* mag_out;               // inverse mode 1: write |x| as fp32 [batch][2 kN floats per window at mag_stride] instead of x
+    long long mag_stride;
 };
 
 template <int MODE, bool INV>
@@ -191,6 +199,10 @@ fft_stage_kernel(const StageArgs a) {
                 if (MODE == 3 && !INV && a.prod_up) {
                     a.prod_up[f * kN + idx] = cmulf(val, a.tmpl_up[idx]);
                     a.prod_dn[f * kN + idx] = cmulf(val, a.tmpl_dn[idx]);
+                } else if (MODE == 1 && INV && a.mag_out) {
+                    // the peak search only needs the magnitude: half the bytes, and the double-precision
+                    // square root moves from the latency-bound peak kernel into this bandwidth-bound stage
+                    a.mag_out[f * a.mag_stride + idx] = cabs_d(val);
                 } else x[idx] = val;
             }
         }
@@ -303,14 +315,16 @@ void fft_forward(float2* d, int batch, const ChirpTablesDev& t, cudaStream_t s) 
     a.data = d; a.tw1 = t.tw1; a.tw2 = t.tw2; a.scale = 1.0f;
     fft_stages<false>(a, batch, s);
 }
-void fft_inverse(float2* d, int batch, const ChirpTablesDev& t, cudaStream_t s) {
+void fft_inverse(float2* d, int batch, const ChirpTablesDev& t, cudaStream_t s, float* mag_out = nullptr, long long mag_stride = 0) {
     StageArgs a{};
-    a.data = d; a.tw1 = t.tw1; a.tw2 = t.tw2; a.scale = 1.0f / kN;
+    a.data = d; a.tw1 = t.tw1; a.tw2 = t.tw2; a.scale = 1.0f / kN; a.mag_out = mag_out; a.mag_stride = mag_stride;
     fft_stages<true>(a, batch, s);
 }
 // forward transform of real rows -> template products -> inverse stage 3 (fused), then inverse stages 2, 1:
 // leaves the two correlations in pu / pd
+// magnitudes in mag_up / mag_dn ([batch] rows of mag_stride floats; may live in `work`, which is free after stage 3)
 void chirp_correlate(const float* samples, long long stride, int n_in, float2* work, float2* pu, float2* pd,
+                     float* mag_up, float* mag_dn, long long mag_stride,
                      int batch, const ChirpTablesDev& t, cudaStream_t s) {
     StageArgs a{};
     a.data = work; a.real_in = samples; a.real_stride = stride; a.n_in = n_in;
@@ -321,9 +335,10 @@ void chirp_correlate(const float* samples, long long stride, int n_in, float2* w
     fft_stage_kernel<2, false><<<g2, kFftThreads, 0, s>>>(a);
     a.prod_up = pu; a.prod_dn = pd;
     fft_stage3_fused_kernel<<<g3, kFftThreads, 0, s>>>(a);
-    for (float2* d : {pu, pd}) {
+    for (int which = 0; which < 2; ++which) {
         StageArgs b{};
-        b.data = d; b.tw1 = t.tw1; b.tw2 = t.tw2; b.scale = 1.0f / kN;
+        b.data = which ? pd : pu; b.tw1 = t.tw1; b.tw2 = t.tw2; b.scale = 1.0f / kN;
+        b.mag_out = which ? mag_dn : mag_up; b.mag_stride = mag_stride;
         fft_stage_kernel<2, true><<<g2, kFftThreads, 0, s>>>(b);
         fft_stage_kernel<1, true><<<g1, kFftThreads, 0, s>>>(b);
     }
@@ -360,17 +375,13 @@ __global__ void conj_kernel(float2* d) {
     if (i < kN) d[i].y = -d[i].y;
 }
 
-__device__ __forceinline__ float cabs_d(float2 a) {
-    const double x = a.x, y = a.y;
-    return static_cast<float>(sqrt(x * x + y * y));
-}
 __device__ __forceinline__ void better(float& bv, int& bi, float v, int i) {
     if (v > bv || (v == bv && v > 0.0f && (bi < 0 || i < bi))) { bv = v; bi = i; }
 }
 
 struct PeakArgs {
     const float* samples; long long frame_stride; int window;
-    const float2* corr_up; const float2* corr_dn;
+    const float* corr_up; const float* corr_dn; long long corr_stride;      // |R| per lag (fp32)
     float* cumsum;                 // [n][window + 1] scratch
     const float2* tmpl_dn_time;
     float threshold, energy_up, energy_dn;
@@ -432,12 +443,12 @@ __device__ void prefix_energy(const float* __restrict__ s, int start, int len, f
 }
 
 // normalised peak over pos < search_len (:677-689); corr index offset `off`
-__device__ void peak_search(const float2* corr, int off, const float* c, int search_len, int chirp_len,
+__device__ void peak_search(const float* corr, int off, const float* c, int search_len, int chirp_len,
                             float tmpl_energy, float* red_v, int* red_i, float* best, int* pos) {
     const int tid = threadIdx.x;
     float bv = 0.0f; int bi = -1;
     for (int p = tid; p < search_len; p += blockDim.x) {
-        const float mag = cabs_d(corr[off + p]);
+        const float mag = corr[off + p];
         const float e = __fsub_rn(c[p + chirp_len], c[p]);
         const float denom = sqrtf(__fmul_rn(e, tmpl_energy));
         const float nc = (denom > 1e-10f) ? __fdiv_rn(mag, denom) : 0.0f;
@@ -526,8 +537,8 @@ chirp_peak_kernel(const PeakArgs a) {
     const int tid = threadIdx.x;
     const float* s = a.samples + f * a.frame_stride;
     float* c = a.cumsum + f * (static_cast<long long>(a.window) + 1);
-    const float2* cu = a.corr_up + static_cast<size_t>(f) * kN;
-    const float2* cd = a.corr_dn + static_cast<size_t>(f) * kN;
+    const float* cu = a.corr_up + static_cast<size_t>(f) * a.corr_stride;
+    const float* cd = a.corr_dn + static_cast<size_t>(f) * a.corr_stride;
     const int CL = a.chirp_len;
     const int n_in = min(a.window, kN);
 
@@ -693,16 +704,20 @@ extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_con
         const int batch = static_cast<int>(n_frames - off < sub ? n_frames - off : sub);
         const float* in = samples_dev + off * frame_stride;
         static const bool unfused = [] { const char* e = std::getenv("RIA_CHIRP_UNFUSED"); return e && e[0] == '1'; }();
+        // |R_up| / |R_dn| go into the signal buffer, which is free once stage 3 has consumed it
+        float* mag_up = reinterpret_cast<float*>(d_sig);
+        float* mag_dn = mag_up + kN;
+        const long long mag_stride = 2LL * kN;
         if (unfused) {
             fft_forward_real_to_products(in, frame_stride, n_in, d_sig, d_pu, d_pd, batch, *t, s);
-            fft_inverse(d_pu, batch, *t, s);
-            fft_inverse(d_pd, batch, *t, s);
+            fft_inverse(d_pu, batch, *t, s, mag_up, mag_stride);
+            fft_inverse(d_pd, batch, *t, s, mag_dn, mag_stride);
         } else {
-            chirp_correlate(in, frame_stride, n_in, d_sig, d_pu, d_pd, batch, *t, s);
+            chirp_correlate(in, frame_stride, n_in, d_sig, d_pu, d_pd, mag_up, mag_dn, mag_stride, batch, *t, s);
         }
         PeakArgs a{};
         a.samples = in; a.frame_stride = frame_stride; a.window = window;
-        a.corr_up = d_pu; a.corr_dn = d_pd; a.cumsum = d_cum; a.tmpl_dn_time = t->tmpl_dn_time;
+        a.corr_up = mag_up; a.corr_dn = mag_dn; a.corr_stride = mag_stride; a.cumsum = d_cum; a.tmpl_dn_time = t->tmpl_dn_time;
         a.threshold = threshold; a.energy_up = t->energy_up; a.energy_dn = t->energy_dn;
         a.chirp_len = t->chirp_len; a.gap = t->gap;
         a.sample_rate = cfg->sample_rate; a.f_start = cfg->f_start; a.f_end = cfg->f_end; a.duration_ms = cfg->duration_ms;
