@@ -412,6 +412,11 @@ class McdpskC3Workload:
     def samples_per_step(self):
         return 2.0 * self.n * self.row_len
 
+    def extra(self, frames_per_s):
+        """every frame is received twice (HARQ round): the chain runs 2 x value receptions per second; the CPU
+        baseline counts single receptions"""
+        return {"receptions_per_s": 2.0 * frames_per_s}
+
     def kernels(self):
         """kind -> (kernel names, ALGORITHMIC bytes per step); two receptions per frame."""
         n2 = 2 * self.n
@@ -844,6 +849,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if hasattr(wl, "extra"):
+            line.update(wl.extra(value))
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_fn(wl, cpu_sample)
         print(json.dumps(line), flush=True)

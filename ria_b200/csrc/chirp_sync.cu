@@ -297,6 +297,131 @@ fft_stage3_fused_kernel(const StageArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// "Slab" kernel: forward stages 2 and 3, both template products and inverse stages 3 and 2 in one pass
+// over HBM.  For a fixed ka the (b, c) plane is one contiguous 32 KB slab of the spectrum, so a CTA loads
+// it with fully coalesced accesses, runs the 64-point transforms over b and over c in shared memory,
+// multiplies by the two template slabs and runs the two inverse transforms back, writing two slabs.
+// With it the three 131072-point transforms are: stage 1 (real input) -> slab kernel -> inverse stage 1
+// for each template = 7.5 MB of HBM traffic per window instead of 14.5 MB (and 21.5 MB originally).
+// MEASURED (B200, profiles/r1_chirp_subbatch.txt): correct (same peak indices / correlations as the staged
+// path) but not faster yet -- 4.37 vs 4.09 ms per 1024 windows: with half the bytes the slab kernel is
+// bound by its nine block barriers and 2-way-conflicted strided shared-memory passes (about twice its
+// issue bound), not by HBM.  It is therefore opt-in (RIA_CHIRP_SLAB=1) until its shared-memory passes are
+// vectorised; tests/test_chirp_gpu.py runs it against the default path.
+// (A variant that fused stages 1+2 over (a, b) planes of four c was measured first: 40 % fewer bytes
+// but 32-byte global segments and two CTAs per SM made it slower still, 5.1 ms per 1024 windows.)
+// ---------------------------------------------------------------------------------------------
+constexpr int kSlabS = 68;                               // row stride (elements): both transform directions 2-way at worst
+constexpr int kSlabElems = kB * kSlabS;                  // 4352 float2 = 34 KB per buffer
+constexpr int kSlabThreads = 256;
+
+// Four 64-point transforms at once (radix 8 x 8): the lanes of a warp are (hi, r), r = line 0..3.
+// Element i of this lane's line is in_[base + i * step] (pass 1 reads `in_`, writes `wk`; pass 2 reads `wk`).
+// On return v[k2] = X[hi + 8 k2] and every lane has finished reading `wk`.
+template <bool INV>
+__device__ __forceinline__ void dft64_line(const float2* in_, float2* wk, int base, int step, int hi,
+                                           const float2* __restrict__ w64, float2 (&v)[8]) {
+#pragma unroll
+    for (int n1 = 0; n1 < 8; ++n1) v[n1] = in_[base + (8 * n1 + hi) * step];
+    dft8<INV>(v);
+    __syncwarp();                                        // in_ may alias wk: everyone has read before anyone writes
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) {
+        float2 w = w64[hi * k1];
+        if (INV) w.y = -w.y;
+        wk[base + (8 * k1 + hi) * step] = (k1 == 0) ? v[0] : cmulf(v[k1], w);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 8; ++n2) v[n2] = wk[base + (8 * hi + n2) * step];
+    dft8<INV>(v);
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kSlabThreads)
+fft_slab_kernel(const StageArgs a) {
+    extern __shared__ __align__(16) float2 slab_smem[];
+    float2* F = slab_smem;                               // forward spectrum of the slab
+    float2* W = slab_smem + kSlabElems;                  // product / inverse work buffer
+    __shared__ float2 w64[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hi = lane >> 2, r = lane & 3;
+    const size_t f = blockIdx.y;
+    const int ka = blockIdx.x;
+    const size_t slab0 = static_cast<size_t>(ka) * (kB * kC);
+    const float2* x = a.data + f * kN + slab0;
+    if (tid < 64) { double sn, cs; sincospi(-2.0 * tid / 64, &sn, &cs); w64[tid] = make_float2(static_cast<float>(cs), static_cast<float>(sn)); }
+    // ---- load the slab: 4096 contiguous points ----
+    for (int e = tid; e < kB * kC / 2; e += kSlabThreads) {
+        const float4 p = reinterpret_cast<const float4*>(x)[e];
+        const int b = (2 * e) / kC, c = (2 * e) % kC;
+        F[b * kSlabS + c] = make_float2(p.x, p.y);
+        F[b * kSlabS + c + 1] = make_float2(p.z, p.w);
+    }
+    __syncthreads();
+    float2 v[8];
+    // ---- forward stage 2: over b (columns c), twiddle W_BC^(kb c) ----
+#pragma unroll 1
+    for (int g = warp; g < kC / 4; g += kSlabThreads / 32) {
+        const int c = 4 * g + r;
+        dft64_line<false>(F, F, c, kSlabS, hi, w64, v);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) { const int kb = hi + 8 * k2; F[kb * kSlabS + c] = cmulf(v[k2], a.tw2[kb * kC + c]); }
+    }
+    __syncthreads();
+    // ---- forward stage 3: over c (rows kb) ----
+#pragma unroll 1
+    for (int g = warp; g < kB / 4; g += kSlabThreads / 32) {
+        const int kb = 4 * g + r;
+        dft64_line<false>(F, F, kb * kSlabS, 1, hi, w64, v);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) F[kb * kSlabS + hi + 8 * k2] = v[k2];
+    }
+    __syncthreads();
+    // ---- per template: product, inverse stage 3 (over kc), inverse stage 2 (over kb), slab out ----
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+        const float2* tm = (which ? a.tmpl_dn : a.tmpl_up) + slab0;
+        float2* out = (which ? a.prod_dn : a.prod_up) + f * kN + slab0;
+        for (int e = tid; e < kB * kC; e += kSlabThreads) {
+            const int b = e / kC, c = e % kC;
+            W[b * kSlabS + c] = cmulf(F[b * kSlabS + c], __ldg(tm + e));
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int g = warp; g < kB / 4; g += kSlabThreads / 32) {
+            const int kb = 4 * g + r;
+            dft64_line<true>(W, W, kb * kSlabS, 1, hi, w64, v);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) {
+                const int c = hi + 8 * k2;
+                float2 w = a.tw2[kb * kC + c]; w.y = -w.y;
+                W[kb * kSlabS + c] = cmulf(v[k2], w);
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int g = warp; g < kC / 4; g += kSlabThreads / 32) {
+            const int c = 4 * g + r;
+            dft64_line<true>(W, W, c, kSlabS, hi, w64, v);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) {
+                const int b = hi + 8 * k2;
+                float2 w = a.tw1[slab0 + static_cast<size_t>(b) * kC + c]; w.y = -w.y;
+                W[b * kSlabS + c] = cmulf(v[k2], w);
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < kB * kC / 2; e += kSlabThreads) {
+            const int b = (2 * e) / kC, c = (2 * e) % kC;
+            const float2 p0 = W[b * kSlabS + c], p1 = W[b * kSlabS + c + 1];
+            reinterpret_cast<float4*>(out)[e] = make_float4(p0.x, p0.y, p1.x, p1.y);
+        }
+        __syncthreads();
+    }
+}
+
 template <bool INV>
 void fft_stages(const StageArgs& a, int batch, cudaStream_t s) {
     const dim3 g1(kB * kC / 32 / kTilesPerCta, batch), g2(kA * kC / 16 / kTilesPerCta, batch), g3(kA * kB / 16 / kTilesPerCta, batch);
@@ -325,21 +450,28 @@ void fft_inverse(float2* d, int batch, const ChirpTablesDev& t, cudaStream_t s, 
 // magnitudes in mag_up / mag_dn ([batch] rows of mag_stride floats; may live in `work`, which is free after stage 3)
 void chirp_correlate(const float* samples, long long stride, int n_in, float2* work, float2* pu, float2* pd,
                      float* mag_up, float* mag_dn, long long mag_stride,
-                     int batch, const ChirpTablesDev& t, cudaStream_t s) {
+                     int batch, const ChirpTablesDev& t, cudaStream_t s, bool use_slab) {
     StageArgs a{};
     a.data = work; a.real_in = samples; a.real_stride = stride; a.n_in = n_in;
     a.prod_up = nullptr; a.prod_dn = nullptr; a.tmpl_up = t.tmpl_up; a.tmpl_dn = t.tmpl_dn;
     a.tw1 = t.tw1; a.tw2 = t.tw2; a.scale = 1.0f;
     const dim3 g1(kB * kC / 32 / kTilesPerCta, batch), g2(kA * kC / 16 / kTilesPerCta, batch), g3(kA * kB / 16 / kTilesPerCta, batch);
-    fft_stage_kernel<1, false><<<g1, kFftThreads, 0, s>>>(a);
-    fft_stage_kernel<2, false><<<g2, kFftThreads, 0, s>>>(a);
-    a.prod_up = pu; a.prod_dn = pd;
-    fft_stage3_fused_kernel<<<g3, kFftThreads, 0, s>>>(a);
+    if (use_slab) {
+        const size_t slab_smem_bytes = 2 * static_cast<size_t>(kSlabElems) * sizeof(float2);
+        fft_stage_kernel<1, false><<<g1, kFftThreads, 0, s>>>(a);
+        a.prod_up = pu; a.prod_dn = pd;
+        fft_slab_kernel<<<dim3(kA, batch), kSlabThreads, slab_smem_bytes, s>>>(a);
+    } else {
+        fft_stage_kernel<1, false><<<g1, kFftThreads, 0, s>>>(a);
+        fft_stage_kernel<2, false><<<g2, kFftThreads, 0, s>>>(a);
+        a.prod_up = pu; a.prod_dn = pd;
+        fft_stage3_fused_kernel<<<g3, kFftThreads, 0, s>>>(a);
+    }
     for (int which = 0; which < 2; ++which) {
         StageArgs b{};
         b.data = which ? pd : pu; b.tw1 = t.tw1; b.tw2 = t.tw2; b.scale = 1.0f / kN;
         b.mag_out = which ? mag_dn : mag_up; b.mag_stride = mag_stride;
-        fft_stage_kernel<2, true><<<g2, kFftThreads, 0, s>>>(b);
+        if (!use_slab) fft_stage_kernel<2, true><<<g2, kFftThreads, 0, s>>>(b);
         fft_stage_kernel<1, true><<<g1, kFftThreads, 0, s>>>(b);
     }
 }
@@ -704,6 +836,14 @@ extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_con
         const int batch = static_cast<int>(n_frames - off < sub ? n_frames - off : sub);
         const float* in = samples_dev + off * frame_stride;
         static const bool unfused = [] { const char* e = std::getenv("RIA_CHIRP_UNFUSED"); return e && e[0] == '1'; }();
+        static const bool slab_env = [] { const char* e = std::getenv("RIA_CHIRP_SLAB"); return e && e[0] == '1'; }();
+        static bool slab_attr = false;
+        if (slab_env && !slab_attr) {
+            RIA_CUDA(ctx, cudaFuncSetAttribute(fft_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(2 * kSlabElems * sizeof(float2))));
+            slab_attr = true;
+        }
+        const bool use_slab = slab_env;
         // |R_up| / |R_dn| go into the signal buffer, which is free once stage 3 has consumed it
         float* mag_up = reinterpret_cast<float*>(d_sig);
         float* mag_dn = mag_up + kN;
@@ -713,7 +853,7 @@ extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_con
             fft_inverse(d_pu, batch, *t, s, mag_up, mag_stride);
             fft_inverse(d_pd, batch, *t, s, mag_dn, mag_stride);
         } else {
-            chirp_correlate(in, frame_stride, n_in, d_sig, d_pu, d_pd, mag_up, mag_dn, mag_stride, batch, *t, s);
+            chirp_correlate(in, frame_stride, n_in, d_sig, d_pu, d_pd, mag_up, mag_dn, mag_stride, batch, *t, s, use_slab);
         }
         PeakArgs a{};
         a.samples = in; a.frame_stride = frame_stride; a.window = window;
@@ -723,7 +863,7 @@ extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_con
         a.sample_rate = cfg->sample_rate; a.f_start = cfg->f_start; a.f_end = cfg->f_end; a.duration_ms = cfg->duration_ms;
         a.out = out_dev + off;
         chirp_peak_kernel<<<batch, kPeakThreads, 0, s>>>(a);
-        ctx->launches += unfused ? 10 : 8;
+        ctx->launches += unfused ? 10 : (use_slab ? 5 : 8);
     }
     time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());

@@ -70,3 +70,37 @@ def test_other_windows_and_edges(ctx, ref):
     r = ref.chirp_detect_dual(np.zeros(120000, np.float32))
     assert z["detected"][0] == r.detected == 0 and z["correlation"][0] == r.correlation == 0.0
     assert cs.detect_dual_batch(torch.zeros((0, 120000), device="cuda")).shape[0] == 0
+
+
+def test_slab_transform_path_matches_the_default_path():
+    """RIA_CHIRP_SLAB=1 (stages 2+3, products and inverse 3+2 in one kernel) is read once per process, so
+    it runs in a child: detections must equal the default staged path on the same seeded windows."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json; sys.path.insert(0, %r)\n"
+        "import numpy as np, torch, ria_b200\n"
+        "from ria_b200 import sync\n"
+        "pre = sync.chirp_generate_host()\n"
+        "rng = np.random.default_rng(3)\n"
+        "rows = []\n"
+        "for i in range(12):\n"
+        "    x = rng.standard_normal(120000).astype(np.float32) * np.float32(0.3)\n"
+        "    p = 2000 + 5000 * i\n"
+        "    x[p:p + len(pre)] += pre\n"
+        "    rows.append(x)\n"
+        "r = sync.results(sync.ChirpSync(ctx=ria_b200.Context(0)).detect_dual_batch(torch.from_numpy(np.stack(rows)).cuda()))\n"
+        "print(json.dumps([[int(a), int(b), float(c)] for a, b, c in zip(r['detected'], r['start_sample'], r['correlation'])]))\n"
+    ) % root
+    outs = []
+    for slab in ("0", "1"):
+        env = dict(os.environ, RIA_CHIRP_SLAB=slab)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
+        outs.append(json.loads(res.stdout.strip().splitlines()[-1]))
+    assert all(d[0] == 1 for d in outs[0])
+    for a, b in zip(*outs):
+        assert a[0] == b[0] and a[1] == b[1]
+        assert abs(a[2] - b[2]) <= 1e-5 * abs(a[2])
