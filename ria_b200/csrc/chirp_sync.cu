@@ -321,9 +321,14 @@ constexpr int kSlabThreads = 256;
 // On return v[k2] = X[hi + 8 k2] and every lane has finished reading `wk`.
 template <bool INV>
 __device__ __forceinline__ void dft64_line(const float2* in_, float2* wk, int base, int step, int hi,
-                                           const float2* __restrict__ w64, float2 (&v)[8]) {
+                                           const float2* __restrict__ w64, float2 (&v)[8],
+                                           const float2* __restrict__ mul = nullptr) {
 #pragma unroll
     for (int n1 = 0; n1 < 8; ++n1) v[n1] = in_[base + (8 * n1 + hi) * step];
+    if (mul) {                                           // pointwise factor on the input (template product): mul[i] for element i
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) v[n1] = cmulf(v[n1], __ldg(mul + 8 * n1 + hi));
+    }
     dft8<INV>(v);
     __syncwarp();                                        // in_ may alias wk: everyone has read before anyone writes
 #pragma unroll
@@ -339,7 +344,7 @@ __device__ __forceinline__ void dft64_line(const float2* in_, float2* wk, int ba
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kSlabThreads)
+__global__ void __launch_bounds__(kSlabThreads, 3)
 fft_slab_kernel(const StageArgs a) {
     extern __shared__ __align__(16) float2 slab_smem[];
     float2* F = slab_smem;                               // forward spectrum of the slab
@@ -384,15 +389,11 @@ fft_slab_kernel(const StageArgs a) {
     for (int which = 0; which < 2; ++which) {
         const float2* tm = (which ? a.tmpl_dn : a.tmpl_up) + slab0;
         float2* out = (which ? a.prod_dn : a.prod_up) + f * kN + slab0;
-        for (int e = tid; e < kB * kC; e += kSlabThreads) {
-            const int b = e / kC, c = e % kC;
-            W[b * kSlabS + c] = cmulf(F[b * kSlabS + c], __ldg(tm + e));
-        }
-        __syncthreads();
+        // the template product rides on the loads of the first inverse pass (F is kept for the second template)
 #pragma unroll 1
         for (int g = warp; g < kB / 4; g += kSlabThreads / 32) {
             const int kb = 4 * g + r;
-            dft64_line<true>(W, W, kb * kSlabS, 1, hi, w64, v);
+            dft64_line<true>(F, W, kb * kSlabS, 1, hi, w64, v, tm + kb * kC);
 #pragma unroll
             for (int k2 = 0; k2 < 8; ++k2) {
                 const int c = hi + 8 * k2;
