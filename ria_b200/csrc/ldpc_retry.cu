@@ -39,7 +39,7 @@ namespace {
 using ldpc_core::kN;
 using ldpc_core::LdpcGather;
 
-constexpr int kRetryWarps = 8;
+constexpr int kMaxRetryWarps = 16;
 constexpr int kMtN = 624, kMtM = 397;
 constexpr float kDefaultFactor = 0.9375f;
 
@@ -132,10 +132,11 @@ __device__ __forceinline__ float canonical(unsigned u) {
     return (r >= 1.0f) ? __uint_as_float(0x3f7fffffu) : r;
 }
 
-// llr[j] = transform(base[j]) + noise_j for j < 648, noise from std::normal_distribution<float>(0, sigma)
+// llr[j] = transform(llr[j]) + noise_j for j < 648, noise from std::normal_distribution<float>(0, sigma)
 // on std::mt19937(seed) exactly as `for (float& llr : v) llr = f(llr) + noise(rng)` consumes it
 // (libstdc++ bits/random.tcc normal_distribution::operator(): polar method, second value saved).
-__device__ void perturb(const float* base, float* llr, unsigned* mt, unsigned seed, float sigma, int mode, int lane) {
+// In place: every soft bit is read and written exactly once, by the lane that owns its accepted pair.
+__device__ void perturb(float* llr, unsigned* mt, unsigned seed, float sigma, int mode, int lane) {
     if (lane == 0) mt_seed(mt, seed);
     __syncwarp();
     int n_acc = 0;                                  // accepted pairs so far (two normals each)
@@ -162,8 +163,8 @@ __device__ void perturb(const float* base, float* llr, unsigned* mt, unsigned se
                 // then ret * stddev + mean (mean = 0)
                 const float n0 = __fadd_rn(__fmul_rn(__fmul_rn(y, mult), sigma), 0.0f);
                 const float n1 = __fadd_rn(__fmul_rn(__fmul_rn(x, mult), sigma), 0.0f);
-                llr[2 * idx] = __fadd_rn(transform(base[2 * idx], mode), n0);
-                llr[2 * idx + 1] = __fadd_rn(transform(base[2 * idx + 1], mode), n1);
+                llr[2 * idx] = __fadd_rn(transform(llr[2 * idx], mode), n0);
+                llr[2 * idx + 1] = __fadd_rn(transform(llr[2 * idx + 1], mode), n1);
             }
             n_acc += __popc(bal);
         }
@@ -181,7 +182,7 @@ struct RetryArgs {
     uint8_t* attempt_g;                  // optional [n_cw]: 0 = first decode, 1..38 = ladder attempt that succeeded, 255 = none
 };
 
-__global__ void __launch_bounds__(kRetryWarps * 32)
+__global__ void __launch_bounds__(kMaxRetryWarps * 32)
 ldpc_retry_kernel(const RetryArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = a.k, m = a.m, dv_max = a.dv_max;
@@ -190,12 +191,15 @@ ldpc_retry_kernel(const RetryArgs a) {
     const size_t tab_bytes = ldpc_core::ldpc_tab_bytes(k, m, dv_max);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kpad = (k + 3) & ~3;
-    const size_t per_warp = (static_cast<size_t>(2 * kN) + kpad + static_cast<size_t>(m) * 8 + kMtN) * 4;
-    float* base = reinterpret_cast<float*>(smem_raw + tab_bytes + per_warp * warp);
-    float* llr = base + kN;
+    // per warp: llr[648] | tot[k] | msg[2][m] -- the same footprint as the first-pass kernel, so as many
+    // codewords stay resident.  The soft bits are re-gathered from global memory for every attempt (648
+    // floats against a 50-80 iteration decode) instead of being kept in a second buffer, and the
+    // mt19937 state lives in the message area, which the decoder re-initialises after the perturbation.
+    const size_t per_warp = (static_cast<size_t>(kN) + kpad + static_cast<size_t>(m) * 8) * 4;
+    float* llr = reinterpret_cast<float*>(smem_raw + tab_bytes + per_warp * warp);
     float* tot = llr + kN;
     float4* msg = reinterpret_cast<float4*>(tot + kpad);
-    unsigned* mt = reinterpret_cast<unsigned*>(msg + 2 * m);
+    unsigned* mt = reinterpret_cast<unsigned*>(msg);             // 624 words <= 8 m words (m >= 108)
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.chk_var_g);
         for (int i = threadIdx.x; i < m; i += blockDim.x) chk_var[i] = src[i];
@@ -218,13 +222,15 @@ ldpc_retry_kernel(const RetryArgs a) {
             bool success = a.ok_g[cw] != 0;
             const bool first_pass_valid = (factor_state == kDefaultFactor);
             if (first_pass_valid && success) continue;       // decoded by the first pass, decoder untouched
-            ldpc_core::gather_codeword(a.llr_g, cw, a.gather, base, lane);
+            ldpc_core::gather_codeword(a.llr_g, cw, a.gather, llr, lane);
             __syncwarp();
+            // data-dependent seed of the perturbations (:1391-1396)
+            unsigned hash = 0;
+            for (int j = 0; j < 16; ++j) hash ^= __float_as_uint(llr[j]) + 0x9e3779b9u + (hash << 6) + (hash >> 2);
             int iters = 0, hit = 255;
             if (!first_pass_valid) {
                 // the decoder was left at 0.875 by an earlier codeword of this frame: its first decode
                 // of this codeword runs with that factor (:1383-1385)
-                for (int j = lane; j < kN; j += 32) llr[j] = base[j];
                 ldpc_core::decode_codeword(llr, tot, msg, chk_var, var_slot, k, m, dv_max, a.max_iter, factor_state, lane, success, iters);
                 if (lane == 0) a.iters_g[cw] = iters;
                 if (success) {
@@ -233,16 +239,19 @@ ldpc_retry_kernel(const RetryArgs a) {
                 }
             }
             if (!success) {
-                // data-dependent seed (:1391-1396)
-                unsigned hash = 0;
-                for (int j = 0; j < 16; ++j) hash ^= __float_as_uint(base[j]) + 0x9e3779b9u + (hash << 6) + (hash >> 2);
                 const int n_attempts = a.per_frame ? 38 : 4;
+                bool dirty = false;                              // llr no longer holds the received soft bits
                 for (int at = 0; at < n_attempts && !success; ++at) {
                     const Attempt A = kLadder[at];
-                    if (A.mode == PM_NONE) {
-                        for (int j = lane; j < kN; j += 32) llr[j] = base[j];
-                    } else {
-                        perturb(base, llr, mt, hash + A.seed_mul * 997u + A.seed_add, A.sigma, A.mode, lane);
+                    if (dirty) {
+                        __syncwarp();
+                        ldpc_core::gather_codeword(a.llr_g, cw, a.gather, llr, lane);
+                        __syncwarp();
+                        dirty = false;
+                    }
+                    if (A.mode != PM_NONE) {
+                        perturb(llr, mt, hash + A.seed_mul * 997u + A.seed_add, A.sigma, A.mode, lane);
+                        dirty = true;
                     }
                     ldpc_core::decode_codeword(llr, tot, msg, chk_var, var_slot, k, m, dv_max, a.max_iter, A.factor, lane, success, iters);
                     if (success) {
@@ -267,17 +276,16 @@ ldpc_retry_kernel(const RetryArgs a) {
 
 // the soft bits ladder attempt `at` decodes, for n codewords (one warp each): observability / tests
 __global__ void ladder_perturb_kernel(const float* __restrict__ llr_g, long long n_cw, int at, float* __restrict__ out_g) {
-    __shared__ float base[kN];
     __shared__ float llr[kN];
     __shared__ unsigned mt[kMtN];
     const int lane = threadIdx.x;
     for (long long cw = blockIdx.x; cw < n_cw; cw += gridDim.x) {
-        for (int j = lane; j < kN; j += 32) { base[j] = llr_g[cw * kN + j]; llr[j] = base[j]; }
+        for (int j = lane; j < kN; j += 32) llr[j] = llr_g[cw * kN + j];
         __syncwarp();
         unsigned hash = 0;
-        for (int j = 0; j < 16; ++j) hash ^= __float_as_uint(base[j]) + 0x9e3779b9u + (hash << 6) + (hash >> 2);
+        for (int j = 0; j < 16; ++j) hash ^= __float_as_uint(llr[j]) + 0x9e3779b9u + (hash << 6) + (hash >> 2);
         const Attempt A = kLadder[at];
-        if (A.mode != PM_NONE) perturb(base, llr, mt, hash + A.seed_mul * 997u + A.seed_add, A.sigma, A.mode, lane);
+        if (A.mode != PM_NONE) perturb(llr, mt, hash + A.seed_mul * 997u + A.seed_add, A.sigma, A.mode, lane);
         __syncwarp();
         for (int j = lane; j < kN; j += 32) out_g[cw * kN + j] = llr[j];
         __syncwarp();
@@ -314,13 +322,24 @@ int ldpc_retry_launch(ria_ctx* ctx, int rate, int max_iter, const float* llr_dev
     if (frame_mode && (reinterpret_cast<uintptr_t>(ok_dev) & 3) != 0)
         return set_error(ctx, RIA_E_INVAL, "ldpc retry: ok buffer must be 4-byte aligned");
     const int kpad = (t->k + 3) & ~3;
-    const size_t per_warp = (static_cast<size_t>(2 * kN) + kpad + static_cast<size_t>(t->m) * 8 + kMtN) * 4;
-    const size_t smem = ldpc_core::ldpc_tab_bytes(t->k, t->m, t->dv_max) + kRetryWarps * per_warp;
-    if (smem > ctx->smem_optin) return set_error(ctx, RIA_E_UNSUPPORTED, "ldpc retry: kernel does not fit in shared memory");
+    const size_t per_warp = (static_cast<size_t>(kN) + kpad + static_cast<size_t>(t->m) * 8) * 4;
+    // warps (= frames in flight) per CTA: whatever keeps the most of them resident per SM
+    const size_t tab = ldpc_core::ldpc_tab_bytes(t->k, t->m, t->dv_max);
+    int W = 0, best = 0;
+    for (int w = 2; w <= kMaxRetryWarps; ++w) {
+        const size_t need = tab + w * per_warp + 1024;
+        if (need > ctx->smem_optin + 1024) break;
+        const int ctas = static_cast<int>(ctx->smem_per_sm / need);
+        const int warps = ctas * w > 48 ? 48 : ctas * w;
+        if (warps > best) { best = warps; W = w; }
+    }
+    if (W == 0) return set_error(ctx, RIA_E_UNSUPPORTED, "ldpc retry: kernel does not fit in shared memory");
+    const size_t smem = tab + W * per_warp;
     auto kern = ldpc_retry_kernel;
     int ctas_per_sm = 0;
     RIA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
-    RIA_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kRetryWarps * 32, smem));
+    RIA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    RIA_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, W * 32, smem));
     if (ctas_per_sm < 1) return set_error(ctx, RIA_E_UNSUPPORTED, "ldpc retry: kernel does not fit (smem %zu)", smem);
     unsigned* list_len = ctx->work_counter + 40;
     unsigned* counter = ctx->work_counter + 41;
@@ -343,9 +362,9 @@ int ldpc_retry_launch(ria_ctx* ctx, int rate, int max_iter, const float* llr_dev
     if (attempt_dev) RIA_CUDA(ctx, cudaMemsetAsync(attempt_dev, 0, static_cast<size_t>(n_units) * (frame_mode ? 4 : 1), s));
     ldpc_fail_list_kernel<<<blocks, threads, 0, s>>>(ok_dev, n_units, a.per_frame, list_scratch, list_len);
     long long grid = static_cast<long long>(ctx->sm_count) * ctas_per_sm;
-    const long long want = (n_units + kRetryWarps - 1) / kRetryWarps;
+    const long long want = (n_units + W - 1) / W;
     if (grid > want) grid = want;
-    ldpc_retry_kernel<<<static_cast<unsigned>(grid), kRetryWarps * 32, smem, s>>>(a);
+    ldpc_retry_kernel<<<static_cast<unsigned>(grid), W * 32, smem, s>>>(a);
     time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
