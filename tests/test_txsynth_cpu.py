@@ -44,3 +44,19 @@ def test_host_preambles_are_the_reference_samples(ref, ria_lib):
     want = ref.chirp_generate()
     got = sync.chirp_generate_host()
     assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_vectorised_frame_builder_matches_the_reference(ref):
+    """txsynth.make_data_frames (bench / sweep inputs): byte-identical to DataFrame::makeData + serialize, and
+    the 0xD5 chunk-start avoidance keeps the frame valid."""
+    rng = np.random.default_rng(9)
+    payloads = rng.integers(0, 256, size=(40, 219), dtype=np.uint8)
+    frames = txsynth.make_data_frames("K1ABC", "W2XYZ", 65520, payloads)
+    for i in range(len(payloads)):
+        assert bytes(frames[i]) == ref.make_data_frame("K1ABC", "W2XYZ", (65520 + i) & 0xFFFF, payloads[i])
+    payloads[:, 60 - 17] = 0xD5
+    frames = txsynth.make_data_frames("K1ABC", "W2XYZ", 0, payloads, bytes_per_cw=60)
+    assert (frames[:, 60] == 0xD4).all()
+    for i in (0, 7, 39):
+        st = ref.parse_header(bytes(frames[i]))
+        assert st.header_valid and st.frame_crc_ok
