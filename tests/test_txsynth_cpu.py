@@ -49,6 +49,7 @@ def test_host_preambles_are_the_reference_samples(ref, ria_lib):
 def test_vectorised_frame_builder_matches_the_reference(ref):
     """txsynth.make_data_frames (bench / sweep inputs): byte-identical to DataFrame::makeData + serialize, and
     the 0xD5 chunk-start avoidance keeps the frame valid."""
+    from ria_b200 import txsynth
     rng = np.random.default_rng(9)
     payloads = rng.integers(0, 256, size=(40, 219), dtype=np.uint8)
     frames = txsynth.make_data_frames("K1ABC", "W2XYZ", 65520, payloads)
