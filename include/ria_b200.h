@@ -422,11 +422,19 @@ int ria_mcdpsk_rx_frames_host(ria_ctx* ctx, const ria_mcdpsk_config* cfg, const 
                               ria_sync_result* sync);
 
 /* ---- HARQ chase combining ---------------------------------------------------------------------- */
-/* Sync preambles of the reference transmitter, evaluated on the host with the reference's expressions
- * (they do not depend on the payload; a batch needs each once).  Return the number of samples written, or
- * minus the required capacity.
- *   ria_zc_preamble_host     sync::ZCSync::generatePreambleForRoot (src/sync/zc_sync.hpp:133-190)
- *   ria_chirp_generate_host  sync::ChirpSync::generate, dual chirp (src/sync/chirp_sync.hpp:61-108) */
+/* Sync preambles of the transmitter (payload-independent; a batch needs each once).  Every sample is a
+ * closed-form evaluation, bit-identical to the reference (glibc's sinf/cosf incl. the large-argument
+ * reduction are restated in csrc/rn_math.h):
+ *   ria_zc_preamble_*     sync::ZCSync::generatePreambleForRoot (src/sync/zc_sync.hpp:133-190)
+ *   ria_chirp_generate_*  sync::ChirpSync::generate, dual chirp (src/sync/chirp_sync.hpp:61-108)
+ * `_samples` return the preamble length; `_dev` run one thread per sample on the context stream and
+ * write out_dev[cap]; `_host` evaluate the same sample functions on the host (no GPU needed).  `_dev` and
+ * `_host` return the number of samples written; `_host` returns minus the required capacity when `out`
+ * is NULL or too small. */
+int ria_zc_preamble_samples(const ria_zc_config* cfg);
+int ria_chirp_generate_samples(const ria_chirp_config* cfg);
+int ria_zc_preamble_dev(ria_ctx* ctx, const ria_zc_config* cfg, int root, float* out_dev, int cap);
+int ria_chirp_generate_dev(ria_ctx* ctx, const ria_chirp_config* cfg, float* out_dev, int cap);
 int ria_zc_preamble_host(const ria_zc_config* cfg, int root, float* out, int cap);
 int ria_chirp_generate_host(const ria_chirp_config* cfg, float* out, int cap);
 

@@ -81,6 +81,10 @@ _SIGNATURES = {
                                          _vp, _i32, _vp, _vp, _vp]),
     "ria_zc_preamble_host": (_i32, [_vp, _i32, _vp, _i32]),
     "ria_chirp_generate_host": (_i32, [_vp, _vp, _i32]),
+    "ria_zc_preamble_samples": (_i32, [_vp]),
+    "ria_chirp_generate_samples": (_i32, [_vp]),
+    "ria_zc_preamble_dev": (_i32, [_vp, _vp, _i32, _vp, _i32]),
+    "ria_chirp_generate_dev": (_i32, [_vp, _vp, _vp, _i32]),
     "ria_mcdpsk_tx_frame_samples": (_i32, [_vp, _i32]),
     "ria_mcdpsk_tx_frames_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _i64]),
     "ria_chase_combine_batch_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64]),

@@ -13,8 +13,8 @@
 //                                the FMA build on every CPU with FMA3, so a + b*c is one fma).
 // glibc is not part of /root/reference; the restatement is pinned bit-for-bit against the
 // container's libm on 2 x 10^7 arguments per function (tests/test_rn_math_cpu.py), and the same
-// source compiles for the device.  Arguments outside the fast paths (|x| >= 120 for sin/cos) go
-// to a correctly rounded double evaluation; the modem never produces them.
+// source compiles for the device.  |x| >= 120 takes sincosf.h's reduce_large (the preamble generators'
+// phases of several thousand radians go through it).
 #pragma once
 
 #include <math.h>
@@ -153,36 +153,6 @@ RN_HD float glibc_atan2f(float y, float x) {
 // ------------------------------------------------------------------------------------------
 // sinf / cosf / sincosf (ARM optimized-routines as built by glibc with FMA)
 // ------------------------------------------------------------------------------------------
-// correctly rounded fallback for |x| >= 120: Cody-Waite by pi/2 in double + Taylor polynomials
-RN_HD void rn_sincos_d(double x, double* s_out, double* c_out) {
-    if (!(fabs(x) < 1.0e5)) { *s_out = sin(x); *c_out = cos(x); return; }
-    const double n = rint(x * 0.63661977236758138243);
-    double r = fma(-n, 1.57079632679489655800e+00, x);
-    r = fma(-n, 6.12323399573676603587e-17, r);
-    const double r2 = r * r;
-    double sp = -7.6471637318198164759e-13;
-    sp = fma(sp, r2, 1.6059043836821614599e-10);
-    sp = fma(sp, r2, -2.5052108385441718775e-08);
-    sp = fma(sp, r2, 2.7557319223985890653e-06);
-    sp = fma(sp, r2, -1.9841269841269841270e-04);
-    sp = fma(sp, r2, 8.3333333333333333333e-03);
-    sp = fma(sp, r2, -1.6666666666666666667e-01);
-    const double s = fma(sp * r2, r, r);
-    double cp = 4.7794773323873852974e-14;
-    cp = fma(cp, r2, -1.1470745597729724714e-11);
-    cp = fma(cp, r2, 2.0876756987868098979e-09);
-    cp = fma(cp, r2, -2.7557319223985890653e-07);
-    cp = fma(cp, r2, 2.4801587301587301587e-05);
-    cp = fma(cp, r2, -1.3888888888888888889e-03);
-    cp = fma(cp, r2, 4.1666666666666666667e-02);
-    const double c = fma(cp * r2, r2, fma(-0.5, r2, 1.0));
-    const int q = static_cast<int>(n) & 3;
-    const double ss = (q & 1) ? c : s;
-    const double cc = (q & 1) ? s : c;
-    *s_out = (q & 2) ? -ss : ss;
-    *c_out = ((q + 1) & 2) ? -cc : cc;
-}
-
 // sincosf.h: __sincosf_table[0]; table[1] is the same with c0..c4 negated (flip = -1)
 #define RN_SC_C0 0x1p0
 #define RN_SC_C1 -0x1.ffffffd0c621cp-2
@@ -222,6 +192,30 @@ RN_HD double rn_sc_reduce(double x, int* np) {
     return fma(-static_cast<double>(n), RN_SC_HPI, x);
 }
 
+// reduce_large (sincosf.h): |y| >= 120.  The 24 significand bits (shifted by exponent & 7) times a
+// 96-bit window of 2/pi selected by the exponent; the top two bits of the product are the quadrant,
+// the rest is the reduced angle as a signed 62-bit fixed-point fraction of pi/2.
+RN_HD double rn_sc_reduce_large(uint32_t xi, int* np) {
+    // 2/pi = 0.A2F9836E 4E441529 FC2757D1 F534DDC0 DB629599 3C439041 ... (hex), 32-bit windows 8 bits apart
+    const uint32_t inv_pio4[24] = {
+        0x000000a2u, 0x0000a2f9u, 0x00a2f983u, 0xa2f9836eu, 0xf9836e4eu, 0x836e4e44u, 0x6e4e4415u, 0x4e441529u,
+        0x441529fcu, 0x1529fc27u, 0x29fc2757u, 0xfc2757d1u, 0x2757d1f5u, 0x57d1f534u, 0xd1f534ddu, 0xf534ddc0u,
+        0x34ddc0dbu, 0xddc0db62u, 0xc0db6295u, 0xdb629599u, 0x6295993cu, 0x95993c43u, 0x993c4390u, 0x3c439041u};
+    const uint32_t* arr = &inv_pio4[(xi >> 26) & 15];
+    const int shift = (xi >> 23) & 7;
+    xi = (xi & 0xffffffu) | 0x800000u;
+    xi <<= shift;
+    uint64_t res0 = static_cast<uint32_t>(xi * arr[0]);
+    const uint64_t res1 = static_cast<uint64_t>(xi) * arr[4];
+    const uint64_t res2 = static_cast<uint64_t>(xi) * arr[8];
+    res0 = (res2 >> 32) | (res0 << 32);
+    res0 += res1;
+    const uint64_t n = (res0 + (1ULL << 61)) >> 62;
+    res0 -= n << 62;
+    *np = static_cast<int>(n);
+    return static_cast<double>(static_cast<int64_t>(res0)) * 0x1.921FB54442D18p-62;
+}
+
 RN_HD void glibc_sincosf(float y, float* sinp, float* cosp) {
     double x = static_cast<double>(y);
     if (rn_abstop12(y) < rn_abstop12(0x1.921FB6p-1f)) {                     // |y| < pi/4
@@ -239,11 +233,20 @@ RN_HD void glibc_sincosf(float y, float* sinp, float* cosp) {
         const float ps = static_cast<float>(rn_sc_sin(x * s, x2));
         const float pc = static_cast<float>(rn_sc_cos(x2, flip));
         if (n & 1) { *sinp = pc; *cosp = ps; } else { *sinp = ps; *cosp = pc; }
+    } else if (rn_abstop12(y) < rn_abstop12(INFINITY)) {
+        const uint32_t xi = rn_fbits(y);
+        const int sign = static_cast<int>(xi >> 31);
+        int n;
+        x = rn_sc_reduce_large(xi, &n);
+        const int m = n + sign;
+        const double s = ((m & 3) == 1 || (m & 3) == 2) ? -1.0 : 1.0;
+        const double flip = (m & 2) ? -1.0 : 1.0;
+        const double x2 = x * x;
+        const float ps = static_cast<float>(rn_sc_sin(x * s, x2));
+        const float pc = static_cast<float>(rn_sc_cos(x2, flip));
+        if (n & 1) { *sinp = pc; *cosp = ps; } else { *sinp = ps; *cosp = pc; }
     } else {
-        double sd, cd;
-        rn_sincos_d(x, &sd, &cd);
-        *sinp = static_cast<float>(sd);
-        *cosp = static_cast<float>(cd);
+        *sinp = *cosp = y - y;                                             // inf / NaN -> NaN
     }
 }
 
@@ -276,9 +279,15 @@ RN_HD float glibc_sinf(float y) {
         const double flip = (n & 2) ? -1.0 : 1.0;
         return static_cast<float>((n & 1) ? rn_sc_cos(x * x, flip) : rn_sc_sin(x * s, x * x));
     }
-    double sd, cd;
-    rn_sincos_d(x, &sd, &cd);
-    return static_cast<float>(sd);
+    if (!(rn_abstop12(y) < rn_abstop12(INFINITY))) return y - y;
+    const uint32_t xi = rn_fbits(y);
+    const int sign = static_cast<int>(xi >> 31);
+    int n;
+    x = rn_sc_reduce_large(xi, &n);
+    const int m = n + sign;
+    const double s = ((m & 3) == 1 || (m & 3) == 2) ? -1.0 : 1.0;
+    const double flip = (m & 2) ? -1.0 : 1.0;
+    return static_cast<float>((n & 1) ? rn_sc_cos(x * x, flip) : rn_sc_sin(x * s, x * x));
 }
 
 RN_HD float glibc_cosf(float y) {
@@ -296,9 +305,15 @@ RN_HD float glibc_cosf(float y) {
         const double flip = (m & 2) ? -1.0 : 1.0;
         return static_cast<float>(((n ^ 1) & 1) ? rn_sc_cos(x * x, flip) : rn_sc_sin(x * s, x * x));
     }
-    double sd, cd;
-    rn_sincos_d(x, &sd, &cd);
-    return static_cast<float>(cd);
+    if (!(rn_abstop12(y) < rn_abstop12(INFINITY))) return y - y;
+    const uint32_t xi = rn_fbits(y);
+    const int sign = static_cast<int>(xi >> 31);
+    int n;
+    x = rn_sc_reduce_large(xi, &n);
+    const int m = n + sign;
+    const double s = ((m & 3) == 1 || (m & 3) == 2) ? -1.0 : 1.0;
+    const double flip = (m & 2) ? -1.0 : 1.0;
+    return static_cast<float>(((n ^ 1) & 1) ? rn_sc_cos(x * x, flip) : rn_sc_sin(x * s, x * x));
 }
 
 // ------------------------------------------------------------------------------------------

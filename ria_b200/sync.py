@@ -171,3 +171,30 @@ def chirp_generate_host(config: Optional[ChirpConfig] = None) -> np.ndarray:
     got = lib().ria_chirp_generate_host(C.addressof(config), out.ctypes.data, n)
     assert got == n
     return out
+
+
+def zc_preamble(config: Optional[ZCConfig] = None, root: int = 5, device=None,
+                ctx: Optional[Context] = None) -> torch.Tensor:
+    """ZCSync::generatePreambleForRoot on the device (one thread per sample), CUDA fp32 [n]."""
+    config = config or ZCConfig.default()
+    n = lib().ria_zc_preamble_samples(C.addressof(config))
+    if n <= 0:
+        raise RiaError("bad ZC configuration")
+    ctx = ctx or default_context()
+    out = torch.empty(n, dtype=torch.float32, device=device or torch.device("cuda", ctx.device))
+    ctx.set_stream(torch.cuda.current_stream(out.device))
+    ctx.check(min(0, lib().ria_zc_preamble_dev(ctx.handle, C.addressof(config), int(root), _ptr(out), n)))
+    return out
+
+
+def chirp_generate(config: Optional[ChirpConfig] = None, device=None, ctx: Optional[Context] = None) -> torch.Tensor:
+    """ChirpSync::generate (dual chirp) on the device, CUDA fp32 [n]."""
+    config = config or ChirpConfig.default()
+    n = lib().ria_chirp_generate_samples(C.addressof(config))
+    if n <= 0:
+        raise RiaError("bad chirp configuration")
+    ctx = ctx or default_context()
+    out = torch.empty(n, dtype=torch.float32, device=device or torch.device("cuda", ctx.device))
+    ctx.set_stream(torch.cuda.current_stream(out.device))
+    ctx.check(min(0, lib().ria_chirp_generate_dev(ctx.handle, C.addressof(config), _ptr(out), n)))
+    return out

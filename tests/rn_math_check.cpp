@@ -29,13 +29,18 @@ int main(int argc, char** argv) {
         bad_sin += rn_fbits(glibc_sinf(x)) != rn_fbits(sinf(x));
         bad_cos += rn_fbits(glibc_cosf(x)) != rn_fbits(cosf(x));
     }
-    // beyond the fast path the fallback is correctly rounded, glibc is within 1 ulp of that
-    for (long i = 0; i < n / 16; ++i) {
-        const float x = static_cast<float>(u(rng) * 5000.0);
-        float s, c;
+    // |x| >= 120: reduce_large, bit for bit (chirp / ZC preamble phases reach several 10^3 rad)
+    for (long i = 0; i < n / 4; ++i) {
+        const int kind = i % 4;
+        float x = static_cast<float>(kind == 0 ? u(rng) * 5000.0 : kind == 1 ? u(rng) * 3.0e5 : kind == 2 ? u(rng) * 1.0e9
+                                               : std::ldexp(u(rng), static_cast<int>(i % 120) + 7));
+        if (std::fabs(x) < 120.0f) x = std::copysign(120.0f + std::fabs(x), x);
+        float s, c, rs, rc;
         glibc_sincosf(x, &s, &c);
-        bad_large += (std::fabs(static_cast<double>(s) - std::sin(static_cast<double>(x))) > 1.2e-7) +
-                     (std::fabs(static_cast<double>(c) - std::cos(static_cast<double>(x))) > 1.2e-7);
+        sincosf(x, &rs, &rc);
+        bad_large += (rn_fbits(s) != rn_fbits(rs)) + (rn_fbits(c) != rn_fbits(rc));
+        bad_large += rn_fbits(glibc_sinf(x)) != rn_fbits(sinf(x));
+        bad_large += rn_fbits(glibc_cosf(x)) != rn_fbits(cosf(x));
     }
     for (long i = 0; i < n; ++i) {
         const int kind = i % 5;

@@ -107,3 +107,20 @@ def test_new_entry_points_reject_bad_arguments_and_accept_empty_batches(ctx):
     with pytest.raises(ria_b200.RiaError):
         ctx.set_decode_flags(8)
     assert ctx.get_decode_flags() == 0
+
+
+def test_device_preambles_are_the_reference_samples(ctx, ref):
+    """ria_zc_preamble_dev / ria_chirp_generate_dev (one thread per sample, glibc sinf/cosf incl. the
+    large-argument reduction restated in rn_math.h) vs ZCSync::generatePreamble and ChirpSync::generate of
+    the unmodified reference: bit-identical."""
+    from oracle.bindings import ZcConfig
+    from ria_b200 import sync
+    zc = ZcConfig.default()
+    for frame_type, root in ((0, zc.root_ping), (1, zc.root_pong), (2, zc.root_data), (3, zc.root_control)):
+        want = ref.zc_preamble(zc, frame_type)
+        got = sync.zc_preamble(sync.ZCConfig.default(), root, ctx=ctx).cpu().numpy()
+        assert len(got) == len(want)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), frame_type
+    want = ref.chirp_generate()
+    got = sync.chirp_generate(ctx=ctx).cpu().numpy()
+    assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
