@@ -217,6 +217,7 @@ class Ref:
         L.ref_burst_deinterleave.argtypes = [_f32p, C.c_int, _f32p]
         L.ref_ladder_perturb.argtypes = [_f32p, C.c_int, C.c_uint, C.c_float, C.c_int, _f32p]
         L.ref_parse_header.argtypes = [_u8p, C.c_int, C.POINTER(FrameStatus)]
+        L.ref_frame_status_reassembled.argtypes = [_u8p, _u8p, C.c_int, C.POINTER(FrameStatus)]
         L.ref_crc16.argtypes = [_u8p, C.c_int]
         L.ref_crc16.restype = C.c_uint16
         L.ref_make_data_frame.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _u8p, C.c_int, _u8p, C.c_int]
@@ -439,6 +440,15 @@ class Ref:
         data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
         st = FrameStatus()
         self.lib.ref_parse_header(data, len(data), C.byref(st))
+        return st
+
+    def frame_status_reassembled(self, data, ok, bpc: int) -> FrameStatus:
+        """header of codeword 0 + whether CodewordStatus::reassemble() gives a frame DataFrame::deserialize accepts"""
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        ok = np.ascontiguousarray(np.asarray(ok, dtype=np.uint8))
+        assert len(data) >= 4 * bpc and len(ok) == 4
+        st = FrameStatus()
+        self.lib.ref_frame_status_reassembled(data, ok, int(bpc), C.byref(st))
         return st
 
     def crc16(self, data) -> int:

@@ -301,6 +301,32 @@ void ref_parse_header(const uint8_t* data, int len, ria_frame_status* st) {
     }
 }
 
+// What decodeFixedFrame's caller sees for a frame whose codeword results are (ok[c], data[c]): the header of
+// codeword 0 (parseHeader) and whether CodewordStatus::reassemble() (frame_v2.cpp:1030-1066, incl. the
+// DATA_CW_MARKER rule of reassembleCodewords :960-985) yields a frame that DataFrame::deserialize accepts.
+void ref_frame_status_reassembled(const uint8_t* data, const uint8_t* ok, int bpc, ria_frame_status* st) {
+    protocol::v2::CodewordStatus cs;
+    for (int c = 0; c < 4; ++c) {
+        cs.decoded.push_back(ok[c] != 0);
+        cs.data.emplace_back(data + c * bpc, data + (c + 1) * bpc);
+    }
+    std::memset(st, 0, sizeof *st);
+    if (!ok[0]) return;
+    auto hi = protocol::v2::parseHeader(cs.data[0]);
+    st->header_valid = hi.valid ? 1 : 0;
+    st->type = static_cast<uint8_t>(hi.type);
+    st->seq = hi.seq;
+    st->src_hash = hi.src_hash;
+    st->dst_hash = hi.dst_hash;
+    st->total_cw = hi.total_cw;
+    st->payload_len = hi.payload_len;
+    if (hi.valid && !hi.is_control) {
+        Bytes fr = cs.reassemble();
+        auto f = protocol::v2::DataFrame::deserialize(ByteSpan(fr.data(), fr.size()));
+        st->frame_crc_ok = f.has_value() ? 1 : 0;
+    }
+}
+
 uint16_t ref_crc16(const uint8_t* data, int len) {
     return protocol::v2::ControlFrame::calculateCRC(data, static_cast<size_t>(len));
 }

@@ -34,8 +34,24 @@ int ensure_stage(ria_ctx* ctx, int which, size_t dev_bytes, size_t pin_bytes) {
     return RIA_OK;
 }
 
+// Fold the recorded launches into the per-kind totals and release their events (waits for them).
+static void fold_timed(ria_ctx* ctx) {
+    for (auto& t : ctx->timed) {
+        float e = 0.f;
+        if (cudaEventSynchronize(t.stop) == cudaSuccess && cudaEventElapsedTime(&e, t.start, t.stop) == cudaSuccess &&
+            t.kind >= 0 && t.kind < 32) {
+            ctx->timed_ms[t.kind] += e;
+            ctx->timed_n[t.kind] += 1;
+        }
+        cudaEventDestroy(t.start);
+        cudaEventDestroy(t.stop);
+    }
+    ctx->timed.clear();
+}
+
 void time_begin(ria_ctx* ctx, int kind) {
     if (!ctx->timing) return;
+    if (ctx->timed.size() >= 2048) fold_timed(ctx);      // bounded event list however long timing stays on
     ria_ctx::TimedLaunch t{kind, nullptr, nullptr};
     if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) return;
     cudaEventRecord(t.start, ctx->stream);
@@ -76,6 +92,10 @@ extern "C" int ria_ctx_create(int device, ria_ctx** out) {
     ctx->device = device;
     auto fail = [&](cudaError_t err, const char* what) {
         fprintf(stderr, "ria_b200: %s: %s\n", what, cudaGetErrorString(err));
+        for (auto& ev : ctx->stage_ev) if (ev) cudaEventDestroy(ev);
+        if (ctx->work_counter) cudaFree(ctx->work_counter);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+        if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         delete ctx;
         return RIA_E_CUDA;
     };
@@ -161,6 +181,7 @@ extern "C" int ria_ctx_set_timing(ria_ctx* ctx, int enable) {
     if (!ctx) return RIA_E_INVAL;
     for (auto& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
     ctx->timed.clear();
+    for (int k = 0; k < 32; ++k) { ctx->timed_ms[k] = 0.0; ctx->timed_n[k] = 0; }
     ctx->timing = enable != 0;
     return RIA_OK;
 }
@@ -168,18 +189,10 @@ extern "C" int ria_ctx_set_timing(ria_ctx* ctx, int enable) {
 extern "C" int ria_ctx_get_timing(ria_ctx* ctx, int kind, double* total_ms, int64_t* launches) {
     if (!ctx || !total_ms || !launches) return RIA_E_INVAL;
     RIA_CUDA(ctx, cudaSetDevice(ctx->device));
-    double ms = 0.0;
-    int64_t n = 0;
-    for (auto& t : ctx->timed) {
-        if (t.kind != kind) continue;
-        RIA_CUDA(ctx, cudaEventSynchronize(t.stop));
-        float e = 0.f;
-        RIA_CUDA(ctx, cudaEventElapsedTime(&e, t.start, t.stop));
-        ms += e;
-        ++n;
-    }
-    *total_ms = ms;
-    *launches = n;
+    ria::fold_timed(ctx);
+    const bool known = kind >= 0 && kind < 32;
+    *total_ms = known ? ctx->timed_ms[kind] : 0.0;
+    *launches = known ? ctx->timed_n[kind] : 0;
     return RIA_OK;
 }
 

@@ -79,15 +79,28 @@ __device__ __forceinline__ void parse_frame(const uint16_t* __restrict__ crc_tab
     st.payload_len = static_cast<uint16_t>((h[13] << 8) | h[14]);
     const uint16_t rx = static_cast<uint16_t>((h[15] << 8) | h[16]);
     if (rx == crc16_dev(crc_tab, h, 15)) st.header_valid = 1;
-    // needs every codeword that carries part of the frame
+    // Frame CRC over CodewordStatus::reassemble()'s view of the four chunks (:960-985), not over their plain
+    // concatenation: a chunk 1..3 that starts with 0xD5 is taken for a marked codeword (DATA_CW_MARKER,
+    // :974) and loses its first two bytes, so such a frame comes out short or shifted and fails -- the same
+    // rule ria_repair::reassemble applies, so the first-pass-only and the full decode report the same flags.
+    // Every codeword that contributes bytes must have decoded.
     const int expected = 17 + st.payload_len + 2;
     if (st.header_valid && expected <= 4 * bpc) {
         bool have = true;
-        for (int c = 0; c < 4; ++c) if (c * bpc < expected && !st.cw_ok[c]) have = false;
-        if (have) {
-            const uint16_t frx = static_cast<uint16_t>((h[expected - 2] << 8) | h[expected - 1]);
-            st.frame_crc_ok = (frx == crc16_dev(crc_tab, h, expected - 2)) ? 1 : 0;
+        int n = 0;
+        unsigned crc = 0xFFFFu, stored = 0;
+        for (int c = 0; c < 4 && n < expected; ++c) {
+            if (!st.cw_ok[c]) have = false;
+            const uint8_t* chunk = h + c * bpc;
+            const int skip = (c > 0 && bpc >= 2 && chunk[0] == 0xD5) ? 2 : 0;
+            const int take = min(expected - n, bpc - skip);
+            for (int b = 0; b < take; ++b, ++n) {
+                const uint8_t v = chunk[skip + b];
+                if (n < expected - 2) crc = ((crc << 8) & 0xFFFFu) ^ crc_tab[((crc >> 8) ^ v) & 0xFFu];
+                else stored = (stored << 8) | v;
+            }
         }
+        if (have && n == expected) st.frame_crc_ok = (stored == crc) ? 1 : 0;
     }
 }
 
@@ -306,7 +319,7 @@ extern "C" int ria_frame_decode_batch_host(ria_ctx* ctx, int rate, int use_chann
     const int bpc = bytes_per_codeword(rate);
     if (bpc < 0) return set_error(ctx, RIA_E_INVAL, "frame: bad rate %d", rate);
     RIA_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int64_t chunk = 65536;
+    const int64_t chunk = n_frames < 65536 ? n_frames : 65536;      // staging sized to the call, not to the maximum
     const int32_t dstride = (kFrameBits + 3) & ~3;
     const size_t in_b = static_cast<size_t>(chunk) * dstride * sizeof(float);
     const size_t out_b = static_cast<size_t>(chunk) * (4 * bpc + sizeof(ria_frame_status));
@@ -375,7 +388,9 @@ extern "C" int ria_ofdm_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg
     RIA_CUDA(ctx, cudaSetDevice(ctx->device));
     // Chunked pipeline on the context stream with two staging buffers; the H2D of chunk c+1 is
     // issued on the copy stream so it overlaps the kernels of chunk c.
-    const int64_t chunk = 8192;                 // 440 MB per upload (smaller chunks measured slower: 0.86 vs 0.91 M frames/s)
+    // 440 MB per upload at 8192 frames (smaller chunks measured slower: 0.86 vs 0.91 M frames/s); a small
+    // call (the batch-1 adapters) only stages what it brings
+    const int64_t chunk = n_frames < 8192 ? n_frames : 8192;
     const size_t in_b = static_cast<size_t>(chunk) * frame_len * sizeof(float);
     const size_t aux_b = static_cast<size_t>(chunk) * 8;                       // cfo + phase
     const size_t out_b = static_cast<size_t>(chunk) * (4 * bpc + sizeof(ria_frame_status) + 4);

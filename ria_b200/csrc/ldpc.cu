@@ -206,7 +206,7 @@ extern "C" int ria_ldpc_decode_batch_host(ria_ctx* ctx, int rate, int max_iter, 
     if (!llr || !info || !ok || !iters) return set_error(ctx, RIA_E_INVAL, "ldpc: null buffer");
     RIA_CUDA(ctx, cudaSetDevice(ctx->device));
     // Double-buffered chunks: H2D(c+1) overlaps decode(c) overlaps D2H(c-1).
-    const int64_t chunk = 32768;
+    const int64_t chunk = n_cw < 32768 ? n_cw : 32768;
     const size_t in_b = static_cast<size_t>(chunk) * kN * sizeof(float);
     const size_t out_b = static_cast<size_t>(chunk) * (info_stride + 1 + 4);
     for (int b = 0; b < 2; ++b) {

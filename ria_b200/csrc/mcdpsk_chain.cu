@@ -116,7 +116,7 @@ extern "C" int ria_mcdpsk_rx_frames_host(ria_ctx* ctx, const ria_mcdpsk_config* 
     if (n_frames == 0) return RIA_OK;
     if (!samples || !info || !ok || !iters || !sync) return set_error(ctx, RIA_E_INVAL, "mcdpsk rx: null buffer");
     RIA_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int64_t chunk = 512;                                             // ~400 MB of samples per staging buffer
+    const int64_t chunk = n_frames < 512 ? n_frames : 512;                 // <= ~400 MB of samples per staging buffer
     const size_t in_b = static_cast<size_t>(chunk) * row_stride * sizeof(float);
     const size_t acc_b = static_cast<size_t>(chunk) * RIA_LDPC_N * sizeof(float);
     const size_t out_b = static_cast<size_t>(chunk) * (info_stride + 1 + 4 + sizeof(ria_sync_result)) + 1024;

@@ -84,6 +84,8 @@ struct ria_ctx {
     bool timing = false;
     struct TimedLaunch { int kind; cudaEvent_t start, stop; };
     std::vector<TimedLaunch> timed;
+    double timed_ms[32] = {};               // folded totals per kind (the event list is bounded, see time_begin)
+    int64_t timed_n[32] = {};
     // staging for *_host entry points (grown on demand)
     void* stage_dev[2] = {nullptr, nullptr};
     size_t stage_dev_bytes[2] = {0, 0};

@@ -331,36 +331,69 @@ class ChaseCache:
             self._ctx = default_context()
         return self._ctx
 
-    def _prune(self):
+    def _release(self, key, stat, busy, flush):
+        """Drop an entry and recycle its HBM rows.  If an item of the current round already targets those
+        rows, the pending combine launch goes out first: the kernel's contract is one writer per row and
+        launch, and the sequential reference semantics are store-then-evict."""
+        slot = self.entries.pop(key)["slot"]
+        if slot in busy:
+            flush()
+        self.free.append(slot)
+        if stat:
+            self.stats[stat] += 1
+
+    def _prune(self, busy=(), flush=lambda: None):
         now = self._time.monotonic()
         for k in [k for k, e in self.entries.items() if now - e["created"] > self.ttl]:
-            self.free.append(self.entries.pop(k)["slot"])
-            self.stats["entries_expired"] += 1
+            self._release(k, "entries_expired", busy, flush)
 
-    def _evict(self):
+    def _evict(self, busy=(), flush=lambda: None):
         while len(self.entries) >= self.max_entries:
             k = min(self.entries, key=lambda q: self.entries[q]["last"])
-            self.free.append(self.entries.pop(k)["slot"])
-            self.stats["entries_evicted"] += 1
+            self._release(k, "entries_evicted", busy, flush)
+
+    def _launch(self, items, slots, first, soft):
+        if not items:
+            return
+        ctx = self.ctx
+        ctx.set_stream(torch.cuda.current_stream(self.device))
+        idx = np.asarray(items, np.int64)
+        d_slots = torch.from_numpy(slots[idx]).to(self.device)
+        d_first = torch.from_numpy(first[idx]).to(self.device)
+        rows = soft if len(idx) == soft.shape[0] else soft.index_select(0, torch.from_numpy(idx).to(self.device))
+        ctx.check(lib().ria_chase_combine_batch_dev(
+            ctx.handle, self.acc.data_ptr(), d_slots.data_ptr(), d_first.data_ptr(), rows.data_ptr(),
+            rows.stride(0), len(idx)))
 
     def store_batch(self, keys, cw_indices, total_cws, soft: torch.Tensor):
         """One reception round: item i stores soft[i] (CUDA fp32 [n, >=648]) under keys[i] /
-        cw_indices[i].  Returns a list of bools like ChaseCache::store."""
+        cw_indices[i].  Returns a list of bools like ChaseCache::store.  Items are applied in order with the
+        reference's sequential semantics; normally that is ONE kernel launch, and an extra launch only when
+        an eviction / expiry inside the round recycles rows that an earlier item of the round wrote."""
         n = len(keys)
         assert soft.is_cuda and soft.dtype == torch.float32 and soft.shape[0] == n and soft.shape[1] >= LDPC_N
+        if soft.stride(1) != 1:
+            soft = soft.contiguous()
         slots = np.full(n, -1, np.int32)
         first = np.zeros(n, np.uint8)
         ok = [False] * n
         seen = set()
+        pending, busy = [], set()          # items not yet launched / entry slots they write
+
+        def flush():
+            self._launch(pending, slots, first, soft)
+            pending.clear()
+            busy.clear()
+
         for i, (key, cw, total) in enumerate(zip(keys, cw_indices, total_cws)):
             if not self.enabled or cw < 0 or cw >= total or total <= 0 or total > self.max_cw or (key, cw) in seen:
                 continue
             self.stats["stores"] += 1
-            self._prune()
+            self._prune(busy, flush)
             e = self.entries.get(key)
             now = self._time.monotonic()
             if e is None:
-                self._evict()
+                self._evict(busy, flush)
                 e = dict(slot=self.free.pop(), total_cw=total, counts=[0] * total, decoded=[False] * total,
                          created=now, last=now)
                 self.entries[key] = e
@@ -373,17 +406,10 @@ class ChaseCache:
                 self.stats["combines"] += 1
             e["counts"][cw] += 1
             seen.add((key, cw))
+            pending.append(i)
+            busy.add(e["slot"])
             ok[i] = True
-        if n:
-            ctx = self.ctx
-            ctx.set_stream(torch.cuda.current_stream(self.device))
-            d_slots = torch.from_numpy(slots).to(self.device)
-            d_first = torch.from_numpy(first).to(self.device)
-            if soft.stride(1) != 1:
-                soft = soft.contiguous()
-            ctx.check(lib().ria_chase_combine_batch_dev(
-                ctx.handle, self.acc.data_ptr(), d_slots.data_ptr(), d_first.data_ptr(), soft.data_ptr(),
-                soft.stride(0), n))
+        flush()
         return ok
 
     def store(self, key, cw_index: int, soft_bits, total_cw: int) -> bool:

@@ -64,29 +64,38 @@ class ModeCache:
             cfg = ofdm.ModemConfig.for_waveform(rec.modulation, rec.rate)
             pool, raw = txsynth.make_frame_pool(cfg, rec.rate, POOL, seed=int(rng.integers(1 << 30)))
             chain = ofdm.OfdmRxChain(cfg, rec.rate, True, self.ctx)
+            sent = np.stack([np.frombuffer(fr, dtype=np.uint8) for fr in raw])        # every frame is 4 x bytes_per_cw long
             mode = dict(kind="ofdm", name=f"OFDM mod{rec.modulation} R{rec.rate}",
-                        pool=torch.from_numpy(pool).to(self.device), chain=chain)
+                        pool=torch.from_numpy(pool).to(self.device), chain=chain,
+                        sent=torch.from_numpy(sent).to(self.device))
         self.modes[key] = mode
         return mode
 
 
 def run_point(mode, snr_db, n_local, first_id, channel_cfg, seed, ctx, device):
-    """-> int64 tensor [frames, frames_ok] for this rank's shard."""
+    """-> int64 tensor [frames, frames_ok, crc_ok_but_wrong] for this rank's shard.  A frame counts as decoded
+    only when its bytes are the bytes that were sent: the false-positive repair of decodeFixedFrame tries tens
+    of thousands of bit flips against a 16-bit CRC, so CRC-valid frames with a wrong payload exist and are
+    reported separately."""
     import torch
     from ria_b200 import sim
     snr = torch.full((n_local,), float(snr_db), dtype=torch.float32, device=device)
     rx = sim.watterson_batch(channel_cfg, mode["pool"], n_local, snr, seed=seed, first_frame_id=first_id, ctx=ctx)
     if mode["kind"] == "ofdm":
-        from ria_b200 import dist as rdist
-        _, status, _ = mode["chain"].process_batch(rx)
-        c = rdist.frame_counters(status)
-        return torch.stack([c[0], c[1]])
+        from ria_b200 import ofdm as ofdm_mod
+        data, status, _ = mode["chain"].process_batch(rx)
+        st = status.view(torch.uint8)
+        off = {k: ofdm_mod.FRAME_STATUS_DTYPE.fields[k][1] for k in ("all_ok", "header_valid", "frame_crc_ok")}
+        crc_ok = (st[:, off["all_ok"]] == 1) & (st[:, off["header_valid"]] == 1) & (st[:, off["frame_crc_ok"]] == 1)
+        want = mode["sent"][(torch.arange(n_local, device=device) + first_id) % POOL]
+        same = (data[:, : want.shape[1]] == want).all(dim=1)
+        return torch.stack([torch.tensor(n_local, device=device), (crc_ok & same).sum(), (crc_ok & ~same).sum()]).to(torch.int64)
     out = mode["dem"].process_batch(rx)
     info, ok, _ = mode["dec"].decode_batch(out["llr"][:, :648].contiguous())
     nbytes = (mode["k"] + 7) // 8
     want = mode["sent"][(torch.arange(n_local, device=device) + first_id) % POOL]
-    good = ok.bool() & (info[:, :nbytes] == want[:, :nbytes]).all(dim=1)
-    return torch.stack([torch.tensor(n_local, device=device), good.sum()]).to(torch.int64)
+    same = (info[:, :nbytes] == want[:, :nbytes]).all(dim=1)
+    return torch.stack([torch.tensor(n_local, device=device), (ok.bool() & same).sum(), (ok.bool() & ~same).sum()]).to(torch.int64)
 
 
 def run_sweep(args):
@@ -118,9 +127,9 @@ def run_sweep(args):
             c = rdist.allreduce_counters(c)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        frames, ok = int(c[0]), int(c[1])
+        frames, ok, wrong = int(c[0]), int(c[1]), int(c[2])
         line = {"snr_db": float(snr_db), "mode": mode["name"], "frames": frames, "frames_ok": ok,
-                "fer": 1.0 - ok / max(1, frames), "estimated_throughput_bps": float(rec.estimated_throughput_bps),
+                "crc_ok_but_wrong_payload": wrong, "fer": 1.0 - ok / max(1, frames), "estimated_throughput_bps": float(rec.estimated_throughput_bps),
                 "frames_per_s": frames / dt}
         results.append(line)
         if rank == 0 and not args.quiet:

@@ -46,6 +46,38 @@ def test_chase_combine_matches_reference(ctx, ref, port):
     assert small.size() == 2 and small.stats["entries_evicted"] == 1 and small.getCombined(("a",), 0) is None
 
 
+def test_chase_round_with_more_keys_than_entries_is_sequential(ctx):
+    """A round that brings more new keys than max_entries: evictions recycle rows that earlier items of the
+    same round wrote, so store_batch must split the launch there.  The result has to be what item-by-item
+    ChaseCache::store calls give (chase_cache.cpp:27-88): same surviving entries, same accumulated soft bits."""
+    import torch
+    from ria_b200 import fec
+    rng = np.random.default_rng(5)
+    n = 40
+    soft = torch.from_numpy(rng.standard_normal((n, 648)).astype(np.float32)).cuda()
+    # keys 0..9 twice (second copy combines), then 20 new keys that evict them while the round is open
+    keys = [(k % 10, 1, 2) for k in range(20)] + [(100 + k, 1, 2) for k in range(20)]
+    cws = [int(c) for c in rng.integers(0, 3, size=n)]
+    seen, cw_fixed = set(), []
+    for k, c in zip(keys, cws):                      # a (key, cw) pair appears once per round
+        while (k, c) in seen:
+            c = (c + 1) % 3
+        seen.add((k, c)); cw_fixed.append(c)
+    batched = fec.ChaseCache(max_entries=8, max_cw=4, ctx=ctx)
+    ok_b = batched.store_batch(keys, cw_fixed, [3] * n, soft)
+    seq = fec.ChaseCache(max_entries=8, max_cw=4, ctx=ctx)
+    ok_s = [seq.store_batch([keys[i]], [cw_fixed[i]], [3], soft[i:i + 1])[0] for i in range(n)]
+    torch.cuda.synchronize()
+    assert ok_b == ok_s and batched.stats == seq.stats
+    assert set(batched.entries) == set(seq.entries) and len(batched.entries) == 8
+    for key, e in seq.entries.items():
+        for cw in range(3):
+            a, b = seq.getCombined(key, cw), batched.getCombined(key, cw)
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert torch.equal(a, b), (key, cw)
+
+
 def test_watterson_statistics_vs_reference(ctx, ref):
     import torch
     from ria_b200 import sim
