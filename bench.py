@@ -10,10 +10,22 @@ scaling: fixed per-GPU batch, no data-path collective) and the only exchange is 
 the error counters.
 
 Workloads
-  ofdm_qam64   (default) BASELINE.json configs[3]: OFDM QAM64 R3/4 coherent, 15 pilots, 1024-FFT
-               CP 96, AWGN 28 dB, 1M frames per GPU: presynced demod -> de-interleave -> 4 x LDPC
-               -> header/CRC, i.e. "decoded frames/s".
-  ldpc         BASELINE.json configs[1]: LDPC R1/4..R3/4 decode of 1M codewords per rate.
+  ofdm_qam64      (default) BASELINE.json configs[3]: OFDM QAM64 R3/4 coherent, 15 pilots, 1024-FFT
+                  CP 96, AWGN 28 dB, 1M frames per GPU: presynced demod -> de-interleave -> 4 x LDPC
+                  -> header/CRC, i.e. "decoded frames/s".
+  ofdm_qam64_cfo  the same chain on frames that arrive with the CFO / mixer phase of their sync
+                  (integer TX carrier offsets in [-3, 3] Hz, told to the receiver with a +-0.2 Hz estimation
+                  error): what production hands to the demodulator.  (SURVEY asks for U(-5, 5):
+                  beyond +-3 Hz the REFERENCE demodulator's own LTS noise estimate drops below 29 dB even with
+                  a perfect estimate and its QAM64 R3/4 frames stop decoding -- measured, DESIGN.md section 4 --
+                  so wider offsets would time the retry ladder, not the CFO path.)
+  ldpc            BASELINE.json configs[1]: LDPC R1/4..R3/4 decode of 1M codewords per rate.
+  mcdpsk          BASELINE.json configs[2]: chirp-acquired MC-DPSK DBPSK 4x at -8 dB, HARQ chase combining.
+
+The default run times ofdm_qam64 as the headline and then a short pass of each of the other three; their
+results (with their own roofline / cpu_baseline / e2e) are in the line's "extra_workloads" object, so that
+they are driver-measured too.  The CPU legs (cpu_baseline, --impl reference) live in oracle/cpu_bench.py and
+never load the product library.
 """
 from __future__ import annotations
 
@@ -47,6 +59,19 @@ def measured_peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def sm_peaks():
+    """SM-side denominators (fp32 rate, shared-memory bandwidth) for the kernels SURVEY.md 8(d) bounds by SM
+    throughput: measured on this pool's B200 with profiles/peaks.cu (committed result), else nominal."""
+    p = os.path.join(ROOT, "profiles", "r2_sm_peaks.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"fp32_tflops": float(d["fp32_fma_tflops"]), "fp32_unfused_tflops": float(d["fp32_unfused_tflops"]),
+                "smem_gbs": 1e3 * float(d["smem_lds128_tb_per_s"]),
+                "source": "measured (profiles/r2_sm_peaks.json: profiles/peaks.cu on this pool's B200)"}
+    return {"fp32_tflops": 148 * 128 * 2 * 1.965e-3, "fp32_unfused_tflops": 148 * 128 * 1.965e-3,
+            "smem_gbs": 148 * 128 * 1.965, "source": "nominal (148 SMs x 128 lanes / 128 B per clock x 1965 MHz)"}
 
 
 class ClockSampler:
@@ -108,8 +133,30 @@ def dist_env():
             int(os.environ.get("LOCAL_RANK", "0")))
 
 
-def host_cores():
-    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+def pin_rank_to_cores(local_rank: int, world: int):
+    """Give every rank its own block of host cores (and, through first touch, host memory near them) so that
+    eight ranks staging ~50 GB/s each do not pile onto one socket's cores.  No effect at world == 1."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // world)
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return [mine[0], mine[-1]]
+    except OSError:
+        return None
+
+
+def hbm_roofline(kern_name, kern_ms, n_launch, alg_bytes_step, steps, traffic=None, traffic_src=None):
+    peak, peak_src = measured_peaks()
+    kern_s = kern_ms / max(1, n_launch) * 1e-3
+    bytes_per_launch = alg_bytes_step * steps / max(1, n_launch)
+    achieved = bytes_per_launch / kern_s / 1e9 if kern_s > 0 else 0.0
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kern_name,
+            "kernel_ms_per_launch": kern_s * 1e3, "launches_per_step": n_launch / steps,
+            "algorithmic_bytes_per_launch": bytes_per_launch}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -117,60 +164,68 @@ def host_cores():
 # ---------------------------------------------------------------------------------------------
 
 class OfdmQam64Workload:
-    name = "ofdm_qam64_r34_15pilots_awgn28dB"
     metric = "decoded_frames_per_s"
     unit = "frames/s"
     dtype = "f32"
     MOD, RATE, SPACING, SNR_DB = 8, 4, 4, 28.0          # QAM64, R3/4, pilot every 4th carrier
-    POOL = 64
+    FRAME_LEN, SYMBOL, PILOTS, DATA_CARRIERS = 12 * 1120, 1120, 15, 44
+    CPU_SAMPLE = 6000
 
-    def __init__(self, n_frames: int):
+    def __init__(self, n_frames: int, cfo_span: float = 0.0):
         self.n = n_frames
-        self._pool = None
-        self.frame_len = 12 * 1120
+        self.cfo_span = float(cfo_span)
+        self.key = "ofdm_qam64_cfo" if cfo_span else "ofdm_qam64"
+        self.name = "ofdm_qam64_r34_15pilots_awgn28dB" + (f"_synccfo{int(cfo_span)}Hz" if cfo_span else "")
+        self.frame_len = self.FRAME_LEN
 
-    def cfg(self):
-        from ria_b200 import ofdm
-        return ofdm.ModemConfig.high_throughput(self.MOD)
+    def cpu_params(self):
+        return {"modulation": self.MOD, "pilot_spacing": self.SPACING, "rate": self.RATE, "snr_db": self.SNR_DB,
+                "pool": 64, "cfo_span": self.cfo_span}
 
-    def pool_host(self, seed=11):
-        """POOL distinct clean TX frames (host numpy TX synthesiser) and their frame bytes."""
-        if self._pool is None:
-            from ria_b200 import txsynth
-            self._pool = txsynth.make_frame_pool(self.cfg(), self.RATE, self.POOL, seed=seed)
-            self.frame_len = self._pool[0].shape[1]
-        return self._pool
+    def cpu_baseline(self, sample):
+        from oracle import cpu_bench
+        return cpu_bench.cpu_ofdm(self.cpu_params(), sample)
 
     def describe(self):
-        c = self.cfg()
-        L = c.getSymbolDuration()
-        return {"workload": self.name, "frames_per_gpu": self.n, "frame_samples": self.frame_len,
-                "modulation": "QAM64", "code_rate": "R3/4", "fft": 1024, "cp": L - 1024,
-                "carriers": 59, "pilots": c.getPilotCarriers(), "data_carriers": c.getDataCarriers(),
-                "channel": f"AWGN {self.SNR_DB} dB generated on the device (Philox); every frame has its own payload, "
-                           "encodeFixedFrame + OFDM TX on the device (sample-identical to the reference transmitter)",
-                "chain": "mix+CFO+CP+FFT1024+LTS/pilot est+MMSE+QAM64 LLR -> frame/channel "
-                         "de-interleave -> complete v2::decodeFixedFrame (4x LDPC R3/4 0.9375/60 it, retry ladder and "
-                         "false-positive repair armed: RIA_DECODE_FULL) -> header+CRC16",
-                "l2": "input batch (53.8 GB at 1M frames) exceeds the 126 MB L2; no flush needed"}
+        d = {"workload": self.name, "frames_per_gpu": self.n, "frame_samples": self.frame_len,
+             "modulation": "QAM64", "code_rate": "R3/4", "fft": 1024, "cp": self.SYMBOL - 1024,
+             "carriers": 59, "pilots": self.PILOTS, "data_carriers": self.DATA_CARRIERS,
+             "channel": f"AWGN {self.SNR_DB} dB generated on the device (Philox); every frame has its own payload, "
+                        "encodeFixedFrame + OFDM TX on the device (sample-identical to the reference transmitter)",
+             "chain": "mix+CFO+CP+FFT1024+LTS/pilot est+MMSE+QAM64 LLR -> frame/channel "
+                      "de-interleave -> complete v2::decodeFixedFrame (4x LDPC R3/4 0.9375/60 it, retry ladder and "
+                      "false-positive repair armed: RIA_DECODE_FULL) -> header+CRC16",
+             "l2": f"input batch ({self.n * self.frame_len * 4 / 1e9:.1f} GB) exceeds the 126 MB L2; no flush needed"}
+        if self.cfo_span:
+            d["cfo"] = (f"TX carrier offset by an integer in [-{self.cfo_span:.0f}, {self.cfo_span:.0f}] Hz per frame; the "
+                        "receiver is told that offset +- U(0, 0.2) Hz (a sync estimate) and the mixer phase 0")
+        return d
 
     def setup(self, ctx, device, rank, world):
         import torch
-        from ria_b200 import ofdm, sim
+        import ria_b200
+        from ria_b200 import ofdm, sim, txsynth
         self.torch, self.ctx = torch, ctx
+        cfg = ofdm.ModemConfig.high_throughput(self.MOD)
+        assert (cfg.getSymbolDuration(), cfg.getPilotCarriers(), cfg.getDataCarriers()) == (self.SYMBOL, self.PILOTS, self.DATA_CARRIERS)
         # Every frame is its own transmission: payload bytes (host RNG) -> v2 data frame (header, CRCs) ->
         # encodeFixedFrame, OFDM training + modulate and the AWGN channel on the device
         # (ria_encode_fixed_frame_batch_dev / ria_ofdm_tx_frames_dev are byte- / sample-identical to the
         # reference transmitter, tests/test_tx_gpu.py).  Generated in chunks so that only one chunk of clean
         # TX samples exists next to the resident RX batch.
-        from ria_b200 import txsynth
         bpc = 60
         self.first_id = rank * self.n                       # global frame ids: sharding-independent payloads and noise
-        cfg = self.cfg()
         bps = cfg.getDataCarriers() * 6
         self.samples = torch.empty((self.n, self.frame_len), dtype=torch.float32, device=device)
         self.sent_len = 4 * bpc - 2
         self.sent_dev = torch.empty((self.n, self.sent_len), dtype=torch.uint8, device=device)
+        self.cfo = self.phase = None
+        if self.cfo_span:
+            g = torch.Generator(device=device).manual_seed(77 + rank)
+            span = int(self.cfo_span)
+            self.tx_off = torch.randint(-span, span + 1, (self.n,), device=device, generator=g)
+            self.cfo = (self.tx_off.float() + (torch.rand(self.n, device=device, generator=g) * 0.4 - 0.2)).contiguous()
+            self.phase = torch.zeros(self.n, dtype=torch.float32, device=device)
         chunk = 65536
         for off in range(0, self.n, chunk):
             m = min(chunk, self.n - off)
@@ -182,24 +237,36 @@ class OfdmQam64Workload:
             coded = ofdm.encode_fixed_frame_batch(fr_dev, self.RATE, True, bps, ctx)
             tx = ofdm.ofdm_tx_frames(cfg, coded, ctx)
             assert tx.shape[1] == self.frame_len
+            gid = self.first_id + off
+            if self.cfo_span:
+                # a transmitter whose carrier is off by d Hz IS the frequency-shifted signal: re-modulate the
+                # frames of each offset group with center_freq + d (row i here is frame i of the chunk; the
+                # roll below only re-orders rows for the channel's pool indexing)
+                offs = self.tx_off[off:off + m]
+                for d in range(-int(self.cfo_span), int(self.cfo_span) + 1):
+                    idx = (offs == d).nonzero().flatten()
+                    if d == 0 or idx.numel() == 0:
+                        continue
+                    cfg_d = ofdm.ModemConfig.from_buffer_copy(bytes(cfg))
+                    cfg_d.center_freq = cfg.center_freq + d
+                    tx[idx] = ofdm.ofdm_tx_frames(cfg_d, coded[idx].contiguous(), ctx)
             # the channel takes TX row (global id % pool rows) and keys its noise by the global id: with the
             # chunk as the pool, rotate it so that frame i of the chunk sits in row (gid + i) % m
-            gid = self.first_id + off
             if gid % m:
                 tx = torch.roll(tx, shifts=gid % m, dims=0)
             sim.awgn_batch(tx, m, self.SNR_DB, seed=2026, first_frame_id=gid, out=self.samples[off:off + m], ctx=ctx)
             del tx, coded, fr_dev
-        import ria_b200
         ctx.set_decode_flags(ria_b200.DECODE_FULL)          # the reference's complete decodeFixedFrame
-        self.chain = ofdm.OfdmRxChain(self.cfg(), self.RATE, True, ctx)
+        self.chain = ofdm.OfdmRxChain(cfg, self.RATE, True, ctx)
         self.out = None
         torch.cuda.synchronize()
 
-    def step(self):
-        self.out = self.chain.process_batch(self.samples)
+    def release(self):
+        self.samples = self.sent_dev = self.out = self.cfo = self.phase = None
+        self._pin = self.e2e_host = None
 
-    def launches_per_step(self):
-        return 3
+    def step(self):
+        self.out = self.chain.process_batch(self.samples, self.cfo, self.phase)
 
     def units_per_step(self):
         return float(self.n)
@@ -214,6 +281,7 @@ class OfdmQam64Workload:
         n_sym, nc, n_llr = 12, 59, 10 * 44 * 6
         samples, bins, llr = self.frame_len * 4, n_sym * nc * 8, n_llr * 4
         return {
+            KK_OFDM_PHASE: ("ofdm_phase_scan_kernel (CFO phase accumulator, CFO frames only)", self.n * 8 if self.cfo_span else 0),
             KK_OFDM_FFT: ("ofdm_fft_kernel", self.n * (samples + bins)),
             KK_OFDM_CARRIER: ("ofdm_carrier_kernel", self.n * (bins + llr)),
             KK_OFDM_DEMOD: ("ofdm_presynced_kernel (residual-CFO re-run frames only)", 0),
@@ -223,6 +291,19 @@ class OfdmQam64Workload:
             KK_FRAME_REPAIR: ("frame_repair_list_kernel + frame_repair_kernel (false-positive repair, invalid frames only)",
                               self.n * (4 + 4 * 60)),
         }
+
+    def roofline(self, kern_ms, steps, counters):
+        """dominant kernel = most device time in the step; HBM bound (demod / FFT / demap stages)"""
+        kinfo = self.kernels()
+        dom = max(kern_ms, key=lambda k: kern_ms[k][0])
+        name, bytes_step = kinfo[dom]
+        ms, n_launch = kern_ms[dom]
+        traffic = measured_traffic("ofdm_qam64", name, self.n * steps / max(1, n_launch))
+        r = hbm_roofline(name, ms, n_launch, bytes_step, steps, traffic,
+                         "profiles/r*_traffic.json: dram bytes per frame of this kernel from one ncu --set full capture "
+                         "x frames per launch" if traffic else None)
+        r["note"] = "dominant kernel = most device time in the step; see DESIGN.md section 3 for the per-frame byte counts"
+        return r
 
     def counters(self):
         """[frames, frames_ok (4/4 cw + header + frame CRC), cw_fail, frames_payload_wrong, sum_iters]"""
@@ -257,9 +338,11 @@ class OfdmQam64Workload:
         torch.cuda.synchronize()
         self._pin = pin
         self.e2e_host = pin.numpy()
+        self.e2e_cfo = self.cfo[:n_e2e].cpu().numpy() if self.cfo is not None else None
+        self.e2e_phase = self.phase[:n_e2e].cpu().numpy() if self.phase is not None else None
 
     def step_e2e(self):
-        return self.chain.process_batch_host(self.e2e_host)
+        return self.chain.process_batch_host(self.e2e_host, self.e2e_cfo, self.e2e_phase)
 
     def e2e_units(self):
         return float(self.e2e_n)
@@ -269,60 +352,8 @@ class OfdmQam64Workload:
         # ria_ofdm_rx_frames_host copies only the 1024-sample FFT window of each 1120-sample symbol (the
         # cyclic prefix is never read by the demodulator): 12 x 1024 x 4 B per frame cross PCIe
         sym_copied = 1024 if os.environ.get("RIA_H2D_FULL_SYMBOLS") != "1" else 1120
-        return (self.e2e_n * (self.frame_len // 1120) * sym_copied * 4,
+        return (self.e2e_n * (self.frame_len // 1120) * sym_copied * 4 + (8 * self.e2e_n if self.cfo_span else 0),
                 self.e2e_n * (240 + ofdm.FRAME_STATUS_DTYPE.itemsize + 4))
-
-
-def _cpu_ofdm_worker(args):
-    """One process per core: make its own received frames (untimed), then time the reference's
-    processPresynced + the complete v2::decodeFixedFrame (first pass, retry ladder, false-positive repair) +
-    parseHeader on them."""
-    _, n_frames, seed, kind = args
-    from oracle.bindings import ModemConfig, Ref
-    wl = OfdmQam64Workload(n_frames)
-    ref = Ref()
-    pool, raw = wl.pool_host()
-    cfg = ModemConfig.from_buffer_copy(bytes(wl.cfg()))
-    rng = np.random.default_rng(seed)
-    bps = cfg.data_carriers() * 6
-    frames = []
-    for i in range(n_frames):
-        tx = pool[i % len(pool)]
-        p = float(np.mean(tx.astype(np.float64) ** 2))
-        frames.append((tx + rng.standard_normal(len(tx)).astype(np.float32) *
-                       np.float32(np.sqrt(p / 10 ** (wl.SNR_DB / 10)))).astype(np.float32))
-    ok = 0
-    t0 = time.perf_counter()
-    for rx in frames:
-        r = ref.ofdm_process_presynced(cfg, rx, 0.0, 0.0)
-        data, cw_ok = ref.decode_fixed_frame_full(r["soft"], wl.RATE, True, bps)
-        st = ref.parse_header(data)
-        ok += int(cw_ok.all() and st.frame_crc_ok)
-    return time.perf_counter() - t0, ok
-
-
-_OFDM_POOL_CACHE = {}
-
-
-def cpu_baseline_ofdm(wl, frames_per_core):
-    import multiprocessing as mp
-    from oracle.bindings import Ref
-    if not Ref.available():
-        return {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference",
-                "sample": "oracle/_ref/libria_ref.so not present"}
-    cores = host_cores()
-    jobs = [("ofdm_qam64", frames_per_core, 1000 + 17 * c, "reference") for c in range(cores)]
-    t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_cpu_ofdm_worker, jobs, chunksize=1)
-    wall = time.perf_counter() - t0
-    rate = sum(frames_per_core / b for b, _ in res)
-    ok = sum(o for _, o in res)
-    return {"value": rate, "unit": "frames/s", "cores": cores, "kind": "reference",
-            "sample": f"{frames_per_core} frames per core x {cores} cores "
-                      f"({ok}/{frames_per_core * cores} decoded with valid CRC), reference "
-                      f"processPresynced + complete decodeFixedFrame + parseHeader, one process "
-                      f"per core, {wall:.1f} s wall, {max(b for b, _ in res):.1f} s max busy"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -335,41 +366,34 @@ class McdpskC3Workload:
     samples of the row (streaming_decoder.cpp:408-411), the frame is demodulated at the detected
     training start with the detected CFO, its soft bits are chase-combined with the previous
     reception and the LDPC R1/4 codeword is decoded.  A step is both receptions of all frames."""
+    key = "mcdpsk"
     name = "mcdpsk_dbpsk_10car_4x_awgn-8dB_chirp_chase"
     metric = "decoded_frames_per_s"
     unit = "frames/s"
     dtype = "f32"
     RATE, MAX_ITER, FACTOR, SNR_DB, POOL, LEAD, TAIL, WINDOW = 0, 50, 0.9375, -8.0, 64, 2000, 800, 120000
+    PREAMBLE, FRAME_LEN = 57600, 4096 + 512 + 133120         # dual chirp; 8 training + 1 reference + 65 x 4 data symbols
+    CHIRP_FLOP_PER_WINDOW = 4 * 5 * 131072 * 17              # SURVEY.md 8(d) K2: two (FFT + IFFT) pairs of 131072 points
+    CPU_SAMPLE = 16
 
     def __init__(self, n_frames: int):
         self.n = n_frames
-        self._pool = None
-        self.row_len = self.frame_len = 0
+        self.frame_len = self.FRAME_LEN
+        self.row_len = self.LEAD + self.PREAMBLE + self.FRAME_LEN + self.TAIL
+
+    def cpu_params(self):
+        return {"pool": 16, "lead": self.LEAD, "tail": self.TAIL, "rate": self.RATE, "snr_db": self.SNR_DB,
+                "window": self.WINDOW, "max_iter": self.MAX_ITER, "factor": self.FACTOR}
+
+    def cpu_baseline(self, sample):
+        from oracle import cpu_bench
+        return cpu_bench.cpu_mcdpsk(self.cpu_params(), sample)
 
     def cfg(self):
         from ria_b200 import mcdpsk
         return mcdpsk.MultiCarrierDPSKConfig.level4_dbpsk(mcdpsk.SPREAD_4X)
 
-    def pool_host(self, seed=31):
-        if self._pool is None:
-            from ria_b200 import txsynth
-            rng = np.random.default_rng(seed)
-            pre = txsynth.chirp_preamble()
-            rows, sent = [], []
-            for _ in range(self.POOL):
-                data = rng.integers(0, 256, size=20, dtype=np.uint8)
-                info_bits = np.concatenate([np.unpackbits(data), np.zeros(2, np.uint8)])       # k = 162
-                cw = np.packbits(txsynth.ldpc_encode_bits(info_bits, self.RATE))
-                body = txsynth.mcdpsk_modulate_frame(self.cfg(), cw.tobytes())
-                self.frame_len = len(body)
-                rows.append(np.concatenate([np.zeros(self.LEAD, np.float32), pre, body, np.zeros(self.TAIL, np.float32)]))
-                sent.append(data)
-            self._pool = (np.stack(rows), np.stack(sent))
-            self.row_len = self._pool[0].shape[1]
-        return self._pool
-
     def describe(self):
-        self.pool_host()
         return {"workload": self.name, "frames_per_gpu": self.n, "receptions_per_frame": 2,
                 "row_samples": self.row_len, "frame_samples": self.frame_len, "modulation": "DBPSK",
                 "carriers": 10, "spreading": 4, "code_rate": "R1/4",
@@ -378,15 +402,25 @@ class McdpskC3Workload:
                 "chain": "per reception: AWGN -> dual-chirp sync (131072-pt FFT matched filter) -> Hilbert CFO "
                          "correction -> 10-carrier correlation demod + 4x despreading -> chase combine -> "
                          "LDPC R1/4 (0.9375, 50 it)",
-                "l2": "one reception of the batch (78 GB at 100k frames) exceeds the 126 MB L2; no flush needed"}
+                "l2": f"one reception of the batch ({self.n * self.row_len * 4 / 1e9:.1f} GB) exceeds the 126 MB L2; no flush needed"}
 
     def setup(self, ctx, device, rank, world):
         import torch
-        from ria_b200 import mcdpsk
+        from ria_b200 import mcdpsk, sync, txsynth
         self.torch, self.ctx, self.device = torch, ctx, device
-        pool, sent = self.pool_host()
-        self.pool_dev = torch.from_numpy(pool).to(device)
-        self.sent_dev = torch.from_numpy(sent).to(device)
+        # TX pool on the device: LDPC-encoded payloads -> MC-DPSK modulator, behind the dual-chirp preamble
+        rng = np.random.default_rng(31)
+        data = rng.integers(0, 256, size=(self.POOL, 20), dtype=np.uint8)
+        info_bits = np.concatenate([np.unpackbits(data, axis=1), np.zeros((self.POOL, 2), np.uint8)], axis=1)    # k = 162
+        cw = np.packbits(txsynth.ldpc_encode_bits(info_bits, self.RATE), axis=1)
+        body = mcdpsk.mcdpsk_tx_frames(self.cfg(), torch.from_numpy(cw).to(device), ctx)
+        pre = sync.chirp_generate(device=device, ctx=ctx)
+        assert body.shape[1] == self.FRAME_LEN and pre.numel() == self.PREAMBLE, (body.shape, pre.numel())
+        pool = torch.zeros((self.POOL, self.row_len), dtype=torch.float32, device=device)
+        pool[:, self.LEAD:self.LEAD + self.PREAMBLE] = pre
+        pool[:, self.LEAD + self.PREAMBLE:self.LEAD + self.PREAMBLE + self.FRAME_LEN] = body
+        self.pool_dev = pool
+        self.sent_dev = torch.from_numpy(data).to(device)
         self.first_id = rank * self.n
         self.rows = torch.empty((self.n, self.row_len), dtype=torch.float32, device=device)
         self.acc = torch.empty((self.n, 648), dtype=torch.float32, device=device)
@@ -395,6 +429,9 @@ class McdpskC3Workload:
         self.first_ok = None
         self.epoch = 0
         torch.cuda.synchronize()
+
+    def release(self):
+        self.rows = self.acc = self.out = self.pool_dev = self._pin = None
 
     def step(self):
         from ria_b200 import sim
@@ -423,12 +460,31 @@ class McdpskC3Workload:
         row, body, win = self.row_len * 4, self.frame_len * 4, self.WINDOW * 4
         return {
             KK_AWGN: ("awgn_kernel", n2 * 2 * row),
-            KK_CHIRP_SYNC: ("chirp_* (3 x 3-stage 131072-pt FFT with fused real load / template products, peak)", n2 * win),
+            KK_CHIRP_SYNC: ("chirp_* (131072-pt matched filter for both chirps + peak search)", n2 * win),
             KK_MCDPSK_CFO: ("mcdpsk_phase_scan_kernel + mcdpsk_cfo_kernel", n2 * 2 * body),
             KK_MCDPSK: ("mcdpsk_demod_kernel", n2 * (body + 652 * 4)),
             KK_CHASE: ("chase_combine_kernel", n2 * 3 * 648 * 4),
             KK_LDPC: ("ldpc_decode_kernel", n2 * (648 * 4 + 24 + 5)),
         }
+
+    def roofline(self, kern_ms, steps, counters):
+        """The matched filter dominates; SURVEY.md 8(d) bounds it by fp32 issue (44.6 Mflop per window for the
+        reference's two FFT + IFFT pairs), HBM traffic being the 480 KB window when staged once."""
+        sp = sm_peaks()
+        ms, n_launch = kern_ms[KK_CHIRP_SYNC]
+        windows_per_launch = 2.0 * self.n * steps / max(1, n_launch)
+        kern_s = ms / max(1, n_launch) * 1e-3
+        achieved = windows_per_launch * self.CHIRP_FLOP_PER_WINDOW / kern_s / 1e12 if kern_s > 0 else 0.0
+        hbm_peak, _ = measured_peaks()
+        return {"bound": "fp32", "achieved": achieved, "peak": sp["fp32_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / sp["fp32_tflops"], "traffic": chirp_traffic(windows_per_launch),
+                "peak_source": sp["source"], "kernel": self.kernels()[KK_CHIRP_SYNC][0],
+                "kernel_ms_per_launch": kern_s * 1e3, "launches_per_step": n_launch / steps,
+                "algorithmic_flop_per_launch": windows_per_launch * self.CHIRP_FLOP_PER_WINDOW,
+                "windows_per_s": windows_per_launch / kern_s if kern_s > 0 else None,
+                "hbm_frac_on_algorithmic_bytes": (windows_per_launch * self.WINDOW * 4 / kern_s / 1e9 / hbm_peak) if kern_s > 0 else None,
+                "note": "algorithmic flops = SURVEY.md 8(d) K2 figure (4 x 5 N log2 N, N = 131072) per window; the share of the "
+                        "step is in `kernels`"}
 
     def counters(self):
         """[frames, ok after the first reception, ok after chase combining, decoded-but-wrong payload, sum iters]"""
@@ -461,56 +517,6 @@ class McdpskC3Workload:
         return (self.e2e_n * self.row_len * 4, self.e2e_n * (24 + 1 + 4 + 32))
 
 
-def _cpu_mcdpsk_worker(args):
-    """One process per core: reference detectDualChirp + MC-DPSK process + LDPC on its own rows."""
-    _, n_frames, seed, _ = args
-    from oracle.bindings import McdpskConfig, Ref
-    wl = McdpskC3Workload(n_frames)
-    ref = Ref()
-    pool, _ = wl.pool_host()
-    cfg = McdpskConfig.from_buffer_copy(bytes(wl.cfg()))
-    rng = np.random.default_rng(seed)
-    rows = []
-    for i in range(n_frames):
-        tx = pool[i % len(pool)]
-        p = float(np.mean(tx.astype(np.float64) ** 2))
-        rows.append((tx + rng.standard_normal(len(tx)).astype(np.float32) *
-                     np.float32(np.sqrt(p / 10 ** (wl.SNR_DB / 10)))).astype(np.float32))
-    ok = 0
-    t0 = time.perf_counter()
-    for rx in rows:
-        s = ref.chirp_detect_dual(rx[:wl.WINDOW], 0.15)
-        if not s.detected:
-            continue
-        start = int(s.aux) + 28800
-        r = ref.mcdpsk_process(cfg, rx[start:start + wl.frame_len], float(s.cfo_hz))
-        if len(r["soft"]) >= 648:
-            _, okk, _ = ref.ldpc_decode_batch(wl.RATE, r["soft"][:648], wl.MAX_ITER, wl.FACTOR, 24)
-            ok += int(okk[0])
-    return time.perf_counter() - t0, ok
-
-
-def cpu_baseline_mcdpsk(wl, frames_per_core):
-    import multiprocessing as mp
-    from oracle.bindings import Ref
-    if not Ref.available():
-        return {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference",
-                "sample": "oracle/_ref/libria_ref.so not present"}
-    cores = host_cores()
-    wl.pool_host()
-    jobs = [("mcdpsk_c3", frames_per_core, 2000 + 13 * c, "reference") for c in range(cores)]
-    t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_cpu_mcdpsk_worker, jobs, chunksize=1)
-    wall = time.perf_counter() - t0
-    rate = sum(frames_per_core / b for b, _ in res)
-    ok = sum(o for _, o in res)
-    return {"value": rate, "unit": "frames/s", "cores": cores, "kind": "reference",
-            "sample": f"{frames_per_core} single receptions per core x {cores} cores ({ok}/{frames_per_core * cores} "
-                      f"decoded), reference detectDualChirp + MC-DPSK process + LDPC decodeSoft, one process per "
-                      f"core, {wall:.1f} s wall; the GPU figure counts TWO receptions per frame"}
-
-
 # ---------------------------------------------------------------------------------------------
 # workload: batched LDPC decode (BASELINE.json configs[1])
 # ---------------------------------------------------------------------------------------------
@@ -519,6 +525,7 @@ class LdpcWorkload:
     """configs[1]: R1/4..R3/4 min-sum decode of 1M codewords per rate from synthetic AWGN LLRs
     (LLR model of tools/test_chase_cache.cpp:20-34; Es/N0 and decoder settings of SURVEY.md 8d)."""
 
+    key = "ldpc"
     name = "ldpc_r14_r34_1M_cw_per_rate"
     metric = "decoded_frames_per_s"
     unit = "frames/s"
@@ -526,17 +533,27 @@ class LdpcWorkload:
     RATES = (0, 2, 3, 4)
     ESN0 = {0: 1.0, 2: 4.0, 3: 6.0, 4: 7.0}
     MAX_ITER = {0: 50, 2: 80, 3: 70, 4: 60}
+    EDGES = {0: 2437, 2: 1623, 3: 1510, 4: 1134}         # edges of the generated H per rate
     FACTOR = 0.9375
     CW_PER_FRAME = 4
+    CPU_SAMPLE = 4096
 
     def __init__(self, n_cw: int):
         self.n_cw = n_cw
+
+    def cpu_params(self):
+        return {"rates": self.RATES, "esn0": self.ESN0, "max_iter": self.MAX_ITER, "factor": self.FACTOR,
+                "cw_per_frame": self.CW_PER_FRAME}
+
+    def cpu_baseline(self, sample):
+        from oracle import cpu_bench
+        return cpu_bench.cpu_ldpc(self.cpu_params(), sample)
 
     def describe(self):
         return {"workload": self.name, "codewords_per_rate_per_gpu": self.n_cw,
                 "rates": "R1/4,R1/2,R2/3,R3/4", "esn0_db": "1,4,6,7", "min_sum_factor": self.FACTOR,
                 "max_iter": "50,80,70,60", "frame": "4 codewords (v2 fixed frame)",
-                "l2": "inputs (2.7 GB per rate) exceed the 126 MB L2; no flush needed"}
+                "l2": f"inputs ({self.n_cw * 648 * 4 / 1e9:.1f} GB per rate) exceed the 126 MB L2; no flush needed"}
 
     def _codeword_bits(self, rate, n_distinct, rng):
         from ria_b200 import fec, txsynth
@@ -566,7 +583,8 @@ class LdpcWorkload:
             snr = 10 ** (self.ESN0[rate] / 10)
             llr = 2.0 * (s + torch.randn(s.shape, device=device, generator=gen) / snr ** 0.5) * snr
             self.llr[rate] = llr.contiguous()
-            k = fec.code_params(rate)[0]
+            k, _, e = fec.code_params(rate)
+            assert e == self.EDGES[rate], (rate, e)
             packed = np.packbits(bits[:, :k], axis=1)
             self.info_ref[rate] = torch.from_numpy(packed).to(device)[pick]
             # info bits that appear in at least one check (R3/4 leaves 162 bits unprotected,
@@ -583,11 +601,12 @@ class LdpcWorkload:
         self.out = None
         torch.cuda.synchronize()
 
+    def release(self):
+        self.llr = self.out = self.info_ref = None
+        self._pinned = self.e2e_llr = None
+
     def step(self):
         self.out = {rate: self.dec[rate].decode_batch(self.llr[rate]) for rate in self.RATES}
-
-    def launches_per_step(self):
-        return len(self.RATES)
 
     def units_per_step(self):
         return len(self.RATES) * self.n_cw / self.CW_PER_FRAME
@@ -599,6 +618,28 @@ class LdpcWorkload:
         from ria_b200 import fec
         return {KK_LDPC: ("ldpc_decode_kernel",
                           sum(self.n_cw * (648 * 4 + (fec.code_params(r)[0] + 7) // 8 + 5) for r in self.RATES))}
+
+    def roofline(self, kern_ms, steps, counters):
+        """shared-memory bound, messages live on chip.  Algorithmic shared-memory bytes =
+        16 B per edge per pass (v2c read, c2v write, c2v read for the totals, parity term), passes = iterations
+        + 1 per codeword; the count uses the decoder's own iteration counters."""
+        sp = sm_peaks()
+        ms, n_launch = kern_ms[KK_LDPC]
+        smem_bytes = edge_updates = 0.0
+        for rate in self.RATES:
+            passes = float(self.out[rate][2].sum().item()) + self.n_cw          # sum(iters) + 1 per codeword
+            smem_bytes += 16.0 * self.EDGES[rate] * passes
+            edge_updates += 2.0 * self.EDGES[rate] * passes
+        kern_s_step = ms / steps * 1e-3
+        achieved = smem_bytes / kern_s_step / 1e9 if kern_s_step > 0 else 0.0
+        hbm = hbm_roofline("ldpc_decode_kernel", ms, n_launch, self.kernels()[KK_LDPC][1], steps)
+        return {"bound": "smem", "achieved": achieved, "peak": sp["smem_gbs"], "unit": "GB/s", "frac": achieved / sp["smem_gbs"],
+                "traffic": None, "peak_source": sp["source"], "kernel": "ldpc_decode_kernel",
+                "kernel_ms_per_launch": ms / max(1, n_launch), "launches_per_step": n_launch / steps,
+                "algorithmic_smem_bytes_per_step": smem_bytes,
+                "edge_updates_per_s": edge_updates / kern_s_step if kern_s_step > 0 else None,
+                "hbm_frac_on_algorithmic_bytes": hbm["frac"],
+                "note": "16 B x E x (iterations + 1) per codeword (SURVEY.md 8d K11) over the kernel's device time"}
 
     def counters(self):
         torch = self.torch
@@ -640,73 +681,60 @@ class LdpcWorkload:
         return h2d, d2h
 
 
-def _cpu_ldpc_worker(args):
-    n, seed, kind = args
-    from oracle.bindings import Port, Ref
-    wl = LdpcWorkload(n)
-    impl = Ref() if kind == "reference" else Port()
-    elapsed = 0.0
-    for rate in wl.RATES:
-        llr = wl.make_llr_host(rate, n, seed + rate)[0]
-        t0 = time.perf_counter()
-        impl.ldpc_decode_batch(rate, llr, wl.MAX_ITER[rate], wl.FACTOR)
-        elapsed += time.perf_counter() - t0
-    return elapsed
-
-
-def cpu_baseline_ldpc(wl, per_rate_per_core):
-    import multiprocessing as mp
-    from oracle.bindings import Ref
-    kind = "reference" if Ref.available() else "port"
-    cores = host_cores()
-    jobs = [(per_rate_per_core, 1000 + 17 * c, kind) for c in range(cores)]
-    t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(cores) as pool:
-        busy = pool.map(_cpu_ldpc_worker, jobs, chunksize=1)
-    wall = time.perf_counter() - t0
-    per_core_cw = len(wl.RATES) * per_rate_per_core
-    rate_sum = sum(per_core_cw / b for b in busy)
-    return {"value": rate_sum / wl.CW_PER_FRAME, "unit": "frames/s", "cores": cores, "kind": kind,
-            "sample": f"{per_rate_per_core} codewords per rate per core x {cores} cores "
-                      f"({cores * per_core_cw} codewords), {wall:.1f} s wall, {max(busy):.1f} s max busy"}
+def _traffic_file():
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return p
+    return None
 
 
 def measured_traffic(workload, kernel_name, frames_per_launch):
     """DRAM bytes per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum from the
-    committed ncu --set full capture (profiles/r1_traffic.json, bytes per frame) x frames per launch."""
+    committed ncu --set full capture (profiles/r*_traffic.json, bytes per frame) x frames per launch."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(_traffic_file()) as f:
             t = json.load(f)
         return t[workload][kernel_name]["dram_bytes_per_frame"] * frames_per_launch
-    except (OSError, KeyError, ValueError):
+    except (OSError, KeyError, ValueError, TypeError):
         return None
 
 
-def make_workload(args):
-    if args.workload == "mcdpsk":
-        return McdpskC3Workload(args.batch or 100_000), cpu_baseline_mcdpsk, args.cpu_sample or 16
-    if args.workload == "ldpc":
-        return LdpcWorkload(args.batch or (1 << 20)), cpu_baseline_ldpc, args.cpu_sample or 4096
-    return OfdmQam64Workload(args.batch or (1 << 20)), cpu_baseline_ofdm, args.cpu_sample or 6000
+def chirp_traffic(windows_per_launch):
+    try:
+        with open(_traffic_file()) as f:
+            t = json.load(f)
+        return t["mcdpsk"]["chirp"]["dram_bytes_per_window"] * windows_per_launch
+    except (OSError, KeyError, ValueError, TypeError):
+        return None
+
+
+def make_workload(name, batch):
+    if name == "mcdpsk":
+        return McdpskC3Workload(batch or 100_000)
+    if name == "ldpc":
+        return LdpcWorkload(batch or (1 << 20))
+    if name == "ofdm_qam64_cfo":
+        return OfdmQam64Workload(batch or (1 << 18), cfo_span=3.0)
+    return OfdmQam64Workload(batch or (1 << 20))
 
 
 # ---------------------------------------------------------------------------------------------
-# main
+# --impl reference
 # ---------------------------------------------------------------------------------------------
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on all host cores, on
-    a bounded sample of the same workload.  Rank 0 only."""
+    a bounded sample of the same workload.  Rank 0 only.  Nothing on this arm imports ria_b200: the inputs
+    come from the reference's own transmitter (oracle/cpu_bench.py)."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    import ria_b200  # noqa: F401  (host-side input synthesis only; no GPU work on this arm)
-    wl, cpu_fn, sample = make_workload(args)
-    if hasattr(wl, "pool_host"):
-        wl.pool_host()                      # built once here, inherited by the forked workers
+    wl = make_workload(args.workload, args.batch)
+    sample = args.cpu_sample or wl.CPU_SAMPLE
     for _ in range(args.warmup):
-        cpu_fn(wl, max(16, sample // 16))
-    runs = [cpu_fn(wl, sample) for _ in range(max(1, args.steps))]
+        wl.cpu_baseline(max(16, sample // 16))
+    runs = [wl.cpu_baseline(sample) for _ in range(max(1, args.steps))]
     v = float(np.mean([r["value"] for r in runs]))
     last = runs[-1]
     units = last["cores"] * sample * (len(wl.RATES) / wl.CW_PER_FRAME if isinstance(wl, LdpcWorkload) else 1)
@@ -718,52 +746,26 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": wl.unit, "cores": last["cores"], "kind": last["kind"],
                          "sample": last["sample"]},
         "e2e": {"value": v, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "product_library_loaded": "ria_b200" in sys.modules,
     }
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ria_b200", choices=["ria_b200", "reference"])
-    ap.add_argument("--workload", default="ofdm_qam64", choices=["ofdm_qam64", "ldpc", "mcdpsk"])
-    ap.add_argument("--batch", type=int, default=0, help="frames (or codewords per rate) per GPU")
-    ap.add_argument("--e2e-batch", type=int, default=1 << 16)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="frames (codewords per rate) per core")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
+# ---------------------------------------------------------------------------------------------
+# one workload on this rank's GPU
+# ---------------------------------------------------------------------------------------------
 
-    if args.impl == "reference":
-        run_reference(args)
-        return
-
+def run_workload(wl, ctx, stream, device, rank, world, local, steps, warmup, e2e_batch, cpu_sample, with_cpu):
     import torch
     import torch.distributed as dist
-    import ria_b200
 
-    rank, world, local = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (ria_b200 has no CPU fallback)")
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
-    ctx = ria_b200.Context(local)
-    stream = torch.cuda.Stream(device)
-    wl, cpu_fn, cpu_sample = make_workload(args)
-    warmup = max(args.warmup, 3)
     with torch.cuda.stream(stream):
         wl.setup(ctx, device, rank, world)
-
-        def barrier():
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-
         for _ in range(warmup):
             wl.step()
         barrier()
@@ -775,7 +777,7 @@ def main():
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             wl.step()
         ev1.record(stream)
         barrier()
@@ -791,14 +793,15 @@ def main():
         if world > 1:
             dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_per_step = float(t.item()) / args.steps
+        ms_per_step = float(t.item()) / steps
         value = wl.units_per_step() * world / (ms_per_step * 1e-3)
+        roofline = wl.roofline(kern_ms, steps, cnt) if rank == 0 else None
 
         # end to end through the host-buffer C ABI (pinned host input, H2D + kernels + D2H timed)
-        wl.setup_e2e(args.e2e_batch)
+        wl.setup_e2e(e2e_batch)
         wl.step_e2e()
         barrier()
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(steps, 3))
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             wl.step_e2e()
@@ -809,50 +812,102 @@ def main():
         e2e_value = wl.e2e_units() * world / float(te.item())
         h2d, d2h = wl.e2e_bytes()
 
+    res = None
     if rank == 0:
-        peak, peak_src = measured_peaks()
         kinfo = wl.kernels()
-        dom_kind = max(kern_ms, key=lambda k: kern_ms[k][0])          # most device time in the step
-        dom_name, dom_bytes_step = kinfo[dom_kind]
-        dom_ms, dom_n = kern_ms[dom_kind]
-        kern_s = dom_ms / max(1, dom_n) * 1e-3
-        bytes_per_launch = dom_bytes_step * args.steps / max(1, dom_n)
-        achieved = bytes_per_launch / kern_s / 1e9
-        traffic = measured_traffic(args.workload, dom_name, wl.units_per_step() * args.steps / max(1, dom_n))
-        step_ms_local = ms / args.steps
-        line = {
+        step_ms_local = ms / steps
+        res = {
             "metric": wl.metric, "value": value, "unit": wl.unit,
-            "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.describe(),
             "rx_msamples_per_s": wl.samples_per_step() * world / (ms_per_step * 1e-3) / 1e6,
             "counters": wl.counter_dict(cnt.cpu().numpy()),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "traffic_source": ("profiles/r1_traffic.json: dram bytes per frame of this kernel from one "
-                                            "ncu --set full capture x frames per launch" if traffic else None),
-                         "peak_source": peak_src,
-                         "kernel": dom_name, "kernel_ms_per_launch": kern_s * 1e3,
-                         "launches_per_step": dom_n / args.steps,
-                         "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "note": "dominant kernel = most device time in the step; see DESIGN.md section 3 "
-                                 "for the per-frame byte counts and what bounds each kernel"},
-            "kernels": {kinfo[k][0]: {"share_of_step": kern_ms[k][0] / args.steps / step_ms_local,
-                                      "ms_per_step": kern_ms[k][0] / args.steps,
-                                      "launches_per_step": kern_ms[k][1] / args.steps,
-                                      "algorithmic_gb_per_s": (kinfo[k][1] * args.steps / (kern_ms[k][0] * 1e-3) / 1e9
+            "roofline": roofline,
+            "kernels": {kinfo[k][0]: {"share_of_step": kern_ms[k][0] / steps / step_ms_local,
+                                      "ms_per_step": kern_ms[k][0] / steps,
+                                      "launches_per_step": kern_ms[k][1] / steps,
+                                      "algorithmic_gb_per_s": (kinfo[k][1] * steps / (kern_ms[k][0] * 1e-3) / 1e9
                                                                if kern_ms[k][0] > 0 else None)}
                         for k in kern_ms},
             "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "batch": getattr(wl, "e2e_n", args.e2e_batch),
+                    "d2h_bytes_per_step": d2h, "batch": getattr(wl, "e2e_n", e2e_batch),
                     "api": "ria_ofdm_rx_frames_host / ria_mcdpsk_rx_frames_host / ria_ldpc_decode_batch_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if hasattr(wl, "extra"):
-            line.update(wl.extra(value))
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_fn(wl, cpu_sample)
+            res.update(wl.extra(value))
+        if with_cpu:
+            res["cpu_baseline"] = wl.cpu_baseline(cpu_sample or wl.CPU_SAMPLE)
+    wl.release()
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ria_b200", choices=["ria_b200", "reference"])
+    ap.add_argument("--workload", default="ofdm_qam64", choices=["ofdm_qam64", "ofdm_qam64_cfo", "ldpc", "mcdpsk"])
+    ap.add_argument("--batch", type=int, default=0, help="frames (or codewords per rate) per GPU")
+    ap.add_argument("--e2e-batch", type=int, default=1 << 16)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="frames (codewords per rate) per core")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short passes of the other workloads")
+    ap.add_argument("--no-cli-simulator", action="store_true", help="skip the cli_simulator-per-core CPU line")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ria_b200
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (ria_b200 has no CPU fallback)")
+    affinity = pin_rank_to_cores(local, world)
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    ctx = ria_b200.Context(local)
+    stream = torch.cuda.Stream(device)
+    warmup = max(args.warmup, 3)
+    with_cpu = world == 1 and not args.no_cpu_baseline
+    line = run_workload(make_workload(args.workload, args.batch), ctx, stream, device, rank, world, local,
+                        args.steps, warmup, args.e2e_batch, args.cpu_sample, with_cpu)
+    if rank == 0 and affinity:
+        line["rank_core_affinity"] = f"each rank pinned to its own block of host cores (rank 0: {affinity[0]}..{affinity[1]})"
+
+    # the other BASELINE configs, a short pass each (driver-measured through this same line)
+    if args.workload == "ofdm_qam64" and not args.batch and not args.no_extras:
+        extras = {}
+        short = max(2, min(args.steps, 4))
+        for name, batch in (("ofdm_qam64_cfo", 1 << 18), ("mcdpsk", 1 << 15), ("ldpc", 1 << 20)):
+            ctx.set_decode_flags(0)
+            r = run_workload(make_workload(name, batch), ctx, stream, device, rank, world, local,
+                             short, 3, min(args.e2e_batch, 1 << 15), 0, with_cpu)
+            if rank == 0:
+                extras[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "counters", "roofline",
+                                                  "kernels", "e2e", "gpu_launches", "clocks", "cpu_baseline", "receptions_per_s",
+                                                  "rx_msamples_per_s") if k in r}
+        if rank == 0:
+            line["extra_workloads"] = extras
+            line["gpu_launches_headline"] = line["gpu_launches"]
+            line["gpu_launches"] = int(line["gpu_launches"] + sum(e["gpu_launches"] for e in extras.values()))
+            if with_cpu and not args.no_cli_simulator:
+                from oracle import cpu_bench
+                line["cpu_baseline"]["cli_simulator_per_core"] = cpu_bench.cli_simulator_per_core()
+
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
