@@ -133,6 +133,7 @@ def _ofdm_case(ctx, name, mod, spacing, rate, snr_db, n, fade_cond=None, cfo_spa
     data = data.cpu().numpy()
     st = ofdm.status_array(status)
     bad = dict(soft_frames=0, soft_bits=0, n_llr=0, snr=0, cfo=0, fading=0, cw_ok=0, data=0)
+    ulp = dict(snr_db_last_bit=0)
     decoded = payload_ok = 0
     for i, (_, w_soft, w_snr, w_cfo, w_fad, w_data, w_ok) in enumerate(want):
         if int(n_llr[i]) != len(w_soft):
@@ -141,14 +142,17 @@ def _ofdm_case(ctx, name, mod, spacing, rate, snr_db, n, fade_cond=None, cfo_spa
         diff = llr[i, : len(w_soft)].view(np.uint32) != w_soft.view(np.uint32)
         bad["soft_frames"] += int(diff.any())
         bad["soft_bits"] += int(diff.sum())
-        bad["snr"] += int(np.float32(snr[i]).view(np.uint32) != w_snr.view(np.uint32))
+        # the SNR report is 10 log10 of a bit-identical linear estimate; CUDA's log10f and glibc's differ in the last
+        # bit on ~10 % of arguments, so the dB figure is held to 1e-6 relative and the last-bit count reported
+        bad["snr"] += int(abs(float(snr[i]) - float(w_snr)) > 1e-6 * max(1.0, abs(float(w_snr))))
+        ulp["snr_db_last_bit"] += int(np.float32(snr[i]).view(np.uint32) != w_snr.view(np.uint32))
         bad["cfo"] += int(np.float32(cfo_o[i]).view(np.uint32) != w_cfo.view(np.uint32))
         bad["fading"] += int(np.float32(fad[i]).view(np.uint32) != w_fad.view(np.uint32))
         bad["cw_ok"] += int(not np.array_equal(st["cw_ok"][i], w_ok))
         bad["data"] += int(not np.array_equal(data[i], w_data))
         decoded += int(w_ok.all())
         payload_ok += int(w_ok.all() and np.array_equal(w_data[: sent.shape[1]], sent[i]))
-    entry = dict(frames=n, frames_full_decode=full_n, mismatches=bad, ref_all_cw_decoded=decoded, ref_payload_correct=payload_ok,
+    entry = dict(frames=n, frames_full_decode=full_n, mismatches=bad, last_bit_differences=ulp, ref_all_cw_decoded=decoded, ref_payload_correct=payload_ok,
                  ladder_frames=int((st["ladder_cw_mask"] != 0).sum()), repaired_frames=int((st["fp_repair"] == 1).sum()),
                  mean_fading_index=float(np.mean(fad)), ref_seconds=round(t_ref, 1), ref_cores=_cores())
     _report(name, entry)
