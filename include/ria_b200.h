@@ -516,6 +516,45 @@ int ria_channel_watterson_batch_dev(ria_ctx* ctx, const ria_watterson_config* cf
                                     const float* snr_db_dev, uint64_t seed, int64_t first_frame_id,
                                     int64_t n_frames, float* out_dev, int64_t out_stride);
 
+/* ---- HOST-buffer variants of the synchronisers and the MC-DPSK demodulator --------------------- */
+/* Same arguments as the `_dev` entry points with host pointers (H2D -> `_dev` -> D2H inside the call, which
+ * returns when the results are in the caller's buffers).  These are what the batch = 1 IWaveform adapters of
+ * include/ria_b200_adapters.hpp call behind detectSync / detectDataSync / process:
+ *   ria_chirp_detect_dual_batch_host  IWaveform::detectSync          (ofdm_chirp_waveform.cpp:163-205, mc_dpsk_waveform.cpp:177-224)
+ *   ria_zc_detect_batch_host          MCDPSKWaveform::detectDataSync (mc_dpsk_waveform.cpp:227-292)
+ *   ria_ofdm_data_sync_batch_host     OFDMChirpWaveform::detectDataSync (ofdm_chirp_waveform.cpp:207-384)
+ *   ria_mcdpsk_process_batch_host     MCDPSKWaveform::process        (mc_dpsk_waveform.cpp:294-338) */
+int ria_chirp_detect_dual_batch_host(ria_ctx* ctx, const ria_chirp_config* cfg, const float* samples,
+                                     int64_t frame_stride, int32_t window, float threshold,
+                                     int64_t n_frames, ria_sync_result* out);
+int ria_zc_detect_batch_host(ria_ctx* ctx, const ria_zc_config* cfg, const float* samples, int64_t frame_stride,
+                             int32_t window, const float* known_cfo, float threshold, uint32_t root_mask,
+                             int64_t n_frames, ria_sync_result* out);
+int ria_ofdm_data_sync_batch_host(ria_ctx* ctx, const ria_modem_config* cfg, const float* samples,
+                                  int64_t frame_stride, int32_t window, const float* known_cfo, float threshold,
+                                  int64_t n_frames, ria_sync_result* out);
+int ria_mcdpsk_process_batch_host(ria_ctx* ctx, const ria_mcdpsk_config* cfg, const float* samples,
+                                  int64_t frame_stride, int32_t frame_len, const float* cfo_hz, const float* phase,
+                                  int64_t n_frames, float* llr, int32_t llr_stride, int32_t* n_llr,
+                                  float* fading, float* cfo_out);
+
+/* ---- error counters and their reduction over the GPUs of the box ------------ */
+/* counters_dev[0..7] += {frames, frames_ok (4/4 codewords + header + frame CRC), codewords, codewords failed,
+ * 0, 0, frames without a valid header, frames whose codewords all decoded but whose CRC failed} of a
+ * ria_frame_status array, produced by a kernel on the context stream (what cli_simulator's per-station
+ * statistics count, tools/cli_simulator.cpp:2226-2290).  The caller zeroes the counters. */
+int ria_frame_counters_dev(ria_ctx* ctx, const ria_frame_status* status_dev, int64_t n_frames, int64_t* counters_dev);
+/* The path's only collective: ncclAllReduce(sum, int64) of a counter vector, in place, on the context
+ * stream.  `nccl_comm` is an ncclComm_t the host created (ncclCommInitRank), or one made with the helpers
+ * below: rank 0 calls ria_nccl_get_unique_id, hands the 128 bytes to the other ranks by any means, every
+ * rank calls ria_nccl_comm_create.  NCCL is resolved from the process image at run time (libria_b200.so does
+ * not link it); RIA_E_UNSUPPORTED when it cannot be found. */
+typedef struct { char internal[128]; } ria_nccl_unique_id;      /* layout of ncclUniqueId */
+int ria_nccl_get_unique_id(ria_nccl_unique_id* id);
+int ria_nccl_comm_create(ria_ctx* ctx, const ria_nccl_unique_id* id, int rank, int world, void** nccl_comm);
+int ria_nccl_comm_destroy(void* nccl_comm);
+int ria_counters_allreduce(ria_ctx* ctx, void* nccl_comm, int64_t* counters_dev, int32_t n);
+
 /* CRC-16/CCITT-FALSE as ControlFrame::calculateCRC (src/protocol/frame_v2.cpp:115-128); host. */
 uint16_t ria_crc16(const uint8_t* data, size_t len);
 /* ChannelInterleaver step: findCoprimeStep (src/fec/ldpc_decoder.cpp:552-577); host. */

@@ -6,8 +6,13 @@
 //
 //   ria::LDPCDecoder        <- ultra::LDPCDecoder              include/ultra/fec.hpp:48-81
 //   ria::LDPCCodec          <- ultra::fec::LDPCCodec / ICodec  src/fec/ldpc_codec.hpp:38-105
-//   ria::OFDMChirpRx        <- RX half of ultra::OFDMChirpWaveform (IWaveform)
+//   ria::OFDMChirpRx        <- RX half of ultra::OFDMChirpWaveform (stand-alone, no reference headers needed)
 //                                                              src/waveform/ofdm_chirp_waveform.cpp:79-105, 391-485
+//   ria::OFDMChirpWaveform  <- ultra::OFDMChirpWaveform   } RIA_WITH_ULTRA only: real ultra::IWaveform objects
+//   ria::MCDPSKWaveform     <- ultra::MCDPSKWaveform      } (src/waveform/waveform_interface.hpp:47-220) whose receive
+//   ria::createWaveform     <- WaveformFactory::create    } half (detectSync / detectDataSync / process / getSoftBits /
+//                                                           status getters) runs on the B200; the transmit half, the sizing
+//                                                           getters and the capabilities are the reference's, inherited
 //   ria::decodeFixedFrame   <- ultra::protocol::v2::decodeFixedFrame (soft bits in: the complete function with
 //                              retry ladder and false-positive repair; samples in: demod + first pass)
 //                                                              src/protocol/frame_v2.cpp:1335-1920
@@ -21,7 +26,9 @@
 // points of the C ABI are what a many-channel receiver should call directly.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -36,6 +43,8 @@
 #ifdef RIA_WITH_ULTRA
 #include "fec/codec_interface.hpp"
 #include "ultra/fec.hpp"
+#include "waveform/mc_dpsk_waveform.hpp"
+#include "waveform/ofdm_chirp_waveform.hpp"
 #endif
 
 namespace ria {
@@ -362,5 +371,285 @@ private:
     bool has_abs_pos_ = false;
     std::vector<float> soft_bits_;
 };
+
+
+#ifdef RIA_WITH_ULTRA
+// ------------------------------------------------------------------------------------------------
+// ultra::IWaveform drop-ins.  They ARE the reference's waveform classes for everything that is not on the
+// receive hot path (preamble / modulate, sizing, capabilities: inherited), and override every virtual that
+// touches receive state so that the reference's own CPU demodulator / synchronisers are never run:
+//   detectSync      -> ria_chirp_detect_dual_batch_host      (ofdm_chirp_waveform.cpp:163-205, mc_dpsk_waveform.cpp:177-224)
+//   detectDataSync  -> ria_ofdm_data_sync_batch_host / ria_zc_detect_batch_host   (:207-384 / :227-292)
+//   process         -> ria_ofdm_presynced_batch_host / ria_mcdpsk_process_batch_host   (:391-468 / :294-338)
+// One instance is driven by one thread at a time, like the reference objects (SURVEY.md 8b "Threading").
+// ------------------------------------------------------------------------------------------------
+inline ria_modem_config toRiaConfig(const ultra::ModemConfig& m) {
+    ria_modem_config c{};
+    c.sample_rate = static_cast<uint32_t>(m.sample_rate);
+    c.center_freq = static_cast<uint32_t>(m.center_freq);
+    c.fft_size = static_cast<uint32_t>(m.fft_size);
+    c.num_carriers = static_cast<uint32_t>(m.num_carriers);
+    c.cp_mode = static_cast<uint32_t>(m.cp_mode);
+    c.symbol_guard = static_cast<uint32_t>(m.symbol_guard);
+    c.use_pilots = m.use_pilots ? 1u : 0u;
+    c.pilot_spacing = static_cast<uint32_t>(m.pilot_spacing);
+    c.modulation = static_cast<uint32_t>(m.modulation);
+    c.training_symbols = 2;
+    return c;
+}
+
+class OFDMChirpWaveform : public ultra::OFDMChirpWaveform {
+public:
+    OFDMChirpWaveform() : ultra::OFDMChirpWaveform() { cfg_ = toRiaConfig(getConfig()); ria_chirp_config_default(&chirp_); }
+    explicit OFDMChirpWaveform(const ultra::ModemConfig& config) : ultra::OFDMChirpWaveform(config) {
+        cfg_ = toRiaConfig(getConfig());
+        ria_chirp_config_default(&chirp_);
+    }
+
+    void configure(ultra::Modulation mod, ultra::CodeRate rate) override {
+        ultra::OFDMChirpWaveform::configure(mod, rate);          // TX side + the pilot layout rule (:79-105)
+        cfg_ = toRiaConfig(getConfig());
+    }
+    void setFrequencyOffset(float cfo_hz) override { cfo_hz_ = cfo_hz; }
+    float getFrequencyOffset() const override { return cfo_hz_; }
+
+    bool detectSync(ultra::SampleSpan samples, ultra::SyncResult& result, float threshold = 0.15f) override {
+        ria_sync_result r{};
+        Context& c = Context::instance();
+        c.check(ria_chirp_detect_dual_batch_host(c.get(), &chirp_, samples.data(), static_cast<int64_t>(samples.size()),
+                                                 static_cast<int32_t>(samples.size()), threshold, 1, &r));
+        result.detected = r.detected != 0;
+        result.correlation = std::max(r.correlation, r.snr_estimate);           // max(up, down) (:173)
+        result.cfo_hz = r.cfo_hz;
+        result.has_training = true;
+        if (result.detected) {
+            synced_ = true;
+            last_cfo_ = r.cfo_hz;
+            const int chirp_samples = static_cast<int>(static_cast<size_t>(chirp_.sample_rate * chirp_.duration_ms / 1000.0f));
+            const int gap_samples = static_cast<int>(static_cast<size_t>(cfg_.sample_rate * 100.0f / 1000.0f));
+            result.start_sample = r.aux + chirp_samples + gap_samples;         // training after the down chirp (:194-196)
+            training_start_ = static_cast<size_t>(result.start_sample);
+        }
+        return result.detected;
+    }
+
+    bool detectDataSync(ultra::SampleSpan samples, ultra::SyncResult& result, float known_cfo_hz = 0.0f,
+                        float threshold = 0.3f) override {
+        result.detected = false;
+        result.correlation = 0.0f;
+        result.cfo_hz = known_cfo_hz;
+        result.has_training = true;
+        if (samples.size() < static_cast<size_t>(getSamplesPerSymbol()) * 3) return false;
+        ria_sync_result r{};
+        Context& c = Context::instance();
+        c.check(ria_ofdm_data_sync_batch_host(c.get(), &cfg_, samples.data(), static_cast<int64_t>(samples.size()),
+                                              static_cast<int32_t>(samples.size()), &known_cfo_hz, threshold, 1, &r));
+        result.correlation = r.correlation;
+        burst_latched_ = burst_pending_ = false;                               // reset at every attempt (:356-358)
+        if (r.detected) {
+            result.detected = true;
+            result.start_sample = r.start_sample;
+            training_start_ = static_cast<size_t>(r.start_sample);
+            synced_ = true;
+            last_cfo_ = known_cfo_hz;
+            burst_pending_ = burst_latched_ = r.aux != 0;                      // negated first LTS = burst marker (:366-375)
+        }
+        return result.detected;
+    }
+
+    void setAbsoluteTrainingPosition(size_t pos) override { abs_pos_ = pos; has_abs_pos_ = true; }
+
+    bool process(ultra::SampleSpan samples) override {
+        if (static_cast<int>(samples.size()) < getSamplesPerSymbol()) return false;
+        const size_t ref = has_abs_pos_ ? abs_pos_ : training_start_;
+        float ph = static_cast<float>(-2.0f * 3.14159265358979323846 * cfo_hz_ * ref / cfg_.sample_rate);   // (:404)
+        while (ph > 3.14159265358979323846) ph -= 2.0f * 3.14159265358979323846;
+        while (ph < -3.14159265358979323846) ph += 2.0f * 3.14159265358979323846;
+        const float* in = samples.data();
+        std::vector<float> undone;
+        if (burst_pending_) {                                                   // one-shot: restore the marked LTS (:423-436)
+            burst_pending_ = false;
+            undone.assign(samples.begin(), samples.end());
+            const size_t L = static_cast<size_t>(getSamplesPerSymbol());
+            for (size_t i = 0; i < L && i < undone.size(); ++i) undone[i] = -undone[i];
+            in = undone.data();
+        }
+        const int n_sym = static_cast<int>(samples.size()) / getSamplesPerSymbol();
+        const int bits = ria_ofdm_data_carriers(&cfg_) * bitsPerCarrier(cfg_.modulation);
+        const int stride = std::max(4, ((n_sym > 2 ? n_sym - 2 : 0) * bits + 3) & ~3);
+        std::vector<float> llr(static_cast<size_t>(stride));
+        int32_t n_llr = 0;
+        float snr = 0, cfo = 0, fad = 0;
+        Context& c = Context::instance();
+        c.check(ria_ofdm_presynced_batch_host(c.get(), &cfg_, in, static_cast<int64_t>(samples.size()),
+                                              static_cast<int32_t>(samples.size()), &cfo_hz_, &ph, 1, llr.data(),
+                                              static_cast<int32_t>(llr.size()), &n_llr, &snr, &cfo, &fad));
+        fading_ = fad;
+        const bool ready = n_llr >= RIA_LDPC_N;
+        if (ready) {
+            llr.resize(static_cast<size_t>(n_llr));
+            soft_bits_ = std::move(llr);
+            last_snr_ = snr;
+            cfo_hz_ = last_cfo_ = cfo;                                          // CFO feedback (:447-455)
+        }
+        return ready;
+    }
+    std::vector<float> getSoftBits() override { return std::move(soft_bits_); }
+    void reset() override { soft_bits_.clear(); synced_ = false; has_abs_pos_ = false; abs_pos_ = 0; }   // CFO kept (:474-485)
+    bool isSynced() const override { return synced_; }
+    bool hasData() const override { return !soft_bits_.empty(); }
+    float estimatedSNR() const override { return last_snr_; }
+    float estimatedCFO() const override { return std::fabs(last_cfo_) > 0.1f ? last_cfo_ : cfo_hz_; }
+    float getFadingIndex() const override { return fading_; }
+    bool wasBurstInterleaved() const override { return burst_latched_; }
+    std::vector<std::complex<float>> getConstellationSymbols() const override { return {}; }
+
+    static int bitsPerCarrier(uint32_t modulation) {
+        switch (modulation) {
+            case RIA_DQPSK: case RIA_QPSK: return 2;
+            case RIA_D8PSK: case RIA_QAM8: return 3;
+            case RIA_QAM16: return 4;
+            case RIA_QAM32: return 5;
+            case RIA_QAM64: return 6;
+            case RIA_QAM256: return 8;
+            default: return 1;
+        }
+    }
+
+private:
+    ria_modem_config cfg_{};
+    ria_chirp_config chirp_{};
+    float cfo_hz_ = 0.0f, last_cfo_ = 0.0f, last_snr_ = 0.0f, fading_ = 0.0f;
+    size_t training_start_ = 0, abs_pos_ = 0;
+    bool has_abs_pos_ = false, synced_ = false, burst_pending_ = false, burst_latched_ = false;
+    std::vector<float> soft_bits_;
+};
+
+class MCDPSKWaveform : public ultra::MCDPSKWaveform {
+public:
+    MCDPSKWaveform() : ultra::MCDPSKWaveform() { sync_configs(); }
+    explicit MCDPSKWaveform(int num_carriers) : ultra::MCDPSKWaveform(num_carriers) { sync_configs(); }
+    explicit MCDPSKWaveform(const ultra::MultiCarrierDPSKConfig& config) : ultra::MCDPSKWaveform(config) { sync_configs(); }
+
+    void configure(ultra::Modulation mod, ultra::CodeRate rate) override {
+        ultra::MCDPSKWaveform::configure(mod, rate);
+        sync_configs();
+    }
+    // setCarrierCount / setSpreadingMode are not virtual in the reference: call these instead of the base's
+    void setCarrierCount(int carriers) { ultra::MCDPSKWaveform::setCarrierCount(carriers); sync_configs(); }
+    void setSpreadingMode(ultra::SpreadingMode mode) { ultra::MCDPSKWaveform::setSpreadingMode(mode); sync_configs(); }
+    void setFrequencyOffset(float cfo_hz) override { cfo_hz_ = cfo_hz; }
+    float getFrequencyOffset() const override { return cfo_hz_; }
+
+    bool detectSync(ultra::SampleSpan samples, ultra::SyncResult& result, float threshold = 0.15f) override {
+        ria_sync_result r{};
+        Context& c = Context::instance();
+        c.check(ria_chirp_detect_dual_batch_host(c.get(), &chirp_, samples.data(), static_cast<int64_t>(samples.size()),
+                                                 static_cast<int32_t>(samples.size()), threshold, 1, &r));
+        result.detected = r.detected != 0;
+        result.start_sample = r.start_sample;                                   // up_chirp_start (:187)
+        result.correlation = std::max(r.correlation, r.snr_estimate);
+        result.cfo_hz = r.cfo_hz;
+        result.has_training = true;
+        if (result.detected) {
+            synced_ = true;
+            last_cfo_ = r.cfo_hz;
+            const int chirp_samples = static_cast<int>(static_cast<size_t>(chirp_.sample_rate * chirp_.duration_ms / 1000.0f));
+            const int gap_samples = static_cast<int>(static_cast<size_t>(cfg_.sample_rate * chirp_.gap_ms / 1000.0f));
+            result.start_sample = r.aux + chirp_samples + gap_samples;         // training after the down chirp (:209-212)
+        }
+        return result.detected;
+    }
+
+    bool detectDataSync(ultra::SampleSpan samples, ultra::SyncResult& result, float known_cfo_hz = 0.0f,
+                        float threshold = 0.2f) override {
+        if (std::fabs(known_cfo_hz) > 0.1f) setFrequencyOffset(known_cfo_hz);   // (:247-249)
+        ria_sync_result r{};
+        Context& c = Context::instance();
+        const uint32_t roots = 4u | 8u;                                         // DATA | CONTROL (:253)
+        c.check(ria_zc_detect_batch_host(c.get(), &zc_, samples.data(), static_cast<int64_t>(samples.size()),
+                                         static_cast<int32_t>(samples.size()), &known_cfo_hz, threshold, roots, 1, &r));
+        result.detected = r.detected != 0;
+        result.correlation = r.correlation;
+        result.cfo_hz = r.cfo_hz;
+        result.has_training = true;
+        if (result.detected) {
+            synced_ = true;
+            result.start_sample = r.start_sample;
+            last_cfo_ = std::fabs(known_cfo_hz) > 0.1f ? known_cfo_hz + r.cfo_hz : r.cfo_hz;      // (:275-281)
+            cfo_hz_ = last_cfo_;
+        }
+        return result.detected;
+    }
+
+    bool process(ultra::SampleSpan samples) override {
+        const int n_soft = ria_mcdpsk_soft_bits_per_frame(&cfg_, static_cast<int32_t>(samples.size()));
+        if (n_soft <= 0) return false;
+        std::vector<float> llr(static_cast<size_t>((n_soft + 3) & ~3));
+        int32_t n_llr = 0;
+        float fad = 0, cfo = 0;
+        Context& c = Context::instance();
+        c.check(ria_mcdpsk_process_batch_host(c.get(), &cfg_, samples.data(), static_cast<int64_t>(samples.size()),
+                                              static_cast<int32_t>(samples.size()), &cfo_hz_, nullptr, 1, llr.data(),
+                                              static_cast<int32_t>(llr.size()), &n_llr, &fad, &cfo));
+        fading_ = fad;
+        const bool ready = n_llr > 0;
+        if (ready) {
+            llr.resize(static_cast<size_t>(n_llr));
+            soft_bits_ = std::move(llr);
+            synced_ = true;
+            last_cfo_ = cfo;
+        }
+        return ready;
+    }
+    std::vector<float> getSoftBits() override { return std::move(soft_bits_); }
+    void reset() override { soft_bits_.clear(); synced_ = false; }
+    bool isSynced() const override { return synced_; }
+    bool hasData() const override { return !soft_bits_.empty(); }
+    float estimatedSNR() const override { return last_snr_; }
+    float estimatedCFO() const override { return last_cfo_; }
+    float getFadingIndex() const override { return fading_; }
+    bool isFading() const override { return fading_ > 0.65f; }
+    std::vector<std::complex<float>> getConstellationSymbols() const override { return {}; }
+
+private:
+    void sync_configs() {
+        const ultra::MultiCarrierDPSKConfig& m = getConfig();
+        cfg_.sample_rate = m.sample_rate;
+        cfg_.num_carriers = static_cast<uint32_t>(m.num_carriers);
+        cfg_.freq_low = m.freq_low;
+        cfg_.freq_high = m.freq_high;
+        cfg_.samples_per_symbol = static_cast<uint32_t>(m.samples_per_symbol);
+        cfg_.bits_per_symbol = static_cast<uint32_t>(m.bits_per_symbol);
+        cfg_.spreading = static_cast<uint32_t>(m.getSpreadingFactor());
+        cfg_.training_symbols = static_cast<uint32_t>(m.training_symbols);
+        ria_chirp_config_default(&chirp_);
+        const auto cc = m.getChirpConfig();
+        chirp_.sample_rate = cc.sample_rate; chirp_.f_start = cc.f_start; chirp_.f_end = cc.f_end;
+        chirp_.duration_ms = cc.duration_ms; chirp_.gap_ms = cc.gap_ms;
+        ria_zc_config_default(&zc_);
+    }
+    ria_mcdpsk_config cfg_{};
+    ria_chirp_config chirp_{};
+    ria_zc_config zc_{};
+    float cfo_hz_ = 0.0f, last_cfo_ = 0.0f, last_snr_ = 0.0f, fading_ = 0.0f;
+    bool synced_ = false;
+    std::vector<float> soft_bits_;
+};
+
+// What WaveformFactory::create(mode) / create(mode, config) (src/waveform/waveform_factory.cpp:13-61) would
+// return for the two waveforms of the hot path; nullptr for every other mode, like the factory's default branch.
+inline ultra::WaveformPtr createWaveform(ultra::protocol::WaveformMode mode) {
+    switch (mode) {
+        case ultra::protocol::WaveformMode::OFDM_CHIRP: return std::make_unique<OFDMChirpWaveform>();
+        case ultra::protocol::WaveformMode::MC_DPSK: return std::make_unique<MCDPSKWaveform>();
+        default: return nullptr;
+    }
+}
+inline ultra::WaveformPtr createWaveform(ultra::protocol::WaveformMode mode, const ultra::ModemConfig& config) {
+    if (mode == ultra::protocol::WaveformMode::OFDM_CHIRP) return std::make_unique<OFDMChirpWaveform>(config);
+    return createWaveform(mode);
+}
+#endif  // RIA_WITH_ULTRA
 
 }  // namespace ria

@@ -93,6 +93,15 @@ _SIGNATURES = {
     "ria_channel_awgn_batch_dev": (_i32, [_vp, _vp, _i32, _i32, _vp, _f32, C.c_uint64, _i64, _i64, _vp, _i64]),
     "ria_watterson_preset": (_i32, [_i32, _f32, _vp]),
     "ria_channel_watterson_batch_dev": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, C.c_uint64, _i64, _i64, _vp, _i64]),
+    "ria_chirp_detect_dual_batch_host": (_i32, [_vp, _vp, _vp, _i64, _i32, _f32, _i64, _vp]),
+    "ria_zc_detect_batch_host": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _f32, C.c_uint32, _i64, _vp]),
+    "ria_ofdm_data_sync_batch_host": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _f32, _i64, _vp]),
+    "ria_mcdpsk_process_batch_host": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
+    "ria_frame_counters_dev": (_i32, [_vp, _vp, _i64, _vp]),
+    "ria_nccl_get_unique_id": (_i32, [_vp]),
+    "ria_nccl_comm_create": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "ria_nccl_comm_destroy": (_i32, [_vp]),
+    "ria_counters_allreduce": (_i32, [_vp, _vp, _vp, _i32]),
     "ria_crc16": (C.c_uint16, [_vp, C.c_size_t]),
     "ria_channel_interleaver_step": (_i32, [_i32, _i32]),
 }

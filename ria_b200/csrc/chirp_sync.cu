@@ -523,62 +523,143 @@ struct PeakArgs {
     ria_sync_result* out;
 };
 
-// Sequential fp32 prefix sum of s^2 over [start, start+len) (:666-669).  The order of the adds is
-// part of the result, so one thread walks the chain -- but only the chain.  Three shared tiles
-// rotate through load -> chain -> store: while thread 0 adds through tile k (4-cycle dependent
-// FADDs, operands prefetched, no memory latency on the chain), the other warps square and stage
-// tile k+1 from global memory and write the prefix values of tile k-1 back, all coalesced.
+// Sequential fp32 prefix sum of s^2 over [start, start+len) (:666-669): c[i+1] = fl(c[i] + fl(s[i]^2)).
+// The order of the adds is part of the result (the rounding of every step depends on the running sum), and
+// round 1 had ONE thread walk the 170 k-step chain per window -- a single active lane costing full issue
+// slots, 43 % of the kernel's instructions.  The chain is evaluated in parallel here, EXACTLY:
+//
+//  * While the running sum stays inside one binade (ulp u), fl(c + t) = c + u * rne(t / u): the increment does
+//    not depend on c, except for exact ties (t / u = n + 1/2), where round-to-even looks at the PARITY of c's
+//    mantissa.  A chunk of L elements is therefore a function parity -> increment (in ulps), and such functions
+//    compose associatively: (a then b)(p) = a(p) + b(p xor (a(p) & 1)).
+//  * Each thread runs its chunk twice with real float adds from two hypothetical sums of this binade with even
+//    and odd mantissa (2^E and 2^E + u): that gives its function (n0, n1) without any integer emulation of the
+//    rounding.  A block scan of the composition gives every thread the mantissa it really starts from.
+//  * Each thread then runs its chunk a third time from that true start, again with real float adds -- these are
+//    the stored values, so they are the reference's values whenever the start is right.
+//  * The start of thread j is right iff it equals what thread j-1 really ended on.  That comparison is made for
+//    every thread; everything before the first mismatch (a binade crossing, or a chunk that left the binade) is
+//    final, the tile restarts there with the new binade.  Thread 0 always starts from a known-exact value, so
+//    every pass makes progress and the result is exact by construction; prediction only affects speed.
+// Chunk length grows with the position (binade crossings are exponentially rarer as the sum grows).
 // Block-collective; ends with a barrier.
-constexpr int kPrefixTile = 1024;
-__device__ __forceinline__ void prefix_chain(float* tile, int n, float& acc) {
-    float4* t4 = reinterpret_cast<float4*>(tile);
-    const int n8 = n >> 3;
-    float4 a = t4[0], b = t4[1];
-    for (int j = 0; j < n8; ++j) {
-        float4 na = a, nb = b;
-        if (j + 1 < n8) { na = t4[2 * j + 2]; nb = t4[2 * j + 3]; }
-        acc = __fadd_rn(acc, a.x); a.x = acc; acc = __fadd_rn(acc, a.y); a.y = acc;
-        acc = __fadd_rn(acc, a.z); a.z = acc; acc = __fadd_rn(acc, a.w); a.w = acc;
-        acc = __fadd_rn(acc, b.x); b.x = acc; acc = __fadd_rn(acc, b.y); b.y = acc;
-        acc = __fadd_rn(acc, b.z); b.z = acc; acc = __fadd_rn(acc, b.w); b.w = acc;
-        t4[2 * j] = a; t4[2 * j + 1] = b;
-        a = na; b = nb;
-    }
-    for (int i = n8 << 3; i < n; ++i) { acc = __fadd_rn(acc, tile[i]); tile[i] = acc; }
+constexpr int kScanThreads = 256;
+constexpr int kScanMaxChunk = 32;
+constexpr int kScanTile = kScanThreads * kScanMaxChunk;          // 8192 elements
+constexpr int kScanPad = kScanTile + kScanTile / 32;             // one pad word per 32: lane-strided chunks hit distinct banks
+
+struct ScanSmem {
+    float t[kScanPad];
+    float c_end[kScanThreads];
+    unsigned wn0[kScanThreads / 32], wn1[kScanThreads / 32];
+    float c_start;
+    int valid, first_nz;
+};
+
+__device__ __forceinline__ int scan_pad(int e) { return e + (e >> 5); }
+__device__ __forceinline__ unsigned sat_add(unsigned a, unsigned b) { const unsigned s = a + b; return s > 0x40000000u ? 0x40000000u : s; }
+// (a then b): parity -> ulps
+__device__ __forceinline__ void scan_compose(unsigned a0, unsigned a1, unsigned b0, unsigned b1, unsigned& r0, unsigned& r1) {
+    r0 = sat_add(a0, (a0 & 1u) ? b1 : b0);
+    r1 = sat_add(a1, (a1 & 1u) ? b0 : b1);
 }
 
-__device__ void prefix_energy(const float* __restrict__ s, int start, int len, float* __restrict__ c,
-                              float (*tiles)[kPrefixTile]) {
-    const int tid = threadIdx.x;
-    const int n_tiles = (len + kPrefixTile - 1) / kPrefixTile;
-    float acc = 0.0f;                                   // only thread 0's copy is meaningful
-    if (tid == 0) c[0] = 0.0f;
-    // phase k: helpers load tile k, thread 0 chains tile k-1, helpers store tile k-2
-    for (int k = 0; k < n_tiles + 2; ++k) {
-        if (tid == 0) {
-            const int t = k - 1;
-            if (t >= 0 && t < n_tiles) prefix_chain(tiles[t % 3], min(kPrefixTile, len - t * kPrefixTile), acc);
-        } else {
-            if (k < n_tiles) {
-                const int base = k * kPrefixTile, n = min(kPrefixTile, len - base);
-                float* tl = tiles[k % 3];
-                const int hs = blockDim.x - 1;
-                int i = tid - 1;
-                for (; i + 3 * hs < n; i += 4 * hs) {                  // four loads in flight per helper thread
-                    const float v0 = s[start + base + i], v1 = s[start + base + i + hs];
-                    const float v2 = s[start + base + i + 2 * hs], v3 = s[start + base + i + 3 * hs];
-                    tl[i] = __fmul_rn(v0, v0); tl[i + hs] = __fmul_rn(v1, v1);
-                    tl[i + 2 * hs] = __fmul_rn(v2, v2); tl[i + 3 * hs] = __fmul_rn(v3, v3);
-                }
-                for (; i < n; i += hs) { const float v = s[start + base + i]; tl[i] = __fmul_rn(v, v); }
-            }
-            const int t = k - 2;
-            if (t >= 0) {
-                const int base = t * kPrefixTile, n = min(kPrefixTile, len - base);
-                const float* tl = tiles[t % 3];
-                for (int i = tid - 1; i < n; i += blockDim.x - 1) c[base + 1 + i] = tl[i];
-            }
+__device__ void prefix_energy(const float* __restrict__ s, int start, int len, float* __restrict__ c, ScanSmem& sm) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { c[0] = 0.0f; sm.c_start = 0.0f; }
+    int pos = 0;
+    __syncthreads();
+    while (pos < len) {
+        const float c_start = sm.c_start;
+        // ---- chunk length for this pass ----
+        int L = kScanMaxChunk;
+        if (pos < kScanTile) { L = 1; while (L < kScanMaxChunk && L * kScanThreads < pos) L <<= 1; }
+        const int tile = min(L * kScanThreads, len - pos);
+        // ---- stage t = s^2 ----
+        for (int e = tid; e < L * kScanThreads; e += kScanThreads) {
+            float v = 0.0f;
+            if (e < tile) v = s[start + pos + e];
+            sm.t[scan_pad(e)] = __fmul_rn(v, v);
         }
+        if (tid == 0) { sm.valid = tile; sm.first_nz = tile; }
+        __syncthreads();
+        if (c_start == 0.0f || pos < 64 || (__float_as_uint(c_start) >> 23) < 24u) {      // (sums below 2^-103: 2^(23-E) overflows)
+            // Start of the chain: zeros add nothing, and right after the first non-zero term the sum changes binade
+            // with almost every add.  Skip the zeros in parallel, then let one thread take up to 64 steps.
+            if (c_start == 0.0f) {
+                for (int e = tid; e < tile; e += kScanThreads)
+                    if (sm.t[scan_pad(e)] != 0.0f) { atomicMin(&sm.first_nz, e); break; }
+                __syncthreads();
+            } else if (tid == 0) sm.first_nz = 0;
+            __syncthreads();
+            const int z = sm.first_nz;                                   // c stays c_start over [0, z)
+            for (int e = tid; e < z; e += kScanThreads) c[pos + e + 1] = c_start;
+            const int n_seq = min(64, tile - z);
+            if (tid == 0) {
+                float acc = c_start;
+                for (int e = z; e < z + n_seq; ++e) { acc = __fadd_rn(acc, sm.t[scan_pad(e)]); c[pos + e + 1] = acc; }
+                sm.c_start = acc;
+            }
+            pos += z + n_seq;
+            __syncthreads();
+            continue;
+        }
+        // ---- pass 1: the chunk as a function parity -> ulps, from two hypothetical sums of this binade ----
+        const unsigned cs_bits = __float_as_uint(c_start);
+        const float h0 = __uint_as_float(cs_bits & 0x7f800000u);         // 2^E: mantissa 2^23, even
+        const float h1 = __uint_as_float((cs_bits & 0x7f800000u) | 1u);  // 2^E + ulp: odd
+        const float inv_u = __uint_as_float((150u + 127u - (cs_bits >> 23)) << 23);   // 2^(23 - E), E = exponent - 127
+        const int base = tid * L;
+        float a0 = h0, a1 = h1;
+#pragma unroll 4
+        for (int k = 0; k < L; ++k) {
+            const float t = sm.t[scan_pad(base + k)];
+            a0 = __fadd_rn(a0, t); a1 = __fadd_rn(a1, t);
+        }
+        // inside the binade the differences are exact multiples of u below 2^24; beyond it the values are
+        // garbage and the start check below rejects everything that depends on them
+        const float d0 = __fmul_rn(__fsub_rn(a0, h0), inv_u), d1 = __fmul_rn(__fsub_rn(a1, h1), inv_u);
+        unsigned n0 = (d0 >= 0.0f && d0 < 16777216.0f) ? static_cast<unsigned>(d0) : 0x40000000u;
+        unsigned n1 = (d1 >= 0.0f && d1 < 16777216.0f) ? static_cast<unsigned>(d1) : 0x40000000u;
+        // ---- block scan of the composition (inclusive over lanes, then over warps) ----
+        unsigned i0 = n0, i1 = n1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned p0 = __shfl_up_sync(0xffffffffu, i0, d), p1 = __shfl_up_sync(0xffffffffu, i1, d);
+            if (lane >= d) { unsigned r0, r1; scan_compose(p0, p1, i0, i1, r0, r1); i0 = r0; i1 = r1; }
+        }
+        if (lane == 31) { sm.wn0[warp] = i0; sm.wn1[warp] = i1; }
+        __syncthreads();
+        // exclusive prefix of this thread: warps before it, then lanes before it
+        unsigned e0 = 0u, e1 = 0u;
+        for (int w = 0; w < warp; ++w) { unsigned r0, r1; scan_compose(e0, e1, sm.wn0[w], sm.wn1[w], r0, r1); e0 = r0; e1 = r1; }
+        {
+            unsigned q0 = __shfl_up_sync(0xffffffffu, i0, 1), q1 = __shfl_up_sync(0xffffffffu, i1, 1);
+            if (lane == 0) { q0 = 0u; q1 = 0u; }
+            unsigned r0, r1; scan_compose(e0, e1, q0, q1, r0, r1); e0 = r0; e1 = r1;
+        }
+        const unsigned inc = (cs_bits & 1u) ? e1 : e0;
+        // adding ulps to a float inside its binade is an integer add on its bit pattern
+        const float c_in = (inc < 0x01000000u) ? __uint_as_float(cs_bits + inc) : __uint_as_float(0x7fc00000u);
+        // ---- pass 2: the real chain from the predicted start; these are the values that get stored ----
+        float acc = c_in;
+#pragma unroll 4
+        for (int k = 0; k < L; ++k) {
+            const int a = scan_pad(base + k);
+            acc = __fadd_rn(acc, sm.t[a]);
+            sm.t[a] = acc;
+        }
+        sm.c_end[tid] = acc;
+        __syncthreads();
+        // ---- which starts were right?  thread j's start must be what thread j-1 really ended on ----
+        if (tid > 0 && base < tile) {
+            if (__float_as_uint(sm.c_end[tid - 1]) != __float_as_uint(c_in)) atomicMin(&sm.valid, base);
+        }
+        __syncthreads();
+        const int valid = sm.valid;                                       // >= L: thread 0 starts from the exact sum
+        for (int e = tid; e < valid; e += kScanThreads) c[pos + e + 1] = sm.t[scan_pad(e)];
+        if (tid == 0) sm.c_start = sm.c_end[(valid - 1) / L];
+        pos += valid;
         __syncthreads();
     }
 }
@@ -684,15 +765,16 @@ __device__ void td_detect(const float* s, int len, const float2* tmpl, int CL, f
     *out_pos = (best >= threshold) ? pos : -1;
 }
 
-// The kernel's time is the latency of the serial prefix chains (~170 k dependent FADDs per window), so what
-// matters is how many windows are in flight: 128-thread CTAs with 1024-element tiles fit 14 per SM,
-// 14 x 148 = 2072 >= one 2048-window slice in a single wave.
-constexpr int kPeakThreads = 128;
-__global__ void __launch_bounds__(kPeakThreads, 14)
+// One CTA per window: exact parallel energy prefix (above), normalised peak over all lags for the up chirp, then the
+// same for the down chirp on the slice the up-chirp peak selects.  (Round 1 ran the prefix as one serial chain per
+// window and needed 14 windows per SM in flight to hide its latency; the parallel prefix needs ~3.5x fewer issue
+// slots and no latency hiding.)
+constexpr int kPeakThreads = kScanThreads;
+__global__ void __launch_bounds__(kPeakThreads, 5)
 chirp_peak_kernel(const PeakArgs a) {
     __shared__ float red_v[256];
     __shared__ int red_i[256];
-    __shared__ __align__(16) float tile[3][kPrefixTile];
+    __shared__ ScanSmem tile;
     const long long f = blockIdx.x;
     const int tid = threadIdx.x;
     const float* s = a.samples + f * a.frame_stride;

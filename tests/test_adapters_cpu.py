@@ -45,3 +45,13 @@ def test_adapters_compile_against_reference_headers(ria_lib):
     if not os.path.isdir("/root/reference/src/fec"):
         pytest.skip("reference tree not present")
     _compile(["-DRIA_WITH_ULTRA", "-I/root/reference/include", "-I/root/reference/src"])
+
+
+def test_waveform_dropins_are_iwaveforms_and_the_harness_links(ria_lib):
+    """ria::OFDMChirpWaveform / ria::MCDPSKWaveform derive from the reference's waveform classes (hence from
+    ultra::IWaveform) and ria::createWaveform hands them out as WaveformPtr: the harness that runs them on the GPU
+    (tests/test_waveform_dropin_gpu.py) compiles and links against the reference objects."""
+    if not os.path.isdir("/root/reference/src/waveform"):
+        pytest.skip("reference tree not present")
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "harness"], check=True)
+    assert os.path.exists(os.path.join(ROOT, "oracle", "_ref", "waveform_harness"))
