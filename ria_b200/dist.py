@@ -74,3 +74,54 @@ def frame_counters(status, sent_ok=None) -> torch.Tensor:
     ok = (st["all_ok"] == 1) & (st["header_valid"] == 1) & (st["frame_crc_ok"] == 1)
     return torch.tensor([len(st), int(ok.sum()), 4 * len(st), int((st["cw_ok"] == 0).sum()), 0, 0, 0,
                          int(((st["all_ok"] == 1) & ~ok).sum())], dtype=torch.int64)
+
+
+def frame_counters_dev(status: torch.Tensor, ctx, out: torch.Tensor = None) -> torch.Tensor:
+    """COUNTER_NAMES of a ria_frame_status device array, accumulated by a kernel on the context stream
+    (ria_frame_counters_dev) into an int64[8] device tensor -- no eager tensor ops, no host sync."""
+    import ctypes as C
+    from ._lib import lib
+    from .ofdm import FRAME_STATUS_DTYPE
+    assert status.is_cuda and status.dtype == torch.uint8 and status.shape[1] == FRAME_STATUS_DTYPE.itemsize
+    status = status.contiguous()
+    if out is None:
+        out = torch.zeros(len(COUNTER_NAMES), dtype=torch.int64, device=status.device)
+    ctx.set_stream(torch.cuda.current_stream(status.device))
+    ctx.check(lib().ria_frame_counters_dev(ctx.handle, C.c_void_p(status.data_ptr()), status.shape[0], C.c_void_p(out.data_ptr())))
+    return out
+
+
+class CounterComm:
+    """The path's one collective through the C ABI: ria_counters_allreduce = ncclAllReduce(sum, int64) on the
+    context stream.  The NCCL communicator is the library's own: rank 0 draws the unique id
+    (ria_nccl_get_unique_id), torch.distributed only carries those 128 bytes to the other ranks."""
+
+    def __init__(self, ctx, rank: int, world: int):
+        import ctypes as C
+        from ._lib import lib
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.comm = C.c_void_p()
+        uid = (C.c_char * 128)()
+        if rank == 0:
+            rc = lib().ria_nccl_get_unique_id(C.addressof(uid))
+            if rc != 0:
+                raise RuntimeError("NCCL is not loadable in this process")
+        box = [bytes(uid)]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        uid = (C.c_char * 128).from_buffer_copy(box[0])
+        ctx.check(lib().ria_nccl_comm_create(ctx.handle, C.addressof(uid), rank, world, C.addressof(self.comm)))
+
+    def allreduce(self, counters: torch.Tensor) -> torch.Tensor:
+        import ctypes as C
+        from ._lib import lib
+        assert counters.is_cuda and counters.dtype == torch.int64 and counters.is_contiguous()
+        self.ctx.set_stream(torch.cuda.current_stream(counters.device))
+        self.ctx.check(lib().ria_counters_allreduce(self.ctx.handle, self.comm, C.c_void_p(counters.data_ptr()), counters.numel()))
+        return counters
+
+    def close(self):
+        from ._lib import lib
+        if self.comm:
+            lib().ria_nccl_comm_destroy(self.comm)
+            self.comm = None
