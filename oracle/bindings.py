@@ -120,7 +120,8 @@ class FrameStatus(C.Structure):
 
 # ultra::Modulation (include/ultra/types.hpp:27-39)
 DBPSK, BPSK, DQPSK, QPSK, D8PSK, QAM8, QAM16, QAM32, QAM64 = range(9)
-BITS_PER_CARRIER = {DBPSK: 1, BPSK: 1, DQPSK: 2, QPSK: 2, D8PSK: 3, QAM8: 3, QAM16: 4, QAM32: 5, QAM64: 6}
+QAM256 = 10
+BITS_PER_CARRIER = {DBPSK: 1, BPSK: 1, DQPSK: 2, QPSK: 2, D8PSK: 3, QAM8: 3, QAM16: 4, QAM32: 5, QAM64: 6, QAM256: 8}
 BYTES_PER_CW = {R1_4: 20, R1_2: 40, R2_3: 54, R3_4: 60, R5_6: 67}
 
 

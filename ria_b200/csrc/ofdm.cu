@@ -123,6 +123,8 @@ struct FrameScalars {
     int noise_count;
     int have_prev_pilot;
     int have_dd;
+    float last_fading;          // last_fading_index (LTS / pilot magnitude CV): gates the D8PSK two-pass demap
+    float2 d8_corr;             // D8PSK two-pass: common phase correction of the current symbol
 };
 
 constexpr int kMaxPilots = 32;      // pilot_spacing >= 2 (checked by ofdm_config_error)
@@ -216,6 +218,18 @@ __device__ __forceinline__ float ce_margin(int mod) {
 }
 
 // QAM32 max-log demap, soft_demap.hpp:68-121
+// demapD8PSK (soft_demap.hpp:238-263): natural-binary 8-phase differential, sin-based LLRs
+__device__ __noinline__ void demap_d8psk(float2 sym, float sym_mag, float2 prev, float nv, float* out) {
+    const float2 diff = cmul(sym, cconj(prev));
+    const float pd = atan2_rn(diff.y, diff.x);
+    const float sp = sym_mag * cabs(prev);
+    if (sp < 1e-6f) { out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; return; }      // neutral, NOT clipped to +-0.01
+    const float conf = sp / (2.0f * nv);
+    out[0] = clip_llr(conf * sin_rn(pd));
+    out[1] = clip_llr(conf * sin_rn(2.0f * pd));
+    out[2] = clip_llr(conf * sin_rn(4.0f * pd));
+}
+
 __device__ void demap_qam32(float2 sym, float nv, float* out) {
     const float I_LEVELS[4] = {-3, -1, 1, 3};
     const int I_GRAY[4] = {0, 1, 3, 2};
@@ -289,6 +303,18 @@ __device__ __forceinline__ float ordered_sum_rows(const float* rows, int n_rows,
         for (int i = 0; i < n; ++i) s = __fadd_rn(s, a[i]);
     }
     return s;
+}
+
+// sqrt(var) / mean of n magnitudes with the reference's loops (mean first, then the squared deviations, both in
+// index order): last_fading_index after the LTS (channel_equalizer.cpp:623-638) and after a pilot update (:1007-1023)
+__device__ __noinline__ float magnitude_cv(const float* mags, int n) {
+    float mean = 0.0f;
+    for (int i = 0; i < n; ++i) mean = __fadd_rn(mean, mags[i]);
+    mean = __fdiv_rn(mean, static_cast<float>(n));
+    float var = 0.0f;
+    for (int i = 0; i < n; ++i) { const float d = __fsub_rn(mags[i], mean); var = __fadd_rn(var, __fmul_rn(d, d)); }
+    var = __fdiv_rn(var, static_cast<float>(n));
+    return (mean > 0.01f) ? __fdiv_rn(sqrtf(var), mean) : 0.0f;
 }
 
 // =============================== carrier-domain processing =================================
@@ -438,6 +464,13 @@ __device__ __forceinline__ void lts_finish(CarState& cs, const OfdmCarrierTable&
             cs.s.snr_lin = snr;
         }
         cs.s.snr_count = 2;                                       // :642
+    }
+    if (a.modulation == RIA_D8PSK) {                                  // LTS fading index (:619-639); only D8PSK reads it
+        gsync<G>();
+        #pragma unroll 1
+        for (int i = g; i < nd; i += G) cs.tmpf[i] = cabs(cs.H[car.data_car[i]]);
+        gsync<G>();
+        if (g == 0) cs.s.last_fading = magnitude_cv(cs.tmpf, nd);
     }
     if (a.h_lts_tap)
         #pragma unroll 1
@@ -637,6 +670,13 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
                 cs.H[c] = make_float2(im * e.x, im * e.y);
             }
         }
+        if (mod == RIA_D8PSK) {                                        // fading index from the pilot magnitudes (:1007-1023)
+            gsync<G>();
+            #pragma unroll 1
+            for (int i = g; i < np; i += G) cs.tmpf[i] = cabs(cs.pil_ls[i]);
+            gsync<G>();
+            if (g == 0) cs.s.last_fading = magnitude_cv(cs.tmpf, np);
+        }
         gsync<G>();     // every thread has read snr_count / have_dd before thread 0 moves them on
         if (g == 0) {
             if (!differential && cs.s.noise_count > 1) {          // :1035-1039
@@ -660,6 +700,8 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
     gsync<G>();
     const bool dd_mod = !differential && (mod == RIA_QPSK || mod == RIA_BPSK || mod == RIA_QAM16 ||
                                           mod == RIA_QAM32 || mod == RIA_QAM64);
+    // D8PSK on a fading channel takes the two-pass demapper (demodulator.cpp:286-296, TWO_PASS_FADING_THRESHOLD 0.30)
+    const bool d8_two_pass = (mod == RIA_D8PSK) && cs.s.last_fading > 0.30f;
     #pragma unroll 1
     for (int i = g; i < nd; i += G) {
         const int c = car.data_car[i];
@@ -757,6 +799,17 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
                 cs.prev_eq[i] = sym;
                 break;
             }
+            case RIA_D8PSK: {                                 // demapD8PSK, soft_demap.hpp:238-263
+                if (d8_two_pass) {                            // needs the phase statistics of ALL carriers first
+                    cs.tmpc[i] = sym;
+                    cs.dd[i] = nv;
+                    break;
+                }
+                const float2 prev = first ? make_float2(1.0f, 0.0f) : cs.prev_eq[i];
+                demap_d8psk(sym, mag, prev, nv, out);
+                cs.prev_eq[i] = sym;
+                break;
+            }
             case RIA_BPSK:                                    // soft_demap.hpp:37-39
                 out[0] = clip_llr(-2.0f * sym.x / nv);
                 break;
@@ -805,6 +858,53 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
                 break;
             }
             default: break;
+        }
+    }
+    if (d8_two_pass) {
+        // demodulateD8PSKTwoPass (demodulator.cpp:533-624).  Pass 1: common phase error against the embedded DQPSK grid
+        // (45, 135, 225, 315 degrees), a power-weighted circular mean whose three sums run in carrier order.
+        gsync<G>();
+        float* w_row = reinterpret_cast<float*>(cs.flag);
+        #pragma unroll 1
+        for (int i = g; i < nd; i += G) {
+            const float2 eq = cs.tmpc[i];
+            const float2 prev = first ? make_float2(1.0f, 0.0f) : cs.prev_eq[i];
+            const float sp = cabs(eq) * cabs(prev);
+            float ts = 0.0f, tc = 0.0f, tw = 0.0f;                 // adding zero leaves the ordered sums unchanged
+            if (sp > 0.1f) {
+                const float2 diff = cmul(eq, cconj(prev));
+                const float phase = atan2_rn(diff.y, diff.x);
+                const float pmo = static_cast<float>(static_cast<double>(phase) - M_PI / 4.0f);
+                int q = static_cast<int>(round(static_cast<double>(pmo * 2.0f) / M_PI));
+                q = ((q % 4) + 4) % 4;
+                const float expected = static_cast<float>(q * M_PI / 2.0f + M_PI / 4.0f);
+                float err = phase - expected;
+                while (err > M_PI) err = static_cast<float>(err - 2 * M_PI);
+                while (err < -M_PI) err = static_cast<float>(err + 2 * M_PI);
+                ts = sp * sin_rn(err); tc = sp * cos_rn(err); tw = sp;
+            }
+            cs.tmpf[i] = ts; cs.tmpg[i] = tc; w_row[i] = tw;
+        }
+        gsync<G>();
+        if (g == 0) {
+            const float sin_sum = ordered_sum(cs.tmpf, nd), cos_sum = ordered_sum(cs.tmpg, nd), w_sum = ordered_sum(w_row, nd);
+            const float mean_error = (w_sum > 0.1f) ? atan2_rn(sin_sum, cos_sum) : 0.0f;
+            float2 corr = make_float2(1.0f, 0.0f);
+            if (fabsf(mean_error) > 0.05f && fabsf(mean_error) < 0.26f) {      // half of errors between 3 and 15 degrees
+                const float ce = mean_error * 0.5f;
+                corr = make_float2(cos_rn(-ce), sin_rn(-ce));
+            }
+            cs.s.d8_corr = corr;
+            cs.s.snr_count += 1;                                               // :292
+        }
+        gsync<G>();
+        // Pass 2: rotate, demap, and keep the ROTATED symbol as the next differential reference (:588-612)
+        #pragma unroll 1
+        for (int i = g; i < nd; i += G) {
+            const float2 prev = first ? make_float2(1.0f, 0.0f) : cs.prev_eq[i];
+            const float2 csym = cmul(cs.tmpc[i], cs.s.d8_corr);
+            demap_d8psk(csym, cabs(csym), prev, cs.dd[i], llr_out + sd * llr_per_sym + i * bpc);
+            cs.prev_eq[i] = csym;
         }
     }
     gsync<G>();      // everybody has read snr_count / have_dd of this symbol
@@ -1520,6 +1620,7 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
     switch (cfg->modulation) {
         case RIA_DBPSK:  carrier_kernel = ofdm_carrier_kernel<RIA_DBPSK>; break;
         case RIA_DQPSK:  carrier_kernel = ofdm_carrier_kernel<RIA_DQPSK>; break;
+        case RIA_D8PSK:  carrier_kernel = ofdm_carrier_kernel<RIA_D8PSK>; break;
         case RIA_BPSK:   carrier_kernel = ofdm_carrier_kernel<RIA_BPSK>; break;
         case RIA_QPSK:   carrier_kernel = ofdm_carrier_kernel<RIA_QPSK>; break;
         case RIA_QAM16:  carrier_kernel = ofdm_carrier_kernel<RIA_QAM16>; break;

@@ -64,9 +64,11 @@ const char* ofdm_config_error(const ria_modem_config& c) {
     if (c.use_pilots && (c.num_carriers + c.pilot_spacing - 1) / c.pilot_spacing > 32)
         return "more than 32 pilot carriers (pilot_spacing must be >= 2)";
     switch (c.modulation) {
-        case RIA_DBPSK: case RIA_BPSK: case RIA_DQPSK: case RIA_QPSK:
+        case RIA_DBPSK: case RIA_BPSK: case RIA_DQPSK: case RIA_QPSK: case RIA_D8PSK:
         case RIA_QAM16: case RIA_QAM32: case RIA_QAM64: case RIA_QAM256: break;
-        default: return "modulation not supported by the batched chain (D8PSK two-pass / QAM8 not built)";
+        // QAM8 has no demapper in the reference either (demodulateSymbol's default branch emits two QPSK soft bits
+        // for a three-bit symbol, demodulator.cpp:404-409)
+        default: return "modulation not supported (QAM8 has no demapper in the reference)";
     }
     if (c.cp_mode > 2) return "bad cp_mode";
     return nullptr;

@@ -18,6 +18,7 @@
 // transmitter is not on the receive hot path, the kernel is written for exactness, not for speed.
 
 #include "ofdm_tables.h"
+#include "rn_math.h"
 
 namespace ria {
 namespace {
@@ -123,6 +124,11 @@ ofdm_tx_kernel(const TxArgs a) {
                         } else if (a.modulation == RIA_DQPSK) {
                             const float2 ph[4] = {make_float2(1.f, 0.f), make_float2(0.f, 1.f), make_float2(-1.f, 0.f), make_float2(0.f, -1.f)};
                             v = cmul_ref(prev[tid], ph[bits & 3]); prev[tid] = v;
+                        } else if (a.modulation == RIA_D8PSK) {
+                            // 45-degree steps with a 22.5-degree offset (modulator.cpp:436-445), cosf / sinf as glibc
+                            const float pi = 3.14159265358979f;
+                            const float angle = __fadd_rn(__fmul_rn(static_cast<float>(bits & 7), pi / 4.0f), pi / 8.0f);
+                            v = cmul_ref(prev[tid], make_float2(glibc_cosf(angle), glibc_sinf(angle))); prev[tid] = v;
                         } else {
                             v = map_bits(bits, a.modulation);
                         }

@@ -2,7 +2,7 @@
 import numpy as np
 
 from oracle.bindings import (ModemConfig, R1_2, R1_4, R2_3, R3_4, BITS_PER_CARRIER, BYTES_PER_CW,
-                             DBPSK, BPSK, DQPSK, QPSK, QAM16, QAM32, QAM64)
+                             DBPSK, BPSK, DQPSK, QPSK, D8PSK, QAM16, QAM32, QAM64, QAM256)
 
 # (name, modulation, pilot_spacing, use_pilots, code rate, snr_db)
 CASES = [
@@ -14,6 +14,8 @@ CASES = [
     ("bpsk_r14_sp5", BPSK, 5, 1, R1_4, 6.0),
     ("dbpsk_r14_sp10", DBPSK, 10, 1, R1_4, 6.0),
     ("dqpsk_nopilots", DQPSK, 2, 0, R1_2, 18.0),
+    ("d8psk_r12_sp8", D8PSK, 8, 1, R1_2, 20.0),         # demapD8PSK (soft_demap.hpp:238-263), single pass on AWGN
+    ("qam256_r34_sp4", QAM256, 4, 1, R3_4, 36.0),       # demapQAM256 (soft_demap.hpp:145-164)
 ]
 
 

@@ -20,7 +20,7 @@ import time
 import numpy as np
 import pytest
 
-from oracle.bindings import (BITS_PER_CARRIER, BYTES_PER_CW, DQPSK, QAM64, R1_2, R1_4, R3_4, McdpskConfig,
+from oracle.bindings import (BITS_PER_CARRIER, BYTES_PER_CW, D8PSK, DQPSK, QAM64, R1_2, R1_4, R3_4, McdpskConfig,
                              ModemConfig, Ref, WattersonConfig as RefWatt)
 
 pytestmark = pytest.mark.gpu
@@ -192,6 +192,17 @@ def test_ofdm_watterson_presets_wide(ctx, ref, cond, cname):
     _assert_exact(e)
     e = _ofdm_case(ctx, f"c1_dqpsk_r12_watterson_{cname}_18dB", DQPSK, 10, R1_2, 18.0, N_FADED, fade_cond=cond)
     _assert_exact(e)
+
+
+def test_d8psk_single_and_two_pass_wide(ctx, ref):
+    """D8PSK (a10): the single-pass demapper on AWGN, and the two-pass demapper that the LTS / pilot fading index
+    switches on above 0.30 (demodulator.cpp:286-296, 533-624) on frames faded by the reference channel."""
+    e = _ofdm_case(ctx, "d8psk_r12_awgn20", D8PSK, 8, R1_2, 20.0, max(256, N_AWGN // 4))
+    _assert_exact(e)
+    assert e["mean_fading_index"] < 0.30
+    e = _ofdm_case(ctx, "d8psk_r12_watterson_moderate_24dB", D8PSK, 8, R1_2, 24.0, max(256, N_FADED // 2), fade_cond=2)
+    _assert_exact(e)
+    assert e["mean_fading_index"] > 0.30, "operating point does not reach the two-pass branch"
 
 
 # ---------------------------------------------------------------------------------------------
