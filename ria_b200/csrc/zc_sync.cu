@@ -13,7 +13,8 @@
 // the ZC template (chips and interpolation) is built on the host with the reference's float
 // expressions.  Kernels:
 //   zc_baseband_kernel   bb[i] = rx[i] * e^{-j 2 pi (fc + known_cfo) i / fs}   (HBM scratch, once per frame)
-//   zc_coarse_kernel     one thread per coarse lag: (sum, energy) -> normalised corr + magnitude
+//   zc_coarse_tile_kernel  one CTA per tile of 256 coarse lags, baseband span and templates staged in shared
+//                        memory, all selected roots per pass: (sum, energy) -> normalised corr + magnitude
 //   zc_finish_kernel     one CTA per frame: coarse arg-max, fine lags, peak, rep-1 adjust,
 //                        combining, CFO, best root
 
@@ -84,25 +85,87 @@ __global__ void zc_baseband_kernel(const float* __restrict__ samples, long long 
     bb[f * bb_stride + i] = make_float2(__fmul_rn(static_cast<float>(c), r), __fmul_rn(static_cast<float>(s), r));
 }
 
-__global__ void __launch_bounds__(128)
-zc_coarse_kernel(const float2* __restrict__ bb, long long bb_stride, int window, const float2* __restrict__ zc_g,
-                 int ref_samples, int step, int n_coarse, int n_roots, const int* __restrict__ root_slot,
-                 float2* __restrict__ coarse_corr, float* __restrict__ coarse_mag) {
-    extern __shared__ float2 zc[];
-    const long long f = blockIdx.z;
-    const int r = blockIdx.y;
-    const float2* zsrc = zc_g + static_cast<size_t>(root_slot[r]) * ref_samples;
-    for (int i = threadIdx.x; i < ref_samples; i += blockDim.x) zc[i] = zsrc[i];
+// Blackwell packed fp32: two IEEE round-to-nearest products / sums per issue slot.  ptxas would contract a packed
+// multiply that feeds a packed ADD into FFMA2 even under --fmad=false, so products only ever feed SCALAR adds.
+__device__ __forceinline__ float2 zc_mul2s(float s, float2 b) {             // (s * b.x, s * b.y)
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%2}; mov.b64 rb, {%3,%4}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(s), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 zc_mul2(float2 a, float2 b) {             // (a.x * b.x, a.y * b.y)
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 zc_add2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+
+// Coarse lags (zc_sync.hpp:522-560): one CTA owns a tile of kCoarseLags consecutive coarse lags of one window and
+// evaluates them for ALL selected roots at once.  The baseband span the tile touches ((lags - 1) * step + R samples)
+// and the templates are staged in shared memory once; each thread then walks its lag's R terms in the reference's
+// order, keeping one (sum, energy) accumulator set in registers -- the baseband sample and the energy term are shared
+// by the roots.  With the odd step the threads of a half-warp read 16 different bank pairs (conflict-free), the
+// template read is a broadcast.  Per term and root: two packed multiplies, two scalar adds, one packed accumulate
+//   b * conj(z) = (bx zx + by zy, by zx - bx zy)   with the template stored as (zx, -zy, zy, zx)
+// (the same products and the same sums as the reference's complex multiply: a - (-c) = a + c exactly).
+constexpr int kCoarseLags = 256;
+
+template <int NR>
+__global__ void __launch_bounds__(kCoarseLags)
+zc_coarse_tile_kernel(const float2* __restrict__ bb, long long bb_stride, int window, const float2* __restrict__ zc_g,
+                      int ref_samples, int step, int n_coarse, const int* __restrict__ root_slot,
+                      float2* __restrict__ coarse_corr, float* __restrict__ coarse_mag) {
+    extern __shared__ __align__(16) unsigned char zc_smem[];
+    float4* zt = reinterpret_cast<float4*>(zc_smem);                         // [NR][R] (zx, -zy, zy, zx)
+    float2* tile = reinterpret_cast<float2*>(zt + static_cast<size_t>(NR) * ref_samples);
+    const long long f = blockIdx.y;
+    const int R = ref_samples;
+    const int k0 = blockIdx.x * kCoarseLags;
+    const int n_here = min(kCoarseLags, n_coarse - k0);
+    const int span = (n_here - 1) * step + R;                                 // <= window - k0 * step by construction
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const float2* zsrc = zc_g + static_cast<size_t>(root_slot[r]) * R;
+        for (int i = threadIdx.x; i < R; i += kCoarseLags) { const float2 z = zsrc[i]; zt[r * R + i] = make_float4(z.x, -z.y, z.y, z.x); }
+    }
+    const float2* src = bb + f * bb_stride + static_cast<long long>(k0) * step;
+    for (int i = threadIdx.x; i < span; i += kCoarseLags) tile[i] = src[i];
     __syncthreads();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_coarse) return;
-    float2 sum; float en;
-    corr_at(bb + f * bb_stride, zc, ref_samples, k * step, &sum, &en);
-    const float ref_energy = static_cast<float>(ref_samples);
+    const int t = threadIdx.x;
+    if (t >= n_here) return;
+    const float2* p = tile + t * step;
+    float2 sum[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) sum[r] = make_float2(0.f, 0.f);
+    float en = 0.f;
+#pragma unroll 2
+    for (int i = 0; i < R; ++i) {
+        const float2 b = p[i];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const float4 z = zt[r * R + i];
+            const float2 p1 = zc_mul2s(b.x, make_float2(z.x, z.y));          // (bx zx, bx (-zy))
+            const float2 p2 = zc_mul2s(b.y, make_float2(z.z, z.w));          // (by zy, by zx)
+            const float re = __fadd_rn(p1.x, p2.x), im = __fadd_rn(p1.y, p2.y);
+            sum[r] = zc_add2(sum[r], make_float2(re, im));
+        }
+        const float2 sq = zc_mul2(b, b);
+        en = __fadd_rn(en, __fadd_rn(sq.x, sq.y));
+    }
+    const float ref_energy = static_cast<float>(R);
     const float denom = sqrtf(__fmul_rn(en, ref_energy));
-    const size_t o = (static_cast<size_t>(f) * n_roots + r) * n_coarse + k;
-    coarse_mag[o] = (denom > 1e-10f) ? __fdiv_rn(cabs_d(sum), denom) : 0.0f;
-    coarse_corr[o] = (denom > 1e-10f) ? make_float2(__fdiv_rn(sum.x, denom), __fdiv_rn(sum.y, denom)) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const size_t o = (static_cast<size_t>(f) * NR + r) * n_coarse + k0 + t;
+        coarse_mag[o] = (denom > 1e-10f) ? __fdiv_rn(cabs_d(sum[r]), denom) : 0.0f;
+        coarse_corr[o] = (denom > 1e-10f) ? make_float2(__fdiv_rn(sum[r].x, denom), __fdiv_rn(sum[r].y, denom)) : make_float2(0.f, 0.f);
+    }
 }
 
 struct FinishArgs {
@@ -354,9 +417,23 @@ extern "C" int ria_zc_detect_batch_dev(ria_ctx* ctx, const ria_zc_config* cfg,
                                                          cfg->sample_rate, d_bb, static_cast<long long>(bb_stride));
     }
     {
-        dim3 grid(static_cast<unsigned>((n_coarse + 127) / 128), static_cast<unsigned>(n_roots), static_cast<unsigned>(n_frames));
-        zc_coarse_kernel<<<grid, 128, R * sizeof(float2), ctx->stream>>>(d_bb, static_cast<long long>(bb_stride), window, t->zc_interp, R,
-                                                                        step, n_coarse, n_roots, d_slots, d_cc, d_cm);
+        dim3 grid(static_cast<unsigned>((n_coarse + kCoarseLags - 1) / kCoarseLags), static_cast<unsigned>(n_frames));
+        const size_t smem = static_cast<size_t>(n_roots) * R * sizeof(float4) +
+                            (static_cast<size_t>(kCoarseLags - 1) * step + R) * sizeof(float2);
+        auto launch = [&](auto kernel) -> int {
+            RIA_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kernel<<<grid, kCoarseLags, smem, ctx->stream>>>(d_bb, static_cast<long long>(bb_stride), window, t->zc_interp, R, step,
+                                                            n_coarse, d_slots, d_cc, d_cm);
+            return RIA_OK;
+        };
+        if (smem > ctx->smem_optin) return set_error(ctx, RIA_E_UNSUPPORTED, "zc: coarse tile does not fit in shared memory");
+        switch (n_roots) {
+            case 1: rc = launch(zc_coarse_tile_kernel<1>); break;
+            case 2: rc = launch(zc_coarse_tile_kernel<2>); break;
+            case 3: rc = launch(zc_coarse_tile_kernel<3>); break;
+            default: rc = launch(zc_coarse_tile_kernel<4>); break;
+        }
+        if (rc != RIA_OK) return rc;
     }
     fa.bb = d_bb; fa.bb_stride = static_cast<long long>(bb_stride); fa.window = window;
     fa.zc_g = t->zc_interp; fa.ref_samples = R; fa.step = step; fa.n_coarse = n_coarse; fa.n_roots = n_roots;

@@ -100,11 +100,14 @@ int main() {
     struct { Modulation mod; CodeRate rate; float snr; } ofdm_cases[] = {
         {Modulation::DQPSK, CodeRate::R1_2, 18.0f}, {Modulation::QAM64, CodeRate::R3_4, 30.0f}, {Modulation::QAM16, CodeRate::R2_3, 24.0f}};
     for (auto& oc : ofdm_cases) {
-        ultra::OFDMChirpWaveform ref;
+        // the modem's configuration (ModemConfig defaults: 1024-point FFT, 59 carriers), as WaveformFactory::create(mode,
+        // config) builds it; the default-constructed waveform is a 512-point / 30-carrier variant the chain does not cover
+        ModemConfig mcfg;
+        ultra::OFDMChirpWaveform ref(mcfg);
 #ifdef HARNESS_SELFTEST      // reference against itself: validates the scenario without a GPU
-        WaveformPtr dut = std::make_unique<ultra::OFDMChirpWaveform>();
+        WaveformPtr dut = std::make_unique<ultra::OFDMChirpWaveform>(mcfg);
 #else
-        WaveformPtr dut = ria::createWaveform(protocol::WaveformMode::OFDM_CHIRP);
+        WaveformPtr dut = ria::createWaveform(protocol::WaveformMode::OFDM_CHIRP, mcfg);
 #endif
         CHECK(dut != nullptr && dut->getMode() == protocol::WaveformMode::OFDM_CHIRP, "factory");
         ref.configure(oc.mod, oc.rate);
