@@ -153,6 +153,13 @@ def main():
         ms = timed(lambda: zc.detect_batch(win, 0.3, sync.ZC_ROOT_MASK_DATA | sync.ZC_ROOT_MASK_CONTROL))
         add("ria_zc_detect_batch_dev  window 7120, roots DATA+CONTROL", n, ms, 7120 * 4 + 32, "windows")
         del win
+        # the production search window of StreamingDecoder (streaming_decoder.cpp:423-435): 31 120 samples
+        row = np.concatenate([np.zeros(9000, np.float32), pre, np.zeros(31120 - 9000 - len(pre), np.float32)])
+        n = 16384
+        win = sim.awgn_batch(torch.from_numpy(np.stack([row] * 4)).to(dev), n, 0.0, seed=7, ctx=ctx)
+        ms = timed(lambda: zc.detect_batch(win, 0.3, sync.ZC_ROOT_MASK_DATA | sync.ZC_ROOT_MASK_CONTROL))
+        add("ria_zc_detect_batch_dev  window 31120 (production), roots DATA+CONTROL", n, ms, 31120 * 4 + 32, "windows")
+        del win
         ch = sync.ChirpSync(None, ctx)
         pre = txsynth.chirp_preamble()
         row = np.concatenate([np.zeros(2000, np.float32), pre, np.zeros(120000 - 2000 - len(pre), np.float32)])

@@ -41,6 +41,13 @@ struct ChirpTablesDev {
     float2* tmpl_dn_time = nullptr;   // (cos, sin) of the down-chirp template, time domain
     float energy_up = 0.f, energy_dn = 0.f;
     int chirp_len = 0, gap = 0;
+    // residue-decomposed transform (default path): twiddle tables, template spectra in [residue][digit-reversed]
+    // order, and the per-CTA spill row of the second template product
+    float2* res_tables = nullptr;     // wa_hi | wa_lo | wb | wc | wr_hi | wr_lo
+    float2* tmpl_up_res = nullptr;    // [8][16384]
+    float2* tmpl_dn_res = nullptr;
+    float2* res_scratch = nullptr;    // [res_grid][16384]
+    int res_grid = 0;
 };
 
 namespace {
@@ -420,6 +427,328 @@ fft_slab_kernel(const StageArgs a) {
             reinterpret_cast<float4*>(out)[e] = make_float4(p0.x, p0.y, p1.x, p1.y);
         }
         __syncthreads();
+    }
+}
+
+// =============================================================================================
+// Residue-decomposed matched filter (default path): the 2^17-point transforms run out of shared memory.
+//
+// N = 8 x M, M = 16384.  With k = 8 q + r the forward transform splits into eight independent M-point transforms,
+// one per residue r:   X[8 q + r] = sum_m W_M^{m q} z_r[m],   z_r[m] = W_N^{m r} sum_a x[M a + m] W_8^{a r}.
+// A CTA owns one (window, r): it reads the real window once (the other seven CTAs of the window hit L2), forms z_r,
+// runs the M-point transform in place in 128 KB of shared memory (four passes, radix 16 x 16 x 8 x 8, decimation in
+// frequency; the spectrum stays in digit-reversed order, which the template spectra share), multiplies by the two
+// template spectra and runs the mirrored decimation-in-time inverse for each, leaving v_r[m] in natural order.
+// What reaches HBM is v_r for the two templates (2 MB per window).  The lag-domain result needs one radix-8
+// butterfly over r,   R[M a + m] = sum_r v'_r[m] W_8^{-a r},   v'_r[m] = W_N^{-m r} v_r[m] / N,
+// which chirp_combine_kernel applies while it forms the magnitudes for the peak search.
+// Per window: 0.48 MB of samples + 2 MB out + 2 MB in + magnitudes instead of ~14.5 MB of spectrum passes.
+//
+// Shared-memory layout: point i lives at i ^ ((i >> 4) & 15).  For every pass the lanes of each half-warp then fall
+// on sixteen different 8-byte bank pairs (thread mappings below), so all 64-bit accesses are conflict-free.
+// Twiddles come from exact tables (pass B: W_1024^e, pass C: W_64^e) or, for the M-point pass-A factors W_M^{t k},
+// from two exact 512-entry tables and one extra product (W_M^{(32 th + tl) k} = W_512^{th k} W_M^{tl k}).
+// =============================================================================================
+constexpr int kM = 16384;
+constexpr int kResThreads = 512;
+
+struct ResidueTables {            // device pointers, built once per context
+    const float2* wa_hi;          // [16][32]  W_512^{th k}
+    const float2* wa_lo;          // [16][32]  W_M^{tl k}
+    const float2* wb;             // [16][64]  W_1024^{t k}
+    const float2* wc;             // [64]      W_64^e
+    const float2* wr_hi;          // [8][128]  W_N^{128 r mh}
+    const float2* wr_lo;          // [8][128]  W_N^{r ml}
+};
+
+struct ResidueArgs {
+    const float* samples; long long stride; int n_in;          // MODE 0: real windows
+    const float2* cplx_in;                                      // MODE 1: one complex input of kN points
+    const float2* tmpl_up; const float2* tmpl_dn;               // [8][kM] conj template spectra, residue / digit-reversed order
+    float2* out_up; float2* out_dn;                             // MODE 0: [n_win][8][kM] v'_r[m];  MODE 1: out_up = [8][kM] conj spectrum
+    float2* scratch;                                            // [gridDim.x][kM] second product, stays in L2
+    ResidueTables t;
+    int n_items;                                                // windows x 8
+    float scale;                                                // 1 / N
+};
+
+__device__ __forceinline__ int res_sw(int i) { return i ^ ((i >> 4) & 15); }
+// The file is compiled with --fmad=false (the bit-exact kernels need it); this transform is not bit-exact by
+// construction (its order is not the reference's radix-2 order), so its complex products use explicit FMAs:
+// four issue slots instead of six, and one rounding less per product.
+__device__ __forceinline__ float2 cmulr(float2 a, float2 b) {   // a * b
+    return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {   // a * conj(b)
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -(a.x * b.y)));
+}
+
+// 16-point DFT, natural order in and out: 4 x 4 with the W_16 factors as constants
+template <bool INV>
+__device__ __forceinline__ void dft16(float2 (&a)[16]) {
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+    float2 b[4][4];                                             // b[n2][k1]
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        float2 col[4] = {a[n2], a[4 + n2], a[8 + n2], a[12 + n2]};
+        dft4<INV>(col);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) b[n2][k1] = col[k1];
+    }
+    // b[n2][k1] *= W_16^{n2 k1} (conjugated for the inverse)
+    auto tw = [&](float2 v, float wr, float wi) {
+        const float wim = INV ? -wi : wi;
+        return make_float2(fmaf(v.x, wr, -(v.y * wim)), fmaf(v.x, wim, v.y * wr));
+    };
+    b[1][1] = tw(b[1][1], c1, -s1);  b[1][2] = tw(b[1][2], h, -h);    b[1][3] = tw(b[1][3], s1, -c1);
+    b[2][1] = tw(b[2][1], h, -h);    b[2][2] = mul_mj<INV>(b[2][2]);  b[2][3] = tw(b[2][3], -h, -h);
+    b[3][1] = tw(b[3][1], s1, -c1);  b[3][2] = tw(b[3][2], -h, -h);   b[3][3] = tw(b[3][3], -c1, s1);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        float2 row[4] = {b[0][k1], b[1][k1], b[2][k1], b[3][k1]};
+        dft4<INV>(row);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) a[k1 + 4 * k2] = row[k2];
+    }
+}
+
+// ---- the four passes of the M-point transform on the swizzled tile D ----
+// Forward (decimation in frequency): DFT first, twiddle after.  Inverse (decimation in time): conjugate twiddle
+// first, inverse DFT after, passes in the opposite order.
+template <bool INV>
+__device__ __forceinline__ void res_pass_a(float2* D, const ResidueTables& t, int tid) {
+#pragma unroll 1
+    for (int u = 0; u < 2; ++u) {
+        const int tp = tid + kResThreads * u;                   // t' in [0, 1024)
+        const int th = tp >> 5, tl = tp & 31;
+        float2 a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = D[res_sw(tp + 1024 * j)];
+        if (INV) {
+#pragma unroll
+            for (int k = 1; k < 16; ++k) a[k] = cmulc(a[k], cmulr(__ldg(t.wa_hi + k * 32 + th), __ldg(t.wa_lo + k * 32 + tl)));
+        }
+        dft16<INV>(a);
+        if (!INV) {
+#pragma unroll
+            for (int k = 1; k < 16; ++k) a[k] = cmulr(a[k], cmulr(__ldg(t.wa_hi + k * 32 + th), __ldg(t.wa_lo + k * 32 + tl)));
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) D[res_sw(tp + 1024 * k)] = a[k];
+    }
+}
+template <bool INV>
+__device__ __forceinline__ void res_pass_b(float2* D, const float2* wb, int tid) {
+#pragma unroll 1
+    for (int u = 0; u < 2; ++u) {
+        const int tau = tid + kResThreads * u;
+        const int tq = tau & 63, base = (tau >> 6) * 1024 + tq;
+        float2 a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = D[res_sw(base + 64 * j)];
+        if (INV) {
+#pragma unroll
+            for (int k = 1; k < 16; ++k) a[k] = cmulc(a[k], wb[k * 64 + tq]);
+        }
+        dft16<INV>(a);
+        if (!INV) {
+#pragma unroll
+            for (int k = 1; k < 16; ++k) a[k] = cmulr(a[k], wb[k * 64 + tq]);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) D[res_sw(base + 64 * k)] = a[k];
+    }
+}
+template <bool INV>
+__device__ __forceinline__ void res_pass_c1(float2* D, const float2* wc, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int t3 = lane & 7;
+#pragma unroll 1
+    for (int u = 0; u < 4; ++u) {
+        const int blk = ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (warp << 2) | (u << 6);
+        const int base = blk * 64 + t3;
+        float2 a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = D[res_sw(base + 8 * j)];
+        if (INV) {
+#pragma unroll
+            for (int k = 1; k < 8; ++k) a[k] = cmulc(a[k], wc[t3 * k]);
+        }
+        dft8<INV>(a);
+        if (!INV) {
+#pragma unroll
+            for (int k = 1; k < 8; ++k) a[k] = cmulr(a[k], wc[t3 * k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) D[res_sw(base + 8 * k)] = a[k];
+    }
+}
+template <bool INV>
+__device__ __forceinline__ void res_pass_c2(float2* D, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll 1
+    for (int u = 0; u < 4; ++u) {
+        // g0 = lane bit 3, g1..g3 = lane bits 0..2, g4 = lane bit 4, g5.. = warp, u
+        const int g = ((lane >> 3) & 1) | ((lane & 7) << 1) | (((lane >> 4) & 1) << 4) | (warp << 5) | (u << 9);
+        float2 a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = D[res_sw(8 * g + j)];
+        dft8<INV>(a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) D[res_sw(8 * g + k)] = a[k];
+    }
+}
+
+// MODE 0: correlate real windows against both templates.  MODE 1: conj spectrum of one complex input (template prep).
+template <int MODE>
+__global__ void __launch_bounds__(kResThreads, 1)
+chirp_residue_kernel(const ResidueArgs a) {
+    extern __shared__ __align__(16) float2 res_smem[];
+    float2* D = res_smem;                                       // [kM], swizzled
+    float2* wb = res_smem + kM;                                 // [1024]
+    float2* wc = wb + 1024;                                     // [64]
+    float2* wrh = wc + 64;                                      // [128]  W_N^{128 r mh}
+    float2* wrl = wrh + 128;                                    // [128]  W_N^{r ml}
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 1024; i += kResThreads) wb[i] = a.t.wb[i];
+    if (tid < 64) wc[tid] = a.t.wc[tid];
+    int loaded_r = -1;
+    float2* my_scratch = a.scratch + static_cast<size_t>(blockIdx.x) * kM;
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        const int w = item >> 3, r = item & 7;
+        __syncthreads();                                        // previous item done with D and the r tables
+        if (r != loaded_r) {
+            if (tid < 128) { wrh[tid] = a.t.wr_hi[r * 128 + tid]; wrl[tid] = a.t.wr_lo[r * 128 + tid]; }
+            loaded_r = r;
+        }
+        __syncthreads();
+        // ---- load: z_r[m] = W_N^{m r} sum_a x[M a + m] W_8^{a r} ----
+        if (MODE == 0) {
+            const float* x = a.samples + static_cast<long long>(w) * a.stride;
+#pragma unroll 1
+            for (int m0 = 4 * tid; m0 < kM; m0 += 4 * kResThreads) {
+                float xa[8][4];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int idx = kM * q + m0;
+                    if (idx + 3 < a.n_in && ((a.stride & 3) == 0) && ((reinterpret_cast<size_t>(a.samples) & 15) == 0)) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(x + idx));
+                        xa[q][0] = v.x; xa[q][1] = v.y; xa[q][2] = v.z; xa[q][3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) xa[q][e] = (idx + e < a.n_in) ? __ldg(x + idx + e) : 0.0f;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float2 v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = make_float2(xa[q][e], 0.0f);
+                    dft8<false>(v);
+                    float2 zr = v[0];
+#pragma unroll
+                    for (int q = 1; q < 8; ++q) if (r == q) zr = v[q];
+                    const int m = m0 + e;
+                    D[res_sw(m)] = cmulr(zr, cmulr(wrh[m >> 7], wrl[m & 127]));
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int m = tid; m < kM; m += kResThreads) {
+                float2 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = a.cplx_in[kM * q + m];
+                dft8<false>(v);
+                float2 zr = v[0];
+#pragma unroll
+                for (int q = 1; q < 8; ++q) if (r == q) zr = v[q];
+                D[res_sw(m)] = cmulr(zr, cmulr(wrh[m >> 7], wrl[m & 127]));
+            }
+        }
+        __syncthreads();
+        // ---- forward M-point transform ----
+        res_pass_a<false>(D, a.t, tid);      __syncthreads();
+        res_pass_b<false>(D, wb, tid);       __syncthreads();
+        res_pass_c1<false>(D, wc, tid);      __syncthreads();
+        res_pass_c2<false>(D, tid);          __syncthreads();
+        if (MODE == 1) {
+            float2* out = a.out_up + static_cast<size_t>(r) * kM;
+            for (int p = tid; p < kM; p += kResThreads) { const float2 z = D[res_sw(p)]; out[p] = make_float2(z.x, -z.y); }
+            continue;
+        }
+        // ---- both template products: the up product stays in shared memory, the down product waits in L2 ----
+        {
+            const float2* tu = a.tmpl_up + static_cast<size_t>(r) * kM;
+            const float2* td = a.tmpl_dn + static_cast<size_t>(r) * kM;
+#pragma unroll 4
+            for (int p = tid; p < kM; p += kResThreads) {
+                const float2 z = D[res_sw(p)];
+                my_scratch[p] = cmulr(z, __ldg(td + p));
+                D[res_sw(p)] = cmulr(z, __ldg(tu + p));
+            }
+        }
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+            __syncthreads();
+            if (which == 1) {
+#pragma unroll 4
+                for (int p = tid; p < kM; p += kResThreads) D[res_sw(p)] = my_scratch[p];
+                __syncthreads();
+            }
+            res_pass_c2<true>(D, tid);       __syncthreads();
+            res_pass_c1<true>(D, wc, tid);   __syncthreads();
+            res_pass_b<true>(D, wb, tid);    __syncthreads();
+            res_pass_a<true>(D, a.t, tid);   __syncthreads();
+            float2* out = (which ? a.out_dn : a.out_up) + (static_cast<size_t>(w) * 8 + r) * kM;
+#pragma unroll 4
+            for (int m = tid; m < kM; m += kResThreads) {
+                const float2 v = cmulc(D[res_sw(m)], cmulr(wrh[m >> 7], wrl[m & 127]));
+                out[m] = make_float2(v.x * a.scale, v.y * a.scale);
+            }
+        }
+    }
+}
+
+// R[M a + m] = sum_r v'_r[m] W_8^{-a r} for both templates, magnitude only (what the peak search reads)
+struct CombineArgs {
+    const float2* v_up; const float2* v_dn;                     // [n_win][8][kM]
+    float* mag_up; float* mag_dn; long long mag_stride;         // [n_win] rows of |R| per lag
+    int n_lags;                                                 // lags the peak search can ask for (< kN)
+};
+__global__ void __launch_bounds__(256)
+chirp_combine_kernel(const CombineArgs a) {
+    const int m = blockIdx.x * 256 + threadIdx.x;               // < kM
+    const size_t w = blockIdx.y;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+        const float2* v = (which ? a.v_dn : a.v_up) + w * 8 * kM + m;
+        float* mag = (which ? a.mag_dn : a.mag_up) + w * a.mag_stride;
+        float2 x[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) x[r] = __ldcs(v + static_cast<size_t>(r) * kM);
+        dft8<true>(x);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int lag = kM * q + m;
+            if (lag < a.n_lags) mag[lag] = cabs_d(x[q]);
+        }
+    }
+}
+
+__global__ void residue_tables_kernel(float2* wa_hi, float2* wa_lo, float2* wb, float2* wc, float2* wr_hi, float2* wr_lo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    auto w = [](double num, double den) { double s, c; sincospi(-2.0 * num / den, &s, &c); return make_float2(static_cast<float>(c), static_cast<float>(s)); };
+    if (i < 512) {                                              // [k][32]
+        const int k = i >> 5, t = i & 31;
+        wa_hi[i] = w(static_cast<double>(t) * k, 512.0);
+        wa_lo[i] = w(static_cast<double>(t) * k, static_cast<double>(kM));
+    }
+    if (i < 1024) { const int k = i >> 6, t = i & 63; wb[i] = w(static_cast<double>(t) * k, 1024.0); }
+    if (i < 64) wc[i] = w(static_cast<double>(i), 64.0);
+    if (i < 1024) {
+        const int r = i >> 7, j = i & 127;
+        wr_hi[i] = w(128.0 * r * j, static_cast<double>(kN));
+        wr_lo[i] = w(static_cast<double>(r) * j, static_cast<double>(kN));
     }
 }
 
@@ -849,7 +1178,17 @@ void chirp_tables_free(ChirpTablesDev* t) {
     if (t->tmpl_up) cudaFree(t->tmpl_up);
     if (t->tmpl_dn) cudaFree(t->tmpl_dn);
     if (t->tmpl_dn_time) cudaFree(t->tmpl_dn_time);
+    if (t->res_tables) cudaFree(t->res_tables);
+    if (t->tmpl_up_res) cudaFree(t->tmpl_up_res);
+    if (t->tmpl_dn_res) cudaFree(t->tmpl_dn_res);
+    if (t->res_scratch) cudaFree(t->res_scratch);
     delete t;
+}
+
+static size_t residue_smem_bytes() { return (static_cast<size_t>(kM) + 1024 + 64 + 256) * sizeof(float2); }
+static ResidueTables residue_tables(const ChirpTablesDev& t) {
+    const float2* tb = t.res_tables;
+    return ResidueTables{tb, tb + 512, tb + 1024, tb + 2048, tb + 2112, tb + 3136};
 }
 
 static int chirp_tables_dev(ria_ctx* ctx, const ria_chirp_config& cfg, ChirpTablesDev** out) {
@@ -887,6 +1226,31 @@ static int chirp_tables_dev(ria_ctx* ctx, const ria_chirp_config& cfg, ChirpTabl
     RIA_CUDA(ctx, cudaMemcpyAsync(t->tmpl_dn, dn.data(), sizeof(float2) * kN, cudaMemcpyHostToDevice, s));
     RIA_CUDA(ctx, cudaMemcpyAsync(t->tmpl_dn_time, dn.data(), sizeof(float2) * chirp_len, cudaMemcpyHostToDevice, s));
     RIA_CUDA(ctx, cudaStreamSynchronize(s));
+    // residue path: tables, then the conjugated template spectra through the same kernel that transforms the windows
+    {
+        constexpr size_t kTab = 512 + 512 + 1024 + 64 + 1024 + 1024;
+        RIA_CUDA(ctx, cudaMalloc(&t->res_tables, kTab * sizeof(float2)));
+        RIA_CUDA(ctx, cudaMalloc(&t->tmpl_up_res, sizeof(float2) * kN));
+        RIA_CUDA(ctx, cudaMalloc(&t->tmpl_dn_res, sizeof(float2) * kN));
+        t->res_grid = ctx->sm_count > 0 ? ctx->sm_count : 148;
+        RIA_CUDA(ctx, cudaMalloc(&t->res_scratch, sizeof(float2) * kM * static_cast<size_t>(t->res_grid)));
+        float2* tb = t->res_tables;
+        residue_tables_kernel<<<4, 256, 0, s>>>(tb, tb + 512, tb + 1024, tb + 2048, tb + 2112, tb + 3136);
+        const size_t smem = residue_smem_bytes();
+        RIA_CUDA(ctx, cudaFuncSetAttribute(chirp_residue_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        RIA_CUDA(ctx, cudaFuncSetAttribute(chirp_residue_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        for (int which = 0; which < 2; ++which) {
+            ResidueArgs ra{};
+            ra.cplx_in = which ? t->tmpl_dn : t->tmpl_up;              // still the time-domain (cos, sin) templates here
+            ra.out_up = which ? t->tmpl_dn_res : t->tmpl_up_res;
+            ra.scratch = t->res_scratch;
+            ra.t = residue_tables(*t);
+            ra.n_items = 8;
+            chirp_residue_kernel<1><<<8, kResThreads, smem, s>>>(ra);
+        }
+        RIA_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 3;
+    }
     // template spectra, conjugated (:586-611), kept in the permuted layout of the stage transform
     fft_forward(t->tmpl_up, 1, *t, s);
     fft_forward(t->tmpl_dn, 1, *t, s);
@@ -958,7 +1322,22 @@ extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_con
         float* mag_up = reinterpret_cast<float*>(d_sig);
         float* mag_dn = mag_up + kN;
         const long long mag_stride = 2LL * kN;
-        if (unfused) {
+        static const bool staged_env = [] { const char* e = std::getenv("RIA_CHIRP_STAGED"); return e && e[0] == '1'; }();
+        if (!staged_env && !unfused && !use_slab) {
+            // default: residue-decomposed transforms out of shared memory, then the radix-8 combine + magnitudes
+            ResidueArgs ra{};
+            ra.samples = in; ra.stride = frame_stride; ra.n_in = n_in;
+            ra.tmpl_up = t->tmpl_up_res; ra.tmpl_dn = t->tmpl_dn_res;
+            ra.out_up = d_pu; ra.out_dn = d_pd; ra.scratch = t->res_scratch;
+            ra.t = residue_tables(*t);
+            ra.n_items = batch * 8;
+            ra.scale = 1.0f / kN;
+            const int grid = ra.n_items < t->res_grid ? ra.n_items : t->res_grid;
+            chirp_residue_kernel<0><<<grid, kResThreads, residue_smem_bytes(), s>>>(ra);
+            CombineArgs ca{};
+            ca.v_up = d_pu; ca.v_dn = d_pd; ca.mag_up = mag_up; ca.mag_dn = mag_dn; ca.mag_stride = mag_stride; ca.n_lags = n_in;
+            chirp_combine_kernel<<<dim3(kM / 256, batch), 256, 0, s>>>(ca);
+        } else if (unfused) {
             fft_forward_real_to_products(in, frame_stride, n_in, d_sig, d_pu, d_pd, batch, *t, s);
             fft_inverse(d_pu, batch, *t, s, mag_up, mag_stride);
             fft_inverse(d_pd, batch, *t, s, mag_dn, mag_stride);
@@ -973,7 +1352,7 @@ extern "C" int ria_chirp_detect_dual_batch_dev(ria_ctx* ctx, const ria_chirp_con
         a.sample_rate = cfg->sample_rate; a.f_start = cfg->f_start; a.f_end = cfg->f_end; a.duration_ms = cfg->duration_ms;
         a.out = out_dev + off;
         chirp_peak_kernel<<<batch, kPeakThreads, 0, s>>>(a);
-        ctx->launches += unfused ? 10 : (use_slab ? 5 : 8);
+        ctx->launches += (!staged_env && !unfused && !use_slab) ? 3 : unfused ? 10 : (use_slab ? 5 : 8);
     }
     time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());

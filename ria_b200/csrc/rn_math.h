@@ -197,7 +197,7 @@ RN_HD double rn_sc_reduce(double x, int* np) {
 // the rest is the reduced angle as a signed 62-bit fixed-point fraction of pi/2.
 RN_HD double rn_sc_reduce_large(uint32_t xi, int* np) {
     // 2/pi = 0.A2F9836E 4E441529 FC2757D1 F534DDC0 DB629599 3C439041 ... (hex), 32-bit windows 8 bits apart
-    const uint32_t inv_pio4[24] = {
+    static const uint32_t inv_pio4[24] = {
         0x000000a2u, 0x0000a2f9u, 0x00a2f983u, 0xa2f9836eu, 0xf9836e4eu, 0x836e4e44u, 0x6e4e4415u, 0x4e441529u,
         0x441529fcu, 0x1529fc27u, 0x29fc2757u, 0xfc2757d1u, 0x2757d1f5u, 0x57d1f534u, 0xd1f534ddu, 0xf534ddc0u,
         0x34ddc0dbu, 0xddc0db62u, 0xc0db6295u, 0xdb629599u, 0x6295993cu, 0x95993c43u, 0x993c4390u, 0x3c439041u};
@@ -257,11 +257,15 @@ RN_HD void glibc_sincosf_uniform(float y, float* sinp, float* cosp) {
     if (!(rn_abstop12(y) < rn_abstop12(120.0f))) { glibc_sincosf(y, sinp, cosp); return; }
     int n;
     const double x = rn_sc_reduce(static_cast<double>(y), &n);
-    const double s = ((n + 1) & 2) ? -1.0 : 1.0;                       // sign[n & 3] = {1, -1, -1, 1}
-    const double flip = (n & 2) ? -1.0 : 1.0;
     const double x2 = x * x;
-    const float ps = static_cast<float>(rn_sc_sin(x * s, x2));
-    const float pc = static_cast<float>(rn_sc_cos(x2, flip));
+    // glibc evaluates sin_poly(x * s) with s = sign[n & 3] = {1, -1, -1, 1} and the cosine polynomial with all
+    // coefficients negated when n & 2.  Both polynomials are built from products and fused multiply-adds only, and
+    // round-to-nearest is symmetric, so negating the argument of the odd polynomial / every coefficient of the even
+    // one negates the result bit for bit: evaluate once with positive signs and flip the float's sign bit instead.
+    const float ps0 = static_cast<float>(rn_sc_sin(x, x2));
+    const float pc0 = static_cast<float>(rn_sc_cos(x2, 1.0));
+    const float ps = rn_ffrom(rn_fbits(ps0) ^ (static_cast<uint32_t>((n + 1) & 2) << 30));
+    const float pc = rn_ffrom(rn_fbits(pc0) ^ (static_cast<uint32_t>(n & 2) << 30));
     *sinp = (n & 1) ? pc : ps;
     *cosp = (n & 1) ? ps : pc;
 }
