@@ -515,15 +515,18 @@ __device__ __forceinline__ void dft16(float2 (&a)[16]) {
 // ---- the four passes of the M-point transform on the swizzled tile D ----
 // Forward (decimation in frequency): DFT first, twiddle after.  Inverse (decimation in time): conjugate twiddle
 // first, inverse DFT after, passes in the opposite order.
+// The swizzle only touches the low four address bits and reads bits 4..7, so inside a pass most of it is a constant of
+// the thread (or of the unrolled loop index): each pass computes its swizzled base once and adds immediates.
 template <bool INV>
 __device__ __forceinline__ void res_pass_a(float2* D, const ResidueTables& t, int tid) {
 #pragma unroll 1
     for (int u = 0; u < 2; ++u) {
         const int tp = tid + kResThreads * u;                   // t' in [0, 1024)
         const int th = tp >> 5, tl = tp & 31;
+        float2* p = D + res_sw(tp);                             // + 1024 j leaves bits 0..7 alone
         float2 a[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) a[j] = D[res_sw(tp + 1024 * j)];
+        for (int j = 0; j < 16; ++j) a[j] = p[1024 * j];
         if (INV) {
 #pragma unroll
             for (int k = 1; k < 16; ++k) a[k] = cmulc(a[k], cmulr(__ldg(t.wa_hi + k * 32 + th), __ldg(t.wa_lo + k * 32 + tl)));
@@ -534,7 +537,7 @@ __device__ __forceinline__ void res_pass_a(float2* D, const ResidueTables& t, in
             for (int k = 1; k < 16; ++k) a[k] = cmulr(a[k], cmulr(__ldg(t.wa_hi + k * 32 + th), __ldg(t.wa_lo + k * 32 + tl)));
         }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) D[res_sw(tp + 1024 * k)] = a[k];
+        for (int k = 0; k < 16; ++k) p[1024 * k] = a[k];
     }
 }
 template <bool INV>
@@ -543,9 +546,13 @@ __device__ __forceinline__ void res_pass_b(float2* D, const float2* wb, int tid)
     for (int u = 0; u < 2; ++u) {
         const int tau = tid + kResThreads * u;
         const int tq = tau & 63, base = (tau >> 6) * 1024 + tq;
+        // i = base + 64 j: bits 4, 5 come from tq, bits 6, 7 from j -> low nibble = (tq & 15) ^ (tq >> 4) ^ ((j & 3) << 2)
+        const int lo = (tq & 15) ^ (tq >> 4);
+        float2* hi = D + (base & ~15);
+        const int l0 = lo, l1 = lo ^ 4, l2 = lo ^ 8, l3 = lo ^ 12;
         float2 a[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) a[j] = D[res_sw(base + 64 * j)];
+        for (int j = 0; j < 16; ++j) a[j] = hi[64 * j + ((j & 3) == 0 ? l0 : (j & 3) == 1 ? l1 : (j & 3) == 2 ? l2 : l3)];
         if (INV) {
 #pragma unroll
             for (int k = 1; k < 16; ++k) a[k] = cmulc(a[k], wb[k * 64 + tq]);
@@ -556,7 +563,7 @@ __device__ __forceinline__ void res_pass_b(float2* D, const float2* wb, int tid)
             for (int k = 1; k < 16; ++k) a[k] = cmulr(a[k], wb[k * 64 + tq]);
         }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) D[res_sw(base + 64 * k)] = a[k];
+        for (int k = 0; k < 16; ++k) hi[64 * k + ((k & 3) == 0 ? l0 : (k & 3) == 1 ? l1 : (k & 3) == 2 ? l2 : l3)] = a[k];
     }
 }
 template <bool INV>
@@ -566,10 +573,12 @@ __device__ __forceinline__ void res_pass_c1(float2* D, const float2* wc, int tid
 #pragma unroll 1
     for (int u = 0; u < 4; ++u) {
         const int blk = ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (warp << 2) | (u << 6);
-        const int base = blk * 64 + t3;
+        // i = 64 blk + 8 j + t3: low nibble = t3 | (j & 1) << 3, bits 4..7 = (j >> 1) | (blk & 3) << 2
+        const int v = t3 ^ ((blk & 3) << 2);                    // thread part of the swizzled low nibble
+        float2* hi = D + blk * 64;
         float2 a[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = D[res_sw(base + 8 * j)];
+        for (int j = 0; j < 8; ++j) a[j] = hi[(8 * j & ~15) + (v ^ (((j & 1) << 3) ^ (j >> 1)))];
         if (INV) {
 #pragma unroll
             for (int k = 1; k < 8; ++k) a[k] = cmulc(a[k], wc[t3 * k]);
@@ -580,7 +589,7 @@ __device__ __forceinline__ void res_pass_c1(float2* D, const float2* wc, int tid
             for (int k = 1; k < 8; ++k) a[k] = cmulr(a[k], wc[t3 * k]);
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) D[res_sw(base + 8 * k)] = a[k];
+        for (int k = 0; k < 8; ++k) hi[(8 * k & ~15) + (v ^ (((k & 1) << 3) ^ (k >> 1)))] = a[k];
     }
 }
 template <bool INV>
@@ -590,12 +599,15 @@ __device__ __forceinline__ void res_pass_c2(float2* D, int tid) {
     for (int u = 0; u < 4; ++u) {
         // g0 = lane bit 3, g1..g3 = lane bits 0..2, g4 = lane bit 4, g5.. = warp, u
         const int g = ((lane >> 3) & 1) | ((lane & 7) << 1) | (((lane >> 4) & 1) << 4) | (warp << 5) | (u << 9);
+        // i = 8 g + j: low nibble = j | (g & 1) << 3, bits 4..7 = (g >> 1) & 15 -> thread part v, loop part j
+        const int v = ((g & 1) << 3) ^ ((g >> 1) & 15);
+        float2* hi = D + ((8 * g) & ~15);
         float2 a[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = D[res_sw(8 * g + j)];
+        for (int j = 0; j < 8; ++j) a[j] = hi[v ^ j];
         dft8<INV>(a);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) D[res_sw(8 * g + k)] = a[k];
+        for (int k = 0; k < 8; ++k) hi[v ^ k] = a[k];
     }
 }
 
@@ -624,33 +636,24 @@ chirp_residue_kernel(const ResidueArgs a) {
         __syncthreads();
         // ---- load: z_r[m] = W_N^{m r} sum_a x[M a + m] W_8^{a r} ----
         if (MODE == 0) {
+            // Real input: with W_8^{(a+4) r} = (-1)^r W_8^{a r} the eight-term sum folds to four real pairs,
+            //   z = sum_{a<4} (x_a + sg x_{a+4}) (c_a - j s_a),  c_a + j s_a = e^{j 2 pi a r / 8}:  11 FMAs per point.
+            // Consecutive lanes take consecutive m: coalesced 128-byte rows, conflict-free table reads and stores.
             const float* x = a.samples + static_cast<long long>(w) * a.stride;
-#pragma unroll 1
-            for (int m0 = 4 * tid; m0 < kM; m0 += 4 * kResThreads) {
-                float xa[8][4];
+            const float h = 0.70710678118654752440f;
+            const float sg = (r & 1) ? -1.0f : 1.0f;
+            // (c_a, s_a) for a = 1, 2, 3 (a = 0 is (1, 0)): e^{j pi a r / 4}
+            const float ct[8] = {1.f, h, 0.f, -h, -1.f, -h, 0.f, h}, st[8] = {0.f, h, 1.f, h, 0.f, -h, -1.f, -h};
+            const float c1 = ct[r & 7], s1 = st[r & 7], c2 = ct[(2 * r) & 7], s2 = st[(2 * r) & 7], c3 = ct[(3 * r) & 7], s3 = st[(3 * r) & 7];
+#pragma unroll 2
+            for (int m = tid; m < kM; m += kResThreads) {
+                float xa[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int idx = kM * q + m0;
-                    if (idx + 3 < a.n_in && ((a.stride & 3) == 0) && ((reinterpret_cast<size_t>(a.samples) & 15) == 0)) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(x + idx));
-                        xa[q][0] = v.x; xa[q][1] = v.y; xa[q][2] = v.z; xa[q][3] = v.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) xa[q][e] = (idx + e < a.n_in) ? __ldg(x + idx + e) : 0.0f;
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float2 v[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = make_float2(xa[q][e], 0.0f);
-                    dft8<false>(v);
-                    float2 zr = v[0];
-#pragma unroll
-                    for (int q = 1; q < 8; ++q) if (r == q) zr = v[q];
-                    const int m = m0 + e;
-                    D[res_sw(m)] = cmulr(zr, cmulr(wrh[m >> 7], wrl[m & 127]));
-                }
+                for (int q = 0; q < 8; ++q) { const int idx = kM * q + m; xa[q] = (idx < a.n_in) ? __ldg(x + idx) : 0.0f; }
+                const float u0 = fmaf(sg, xa[4], xa[0]), u1 = fmaf(sg, xa[5], xa[1]), u2 = fmaf(sg, xa[6], xa[2]), u3 = fmaf(sg, xa[7], xa[3]);
+                const float re = fmaf(u3, c3, fmaf(u2, c2, fmaf(u1, c1, u0)));
+                const float im = -fmaf(u3, s3, fmaf(u2, s2, u1 * s1));
+                D[res_sw(m)] = cmulr(make_float2(re, im), cmulr(wrh[m >> 7], wrl[m & 127]));
             }
         } else {
 #pragma unroll 1

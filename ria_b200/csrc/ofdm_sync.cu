@@ -25,8 +25,8 @@ namespace {
 
 constexpr int kTaps = 65;
 constexpr int kDelay = 32;
-constexpr int kThreads = 256;
-constexpr int kMaxCand = 2048;
+constexpr int kThreads = 512;          // one CTA per SM (the tile is ~100 KB): 16 warps to hide the shared-memory latency
+constexpr int kMaxCand = 1280;         // >= the widest coarse grid: 8 symbols / 8, symbols <= 1160 samples
 
 __device__ __forceinline__ float cabs_d(float2 a) {
     const double x = a.x, y = a.y;
@@ -37,17 +37,41 @@ struct SyncArgs {
     const float* samples; long long frame_stride; int window;
     const float* known_cfo; float threshold; int sym; float sample_rate;
     const float* taps_g;
-    float2* analytic; long long an_stride;      // scratch [n][window]
-    float* cand; long long cand_stride;         // scratch [n][4 * kMaxCand]: corr, P.re, P.im
+    int an_cap;                                 // analytic samples the shared-memory tile holds
     ria_sync_result* out;
 };
 
-// P = sum conj(s1) s2, energies, in order (:283-295)
+// The analytic signal of the span the search touches lives in shared memory, sample i of the span at
+// an_pad(i) = i + (i >> 3): candidates are 8 samples apart, so the threads of a half-warp (one candidate each) read
+// float2 words 9 apart -- sixteen different bank pairs.
+__device__ __forceinline__ int an_pad(int i) { return i + (i >> 3); }
+
+// Blackwell packed fp32; products only ever feed scalar adds (ptxas would contract a packed multiply into a packed add)
+__device__ __forceinline__ float2 ds_mul2s(float s, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%2}; mov.b64 rb, {%3,%4}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(s), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 ds_mul2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 ds_add2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+
+// P = sum conj(s1) s2, energies, in order (:283-295); `offset` is relative to the tile
 __device__ __forceinline__ void lag_corr(const float2* an, int offset, int sym, float* corr, float2* P_out) {
     float2 P = make_float2(0.f, 0.f);
     float e1 = 0.f, e2 = 0.f;
     for (int n = 0; n < sym; ++n) {
-        const float2 s1 = an[offset + n], s2 = an[offset + n + sym];
+        const float2 s1 = an[an_pad(offset + n)], s2 = an[an_pad(offset + n + sym)];
         // conj(s1) * s2
         const float re = __fsub_rn(__fmul_rn(s1.x, s2.x), __fmul_rn(-s1.y, s2.y));
         const float im = __fadd_rn(__fmul_rn(s1.x, s2.y), __fmul_rn(-s1.y, s2.x));
@@ -60,17 +84,46 @@ __device__ __forceinline__ void lag_corr(const float2* an, int offset, int sym, 
     *P_out = P;
 }
 
+// The coarse grid: candidate c sits at tile offset 8 c.  Its second energy sum, over [8 c + sym, 8 c + 2 sym), is the
+// FIRST energy sum of the candidate sym / 8 places further on -- the same terms in the same order, hence the same
+// float -- so each thread accumulates P and one energy, and extra threads supply the energies past the last candidate.
+// Same products and sums as lag_corr: conj(s1) s2 = (s1x s2x + s1y s2y, s1x s2y - s1y s2x), a - (-t) = a + t exactly.
+__device__ __forceinline__ void coarse_corr(const float2* an, int offset, int sym, bool want_p, float2* P_out, float* e_out) {
+    float2 P = make_float2(0.f, 0.f);
+    float e1 = 0.f;
+    if (want_p) {
+#pragma unroll 2
+        for (int n = 0; n < sym; ++n) {
+            const float2 s1 = an[an_pad(offset + n)], s2 = an[an_pad(offset + n + sym)];
+            const float2 p1 = ds_mul2s(s1.x, s2);                              // (s1x s2x, s1x s2y)
+            const float2 p2 = ds_mul2s(s1.y, make_float2(s2.y, s2.x));         // (s1y s2y, s1y s2x)
+            P = ds_add2(P, make_float2(__fadd_rn(p1.x, p2.x), __fsub_rn(p1.y, p2.y)));
+            const float2 sq = ds_mul2(s1, s1);
+            e1 = __fadd_rn(e1, __fadd_rn(sq.x, sq.y));
+        }
+    } else {
+#pragma unroll 4
+        for (int n = 0; n < sym; ++n) {
+            const float2 s1 = an[an_pad(offset + n)];
+            const float2 sq = ds_mul2(s1, s1);
+            e1 = __fadd_rn(e1, __fadd_rn(sq.x, sq.y));
+        }
+    }
+    *P_out = P; *e_out = e1;
+}
+
 __global__ void __launch_bounds__(kThreads)
 ofdm_data_sync_kernel(const SyncArgs a) {
+    extern __shared__ __align__(16) float2 an_tile[];          // analytic signal of the searched span, padded (an_pad)
     __shared__ float taps[kTaps + 3];
     __shared__ int s_i[kThreads];
     __shared__ float s_f[4];
     __shared__ int s_n[4];
+    __shared__ float cand[3 * kMaxCand];                         // corr | P.re | P.im per candidate
+    __shared__ float e_sum[kMaxCand + 520];                      // first energy sum per grid position
     const long long f = blockIdx.x;
     const int tid = threadIdx.x;
     const float* x = a.samples + f * a.frame_stride;
-    float2* an = a.analytic + f * a.an_stride;
-    float* cand = a.cand + f * a.cand_stride;
     const int N = a.window, sym = a.sym;
     const float known = a.known_cfo ? a.known_cfo[f] : 0.0f;
 
@@ -113,25 +166,43 @@ ofdm_data_sync_kernel(const SyncArgs a) {
     const int search_end = min(signal_start + actual, N - sym * 2);
 
     // ---- analytic signal over the span the search touches (:266-270, filters.cpp:293-317) ----
-    const int an_lo = max(0, signal_start - 4), an_hi = min(N, search_end + 2 * sym + 8);
-    for (int i = an_lo + tid; i < an_hi; i += kThreads) {
+    // The tile starts at the first candidate (the refinement never goes below signal_start, :327).
+    const int an_lo = signal_start, an_hi = min(N, search_end + 2 * sym + 8);
+    float2* an = an_tile;
+    for (int i = an_lo + tid; i < an_hi && i - an_lo < a.an_cap; i += kThreads) {
         float q = 0.0f;
         for (int k = 1; k < kTaps; k += 2) {                       // even taps are exactly zero
             const int j = i - k;
             const float v = (j >= 0) ? x[j] : 0.0f;
             q = __fadd_rn(q, __fmul_rn(taps[k], v));
         }
-        an[i] = make_float2(i >= kDelay ? x[i - kDelay] : 0.0f, q);
+        an[an_pad(i - an_lo)] = make_float2(i >= kDelay ? x[i - kDelay] : 0.0f, q);
     }
     __syncthreads();
 
     // ---- coarse candidates, all in parallel (:283-312) ----
     int n_cand = (search_end > signal_start) ? (search_end - signal_start + 7) / 8 : 0;
     if (n_cand > kMaxCand) n_cand = kMaxCand;
-    for (int c = tid; c < n_cand; c += kThreads) {
-        float corr; float2 P;
-        lag_corr(an, signal_start + 8 * c, sym, &corr, &P);
-        cand[c] = corr; cand[kMaxCand + c] = P.x; cand[2 * kMaxCand + c] = P.y;
+    const bool share = (sym % 8) == 0 && sym / 8 <= 520;            // second energy = first energy sym / 8 places on
+    if (share) {
+        const int hop = sym / 8;
+        for (int c = tid; c < n_cand + hop; c += kThreads) {
+            float2 P; float e;
+            coarse_corr(an, 8 * c, sym, c < n_cand, &P, &e);
+            e_sum[c] = e;
+            if (c < n_cand) { cand[kMaxCand + c] = P.x; cand[2 * kMaxCand + c] = P.y; }
+        }
+        __syncthreads();
+        for (int c = tid; c < n_cand; c += kThreads) {
+            const float denom = __fadd_rn(sqrtf(__fmul_rn(e_sum[c], e_sum[c + hop])), 1e-10f);
+            cand[c] = __fdiv_rn(cabs_d(make_float2(cand[kMaxCand + c], cand[2 * kMaxCand + c])), denom);
+        }
+    } else {
+        for (int c = tid; c < n_cand; c += kThreads) {
+            float corr; float2 P;
+            lag_corr(an, 8 * c, sym, &corr, &P);
+            cand[c] = corr; cand[kMaxCand + c] = P.x; cand[2 * kMaxCand + c] = P.y;
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -151,7 +222,7 @@ ofdm_data_sync_kernel(const SyncArgs a) {
         const int r0 = max(signal_start, best_offset - 4), r1 = min(search_end, best_offset + 5);
         if (tid < r1 - r0 && r0 + tid != best_offset) {
             float corr; float2 P;
-            lag_corr(an, r0 + tid, sym, &corr, &P);
+            lag_corr(an, r0 + tid - an_lo, sym, &corr, &P);
             cand[tid] = corr; cand[kMaxCand + tid] = P.x; cand[2 * kMaxCand + tid] = P.y;
         }
         __syncthreads();
@@ -212,20 +283,20 @@ extern "C" int ria_ofdm_data_sync_batch_dev(ria_ctx* ctx, const ria_modem_config
         RIA_CUDA(ctx, cudaMalloc(&ctx->hilbert65, sizeof taps));
         RIA_CUDA(ctx, cudaMemcpy(ctx->hilbert65, taps, sizeof taps, cudaMemcpyHostToDevice));
     }
-    const size_t an_stride = (static_cast<size_t>(window) + 1) & ~size_t(1);
-    const size_t s_an = (static_cast<size_t>(n_frames) * an_stride * sizeof(float2) + 255) & ~size_t(255);
-    const size_t cand_stride = 3 * kMaxCand;
-    int rc = ensure_scratch(ctx, s_an + static_cast<size_t>(n_frames) * cand_stride * sizeof(float) + 256);
-    if (rc != RIA_OK) return rc;
+    // shared-memory tile: the widest search is 8 symbols (buffer starts inside a burst, :273-276) plus the two symbols
+    // the last candidate correlates over, padded one word per eight
+    const int an_cap = 10 * sym + 16;
+    const size_t smem = static_cast<size_t>(an_cap + an_cap / 8 + 8) * sizeof(float2);
+    if (smem + 48 * 1024 > ctx->smem_optin) return set_error(ctx, RIA_E_UNSUPPORTED, "data sync: symbol too long for the shared-memory tile");
+    RIA_CUDA(ctx, cudaFuncSetAttribute(ofdm_data_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     SyncArgs a{};
     a.samples = samples_dev; a.frame_stride = frame_stride; a.window = window;
     a.known_cfo = known_cfo_dev; a.threshold = threshold; a.sym = sym; a.sample_rate = static_cast<float>(cfg->sample_rate);
     a.taps_g = ctx->hilbert65;
-    a.analytic = static_cast<float2*>(ctx->scratch); a.an_stride = static_cast<long long>(an_stride);
-    a.cand = reinterpret_cast<float*>(static_cast<unsigned char*>(ctx->scratch) + s_an); a.cand_stride = static_cast<long long>(cand_stride);
+    a.an_cap = an_cap;
     a.out = out_dev;
     time_begin(ctx, KK_OFDM_SYNC);
-    ofdm_data_sync_kernel<<<static_cast<unsigned>(n_frames), kThreads, 0, ctx->stream>>>(a);
+    ofdm_data_sync_kernel<<<static_cast<unsigned>(n_frames), kThreads, smem, ctx->stream>>>(a);
     time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
