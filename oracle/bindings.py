@@ -65,6 +65,12 @@ class ModemConfig(C.Structure):
         return self.num_carriers - self.pilots()
 
 
+class StreamDecodeResult(C.Structure):
+    """gui::DecodeResult fields (src/gui/modem/streaming_decoder.hpp:70-79)"""
+    _fields_ = [("success", C.c_int32), ("frame_type", C.c_int32), ("codewords_ok", C.c_int32),
+                ("codewords_failed", C.c_int32), ("is_ping", C.c_int32), ("n_bytes", C.c_int32)]
+
+
 class McdpskConfig(C.Structure):
     """Same layout as ria_mcdpsk_config (include/ria_b200.h)."""
     _fields_ = [("sample_rate", C.c_float), ("num_carriers", C.c_uint32), ("freq_low", C.c_float),
@@ -219,6 +225,11 @@ class Ref:
         L.ref_ladder_perturb.argtypes = [_f32p, C.c_int, C.c_uint, C.c_float, C.c_int, _f32p]
         L.ref_parse_header.argtypes = [_u8p, C.c_int, C.POINTER(FrameStatus)]
         L.ref_frame_status_reassembled.argtypes = [_u8p, _u8p, C.c_int, C.POINTER(FrameStatus)]
+        L.ref_stream_decoder_new.restype = C.c_void_p
+        L.ref_stream_decoder_free.argtypes = [C.c_void_p]
+        L.ref_stream_decode_mcdpsk_frame.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.POINTER(StreamDecodeResult), _u8p, C.c_int]
+        L.ref_encode_frame_with_ldpc.argtypes = [_u8p, C.c_int, C.c_int, _u8p, C.c_int]
+        L.ref_encode_frame_with_ldpc.restype = C.c_int
         L.ref_crc16.argtypes = [_u8p, C.c_int]
         L.ref_crc16.restype = C.c_uint16
         L.ref_make_data_frame.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _u8p, C.c_int, _u8p, C.c_int]
@@ -451,6 +462,30 @@ class Ref:
         st = FrameStatus()
         self.lib.ref_frame_status_reassembled(data, ok, int(bpc), C.byref(st))
         return st
+
+    # ---- StreamingDecoder frame-level decode ----
+    def stream_decoder(self):
+        """a reference StreamingDecoder object (owns a HARQ chase cache); free with stream_decoder_free"""
+        return self.lib.ref_stream_decoder_new()
+
+    def stream_decoder_free(self, h):
+        self.lib.ref_stream_decoder_free(h)
+
+    def stream_decode_mcdpsk_frame(self, h, soft, rate: int):
+        """StreamingDecoder::decodeMCDPSKFrame -> (StreamDecodeResult, frame bytes)"""
+        soft = np.ascontiguousarray(soft, dtype=np.float32)
+        res = StreamDecodeResult()
+        buf = np.zeros(1024, np.uint8)
+        self.lib.ref_stream_decode_mcdpsk_frame(h, soft, len(soft), int(rate), C.byref(res), buf, len(buf))
+        return res, bytes(buf[: res.n_bytes])
+
+    def encode_frame_with_ldpc(self, frame, rate: int) -> np.ndarray:
+        """v2::encodeFrameWithLDPC -> coded bytes [n_cw, 81]"""
+        frame = np.ascontiguousarray(np.frombuffer(bytes(frame), dtype=np.uint8))
+        out = np.zeros((32, 81), np.uint8)
+        n = self.lib.ref_encode_frame_with_ldpc(frame, len(frame), int(rate), out, 32)
+        assert n > 0, n
+        return out[:n].copy()
 
     def crc16(self, data) -> int:
         data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))

@@ -25,6 +25,7 @@
 #include "sim/hf_channel.hpp"
 #include "waveform/ofdm_chirp_waveform.hpp"
 #include "protocol/waveform_selection.hpp"
+#include "gui/modem/streaming_decoder.hpp"   // frame-level decode semantics (private members reached with -fno-access-control)
 
 #include "ria_b200.h"                     // POD config / status structs shared with the product ABI
 
@@ -343,6 +344,48 @@ int ref_make_data_frame(const char* src, const char* dst, int seq, const uint8_t
     return n;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// StreamingDecoder frame-level decode (src/gui/modem/streaming_decoder.cpp)
+// ---------------------------------------------------------------------------------------------
+// One StreamingDecoder object = one receiver: its HARQ chase cache persists across calls, so feeding it the
+// receptions of a retransmitted frame one after the other exercises the combining path (:2762-2789).
+void* ref_stream_decoder_new(void) { return new gui::StreamingDecoder(); }
+void ref_stream_decoder_free(void* h) { delete static_cast<gui::StreamingDecoder*>(h); }
+
+struct ref_decode_result {
+    int32_t success, frame_type, codewords_ok, codewords_failed, is_ping, n_bytes;
+};
+
+// StreamingDecoder::decodeMCDPSKFrame(soft_bits, rate, bytes_per_cw, snr, cfo) (:2580-2822)
+void ref_stream_decode_mcdpsk_frame(void* h, const float* soft, int n_soft, int rate, ref_decode_result* out,
+                                    uint8_t* bytes, int cap) {
+    auto* d = static_cast<gui::StreamingDecoder*>(h);
+    std::vector<float> v(soft, soft + n_soft);
+    CodeRate r = static_cast<CodeRate>(rate);
+    auto res = d->decodeMCDPSKFrame(v, r, protocol::v2::getBytesPerCodeword(r), 0.0f, 0.0f);
+    out->success = res.success ? 1 : 0;
+    out->frame_type = static_cast<int32_t>(res.frame_type);
+    out->codewords_ok = res.codewords_ok;
+    out->codewords_failed = res.codewords_failed;
+    out->is_ping = res.is_ping ? 1 : 0;
+    out->n_bytes = static_cast<int32_t>(res.frame_data.size());
+    std::memcpy(bytes, res.frame_data.data(), std::min<size_t>(res.frame_data.size(), static_cast<size_t>(cap)));
+}
+
+// v2::encodeFrameWithLDPC(frame_data, rate): CW0 = first bytes of the frame, CW1+ carry [0xD5][index][payload]
+// (frame_v2.cpp:925-957) -- the multi-codeword transmit format of MC-DPSK frames.  Returns the codeword count.
+int ref_encode_frame_with_ldpc(const uint8_t* frame, int len, int rate, uint8_t* out /*[n_cw][81]*/, int cap_cw) {
+    Bytes f(frame, frame + len);
+    auto cws = protocol::v2::encodeFrameWithLDPC(f, static_cast<CodeRate>(rate));
+    const int n = static_cast<int>(cws.size());
+    if (n > cap_cw) return -n;
+    for (int i = 0; i < n; ++i) {
+        std::memset(out + i * 81, 0, 81);
+        std::memcpy(out + i * 81, cws[i].data(), std::min<size_t>(81, cws[i].size()));
+    }
+    return n;
+}
 
 // ---------------------------------------------------------------------------------------------
 // MC-DPSK  (src/psk/multi_carrier_dpsk.hpp)

@@ -645,7 +645,7 @@ chirp_residue_kernel(const ResidueArgs a) {
             // (c_a, s_a) for a = 1, 2, 3 (a = 0 is (1, 0)): e^{j pi a r / 4}
             const float ct[8] = {1.f, h, 0.f, -h, -1.f, -h, 0.f, h}, st[8] = {0.f, h, 1.f, h, 0.f, -h, -1.f, -h};
             const float c1 = ct[r & 7], s1 = st[r & 7], c2 = ct[(2 * r) & 7], s2 = st[(2 * r) & 7], c3 = ct[(3 * r) & 7], s3 = st[(3 * r) & 7];
-#pragma unroll 2
+#pragma unroll 4
             for (int m = tid; m < kM; m += kResThreads) {
                 float xa[8];
 #pragma unroll

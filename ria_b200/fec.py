@@ -440,6 +440,12 @@ class ChaseCache:
         if all(e["decoded"]):
             self.free.append(self.entries.pop(key)["slot"])
 
+    def removeEntry(self, key) -> None:
+        """ChaseCache::removeEntry: drop the entry of a frame that decoded completely."""
+        e = self.entries.pop(key, None)
+        if e is not None:
+            self.free.append(e["slot"])
+
     def size(self) -> int:
         return len(self.entries)
 
