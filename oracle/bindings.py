@@ -229,6 +229,8 @@ class Ref:
         L.ref_stream_decoder_free.argtypes = [C.c_void_p]
         L.ref_stream_decode_mcdpsk_frame.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.POINTER(StreamDecodeResult), _u8p, C.c_int]
         L.ref_encode_frame_with_ldpc.argtypes = [_u8p, C.c_int, C.c_int, _u8p, C.c_int]
+        L.ref_stream_decode_ofdm_frame.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                   C.POINTER(StreamDecodeResult), _u8p, C.c_int]
         L.ref_encode_frame_with_ldpc.restype = C.c_int
         L.ref_crc16.argtypes = [_u8p, C.c_int]
         L.ref_crc16.restype = C.c_uint16
@@ -477,6 +479,16 @@ class Ref:
         res = StreamDecodeResult()
         buf = np.zeros(1024, np.uint8)
         self.lib.ref_stream_decode_mcdpsk_frame(h, soft, len(soft), int(rate), C.byref(res), buf, len(buf))
+        return res, bytes(buf[: res.n_bytes])
+
+    def stream_decode_ofdm_frame(self, h, soft, connected: bool, modulation: int, rate: int, data_carriers: int,
+                                 use_channel_interleave: bool = True):
+        """StreamingDecoder::decodeFrame for an OFDM receiver in that state -> (StreamDecodeResult, frame bytes)"""
+        soft = np.ascontiguousarray(soft, dtype=np.float32)
+        res = StreamDecodeResult()
+        buf = np.zeros(1024, np.uint8)
+        self.lib.ref_stream_decode_ofdm_frame(h, soft, len(soft), int(bool(connected)), int(modulation), int(rate),
+                                              int(data_carriers), int(bool(use_channel_interleave)), C.byref(res), buf, len(buf))
         return res, bytes(buf[: res.n_bytes])
 
     def encode_frame_with_ldpc(self, frame, rate: int) -> np.ndarray:

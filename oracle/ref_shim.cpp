@@ -373,6 +373,32 @@ void ref_stream_decode_mcdpsk_frame(void* h, const float* soft, int n_soft, int 
     std::memcpy(bytes, res.frame_data.data(), std::min<size_t>(res.frame_data.size(), static_cast<size_t>(cap)));
 }
 
+// StreamingDecoder::decodeFrame(soft_bits, snr, cfo) (:2820-3056) for an OFDM receiver in the given state.  The state
+// a StreamingDecoder reaches through setMode / setConnectedOFDMMode / setDataMode is written directly (private
+// members, -fno-access-control) so that no audio has to be streamed through it.
+void ref_stream_decode_ofdm_frame(void* h, const float* soft, int n_soft, int connected, int modulation, int rate,
+                                  int data_carriers, int use_channel_interleave, ref_decode_result* out,
+                                  uint8_t* bytes, int cap) {
+    auto* d = static_cast<gui::StreamingDecoder*>(h);
+    d->mode_ = protocol::WaveformMode::OFDM_CHIRP;
+    d->connected_ = connected != 0;
+    d->current_modulation_ = static_cast<Modulation>(modulation);
+    d->code_rate_ = static_cast<CodeRate>(rate);
+    d->ofdm_data_carriers_ = data_carriers;
+    d->use_channel_interleave_ = use_channel_interleave != 0;
+    d->interleaver_ = std::make_unique<ChannelInterleaver>(
+        static_cast<size_t>(data_carriers) * getBitsPerSymbol(static_cast<Modulation>(modulation)), protocol::v2::LDPC_CODEWORD_BITS);
+    std::vector<float> v(soft, soft + n_soft);
+    auto res = d->decodeFrame(v, 0.0f, 0.0f);
+    out->success = res.success ? 1 : 0;
+    out->frame_type = static_cast<int32_t>(res.frame_type);
+    out->codewords_ok = res.codewords_ok;
+    out->codewords_failed = res.codewords_failed;
+    out->is_ping = res.is_ping ? 1 : 0;
+    out->n_bytes = static_cast<int32_t>(res.frame_data.size());
+    std::memcpy(bytes, res.frame_data.data(), std::min<size_t>(res.frame_data.size(), static_cast<size_t>(cap)));
+}
+
 // v2::encodeFrameWithLDPC(frame_data, rate): CW0 = first bytes of the frame, CW1+ carry [0xD5][index][payload]
 // (frame_v2.cpp:925-957) -- the multi-codeword transmit format of MC-DPSK frames.  Returns the codeword count.
 int ref_encode_frame_with_ldpc(const uint8_t* frame, int len, int rate, uint8_t* out /*[n_cw][81]*/, int cap_cw) {

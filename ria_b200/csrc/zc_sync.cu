@@ -79,10 +79,12 @@ __global__ void zc_baseband_kernel(const float* __restrict__ samples, long long 
     const float dc = carrier + (known_cfo ? known_cfo[f] : 0.0f);           // downconvert_freq (:500)
     const float t = static_cast<float>(i) / sample_rate;                     // :502
     const float phase = static_cast<float>(-2.0f * M_PI * static_cast<double>(dc) * static_cast<double>(t));
-    double s, c;
-    sincos(static_cast<double>(phase), &s, &c);
+    // std::cos / std::sin of a float = glibc's cosf / sinf; the mixer phase runs to several thousand radians, where glibc
+    // takes its large-argument reduction (restated bit for bit in rn_math.h)
+    float s, c;
+    glibc_sincosf(phase, &s, &c);
     const float r = samples[f * frame_stride + i];
-    bb[f * bb_stride + i] = make_float2(__fmul_rn(static_cast<float>(c), r), __fmul_rn(static_cast<float>(s), r));
+    bb[f * bb_stride + i] = make_float2(__fmul_rn(c, r), __fmul_rn(s, r));
 }
 
 // Blackwell packed fp32: two IEEE round-to-nearest products / sums per issue slot.  ptxas would contract a packed

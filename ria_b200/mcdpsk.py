@@ -247,10 +247,13 @@ class McdpskFrameDecoder:
         if n == 0 or C_slots == 0:
             return out
         cw = soft[:, : C_slots * 648].contiguous().view(n * C_slots, 648)
-        info_d, ok_d, _, _ = self.dec.robust_decode_batch(cw, info_stride=24)
-        info = info_d.cpu().numpy().reshape(n, C_slots, 24)
+        stride = (((self.k + 7) // 8) + 3) & ~3
+        info_d, ok_d, _, _ = self.dec.robust_decode_batch(cw, info_stride=stride)
+        info = info_d.cpu().numpy().reshape(n, C_slots, stride)
         ok = ok_d.cpu().numpy().reshape(n, C_slots).astype(bool)
-        d0 = info[:, 0, :].copy()
+        d0 = np.zeros((n, max(stride, 24)), np.uint8)
+        d0[:, :stride] = info[:, 0, :]
+        d0len = np.full(n, bpc, np.int32)                       # data0.resize(bytes_per_cw) (:2686)
         good0 = ok[:, 0] & (d0[:, 0] == 0x55) & (d0[:, 1] == 0x4C)
         if self.dec_r14 is not None and (~good0).any():       # control frames are always R1/4 (:2639-2649)
             idx = np.nonzero(~good0)[0]
@@ -258,16 +261,18 @@ class McdpskFrameDecoder:
             i2, o2, _, _ = self.dec_r14.robust_decode_batch(sel, info_stride=24)
             i2, o2 = i2.cpu().numpy(), o2.cpu().numpy().astype(bool)
             hit = o2 & (i2[:, 0] == 0x55) & (i2[:, 1] == 0x4C)
-            d0[idx[hit]] = i2[hit]
+            d0[idx[hit]] = 0
+            d0[idx[hit], :24] = i2[hit]
+            d0len[idx[hit]] = min(21, bpc)                     # the R1/4 decode returns ceil(162 / 8) bytes
             good0[idx[hit]] = True
             self.stats["r14_fallbacks"] += int(hit.sum())
         # ---- v2::parseHeader on the first bytes_per_cw bytes (frame_v2.cpp:1195-1253; needs >= 20 bytes) ----
-        d0 = d0[:, :bpc] if bpc >= 20 else np.pad(d0[:, :bpc], ((0, 0), (0, 20 - bpc)))
+        d0[np.arange(d0.shape[1])[None, :] >= d0len[:, None]] = 0
         ftype = d0[:, 2].astype(np.int32)
         is_control = np.isin(ftype, _CONTROL_TYPES)
         crc_ctl = _crc16_rows(d0[:, :18]) == ((d0[:, 18].astype(np.uint16) << 8) | d0[:, 19])
         crc_dat = _crc16_rows(d0[:, :15]) == ((d0[:, 15].astype(np.uint16) << 8) | d0[:, 16])
-        valid = good0 & (bpc >= 20) & np.where(is_control, crc_ctl, crc_dat)
+        valid = good0 & (d0len >= 20) & np.where(is_control, crc_ctl, crc_dat)
         total_cw = np.where(is_control, 1, d0[:, 12].astype(np.int32))
         payload_len = np.where(is_control, 0, (d0[:, 13].astype(np.int32) << 8) | d0[:, 14])
         seq = (d0[:, 4].astype(np.int32) << 8) | d0[:, 5]
@@ -280,14 +285,15 @@ class McdpskFrameDecoder:
         out["codewords_ok"][valid] = 1
         # ---- one-codeword (control) frames ----
         one = valid & (total_cw == 1)
+        W = out["frame"].shape[1]
         out["success"][one] = 1
-        out["frame"][one, :bpc] = d0[one, :bpc]
-        out["frame_len"][one] = bpc
+        out["frame"][one, : min(W, d0.shape[1])] = d0[one, : min(W, d0.shape[1])]
+        out["frame_len"][one] = d0len[one]
         # ---- multi-codeword frames ----
         multi = valid & (total_cw > 1)
         partial = multi & (total_cw > C_slots)                   # not all codewords are in the buffer yet (:2745-2751)
-        out["frame"][partial, :bpc] = d0[partial, :bpc]
-        out["frame_len"][partial] = bpc
+        out["frame"][partial, : min(W, d0.shape[1])] = d0[partial, : min(W, d0.shape[1])]
+        out["frame_len"][partial] = d0len[partial]
         full = np.nonzero(multi & ~partial)[0]
         if len(full) == 0:
             return out
@@ -295,7 +301,7 @@ class McdpskFrameDecoder:
         needed = (cw_idx >= 1) & (cw_idx < total_cw[full, None])             # codewords 1 .. total_cw - 1
         cw_ok = ok[full] & needed
         cw_data = info[full][:, :, :bpc].copy()
-        cw_data[:, 0, :] = d0[full, :bpc]
+        cw0_full = d0[full]
         failed_f, failed_c = np.nonzero(needed & ~cw_ok)
         cache = self.cache
         if cache is not None and cache.enabled and len(failed_f):
@@ -304,10 +310,18 @@ class McdpskFrameDecoder:
             stored = cache.store_batch(keys, [int(c) for c in failed_c], [int(total_cw[full[f]]) for f in failed_f],
                                        cw.index_select(0, rows))
             self.stats["chase_stores"] += int(sum(stored))
-            retry = [j for j in range(len(keys)) if cache.getCombineCount(keys[j], int(failed_c[j])) > 1]
+            # decode the combined soft bits where earlier receptions are cached (:2771-2787); getCombined refuses
+            # codewords the cache already holds as decoded
+            retry, rows_c = [], []
+            for j in range(len(keys)):
+                if cache.getCombineCount(keys[j], int(failed_c[j])) > 1:
+                    t = cache.getCombined(keys[j], int(failed_c[j]))
+                    if t is not None:
+                        retry.append(j)
+                        rows_c.append(t)
             if retry:
-                comb = torch.stack([cache.getCombined(keys[j], int(failed_c[j])) for j in retry])
-                i3, o3, _, _ = self.dec.robust_decode_batch(comb.contiguous(), info_stride=24)
+                comb = torch.stack(rows_c)
+                i3, o3, _, _ = self.dec.robust_decode_batch(comb.contiguous(), info_stride=stride)
                 i3, o3 = i3.cpu().numpy(), o3.cpu().numpy().astype(bool)
                 for t, j in enumerate(retry):
                     if o3[t]:
@@ -339,7 +353,7 @@ class McdpskFrameDecoder:
             for c in range(int(total_cw[g])):
                 if have >= expected:
                     break
-                chunk = cw_data[f, c]
+                chunk = cw_data[f, c] if c > 0 else cw0_full[f, : d0len[g]]
                 if c > 0 and bpc >= 2 and chunk[0] == 0xD5:
                     chunk = chunk[2:]
                 chunk = chunk[: expected - have]

@@ -371,3 +371,215 @@ class OFDMChirpWaveform:
     def reset(self) -> None:
         self.soft_bits_ = np.zeros(0, np.float32)
         self.abs_training_start_ = None               # CFO is preserved across reset (:474-485)
+
+
+# ---------------------------------------------------------------------------------------------
+# Frame-level decode of OFDM receptions: StreamingDecoder::decodeFrame for a batch
+# ---------------------------------------------------------------------------------------------
+class OfdmFrameDecoder:
+    """StreamingDecoder::decodeFrame (src/gui/modem/streaming_decoder.cpp:2820-3056) for a batch of OFDM receptions, the
+    reference's "try both" strategy:
+      1. R1/4 control fast path when the data rate is not R1/4 (:2864-2886): codec decode of the first 648 soft bits
+         at R1/4; a valid one-codeword header ends the frame;
+      2. codeword 0 decoded raw at the data rate (:2892-2925): a one-codeword header ends the frame, a four-codeword
+         header (or no header at all) goes on to the frame-interleaved decode;
+      3. v2::decodeFixedFrame -- complete, with retry ladder and false-positive repair -- and reassembly
+         (:2928-2967); when it fails, the one-codeword salvage with robustDecodeSingleCW at R1/4, then at the data
+         rate (:2972-3008);
+      4. the legacy sequential path for headers that announce another codeword count (:3013-3053).
+    Every LDPC decode runs on the device, batched over the receptions that reach the step; the branching between the
+    steps is host logic, as in the reference.  rate = the connected data rate (a disconnected receiver decodes R1/4)."""
+
+    def __init__(self, modulation: int, rate: int, data_carriers: int, connected: bool = True,
+                 use_channel_interleave: bool = True, ctx: Optional[Context] = None):
+        from . import fec
+        self.modulation, self.data_carriers = int(modulation), int(data_carriers)
+        self.rate = int(rate) if connected else 0                     # :2831
+        self.use_ci = bool(use_channel_interleave)
+        self._ctx = ctx
+        self.k = fec.code_params(self.rate)[0]
+        self.bpc = self.k // 8
+        self.bps = self.data_carriers * getBitsPerSymbol(self.modulation)
+
+        def codec(r):                                                 # LDPCCodec::decode: factor 0.75, recommended iterations
+            d = fec.LDPCDecoder(r, ctx)
+            d.setMaxIterations(fec.recommended_iterations(r))
+            d.setMinSumFactor(0.75)
+            return d
+        self.codec = codec(self.rate)
+        self.codec_r14 = codec(0) if self.rate != 0 else None
+        self.robust = fec.LDPCDecoder(self.rate, ctx)
+        self.robust_r14 = fec.LDPCDecoder(0, ctx)
+
+    @staticmethod
+    def _header(d0, d0len):
+        """v2::parseHeader on rows of codeword-0 bytes -> (valid, type, total_cw, payload_len, is_control)"""
+        from .mcdpsk import _CONTROL_TYPES, _crc16_rows
+        ftype = d0[:, 2].astype(np.int32)
+        is_control = np.isin(ftype, _CONTROL_TYPES)
+        crc_ctl = _crc16_rows(d0[:, :18]) == ((d0[:, 18].astype(np.uint16) << 8) | d0[:, 19])
+        crc_dat = _crc16_rows(d0[:, :15]) == ((d0[:, 15].astype(np.uint16) << 8) | d0[:, 16])
+        valid = (d0len >= 20) & (d0[:, 0] == 0x55) & (d0[:, 1] == 0x4C) & np.where(is_control, crc_ctl, crc_dat)
+        total_cw = np.where(is_control, 1, d0[:, 12].astype(np.int32))
+        payload_len = np.where(is_control, 0, (d0[:, 13].astype(np.int32) << 8) | d0[:, 14])
+        return valid, ftype, total_cw, payload_len, is_control
+
+    def _decode_cw(self, dec, rows: torch.Tensor, robust: bool):
+        stride = 64                                                   # ceil(486 / 8) = 61 bytes at R3/4
+        if robust:
+            info, ok, _, _ = dec.robust_decode_batch(rows.contiguous(), info_stride=stride)
+        else:
+            info, ok, _ = dec.decode_batch(rows.contiguous(), info_stride=stride)
+        return info.cpu().numpy(), ok.cpu().numpy().astype(bool)
+
+    def decode_batch(self, soft: torch.Tensor):
+        """soft: CUDA fp32 [n, L], L >= 648 soft bits per reception.  Returns numpy arrays success u8[n], frame_type i32[n],
+        codewords_ok / codewords_failed i32[n], frame_len i32[n], frame u8[n, W]."""
+        from .fec import code_params
+        if not (isinstance(soft, torch.Tensor) and soft.is_cuda and soft.dtype == torch.float32 and soft.dim() == 2):
+            raise RiaError("decode_batch wants CUDA fp32 [n, L] (no CPU fallback)")
+        n, L = soft.shape
+        bpc = self.bpc
+        W = max(4 * bpc, (L // 648) * max(bpc, 21), 64)
+        out = dict(success=np.zeros(n, np.uint8), frame_type=np.full(n, 0x10, np.int32), codewords_ok=np.zeros(n, np.int32),
+                   codewords_failed=np.zeros(n, np.int32), frame_len=np.zeros(n, np.int32), frame=np.zeros((n, W), np.uint8))
+        if n == 0 or L < 648:
+            return out
+        dev = soft.device
+        alive = np.ones(n, bool)                                      # receptions that have not returned yet
+
+        def finish_control(idx, data, dlen, ftype):
+            out["success"][idx] = 1
+            out["codewords_ok"][idx] = 1
+            out["codewords_failed"][idx] = 0
+            out["frame_type"][idx] = ftype
+            out["frame"][idx, :64] = 0
+            for j, g in enumerate(idx):
+                out["frame"][g, : dlen[j]] = data[j, : dlen[j]]
+            out["frame_len"][idx] = dlen
+            alive[idx] = False
+
+        cw0 = soft[:, :648]
+        # ---- 1. R1/4 control fast path ----
+        if self.codec_r14 is not None:
+            info, ok = self._decode_cw(self.codec_r14, cw0, robust=False)
+            dlen = np.full(n, 20, np.int32)                           # data_r14.resize(bytes per codeword of R1/4)
+            d = info.copy(); d[:, 20:] = 0
+            valid, ftype, total_cw, _, _ = self._header(d, dlen)
+            hit = np.nonzero(ok & valid & (total_cw == 1))[0]
+            if len(hit):
+                finish_control(hit, d[hit], dlen[hit], ftype[hit])
+        # ---- 2. codeword 0 raw at the data rate ----
+        info0, ok0 = self._decode_cw(self.codec, cw0, robust=False)
+        d0 = info0.copy(); d0[:, bpc:] = 0
+        d0len = np.full(n, bpc, np.int32)
+        magic0 = ok0 & (d0[:, 0] == 0x55) & (d0[:, 1] == 0x4C)
+        valid0, ftype0, total0, payload0, is_ctl0 = self._header(d0, d0len)
+        valid0 &= magic0
+        out["frame_type"][alive & valid0] = ftype0[alive & valid0]
+        hit = np.nonzero(alive & valid0 & (total0 == 1))[0]
+        if len(hit):
+            finish_control(hit, d0[hit], d0len[hit], ftype0[hit])
+        try_fi = alive & (~magic0 | (valid0 & (total0 == 4)))
+        # ---- 3. frame-interleaved decode of the four-codeword frame ----
+        fi = np.nonzero(try_fi & (L >= 2592))[0] if L >= 2592 else np.zeros(0, np.int64)
+        if len(fi):
+            sel = soft.index_select(0, torch.from_numpy(fi).to(dev))
+            data, status = decode_fixed_frame_batch(sel, self.rate, self.use_ci, self.bps, self._ctx,
+                                                    retry_ladder=True, fp_repair=True)
+            data = data.cpu().numpy()
+            st = status_array(status)
+            n_ok = (st["cw_ok"] != 0).sum(axis=1)
+            out["codewords_ok"][fi] = n_ok
+            out["codewords_failed"][fi] = 4 - n_ok
+            allok = n_ok == 4
+            # CodewordStatus::reassemble: header of codeword 0, then chunks 1..3 (a chunk that starts with 0xD5 loses two bytes)
+            for j in np.nonzero(allok)[0]:
+                g = fi[j]
+                chunks = data[j].reshape(4, bpc)
+                hv, _, _, plen, isc = self._header(chunks[:1], np.array([bpc]))
+                frame = b""
+                if hv[0]:
+                    expected = 20 if isc[0] else 17 + int(plen[0]) + 2
+                    parts, have = [], 0
+                    for c in range(4):
+                        if have >= expected:
+                            break
+                        ch = chunks[c]
+                        if c > 0 and bpc >= 2 and ch[0] == 0xD5:
+                            ch = ch[2:]
+                        ch = ch[: expected - have]
+                        parts.append(ch); have += len(ch)
+                    frame = np.concatenate(parts).tobytes()
+                out["success"][g] = 1 if frame else 0                # 4/4 but reassemble failed: LDPC false positive (:2946-2950)
+                out["frame"][g, : len(frame)] = np.frombuffer(frame, np.uint8)
+                out["frame_len"][g] = len(frame)
+                if len(frame) >= 3:
+                    out["frame_type"][g] = frame[2]
+                alive[g] = False
+            # one-codeword salvage of what the four-codeword decode could not read (:2972-3008)
+            bad = fi[~allok]
+            for dec, r in ((self.robust_r14, 0), (self.robust, self.rate)):
+                if len(bad) == 0 or (r == self.rate and self.rate == 0 and dec is self.robust):
+                    continue
+                infoS, okS = self._decode_cw(dec, cw0.index_select(0, torch.from_numpy(bad).to(dev)), robust=True)
+                bpc_s = code_params(r)[0] // 8
+                dS = infoS.copy(); dS[:, bpc_s:] = 0
+                lenS = np.full(len(bad), bpc_s, np.int32)
+                vS, tS, totS, _, _ = self._header(dS, lenS)
+                hitS = okS & vS & (totS == 1)
+                if hitS.any():
+                    finish_control(bad[hitS], dS[hitS], lenS[hitS], tS[hitS])
+                bad = bad[~hitS]
+        # ---- 4. legacy sequential path (:3013-3053) ----
+        leg = np.nonzero(alive & magic0)[0]
+        if len(leg):
+            out["codewords_ok"][leg] = 1
+            out["codewords_failed"][leg] = np.where(np.isin(leg, fi), out["codewords_failed"][leg], 0)
+            keep = valid0[leg]
+            leg = leg[keep]
+            avail = L // 648
+            short = total0[leg] > avail
+            out["frame"][leg[short], :64] = d0[leg[short]]
+            out["frame_len"][leg[short]] = bpc
+            leg = leg[~short]
+            if len(leg):
+                tmax = int(total0[leg].max())
+                ci = None
+                if self.use_ci:                                       # ChannelInterleaver::deinterleave: out[i] = in[(i * step) % 648]
+                    step = channel_interleaver_step(self.bps, 648)
+                    ci = torch.from_numpy((np.arange(648) * step) % 648).to(dev)
+                okm = np.zeros((len(leg), tmax), bool); okm[:, 0] = True
+                datam = np.zeros((len(leg), tmax, bpc), np.uint8); datam[:, 0] = d0[leg, :bpc]
+                rows_t = torch.from_numpy(leg).to(dev)
+                for c in range(1, tmax):
+                    need = np.nonzero(total0[leg] > c)[0]
+                    if len(need) == 0:
+                        break
+                    bits = soft.index_select(0, rows_t[torch.from_numpy(need).to(dev)])[:, c * 648:(c + 1) * 648]
+                    if ci is not None:
+                        bits = bits.index_select(1, ci)
+                    infoC, okC = self._decode_cw(self.codec, bits, robust=False)
+                    okm[need, c] = okC
+                    datam[need, c] = infoC[:, :bpc]
+                for j, g in enumerate(leg):
+                    t = int(total0[g])
+                    nok = int(okm[j, :t].sum())
+                    out["codewords_ok"][g] = nok
+                    out["codewords_failed"][g] += t - nok              # on top of what a failed four-codeword decode counted
+                    if nok == t:
+                        expected = 20 if is_ctl0[g] else 17 + int(payload0[g]) + 2
+                        parts, have = [], 0
+                        for c in range(t):
+                            if have >= expected:
+                                break
+                            ch = datam[j, c]
+                            if c > 0 and bpc >= 2 and ch[0] == 0xD5:
+                                ch = ch[2:]
+                            ch = ch[: expected - have]
+                            parts.append(ch); have += len(ch)
+                        fr = np.concatenate(parts)
+                        out["success"][g] = 1
+                        out["frame"][g, : len(fr)] = fr
+                        out["frame_len"][g] = len(fr)
+        return out

@@ -142,3 +142,62 @@ def test_zc_acquired_chain_matches_reference_calls(ctx, ref):
     finally:
         ref.stream_decoder_free(h)
     assert n_ok >= n // 2
+
+
+@pytest.mark.parametrize("mod_name,rate,spacing,esn0", [("QAM16", 3, 5, 5.4), ("DQPSK", 2, 10, 1.9), ("DQPSK", 0, 10, -2.2)])
+def test_decode_frame_ofdm_matches_streaming_decoder(ctx, ref, mod_name, rate, spacing, esn0):
+    """Batched StreamingDecoder::decodeFrame for OFDM receivers (ria_b200.ofdm.OfdmFrameDecoder): four-codeword data frames
+    through the frame-interleaved decode, one-codeword control frames through the R1/4 fast path / raw codeword 0, the
+    salvage of control frames after a failed four-codeword decode, frames too noisy to decode, and short buffers."""
+    import torch
+    import oracle.bindings as ob
+    from oracle.bindings import BITS_PER_CARRIER, BYTES_PER_CW, ModemConfig
+    from ria_b200 import ofdm
+    mod = getattr(ob, mod_name)
+    cfg = ModemConfig.make(mod, spacing, 1)
+    bps = cfg.data_carriers() * BITS_PER_CARRIER[mod]
+    bpc = BYTES_PER_CW[rate]
+    rng = np.random.default_rng(900 + rate)
+    snr = 10 ** (esn0 / 10)
+    rows = []
+    for i in range(60):
+        kind = i % 6
+        noise_db = (0.0, 1.0, 3.0, -2.0, 4.0, -6.0)[kind]
+        if kind in (0, 1, 3, 5):                                   # four-codeword data frame, frame + channel interleaved
+            frame = ref.make_data_frame("K1ABC", "W2XYZ", i, rng.integers(0, 256, size=4 * bpc - 19 - int(rng.integers(0, 30)), dtype=np.uint8))
+            coded = np.frombuffer(bytes(ref.encode_fixed_frame(frame, rate, True, bps)), np.uint8)
+            bits = np.unpackbits(coded)[:2592].astype(np.float32)
+        else:                                                      # one-codeword control frame: R1/4, not interleaved, padded with noise
+            ctl = bytearray(20)
+            ctl[0:2] = b"\x55\x4c"; ctl[2] = (0x20, 0x16)[kind == 4]; ctl[4:6] = int(i).to_bytes(2, "big")
+            ctl[6:12] = bytes(rng.integers(0, 256, size=6, dtype=np.uint8))
+            ctl[18:20] = int(ref.crc16(bytes(ctl[:18]))).to_bytes(2, "big")
+            cw = ref.ldpc_encode(0, np.frombuffer(bytes(ctl), np.uint8))[:81]
+            bits = np.concatenate([np.unpackbits(cw)[:648], rng.integers(0, 2, size=2592 - 648)]).astype(np.float32)
+        s = 1.0 - 2.0 * bits
+        g = snr * 10 ** (noise_db / 10)
+        llr = (2.0 * (s + rng.standard_normal(s.shape).astype(np.float32) / np.sqrt(g)) * g).astype(np.float32)
+        if kind == 2 and i % 12 == 2:
+            llr[648:] = 0.0
+        rows.append(llr)
+    rows = np.stack(rows)
+    dec = ofdm.OfdmFrameDecoder(mod, rate, cfg.data_carriers(), True, True, ctx)
+    got = dec.decode_batch(torch.from_numpy(rows).cuda())
+    short = dec.decode_batch(torch.from_numpy(rows[:12, :1300]).cuda())      # buffers that end inside codeword 2
+    h = ref.stream_decoder()
+    n_ok = n_ctl = 0
+    try:
+        for tag, out, data_rows in (("full", got, rows), ("short", short, rows[:12, :1300])):
+            for i, row in enumerate(data_rows):
+                res, data = ref.stream_decode_ofdm_frame(h, row, True, mod, rate, cfg.data_carriers(), True)
+                assert out["success"][i] == res.success, (tag, i, out["success"][i], res.success)
+                assert out["codewords_ok"][i] == res.codewords_ok and out["codewords_failed"][i] == res.codewords_failed, \
+                    (tag, i, out["codewords_ok"][i], res.codewords_ok, out["codewords_failed"][i], res.codewords_failed)
+                assert out["frame_len"][i] == len(data) and bytes(out["frame"][i, : len(data)]) == data, (tag, i)
+                if res.success:
+                    assert out["frame_type"][i] == res.frame_type, (tag, i)
+                    n_ok += 1
+                    n_ctl += int(res.codewords_ok == 1)
+    finally:
+        ref.stream_decoder_free(h)
+    assert n_ok >= 20 and n_ctl >= 5, (n_ok, n_ctl)
