@@ -243,6 +243,15 @@ class Ref:
         L.ref_chase_combine.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int)]
         L.ref_chase_combine.restype = C.c_int
         L.ref_ofdm_data_sync.argtypes = [C.POINTER(ModemConfig), _f32p, C.c_int, C.c_float, C.c_float, C.POINTER(SyncResult)]
+        L.ref_ofdm_cox_tx_frame.argtypes = [C.POINTER(ModemConfig), _u8p, C.c_int, _f32p, C.c_int]
+        L.ref_ofdm_cox_tx_frame.restype = C.c_int
+        L.ref_ofdm_cox_search_sync.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.POINTER(C.c_float),
+                                               C.POINTER(C.c_longlong), C.POINTER(C.c_float)]
+        L.ref_ofdm_cox_search_sync.restype = C.c_int
+        L.ref_ofdm_cox_correlation.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int]
+        L.ref_ofdm_cox_correlation.restype = C.c_float
+        L.ref_ofdm_cox_refine_lts.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        L.ref_ofdm_cox_refine_lts.restype = C.c_longlong
         zcp = C.POINTER(ZcConfig)
         L.ref_zc_preamble.argtypes = [zcp, C.c_int, _f32p, C.c_int]
         L.ref_zc_preamble.restype = C.c_int
@@ -301,6 +310,33 @@ class Ref:
         n = self.lib.ref_ofdm_tx_frame(C.byref(cfg), data, len(data), out, cap)
         assert n >= 0, n
         return out[:n].copy()
+
+    def ofdm_cox_tx_frame(self, cfg: ModemConfig, data) -> np.ndarray:
+        """[guard][4 x STS][2 x LTS][data symbols] as OFDMNvisWaveform transmits it"""
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        cap = cfg.symbol_samples() * (8 + len(data) * 8 // max(1, cfg.data_carriers()) + 4)
+        out = np.zeros(cap, np.float32)
+        n = self.lib.ref_ofdm_cox_tx_frame(C.byref(cfg), data, len(data), out, cap)
+        assert n >= 0, n
+        return out[:n].copy()
+
+    def ofdm_cox_search_sync(self, cfg: ModemConfig, samples, threshold=0.8, noise_floor=0.0):
+        """OFDMDemodulator::searchForSync -> (found, lts_position or -1, cfo_hz, noise_floor_after)"""
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        nf = C.c_float(noise_floor); pos = C.c_longlong(-1); cfo = C.c_float(0)
+        f = self.lib.ref_ofdm_cox_search_sync(self._demod(cfg), samples, len(samples), threshold,
+                                              C.byref(nf), C.byref(pos), C.byref(cfo))
+        return bool(f), pos.value, cfo.value, nf.value
+
+    def ofdm_cox_correlation(self, cfg: ModemConfig, samples, offset) -> float:
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        return self.lib.ref_ofdm_cox_correlation(self._demod(cfg), samples, len(samples), int(offset))
+
+    def ofdm_cox_refine_lts(self, cfg: ModemConfig, samples, coarse_sts):
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        cfo = C.c_float(0)
+        r = self.lib.ref_ofdm_cox_refine_lts(self._demod(cfg), samples, len(samples), int(coarse_sts), C.byref(cfo))
+        return r, cfo.value
 
     def _demod(self, cfg: ModemConfig):
         key = bytes(cfg)

@@ -575,6 +575,57 @@ int ref_chase_combine(const float* soft, int n_receptions, int cw_index, int tot
 }
 
 
+// OFDM_COX transmit frame: OFDMNvisWaveform::generatePreamble() + modulate() (src/waveform/ofdm_cox_waveform.cpp:106-119),
+// i.e. OFDMModulator::generatePreamble (src/ofdm/modulator.cpp:479-532: guard, 4 x STS, 2 x LTS) followed by
+// OFDMModulator::modulate with the mixer running on.
+int ref_ofdm_cox_tx_frame(const ria_modem_config* c, const uint8_t* data, int len, float* out, int cap) {
+    ModemConfig m = to_cfg(c);
+    OFDMModulator mod(m);
+    Samples pre = mod.generatePreamble();
+    Samples d = mod.modulate(ByteSpan(data, static_cast<size_t>(len)), m.modulation);
+    int n = static_cast<int>(pre.size() + d.size());
+    if (n > cap) return -n;
+    std::memcpy(out, pre.data(), pre.size() * sizeof(float));
+    std::memcpy(out + pre.size(), d.data(), d.size() * sizeof(float));
+    return n;
+}
+
+// OFDMDemodulator::searchForSync (src/ofdm/demodulator.cpp:1450-1542) = what OFDMNvisWaveform::detectSync runs.
+// noise_floor (optional) is Impl::noise_floor_energy before / after the call: the only state the search keeps.
+int ref_ofdm_cox_search_sync(void* h, const float* samples, int n, float threshold, float* noise_floor,
+                             long long* position, float* cfo_hz) {
+    auto* d = static_cast<RefOfdmDemod*>(h);
+    if (noise_floor) d->dem.impl_->noise_floor_energy = *noise_floor;
+    size_t pos = 0; float cfo = 0.0f;
+    bool found = d->dem.searchForSync(SampleSpan(samples, static_cast<size_t>(n)), pos, cfo, threshold);
+    if (noise_floor) *noise_floor = d->dem.impl_->noise_floor_energy;
+    *position = found ? static_cast<long long>(pos) : -1;
+    *cfo_hz = found ? cfo : 0.0f;
+    return found ? 1 : 0;
+}
+
+// taps for the acquisition stages: Impl::measureCorrelation / refineLTSTiming / estimateCoarseCFO on a buffer
+float ref_ofdm_cox_correlation(void* h, const float* samples, int n, int offset) {
+    auto* d = static_cast<RefOfdmDemod*>(h);
+    auto& im = *d->dem.impl_;
+    std::vector<float> saved = std::move(im.rx_buffer);
+    im.rx_buffer.assign(samples, samples + n);
+    float c = im.measureCorrelation(static_cast<size_t>(offset));
+    im.rx_buffer = std::move(saved);
+    return c;
+}
+
+long long ref_ofdm_cox_refine_lts(void* h, const float* samples, int n, int coarse_sts, float* cfo_hz) {
+    auto* d = static_cast<RefOfdmDemod*>(h);
+    auto& im = *d->dem.impl_;
+    std::vector<float> saved = std::move(im.rx_buffer);
+    im.rx_buffer.assign(samples, samples + n);
+    size_t r = im.refineLTSTiming(static_cast<size_t>(coarse_sts));
+    if (cfo_hz) *cfo_hz = im.estimateCoarseCFO(static_cast<size_t>(coarse_sts));
+    im.rx_buffer = std::move(saved);
+    return r == SIZE_MAX ? -1 : static_cast<long long>(r);
+}
+
 // OFDMChirpWaveform::detectDataSync (src/waveform/ofdm_chirp_waveform.cpp:207-384)
 void ref_ofdm_data_sync(const ria_modem_config* c, const float* samples, int n, float known_cfo, float threshold,
                         ria_sync_result* out) {
