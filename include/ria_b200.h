@@ -263,6 +263,9 @@ int ria_encode_fixed_frame_batch_dev(ria_ctx* ctx, int rate, int use_channel_int
 /* Samples of one transmitted frame: (training_symbols + ceil(8 coded_len / bits per OFDM symbol)) symbols. */
 int ria_ofdm_tx_frame_samples(const ria_modem_config* cfg, int32_t coded_len);
 
+/* OFDM_COX: samples of one transmitted frame = one symbol of silence + 4 STS + the frame above. */
+int ria_ofdm_cox_tx_frame_samples(const ria_modem_config* cfg, int32_t coded_len);
+
 /* Batched OFDMModulator::generateTrainingSymbols(cfg->training_symbols) + modulate(coded, cfg->modulation)
  * (src/ofdm/modulator.cpp:528-582, 348-477): what OFDMChirpWaveform transmits after the chirp and what
  * IWaveform::process is handed on the receive side.  Sample-identical to the reference (same radix-2
@@ -271,6 +274,14 @@ int ria_ofdm_tx_frame_samples(const ria_modem_config* cfg, int32_t coded_len);
 int ria_ofdm_tx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg,
                            const uint8_t* coded_dev, int64_t coded_stride, int32_t coded_len,
                            int64_t n_frames, float* samples_dev, int64_t out_stride);
+
+/* Batched OFDMModulator::generatePreamble() + modulate(coded, cfg->modulation) (src/ofdm/modulator.cpp:479-532,
+ * 348-477): what OFDMNvisWaveform (OFDM_COX) transmits (src/waveform/ofdm_cox_waveform.cpp:106-119) -- guard,
+ * 4 Schmidl-Cox STS (one symbol repeated), 2 LTS (one symbol repeated), data.  Sample-identical to the
+ * reference.  out_stride >= ria_ofdm_cox_tx_frame_samples(); cfg->symbol_guard must be 0. */
+int ria_ofdm_cox_tx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg,
+                               const uint8_t* coded_dev, int64_t coded_stride, int32_t coded_len,
+                               int64_t n_frames, float* samples_dev, int64_t out_stride);
 
 /* Batched fec::BurstInterleaver::deinterleave (src/fec/burst_interleaver.cpp:39-78), applied by
  * StreamingDecoder::finalizeBurstGroup (src/gui/modem/streaming_decoder.cpp:3209-3216) to the soft bits of
@@ -349,6 +360,25 @@ int ria_ofdm_data_sync_batch_dev(ria_ctx* ctx, const ria_modem_config* cfg,
                                  const float* samples_dev, int64_t frame_stride, int32_t window,
                                  const float* known_cfo_dev, float threshold, int64_t n_frames,
                                  ria_sync_result* out_dev);
+
+/* Batched replacement for OFDMDemodulator::searchForSync(samples, out_position, out_cfo_hz, threshold)
+ * (src/ofdm/demodulator.cpp:1450-1542) -- what OFDMNvisWaveform::detectSync (OFDM_COX) runs
+ * (src/waveform/ofdm_cox_waveform.cpp:121-153): energy-gated Schmidl-Cox search in steps of 64 samples, plateau
+ * check, LTS fine timing, coarse CFO.  Result fields: detected, start_sample = first LTS sample (what
+ * processPresynced is then handed), cfo_hz, correlation = 0.9 (the waveform's constant), aux = the Schmidl-Cox
+ * peak position.  noise_floor_dev (nullable) is OFDMDemodulator::Impl::noise_floor_energy per window before /
+ * after the call, the only state the reference search carries between calls (0 = fresh demodulator).
+ * window <= 65536 samples. */
+int ria_ofdm_cox_search_sync_batch_dev(ria_ctx* ctx, const ria_modem_config* cfg,
+                                       const float* samples_dev, int64_t window_stride, int32_t window,
+                                       float threshold, float* noise_floor_dev, int64_t n_windows,
+                                       ria_sync_result* out_dev);
+
+/* Tap of the search above: OFDMDemodulator::Impl::measureCorrelation(offset) (src/ofdm/ofdm_sync.cpp:118-190), the
+ * Schmidl-Cox metric of the FFT window that follows offset + cyclic prefix, one offset per window. */
+int ria_ofdm_cox_correlation_batch_dev(ria_ctx* ctx, const ria_modem_config* cfg,
+                                       const float* samples_dev, int64_t window_stride, int32_t window,
+                                       const int32_t* offsets_dev, int64_t n_windows, float* corr_dev);
 
 /* ---- MC-DPSK receive path -------------------------------------------------------------------- */
 /* POD mirror of the RX-relevant fields of ultra::MultiCarrierDPSKConfig
@@ -523,7 +553,9 @@ int ria_channel_watterson_batch_dev(ria_ctx* ctx, const ria_watterson_config* cf
  *   ria_chirp_detect_dual_batch_host  IWaveform::detectSync          (ofdm_chirp_waveform.cpp:163-205, mc_dpsk_waveform.cpp:177-224)
  *   ria_zc_detect_batch_host          MCDPSKWaveform::detectDataSync (mc_dpsk_waveform.cpp:227-292)
  *   ria_ofdm_data_sync_batch_host     OFDMChirpWaveform::detectDataSync (ofdm_chirp_waveform.cpp:207-384)
- *   ria_mcdpsk_process_batch_host     MCDPSKWaveform::process        (mc_dpsk_waveform.cpp:294-338) */
+ *   ria_mcdpsk_process_batch_host     MCDPSKWaveform::process        (mc_dpsk_waveform.cpp:294-338)
+ *   ria_ofdm_cox_search_sync_batch_host  OFDMNvisWaveform::detectSync (ofdm_cox_waveform.cpp:121-153); noise_floor is
+ *                                     a host array here too */
 int ria_chirp_detect_dual_batch_host(ria_ctx* ctx, const ria_chirp_config* cfg, const float* samples,
                                      int64_t frame_stride, int32_t window, float threshold,
                                      int64_t n_frames, ria_sync_result* out);
@@ -533,6 +565,9 @@ int ria_zc_detect_batch_host(ria_ctx* ctx, const ria_zc_config* cfg, const float
 int ria_ofdm_data_sync_batch_host(ria_ctx* ctx, const ria_modem_config* cfg, const float* samples,
                                   int64_t frame_stride, int32_t window, const float* known_cfo, float threshold,
                                   int64_t n_frames, ria_sync_result* out);
+int ria_ofdm_cox_search_sync_batch_host(ria_ctx* ctx, const ria_modem_config* cfg, const float* samples,
+                                        int64_t window_stride, int32_t window, float threshold, float* noise_floor,
+                                        int64_t n_windows, ria_sync_result* out);
 int ria_mcdpsk_process_batch_host(ria_ctx* ctx, const ria_mcdpsk_config* cfg, const float* samples,
                                   int64_t frame_stride, int32_t frame_len, const float* cfo_hz, const float* phase,
                                   int64_t n_frames, float* llr, int32_t llr_stride, int32_t* n_llr,

@@ -139,6 +139,7 @@ extern "C" int ria_ctx_destroy(ria_ctx* ctx) {
     for (auto* t : ctx->zc_tables) ria::zc_tables_free(t);
     for (auto* t : ctx->chirp_tables) ria::chirp_tables_free(t);
     for (auto* t : ctx->mcdpsk_tx_tables) ria::mcdpsk_tx_tables_free(t);
+    for (auto* t : ctx->cox_tables) ria::cox_tables_free(t);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->ofdm_scratch) cudaFree(ctx->ofdm_scratch);
     if (ctx->chain_scratch) cudaFree(ctx->chain_scratch);

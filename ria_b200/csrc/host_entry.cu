@@ -119,6 +119,38 @@ extern "C" int ria_ofdm_data_sync_batch_host(ria_ctx* ctx, const ria_modem_confi
     return RIA_OK;
 }
 
+extern "C" int ria_ofdm_cox_search_sync_batch_host(ria_ctx* ctx, const ria_modem_config* cfg, const float* samples,
+                                                   int64_t window_stride, int32_t window, float threshold,
+                                                   float* noise_floor, int64_t n_windows, ria_sync_result* out) {
+    if (!ctx || !cfg) return RIA_E_INVAL;
+    if (n_windows < 0 || window < 0 || window_stride < window) return set_error(ctx, RIA_E_INVAL, "ofdm cox host: bad sizes");
+    if (n_windows == 0) return RIA_OK;
+    if (!samples || !out) return set_error(ctx, RIA_E_INVAL, "ofdm cox host: null buffer");
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t chunk = std::min<int64_t>(n_windows, 4096);
+    const int32_t d_stride = (window + 3) & ~3;
+    const size_t b_in = align256(static_cast<size_t>(chunk) * d_stride * sizeof(float));
+    const size_t b_nf = align256(static_cast<size_t>(chunk) * sizeof(float));
+    int rc = ensure_stage(ctx, 0, b_in + b_nf + chunk * sizeof(ria_sync_result) + 256, 0);
+    if (rc != RIA_OK) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->stage_dev[0]);
+    float* d_in = reinterpret_cast<float*>(base);
+    float* d_nf = reinterpret_cast<float*>(base + b_in);
+    ria_sync_result* d_out = reinterpret_cast<ria_sync_result*>(base + b_in + b_nf);
+    for (int64_t off = 0; off < n_windows; off += chunk) {
+        const int64_t n = std::min(chunk, n_windows - off);
+        RIA_CUDA(ctx, cudaMemcpy2DAsync(d_in, d_stride * sizeof(float), samples + off * window_stride, window_stride * sizeof(float),
+                                        window * sizeof(float), n, cudaMemcpyHostToDevice, ctx->stream));
+        if (noise_floor) RIA_CUDA(ctx, cudaMemcpyAsync(d_nf, noise_floor + off, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = ria_ofdm_cox_search_sync_batch_dev(ctx, cfg, d_in, d_stride, window, threshold, noise_floor ? d_nf : nullptr, n, d_out)) != RIA_OK)
+            return rc;
+        RIA_CUDA(ctx, cudaMemcpyAsync(out + off, d_out, n * sizeof(ria_sync_result), cudaMemcpyDeviceToHost, ctx->stream));
+        if (noise_floor) RIA_CUDA(ctx, cudaMemcpyAsync(noise_floor + off, d_nf, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        RIA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return RIA_OK;
+}
+
 extern "C" int ria_mcdpsk_process_batch_host(ria_ctx* ctx, const ria_mcdpsk_config* cfg, const float* samples,
                                              int64_t frame_stride, int32_t frame_len, const float* cfo_hz, const float* phase,
                                              int64_t n_frames, float* llr, int32_t llr_stride, int32_t* n_llr,

@@ -33,6 +33,10 @@ struct TxArgs {
     const float2* tw; const float2* nco; const OfdmCarrierTable* car;
     int N, logN, cp, guard, sym_len, n_train, n_data_sym, modulation, bpc;
     float scale;
+    // OFDM_COX preamble (OFDMModulator::generatePreamble, modulator.cpp:479-532): pre_guard silent samples, then n_sts
+    // Schmidl-Cox symbols (sync sequence on the even bins only, createSchmidlCoxSTS :298-330) before the LTS.
+    // 0 / 0 for the chirp waveform.
+    int pre_guard, n_sts;
 };
 
 __device__ __forceinline__ float2 cmul_ref(float2 a, float2 b) {       // std::complex<float> operator* (finite operands)
@@ -92,23 +96,34 @@ ofdm_tx_kernel(const TxArgs a) {
     __syncthreads();
     const int N = a.N, nd = car.n_data, np = car.n_pilot;
     const int total_bits = a.coded_len * 8;
-    const int n_sym = a.n_train + a.n_data_sym;
+    const int n_sym = a.n_sts + a.n_train + a.n_data_sym;
+    const int s_lts = a.n_sts, s_data = a.n_sts + a.n_train;
 
     for (long long f = blockIdx.x; f < a.n_frames; f += gridDim.x) {
         const uint8_t* data = a.coded + f * a.coded_stride;
         float* out = a.out + f * a.out_stride;
         if (tid < nd) prev[tid] = make_float2(1.0f, 0.0f);          // generateTrainingSymbols: dbpsk_prev_symbols = 1 (:540)
+        for (int i = tid; i < a.pre_guard; i += kTxThreads) out[i] = 0.0f;
+        out += a.pre_guard;
         for (int s = 0; s < n_sym; ++s) {
+            // mixer position of the symbol's first sample.  generatePreamble converts ONE STS and ONE LTS symbol to
+            // passband and repeats the samples (modulator.cpp:513-530), so the mixer advances one symbol for the four
+            // STS and one for the two LTS; generateTrainingSymbols converts every LTS symbol (:566-572).
+            int nco_base = s * a.sym_len;
+            if (a.n_sts > 0) nco_base = (s < s_lts) ? 0 : (s < s_data) ? a.sym_len : (2 + s - s_data) * a.sym_len;
             for (int i = tid; i < N; i += kTxThreads) fd[i] = make_float2(0.0f, 0.0f);
             __syncthreads();
             // ---- frequency domain, written at the bit-reversed position (fft.cpp:98-104) ----
             if (tid < nd) {
                 float2 v = make_float2(0.0f, 0.0f);
                 bool place = true;
-                if (s < a.n_train) {
+                if (s < s_lts) {
+                    v = car.tx_data[tid];                                // STS: even FFT bins only (:305-311)
+                    place = (car.fft_idx[car.data_car[tid]] & 1) == 0;
+                } else if (s < s_data) {
                     v = car.tx_data[tid];                                // sync_sequence[i % N] (:561-564)
                 } else {
-                    const int b0 = ((s - a.n_train) * nd + tid) * a.bpc;
+                    const int b0 = ((s - s_data) * nd + tid) * a.bpc;
                     if (b0 >= total_bits) {
                         place = true;                                    // padded with Complex(0, 0) (:455-458)
                     } else {
@@ -135,7 +150,7 @@ ofdm_tx_kernel(const TxArgs a) {
                     }
                 }
                 if (place) fd[__brev(static_cast<unsigned>(car.fft_idx[car.data_car[tid]])) >> (32 - a.logN)] = v;
-            } else if (tid >= 64 && tid - 64 < np) {
+            } else if (tid >= 64 && tid - 64 < np && s >= s_lts) {
                 const int i = tid - 64;
                 fd[__brev(static_cast<unsigned>(car.fft_idx[car.pilot_car[i]])) >> (32 - a.logN)] = make_float2(car.pilot_sign[i], 0.0f);
             }
@@ -161,7 +176,7 @@ ofdm_tx_kernel(const TxArgs a) {
                 if (i < a.cp + N) {
                     const int src = (i < a.cp) ? N - a.cp + i : i - a.cp;
                     const float2 z = make_float2(__fmul_rn(fd[src].x, inv_n), __fmul_rn(fd[src].y, inv_n));
-                    const float2 m = a.nco[s * a.sym_len + i];
+                    const float2 m = a.nco[nco_base + i];
                     o = __fmul_rn(__fsub_rn(__fmul_rn(z.x, m.x), __fmul_rn(z.y, m.y)), a.scale);
                 }
                 out[s * a.sym_len + i] = o;
@@ -244,16 +259,17 @@ extern "C" int ria_ofdm_tx_frame_samples(const ria_modem_config* cfg, int32_t co
     return (static_cast<int>(cfg->training_symbols) + n_data_sym) * ofdm_symbol_samples(*cfg);
 }
 
-extern "C" int ria_ofdm_tx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg,
-                                      const uint8_t* coded_dev, int64_t coded_stride, int32_t coded_len,
-                                      int64_t n_frames, float* samples_dev, int64_t out_stride) {
-    using namespace ria;
+namespace ria {
+namespace {
+int ofdm_tx_launch(ria_ctx* ctx, const ria_modem_config* cfg, const uint8_t* coded_dev, int64_t coded_stride, int32_t coded_len,
+                   int64_t n_frames, float* samples_dev, int64_t out_stride, bool cox) {
     if (!ctx || !cfg) return RIA_E_INVAL;
     if (n_frames < 0 || coded_len <= 0 || coded_stride < coded_len) return set_error(ctx, RIA_E_INVAL, "ofdm tx: bad sizes");
     if (n_frames == 0) return RIA_OK;
     if (!coded_dev || !samples_dev) return set_error(ctx, RIA_E_INVAL, "ofdm tx: null buffer");
     if (const char* err = ofdm_config_error(*cfg)) return set_error(ctx, RIA_E_UNSUPPORTED, "ofdm: %s", err);
-    const int frame_len = ria_ofdm_tx_frame_samples(cfg, coded_len);
+    if (cox && cfg->symbol_guard != 0) return set_error(ctx, RIA_E_UNSUPPORTED, "ofdm cox tx: symbol_guard must be 0");
+    const int frame_len = cox ? ria_ofdm_cox_tx_frame_samples(cfg, coded_len) : ria_ofdm_tx_frame_samples(cfg, coded_len);
     if (out_stride < frame_len) return set_error(ctx, RIA_E_INVAL, "ofdm tx: out_stride %lld < %d samples per frame",
                                                  static_cast<long long>(out_stride), frame_len);
     const int N = static_cast<int>(cfg->fft_size);
@@ -269,7 +285,9 @@ extern "C" int ria_ofdm_tx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg,
     a.N = N; a.logN = 0; while ((1 << a.logN) < N) ++a.logN;
     a.cp = t->cp; a.guard = static_cast<int>(cfg->symbol_guard); a.sym_len = t->sym_len;
     a.n_train = static_cast<int>(cfg->training_symbols);
-    a.n_data_sym = frame_len / t->sym_len - a.n_train;
+    a.pre_guard = cox ? N + t->cp : 0;                  // one preamble symbol of silence (modulator.cpp:503-504)
+    a.n_sts = cox ? 4 : 0;
+    a.n_data_sym = (frame_len - a.pre_guard) / t->sym_len - a.n_train - a.n_sts;
     a.modulation = static_cast<int>(cfg->modulation); a.bpc = ofdm_bits_per_carrier(cfg->modulation);
     a.scale = 40.0f;                                    // ModemConfig::output_scale (include/ultra/types.hpp:235)
     long long grid = static_cast<long long>(ctx->sm_count) * 8;
@@ -278,6 +296,27 @@ extern "C" int ria_ofdm_tx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg,
     RIA_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return RIA_OK;
+}
+}  // namespace
+}  // namespace ria
+
+extern "C" int ria_ofdm_tx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg,
+                                      const uint8_t* coded_dev, int64_t coded_stride, int32_t coded_len,
+                                      int64_t n_frames, float* samples_dev, int64_t out_stride) {
+    return ria::ofdm_tx_launch(ctx, cfg, coded_dev, coded_stride, coded_len, n_frames, samples_dev, out_stride, false);
+}
+
+extern "C" int ria_ofdm_cox_tx_frame_samples(const ria_modem_config* cfg, int32_t coded_len) {
+    // guard + 4 STS + the chirp waveform's frame (2 LTS + data): modulator.cpp:479-532
+    const int body = ria_ofdm_tx_frame_samples(cfg, coded_len);
+    if (body < 0) return body;
+    return body + 5 * (static_cast<int>(cfg->fft_size) + ria::ofdm_cyclic_prefix(*cfg));
+}
+
+extern "C" int ria_ofdm_cox_tx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg,
+                                          const uint8_t* coded_dev, int64_t coded_stride, int32_t coded_len,
+                                          int64_t n_frames, float* samples_dev, int64_t out_stride) {
+    return ria::ofdm_tx_launch(ctx, cfg, coded_dev, coded_stride, coded_len, n_frames, samples_dev, out_stride, true);
 }
 
 extern "C" int ria_encode_fixed_frame_batch_dev(ria_ctx* ctx, int rate, int use_channel_interleave, int bits_per_symbol,

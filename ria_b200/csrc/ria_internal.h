@@ -38,6 +38,7 @@ struct McdpskTablesDev; // mcdpsk.cu
 struct ZcTablesDev;     // zc_sync.cu
 struct ChirpTablesDev;  // chirp_sync.cu
 struct McdpskTxTablesDev;  // mcdpsk_tx.cu
+struct CoxTablesDev;    // ofdm_cox.cu
 
 struct LdpcCodeDev {
     bool ready = false;
@@ -71,6 +72,7 @@ struct ria_ctx {
     std::vector<ria::ZcTablesDev*> zc_tables;
     std::vector<ria::ChirpTablesDev*> chirp_tables;
     std::vector<ria::McdpskTxTablesDev*> mcdpsk_tx_tables;
+    std::vector<ria::CoxTablesDev*> cox_tables;
     float* hilbert65 = nullptr;             // 65-tap Hilbert FIR (OFDM data sync)
     // scratch owned by the context for the fused chain entry points
     void* scratch = nullptr;
@@ -105,6 +107,7 @@ void mcdpsk_tables_free(McdpskTablesDev* t);
 void zc_tables_free(ZcTablesDev* t);
 void chirp_tables_free(ChirpTablesDev* t);
 void mcdpsk_tx_tables_free(McdpskTxTablesDev* t);
+void cox_tables_free(CoxTablesDev* t);
 int ensure_scratch(ria_ctx* ctx, size_t bytes);
 int recommended_ldpc_iterations(int rate);          // LDPCCodec::getRecommendedIterations (frame.cu)
 // ldpc.cu / ldpc_retry.cu

@@ -233,6 +233,24 @@ def ofdm_tx_frames(config: ModemConfig, coded: torch.Tensor, ctx: Optional[Conte
     return out
 
 
+def ofdm_cox_tx_frames(config: ModemConfig, coded: torch.Tensor, ctx: Optional[Context] = None) -> torch.Tensor:
+    """OFDMModulator::generatePreamble + modulate for a batch on the device (src/ofdm/modulator.cpp:479-532, 348-477) =
+    what OFDMNvisWaveform (OFDM_COX) transmits: [silence][4 x STS][2 x LTS][data], sample-identical to the reference."""
+    if not (isinstance(coded, torch.Tensor) and coded.is_cuda and coded.dtype == torch.uint8 and coded.dim() == 2):
+        raise RiaError("ofdm_cox_tx_frames wants a CUDA uint8 [n, coded_len] tensor")
+    coded = coded.contiguous()
+    ctx = ctx or default_context()
+    n, clen = coded.shape
+    flen = lib().ria_ofdm_cox_tx_frame_samples(C.addressof(config), clen)
+    if flen <= 0:
+        raise RiaError("ofdm_cox_tx_frames: unsupported configuration")
+    out = torch.empty((n, flen), dtype=torch.float32, device=coded.device)
+    ctx.set_stream(torch.cuda.current_stream(coded.device))
+    ctx.check(lib().ria_ofdm_cox_tx_frames_dev(ctx.handle, C.addressof(config), _ptr(coded), coded.stride(0), clen, n,
+                                               _ptr(out), out.stride(0)))
+    return out
+
+
 def status_array(status: torch.Tensor) -> np.ndarray:
     return status.cpu().numpy().view(FRAME_STATUS_DTYPE).reshape(-1)
 

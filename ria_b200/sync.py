@@ -151,6 +151,40 @@ def ofdm_data_sync_batch(config, samples: torch.Tensor, known_cfo_hz: Optional[t
     return out
 
 
+def ofdm_cox_search_sync_batch(config, samples: torch.Tensor, threshold: float = 0.8,
+                               noise_floor: Optional[torch.Tensor] = None, ctx: Optional[Context] = None) -> torch.Tensor:
+    """OFDMDemodulator::searchForSync (src/ofdm/demodulator.cpp:1450-1542) = OFDMNvisWaveform::detectSync for every
+    row of samples (CUDA fp32 [n, window <= 65536]).  Result rows: detected, start_sample = first LTS sample,
+    cfo_hz, aux = Schmidl-Cox peak.  ``noise_floor`` (CUDA fp32 [n], updated in place) carries the demodulator's
+    noise-floor tracker from one call to the next; None = fresh demodulators."""
+    samples = _check_windows(samples)
+    n, window = samples.shape
+    if noise_floor is not None and not (noise_floor.is_cuda and noise_floor.dtype == torch.float32
+                                        and noise_floor.is_contiguous() and noise_floor.numel() == n):
+        raise RiaError("noise_floor must be a contiguous CUDA fp32 [n] tensor")
+    out = torch.empty((n, SYNC_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=samples.device)
+    ctx = ctx or default_context()
+    ctx.set_stream(torch.cuda.current_stream(samples.device))
+    ctx.check(lib().ria_ofdm_cox_search_sync_batch_dev(
+        ctx.handle, C.addressof(config), _ptr(samples), samples.stride(0), window, float(threshold),
+        _ptr(noise_floor), n, _ptr(out)))
+    return out
+
+
+def ofdm_cox_correlation_batch(config, samples: torch.Tensor, offsets: torch.Tensor,
+                               ctx: Optional[Context] = None) -> torch.Tensor:
+    """Impl::measureCorrelation(offset) (src/ofdm/ofdm_sync.cpp:118-190), one offset (CUDA int32 [n]) per window."""
+    samples = _check_windows(samples)
+    n, window = samples.shape
+    offsets = offsets.to(torch.int32).contiguous()
+    out = torch.empty(n, dtype=torch.float32, device=samples.device)
+    ctx = ctx or default_context()
+    ctx.set_stream(torch.cuda.current_stream(samples.device))
+    ctx.check(lib().ria_ofdm_cox_correlation_batch_dev(
+        ctx.handle, C.addressof(config), _ptr(samples), samples.stride(0), window, _ptr(offsets), n, _ptr(out)))
+    return out
+
+
 def zc_preamble_host(config: Optional[ZCConfig] = None, root: int = 5) -> np.ndarray:
     """sync::ZCSync::generatePreambleForRoot (src/sync/zc_sync.hpp:133-190), the reference's samples
     (host evaluation; root 5 = DATA frames)."""
