@@ -45,6 +45,7 @@
 #include "ultra/fec.hpp"
 #include "waveform/mc_dpsk_waveform.hpp"
 #include "waveform/ofdm_chirp_waveform.hpp"
+#include "waveform/ofdm_cox_waveform.hpp"
 #endif
 
 namespace ria {
@@ -637,17 +638,119 @@ private:
     std::vector<float> soft_bits_;
 };
 
+// OFDM_COX (ultra::OFDMNvisWaveform, src/waveform/ofdm_cox_waveform.cpp): Schmidl-Cox acquisition instead of the chirp,
+// then the same presynced demodulator.
+//   detectSync -> ria_ofdm_cox_search_sync_batch_host   (OFDMDemodulator::searchForSync, :121-153)
+//   process    -> ria_ofdm_presynced_batch_host         (:160-218)
+// The library covers the modem's 1024-point configuration (ModemConfig defaults / createNvisMode()); the
+// default-constructed 512-point variant is reported as RIA_E_UNSUPPORTED by the calls below.
+class OFDMNvisWaveform : public ultra::OFDMNvisWaveform {
+public:
+    OFDMNvisWaveform() : ultra::OFDMNvisWaveform() { cfg_ = toRiaConfig(getConfig()); }
+    explicit OFDMNvisWaveform(const ultra::ModemConfig& config) : ultra::OFDMNvisWaveform(config) { cfg_ = toRiaConfig(getConfig()); }
+
+    // configure / setTxFrequencyOffset / setUsePilots rebuild the reference's demodulator (initComponents), which also
+    // forgets its noise-floor tracker
+    void configure(ultra::Modulation mod, ultra::CodeRate rate) override {
+        ultra::OFDMNvisWaveform::configure(mod, rate);
+        cfg_ = toRiaConfig(getConfig());
+        noise_floor_ = 0.0f; est_cfo_ = 0.0f; last_snr_ = 0.0f; demod_synced_ = false;
+    }
+    void setTxFrequencyOffset(float cfo_hz) override {
+        ultra::OFDMNvisWaveform::setTxFrequencyOffset(cfo_hz);
+        noise_floor_ = 0.0f; est_cfo_ = 0.0f; last_snr_ = 0.0f; demod_synced_ = false;
+    }
+    void setUsePilots(bool use_pilots) {                                        // not virtual in the reference
+        ultra::OFDMNvisWaveform::setUsePilots(use_pilots);
+        cfg_ = toRiaConfig(getConfig());
+        noise_floor_ = 0.0f; est_cfo_ = 0.0f; last_snr_ = 0.0f; demod_synced_ = false;
+    }
+    void setFrequencyOffset(float cfo_hz) override { cfo_hz_ = est_cfo_ = cfo_hz; }
+    float getFrequencyOffset() const override { return cfo_hz_; }
+
+    bool detectSync(ultra::SampleSpan samples, ultra::SyncResult& result, float threshold = 0.8f) override {
+        ria_sync_result r{};
+        Context& c = Context::instance();
+        c.check(ria_ofdm_cox_search_sync_batch_host(c.get(), &cfg_, samples.data(), static_cast<int64_t>(samples.size()),
+                                                    static_cast<int32_t>(samples.size()), threshold, &noise_floor_, 1, &r));
+        if (!r.detected) return false;                                          // result untouched (:151-152)
+        result.detected = true;
+        result.start_sample = r.start_sample;                                   // first LTS sample
+        result.cfo_hz = r.cfo_hz;
+        result.snr_estimate = 0.0f;
+        result.has_training = true;
+        result.correlation = 0.9f;
+        cfo_hz_ = r.cfo_hz;
+        synced_ = true;
+        training_start_ = static_cast<size_t>(r.start_sample);
+        return true;
+    }
+
+    void setAbsoluteTrainingPosition(size_t pos) override { abs_pos_ = pos; has_abs_pos_ = true; }
+
+    bool process(ultra::SampleSpan samples) override {
+        if (!soft_bits_.empty()) return true;                                   // (:165-167)
+        const size_t ref = has_abs_pos_ ? abs_pos_ : training_start_;
+        float ph = static_cast<float>(-2.0f * 3.14159265358979323846 * cfo_hz_ * ref / cfg_.sample_rate);   // (:176)
+        while (ph > 3.14159265358979323846) ph -= 2.0f * 3.14159265358979323846;
+        while (ph < -3.14159265358979323846) ph += 2.0f * 3.14159265358979323846;
+        est_cfo_ = cfo_hz_;                                                     // setFrequencyOffsetWithPhase
+        if (static_cast<int>(samples.size()) < getSamplesPerSymbol()) return false;
+        demod_synced_ = true;
+        const int n_sym = static_cast<int>(samples.size()) / getSamplesPerSymbol();
+        const int bits = ria_ofdm_data_carriers(&cfg_) * OFDMChirpWaveform::bitsPerCarrier(cfg_.modulation);
+        const int stride = std::max(4, ((n_sym > 2 ? n_sym - 2 : 0) * bits + 3) & ~3);
+        std::vector<float> llr(static_cast<size_t>(stride));
+        int32_t n_llr = 0;
+        float snr = 0, cfo = 0, fad = 0;
+        Context& c = Context::instance();
+        c.check(ria_ofdm_presynced_batch_host(c.get(), &cfg_, samples.data(), static_cast<int64_t>(samples.size()),
+                                              static_cast<int32_t>(samples.size()), &cfo_hz_, &ph, 1, llr.data(),
+                                              static_cast<int32_t>(llr.size()), &n_llr, &snr, &cfo, &fad));
+        est_cfo_ = cfo;
+        last_snr_ = snr;
+        const bool ready = n_llr >= RIA_LDPC_N;
+        if (ready) {
+            llr.resize(static_cast<size_t>(n_llr));
+            soft_bits_ = std::move(llr);
+            cfo_hz_ = cfo;                                                      // CFO feedback (:205-210)
+        }
+        return ready;
+    }
+    std::vector<float> getSoftBits() override { return std::move(soft_bits_); }
+    void reset() override {                                                     // CFO kept (:224-235); the demodulator's is not
+        soft_bits_.clear();
+        synced_ = demod_synced_ = false;
+        training_start_ = 0; has_abs_pos_ = false; abs_pos_ = 0;
+        est_cfo_ = 0.0f;
+    }
+    bool isSynced() const override { return synced_ || demod_synced_; }
+    bool hasData() const override { return !soft_bits_.empty(); }
+    float estimatedSNR() const override { return last_snr_; }
+    float estimatedCFO() const override { return est_cfo_; }
+    std::vector<std::complex<float>> getConstellationSymbols() const override { return {}; }
+
+private:
+    ria_modem_config cfg_{};
+    float cfo_hz_ = 0.0f, est_cfo_ = 0.0f, last_snr_ = 0.0f, noise_floor_ = 0.0f;
+    size_t training_start_ = 0, abs_pos_ = 0;
+    bool has_abs_pos_ = false, synced_ = false, demod_synced_ = false;
+    std::vector<float> soft_bits_;
+};
+
 // What WaveformFactory::create(mode) / create(mode, config) (src/waveform/waveform_factory.cpp:13-61) would
-// return for the two waveforms of the hot path; nullptr for every other mode, like the factory's default branch.
+// return for the three waveforms of the hot path; nullptr for every other mode, like the factory's default branch.
 inline ultra::WaveformPtr createWaveform(ultra::protocol::WaveformMode mode) {
     switch (mode) {
         case ultra::protocol::WaveformMode::OFDM_CHIRP: return std::make_unique<OFDMChirpWaveform>();
         case ultra::protocol::WaveformMode::MC_DPSK: return std::make_unique<MCDPSKWaveform>();
+        case ultra::protocol::WaveformMode::OFDM_COX: return std::make_unique<OFDMNvisWaveform>();
         default: return nullptr;
     }
 }
 inline ultra::WaveformPtr createWaveform(ultra::protocol::WaveformMode mode, const ultra::ModemConfig& config) {
     if (mode == ultra::protocol::WaveformMode::OFDM_CHIRP) return std::make_unique<OFDMChirpWaveform>(config);
+    if (mode == ultra::protocol::WaveformMode::OFDM_COX) return std::make_unique<OFDMNvisWaveform>(config);
     return createWaveform(mode);
 }
 #endif  // RIA_WITH_ULTRA

@@ -85,6 +85,16 @@ def main():
                 ms = timed(lambda: sync.ofdm_data_sync_batch(cfg, win, None, 0.3, ctx))
                 add("ria_ofdm_data_sync_batch_dev  window 8192", 32768, ms, 8192 * 4 + 32, "windows")
                 del rows_sync, win
+                # OFDM_COX acquisition: [2000 quiet][silent symbol][4 STS][2 LTS][data ...] in a 24000-sample window
+                coded = torch.randint(0, 256, (8, 324), dtype=torch.uint8, device=dev)
+                cox = ofdm.ofdm_cox_tx_frames(cfg, coded, ctx)
+                rows_cox = sim.awgn_batch(torch.cat([torch.zeros((8, 2000), device=dev), cox], dim=1)[:, :24000].contiguous(),
+                                          8192, 20.0, seed=4, ctx=ctx)
+                res = sync.results(sync.ofdm_cox_search_sync_batch(cfg, rows_cox, 0.8, None, ctx))
+                ms = timed(lambda: sync.ofdm_cox_search_sync_batch(cfg, rows_cox, 0.8, None, ctx))
+                add(f"ria_ofdm_cox_search_sync_batch_dev  window 24000 ({int(res['detected'].sum())}/8192 found)", 8192, ms,
+                    24000 * 4 + 32, "windows")
+                del rows_cox, cox
             del rx, out
             torch.cuda.empty_cache()
 

@@ -3,7 +3,7 @@
 //
 // Built HERE (where /root/reference exists) by oracle/Makefile into oracle/_ref/waveform_harness from this file,
 // the reference's own headers / objects and libria_b200.so; tests/test_waveform_dropin_gpu.py runs the binary
-// on the B200.  Every waveform is created twice -- ultra::OFDMChirpWaveform / ultra::MCDPSKWaveform and
+// on the B200.  Every waveform is created twice -- ultra::OFDMChirpWaveform / MCDPSKWaveform / OFDMNvisWaveform and
 // ria::createWaveform(mode) -- and driven through the same IWaveform calls a StreamingDecoder makes:
 //   connect frame:   generatePreamble + modulate -> channel -> detectSync -> setFrequencyOffset -> process -> getSoftBits
 //   connected frame: generateDataPreamble + modulate -> channel -> detectDataSync -> process -> getSoftBits
@@ -55,16 +55,16 @@ static void compare_sync(const char* what, bool da, const SyncResult& a, bool db
 }
 
 static void run_frame(const char* what, IWaveform& ref, IWaveform& dut, const Samples& rx, bool data_preamble, int frame_samples,
-                      float known_cfo) {
+                      float known_cfo, float sync_threshold = 0.15f, size_t sync_window = 120000) {
     SyncResult ra, rb;
     bool da, db;
     if (data_preamble) {
         da = ref.detectDataSync(SampleSpan(rx.data(), rx.size()), ra, known_cfo, 0.2f);
         db = dut.detectDataSync(SampleSpan(rx.data(), rx.size()), rb, known_cfo, 0.2f);
     } else {
-        const size_t window = std::min<size_t>(rx.size(), 120000);           // StreamingDecoder's chirp search window
-        da = ref.detectSync(SampleSpan(rx.data(), window), ra, 0.15f);
-        db = dut.detectSync(SampleSpan(rx.data(), window), rb, 0.15f);
+        const size_t window = std::min<size_t>(rx.size(), sync_window);      // default: StreamingDecoder's chirp search window
+        da = ref.detectSync(SampleSpan(rx.data(), window), ra, sync_threshold);
+        db = dut.detectSync(SampleSpan(rx.data(), window), rb, sync_threshold);
     }
     compare_sync(what, da, ra, db, rb);
     if (!da || !db) { CHECK(false, "%s: not detected (ref %d, dut %d)", what, da, db); return; }
@@ -173,6 +173,53 @@ int main() {
             Samples drx = channel(dtx, 400 + 29 * rep, 1200, mc.snr + 4.0f, 400 + rep);
             snprintf(name, sizeof name, "mc_dpsk bits %d zc frame %d", cfg.bits_per_symbol, rep);
             run_frame(name, ref, d, drx, true, static_cast<int>(dtx.size()) - 2512, 0.0f);
+        }
+    }
+    // ---- OFDM-COX (Schmidl-Cox acquisition) ----
+    struct { Modulation mod; CodeRate rate; float snr; } cox_cases[] = {
+        {Modulation::DQPSK, CodeRate::R1_2, 20.0f}, {Modulation::QPSK, CodeRate::R1_2, 22.0f}, {Modulation::QAM16, CodeRate::R3_4, 26.0f}};
+    for (auto& oc : cox_cases) {
+        ModemConfig mcfg;
+        ultra::OFDMNvisWaveform ref(mcfg);
+#ifdef HARNESS_SELFTEST
+        WaveformPtr dut = std::make_unique<ultra::OFDMNvisWaveform>(mcfg);
+#else
+        WaveformPtr dut = ria::createWaveform(protocol::WaveformMode::OFDM_COX, mcfg);
+#endif
+        CHECK(dut != nullptr && dut->getMode() == protocol::WaveformMode::OFDM_COX, "cox factory");
+        ref.configure(oc.mod, oc.rate);
+        dut->configure(oc.mod, oc.rate);
+        CHECK(ref.getSamplesPerSymbol() == dut->getSamplesPerSymbol() && ref.getPreambleSamples() == dut->getPreambleSamples() &&
+              ref.getMinSamplesForFrame() == dut->getMinSamplesForFrame() && ref.getPilotSpacing() == dut->getPilotSpacing(), "cox sizing");
+        Bytes coded(324);
+        for (auto& b : coded) b = static_cast<uint8_t>(rng());
+        char name[96];
+        for (int rep = 0; rep < 4; ++rep) {
+            Samples pre = ref.generatePreamble(), body = ref.modulate(coded);
+            Samples tx = pre;
+            tx.insert(tx.end(), body.begin(), body.end());
+            // LTS + data = everything behind the silent symbol and the four STS
+            const int frame_samples = static_cast<int>(tx.size()) - 5 * ref.getSamplesPerSymbol();
+            Samples rx = channel(tx, 900 + 1337 * rep, 3000, oc.snr, 500 + rep);
+            snprintf(name, sizeof name, "ofdm_cox mod %d frame %d", static_cast<int>(oc.mod), rep);
+            // the same objects see all four frames, so the noise-floor tracker of the search is carried along
+            run_frame(name, ref, *dut, rx, false, frame_samples, 0.0f, 0.8f, 48000);
+        }
+        // noise only: nothing to find, result untouched; noise + a steady tone: whatever the reference makes of it
+        for (int tone = 0; tone < 2; ++tone) {
+            std::mt19937 nrng(77 + tone);
+            std::normal_distribution<float> g(0.0f, 0.1f);
+            Samples noise(30000);
+            for (size_t i = 0; i < noise.size(); ++i) noise[i] = g(nrng) + (tone ? 0.5f * std::sin(0.37f * static_cast<float>(i)) : 0.0f);
+            SyncResult ra, rb;
+            ra.start_sample = rb.start_sample = -7;
+            const bool da = ref.detectSync(SampleSpan(noise.data(), noise.size()), ra, 0.8f);
+            const bool db = dut->detectSync(SampleSpan(noise.data(), noise.size()), rb, 0.8f);
+            CHECK(da == db && ra.start_sample == rb.start_sample && (tone || !da), "cox %s window: %d %d, %d %d",
+                  tone ? "tone" : "noise-only", da, db, ra.start_sample, rb.start_sample);
+            if (da && db) CHECK(ra.cfo_hz == rb.cfo_hz, "cox tone cfo %.6f vs %.6f", ra.cfo_hz, rb.cfo_hz);
+            ref.reset();
+            dut->reset();
         }
     }
 #ifndef HARNESS_SELFTEST
