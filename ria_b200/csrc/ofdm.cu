@@ -172,9 +172,17 @@ struct KernelArgs {
     long long frame_begin, frame_end;   // chunk of the batch this launch covers
 };
 
-// Group of G threads working on one frame: a CTA (G = 128) or a warp (G = 32).
+// Group of G threads working on one frame: a CTA (G = 128), a warp (G = 32) or a half-warp (G = 16: two frames share
+// a warp, each with its own member mask, so that the two halves may sit in different branches).
+template <int G> __device__ __forceinline__ unsigned gmask() {
+    return (G == 16) ? (0xFFFFu << (threadIdx.x & 16)) : 0xffffffffu;
+}
 template <int G> __device__ __forceinline__ void gsync() {
-    if (G == 32) __syncwarp(); else __syncthreads();
+    if (G == 16) __syncwarp(gmask<16>()); else if (G == 32) __syncwarp(); else __syncthreads();
+}
+// value of lane `src` of the group's first warp (G >= 32) / of the half-warp (G = 16)
+template <int G> __device__ __forceinline__ float gshfl(float v, int src) {
+    return __shfl_sync(gmask<G>(), v, src, G < 32 ? G : 32);
 }
 
 // hardDecision, channel_equalizer.cpp:1168-1230
@@ -585,11 +593,11 @@ __device__ __forceinline__ void data_symbol(CarState& cs, const OfdmCarrierTable
         gsync<G>();
         if (g < 32) {       // the group's first warp (all of it)
             const float rs = ordered_sum_rows(red, 5, np, g);
-            cpe_x = __shfl_sync(0xffffffffu, rs, 0);
-            cpe_y = __shfl_sync(0xffffffffu, rs, 1);
-            cpe_w = __shfl_sync(0xffffffffu, rs, 2);
-            const float sp = __shfl_sync(0xffffffffu, rs, 3);
-            float npow = __shfl_sync(0xffffffffu, rs, 4);
+            cpe_x = gshfl<G>(rs, 0);
+            cpe_y = gshfl<G>(rs, 1);
+            cpe_w = gshfl<G>(rs, 2);
+            const float sp = gshfl<G>(rs, 3);
+            float npow = gshfl<G>(rs, 4);
             if (g == 0) {
                 // pilot power and temporal noise count (:778-800)
                 cs.s.signal_power = sp / static_cast<float>(np);
@@ -1350,6 +1358,88 @@ ofdm_carrier_kernel(const KernelArgs a) {
     }
 }
 
+// Two frames per warp (G = 16): 15 pilots fill one pass of a half-warp and 44 data carriers three, against one half-empty
+// and two passes of a whole warp, and the serial sections (ordered sums, phase estimates on the group's first lane) run
+// for two frames at once.  The halves advance in lock step through the frame loop; a half whose frame leaves early
+// (too short, residual-CFO re-run, end of the batch) sits out the rest of the iteration.
+constexpr int kCar2Warps = 2;       // 4 frames per CTA
+
+template <int MOD>
+__global__ void __launch_bounds__(kCar2Warps * 32)
+ofdm_carrier2_kernel(const KernelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CarSmem& sm = *reinterpret_cast<CarSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, g = tid & 15, grp = tid >> 4;
+    if (a.second_pass && *a.rerun_count == 0) return;
+    {
+        const int* src = reinterpret_cast<const int*>(a.car_g);
+        int* dst = reinterpret_cast<int*>(&sm.car);
+        for (int i = tid; i < static_cast<int>(sizeof(OfdmCarrierTable) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const OfdmCarrierTable& car = sm.car;
+    CarState& cs = sm.cs[grp];
+    const int nc = car.num_carriers;
+    const int n_sym = a.frame_len / a.sym_len;
+    const int n_data_sym = n_sym - 2;
+    constexpr int kPer = kMaxCarriers / 16;
+
+    for (;;) {
+        __syncwarp();
+        long long f = -1;
+        if (g == 0) {
+            const long long i = static_cast<long long>(atomicAdd(a.counter, 1u));
+            if (a.second_pass) { if (i < static_cast<long long>(*a.rerun_count)) f = a.frame_begin + a.rerun_list[i]; }
+            else if (a.frame_begin + i < a.frame_end) f = a.frame_begin + i;
+        }
+        f = __shfl_sync(0xffffffffu, f, lane & 16);
+        if (__all_sync(0xffffffffu, f < 0)) break;
+        bool active = f >= 0;
+        if (active && n_sym < 2) { frame_too_short<16>(a, f, g); active = false; }
+        const float2* fb = a.bins + (active ? (f - a.bins_frame0) : 0) * n_sym * nc;
+        if (active) {
+            frame_reset<16>(cs, a, f, g);
+            // ---- LTS: estimateChannelFromLTS (channel_equalizer.cpp:193-643) ----
+            for (int s = 0; s < 2; ++s) {
+                for (int c = g; c < nc; c += 16) cs.bin[c] = fb[s * nc + c];
+                gsync<16>();
+                lts_symbol<16>(cs, car, s, g);
+            }
+            // residual-CFO re-run: the frame goes back to the phase-scan / FFT stages (see ofdm_carrier_kernel)
+            if (!a.second_pass && lts_residual<16>(cs, car, a, g)) {
+                if (g == 0) {
+                    const int fl = static_cast<int>(f - a.frame_begin);
+                    a.rerun_cfo[fl] = cs.s.cfo_hz;
+                    a.rerun_list[atomicAdd(a.rerun_count, 1u)] = fl;
+                }
+                active = false;
+            }
+        }
+        if (active) {
+            lts_finish<16>(cs, car, a, f, g);
+            // ---- data symbols (demodulator.cpp:1361-1382) ----
+            float* llr_out = a.llr + f * a.llr_stride;
+            float2 nb[kPer];
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+                nb[q] = make_float2(0.f, 0.f);
+                if (n_data_sym > 0 && g + 16 * q < nc) nb[q] = fb[2 * nc + g + 16 * q];
+            }
+            for (int sd = 0; sd < n_data_sym; ++sd) {
+#pragma unroll
+                for (int q = 0; q < kPer; ++q) if (g + 16 * q < nc) cs.bin[g + 16 * q] = nb[q];
+                gsync<16>();
+                if (sd + 1 < n_data_sym) {          // prefetch the next symbol's bins
+#pragma unroll
+                    for (int q = 0; q < kPer; ++q) if (g + 16 * q < nc) nb[q] = fb[(3 + sd) * nc + g + 16 * q];
+                }
+                data_symbol<16, MOD>(cs, car, a, llr_out, sd, g);
+            }
+            frame_outputs<16>(cs, car, a, f, n_data_sym, g);
+        }
+    }
+}
+
 // ------------------------------- monolithic kernel -----------------------------------------
 // FFT + carriers of one frame in one CTA.  Serves the frames the carrier kernel handed over
 // (residual CFO re-run); `rerun_list == nullptr` runs every frame of [frame_begin, frame_end).
@@ -1617,7 +1707,21 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
         if (m == 0 || per < fft_per_sm) fft_per_sm = per;
     }
     void (*carrier_kernel)(const KernelArgs) = nullptr;
-    switch (cfg->modulation) {
+    static const bool carrier_g32 = getenv("RIA_CARRIER_G32") != nullptr;      // A/B: one frame per warp
+    const int car_threads = carrier_g32 ? kCarWarps * 32 : kCar2Warps * 32;
+    if (!carrier_g32) switch (cfg->modulation) {
+        case RIA_DBPSK:  carrier_kernel = ofdm_carrier2_kernel<RIA_DBPSK>; break;
+        case RIA_DQPSK:  carrier_kernel = ofdm_carrier2_kernel<RIA_DQPSK>; break;
+        case RIA_D8PSK:  carrier_kernel = ofdm_carrier2_kernel<RIA_D8PSK>; break;
+        case RIA_BPSK:   carrier_kernel = ofdm_carrier2_kernel<RIA_BPSK>; break;
+        case RIA_QPSK:   carrier_kernel = ofdm_carrier2_kernel<RIA_QPSK>; break;
+        case RIA_QAM16:  carrier_kernel = ofdm_carrier2_kernel<RIA_QAM16>; break;
+        case RIA_QAM32:  carrier_kernel = ofdm_carrier2_kernel<RIA_QAM32>; break;
+        case RIA_QAM64:  carrier_kernel = ofdm_carrier2_kernel<RIA_QAM64>; break;
+        case RIA_QAM256: carrier_kernel = ofdm_carrier2_kernel<RIA_QAM256>; break;
+        default: return set_error(ctx, RIA_E_UNSUPPORTED, "ofdm: modulation %u has no demapper", cfg->modulation);
+    }
+    else switch (cfg->modulation) {
         case RIA_DBPSK:  carrier_kernel = ofdm_carrier_kernel<RIA_DBPSK>; break;
         case RIA_DQPSK:  carrier_kernel = ofdm_carrier_kernel<RIA_DQPSK>; break;
         case RIA_D8PSK:  carrier_kernel = ofdm_carrier_kernel<RIA_D8PSK>; break;
@@ -1629,7 +1733,7 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
         case RIA_QAM256: carrier_kernel = ofdm_carrier_kernel<RIA_QAM256>; break;
         default: return set_error(ctx, RIA_E_UNSUPPORTED, "ofdm: modulation %u has no demapper", cfg->modulation);
     }
-    rc = blocks_per_sm(ctx, carrier_kernel, kCarWarps * 32, sizeof(CarSmem), &car_per_sm);
+    rc = blocks_per_sm(ctx, carrier_kernel, car_threads, sizeof(CarSmem), &car_per_sm);
     if (rc != RIA_OK) return rc;
 
     // chunk of frames whose carrier bins live in scratch between the stages
@@ -1680,7 +1784,7 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
             time_end(ctx);
             a.counter = ctr + (pass ? 4 : 1);
             time_begin(ctx, KK_OFDM_CARRIER);
-            carrier_kernel<<<static_cast<unsigned>(car_grid), kCarWarps * 32, sizeof(CarSmem), st>>>(a);
+            carrier_kernel<<<static_cast<unsigned>(car_grid), car_threads, sizeof(CarSmem), st>>>(a);
             time_end(ctx);
             ctx->launches += 2;
         }
