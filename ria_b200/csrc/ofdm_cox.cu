@@ -16,12 +16,12 @@
 // and stops at the first position that passes everything.
 //
 // Which positions are visited depends only on the energies (the skip rule) and everything a candidate goes through
-// is independent of earlier failures, so the batch runs as three launches without host synchronisation:
+// is independent of earlier failures, so the batch runs as two launches without host synchronisation:
 //   cox_scan_kernel    one CTA per window: decimated energies at every multiple of 32, then the noise-floor walk
 //                      (one thread, it is a recurrence) -> list of visited positions + the noise floor at each
-//   cox_corr_kernel    one warp per (window, visited position), dynamic scheduling: the Schmidl-Cox metric
-//   cox_decide_kernel  one CTA per window: first visited position above threshold -> plateau metrics (one warp each)
-//                      -> LTS search (all threads) -> CFO; on failure the next candidate
+//   cox_decide_kernel  one CTA per window: the Schmidl-Cox metric at the visited positions, eight at a time (one
+//                      per warp), until one is above threshold -> plateau metrics (one warp each) -> LTS search
+//                      (all threads) -> CFO; on failure the walk goes on behind the candidate
 // Every sum is accumulated in the reference's order with un-fused fp32 operations and the FFT is the reference's
 // radix-2 (src/dsp/fft.cpp:96-128), so positions and CFO are the reference's bits.
 
@@ -185,8 +185,7 @@ struct CoxArgs {
     float* noise_floor;                 // nullable, in/out per window (Impl::noise_floor_energy)
     float threshold;
     int cp, sym, search_end, corr_window, total_len, max_visit;
-    int* visit_off; float* visit_nf; float* visit_corr; int* n_visit;
-    unsigned long long* counter;
+    int* visit_off; float* visit_nf; int* n_visit;
     const float2* tw; const float2* lts_iq; int tmpl_len; float energy_ref;
     float sample_rate;
     ria_sync_result* out;
@@ -231,33 +230,7 @@ cox_scan_kernel(const CoxArgs a) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// metric at every visited position
-// ---------------------------------------------------------------------------------------------
 constexpr size_t kTileSmem = sizeof(float2) * (kN / 2) + sizeof(WarpTile) * kWarps;
-
-__global__ void __launch_bounds__(kThreads)
-cox_corr_kernel(const CoxArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw = reinterpret_cast<float2*>(smem_raw);
-    WarpTile* tiles = reinterpret_cast<WarpTile*>(smem_raw + sizeof(float2) * (kN / 2));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < kN / 2; i += kThreads) tw[i] = a.tw[i];
-    __syncthreads();
-    const unsigned long long total = static_cast<unsigned long long>(a.n) * a.max_visit;
-    for (;;) {
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(a.counter, 1ull);
-        item = __shfl_sync(kFull, item, 0);
-        if (item >= total) break;
-        const long long w = static_cast<long long>(item / a.max_visit);
-        const int v = static_cast<int>(item - static_cast<unsigned long long>(w) * a.max_visit);
-        if (v >= a.n_visit[w]) continue;
-        const int off = a.visit_off[w * a.max_visit + v];
-        const float c = warp_correlation(a.win + w * a.stride, off, a.cp, tiles[warp], tw, lane);
-        if (lane == 0) a.visit_corr[w * a.max_visit + v] = c;
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // per window: candidates in order -> plateau -> LTS -> CFO
@@ -271,6 +244,7 @@ cox_decide_kernel(const CoxArgs a) {
     unsigned char* region = smem_raw + sizeof(float2) * (kN / 2);
     WarpTile* tiles = reinterpret_cast<WarpTile*>(region);
     __shared__ float pc[kPlateauWindow / 8 + 2];
+    __shared__ float chunk_c[kWarps];
     __shared__ int sh_i[4];
     __shared__ float red_c[kWarps];
     __shared__ int red_o[kWarps];
@@ -283,35 +257,49 @@ cox_decide_kernel(const CoxArgs a) {
     const int n_off = back + fwd + 1;
     // LTS phase aliases the transform tiles: window span, template, correlations
     float* span = reinterpret_cast<float*>(region);
-    float2* tmpl = reinterpret_cast<float2*>(span + ((n_off + a.tmpl_len + 3) & ~3));
+    const int n_off_pad = (n_off + 4 * kThreads - 1) / (4 * kThreads) * (4 * kThreads);
+    float2* tmpl = reinterpret_cast<float2*>(span + ((n_off_pad + a.tmpl_len + 3) & ~3));
     float* lcorr = reinterpret_cast<float*>(tmpl + a.tmpl_len);
 
     for (long long w = blockIdx.x; w < a.n; w += gridDim.x) {
         const float* win = a.win + w * a.stride;
         const int nv = a.n_visit[w];
         const int* voff = a.visit_off + w * a.max_visit;
-        const float* vcorr = a.visit_corr + w * a.max_visit;
         const float* vnf = a.visit_nf + w * (a.max_visit + 1);
         int cursor = 0;
         bool done = false;
         while (!done) {
-            if (tid == 0) {
-                int v = cursor;
-                while (v < nv && !(vcorr[v] > a.threshold)) ++v;
-                sh_i[0] = v;
+            // the metric at the next kWarps visited positions, one per warp; the first one above threshold is the
+            // candidate (positions behind a success are never evaluated, like the reference's break)
+            {
+                const int v = cursor + warp;
+                float c = 0.0f;
+                if (v < nv) c = warp_correlation(win, voff[v], a.cp, tiles[warp], tw, lane);
+                if (lane == 0) chunk_c[warp] = c;
             }
             __syncthreads();
-            const int v = sh_i[0];
-            if (v >= nv) {                                   // nothing (left) above threshold
-                if (tid == 0) {
-                    ria_sync_result r{};
-                    a.out[w] = r;
-                    if (a.noise_floor) a.noise_floor[w] = vnf[nv];
-                }
-                done = true;
-                __syncthreads();
-                break;
+            if (tid == 0) {
+                int hit = -1;
+                for (int k = 0; k < kWarps && cursor + k < nv; ++k)
+                    if (chunk_c[k] > a.threshold) { hit = k; break; }
+                sh_i[0] = hit;
             }
+            __syncthreads();
+            if (sh_i[0] < 0) {
+                cursor += kWarps;
+                if (cursor >= nv) {                          // nothing (left) above threshold
+                    if (tid == 0) {
+                        ria_sync_result r{};
+                        a.out[w] = r;
+                        if (a.noise_floor) a.noise_floor[w] = vnf[nv];
+                    }
+                    done = true;
+                }
+                __syncthreads();
+                continue;
+            }
+            const int v = cursor + sh_i[0];
+            const float v_corr = chunk_c[sh_i[0]];
             const int i0 = voff[v];
             int nj = 0;
             for (int j = 0; j <= kPlateauWindow && i0 + j + a.total_len < a.L; j += 8) ++nj;
@@ -322,7 +310,7 @@ cox_decide_kernel(const CoxArgs a) {
             __syncthreads();
             if (tid == 0) {
                 int plateau = 0, peak_pos = i0;
-                float peak = vcorr[v];
+                float peak = v_corr;
                 for (int q = 0; q < nj; ++q) {
                     const float c = pc[q];
                     if (c >= kPlateauThreshold) ++plateau;
@@ -343,26 +331,36 @@ cox_decide_kernel(const CoxArgs a) {
                     const int base = coarse - back;
                     const int span_len = n_off + a.tmpl_len - 1;
                     __syncthreads();
-                    for (int i = tid; i < span_len; i += kThreads) span[i] = win[base + i];
+                    for (int i = tid; i < n_off_pad + a.tmpl_len; i += kThreads) span[i] = (i < span_len) ? win[base + i] : 0.0f;
                     for (int i = tid; i < a.tmpl_len; i += kThreads) tmpl[i] = a.lts_iq[i];
                     __syncthreads();
                     float my_best = 0.0f; int my_off = 0x7fffffff;
-                    for (int o = tid; o < n_off; o += kThreads) {
-                        float cI = 0.0f, cQ = 0.0f, e = 0.0f;
-                        const float* s = span + o;
-#pragma unroll 4
+                    // four offsets per thread and pass share one template load; each keeps its three sums in the
+                    // reference's order (:420-433).  The span is padded so the loads of idle offsets stay inside it.
+                    for (int o0 = tid; o0 < n_off; o0 += 4 * kThreads) {
+                        float cI[4] = {0.f, 0.f, 0.f, 0.f}, cQ[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
+                        const float* s0 = span + o0;
+#pragma unroll 2
                         for (int i = 0; i < a.tmpl_len; ++i) {
-                            const float r = s[i];
                             const float2 t = tmpl[i];
-                            cI = __fadd_rn(cI, __fmul_rn(r, t.x));
-                            cQ = __fadd_rn(cQ, __fmul_rn(r, t.y));
-                            e = __fadd_rn(e, __fmul_rn(r, r));
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float r = s0[q * kThreads + i];
+                                cI[q] = __fadd_rn(cI[q], __fmul_rn(r, t.x));
+                                cQ[q] = __fadd_rn(cQ[q], __fmul_rn(r, t.y));
+                                e[q] = __fadd_rn(e[q], __fmul_rn(r, r));
+                            }
                         }
-                        const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(cI, cI), __fmul_rn(cQ, cQ)));
-                        const float norm = __fsqrt_rn(__fmul_rn(e, a.energy_ref));
-                        const float c = (norm > 1e-6f) ? __fdiv_rn(mag, norm) : 0.0f;
-                        lcorr[o] = c;
-                        if (c > my_best) { my_best = c; my_off = o; }       // ascending offsets: first maximum wins
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int o = o0 + q * kThreads;
+                            if (o >= n_off) break;
+                            const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(cI[q], cI[q]), __fmul_rn(cQ[q], cQ[q])));
+                            const float norm = __fsqrt_rn(__fmul_rn(e[q], a.energy_ref));
+                            const float c = (norm > 1e-6f) ? __fdiv_rn(mag, norm) : 0.0f;
+                            lcorr[o] = c;
+                            if (c > my_best) { my_best = c; my_off = o; }   // ascending offsets: first maximum wins
+                        }
                     }
                     // arg-max, ties to the earliest offset (strict > in the reference's ascending loop, :436-448)
                     for (int d = 16; d > 0; d >>= 1) {
@@ -544,32 +542,27 @@ extern "C" int ria_ofdm_cox_search_sync_batch_dev(ria_ctx* ctx, const ria_modem_
     const size_t b_off = align256(static_cast<size_t>(n_windows) * a.max_visit * sizeof(int));
     const size_t b_nf = align256(static_cast<size_t>(n_windows) * (a.max_visit + 1) * sizeof(float));
     const size_t b_nv = align256(static_cast<size_t>(n_windows) * sizeof(int));
-    if ((rc = ensure_scratch(ctx, 2 * b_off + b_nf + b_nv + 256)) != RIA_OK) return rc;
+    if ((rc = ensure_scratch(ctx, b_off + b_nf + b_nv + 256)) != RIA_OK) return rc;
     unsigned char* base = static_cast<unsigned char*>(ctx->scratch);
     a.visit_off = reinterpret_cast<int*>(base);
-    a.visit_corr = reinterpret_cast<float*>(base + b_off);
-    a.visit_nf = reinterpret_cast<float*>(base + 2 * b_off);
-    a.n_visit = reinterpret_cast<int*>(base + 2 * b_off + b_nf);
-    a.counter = reinterpret_cast<unsigned long long*>(base + 2 * b_off + b_nf + b_nv);
+    a.visit_nf = reinterpret_cast<float*>(base + b_off);
+    a.n_visit = reinterpret_cast<int*>(base + b_off + b_nf);
     a.tw = ot->twiddle_nat; a.lts_iq = ct->lts_iq; a.tmpl_len = ct->tmpl_len; a.energy_ref = ct->energy_ref;
     a.sample_rate = static_cast<float>(cfg->sample_rate);
     a.out = out_dev;
-    RIA_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), ctx->stream));
 
-    if (!ctx->occ_cache.count(reinterpret_cast<const void*>(cox_corr_kernel))) {
-        RIA_CUDA(ctx, cudaFuncSetAttribute(cox_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTileSmem)));
+    if (!ctx->occ_cache.count(reinterpret_cast<const void*>(cox_decide_kernel))) {
         RIA_CUDA(ctx, cudaFuncSetAttribute(cox_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTileSmem)));
-        ctx->occ_cache[reinterpret_cast<const void*>(cox_corr_kernel)] = 2;
+        ctx->occ_cache[reinterpret_cast<const void*>(cox_decide_kernel)] = 2;
     }
     time_begin(ctx, KK_OFDM_SYNC);
     long long g = std::min<long long>(n_windows, static_cast<long long>(ctx->sm_count) * 8);
     cox_scan_kernel<<<static_cast<unsigned>(g), 128, 0, ctx->stream>>>(a);
-    cox_corr_kernel<<<static_cast<unsigned>(ctx->sm_count * 2), kThreads, kTileSmem, ctx->stream>>>(a);
     g = std::min<long long>(n_windows, static_cast<long long>(ctx->sm_count) * 2);
     cox_decide_kernel<<<static_cast<unsigned>(g), kThreads, kTileSmem, ctx->stream>>>(a);
     time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 3;
+    ctx->launches += 2;
     return RIA_OK;
 }
 
