@@ -546,6 +546,13 @@ int ria_channel_watterson_batch_dev(ria_ctx* ctx, const ria_watterson_config* cf
                                     const float* snr_db_dev, uint64_t seed, int64_t first_frame_id,
                                     int64_t n_frames, float* out_dev, int64_t out_stride);
 
+/* The PING energy test of StreamingDecoder::decodeCurrentFrame (src/gui/modem/streaming_decoder.cpp:1127-1160,
+ * 1219-1229) for a batch of receptions that start at the sync position: RMS of the first training_skip samples
+ * (4608 for MC-DPSK) against the RMS of the <= 5000 samples behind them, sums in sample order.
+ * out_dev [n][4] fp32 = {training_rms, data_rms, ratio (0 when training_rms <= 0.001), is_ping (ratio < 0.6)}. */
+int ria_ping_energy_batch_dev(ria_ctx* ctx, const float* frames_dev, int64_t frame_stride, int32_t frame_len,
+                              int32_t training_skip, int64_t n_frames, float* out_dev);
+
 /* ---- HOST-buffer variants of the synchronisers and the MC-DPSK demodulator --------------------- */
 /* Same arguments as the `_dev` entry points with host pointers (H2D -> `_dev` -> D2H inside the call, which
  * returns when the results are in the caller's buffers).  These are what the batch = 1 IWaveform adapters of

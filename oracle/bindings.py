@@ -71,6 +71,12 @@ class StreamDecodeResult(C.Structure):
                 ("codewords_failed", C.c_int32), ("is_ping", C.c_int32), ("n_bytes", C.c_int32)]
 
 
+class StreamStepResult(C.Structure):
+    """result of one StreamingDecoder::decodeCurrentFrame step (oracle/ref_shim.cpp ref_stream_step)"""
+    _fields_ = [("state", C.c_int32), ("pending_total_cw", C.c_int32), ("has_frame", C.c_int32),
+                ("frame", StreamDecodeResult), ("last_cfo", C.c_float), ("sync_pos", C.c_int32)]
+
+
 class McdpskConfig(C.Structure):
     """Same layout as ria_mcdpsk_config (include/ria_b200.h)."""
     _fields_ = [("sample_rate", C.c_float), ("num_carriers", C.c_uint32), ("freq_low", C.c_float),
@@ -243,6 +249,16 @@ class Ref:
         L.ref_chase_combine.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int)]
         L.ref_chase_combine.restype = C.c_int
         L.ref_ofdm_data_sync.argtypes = [C.POINTER(ModemConfig), _f32p, C.c_int, C.c_float, C.c_float, C.POINTER(SyncResult)]
+        L.ref_stream_setup_ofdm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.ref_stream_setup_mcdpsk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.ref_stream_min_control_samples.argtypes = [C.c_void_p]
+        L.ref_stream_min_control_samples.restype = C.c_int
+        L.ref_stream_step.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
+                                      C.POINTER(StreamStepResult), _u8p, C.c_int]
+        L.ref_stream_encode.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, _f32p, C.c_int]
+        L.ref_stream_encode.restype = C.c_int
+        L.ref_make_ack_frame.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, _u8p, C.c_int]
+        L.ref_make_ack_frame.restype = C.c_int
         L.ref_ofdm_cox_tx_frame.argtypes = [C.POINTER(ModemConfig), _u8p, C.c_int, _f32p, C.c_int]
         L.ref_ofdm_cox_tx_frame.restype = C.c_int
         L.ref_ofdm_cox_search_sync.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.POINTER(C.c_float),
@@ -526,6 +542,42 @@ class Ref:
         self.lib.ref_stream_decode_ofdm_frame(h, soft, len(soft), int(bool(connected)), int(modulation), int(rate),
                                               int(data_carriers), int(bool(use_channel_interleave)), C.byref(res), buf, len(buf))
         return res, bytes(buf[: res.n_bytes])
+
+    def stream_setup_ofdm(self, h, connected: bool, modulation: int, rate: int):
+        self.lib.ref_stream_setup_ofdm(C.c_void_p(h), int(bool(connected)), int(modulation), int(rate))
+
+    def stream_setup_mcdpsk(self, h, connected: bool, carriers: int, modulation: int, rate: int, spreading: int):
+        """spreading: SpreadingMode enum (0 NONE, 1 TIME_2X, 2 TIME_4X)"""
+        self.lib.ref_stream_setup_mcdpsk(C.c_void_p(h), int(bool(connected)), int(carriers), int(modulation), int(rate), int(spreading))
+
+    def stream_min_control_samples(self, h) -> int:
+        return int(self.lib.ref_stream_min_control_samples(C.c_void_p(h)))
+
+    def stream_step(self, h, samples, sync_pos=0, sync_cfo=0.0, sync_snr=10.0, pending_total_cw=0, last_cfo=0.0):
+        """StreamingDecoder::decodeCurrentFrame with the ring buffer holding `samples` and sync found at sync_pos
+        -> (StreamStepResult, frame bytes)"""
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        res = StreamStepResult()
+        buf = np.zeros(1024, np.uint8)
+        self.lib.ref_stream_step(C.c_void_p(h), samples, len(samples), int(sync_pos), float(sync_cfo), float(sync_snr), int(pending_total_cw),
+                                 float(last_cfo), C.byref(res), buf, len(buf))
+        return res, bytes(buf[: res.frame.n_bytes])
+
+    def stream_encode(self, waveform: int, modulation: int, rate: int, kind: int, frame=b"", carriers=10, spreading=0) -> np.ndarray:
+        """StreamingEncoder::encodeFrame (kind 0) / encodeFrameLight (1) / encodePing (2); waveform 1 OFDM_CHIRP, 2 MC_DPSK"""
+        frame = np.ascontiguousarray(np.frombuffer(bytes(frame), dtype=np.uint8)) if len(frame) else np.zeros(1, np.uint8)
+        cap = 400000
+        out = np.zeros(cap, np.float32)
+        n = self.lib.ref_stream_encode(int(waveform), int(carriers), int(spreading), int(modulation), int(rate), int(kind),
+                                       frame, len(frame), out, cap)
+        assert n > 0, n
+        return out[:n].copy()
+
+    def make_ack_frame(self, src: str, dst: str, seq: int, nack=False) -> bytes:
+        out = np.zeros(64, np.uint8)
+        n = self.lib.ref_make_ack_frame(src.encode(), dst.encode(), int(seq), int(bool(nack)), out, len(out))
+        assert n > 0, n
+        return bytes(out[:n])
 
     def encode_frame_with_ldpc(self, frame, rate: int) -> np.ndarray:
         """v2::encodeFrameWithLDPC -> coded bytes [n_cw, 81]"""

@@ -25,7 +25,8 @@
 #include "sim/hf_channel.hpp"
 #include "waveform/ofdm_chirp_waveform.hpp"
 #include "protocol/waveform_selection.hpp"
-#include "gui/modem/streaming_decoder.hpp"   // frame-level decode semantics (private members reached with -fno-access-control)
+#include "gui/modem/streaming_decoder.hpp"
+#include "gui/modem/streaming_encoder.hpp"   // test transmissions exactly as a station sends them   // frame-level decode semantics (private members reached with -fno-access-control)
 
 #include "ria_b200.h"                     // POD config / status structs shared with the product ABI
 
@@ -397,6 +398,122 @@ void ref_stream_decode_ofdm_frame(void* h, const float* soft, int n_soft, int co
     out->is_ping = res.is_ping ? 1 : 0;
     out->n_bytes = static_cast<int32_t>(res.frame_data.size());
     std::memcpy(bytes, res.frame_data.data(), std::min<size_t>(res.frame_data.size(), static_cast<size_t>(cap)));
+}
+
+// One step of the receive state machine: StreamingDecoder::decodeCurrentFrame (:1060-1760) on `samples` placed at the
+// start of the ring buffer as if sync had been found at their first sample (detectSync / detectDataSync having left
+// the waveform with `training_start` / the burst marker is not reproduced: the samples start AT the training
+// symbols at samples[sync_pos]).  The decoder object keeps its mode between calls (ref_stream_setup_*).
+struct ref_stream_step_out {
+    int32_t state;              // DecoderState after the step (0 SEARCHING, 1 SYNC_FOUND, 2 DECODING, 3 BURST_ACCUMULATING)
+    int32_t pending_total_cw;   // escalation request (0 = none)
+    int32_t has_frame;
+    ref_decode_result frame;
+    float last_cfo;
+    int32_t sync_pos;           // sync_position_ after the step (moved by the multi-candidate recovery)
+};
+
+void ref_stream_setup_ofdm(void* h, int connected, int modulation, int rate) {
+    auto* d = static_cast<gui::StreamingDecoder*>(h);
+    ModemConfig cfg;                                            // the modem's configuration: 1024-point FFT, 59 carriers
+    cfg.use_pilots = true;
+    cfg.pilot_spacing = 10;
+    if (connected) d->setConnectedOFDMMode(protocol::WaveformMode::OFDM_CHIRP, cfg, static_cast<Modulation>(modulation),
+                                           static_cast<CodeRate>(rate));
+    else { d->setMode(protocol::WaveformMode::OFDM_CHIRP, false); d->setOFDMConfig(cfg);
+           d->setDataMode(static_cast<Modulation>(modulation), static_cast<CodeRate>(rate)); }
+}
+
+void ref_stream_setup_mcdpsk(void* h, int connected, int carriers, int modulation, int rate, int spreading) {
+    auto* d = static_cast<gui::StreamingDecoder*>(h);
+    d->setMCDPSKCarriers(carriers);
+    d->setSpreadingMode(static_cast<SpreadingMode>(spreading));
+    d->mode_ = protocol::WaveformMode::OFDM_CHIRP;              // force setMode to rebuild the waveform
+    d->setMode(protocol::WaveformMode::MC_DPSK, connected != 0);
+    if (connected) d->setDataMode(static_cast<Modulation>(modulation), static_cast<CodeRate>(rate));
+}
+
+int ref_stream_min_control_samples(void* h) {
+    auto* d = static_cast<gui::StreamingDecoder*>(h);
+    return d->waveform_ ? d->waveform_->getMinSamplesForControlFrame() : 0;
+}
+
+void ref_stream_step(void* h, const float* samples, int n, int sync_pos, float sync_cfo, float sync_snr, int pending_total_cw,
+                     float last_cfo, ref_stream_step_out* out, uint8_t* bytes, int cap) {
+    auto* d = static_cast<gui::StreamingDecoder*>(h);
+    {
+        std::lock_guard<std::mutex> lock(d->buffer_mutex_);
+        if (d->buffer_.size() < gui::StreamingDecoder::MAX_BUFFER_SAMPLES) d->buffer_.assign(gui::StreamingDecoder::MAX_BUFFER_SAMPLES, 0.0f);
+        std::memcpy(d->buffer_.data(), samples, static_cast<size_t>(n) * sizeof(float));
+        d->write_pos_ = static_cast<size_t>(n);
+        d->total_fed_ = static_cast<size_t>(n);
+        d->sync_position_ = static_cast<size_t>(sync_pos);
+        d->correlation_pos_ = static_cast<size_t>(sync_pos);
+    }
+    while (!d->frame_queue_.empty()) d->frame_queue_.pop();
+    d->sync_cfo_ = sync_cfo;
+    d->sync_snr_ = sync_snr;
+    d->last_cfo_.store(last_cfo);
+    d->pending_total_cw_ = pending_total_cw;
+    d->state_ = gui::DecoderState::DECODING;
+    if (d->waveform_) {                                         // what searchForSync leaves behind (:880-897)
+        d->waveform_->reset();
+        d->waveform_->setAbsoluteTrainingPosition(static_cast<size_t>(sync_pos));
+    }
+    d->decodeCurrentFrame();
+    out->sync_pos = static_cast<int32_t>(d->sync_position_);
+    out->state = static_cast<int32_t>(d->state_);
+    out->pending_total_cw = d->pending_total_cw_;
+    out->last_cfo = d->last_cfo_.load();
+    out->has_frame = d->frame_queue_.empty() ? 0 : 1;
+    std::memset(&out->frame, 0, sizeof out->frame);
+    if (out->has_frame) {
+        auto res = d->frame_queue_.front();
+        out->frame.success = res.success ? 1 : 0;
+        out->frame.frame_type = static_cast<int32_t>(res.frame_type);
+        out->frame.codewords_ok = res.codewords_ok;
+        out->frame.codewords_failed = res.codewords_failed;
+        out->frame.is_ping = res.is_ping ? 1 : 0;
+        out->frame.n_bytes = static_cast<int32_t>(res.frame_data.size());
+        std::memcpy(bytes, res.frame_data.data(), std::min<size_t>(res.frame_data.size(), static_cast<size_t>(cap)));
+    }
+}
+
+// v2::ControlFrame::makeAck / makeNack(...).serialize(): 20-byte control frames (frame_v2.cpp)
+int ref_make_ack_frame(const char* src, const char* dst, int seq, int nack, uint8_t* out, int cap) {
+    auto f = nack ? protocol::v2::ControlFrame::makeNack(src, dst, static_cast<uint16_t>(seq), 0)
+                  : protocol::v2::ControlFrame::makeAck(src, dst, static_cast<uint16_t>(seq));
+    Bytes b = f.serialize();
+    if (static_cast<int>(b.size()) > cap) return -static_cast<int>(b.size());
+    std::memcpy(out, b.data(), b.size());
+    return static_cast<int>(b.size());
+}
+
+// StreamingEncoder::encodeFrame / encodeFrameLight / encodePing (src/gui/modem/streaming_encoder.cpp:209-300, 392-430):
+// what a station transmits for one frame.  waveform 1 = OFDM_CHIRP (modem configuration), 2 = MC_DPSK.
+// kind 0 = full preamble, 1 = light (connected-mode) preamble, 2 = PING (frame ignored).
+int ref_stream_encode(int waveform, int carriers, int spreading, int modulation, int rate, int kind,
+                      const uint8_t* frame, int len, float* out, int cap) {
+    gui::StreamingEncoder enc;
+    if (waveform == 1) {
+        enc.setMode(protocol::WaveformMode::OFDM_CHIRP);
+        ModemConfig cfg;                                        // the modem's configuration; pilots on, as the engine sets it
+        cfg.use_pilots = true;
+        cfg.pilot_spacing = 10;
+        enc.setOFDMConfig(cfg);
+        enc.setDataMode(Modulation::QPSK, CodeRate::R1_2);      // setDataMode returns early when nothing changes: move off the target first
+    } else {
+        enc.setMCDPSKCarriers(carriers);
+        enc.setSpreadingMode(static_cast<SpreadingMode>(spreading));
+        enc.setMode(protocol::WaveformMode::MC_DPSK);
+    }
+    enc.setDataMode(static_cast<Modulation>(modulation), static_cast<CodeRate>(rate));
+    Bytes f(frame, frame + len);
+    std::vector<float> s = kind == 2 ? enc.encodePing() : kind == 1 ? enc.encodeFrameLight(f) : enc.encodeFrame(f);
+    const int n = static_cast<int>(s.size());
+    if (n > cap) return -n;
+    std::memcpy(out, s.data(), s.size() * sizeof(float));
+    return n;
 }
 
 // v2::encodeFrameWithLDPC(frame_data, rate): CW0 = first bytes of the frame, CW1+ carry [0xD5][index][payload]

@@ -13,5 +13,6 @@ from . import sync  # noqa: F401
 from . import dist  # noqa: F401
 from . import selection  # noqa: F401
 from . import txsynth  # noqa: F401
+from . import stream  # noqa: F401
 
-__all__ = ["Context", "RiaError", "LIB_PATH", "exported_symbols", "lib", "fec", "ofdm", "mcdpsk", "sim", "sync", "dist", "selection", "txsynth"]
+__all__ = ["Context", "RiaError", "LIB_PATH", "exported_symbols", "lib", "fec", "ofdm", "mcdpsk", "sim", "sync", "dist", "selection", "txsynth", "stream"]

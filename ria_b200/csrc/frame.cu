@@ -445,3 +445,79 @@ extern "C" int ria_ofdm_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg
     RIA_CUDA(ctx, cudaStreamSynchronize(s));
     return RIA_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// PING energy test of StreamingDecoder::decodeCurrentFrame (src/gui/modem/streaming_decoder.cpp:1127-1160, 1219-1229)
+// ---------------------------------------------------------------------------------------------
+namespace ria {
+namespace {
+
+// One warp per frame: the samples are squared by all lanes (the product is exact per sample) and summed in sample order:
+// lane 0 walks the training region, lane 1 the data region behind it, both out of a shared staging tile.
+constexpr int kPingWarps = 4;
+constexpr int kPingTile = 1024;
+
+__global__ void __launch_bounds__(kPingWarps * 32)
+ping_energy_kernel(const float* __restrict__ frames, long long stride, int frame_len, int training_skip, long long n,
+                   float* __restrict__ out) {
+    __shared__ __align__(16) float tile[kPingWarps][kPingTile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* t = tile[warp];
+    for (long long f = static_cast<long long>(blockIdx.x) * kPingWarps + warp; f < n; f += static_cast<long long>(gridDim.x) * kPingWarps) {
+        const float* x = frames + f * stride;
+        const int train_len = min(training_skip, frame_len);
+        const int check_len = min(frame_len - train_len, 5000);
+        float sums[2] = {0.0f, 0.0f};
+        for (int region = 0; region < 2; ++region) {
+            const int base = region ? train_len : 0;
+            const int len = region ? check_len : train_len;
+            float acc = 0.0f;
+            for (int o = 0; o < len; o += kPingTile) {
+                const int m = min(kPingTile, len - o);
+                for (int i = lane; i < m; i += 32) { const float v = x[base + o + i]; t[i] = __fmul_rn(v, v); }
+                __syncwarp();
+                if (lane == 0) {
+                    int i = 0;
+                    for (; i + 4 <= m; i += 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(t + i);
+                        acc = __fadd_rn(acc, q.x); acc = __fadd_rn(acc, q.y); acc = __fadd_rn(acc, q.z); acc = __fadd_rn(acc, q.w);
+                    }
+                    for (; i < m; ++i) acc = __fadd_rn(acc, t[i]);
+                }
+                __syncwarp();
+            }
+            sums[region] = acc;
+        }
+        if (lane == 0) {
+            const float training_rms = train_len > 0 ? __fsqrt_rn(__fdiv_rn(sums[0], static_cast<float>(train_len))) : 0.0f;
+            const float rms = check_len > 0 ? __fsqrt_rn(__fdiv_rn(sums[1], static_cast<float>(check_len))) : 0.0f;
+            const float ratio = (training_rms > 0.001f) ? __fdiv_rn(rms, training_rms) : 0.0f;
+            float4 r = make_float4(training_rms, rms, ratio, ratio < 0.6f ? 1.0f : 0.0f);
+            *reinterpret_cast<float4*>(out + f * 4) = r;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace ria
+
+extern "C" int ria_ping_energy_batch_dev(ria_ctx* ctx, const float* frames_dev, int64_t frame_stride, int32_t frame_len,
+                                         int32_t training_skip, int64_t n_frames, float* out_dev) {
+    using namespace ria;
+    if (!ctx) return RIA_E_INVAL;
+    if (n_frames < 0 || frame_len < 0 || frame_stride < frame_len || training_skip < 0)
+        return set_error(ctx, RIA_E_INVAL, "ping energy: bad sizes");
+    if (n_frames == 0) return RIA_OK;
+    if (!frames_dev || !out_dev) return set_error(ctx, RIA_E_INVAL, "ping energy: null buffer");
+    if (reinterpret_cast<uintptr_t>(out_dev) & 15) return set_error(ctx, RIA_E_INVAL, "ping energy: output must be 16-byte aligned");
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    long long grid = (n_frames + kPingWarps - 1) / kPingWarps;
+    const long long cap = static_cast<long long>(ctx->sm_count) * 8;
+    if (grid > cap) grid = cap;
+    ping_energy_kernel<<<static_cast<unsigned>(grid), kPingWarps * 32, 0, ctx->stream>>>(frames_dev, frame_stride, frame_len,
+                                                                                          training_skip, n_frames, out_dev);
+    RIA_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return RIA_OK;
+}

@@ -1,0 +1,350 @@
+"""One step of the reference's receive state machine for a batch of receptions:
+StreamingDecoder::decodeCurrentFrame (src/gui/modem/streaming_decoder.cpp:1060-2125).
+
+The reference runs this once sync has been found and enough samples have arrived: it copies a control-sized (or, after
+an escalation, an exactly sized) frame from its ring buffer, classifies it (PING energy test, control-first peek),
+demodulates, peeks at codeword 0, either asks for more samples (`pending_total_cw`) or decodes the frame, and falls back
+on a few recovery steps when the decode fails.  Here the same decisions are taken for many receptions at once: every
+demodulation and every LDPC decode is a device launch over the receptions that reach the step, the branching between
+the steps is host logic like the reference's.  A reception is a window of samples plus the sync position inside it; the
+caller repeats the step with the returned `pending_total_cw` when the state says SYNC_FOUND, exactly as
+checkIfReadyToDecode hands the frame back to decodeCurrentFrame.
+
+Built: the connected OFDM_CHIRP branch complete (control-first peek at the DQPSK R1/4 profile, CFO feedback with the 2 Hz
+drift clamp, the R1/4 / data-rate codeword-0 peek, QAM partial-frame escalation, decodeFrame, small-frame recovery, the
+multi-candidate light-sync recovery) and the PING energy test a disconnected receiver classifies chirp-only
+transmissions with (`ping_energy_batch`).  Not built: CSS frame typing, the MC-DPSK handshake rules around the
+codeword-0 peek with their retries at the alternate modulation / neighbouring sync offsets (:1443-1795; the decode
+itself is `mcdpsk.McdpskFrameDecoder`) and the burst-group accumulation state.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ._lib import Context, RiaError, lib
+from . import fec, ofdm
+from .mcdpsk import _CONTROL_TYPES, _crc16_rows
+
+SEARCHING, SYNC_FOUND, DECODING, BURST_ACCUMULATING = 0, 1, 2, 3
+LDPC_BLOCK = 648
+R1_4 = 0
+
+
+def _parse_header(d0: np.ndarray):
+    """v2::parseHeader on rows of >= 20 codeword-0 bytes -> (valid, type, total_cw)"""
+    ftype = d0[:, 2].astype(np.int32)
+    is_control = np.isin(ftype, _CONTROL_TYPES)
+    crc_ctl = _crc16_rows(d0[:, :18]) == ((d0[:, 18].astype(np.uint16) << 8) | d0[:, 19])
+    crc_dat = _crc16_rows(d0[:, :15]) == ((d0[:, 15].astype(np.uint16) << 8) | d0[:, 16])
+    valid = (d0[:, 0] == 0x55) & (d0[:, 1] == 0x4C) & np.where(is_control, crc_ctl, crc_dat)
+    total_cw = np.where(is_control, 1, d0[:, 12].astype(np.int32))
+    return valid, ftype, total_cw, is_control
+
+
+def _initial_phase(cfo_hz: np.ndarray, ref_sample: np.ndarray, sample_rate: float) -> np.ndarray:
+    """OFDMChirpWaveform::process (ofdm_chirp_waveform.cpp:402-411): a double expression rounded to float, then wrapped
+    to [-pi, pi] in double steps rounded to float"""
+    out = np.zeros(len(cfo_hz), np.float32)
+    for i in range(len(cfo_hz)):
+        p = np.float32(-2.0 * np.pi * float(cfo_hz[i]) * float(ref_sample[i]) / float(sample_rate))
+        while float(p) > np.pi:
+            p = np.float32(float(p) - 2.0 * np.pi)
+        while float(p) < -np.pi:
+            p = np.float32(float(p) + 2.0 * np.pi)
+        out[i] = p
+    return out
+
+
+class OfdmConnectedStep:
+    """decodeCurrentFrame for connected OFDM_CHIRP receivers that run `modulation` / `rate` as their data profile."""
+
+    def __init__(self, modulation: int, rate: int, ctx: Optional[Context] = None):
+        self.ctx = ctx
+        self.modulation, self.rate = int(modulation), int(rate)
+        self.cfg = ofdm.ModemConfig.for_waveform(modulation, rate)                 # waveform_->configure(mod, rate)
+        self.cfg_ctl = ofdm.ModemConfig.for_waveform(ofdm.DQPSK, R1_4)             # the control profile (:1281-1283)
+        self.dem = ofdm.OFDMDemodulator(self.cfg, ctx)
+        self.dem_ctl = ofdm.OFDMDemodulator(self.cfg_ctl, ctx)
+        self.sym = self.cfg.getSymbolDuration()
+        self.data_carriers = self.cfg.getDataCarriers()
+        self.bits_per_symbol = self.data_carriers * ofdm.getBitsPerSymbol(modulation)
+        self.decoder = ofdm.OfdmFrameDecoder(modulation, rate, self.data_carriers, connected=True,
+                                             use_channel_interleave=True, ctx=ctx)
+        self.robust_r14 = fec.LDPCDecoder(R1_4, ctx)
+        self.robust_rate = fec.LDPCDecoder(rate, ctx)
+        self.bpc = fec.code_params(rate)[0] // 8
+
+    # ---- sizing (ofdm_chirp_waveform.cpp getMinSamplesForCWCount; streaming_decoder.cpp:42-68) ----
+    def samples_for_cw(self, n_cw: int) -> int:
+        data_symbols = (n_cw * LDPC_BLOCK + self.bits_per_symbol - 1) // self.bits_per_symbol
+        return (2 + data_symbols) * self.sym
+
+    def control_samples(self) -> int:
+        default = self.samples_for_cw(1)
+        if self.modulation == ofdm.DQPSK and self.rate == R1_4:
+            return default
+        carriers = int(self.cfg.num_carriers)
+        pilot_count = (carriers + 10 - 1) // 10
+        bits = max(1, carriers - pilot_count) * 2
+        return max(default, (2 + (LDPC_BLOCK + bits - 1) // bits) * self.sym)
+
+    # ---- waveform_->setFrequencyOffset(cfo); waveform_->process(frame) for a subset ----
+    def _process(self, dem, window, idx, pos, length, cfo):
+        """-> (ready bool[m], soft (CUDA [m, stride]), n_soft int[m], cfo_out f32[m], fading f32[m])"""
+        m = len(idx)
+        dev = window.device
+        L = window.shape[1]
+        ready = np.zeros(m, bool)
+        n_soft = np.zeros(m, np.int32)
+        cfo_out = cfo.astype(np.float32).copy()
+        fading = np.zeros(m, np.float32)
+        soft = None
+        lens = np.minimum(length, L - pos)
+        for ln in np.unique(lens):
+            sel = np.nonzero(lens == ln)[0]
+            if ln < self.sym:
+                continue                                                       # process() returns false (:463 of the adapter)
+            rows = torch.from_numpy(idx[sel]).to(dev)
+            cols = torch.from_numpy(pos[sel].astype(np.int64)).to(dev)[:, None] + torch.arange(int(ln), device=dev)[None, :]
+            frames = torch.gather(window.index_select(0, rows), 1, cols)
+            phase = _initial_phase(cfo[sel], pos[sel], float(dem.config.sample_rate))
+            out = dem.process_presynced_batch(frames, torch.from_numpy(cfo[sel].astype(np.float32)).to(dev),
+                                              torch.from_numpy(phase).to(dev))
+            ns = out["n_llr"].cpu().numpy()
+            if soft is None or soft.shape[1] < out["llr"].shape[1]:
+                grown = torch.zeros((m, out["llr"].shape[1]), dtype=torch.float32, device=dev)
+                if soft is not None:
+                    grown[:, : soft.shape[1]] = soft
+                soft = grown
+            soft[torch.from_numpy(sel).to(dev), : out["llr"].shape[1]] = out["llr"]
+            n_soft[sel] = ns
+            ready[sel] = ns >= LDPC_BLOCK
+            cfo_out[sel] = out["cfo"].cpu().numpy()
+            fading[sel] = out["fading"].cpu().numpy()
+        if soft is None:
+            soft = torch.zeros((m, 4), dtype=torch.float32, device=dev)
+        return ready, soft, n_soft, cfo_out, fading
+
+    def _robust_cw0(self, dec, soft):
+        info, ok, _, _ = dec.robust_decode_batch(soft[:, :LDPC_BLOCK].contiguous(), info_stride=64)
+        return info.cpu().numpy(), ok.cpu().numpy().astype(bool)
+
+    def _decode_frame(self, soft, n_soft):
+        """decodeFrame on receptions whose soft-bit counts may differ: grouped by count"""
+        m = soft.shape[0]
+        res = None
+        for ns in np.unique(n_soft):
+            sel = np.nonzero(n_soft == ns)[0]
+            r = self.decoder.decode_batch(soft.index_select(0, torch.from_numpy(sel).to(soft.device))[:, : int(ns)].contiguous())
+            if res is None:
+                res = {k: (np.zeros((m,) + v.shape[1:], v.dtype) if k != "frame" else np.zeros((m, 1024), np.uint8)) for k, v in r.items()}
+            for k, v in r.items():
+                if k == "frame":
+                    res[k][sel, : v.shape[1]] = v
+                else:
+                    res[k][sel] = v
+        return res
+
+    def step(self, window: torch.Tensor, sync_pos, sync_cfo, last_cfo, pending_total_cw=None):
+        """window: CUDA fp32 [n, L]; sync_pos int[n] (first LTS sample); sync_cfo / last_cfo f32[n] (sync_cfo_ / last_cfo_
+        of each receiver); pending_total_cw int[n] (0 = first pass).  Returns numpy arrays: state, pending_total_cw,
+        has_frame, success, frame_type, codewords_ok, codewords_failed, frame_len, frame u8[n, 1024], last_cfo, sync_pos,
+        consumed_len."""
+        if not (isinstance(window, torch.Tensor) and window.is_cuda and window.dtype == torch.float32 and window.dim() == 2):
+            raise RiaError("step wants CUDA fp32 [n, L] windows (no CPU fallback)")
+        n, L = window.shape
+        sync_pos = np.asarray(sync_pos, np.int64).copy()
+        sync_cfo = np.asarray(sync_cfo, np.float32).copy()
+        last_cfo = np.asarray(last_cfo, np.float32).copy()
+        pending = np.zeros(n, np.int32) if pending_total_cw is None else np.asarray(pending_total_cw, np.int32).copy()
+        out = dict(state=np.full(n, SEARCHING, np.int32), pending_total_cw=pending.copy(), has_frame=np.zeros(n, np.uint8),
+                   success=np.zeros(n, np.uint8), frame_type=np.zeros(n, np.int32), codewords_ok=np.zeros(n, np.int32),
+                   codewords_failed=np.zeros(n, np.int32), frame_len=np.zeros(n, np.int32),
+                   frame=np.zeros((n, 1024), np.uint8), last_cfo=last_cfo, sync_pos=sync_pos,
+                   consumed_len=np.zeros(n, np.int64))
+        ctl_len = self.control_samples()
+        frame_len = np.where(pending > 0, [self.samples_for_cw(int(p)) if p > 0 else 0 for p in pending], ctl_len).astype(np.int64)
+        frame_len = np.minimum(frame_len, L - sync_pos)
+        out["consumed_len"][:] = frame_len
+        alive = frame_len > 0                                                  # empty frame buffer -> SEARCHING (:1118-1125)
+        all_idx = np.arange(n)
+
+        def finish(idx, res_rows, res):
+            """queue the DecodeResult rows `res_rows` of `res` for receptions idx"""
+            for k in ("success", "frame_type", "codewords_ok", "codewords_failed", "frame_len"):
+                out[k][idx] = res[k][res_rows]
+            out["frame"][idx] = res["frame"][res_rows]
+            out["has_frame"][idx] = (res["success"][res_rows] != 0) | (res["codewords_ok"][res_rows] > 0)
+
+        # ---- control-first hypothesis (:1271-1344) ----
+        peek = np.nonzero(alive & (pending == 0) & (frame_len <= ctl_len))[0]
+        if len(peek):
+            ready, soft, n_soft, _, _ = self._process(self.dem_ctl, window, peek, sync_pos[peek], frame_len[peek], sync_cfo[peek])
+            cand = np.nonzero(ready)[0]
+            if len(cand):
+                info, ok = self._robust_cw0(self.robust_r14, soft.index_select(0, torch.from_numpy(cand).to(window.device)))
+                d = info[:, :20].copy()
+                valid, ftype, total_cw, is_ctl = _parse_header(d)
+                hit = np.nonzero(ok & valid & (total_cw == 1) & is_ctl)[0]
+                g = peek[cand[hit]]
+                out["success"][g] = 1
+                out["has_frame"][g] = 1
+                out["frame_type"][g] = ftype[hit]
+                out["codewords_ok"][g] = 1
+                out["frame_len"][g] = 20
+                out["frame"][g, :20] = d[hit]
+                alive[g] = False
+        # ---- data profile (:1346-1378) ----
+        idx = np.nonzero(alive)[0]
+        if len(idx) == 0:
+            return out
+        ready, soft, n_soft, cfo_est, _ = self._process(self.dem, window, idx, sync_pos[idx], frame_len[idx], sync_cfo[idx])
+        # process() failed / no soft bits -> back to SEARCHING without a frame
+        keep = np.nonzero(ready)[0]
+        idx, soft, n_soft, cfo_est = idx[keep], soft.index_select(0, torch.from_numpy(keep).to(window.device)), n_soft[keep], cfo_est[keep]
+        if len(idx) == 0:
+            return out
+        # ---- pilot-corrected CFO feedback, drift clamped to 2 Hz while connected (:1411-1434) ----
+        cur = last_cfo[idx]
+        drift = (cfo_est - cur).astype(np.float32)
+        clamp = np.abs(drift) > np.float32(2.0)
+        corrected = np.where(clamp, (cur + np.copysign(np.float32(2.0), drift)).astype(np.float32), cfo_est).astype(np.float32)
+        last_cfo[idx] = corrected
+        sync_cfo[idx] = corrected
+        # ---- codeword-0 peek on a one-codeword buffer (:1505-1572) ----
+        go = np.ones(len(idx), bool)                                            # receptions that reach decodeFrame
+        one = np.nonzero((pending[idx] == 0) & (n_soft >= LDPC_BLOCK) & (n_soft < 2 * LDPC_BLOCK))[0]
+        if len(one):
+            sub = soft.index_select(0, torch.from_numpy(one).to(window.device))
+            info, ok = self._robust_cw0(self.robust_r14, sub)
+            d = info[:, :20].copy()
+            valid, _, total_cw, _ = _parse_header(d)
+            magic = ok & (d[:, 0] == 0x55) & (d[:, 1] == 0x4C)
+            fell = magic & valid & (total_cw == 1)
+            esc = magic & valid & (total_cw > 1)
+            new_pending = np.where(esc, total_cw, 0).astype(np.int32)
+            unresolved = ~fell & ~esc
+            if self.rate != R1_4 and unresolved.any():
+                u = np.nonzero(unresolved)[0]
+                info2, ok2 = self._robust_cw0(self.robust_rate, sub.index_select(0, torch.from_numpy(u).to(window.device)))
+                d2 = info2[:, : max(self.bpc, 20)].copy()
+                d2[:, self.bpc:] = 0
+                v2_, _, t2, _ = _parse_header(d2)
+                m2 = ok2 & (d2[:, 0] == 0x55) & (d2[:, 1] == 0x4C)
+                fell[u] = m2 & v2_ & (t2 == 1)
+                new_pending[u] = np.where(m2 & v2_ & (t2 > 1), t2, np.where(m2 & ~(v2_ & (t2 == 1)), 4, 0))
+                # decode failed at both rates -> four codewords (:1566-1571)
+                new_pending[u] = np.where(~m2, 4, new_pending[u])
+            else:
+                new_pending = np.where(unresolved, 4, new_pending).astype(np.int32)
+            escal = ~fell
+            g = idx[one[escal]]
+            out["state"][g] = SYNC_FOUND
+            out["pending_total_cw"][g] = new_pending[escal]
+            go[one[escal]] = False
+        # ---- QAM partial frame (:1580-1596) ----
+        if self.modulation in (ofdm.QAM16, ofdm.QAM32, ofdm.QAM64, ofdm.QAM256):
+            part = go & (pending[idx] == 0) & (n_soft >= 2 * LDPC_BLOCK) & (n_soft < 4 * LDPC_BLOCK)
+            g = idx[part]
+            out["state"][g] = SYNC_FOUND
+            out["pending_total_cw"][g] = 4
+            go &= ~part
+        sel = np.nonzero(go)[0]
+        if len(sel) == 0:
+            return out
+        idx, n_soft = idx[sel], n_soft[sel]
+        soft = soft.index_select(0, torch.from_numpy(sel).to(window.device))
+        res = self._decode_frame(soft, n_soft)
+        finish(idx, np.arange(len(idx)), res)
+        # ---- small-frame recovery (:1803-1852) ----
+        failed = np.nonzero(res["success"] == 0)[0]
+        one_cw = self.samples_for_cw(1)
+        failed = failed[frame_len[idx[failed]] >= one_cw]
+        if len(failed):
+            g = idx[failed]
+            rdy, sbits, ns, _, _ = self._process(self.dem, window, g, sync_pos[g], np.full(len(g), one_cw, np.int64), sync_cfo[g])
+            todo = np.nonzero(ns >= LDPC_BLOCK)[0]
+            for dec, bpc in ((self.robust_r14, 20), (self.robust_rate, self.bpc)):
+                if len(todo) == 0 or (dec is self.robust_rate and self.rate == R1_4):
+                    break
+                sub = sbits.index_select(0, torch.from_numpy(todo).to(window.device))
+                info, ok = self._robust_cw0(dec, sub)
+                d = info[:, : max(bpc, 20)].copy()
+                d[:, bpc:] = 0
+                valid, _, total_cw, _ = _parse_header(d)
+                magic = ok & (d[:, 0] == 0x55) & (d[:, 1] == 0x4C)
+                single = np.nonzero(magic & valid & (total_cw == 1))[0]
+                if len(single):
+                    r1 = self._decode_frame(sub.index_select(0, torch.from_numpy(single).to(window.device)), ns[todo[single]])
+                    finish(g[todo[single]], np.arange(len(single)), r1)
+                    out["consumed_len"][g[todo[single]]] = one_cw
+                multi = np.nonzero(magic & valid & (total_cw > 1) & (total_cw < 4))[0]
+                for j in multi:                                                # 2-3 codeword frames: reprocess at the exact size
+                    gi = g[todo[j]: todo[j] + 1]
+                    exact = min(self.samples_for_cw(int(total_cw[j])), int(frame_len[gi[0]]))
+                    _, sb, nsb, _, _ = self._process(self.dem, window, gi, sync_pos[gi], np.array([exact], np.int64), sync_cfo[gi])
+                    r2 = self._decode_frame(sb, nsb)
+                    finish(gi, np.arange(1), r2)
+                    out["consumed_len"][gi] = exact
+                handled = np.zeros(len(todo), bool)
+                handled[single] = True
+                handled[multi] = True
+                todo = todo[~handled]
+        # ---- multi-candidate light-sync recovery (:1859-1962) ----
+        retry = idx[(out["success"][idx] == 0) & (out["codewords_ok"][idx] == 0)]
+        for delta in (8, -8, 16, -16, 24, -24, 32, -32):
+            if len(retry) == 0:
+                break
+            pos = sync_pos[retry] + delta
+            ok_pos = (pos >= 0) & (pos < L)
+            cand = retry[ok_pos]
+            if len(cand) == 0:
+                continue
+            ln = np.minimum(out["consumed_len"][cand], L - pos[ok_pos])
+            rdy, sb, nsb, cfo_r, _ = self._process(self.dem, window, cand, pos[ok_pos], ln, sync_cfo[cand])
+            use = np.nonzero(rdy & (nsb > 0))[0]
+            if len(use) == 0:
+                continue
+            r3 = self._decode_frame(sb.index_select(0, torch.from_numpy(use).to(window.device)), nsb[use])
+            good = np.nonzero((r3["success"] != 0) | (r3["codewords_ok"] > 0))[0]
+            if len(good) == 0:
+                continue
+            g = cand[use[good]]
+            finish(g, good, r3)
+            cur = last_cfo[g]
+            est = cfo_r[use[good]]
+            drift = (est - cur).astype(np.float32)
+            clamp = np.abs(drift) > np.float32(2.0)
+            corrected = np.where(clamp, (cur + np.copysign(np.float32(2.0), drift)).astype(np.float32), est).astype(np.float32)
+            last_cfo[g] = corrected
+            sync_pos[g] = pos[ok_pos][use[good]]
+            out["consumed_len"][g] = ln[use[good]]
+            retry = np.setdiff1d(retry, g)
+        return out
+
+
+def ping_energy_batch(frames: torch.Tensor, training_skip: int = 4608, ctx: Optional[Context] = None) -> np.ndarray:
+    """The legacy PING test of decodeCurrentFrame (:1127-1160, 1219-1229) for a batch: frames CUDA fp32 [n, frame_len]
+    start at the sync position; RMS of the first `training_skip` samples (4608 for MC-DPSK: training + reference
+    symbols; the light-preamble length for OFDM) against the RMS of the <= 5000 samples behind them, both sums in the
+    reference's sample order.  Returns a structured array (training_rms, data_rms, ratio, is_ping): a ratio under 0.6
+    means the transmission ends with the preamble (PING / PONG)."""
+    if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype == torch.float32 and frames.dim() == 2):
+        raise RiaError("ping_energy_batch wants CUDA fp32 [n, frame_len] (no CPU fallback)")
+    frames = frames if frames.stride(1) == 1 else frames.contiguous()
+    n, flen = frames.shape
+    from .fec import default_context
+    ctx = ctx or default_context()
+    out = torch.empty((n, 4), dtype=torch.float32, device=frames.device)
+    ctx.set_stream(torch.cuda.current_stream(frames.device))
+    ctx.check(lib().ria_ping_energy_batch_dev(ctx.handle, C.c_void_p(frames.data_ptr()), frames.stride(0), flen,
+                                              int(training_skip), n, C.c_void_p(out.data_ptr())))
+    o = out.cpu().numpy()
+    res = np.zeros(n, dtype=[("training_rms", np.float32), ("data_rms", np.float32), ("ratio", np.float32), ("is_ping", np.uint8)])
+    res["training_rms"], res["data_rms"], res["ratio"] = o[:, 0], o[:, 1], o[:, 2]
+    res["is_ping"] = o[:, 3] != 0
+    return res
