@@ -257,6 +257,11 @@ class Ref:
                                       C.POINTER(StreamStepResult), _u8p, C.c_int]
         L.ref_stream_encode.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, _f32p, C.c_int]
         L.ref_stream_encode.restype = C.c_int
+        L.ref_stream_encode_burst.argtypes = [C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, _f32p, C.c_int]
+        L.ref_stream_encode_burst.restype = C.c_int
+        L.ref_stream_burst_group.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
+                                             C.POINTER(StreamDecodeResult), _u8p, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        L.ref_stream_burst_group.restype = C.c_int
         L.ref_make_ack_frame.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, _u8p, C.c_int]
         L.ref_make_ack_frame.restype = C.c_int
         L.ref_ofdm_cox_tx_frame.argtypes = [C.POINTER(ModemConfig), _u8p, C.c_int, _f32p, C.c_int]
@@ -572,6 +577,29 @@ class Ref:
                                        frame, len(frame), out, cap)
         assert n > 0, n
         return out[:n].copy()
+
+    def stream_encode_burst(self, modulation: int, rate: int, frames, group: int = 4) -> np.ndarray:
+        """StreamingEncoder::encodeBurstLight with burst interleaving on; frames: equally long byte strings"""
+        flen = len(frames[0])
+        buf = np.ascontiguousarray(np.frombuffer(b"".join(bytes(f) for f in frames), dtype=np.uint8))
+        cap = 1200000
+        out = np.zeros(cap, np.float32)
+        n = self.lib.ref_stream_encode_burst(int(modulation), int(rate), int(group), buf, flen, len(frames), out, cap)
+        assert n > 0, n
+        return out[:n].copy()
+
+    def stream_burst_group(self, h, samples, sync_pos, sync_cfo=0.0, last_cfo=0.0, group=4):
+        """decodeCurrentFrame with the burst marker latched + accumulateBurstFrames to the end of the group
+        -> (list of (StreamDecodeResult, frame bytes), last_cfo) or (None, last_cfo) when the group was not finished"""
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        res = (StreamDecodeResult * 16)()
+        buf = np.zeros((16, 1024), np.uint8)
+        lc = C.c_float(0)
+        n = self.lib.ref_stream_burst_group(C.c_void_p(h), samples, len(samples), int(sync_pos), float(sync_cfo), float(last_cfo),
+                                            int(group), res, buf, 1024, 16, C.byref(lc))
+        if n < 0:
+            return None, lc.value
+        return [(res[i], bytes(buf[i, : res[i].n_bytes])) for i in range(n)], lc.value
 
     def make_ack_frame(self, src: str, dst: str, seq: int, nack=False) -> bytes:
         out = np.zeros(64, np.uint8)

@@ -479,6 +479,83 @@ void ref_stream_step(void* h, const float* samples, int n, int sync_pos, float s
     }
 }
 
+// StreamingEncoder::encodeBurstLight (streaming_encoder.cpp:302-390) of `n_frames` equally long frames with the burst
+// interleaver on: every group of `group` frames is interleaved and its first LTS symbol negated as the marker.
+int ref_stream_encode_burst(int modulation, int rate, int group, const uint8_t* frames, int frame_len, int n_frames,
+                            float* out, int cap) {
+    gui::StreamingEncoder enc;
+    enc.setMode(protocol::WaveformMode::OFDM_CHIRP);
+    ModemConfig cfg;
+    cfg.use_pilots = true;
+    cfg.pilot_spacing = 10;
+    enc.setOFDMConfig(cfg);
+    enc.setDataMode(Modulation::QPSK, CodeRate::R1_2);
+    enc.setDataMode(static_cast<Modulation>(modulation), static_cast<CodeRate>(rate));
+    enc.setBurstInterleave(true);
+    enc.setBurstInterleaveGroupSize(group);
+    std::vector<Bytes> list;
+    for (int i = 0; i < n_frames; ++i) list.emplace_back(frames + i * frame_len, frames + (i + 1) * frame_len);
+    std::vector<float> s = enc.encodeBurstLight(list);
+    const int n = static_cast<int>(s.size());
+    if (n > cap) return -n;
+    std::memcpy(out, s.data(), s.size() * sizeof(float));
+    return n;
+}
+
+// A burst group through the reference state machine: decodeCurrentFrame with the burst marker latched (what
+// detectDataSync leaves behind when it sees the negated LTS, ofdm_chirp_waveform.cpp:366-375), then
+// accumulateBurstFrames until the group is finalised or aborted (:3065-3240).  Results: the queued DecodeResults in
+// order (frame bytes concatenated with stride `stride`); returns their count, or -1 - state when the decoder did not
+// return to SEARCHING.
+int ref_stream_burst_group(void* h, const float* samples, int n, int sync_pos, float sync_cfo, float last_cfo, int group,
+                           ref_decode_result* results, uint8_t* bytes, int stride, int cap, float* last_cfo_out) {
+    auto* d = static_cast<gui::StreamingDecoder*>(h);
+    {
+        std::lock_guard<std::mutex> lock(d->buffer_mutex_);
+        if (d->buffer_.size() < gui::StreamingDecoder::MAX_BUFFER_SAMPLES) d->buffer_.assign(gui::StreamingDecoder::MAX_BUFFER_SAMPLES, 0.0f);
+        std::memcpy(d->buffer_.data(), samples, static_cast<size_t>(n) * sizeof(float));
+        d->write_pos_ = static_cast<size_t>(n);
+        d->total_fed_ = static_cast<size_t>(n);
+        d->sync_position_ = static_cast<size_t>(sync_pos);
+        d->correlation_pos_ = static_cast<size_t>(sync_pos);
+    }
+    while (!d->frame_queue_.empty()) d->frame_queue_.pop();
+    d->sync_cfo_ = sync_cfo;
+    d->sync_snr_ = 15.0f;
+    d->last_cfo_.store(last_cfo);
+    d->pending_total_cw_ = 0;
+    d->use_burst_interleave_ = true;
+    d->burst_group_size_ = group;
+    d->state_ = gui::DecoderState::DECODING;
+    auto* wf = dynamic_cast<OFDMChirpWaveform*>(d->waveform_.get());
+    if (!wf) return -100;
+    wf->reset();
+    wf->setAbsoluteTrainingPosition(static_cast<size_t>(sync_pos));
+    wf->burst_interleaved_detected_ = true;
+    wf->burst_interleave_latched_ = true;
+    d->decodeCurrentFrame();
+    for (int it = 0; it < 4 * group && d->state_ == gui::DecoderState::BURST_ACCUMULATING; ++it) d->accumulateBurstFrames();
+    wf->burst_interleave_latched_ = false;
+    *last_cfo_out = d->last_cfo_.load();
+    if (d->state_ != gui::DecoderState::SEARCHING) return -1 - static_cast<int>(d->state_);
+    int count = 0;
+    while (!d->frame_queue_.empty() && count < cap) {
+        auto res = d->frame_queue_.front();
+        d->frame_queue_.pop();
+        ref_decode_result& o = results[count];
+        o.success = res.success ? 1 : 0;
+        o.frame_type = static_cast<int32_t>(res.frame_type);
+        o.codewords_ok = res.codewords_ok;
+        o.codewords_failed = res.codewords_failed;
+        o.is_ping = res.is_ping ? 1 : 0;
+        o.n_bytes = static_cast<int32_t>(res.frame_data.size());
+        std::memcpy(bytes + static_cast<size_t>(count) * stride, res.frame_data.data(),
+                    std::min<size_t>(res.frame_data.size(), static_cast<size_t>(stride)));
+        ++count;
+    }
+    return count;
+}
+
 // v2::ControlFrame::makeAck / makeNack(...).serialize(): 20-byte control frames (frame_v2.cpp)
 int ref_make_ack_frame(const char* src, const char* dst, int seq, int nack, uint8_t* out, int cap) {
     auto f = nack ? protocol::v2::ControlFrame::makeNack(src, dst, static_cast<uint16_t>(seq), 0)

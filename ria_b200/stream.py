@@ -13,9 +13,10 @@ checkIfReadyToDecode hands the frame back to decodeCurrentFrame.
 Built: the connected OFDM_CHIRP branch complete (control-first peek at the DQPSK R1/4 profile, CFO feedback with the 2 Hz
 drift clamp, the R1/4 / data-rate codeword-0 peek, QAM partial-frame escalation, decodeFrame, small-frame recovery, the
 multi-candidate light-sync recovery) and the PING energy test a disconnected receiver classifies chirp-only
-transmissions with (`ping_energy_batch`).  Not built: CSS frame typing, the MC-DPSK handshake rules around the
+transmissions with (`ping_energy_batch`), and burst-interleaved groups (`OfdmConnectedStep.burst_group`).  Not built:
+CSS frame typing, the burst timeout clock, the MC-DPSK handshake rules around the
 codeword-0 peek with their retries at the alternate modulation / neighbouring sync offsets (:1443-1795; the decode
-itself is `mcdpsk.McdpskFrameDecoder`) and the burst-group accumulation state.
+itself is `mcdpsk.McdpskFrameDecoder`).
 """
 from __future__ import annotations
 
@@ -93,8 +94,9 @@ class OfdmConnectedStep:
         return max(default, (2 + (LDPC_BLOCK + bits - 1) // bits) * self.sym)
 
     # ---- waveform_->setFrequencyOffset(cfo); waveform_->process(frame) for a subset ----
-    def _process(self, dem, window, idx, pos, length, cfo):
-        """-> (ready bool[m], soft (CUDA [m, stride]), n_soft int[m], cfo_out f32[m], fading f32[m])"""
+    def _process(self, dem, window, idx, pos, length, cfo, phase_ref=None, undo_marker=False):
+        """-> (ready bool[m], soft (CUDA [m, stride]), n_soft int[m], cfo_out f32[m], fading f32[m]).  phase_ref: the
+        sample index the initial CFO phase refers to (default: pos); undo_marker: restore a negated first LTS symbol."""
         m = len(idx)
         dev = window.device
         L = window.shape[1]
@@ -111,7 +113,9 @@ class OfdmConnectedStep:
             rows = torch.from_numpy(idx[sel]).to(dev)
             cols = torch.from_numpy(pos[sel].astype(np.int64)).to(dev)[:, None] + torch.arange(int(ln), device=dev)[None, :]
             frames = torch.gather(window.index_select(0, rows), 1, cols)
-            phase = _initial_phase(cfo[sel], pos[sel], float(dem.config.sample_rate))
+            if undo_marker:                                                    # ofdm_chirp_waveform.cpp:423-436
+                frames[:, : self.sym] = -frames[:, : self.sym]
+            phase = _initial_phase(cfo[sel], (pos if phase_ref is None else phase_ref)[sel], float(dem.config.sample_rate))
             out = dem.process_presynced_batch(frames, torch.from_numpy(cfo[sel].astype(np.float32)).to(dev),
                                               torch.from_numpy(phase).to(dev))
             ns = out["n_llr"].cpu().numpy()
@@ -325,6 +329,82 @@ class OfdmConnectedStep:
             out["consumed_len"][g] = ln[use[good]]
             retry = np.setdiff1d(retry, g)
         return out
+
+    def burst_group(self, window: torch.Tensor, sync_pos, sync_cfo, last_cfo, group_size: int = 4):
+        """A burst-interleaved group (decodeCurrentFrame with the burst marker latched, :1380-1409, then
+        accumulateBurstFrames / tryDemodulateNextBurstFrame / finalizeBurstGroup, :3065-3240) for receptions whose
+        light sync reported the marker (negated first LTS): `group_size` frames back to back from sync_pos, the first
+        demodulated with the marker undone, every further block after an energy check, the CFO fed back from frame to
+        frame with the 2 Hz clamp, then BurstInterleaver::deinterleave and decodeFrame of every logical frame.
+        Returns (results, last_cfo): results[k] = dict of numpy arrays for logical frame k (success, frame_type,
+        codewords_ok, codewords_failed, frame_len, frame, queued) with queued = the reference pushes the result
+        (success or a codeword decoded); a group that was aborted has queued = 0 everywhere."""
+        n, L = window.shape
+        dev = window.device
+        sync_pos = np.asarray(sync_pos, np.int64)
+        burst_cfo = np.asarray(sync_cfo, np.float32).copy()
+        last_cfo = np.asarray(last_cfo, np.float32).copy()
+        G = max(2, int(group_size))
+        block = self.samples_for_cw(4)                                          # burst_min_block_ = getMinSamplesForFrame()
+        alive = np.ones(n, bool)
+        soft_all = torch.zeros((n, G, 2592), dtype=torch.float32, device=dev)
+        all_idx = np.arange(n)
+
+        def clamp_to(cur, est):
+            drift = (est - cur).astype(np.float32)
+            big = np.abs(drift) > np.float32(2.0)
+            return np.where(big, (cur + np.copysign(np.float32(2.0), drift)).astype(np.float32), est).astype(np.float32)
+
+        for k in range(G):
+            idx = all_idx[alive]
+            if len(idx) == 0:
+                break
+            pos = sync_pos[idx] + k * block
+            enough = pos + block <= L
+            if k > 0:
+                # a block that has not arrived yet: the reference waits, then times out and discards the group
+                alive[idx[~enough]] = False
+                idx, pos = idx[enough], pos[enough]
+                if len(idx) == 0:
+                    break
+                # energy check on [1024, 1024 + 5000) of the block (:3153-3169)
+                cols = torch.from_numpy(pos).to(dev)[:, None] + torch.arange(1024, min(block, 1024 + 5000), device=dev)[None, :]
+                seg = torch.gather(window.index_select(0, torch.from_numpy(idx).to(dev)), 1, cols).contiguous()
+                e = ping_energy_batch(seg, 0, self.ctx)                         # training_skip 0: the data RMS is the block's
+                lost = e["data_rms"] < np.float32(0.04)
+                alive[idx[lost]] = False
+                idx, pos = idx[~lost], pos[~lost]
+                if len(idx) == 0:
+                    break
+            ready, soft, n_soft, cfo_est, _ = self._process(self.dem, window, idx, pos, np.full(len(idx), block, np.int64),
+                                                            burst_cfo[idx], phase_ref=sync_pos[idx] if k else None,
+                                                            undo_marker=(k == 0))
+            ok = ready & (n_soft >= 2592)
+            alive[idx[~ok]] = False
+            keep = np.nonzero(ok)[0]
+            idx = idx[keep]
+            if len(idx) == 0:
+                break
+            soft_all[torch.from_numpy(idx).to(dev), k] = soft.index_select(0, torch.from_numpy(keep).to(dev))[:, :2592]
+            cur = last_cfo[idx] if k == 0 else burst_cfo[idx]                   # frame 0 clamps against last_cfo_ (:1394-1402)
+            corrected = clamp_to(cur, cfo_est[keep])
+            burst_cfo[idx] = corrected
+            last_cfo[idx] = corrected
+        results = []
+        done = all_idx[alive]
+        logical = fec.burst_deinterleave_batch(soft_all.index_select(0, torch.from_numpy(done).to(dev)), self.ctx) if len(done) else None
+        for k in range(G):
+            r = dict(success=np.zeros(n, np.uint8), frame_type=np.zeros(n, np.int32), codewords_ok=np.zeros(n, np.int32),
+                     codewords_failed=np.zeros(n, np.int32), frame_len=np.zeros(n, np.int32), frame=np.zeros((n, 1024), np.uint8),
+                     queued=np.zeros(n, np.uint8))
+            if len(done):
+                d = self.decoder.decode_batch(logical[:, k].contiguous())
+                for key in ("success", "frame_type", "codewords_ok", "codewords_failed", "frame_len"):
+                    r[key][done] = d[key]
+                r["frame"][done, : d["frame"].shape[1]] = d["frame"]
+                r["queued"][done] = (d["success"] != 0) | (d["codewords_ok"] > 0)
+            results.append(r)
+        return results, last_cfo
 
 
 def ping_energy_batch(frames: torch.Tensor, training_skip: int = 4608, ctx: Optional[Context] = None) -> np.ndarray:

@@ -133,3 +133,67 @@ def test_ping_energy_matches_the_reference_decision(ctx, ref):
         tr = np.sqrt(np.float32(acc / np.float32(4608)), dtype=np.float32)
         assert got["training_rms"][i].view(np.uint32) == np.float32(tr).view(np.uint32), i
     ref.stream_decoder_free(h)
+
+
+@pytest.mark.parametrize("modulation,rate", [(QAM16, R3_4), (DQPSK, R1_2)])
+def test_burst_group_matches_the_reference(ctx, ref, modulation, rate):
+    """burst-interleaved groups: marker frame, three continuation blocks, de-interleave, four decodes; plus a group whose
+    third block lost its energy (aborted) and one whose last block never arrives"""
+    from ria_b200 import stream
+    rng = np.random.default_rng(11 + modulation)
+    h = ref.stream_decoder()
+    ref.stream_setup_ofdm(h, True, modulation, rate)
+    stepper = stream.OfdmConnectedStep(modulation, rate, ctx)
+    block = stepper.samples_for_cw(4)
+    Lw = 4 * block + 4000
+    wins, sync, cfos, kinds, sent = [], [], [], [], []
+    for i in range(8):
+        kind = ("ok", "ok", "lost", "ok_cfo", "late", "ok_low", "ok", "ok")[i]
+        frames = [ref.make_data_frame("K1ABC", "W2XYZ", 4 * i + k, rng.integers(0, 256, size=4 * BYTES_PER_CW[rate] - 19, dtype=np.uint8))
+                  for k in range(4)]
+        tx = ref.stream_encode_burst(modulation, rate, frames, 4)
+        assert len(tx) == 4 * block
+        pos = int(rng.integers(100, 2500))
+        cfo = 1.3 if kind == "ok_cfo" else 0.0
+        w = np.zeros(Lw, np.float32)
+        w[pos:pos + len(tx)] = tx
+        if cfo:
+            w = apply_cfo(w, cfo)
+        if kind == "lost":
+            w[pos + 2 * block: pos + 3 * block] = 0.0
+        p = float(np.mean(tx.astype(np.float64) ** 2))
+        w = _noisy(w, 12.0 if kind == "ok_low" else 28.0, rng, p)
+        if kind == "lost":
+            w[pos + 2 * block: pos + 3 * block] *= np.float32(0.01)
+        if kind == "late":
+            w = w[: pos + 3 * block + 500].copy()
+            w = np.concatenate([w, np.zeros(Lw - len(w), np.float32)])         # the batch is rectangular; see n_valid below
+        wins.append(w); sync.append(pos); cfos.append(cfo); kinds.append(kind); sent.append(frames)
+    x = torch.from_numpy(np.stack(wins)).cuda()
+    # the late group: hand the reference only the samples that arrived; the batched call sees a window that ends there too
+    late = kinds.index("late")
+    n_valid = sync[late] + 3 * block + 500
+    got_main, last_main = stepper.burst_group(x, np.array(sync), np.array(cfos, np.float32), np.array(cfos, np.float32), 4)
+    got_late, last_late = stepper.burst_group(x[late:late + 1, :n_valid].contiguous(), np.array(sync[late:late + 1]),
+                                              np.array(cfos[late:late + 1], np.float32), np.array(cfos[late:late + 1], np.float32), 4)
+    n_ok = 0
+    for i in range(8):
+        samples = wins[i][:n_valid] if i == late else wins[i]
+        res, lc = ref.stream_burst_group(h, samples, sync[i], cfos[i], cfos[i], 4)
+        got, last, j = (got_late, last_late, 0) if i == late else (got_main, last_main, i)
+        queued = [k for k in range(4) if got[k]["queued"][j]]
+        if res is None:                                                        # still accumulating: nothing delivered
+            assert kinds[i] == "late" and queued == []
+            continue
+        assert np.float32(last[j]).view(np.uint32) == np.float32(lc).view(np.uint32), (i, kinds[i], last[j], lc)
+        assert len(queued) == len(res), (i, kinds[i], queued, len(res))
+        for k, (r, data) in zip(queued, res):
+            g = got[k]
+            assert (g["success"][j], g["codewords_ok"][j], g["codewords_failed"][j]) == (r.success, r.codewords_ok, r.codewords_failed), (i, k)
+            if r.success:
+                assert bytes(g["frame"][j, : r.n_bytes]) == data == sent[i][k], (i, k)
+                n_ok += 1
+        if kinds[i] == "lost":
+            assert res == []
+    ref.stream_decoder_free(h)
+    assert n_ok >= 16, n_ok
