@@ -47,6 +47,7 @@ KK_LDPC, KK_OFDM_DEMOD, KK_FRAME_STATUS, KK_AWGN = 0, 1, 2, 3
 KK_OFDM_FFT, KK_OFDM_CARRIER, KK_OFDM_PHASE = 11, 12, 13
 KK_LDPC_RETRY, KK_FRAME_REPAIR = 14, 15
 KK_MCDPSK, KK_CHIRP_SYNC, KK_CHASE, KK_MCDPSK_CFO = 4, 6, 7, 9
+KK_OFDM_SYNC = 10
 
 
 # ---------------------------------------------------------------------------------------------
@@ -354,6 +355,154 @@ class OfdmQam64Workload:
         sym_copied = 1024 if os.environ.get("RIA_H2D_FULL_SYMBOLS") != "1" else 1120
         return (self.e2e_n * (self.frame_len // 1120) * sym_copied * 4 + (8 * self.e2e_n if self.cfo_span else 0),
                 self.e2e_n * (240 + ofdm.FRAME_STATUS_DTYPE.itemsize + 4))
+
+
+# ---------------------------------------------------------------------------------------------
+# workload: OFDM_COX -- the same frames behind a Schmidl-Cox preamble, acquired by the batched searchForSync
+# (SURVEY.md 8f rank 4): window -> search -> frames at the LTS position with the CFO found -> the chain above
+# ---------------------------------------------------------------------------------------------
+class OfdmCoxWorkload(OfdmQam64Workload):
+    LEAD, WINDOW = 2000, 24000                          # [2000 quiet][silent symbol][4 STS][2 LTS][10 data symbols][tail]
+    CPU_SAMPLE = 150
+    e2e_api = ("pinned host windows -> device copy -> ria_ofdm_cox_search_sync_batch_dev + ria_ofdm_rx_frames_dev -> "
+               "decoded frames and status copied back (ria_b200.sync / ria_b200.ofdm)")
+
+    def __init__(self, n_frames: int):
+        super().__init__(n_frames)
+        self.key = "ofdm_cox"
+        self.name = "ofdm_cox_qam64_r34_15pilots_awgn28dB_schmidl_cox_acquisition"
+
+    def cpu_params(self):
+        p = super().cpu_params()
+        p["cox"] = {"lead": self.LEAD, "window": self.WINDOW, "frame_len": self.FRAME_LEN}
+        p["pool"] = 16
+        return p
+
+    def describe(self):
+        d = super().describe()
+        d["window_samples"] = self.WINDOW
+        d["chain"] = ("searchForSync (energy walk, Schmidl-Cox metric, plateau, LTS timing, coarse CFO) -> gather at the LTS "
+                      "position -> " + d["chain"])
+        d["l2"] = f"input batch ({self.n * self.WINDOW * 4 / 1e9:.1f} GB) exceeds the 126 MB L2; no flush needed"
+        return d
+
+    def setup(self, ctx, device, rank, world):
+        import torch
+        import ria_b200
+        from ria_b200 import ofdm, sim, sync, txsynth
+        self.torch, self.ctx, self.sync = torch, ctx, sync
+        cfg = self.cfg = ofdm.ModemConfig.high_throughput(self.MOD)
+        bpc = 60
+        self.first_id = rank * self.n
+        bps = cfg.getDataCarriers() * 6
+        self.windows = torch.empty((self.n, self.WINDOW), dtype=torch.float32, device=device)
+        self.sent_len = 4 * bpc - 2
+        self.sent_dev = torch.empty((self.n, self.sent_len), dtype=torch.uint8, device=device)
+        chunk = 32768
+        for off in range(0, self.n, chunk):
+            m = min(chunk, self.n - off)
+            rng = np.random.default_rng([2027, self.first_id + off])
+            frames = txsynth.make_data_frames("K1ABC", "W2XYZ", self.first_id + off,
+                                              rng.integers(0, 256, size=(m, 4 * bpc - 19 - 2), dtype=np.uint8), bpc)
+            fr_dev = torch.from_numpy(frames).to(device)
+            self.sent_dev[off:off + m] = fr_dev
+            coded = ofdm.encode_fixed_frame_batch(fr_dev, self.RATE, True, bps, ctx)
+            tx = ofdm.ofdm_cox_tx_frames(cfg, coded, ctx)
+            rows = torch.zeros((m, self.WINDOW), dtype=torch.float32, device=device)
+            rows[:, self.LEAD:self.LEAD + tx.shape[1]] = tx
+            gid = self.first_id + off
+            if gid % m:
+                rows = torch.roll(rows, shifts=gid % m, dims=0)
+            sim.awgn_batch(rows, m, self.SNR_DB, seed=2027, first_frame_id=gid, out=self.windows[off:off + m], ctx=ctx)
+            del tx, coded, fr_dev, rows
+        ctx.set_decode_flags(ria_b200.DECODE_FULL)
+        self.chain = ofdm.OfdmRxChain(cfg, self.RATE, True, ctx)
+        self.cols = torch.arange(self.FRAME_LEN, device=device)[None, :]
+        self.out = None
+        torch.cuda.synchronize()
+
+    def release(self):
+        self.windows = self.sent_dev = self.out = self.cols = None
+        self._pin = None
+
+    def _run(self, windows):
+        torch = self.torch
+        res = self.sync.ofdm_cox_search_sync_batch(self.cfg, windows, 0.8, None, self.ctx)
+        r32 = res.view(torch.int32)                        # ria_sync_result: detected, start_sample, correlation, cfo_hz, ...
+        det = r32[:, 0] != 0
+        start = torch.where(det, r32[:, 1], torch.zeros_like(r32[:, 1])).clamp_(0, windows.shape[1] - self.FRAME_LEN).long()
+        cfo = torch.where(det, r32[:, 3].view(torch.float32), torch.zeros(len(det), device=windows.device)).contiguous()
+        # OFDMNvisWaveform::process: initial mixer phase from the CFO and the LTS position (fp64 expression -> fp32, wrapped)
+        ph = (-2.0 * np.pi) * cfo.double() * start.double() / 48000.0
+        ph = ph.float()
+        ph = torch.where(ph > np.pi, (ph.double() - 2.0 * np.pi).float(), ph)
+        ph = torch.where(ph < -np.pi, (ph.double() + 2.0 * np.pi).float(), ph)
+        frames = torch.gather(windows, 1, start[:, None] + self.cols)
+        out = self.chain.process_batch(frames, cfo, ph.contiguous())
+        self.detected = det
+        return out
+
+    def step(self):
+        self.out = self._run(self.windows)
+
+    def samples_per_step(self):
+        return float(self.n) * self.WINDOW
+
+    def kernels(self):
+        k = super().kernels()
+        k[KK_OFDM_PHASE] = ("ofdm_phase_scan_kernel (CFO phase accumulator)", self.n * 8)
+        k[KK_OFDM_SYNC] = ("cox_scan_kernel + cox_decide_kernel (Schmidl-Cox acquisition)", self.n * (self.WINDOW * 4 + 32))
+        return k
+
+    # per window of this layout: the LTS passband search at 3921 offsets x 1120 taps x (3 multiplies + 3 adds) = 26.3 Mflop,
+    # plus ~74 Schmidl-Cox metrics (35 visited positions, 38 plateau points, the CFO estimate) of two 1024-point
+    # transforms (2 x 5 N log2 N) and 4 x 512-term sums each = 8.1 Mflop
+    COX_FLOP_PER_WINDOW = 3921 * 1120 * 6 + 74 * (2 * 5 * 1024 * 10 + 7 * 1024)
+
+    def roofline(self, kern_ms, steps, counters):
+        """the acquisition is arithmetic on shared-memory tiles: fp32 bound (un-fused multiplies and adds, the order of
+        every sum being the reference's); HBM traffic is the 96 KB window"""
+        sp = sm_peaks()
+        ms, n_launch = kern_ms[KK_OFDM_SYNC]
+        kern_s = ms / steps * 1e-3
+        achieved = self.n * self.COX_FLOP_PER_WINDOW / kern_s / 1e12 if kern_s > 0 else 0.0
+        hbm_peak, _ = measured_peaks()
+        return {"bound": "fp32", "achieved": achieved, "peak": sp["fp32_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / sp["fp32_tflops"], "traffic": None, "peak_source": sp["source"],
+                "kernel": self.kernels()[KK_OFDM_SYNC][0], "kernel_ms_per_launch": ms / max(1, n_launch),
+                "launches_per_step": n_launch / steps, "algorithmic_flop_per_step": self.n * self.COX_FLOP_PER_WINDOW,
+                "windows_per_s": self.n / kern_s if kern_s > 0 else None,
+                "hbm_frac_on_algorithmic_bytes": (self.n * self.WINDOW * 4 / kern_s / 1e9 / hbm_peak) if kern_s > 0 else None,
+                "note": "peak = measured FMA rate; the kernel may not fuse (bit-exact sums), so 0.5 is its ceiling"}
+
+    def counters(self):
+        c = super().counters()
+        c = self.torch.cat([c, self.detected.sum().reshape(1).to(c.dtype)])
+        return c
+
+    def counter_dict(self, c):
+        d = super().counter_dict(c)
+        d["sync_found"] = int(c[5])
+        return d
+
+    def setup_e2e(self, n_e2e):
+        torch = self.torch
+        self.e2e_n = n_e2e = min(n_e2e, self.n)
+        pin = torch.empty((n_e2e, self.WINDOW), dtype=torch.float32, pin_memory=True)
+        pin.copy_(self.windows[:n_e2e])
+        torch.cuda.synchronize()
+        self._pin = pin
+        self._dev_in = torch.empty((n_e2e, self.WINDOW), dtype=torch.float32, device=self.windows.device)
+
+    def step_e2e(self):
+        # pinned host windows -> device -> acquisition + chain -> decoded frames and status back on the host
+        self._dev_in.copy_(self._pin, non_blocking=True)
+        data, status, snr = self._run(self._dev_in)
+        return data.cpu(), status.cpu(), snr.cpu()
+
+    def e2e_bytes(self):
+        from ria_b200 import ofdm
+        return (self.e2e_n * self.WINDOW * 4, self.e2e_n * (240 + ofdm.FRAME_STATUS_DTYPE.itemsize + 4))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -716,6 +865,8 @@ def make_workload(name, batch):
         return LdpcWorkload(batch or (1 << 20))
     if name == "ofdm_qam64_cfo":
         return OfdmQam64Workload(batch or (1 << 18), cfo_span=3.0)
+    if name == "ofdm_cox":
+        return OfdmCoxWorkload(batch or (1 << 16))
     return OfdmQam64Workload(batch or (1 << 20))
 
 
@@ -832,7 +983,8 @@ def run_workload(wl, ctx, stream, device, rank, world, local, steps, warmup, e2e
                         for k in kern_ms},
             "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "batch": getattr(wl, "e2e_n", e2e_batch),
-                    "api": "ria_ofdm_rx_frames_host / ria_mcdpsk_rx_frames_host / ria_ldpc_decode_batch_host (pinned host buffers)"},
+                    "api": getattr(wl, "e2e_api", "ria_ofdm_rx_frames_host / ria_mcdpsk_rx_frames_host / ria_ldpc_decode_batch_host "
+                                                  "(pinned host buffers)")},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -851,7 +1003,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ria_b200", choices=["ria_b200", "reference"])
-    ap.add_argument("--workload", default="ofdm_qam64", choices=["ofdm_qam64", "ofdm_qam64_cfo", "ldpc", "mcdpsk"])
+    ap.add_argument("--workload", default="ofdm_qam64", choices=["ofdm_qam64", "ofdm_qam64_cfo", "ofdm_cox", "ldpc", "mcdpsk"])
     ap.add_argument("--batch", type=int, default=0, help="frames (or codewords per rate) per GPU")
     ap.add_argument("--e2e-batch", type=int, default=1 << 16)
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames (codewords per rate) per core")
@@ -891,7 +1043,7 @@ def main():
     if args.workload == "ofdm_qam64" and not args.batch and not args.no_extras:
         extras = {}
         short = max(2, min(args.steps, 4))
-        for name, batch in (("ofdm_qam64_cfo", 1 << 18), ("mcdpsk", 1 << 15), ("ldpc", 1 << 20)):
+        for name, batch in (("ofdm_qam64_cfo", 1 << 18), ("ofdm_cox", 1 << 15), ("mcdpsk", 1 << 15), ("ldpc", 1 << 20)):
             ctx.set_decode_flags(0)
             r = run_workload(make_workload(name, batch), ctx, stream, device, rank, world, local,
                              short, 3, min(args.e2e_batch, 1 << 15), 0, with_cpu)

@@ -48,7 +48,8 @@ def ofdm_pool(p):
     """p["pool"] clean TX frames made by the reference transmitter (makeData -> encodeFixedFrame ->
     OFDMModulator), no chunk 1..3 starting with 0xD5 (CodewordStatus::reassemble would drop such frames)."""
     span = int(p.get("cfo_span", 0))
-    key = ("ofdm", p["modulation"], p["pilot_spacing"], p["rate"], p["pool"], span)
+    cox = p.get("cox")                                       # {"lead": .., "window": ..}: Schmidl-Cox preamble, window rows
+    key = ("ofdm", p["modulation"], p["pilot_spacing"], p["rate"], p["pool"], span, str(cox))
     if key not in _POOLS:
         from oracle.bindings import BITS_PER_CARRIER, BYTES_PER_CW, ModemConfig, Ref
         ref = Ref()
@@ -65,7 +66,14 @@ def ofdm_pool(p):
             d = int(rng.integers(-span, span + 1)) if span else 0
             tx_cfg = ModemConfig.from_buffer_copy(bytes(cfg))
             tx_cfg.center_freq = cfg.center_freq + d
-            pool.append(ref.ofdm_tx_frame(tx_cfg, ref.encode_fixed_frame(frame, p["rate"], True, bps)))
+            coded = ref.encode_fixed_frame(frame, p["rate"], True, bps)
+            if cox:
+                tx = ref.ofdm_cox_tx_frame(tx_cfg, coded)
+                row = np.zeros(cox["window"], np.float32)
+                row[cox["lead"]:cox["lead"] + len(tx)] = tx[: cox["window"] - cox["lead"]]
+                pool.append(row)
+            else:
+                pool.append(ref.ofdm_tx_frame(tx_cfg, coded))
             offs.append(d)
         _POOLS[key] = (cfg, bps, pool, offs)
     return _POOLS[key]
@@ -81,8 +89,22 @@ def _ofdm_worker(args):
     # the receiver is told the frame's carrier offset the way a sync stage would: +- 0.2 Hz
     cfo = np.array([offs[i % len(pool)] + (rng.uniform(-0.2, 0.2) if p.get("cfo_span") else 0.0) for i in range(n_frames)])
     ok = 0
+    cox = p.get("cox")
     t0 = time.perf_counter()
     for rx, c in zip(frames, cfo):
+        if cox:                                              # OFDMNvisWaveform::detectSync + process
+            found, pos, c, _ = ref.ofdm_cox_search_sync(cfg, rx, 0.8, 0.0)
+            if not found:
+                continue
+            ph = np.float32(-2.0 * np.pi * float(c) * float(pos) / 48000.0)
+            while float(ph) > np.pi:
+                ph = np.float32(float(ph) - 2.0 * np.pi)
+            while float(ph) < -np.pi:
+                ph = np.float32(float(ph) + 2.0 * np.pi)
+            r = ref.ofdm_process_presynced(cfg, rx[pos:pos + cox["frame_len"]], float(c), float(ph))
+            data, cw_ok = ref.decode_fixed_frame_full(r["soft"], p["rate"], True, bps)
+            ok += int(cw_ok.all() and ref.parse_header(data).frame_crc_ok)
+            continue
         r = ref.ofdm_process_presynced(cfg, rx, float(c), 0.0)
         data, cw_ok = ref.decode_fixed_frame_full(r["soft"], p["rate"], True, bps)
         ok += int(cw_ok.all() and ref.parse_header(data).frame_crc_ok)
@@ -102,7 +124,7 @@ def cpu_ofdm(p, frames_per_core):
     ok = sum(o for _, o in res)
     return {"value": rate, "unit": "frames/s", "cores": cores, "kind": "reference",
             "sample": f"{frames_per_core} frames per core x {cores} cores ({ok}/{frames_per_core * cores} decoded with valid CRC), "
-                      f"reference processPresynced + complete decodeFixedFrame + parseHeader, one process per core, "
+                      f"reference {'searchForSync (Schmidl-Cox acquisition) + ' if p.get('cox') else ''}processPresynced + complete decodeFixedFrame + parseHeader, one process per core, "
                       f"{wall:.1f} s wall, {max(b for b, _ in res):.1f} s max busy"}
 
 

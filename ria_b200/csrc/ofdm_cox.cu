@@ -70,6 +70,14 @@ __device__ __forceinline__ float2 cmul_ref(float2 a, float2 b) {       // std::c
     return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)),
                        __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
 }
+// Blackwell packed fp32 multiply (two IEEE round-to-nearest products per issue slot); the products feed scalar adds,
+// never a packed add (ptxas would contract that pair into FFMA2 even under --fmad=false)
+__device__ __forceinline__ float2 mul2s(float s, float2 b) {            // (s * b.x, s * b.y)
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%2}; mov.b64 rb, {%3,%4}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(s), "f"(b.x), "f"(b.y));
+    return r;
+}
 __device__ __forceinline__ float cnorm(float2 a) { return __fadd_rn(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y)); }
 __device__ __forceinline__ unsigned brev10(unsigned i) { return __brev(i) >> 22; }
 
@@ -143,18 +151,32 @@ __device__ void warp_schmidl_cox(const float* __restrict__ src, bool remove_dc, 
         t.x[i] = make_float2(__fmul_rn(v.x, scale), __fmul_rn(v.y, scale));
     }
     __syncwarp();
-    // four sequential chains of N/2 terms (:149-153): P.re, P.im, R1, R2 on lanes 0..3
+    // four sequential chains of N/2 terms (:149-153).  The terms are independent of the running sums: every lane
+    // computes 16 of each kind into two term planes (the sample staging area and the upper half of the transform tile,
+    // both dead by now), then lanes 0..3 walk one chain each with 128-bit loads.
+    float* term_a = t.s;                                                // [0, 512): Re conj(a) b   [512, 1024): Im conj(a) b
+    float* term_b = reinterpret_cast<float*>(t.x);                      // [0, 512): |a|^2          [512, 1024): |b|^2
+    float2 av[kN / 64], bv[kN / 64];
+#pragma unroll
+    for (int q = 0; q < kN / 64; ++q) { av[q] = t.x[lane + 32 * q]; bv[q] = t.x[lane + 32 * q + kN / 2]; }
+    __syncwarp();                                                       // every a / b is in registers before the tile is reused
+#pragma unroll
+    for (int q = 0; q < kN / 64; ++q) {
+        const int i = lane + 32 * q;
+        const float2 a = av[q], b = bv[q];
+        term_a[i] = __fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+        term_a[i + kN / 2] = __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x));
+        term_b[i] = cnorm(a);
+        term_b[i + kN / 2] = cnorm(b);
+    }
+    __syncwarp();
     float acc = 0.0f;
     if (lane < 4) {
+        const float4* src = reinterpret_cast<const float4*>((lane < 2 ? term_a : term_b) + (lane & 1) * (kN / 2));
 #pragma unroll 4
-        for (int i = 0; i < kN / 2; ++i) {
-            const float2 a = t.x[i], b = t.x[i + kN / 2];
-            float term;
-            if (lane == 0) term = __fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));         // Re conj(a) b
-            else if (lane == 1) term = __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x));    // Im conj(a) b
-            else if (lane == 2) term = cnorm(a);
-            else term = cnorm(b);
-            acc = __fadd_rn(acc, term);
+        for (int i = 0; i < kN / 8; ++i) {
+            const float4 v = src[i];
+            acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
         }
     }
     P.x = __shfl_sync(kFull, acc, 0);
@@ -257,7 +279,7 @@ cox_decide_kernel(const CoxArgs a) {
     const int n_off = back + fwd + 1;
     // LTS phase aliases the transform tiles: window span, template, correlations
     float* span = reinterpret_cast<float*>(region);
-    const int n_off_pad = (n_off + 4 * kThreads - 1) / (4 * kThreads) * (4 * kThreads);
+    const int n_off_pad = ((n_off + 3) & ~3) + 8;           // four adjacent offsets per thread + the look-ahead load
     float2* tmpl = reinterpret_cast<float2*>(span + ((n_off_pad + a.tmpl_len + 3) & ~3));
     float* lcorr = reinterpret_cast<float*>(tmpl + a.tmpl_len);
 
@@ -335,25 +357,38 @@ cox_decide_kernel(const CoxArgs a) {
                     for (int i = tid; i < a.tmpl_len; i += kThreads) tmpl[i] = a.lts_iq[i];
                     __syncthreads();
                     float my_best = 0.0f; int my_off = 0x7fffffff;
-                    // four offsets per thread and pass share one template load; each keeps its three sums in the
-                    // reference's order (:420-433).  The span is padded so the loads of idle offsets stay inside it.
-                    for (int o0 = tid; o0 < n_off; o0 += 4 * kThreads) {
+                    // Four ADJACENT offsets per thread: the seven samples they need for four template taps come from
+                    // two 128-bit loads, the squares are formed once per sample, the two template products are one
+                    // packed multiply.  Each offset keeps its three sums in the reference's order (:420-433).
+                    const float4* span4 = reinterpret_cast<const float4*>(span);
+                    const float4* tmpl4 = reinterpret_cast<const float4*>(tmpl);
+                    for (int t4 = tid; 4 * t4 < n_off; t4 += kThreads) {
                         float cI[4] = {0.f, 0.f, 0.f, 0.f}, cQ[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
-                        const float* s0 = span + o0;
+                        float4 lo = span4[t4];
 #pragma unroll 2
-                        for (int i = 0; i < a.tmpl_len; ++i) {
-                            const float2 t = tmpl[i];
+                        for (int i4 = 0; i4 < a.tmpl_len / 4; ++i4) {
+                            const float4 hi = span4[t4 + i4 + 1];
+                            const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                            float v2[7];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float r = s0[q * kThreads + i];
-                                cI[q] = __fadd_rn(cI[q], __fmul_rn(r, t.x));
-                                cQ[q] = __fadd_rn(cQ[q], __fmul_rn(r, t.y));
-                                e[q] = __fadd_rn(e[q], __fmul_rn(r, r));
+                            for (int j = 0; j < 7; ++j) v2[j] = __fmul_rn(v[j], v[j]);
+                            const float4 ta = tmpl4[2 * i4], tb = tmpl4[2 * i4 + 1];
+                            const float2 tt[4] = {make_float2(ta.x, ta.y), make_float2(ta.z, ta.w), make_float2(tb.x, tb.y), make_float2(tb.z, tb.w)};
+#pragma unroll
+                            for (int ii = 0; ii < 4; ++ii) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 p = mul2s(v[ii + q], tt[ii]);
+                                    cI[q] = __fadd_rn(cI[q], p.x);
+                                    cQ[q] = __fadd_rn(cQ[q], p.y);
+                                    e[q] = __fadd_rn(e[q], v2[ii + q]);
+                                }
                             }
+                            lo = hi;
                         }
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const int o = o0 + q * kThreads;
+                            const int o = 4 * t4 + q;
                             if (o >= n_off) break;
                             const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(cI[q], cI[q]), __fmul_rn(cQ[q], cQ[q])));
                             const float norm = __fsqrt_rn(__fmul_rn(e[q], a.energy_ref));
