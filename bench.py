@@ -48,6 +48,7 @@ KK_OFDM_FFT, KK_OFDM_CARRIER, KK_OFDM_PHASE = 11, 12, 13
 KK_LDPC_RETRY, KK_FRAME_REPAIR = 14, 15
 KK_MCDPSK, KK_CHIRP_SYNC, KK_CHASE, KK_MCDPSK_CFO = 4, 6, 7, 9
 KK_OFDM_SYNC = 10
+KK_ZC_SYNC = 5
 
 
 # ---------------------------------------------------------------------------------------------
@@ -524,6 +525,7 @@ class McdpskC3Workload:
     PREAMBLE, FRAME_LEN = 57600, 4096 + 512 + 133120         # dual chirp; 8 training + 1 reference + 65 x 4 data symbols
     CHIRP_FLOP_PER_WINDOW = 4 * 5 * 131072 * 17              # two (FFT + IFFT) pairs of 131072 points
     CPU_SAMPLE = 16
+    CHIRP_RECEPTIONS = 2
 
     def __init__(self, n_frames: int):
         self.n = n_frames
@@ -621,7 +623,7 @@ class McdpskC3Workload:
         reference's two FFT + IFFT pairs), HBM traffic being the 480 KB window when staged once."""
         sp = sm_peaks()
         ms, n_launch = kern_ms[KK_CHIRP_SYNC]
-        windows_per_launch = 2.0 * self.n * steps / max(1, n_launch)
+        windows_per_launch = float(self.CHIRP_RECEPTIONS) * self.n * steps / max(1, n_launch)
         kern_s = ms / max(1, n_launch) * 1e-3
         achieved = windows_per_launch * self.CHIRP_FLOP_PER_WINDOW / kern_s / 1e12 if kern_s > 0 else 0.0
         hbm_peak, _ = measured_peaks()
@@ -664,6 +666,63 @@ class McdpskC3Workload:
 
     def e2e_bytes(self):
         return (self.e2e_n * self.row_len * 4, self.e2e_n * (24 + 1 + 4 + 32))
+
+
+# ---------------------------------------------------------------------------------------------
+# workload: configs[2] with the retransmission received the way a connected station receives it: first reception
+# behind the dual chirp, HARQ retransmission behind the Zadoff-Chu data preamble ("ZC + CHIRP acquisition")
+# ---------------------------------------------------------------------------------------------
+class McdpskZcRetxWorkload(McdpskC3Workload):
+    key = "mcdpsk_zc_retx"
+    name = "mcdpsk_dbpsk_10car_4x_awgn-8dB_chirp_then_zc_retransmission_chase"
+    ZC_WINDOW = 31120                                    # connected-mode search window (streaming_decoder.cpp:423-435)
+    CHIRP_RECEPTIONS = 1
+
+    def kernels(self):
+        k = super().kernels()
+        n = self.n
+        k[KK_CHIRP_SYNC] = (k[KK_CHIRP_SYNC][0], n * self.WINDOW * 4)
+        k[KK_ZC_SYNC] = ("zc_baseband_kernel + zc_coarse_tile_kernel + zc_finish_kernel", n * self.ZC_WINDOW * 4)
+        return k
+
+    def describe(self):
+        d = super().describe()
+        d["chain"] = ("reception 1: " + d["chain"].replace("per reception: ", "") + "; reception 2 (HARQ retransmission, connected "
+                      "mode): AWGN -> Zadoff-Chu data-preamble sync (roots DATA | CONTROL, 31 120-sample window) -> same demod "
+                      "-> chase combine with reception 1 -> LDPC")
+        return d
+
+    def setup(self, ctx, device, rank, world):
+        super().setup(ctx, device, rank, world)
+        import torch
+        from ria_b200 import sync
+        pre = sync.zc_preamble(root=2, device=device, ctx=ctx)       # DATA root
+        body = self.pool_dev[:, self.LEAD + self.PREAMBLE:self.LEAD + self.PREAMBLE + self.FRAME_LEN]
+        self.row_len2 = self.LEAD + pre.numel() + self.FRAME_LEN + self.TAIL
+        pool2 = torch.zeros((self.POOL, self.row_len2), dtype=torch.float32, device=device)
+        pool2[:, self.LEAD:self.LEAD + pre.numel()] = pre
+        pool2[:, self.LEAD + pre.numel():self.LEAD + pre.numel() + self.FRAME_LEN] = body
+        self.pool2_dev = pool2
+        self.rows2 = self.rows.view(-1)[: self.n * self.row_len2].view(self.n, self.row_len2)    # same storage, narrower rows
+        torch.cuda.synchronize()
+
+    def release(self):
+        self.pool2_dev = self.rows2 = None
+        super().release()
+
+    def step(self):
+        from ria_b200 import sim
+        sim.awgn_batch(self.pool_dev, self.n, self.SNR_DB, seed=9000 + 2 * self.epoch, first_frame_id=self.first_id,
+                       out=self.rows, ctx=self.ctx)
+        self.out = self.chain.process_batch(self.rows, self.frame_len, self.WINDOW, self.acc, True, self.out)
+        self.first_ok = self.out["ok"].clone()
+        sim.awgn_batch(self.pool2_dev, self.n, self.SNR_DB, seed=9001 + 2 * self.epoch, first_frame_id=self.first_id,
+                       out=self.rows2, ctx=self.ctx)
+        self.out = self.chain.process_batch_zc(self.rows2, self.frame_len, self.ZC_WINDOW, self.acc, False, self.out)
+        self.epoch += 1
+
+    def samples_per_step(self):
+        return float(self.n) * (self.row_len + self.row_len2)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -861,6 +920,8 @@ def chirp_traffic(windows_per_launch):
 def make_workload(name, batch):
     if name == "mcdpsk":
         return McdpskC3Workload(batch or 100_000)
+    if name == "mcdpsk_zc_retx":
+        return McdpskZcRetxWorkload(batch or 100_000)
     if name == "ldpc":
         return LdpcWorkload(batch or (1 << 20))
     if name == "ofdm_qam64_cfo":
@@ -1003,7 +1064,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ria_b200", choices=["ria_b200", "reference"])
-    ap.add_argument("--workload", default="ofdm_qam64", choices=["ofdm_qam64", "ofdm_qam64_cfo", "ofdm_cox", "ldpc", "mcdpsk"])
+    ap.add_argument("--workload", default="ofdm_qam64", choices=["ofdm_qam64", "ofdm_qam64_cfo", "ofdm_cox", "ldpc", "mcdpsk", "mcdpsk_zc_retx"])
     ap.add_argument("--batch", type=int, default=0, help="frames (or codewords per rate) per GPU")
     ap.add_argument("--e2e-batch", type=int, default=1 << 16)
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames (codewords per rate) per core")
@@ -1043,7 +1104,8 @@ def main():
     if args.workload == "ofdm_qam64" and not args.batch and not args.no_extras:
         extras = {}
         short = max(2, min(args.steps, 4))
-        for name, batch in (("ofdm_qam64_cfo", 1 << 18), ("ofdm_cox", 1 << 15), ("mcdpsk", 1 << 15), ("ldpc", 1 << 20)):
+        for name, batch in (("ofdm_qam64_cfo", 1 << 18), ("ofdm_cox", 1 << 15), ("mcdpsk", 1 << 15), ("mcdpsk_zc_retx", 1 << 15),
+                            ("ldpc", 1 << 20)):
             ctx.set_decode_flags(0)
             r = run_workload(make_workload(name, batch), ctx, stream, device, rank, world, local,
                              short, 3, min(args.e2e_batch, 1 << 15), 0, with_cpu)

@@ -443,6 +443,19 @@ int ria_mcdpsk_rx_frames_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg, const r
                              uint8_t* info_dev, int32_t info_stride, uint8_t* ok_dev, int32_t* iters_dev,
                              ria_sync_result* sync_dev);
 
+/* The same chain for connected-mode receptions, acquired on the Zadoff-Chu data preamble:
+ * MCDPSKWaveform::detectDataSync (src/waveform/mc_dpsk_waveform.cpp:227-292: ZCSync::detect with root_mask, e.g.
+ * DATA | CONTROL, in a sync_window of 31 120 samples, streaming_decoder.cpp:423-435) -> process at the reported training
+ * start with known + residual CFO (:275-281; known_cfo_dev nullable) -> chase combining -> LDPC.  A retransmission of a
+ * chirp-acquired frame (first_reception = 0, same acc_dev rows) is combined with it. */
+int ria_mcdpsk_zc_rx_frames_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg, const ria_zc_config* zc,
+                                const float* samples_dev, int64_t row_stride, int32_t sync_window,
+                                int32_t frame_len, const float* known_cfo_dev, float threshold, uint32_t root_mask,
+                                int64_t n_frames, int rate, int max_iter, float min_sum_factor,
+                                float* acc_dev, int first_reception,
+                                uint8_t* info_dev, int32_t info_stride, uint8_t* ok_dev, int32_t* iters_dev,
+                                ria_sync_result* sync_dev);
+
 /* Same with HOST buffers (single reception, no cache): chunked H2D -> chain -> D2H inside the call. */
 int ria_mcdpsk_rx_frames_host(ria_ctx* ctx, const ria_mcdpsk_config* cfg, const ria_chirp_config* chirp,
                               const float* samples, int64_t row_stride, int32_t sync_window,

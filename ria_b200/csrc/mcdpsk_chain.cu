@@ -32,6 +32,21 @@ __global__ void chain_prepare_kernel(const ria_sync_result* __restrict__ sync, l
     first[f] = static_cast<unsigned char>(first_flag);
 }
 
+// the same for a ZC-acquired reception: start = training start reported by the detector, CFO = known + residual when
+// a CFO is known (mc_dpsk_waveform.cpp:275-281)
+__global__ void chain_prepare_zc_kernel(const ria_sync_result* __restrict__ sync, const float* __restrict__ known_cfo,
+                                        long long n, int first_flag, int* __restrict__ start, float* __restrict__ cfo,
+                                        int* __restrict__ slot, unsigned char* __restrict__ first) {
+    const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (f >= n) return;
+    const ria_sync_result r = sync[f];
+    const float k = known_cfo ? known_cfo[f] : 0.0f;
+    start[f] = r.detected ? r.start_sample : -1;
+    cfo[f] = r.detected ? ((fabsf(k) > 0.1f) ? __fadd_rn(k, r.cfo_hz) : r.cfo_hz) : 0.0f;
+    slot[f] = static_cast<int>(f);
+    first[f] = static_cast<unsigned char>(first_flag);
+}
+
 int ensure_chain_scratch(ria_ctx* ctx, size_t bytes) {
     if (bytes > ctx->chain_scratch_bytes) {
         if (ctx->chain_scratch) RIA_CUDA(ctx, cudaFree(ctx->chain_scratch));
@@ -97,6 +112,53 @@ extern "C" int ria_mcdpsk_rx_frames_dev(ria_ctx* ctx, const ria_mcdpsk_config* c
                                          d_llr, llr_stride, iters_dev /* n_llr, overwritten by the decoder */, nullptr, nullptr);
     if (rc != RIA_OK) return rc;
     // ---- chase combining into the caller's accumulators, then LDPC on the sums ----
+    rc = ria_chase_combine_batch_dev(ctx, acc_dev, d_slot, d_first, d_llr, llr_stride, n_frames);
+    if (rc != RIA_OK) return rc;
+    return ria_ldpc_decode_batch_dev(ctx, rate, max_iter, min_sum_factor, acc_dev, n_frames, info_dev, info_stride,
+                                     ok_dev, iters_dev);
+}
+
+// Connected-mode receptions: the Zadoff-Chu data preamble instead of the dual chirp (SURVEY.md 8d configs[2] variant ii;
+// MCDPSKWaveform::detectDataSync, src/waveform/mc_dpsk_waveform.cpp:227-292), then the same process -> chase -> LDPC.
+extern "C" int ria_mcdpsk_zc_rx_frames_dev(ria_ctx* ctx, const ria_mcdpsk_config* cfg, const ria_zc_config* zc,
+                                           const float* samples_dev, int64_t row_stride, int32_t sync_window,
+                                           int32_t frame_len, const float* known_cfo_dev, float threshold, uint32_t root_mask,
+                                           int64_t n_frames, int rate, int max_iter, float min_sum_factor,
+                                           float* acc_dev, int first_reception,
+                                           uint8_t* info_dev, int32_t info_stride, uint8_t* ok_dev, int32_t* iters_dev,
+                                           ria_sync_result* sync_dev) {
+    using namespace ria;
+    if (!ctx || !cfg || !zc) return RIA_E_INVAL;
+    if (n_frames < 0 || frame_len <= 0 || sync_window <= 0 || row_stride < sync_window)
+        return set_error(ctx, RIA_E_INVAL, "mcdpsk zc rx: bad sizes");
+    if (n_frames == 0) return RIA_OK;
+    if (!samples_dev || !acc_dev || !info_dev || !ok_dev || !iters_dev || !sync_dev)
+        return set_error(ctx, RIA_E_INVAL, "mcdpsk zc rx: null buffer");
+    const int n_soft = ria_mcdpsk_soft_bits_per_frame(cfg, frame_len);
+    if (n_soft < RIA_LDPC_N) return set_error(ctx, RIA_E_INVAL, "mcdpsk zc rx: frame_len %d holds %d soft bits, one codeword needs %d",
+                                             frame_len, n_soft, RIA_LDPC_N);
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int llr_stride = (n_soft + 3) & ~3;
+    const size_t b_llr = static_cast<size_t>(n_frames) * llr_stride * sizeof(float);
+    const size_t b_i = (static_cast<size_t>(n_frames) * 4 + 255) & ~size_t(255);
+    int rc = ensure_chain_scratch(ctx, b_llr + 4 * b_i + 256);
+    if (rc != RIA_OK) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->chain_scratch);
+    float* d_llr = reinterpret_cast<float*>(base);
+    int* d_start = reinterpret_cast<int*>(base + b_llr);
+    float* d_cfo = reinterpret_cast<float*>(base + b_llr + b_i);
+    int* d_slot = reinterpret_cast<int*>(base + b_llr + 2 * b_i);
+    unsigned char* d_first = base + b_llr + 3 * b_i;
+    rc = ria_zc_detect_batch_dev(ctx, zc, samples_dev, row_stride, sync_window, known_cfo_dev, threshold, root_mask, n_frames, sync_dev);
+    if (rc != RIA_OK) return rc;
+    chain_prepare_zc_kernel<<<static_cast<unsigned>((n_frames + 255) / 256), 256, 0, st>>>(
+        sync_dev, known_cfo_dev, n_frames, first_reception ? 1 : 0, d_start, d_cfo, d_slot, d_first);
+    RIA_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    rc = ria_mcdpsk_process_batch_at_dev(ctx, cfg, samples_dev, row_stride, frame_len, d_start, d_cfo, nullptr, n_frames,
+                                         d_llr, llr_stride, iters_dev, nullptr, nullptr);
+    if (rc != RIA_OK) return rc;
     rc = ria_chase_combine_batch_dev(ctx, acc_dev, d_slot, d_first, d_llr, llr_stride, n_frames);
     if (rc != RIA_OK) return rc;
     return ria_ldpc_decode_batch_dev(ctx, rate, max_iter, min_sum_factor, acc_dev, n_frames, info_dev, info_stride,

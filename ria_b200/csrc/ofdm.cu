@@ -203,9 +203,11 @@ __device__ float2 hard_decision(float2 s, int mod) {
         }
         case RIA_QAM64: {
             const float d = 0.1543f;
+            // the reference's chain of seven ascending thresholds (first true wins) as a three-level search over the
+            // same threshold and level expressions: identical result for every x, NaN included (all compares false)
             auto sl = [d](float x) {
-                return x < -6 * d ? -7 * d : x < -4 * d ? -5 * d : x < -2 * d ? -3 * d : x < 0 ? -d
-                     : x < 2 * d ? d : x < 4 * d ? 3 * d : x < 6 * d ? 5 * d : 7 * d; };
+                return x < 0 ? (x < -4 * d ? (x < -6 * d ? -7 * d : -5 * d) : (x < -2 * d ? -3 * d : -d))
+                             : (x < 4 * d ? (x < 2 * d ? d : 3 * d) : (x < 6 * d ? 5 * d : 7 * d)); };
             return make_float2(sl(s.x), sl(s.y));
         }
         default:   // QPSK and everything else

@@ -138,6 +138,36 @@ class McdpskRxChain:
             _ptr(out["iters"]), _ptr(out["sync"])))
         return out
 
+    def process_batch_zc(self, rows: torch.Tensor, frame_len: int, sync_window: int, acc: torch.Tensor,
+                         first_reception: bool = False, out=None, known_cfo_hz: Optional[torch.Tensor] = None,
+                         threshold: float = 0.2):
+        """The same chain for connected-mode receptions behind the Zadoff-Chu data preamble
+        (``ria_mcdpsk_zc_rx_frames_dev``): ZC detect (roots DATA | CONTROL) -> process -> chase -> LDPC."""
+        from .sync import SYNC_RESULT_DTYPE, ZCConfig, ZC_ROOT_MASK_CONTROL, ZC_ROOT_MASK_DATA
+        if not (isinstance(rows, torch.Tensor) and rows.is_cuda and rows.dtype == torch.float32 and rows.dim() == 2):
+            raise RiaError("process_batch_zc wants CUDA fp32 [n_frames, row_len] (no CPU fallback)")
+        if rows.stride(1) != 1:
+            rows = rows.contiguous()
+        n = rows.shape[0]
+        dev = rows.device
+        info_stride = (self.info_bytes + 3) & ~3
+        if out is None:
+            out = dict(info=torch.empty((n, info_stride), dtype=torch.uint8, device=dev),
+                       ok=torch.empty((n,), dtype=torch.uint8, device=dev),
+                       iters=torch.empty((n,), dtype=torch.int32, device=dev),
+                       sync=torch.empty((n, SYNC_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev))
+        out["acc"] = acc
+        if not hasattr(self, "_zc"):
+            self._zc = ZCConfig.default()
+        ctx = self.ctx
+        ctx.set_stream(torch.cuda.current_stream(dev))
+        ctx.check(lib().ria_mcdpsk_zc_rx_frames_dev(
+            ctx.handle, C.addressof(self.config), C.addressof(self._zc), _ptr(rows), rows.stride(0), int(sync_window),
+            int(frame_len), _ptr(known_cfo_hz), float(threshold), ZC_ROOT_MASK_DATA | ZC_ROOT_MASK_CONTROL, n, self.rate,
+            self.max_iter, self.factor, _ptr(acc), int(bool(first_reception)), _ptr(out["info"]), out["info"].stride(0),
+            _ptr(out["ok"]), _ptr(out["iters"]), _ptr(out["sync"])))
+        return out
+
     def process_batch_host(self, rows, frame_len: int, sync_window: int):
         """rows: host fp32 array or (pinned) CPU tensor [n, row_len]; H2D, chain and D2H happen inside the call."""
         import numpy as np
