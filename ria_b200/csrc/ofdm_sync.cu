@@ -25,7 +25,7 @@ namespace {
 
 constexpr int kTaps = 65;
 constexpr int kDelay = 32;
-constexpr int kThreads = 512;          // one CTA per SM (the tile is ~100 KB): 16 warps to hide the shared-memory latency
+constexpr int kThreads = 512;          // one CTA per SM (tile + energy plane ~140 KB)
 constexpr int kMaxCand = 1280;         // >= the widest coarse grid: 8 symbols / 8, symbols <= 1160 samples
 
 __device__ __forceinline__ float cabs_d(float2 a) {
@@ -38,13 +38,14 @@ struct SyncArgs {
     const float* known_cfo; float threshold; int sym; float sample_rate;
     const float* taps_g;
     int an_cap;                                 // analytic samples the shared-memory tile holds
+    int an_words;                               // float2 slots of the tile; the energy plane (floats, same padding) follows
     ria_sync_result* out;
 };
 
 // The analytic signal of the span the search touches lives in shared memory, sample i of the span at
-// an_pad(i) = i + (i >> 3): candidates are 8 samples apart, so the threads of a half-warp (one candidate each) read
-// float2 words 9 apart -- sixteen different bank pairs.
-__device__ __forceinline__ int an_pad(int i) { return i + (i >> 3); }
+// an_pad(i) = i + (i >> 5).  In the coarse search a thread owns four neighbouring candidates (32 samples), so the threads
+// of a warp read float2 words 33 apart (and floats 33 apart in the energy plane): an odd stride, conflict-free.
+__device__ __forceinline__ int an_pad(int i) { return i + (i >> 5); }
 
 // Blackwell packed fp32; products only ever feed scalar adds (ptxas would contract a packed multiply into a packed add)
 __device__ __forceinline__ float2 ds_mul2s(float s, float2 b) {
@@ -84,32 +85,46 @@ __device__ __forceinline__ void lag_corr(const float2* an, int offset, int sym, 
     *P_out = P;
 }
 
-// The coarse grid: candidate c sits at tile offset 8 c.  Its second energy sum, over [8 c + sym, 8 c + 2 sym), is the
-// FIRST energy sum of the candidate sym / 8 places further on -- the same terms in the same order, hence the same
-// float -- so each thread accumulates P and one energy, and extra threads supply the energies past the last candidate.
-// Same products and sums as lag_corr: conj(s1) s2 = (s1x s2x + s1y s2y, s1x s2y - s1y s2x), a - (-t) = a + t exactly.
-__device__ __forceinline__ void coarse_corr(const float2* an, int offset, int sym, bool want_p, float2* P_out, float* e_out) {
-    float2 P = make_float2(0.f, 0.f);
-    float e1 = 0.f;
-    if (want_p) {
-#pragma unroll 2
-        for (int n = 0; n < sym; ++n) {
-            const float2 s1 = an[an_pad(offset + n)], s2 = an[an_pad(offset + n + sym)];
-            const float2 p1 = ds_mul2s(s1.x, s2);                              // (s1x s2x, s1x s2y)
-            const float2 p2 = ds_mul2s(s1.y, make_float2(s2.y, s2.x));         // (s1y s2y, s1y s2x)
-            P = ds_add2(P, make_float2(__fadd_rn(p1.x, p2.x), __fsub_rn(p1.y, p2.y)));
-            const float2 sq = ds_mul2(s1, s1);
-            e1 = __fadd_rn(e1, __fadd_rn(sq.x, sq.y));
-        }
-    } else {
-#pragma unroll 4
-        for (int n = 0; n < sym; ++n) {
-            const float2 s1 = an[an_pad(offset + n)];
-            const float2 sq = ds_mul2(s1, s1);
-            e1 = __fadd_rn(e1, __fadd_rn(sq.x, sq.y));
-        }
+// The coarse grid: candidate c sits at tile offset 8 c and sums, in sample order (:283-295),
+//   P(c) = sum_n conj(a[8c+n]) a[8c+n+sym],   e1(c) = sum_n |a[8c+n]|^2,   e2(c) = sum_n |a[8c+n+sym]|^2 = e1(c + sym/8).
+// The TERMS depend on the sample index k = 8c + n alone, so they are formed once per sample -- T[k] = conj(a[k]) a[k+sym]
+// (in place of a[k]) and E[k] = |a[k]|^2 -- with the reference's products (conj(s1) s2 = (s1x s2x + s1y s2y,
+// s1x s2y - s1y s2x); a - (-t) = a + t exactly), and a candidate only ADDS its 'sym' terms in order: the same floats
+// added in the same order as the reference's loop.  A thread owns four neighbouring candidates and slides a window of
+// four 8-sample blocks over the term planes, loading each block once.
+constexpr int kCandPerThread = 4;
+
+struct Blk { float2 t[8]; float e[8]; };
+
+__device__ __forceinline__ void load_blk(const float2* T, const float* E, int b, Blk& o) {
+    const int base = an_pad(8 * b);            // 8 b is a multiple of 8: the block sits inside one padded group of 32
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o.t[j] = T[base + j]; o.e[j] = E[base + j]; }
+}
+__device__ __forceinline__ void add_blk(const Blk& b, float2& P, float& e) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { P = ds_add2(P, b.t[j]); e = __fadd_rn(e, b.e[j]); }
+}
+
+// candidates c0 .. c0+3: (P, e1) each
+__device__ __forceinline__ void coarse_quad(const float2* T, const float* E, int c0, int n_blocks, float2 (&P)[4], float (&e)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { P[q] = make_float2(0.f, 0.f); e[q] = 0.f; }
+    Blk w0, w1, w2, w3;
+    load_blk(T, E, c0, w0); load_blk(T, E, c0 + 1, w1); load_blk(T, E, c0 + 2, w2);
+    int b = 0;
+    // step b adds block (c0 + q + b) to candidate q; the window rotates through four names
+    for (; b + 4 <= n_blocks; b += 4) {
+        load_blk(T, E, c0 + 3 + b, w3); add_blk(w0, P[0], e[0]); add_blk(w1, P[1], e[1]); add_blk(w2, P[2], e[2]); add_blk(w3, P[3], e[3]);
+        load_blk(T, E, c0 + 4 + b, w0); add_blk(w1, P[0], e[0]); add_blk(w2, P[1], e[1]); add_blk(w3, P[2], e[2]); add_blk(w0, P[3], e[3]);
+        load_blk(T, E, c0 + 5 + b, w1); add_blk(w2, P[0], e[0]); add_blk(w3, P[1], e[1]); add_blk(w0, P[2], e[2]); add_blk(w1, P[3], e[3]);
+        load_blk(T, E, c0 + 6 + b, w2); add_blk(w3, P[0], e[0]); add_blk(w0, P[1], e[1]); add_blk(w1, P[2], e[2]); add_blk(w2, P[3], e[3]);
     }
-    *P_out = P; *e_out = e1;
+    for (; b < n_blocks; ++b) {                // n_blocks % 4 leftover steps
+        load_blk(T, E, c0 + 3 + b, w3);
+        add_blk(w0, P[0], e[0]); add_blk(w1, P[1], e[1]); add_blk(w2, P[2], e[2]); add_blk(w3, P[3], e[3]);
+        w0 = w1; w1 = w2; w2 = w3;
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -133,11 +148,25 @@ ofdm_data_sync_kernel(const SyncArgs a) {
     if (N < sym * 3) { if (tid == 0) a.out[f] = res; return; }      // :222-224
 
     if (tid < kTaps) taps[tid] = a.taps_g[tid];
-    // ---- energy gate (:232-260) ----
+    // The window is staged once in the energy plane (it is free until the term planes are built): the energy gate, the
+    // signal-start search and the Hilbert FIR then read shared memory.  Windows longer than the plane fall back to global.
+    float* xs = reinterpret_cast<float*>(an_tile + a.an_words);
+    const bool staged = N + 8 <= a.an_words;
+    if (staged) for (int i = tid; i < N; i += kThreads) xs[i] = x[i];
+    __syncthreads();
+    const float* xr = staged ? xs : x;                              // same values either way
+    // ---- energy gate (:232-260): a sequential sum of up to 4800 squares ----
+    const int ns = min(N / 4, 4800);
     if (tid == 0) {
-        const int ns = min(N / 4, 4800);
         float nf = 0.0f;
-        for (int i = 0; i < ns; ++i) nf = __fadd_rn(nf, __fmul_rn(x[i], x[i]));
+        int i = 0;
+        if (staged)
+            for (; i + 4 <= ns; i += 4) {
+                const float4 q = *reinterpret_cast<const float4*>(xs + i);
+                nf = __fadd_rn(nf, __fmul_rn(q.x, q.x)); nf = __fadd_rn(nf, __fmul_rn(q.y, q.y));
+                nf = __fadd_rn(nf, __fmul_rn(q.z, q.z)); nf = __fadd_rn(nf, __fmul_rn(q.w, q.w));
+            }
+        for (; i < ns; ++i) nf = __fadd_rn(nf, __fmul_rn(xr[i], xr[i]));
         nf = sqrtf(nf / ns);
         s_f[0] = nf;
         s_f[1] = nf * 3.0f + 0.01f;
@@ -151,7 +180,12 @@ ofdm_data_sync_kernel(const SyncArgs a) {
         const int lim = N - sym * 2;
         for (int i = tid; i < lim && i < first; i += kThreads) {
             float e = 0.0f;
-            for (int j = 0; j < 64; ++j) if (i + j < N) e = __fadd_rn(e, __fmul_rn(x[i + j], x[i + j]));
+            if (i + 64 <= N) {
+#pragma unroll 8
+                for (int j = 0; j < 64; ++j) e = __fadd_rn(e, __fmul_rn(xr[i + j], xr[i + j]));
+            } else {
+                for (int j = 0; j < 64; ++j) if (i + j < N) e = __fadd_rn(e, __fmul_rn(xr[i + j], xr[i + j]));
+            }
             e = sqrtf(e / 64);
             if (e > thr) { first = i; break; }
         }
@@ -169,28 +203,87 @@ ofdm_data_sync_kernel(const SyncArgs a) {
     // The tile starts at the first candidate (the refinement never goes below signal_start, :327).
     const int an_lo = signal_start, an_hi = min(N, search_end + 2 * sym + 8);
     float2* an = an_tile;
-    for (int i = an_lo + tid; i < an_hi && i - an_lo < a.an_cap; i += kThreads) {
+    float* E = reinterpret_cast<float*>(an_tile + a.an_words);
+    // src[j] = sample j of the window (src = the staged copy, or a re-staged piece of it shifted by `shift`)
+    auto analytic_at = [&](const float* src, int shift, int i) {
         float q = 0.0f;
+#pragma unroll 8
         for (int k = 1; k < kTaps; k += 2) {                       // even taps are exactly zero
             const int j = i - k;
-            const float v = (j >= 0) ? x[j] : 0.0f;
+            const float v = (j >= 0) ? src[j - shift] : 0.0f;
             q = __fadd_rn(q, __fmul_rn(taps[k], v));
         }
-        an[an_pad(i - an_lo)] = make_float2(i >= kDelay ? x[i - kDelay] : 0.0f, q);
-    }
+        return make_float2(i >= kDelay ? src[i - kDelay - shift] : 0.0f, q);
+    };
+    for (int i = an_lo + tid; i < an_hi && i - an_lo < a.an_cap; i += kThreads) an[an_pad(i - an_lo)] = analytic_at(xr, 0, i);
     __syncthreads();
 
     // ---- coarse candidates, all in parallel (:283-312) ----
     int n_cand = (search_end > signal_start) ? (search_end - signal_start + 7) / 8 : 0;
     if (n_cand > kMaxCand) n_cand = kMaxCand;
     const bool share = (sym % 8) == 0 && sym / 8 <= 520;            // second energy = first energy sym / 8 places on
-    if (share) {
+    if (share && n_cand > 0) {
         const int hop = sym / 8;
-        for (int c = tid; c < n_cand + hop; c += kThreads) {
-            float2 P; float e;
-            coarse_corr(an, 8 * c, sym, c < n_cand, &P, &e);
-            e_sum[c] = e;
-            if (c < n_cand) { cand[kMaxCand + c] = P.x; cand[2 * kMaxCand + c] = P.y; }
+        const int have = min(an_hi - an_lo, a.an_cap);              // analytic samples in the tile
+        // term planes: T[k] needs a[k] and a[k + sym]; candidates past the data read zeros, as the tile did before
+        const int n_e = min(have, 8 * (n_cand + hop - 1) + sym);
+        const int n_t = min(max(have - sym, 0), 8 * (n_cand - 1) + sym);
+        // in place, ascending chunks of <= sym samples: a chunk reads a[k], a[k + sym], then (barrier) writes T[k] over a[k]
+        const int chunk = (sym < 2 * kThreads) ? kThreads : 2 * kThreads;
+        for (int k0 = 0; k0 < n_e; k0 += chunk) {
+            float2 tv[2]; float ev[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int k = k0 + tid + u * kThreads;
+                tv[u] = make_float2(0.f, 0.f); ev[u] = 0.f;
+                if (u * kThreads < chunk && k < n_e) {
+                    const float2 s1 = an[an_pad(k)];
+                    const float2 sq = ds_mul2(s1, s1);
+                    ev[u] = __fadd_rn(sq.x, sq.y);
+                    if (k < n_t) {
+                        const float2 s2 = an[an_pad(k + sym)];
+                        const float2 p1 = ds_mul2s(s1.x, s2);                              // (s1x s2x, s1x s2y)
+                        const float2 p2 = ds_mul2s(s1.y, make_float2(s2.y, s2.x));         // (s1y s2y, s1y s2x)
+                        tv[u] = make_float2(__fadd_rn(p1.x, p2.x), __fsub_rn(p1.y, p2.y));
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int k = k0 + tid + u * kThreads;
+                if (u * kThreads < chunk && k < n_e) { an[an_pad(k)] = tv[u]; E[an_pad(k)] = ev[u]; }
+            }
+            __syncthreads();
+        }
+        // zero what the sliding windows may touch past the planes (a block is loaded whole)
+        const int n_zero = 8 * (n_cand + hop + kCandPerThread + 4) + sym;
+        for (int k = n_e + tid; k < n_zero && k < a.an_cap; k += kThreads) { an[an_pad(k)] = make_float2(0.f, 0.f); E[an_pad(k)] = 0.f; }
+        for (int k = n_t + tid; k < n_e; k += kThreads) an[an_pad(k)] = make_float2(0.f, 0.f);
+        __syncthreads();
+        const int n_quads = (n_cand + kCandPerThread - 1) / kCandPerThread;
+        const int n_blocks = sym / 8;
+        if (tid < n_quads) {
+            float2 P[4]; float e[4];
+            coarse_quad(an, E, kCandPerThread * tid, n_blocks, P, e);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = kCandPerThread * tid + q;
+                if (c < n_cand) { e_sum[c] = e[q]; cand[kMaxCand + c] = P[q].x; cand[2 * kMaxCand + c] = P[q].y; }
+            }
+        } else {
+            // the other warps: first energy sums of the grid positions behind the last candidate (second energies of the
+            // last sym / 8 candidates)
+            const int first_tail_thread = (n_quads + 31) & ~31;
+            for (int c = n_cand + (tid - first_tail_thread); tid >= first_tail_thread && c < n_cand + hop; c += kThreads - first_tail_thread) {
+                float e1 = 0.f;
+                for (int b = 0; b < n_blocks; ++b) {
+                    const float* eb = E + an_pad(8 * (c + b));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) e1 = __fadd_rn(e1, eb[j]);
+                }
+                e_sum[c] = e1;
+            }
         }
         __syncthreads();
         for (int c = tid; c < n_cand; c += kThreads) {
@@ -220,10 +313,54 @@ ofdm_data_sync_kernel(const SyncArgs a) {
     // ---- +-4 refinement (:318-350) ----
     if (best_corr > a.threshold) {
         const int r0 = max(signal_start, best_offset - 4), r1 = min(search_end, best_offset + 5);
-        if (tid < r1 - r0 && r0 + tid != best_offset) {
-            float corr; float2 P;
-            lag_corr(an, r0 + tid - an_lo, sym, &corr, &P);
-            cand[tid] = corr; cand[kMaxCand + tid] = P.x; cand[2 * kMaxCand + tid] = P.y;
+        // The fine lags are one sample apart: their terms T[k] = conj(a[k]) a[k + sym], E[k] = |a[k]|^2 over
+        // k in [r0, r1 + 2 sym) are formed once, then one thread per (lag, sum) walks its 'sym' terms in order
+        // (lag_corr's three sums, :283-295).  Layout inside the tile: analytic samples | T plane | E plane.
+        const int n_fine = r1 - r0;
+        const int fine_hi = min(N, r1 + 2 * sym);
+        const int n_an = fine_hi - r0;                               // analytic samples of the fine lags
+        {
+            // re-stage the samples the FIR needs (the energy plane held terms) and rebuild the analytic samples
+            const int lo = max(0, r0 - kTaps);
+            __syncthreads();
+            if (staged) for (int i = lo + tid; i < fine_hi; i += kThreads) xs[i - lo] = x[i];
+            __syncthreads();
+            for (int i = r0 + tid; i < fine_hi; i += kThreads) an[an_pad(i - r0)] = staged ? analytic_at(xs, lo, i) : analytic_at(x, 0, i);
+            __syncthreads();
+        }
+        float2* FT = an + an_pad(n_an) + 8;                          // n_fine - 1 + sym terms
+        float* FE = reinterpret_cast<float*>(FT + (n_fine + sym + 8)); // n_fine - 1 + 2 sym terms
+        for (int k = tid; k < n_an; k += kThreads) {
+            const float2 s1 = an[an_pad(k)];
+            FE[k] = __fadd_rn(__fmul_rn(s1.x, s1.x), __fmul_rn(s1.y, s1.y));
+            if (k + sym < n_an) {
+                const float2 s2 = an[an_pad(k + sym)];
+                FT[k] = make_float2(__fsub_rn(__fmul_rn(s1.x, s2.x), __fmul_rn(-s1.y, s2.y)),
+                                    __fadd_rn(__fmul_rn(s1.x, s2.y), __fmul_rn(-s1.y, s2.x)));
+            }
+        }
+        __syncthreads();
+        if (tid < 3 * n_fine) {
+            const int d = tid / 3, kind = tid - 3 * d;               // 0: P, 1: e1, 2: e2
+            if (r0 + d != best_offset) {
+                if (kind == 0) {
+                    float2 P = make_float2(0.f, 0.f);
+#pragma unroll 4
+                    for (int n = 0; n < sym; ++n) { const float2 t = FT[d + n]; P.x = __fadd_rn(P.x, t.x); P.y = __fadd_rn(P.y, t.y); }
+                    cand[kMaxCand + d] = P.x; cand[2 * kMaxCand + d] = P.y;
+                } else {
+                    const float* e = FE + d + (kind == 2 ? sym : 0);
+                    float acc = 0.f;
+#pragma unroll 4
+                    for (int n = 0; n < sym; ++n) acc = __fadd_rn(acc, e[n]);
+                    e_sum[2 * d + (kind - 1)] = acc;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < n_fine && r0 + tid != best_offset) {
+            const float denom = __fadd_rn(sqrtf(__fmul_rn(e_sum[2 * tid], e_sum[2 * tid + 1])), 1e-10f);
+            cand[tid] = __fdiv_rn(cabs_d(make_float2(cand[kMaxCand + tid], cand[2 * kMaxCand + tid])), denom);
         }
         __syncthreads();
         if (tid == 0) {
@@ -286,7 +423,8 @@ extern "C" int ria_ofdm_data_sync_batch_dev(ria_ctx* ctx, const ria_modem_config
     // shared-memory tile: the widest search is 8 symbols (buffer starts inside a burst, :273-276) plus the two symbols
     // the last candidate correlates over, padded one word per eight
     const int an_cap = 10 * sym + 16;
-    const size_t smem = static_cast<size_t>(an_cap + an_cap / 8 + 8) * sizeof(float2);
+    const int an_words = an_cap + an_cap / 32 + 8;
+    const size_t smem = static_cast<size_t>(an_words) * (sizeof(float2) + sizeof(float));
     if (smem + 48 * 1024 > ctx->smem_optin) return set_error(ctx, RIA_E_UNSUPPORTED, "data sync: symbol too long for the shared-memory tile");
     RIA_CUDA(ctx, cudaFuncSetAttribute(ofdm_data_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     SyncArgs a{};
@@ -294,6 +432,7 @@ extern "C" int ria_ofdm_data_sync_batch_dev(ria_ctx* ctx, const ria_modem_config
     a.known_cfo = known_cfo_dev; a.threshold = threshold; a.sym = sym; a.sample_rate = static_cast<float>(cfg->sample_rate);
     a.taps_g = ctx->hilbert65;
     a.an_cap = an_cap;
+    a.an_words = an_words;
     a.out = out_dev;
     time_begin(ctx, KK_OFDM_SYNC);
     ofdm_data_sync_kernel<<<static_cast<unsigned>(n_frames), kThreads, smem, ctx->stream>>>(a);

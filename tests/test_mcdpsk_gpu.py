@@ -211,3 +211,61 @@ def test_chirp_acquired_chain_matches_reference(ctx, ref, port):
         if second["ok"][i]:
             assert bytes(second["info"][i, :20]) == sent[i].tobytes()
     assert combined_better >= 0 and second["ok"].sum() >= 8
+
+
+def test_zc_acquired_retransmission_chain_matches_reference(ctx, ref, port):
+    """ria_mcdpsk_zc_rx_frames_dev: a frame first received behind the dual chirp, then retransmitted in connected mode
+    behind the Zadoff-Chu data preamble (MCDPSKWaveform::detectDataSync, roots DATA | CONTROL, 31 120-sample window):
+    ZC sync result exact, the chase-combined decode equal to the reference run stage by stage on the same rows."""
+    import torch
+    from oracle.bindings import ZcConfig
+    from ria_b200 import mcdpsk, txsynth
+    from ria_b200.sync import SYNC_RESULT_DTYPE
+    cfg = McdpskConfig.make(1, 4, 10)
+    rcfg = mcdpsk.MultiCarrierDPSKConfig.from_buffer_copy(bytes(cfg))
+    rng = np.random.default_rng(33)
+    chirp = txsynth.chirp_preamble()
+    zc = ZcConfig.default()
+    zpre = ref.zc_preamble(zc, 2)                                       # DATA root
+    rows1, rows2, sent = [], [], []
+    frame_len = None
+    for i in range(10):
+        data = rng.integers(0, 256, size=20, dtype=np.uint8)
+        cw = port.ldpc_encode(R1_4, data)[:81]
+        body = txsynth.mcdpsk_modulate_frame(rcfg, cw.tobytes())
+        frame_len = len(body)
+        tx1 = np.concatenate([np.zeros(1500 + 37 * i, np.float32), chirp, body, np.zeros(1200 - 37 * i, np.float32)])
+        lead2 = 900 + 211 * i
+        tx2 = np.concatenate([np.zeros(lead2, np.float32), zpre, body, np.zeros(4000 - lead2, np.float32)])
+        rows1.append(awgn(tx1, -8.0, rng))
+        rows2.append(awgn(tx2, -5.0, rng))
+        sent.append(data)
+    chain = mcdpsk.McdpskRxChain(rcfg, R1_4, 50, 0.9375, 0.15, ctx)
+    r1 = chain.process_batch(torch.from_numpy(np.stack(rows1)).cuda(), frame_len, 120000, None, True)
+    torch.cuda.synchronize()
+    first = {k: v.cpu().numpy().copy() for k, v in r1.items()}
+    r2 = chain.process_batch_zc(torch.from_numpy(np.stack(rows2)).cuda(), frame_len, 31120, r1["acc"], False, None, None, 0.2)
+    torch.cuda.synchronize()
+    second = {k: v.cpu().numpy().copy() for k, v in r2.items()}
+    n_ok = n_det = 0
+    for i in range(10):
+        g1 = first["sync"].view(SYNC_RESULT_DTYPE)[i, 0]
+        s1 = ref.chirp_detect_dual(rows1[i][:120000], 0.15)
+        assert s1.detected and int(g1["aux"]) == int(s1.aux)
+        a = ref.mcdpsk_process(cfg, rows1[i][int(s1.aux) + 28800:int(s1.aux) + 28800 + frame_len], float(g1["cfo_hz"]))["soft"][:648]
+        g2 = second["sync"].view(SYNC_RESULT_DTYPE)[i, 0]
+        s2 = ref.zc_detect(zc, rows2[i][:31120], 0.2, 4 | 8, 0.0)
+        assert bool(g2["detected"]) == bool(s2.detected), i
+        if not s2.detected:
+            continue
+        n_det += 1
+        assert int(g2["start_sample"]) == int(s2.start_sample) and np.float32(g2["cfo_hz"]) == np.float32(s2.cfo_hz), i
+        st = int(s2.start_sample)
+        b = ref.mcdpsk_process(cfg, rows2[i][st:st + frame_len], float(s2.cfo_hz))["soft"][:648]
+        w = ref.ldpc_decode_batch(R1_4, (a.astype(np.float32) + b.astype(np.float32)).astype(np.float32), 50, 0.9375, 24)
+        assert second["ok"][i] == w[1][0] and second["iters"][i] == w[2][0], (i, second["ok"][i], w[1][0])
+        assert np.array_equal(second["info"][i, :21], w[0][0][:21])
+        if second["ok"][i]:
+            assert bytes(second["info"][i, :20]) == sent[i].tobytes()
+            n_ok += 1
+    assert n_det >= 6 and n_ok >= 5, (n_det, n_ok)
