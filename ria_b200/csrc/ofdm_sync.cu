@@ -25,7 +25,7 @@ namespace {
 
 constexpr int kTaps = 65;
 constexpr int kDelay = 32;
-constexpr int kThreads = 512;          // one CTA per SM (tile + energy plane ~140 KB)
+constexpr int kThreads = 256;          // two CTAs per SM (tile + energy plane ~84 KB each)
 constexpr int kMaxCand = 1280;         // >= the widest coarse grid: 8 symbols / 8, symbols <= 1160 samples
 
 __device__ __forceinline__ float cabs_d(float2 a) {
@@ -127,9 +127,9 @@ __device__ __forceinline__ void coarse_quad(const float2* T, const float* E, int
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 ofdm_data_sync_kernel(const SyncArgs a) {
-    extern __shared__ __align__(16) float2 an_tile[];          // analytic signal of the searched span, padded (an_pad)
+    extern __shared__ __align__(16) float2 an_tile[];          // analytic samples, then product terms, of one pass (an_pad)
     __shared__ float taps[kTaps + 3];
     __shared__ int s_i[kThreads];
     __shared__ float s_f[4];
@@ -148,10 +148,11 @@ ofdm_data_sync_kernel(const SyncArgs a) {
     if (N < sym * 3) { if (tid == 0) a.out[f] = res; return; }      // :222-224
 
     if (tid < kTaps) taps[tid] = a.taps_g[tid];
-    // The window is staged once in the energy plane (it is free until the term planes are built): the energy gate, the
-    // signal-start search and the Hilbert FIR then read shared memory.  Windows longer than the plane fall back to global.
-    float* xs = reinterpret_cast<float*>(an_tile + a.an_words);
-    const bool staged = N + 8 <= a.an_words;
+    float* E = reinterpret_cast<float*>(an_tile + a.an_words);       // energy plane; before that, staged samples
+    // The window is staged once as floats in the tile (free until the first pass builds its analytic samples): the energy
+    // gate and the signal-start search then read shared memory.  Windows longer than the tile fall back to global memory.
+    float* xs = reinterpret_cast<float*>(an_tile);
+    const bool staged = N + 8 <= 2 * a.an_words;
     if (staged) for (int i = tid; i < N; i += kThreads) xs[i] = x[i];
     __syncthreads();
     const float* xr = staged ? xs : x;                              // same values either way
@@ -199,13 +200,8 @@ ofdm_data_sync_kernel(const SyncArgs a) {
     const int actual = in_noise ? search_window : max(search_window, sym * 8);
     const int search_end = min(signal_start + actual, N - sym * 2);
 
-    // ---- analytic signal over the span the search touches (:266-270, filters.cpp:293-317) ----
-    // The tile starts at the first candidate (the refinement never goes below signal_start, :327).
-    const int an_lo = signal_start, an_hi = min(N, search_end + 2 * sym + 8);
-    float2* an = an_tile;
-    float* E = reinterpret_cast<float*>(an_tile + a.an_words);
-    // src[j] = sample j of the window (src = the staged copy, or a re-staged piece of it shifted by `shift`)
-    auto analytic_at = [&](const float* src, int shift, int i) {
+    // src[j - shift] = sample j of the window (a staged piece of it that starts at sample `shift`, or the window itself)
+    auto analytic_at = [&](const float* src, int shift, int i) {      // (:266-270, filters.cpp:293-317)
         float q = 0.0f;
 #pragma unroll 8
         for (int k = 1; k < kTaps; k += 2) {                       // even taps are exactly zero
@@ -215,99 +211,119 @@ ofdm_data_sync_kernel(const SyncArgs a) {
         }
         return make_float2(i >= kDelay ? src[i - kDelay - shift] : 0.0f, q);
     };
-    for (int i = an_lo + tid; i < an_hi && i - an_lo < a.an_cap; i += kThreads) an[an_pad(i - an_lo)] = analytic_at(xr, 0, i);
-    __syncthreads();
+    // samples [lo, hi) of the window -> the energy plane; analytic samples [alo, hi) -> the tile (tile index 0 = alo)
+    auto build_analytic = [&](int alo, int hi) {
+        const int lo = max(0, alo - kTaps);
+        __syncthreads();
+        for (int i = lo + tid; i < hi; i += kThreads) E[i - lo] = x[i];
+        __syncthreads();
+        for (int i = alo + tid; i < hi; i += kThreads) an_tile[an_pad(i - alo)] = analytic_at(E, lo, i);
+        __syncthreads();
+    };
+    float2* an = an_tile;
 
-    // ---- coarse candidates, all in parallel (:283-312) ----
+    // ---- coarse candidates (:283-312), in passes of at most kPassCand candidates (four symbols of offsets): a pass
+    // stages its span, forms its term planes and sums its candidates; the scan semantics (running best, first > 0.95
+    // stops) are applied after each pass, so a hit in the first pass ends the search like the reference's break ----
     int n_cand = (search_end > signal_start) ? (search_end - signal_start + 7) / 8 : 0;
     if (n_cand > kMaxCand) n_cand = kMaxCand;
     const bool share = (sym % 8) == 0 && sym / 8 <= 520;            // second energy = first energy sym / 8 places on
-    if (share && n_cand > 0) {
-        const int hop = sym / 8;
-        const int have = min(an_hi - an_lo, a.an_cap);              // analytic samples in the tile
-        // term planes: T[k] needs a[k] and a[k + sym]; candidates past the data read zeros, as the tile did before
-        const int n_e = min(have, 8 * (n_cand + hop - 1) + sym);
-        const int n_t = min(max(have - sym, 0), 8 * (n_cand - 1) + sym);
-        // in place, ascending chunks of <= sym samples: a chunk reads a[k], a[k + sym], then (barrier) writes T[k] over a[k]
-        const int chunk = (sym < 2 * kThreads) ? kThreads : 2 * kThreads;
-        for (int k0 = 0; k0 < n_e; k0 += chunk) {
-            float2 tv[2]; float ev[2];
+    const int hop = sym / 8, n_blocks = sym / 8;
+    // a pass of nc candidates needs 8 (nc + hop - 1) + sym terms (term planes) or 8 (nc - 1) + 2 sym analytic samples
+    const int pass_cand = share ? (max(8, (a.an_cap - sym) / 8 + 1 - hop - 8) & ~3) : max(8, (a.an_cap - 2 * sym) / 8);
+    if (tid == 0) { s_f[2] = 0.0f; s_n[0] = 0; s_f[0] = 0.f; s_f[1] = 0.f; s_n[1] = 0; }
+    __syncthreads();
+    for (int c_lo = 0; c_lo < n_cand; c_lo += pass_cand) {
+        const int nc = min(pass_cand, n_cand - c_lo);                // candidates of this pass
+        const int alo = signal_start + 8 * c_lo;                     // tile origin
+        if (share) {
+            const int want = 8 * (nc + hop - 1) + sym;               // energy terms the pass sums
+            const int hi = min(N, alo + want);
+            build_analytic(alo, hi);
+            const int have = hi - alo;
+            const int n_e = have;
+            const int n_t = min(max(have - sym, 0), 8 * (nc - 1) + sym);
+            // in place, ascending chunks of <= sym samples: a chunk reads a[k], a[k + sym], then (barrier) writes T[k] over a[k]
+            const int chunk = (sym < 4 * kThreads) ? ((sym < 2 * kThreads) ? kThreads : 2 * kThreads) : 4 * kThreads;
+            for (int k0 = 0; k0 < n_e; k0 += chunk) {
+                float2 tv[4]; float ev[4];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int k = k0 + tid + u * kThreads;
-                tv[u] = make_float2(0.f, 0.f); ev[u] = 0.f;
-                if (u * kThreads < chunk && k < n_e) {
-                    const float2 s1 = an[an_pad(k)];
-                    const float2 sq = ds_mul2(s1, s1);
-                    ev[u] = __fadd_rn(sq.x, sq.y);
-                    if (k < n_t) {
-                        const float2 s2 = an[an_pad(k + sym)];
-                        const float2 p1 = ds_mul2s(s1.x, s2);                              // (s1x s2x, s1x s2y)
-                        const float2 p2 = ds_mul2s(s1.y, make_float2(s2.y, s2.x));         // (s1y s2y, s1y s2x)
-                        tv[u] = make_float2(__fadd_rn(p1.x, p2.x), __fsub_rn(p1.y, p2.y));
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + tid + u * kThreads;
+                    tv[u] = make_float2(0.f, 0.f); ev[u] = 0.f;
+                    if (u * kThreads < chunk && k < n_e) {
+                        const float2 s1 = an[an_pad(k)];
+                        const float2 sq = ds_mul2(s1, s1);
+                        ev[u] = __fadd_rn(sq.x, sq.y);
+                        if (k < n_t) {
+                            const float2 s2 = an[an_pad(k + sym)];
+                            const float2 p1 = ds_mul2s(s1.x, s2);                              // (s1x s2x, s1x s2y)
+                            const float2 p2 = ds_mul2s(s1.y, make_float2(s2.y, s2.x));         // (s1y s2y, s1y s2x)
+                            tv[u] = make_float2(__fadd_rn(p1.x, p2.x), __fsub_rn(p1.y, p2.y));
+                        }
                     }
                 }
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + tid + u * kThreads;
+                    if (u * kThreads < chunk && k < n_e) { an[an_pad(k)] = tv[u]; E[an_pad(k)] = ev[u]; }
+                }
+                __syncthreads();
+            }
+            // zero what the sliding windows may touch past the planes (a block is loaded whole)
+            for (int k = n_e + tid; k < a.an_cap; k += kThreads) { an[an_pad(k)] = make_float2(0.f, 0.f); E[an_pad(k)] = 0.f; }
+            __syncthreads();
+            const int n_quads = (nc + kCandPerThread - 1) / kCandPerThread;
+            if (tid < n_quads) {
+                float2 P[4]; float e[4];
+                coarse_quad(an, E, kCandPerThread * tid, n_blocks, P, e);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = kCandPerThread * tid + q;
+                    if (c < nc) { e_sum[c_lo + c] = e[q]; cand[kMaxCand + c_lo + c] = P[q].x; cand[2 * kMaxCand + c_lo + c] = P[q].y; }
+                }
+            } else {
+                // the other warps: first energy sums of the grid positions behind the pass's last candidate (the second
+                // energies of its last sym / 8 candidates)
+                const int first_tail_thread = (n_quads + 31) & ~31;
+                for (int c = nc + (tid - first_tail_thread); tid >= first_tail_thread && c < nc + hop; c += kThreads - first_tail_thread) {
+                    float e1 = 0.f;
+                    for (int b = 0; b < n_blocks; ++b) {
+                        const float* eb = E + an_pad(8 * (c + b));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) e1 = __fadd_rn(e1, eb[j]);
+                    }
+                    e_sum[c_lo + c] = e1;
+                }
             }
             __syncthreads();
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int k = k0 + tid + u * kThreads;
-                if (u * kThreads < chunk && k < n_e) { an[an_pad(k)] = tv[u]; E[an_pad(k)] = ev[u]; }
-            }
-            __syncthreads();
-        }
-        // zero what the sliding windows may touch past the planes (a block is loaded whole)
-        const int n_zero = 8 * (n_cand + hop + kCandPerThread + 4) + sym;
-        for (int k = n_e + tid; k < n_zero && k < a.an_cap; k += kThreads) { an[an_pad(k)] = make_float2(0.f, 0.f); E[an_pad(k)] = 0.f; }
-        for (int k = n_t + tid; k < n_e; k += kThreads) an[an_pad(k)] = make_float2(0.f, 0.f);
-        __syncthreads();
-        const int n_quads = (n_cand + kCandPerThread - 1) / kCandPerThread;
-        const int n_blocks = sym / 8;
-        if (tid < n_quads) {
-            float2 P[4]; float e[4];
-            coarse_quad(an, E, kCandPerThread * tid, n_blocks, P, e);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int c = kCandPerThread * tid + q;
-                if (c < n_cand) { e_sum[c] = e[q]; cand[kMaxCand + c] = P[q].x; cand[2 * kMaxCand + c] = P[q].y; }
+            for (int c = c_lo + tid; c < c_lo + nc; c += kThreads) {
+                const float denom = __fadd_rn(sqrtf(__fmul_rn(e_sum[c], e_sum[c + hop])), 1e-10f);
+                cand[c] = __fdiv_rn(cabs_d(make_float2(cand[kMaxCand + c], cand[2 * kMaxCand + c])), denom);
             }
         } else {
-            // the other warps: first energy sums of the grid positions behind the last candidate (second energies of the
-            // last sym / 8 candidates)
-            const int first_tail_thread = (n_quads + 31) & ~31;
-            for (int c = n_cand + (tid - first_tail_thread); tid >= first_tail_thread && c < n_cand + hop; c += kThreads - first_tail_thread) {
-                float e1 = 0.f;
-                for (int b = 0; b < n_blocks; ++b) {
-                    const float* eb = E + an_pad(8 * (c + b));
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) e1 = __fadd_rn(e1, eb[j]);
-                }
-                e_sum[c] = e1;
+            build_analytic(alo, min(N, alo + 8 * (nc - 1) + 2 * sym));
+            for (int c = tid; c < nc; c += kThreads) {
+                float corr; float2 P;
+                lag_corr(an, 8 * c, sym, &corr, &P);
+                cand[c_lo + c] = corr; cand[kMaxCand + c_lo + c] = P.x; cand[2 * kMaxCand + c_lo + c] = P.y;
             }
         }
         __syncthreads();
-        for (int c = tid; c < n_cand; c += kThreads) {
-            const float denom = __fadd_rn(sqrtf(__fmul_rn(e_sum[c], e_sum[c + hop])), 1e-10f);
-            cand[c] = __fdiv_rn(cabs_d(make_float2(cand[kMaxCand + c], cand[2 * kMaxCand + c])), denom);
+        if (tid == 0) {
+            float best = s_f[2]; int bo = s_n[0]; float2 bp = make_float2(s_f[0], s_f[1]);
+            int stop = 0;
+            for (int c = c_lo; c < c_lo + nc; ++c) {
+                const float corr = cand[c];
+                if (corr > best) { best = corr; bo = signal_start + 8 * c; bp = make_float2(cand[kMaxCand + c], cand[2 * kMaxCand + c]); }
+                if (corr > 0.95f) { stop = 1; break; }                // first high-confidence peak
+            }
+            s_f[2] = best; s_n[0] = bo; s_f[0] = bp.x; s_f[1] = bp.y; s_n[1] = stop;
         }
-    } else {
-        for (int c = tid; c < n_cand; c += kThreads) {
-            float corr; float2 P;
-            lag_corr(an, 8 * c, sym, &corr, &P);
-            cand[c] = corr; cand[kMaxCand + c] = P.x; cand[2 * kMaxCand + c] = P.y;
-        }
+        __syncthreads();
+        if (s_n[1]) break;
     }
-    __syncthreads();
-    if (tid == 0) {
-        float best = 0.0f; int bo = 0; float2 bp = make_float2(0.f, 0.f);
-        for (int c = 0; c < n_cand; ++c) {
-            const float corr = cand[c];
-            if (corr > best) { best = corr; bo = signal_start + 8 * c; bp = make_float2(cand[kMaxCand + c], cand[2 * kMaxCand + c]); }
-            if (corr > 0.95f) break;                                 // first high-confidence peak
-        }
-        s_f[2] = best; s_n[0] = bo; s_f[0] = bp.x; s_f[1] = bp.y;
-    }
-    __syncthreads();
     float best_corr = s_f[2]; int best_offset = s_n[0]; float2 best_p = make_float2(s_f[0], s_f[1]);
     __syncthreads();
     // ---- +-4 refinement (:318-350) ----
@@ -315,19 +331,12 @@ ofdm_data_sync_kernel(const SyncArgs a) {
         const int r0 = max(signal_start, best_offset - 4), r1 = min(search_end, best_offset + 5);
         // The fine lags are one sample apart: their terms T[k] = conj(a[k]) a[k + sym], E[k] = |a[k]|^2 over
         // k in [r0, r1 + 2 sym) are formed once, then one thread per (lag, sum) walks its 'sym' terms in order
-        // (lag_corr's three sums, :283-295).  Layout inside the tile: analytic samples | T plane | E plane.
+        // (lag_corr's three sums, :283-295), the three kinds of sum on three warps.  Layout inside the tile:
+        // analytic samples | T plane | E plane.
         const int n_fine = r1 - r0;
         const int fine_hi = min(N, r1 + 2 * sym);
         const int n_an = fine_hi - r0;                               // analytic samples of the fine lags
-        {
-            // re-stage the samples the FIR needs (the energy plane held terms) and rebuild the analytic samples
-            const int lo = max(0, r0 - kTaps);
-            __syncthreads();
-            if (staged) for (int i = lo + tid; i < fine_hi; i += kThreads) xs[i - lo] = x[i];
-            __syncthreads();
-            for (int i = r0 + tid; i < fine_hi; i += kThreads) an[an_pad(i - r0)] = staged ? analytic_at(xs, lo, i) : analytic_at(x, 0, i);
-            __syncthreads();
-        }
+        build_analytic(r0, fine_hi);
         float2* FT = an + an_pad(n_an) + 8;                          // n_fine - 1 + sym terms
         float* FE = reinterpret_cast<float*>(FT + (n_fine + sym + 8)); // n_fine - 1 + 2 sym terms
         for (int k = tid; k < n_an; k += kThreads) {
@@ -340,9 +349,9 @@ ofdm_data_sync_kernel(const SyncArgs a) {
             }
         }
         __syncthreads();
-        if (tid < 3 * n_fine) {
-            const int d = tid / 3, kind = tid - 3 * d;               // 0: P, 1: e1, 2: e2
-            if (r0 + d != best_offset) {
+        {
+            const int kind = tid >> 5, d = tid & 31;                  // warp 0: P, warp 1: e1, warp 2: e2
+            if (kind < 3 && d < n_fine && r0 + d != best_offset) {
                 if (kind == 0) {
                     float2 P = make_float2(0.f, 0.f);
 #pragma unroll 4
@@ -420,9 +429,10 @@ extern "C" int ria_ofdm_data_sync_batch_dev(ria_ctx* ctx, const ria_modem_config
         RIA_CUDA(ctx, cudaMalloc(&ctx->hilbert65, sizeof taps));
         RIA_CUDA(ctx, cudaMemcpy(ctx->hilbert65, taps, sizeof taps, cudaMemcpyHostToDevice));
     }
-    // shared-memory tile: the widest search is 8 symbols (buffer starts inside a burst, :273-276) plus the two symbols
-    // the last candidate correlates over, padded one word per eight
-    const int an_cap = 10 * sym + 16;
+    // shared-memory tile of one pass: four symbols of candidate offsets plus the two symbols the last candidate
+    // correlates over (the widest search, eight symbols when the buffer starts inside a burst, :273-276, takes two
+    // passes), padded one word per 32
+    const int an_cap = 6 * sym + 64;
     const int an_words = an_cap + an_cap / 32 + 8;
     const size_t smem = static_cast<size_t>(an_words) * (sizeof(float2) + sizeof(float));
     if (smem + 48 * 1024 > ctx->smem_optin) return set_error(ctx, RIA_E_UNSUPPORTED, "data sync: symbol too long for the shared-memory tile");
