@@ -127,6 +127,26 @@ __device__ __forceinline__ void coarse_quad(const float2* T, const float* E, int
     }
 }
 
+// Four Hilbert outputs of one parity (see build_analytic): P = 0 even outputs, 1 odd outputs relative to the staged
+// origin.  w[] holds src[4 g - 32 .. 4 g + 3]; tap t of output u reads w[31 + u - t + P].
+template <int P>
+__device__ __forceinline__ void hilbert4(const float* __restrict__ src, const float* taps, int g, float (&q)[4]) {
+    float w[36];
+#pragma unroll
+    for (int v = 0; v < 9; ++v) {
+        const float4 q4 = *reinterpret_cast<const float4*>(src + 4 * g - 32 + 4 * v);
+        w[4 * v] = q4.x; w[4 * v + 1] = q4.y; w[4 * v + 2] = q4.z; w[4 * v + 3] = q4.w;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        const float tp = taps[2 * t + 1];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = __fadd_rn(q[u], __fmul_rn(tp, w[31 + u - t + P]));
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 ofdm_data_sync_kernel(const SyncArgs a) {
     extern __shared__ __align__(16) float2 an_tile[];          // analytic samples, then product terms, of one pass (an_pad)
@@ -149,25 +169,27 @@ ofdm_data_sync_kernel(const SyncArgs a) {
 
     if (tid < kTaps) taps[tid] = a.taps_g[tid];
     float* E = reinterpret_cast<float*>(an_tile + a.an_words);       // energy plane; before that, staged samples
-    // The window is staged once as floats in the tile (free until the first pass builds its analytic samples): the energy
-    // gate and the signal-start search then read shared memory.  Windows longer than the tile fall back to global memory.
-    float* xs = reinterpret_cast<float*>(an_tile);
+    // The SQUARES of the window's samples are staged once in the tile (free until the first pass builds its analytic
+    // samples; the product is exact per sample): the energy gate and the signal-start search only ever add squares.
+    // Windows longer than the tile fall back to global memory.
+    float* sq = reinterpret_cast<float*>(an_tile);
     const bool staged = N + 8 <= 2 * a.an_words;
-    if (staged) for (int i = tid; i < N; i += kThreads) xs[i] = x[i];
+    if (staged) for (int i = tid; i < N; i += kThreads) { const float v = x[i]; sq[i] = __fmul_rn(v, v); }
     __syncthreads();
-    const float* xr = staged ? xs : x;                              // same values either way
     // ---- energy gate (:232-260): a sequential sum of up to 4800 squares ----
     const int ns = min(N / 4, 4800);
     if (tid == 0) {
         float nf = 0.0f;
         int i = 0;
-        if (staged)
+        if (staged) {
             for (; i + 4 <= ns; i += 4) {
-                const float4 q = *reinterpret_cast<const float4*>(xs + i);
-                nf = __fadd_rn(nf, __fmul_rn(q.x, q.x)); nf = __fadd_rn(nf, __fmul_rn(q.y, q.y));
-                nf = __fadd_rn(nf, __fmul_rn(q.z, q.z)); nf = __fadd_rn(nf, __fmul_rn(q.w, q.w));
+                const float4 q = *reinterpret_cast<const float4*>(sq + i);
+                nf = __fadd_rn(nf, q.x); nf = __fadd_rn(nf, q.y); nf = __fadd_rn(nf, q.z); nf = __fadd_rn(nf, q.w);
             }
-        for (; i < ns; ++i) nf = __fadd_rn(nf, __fmul_rn(xr[i], xr[i]));
+            for (; i < ns; ++i) nf = __fadd_rn(nf, sq[i]);
+        } else {
+            for (; i < ns; ++i) nf = __fadd_rn(nf, __fmul_rn(x[i], x[i]));
+        }
         nf = sqrtf(nf / ns);
         s_f[0] = nf;
         s_f[1] = nf * 3.0f + 0.01f;
@@ -181,11 +203,11 @@ ofdm_data_sync_kernel(const SyncArgs a) {
         const int lim = N - sym * 2;
         for (int i = tid; i < lim && i < first; i += kThreads) {
             float e = 0.0f;
-            if (i + 64 <= N) {
-#pragma unroll 8
-                for (int j = 0; j < 64; ++j) e = __fadd_rn(e, __fmul_rn(xr[i + j], xr[i + j]));
+            if (staged && i + 64 <= N) {
+#pragma unroll 16
+                for (int j = 0; j < 64; ++j) e = __fadd_rn(e, sq[i + j]);
             } else {
-                for (int j = 0; j < 64; ++j) if (i + j < N) e = __fadd_rn(e, __fmul_rn(xr[i + j], xr[i + j]));
+                for (int j = 0; j < 64; ++j) if (i + j < N) e = __fadd_rn(e, __fmul_rn(x[i + j], x[i + j]));
             }
             e = sqrtf(e / 64);
             if (e > thr) { first = i; break; }
@@ -200,24 +222,40 @@ ofdm_data_sync_kernel(const SyncArgs a) {
     const int actual = in_noise ? search_window : max(search_window, sym * 8);
     const int search_end = min(signal_start + actual, N - sym * 2);
 
-    // src[j - shift] = sample j of the window (a staged piece of it that starts at sample `shift`, or the window itself)
-    auto analytic_at = [&](const float* src, int shift, int i) {      // (:266-270, filters.cpp:293-317)
-        float q = 0.0f;
-#pragma unroll 8
-        for (int k = 1; k < kTaps; k += 2) {                       // even taps are exactly zero
-            const int j = i - k;
-            const float v = (j >= 0) ? src[j - shift] : 0.0f;
-            q = __fadd_rn(q, __fmul_rn(taps[k], v));
-        }
-        return make_float2(i >= kDelay ? src[i - kDelay - shift] : 0.0f, q);
-    };
-    // samples [lo, hi) of the window -> the energy plane; analytic samples [alo, hi) -> the tile (tile index 0 = alo)
+    // Analytic samples [alo, hi) of the window -> the tile (tile index 0 = alo) (:266-270, filters.cpp:293-317).
+    // Only the odd taps of the 65-tap Hilbert FIR are non-zero, so output i reads the samples of the OTHER parity:
+    //   q(i) = sum_{t=0..31} taps[2t+1] x[i - 2t - 1]   (accumulated in this order),   re(i) = x[i - 32].
+    // The span is staged de-interleaved in the energy plane (even samples | odd samples, zeros before sample 0), which
+    // makes the 32 samples of an output a contiguous run and the runs of outputs i, i+2, i+4, i+6 overlap: a thread
+    // produces those four outputs from nine 128-bit loads.  Threads 0..127 take the even outputs, 128..255 the odd ones.
     auto build_analytic = [&](int alo, int hi) {
-        const int lo = max(0, alo - kTaps);
+        const int j0 = (alo - 64) & ~7;                               // staged sample 0 (may be negative: zeros)
+        const int n_st = hi - j0;                                     // staged samples
+        const int half = ((n_st + 1) / 2 + 7) & ~3;                   // floats per parity plane, 16-byte granules
+        float* Ee = E;
+        float* Eo = E + half;
         __syncthreads();
-        for (int i = lo + tid; i < hi; i += kThreads) E[i - lo] = x[i];
+        for (int m = tid; m < half; m += kThreads) {
+            const int je = j0 + 2 * m, jo = je + 1;
+            Ee[m] = (je >= 0 && je < hi) ? x[je] : 0.0f;
+            Eo[m] = (jo >= 0 && jo < hi) ? x[jo] : 0.0f;
+        }
         __syncthreads();
-        for (int i = alo + tid; i < hi; i += kThreads) an_tile[an_pad(i - alo)] = analytic_at(E, lo, i);
+        const int p = tid >> 7;                                       // output parity relative to j0 (j0 is even)
+        const float* src = p ? Ee : Eo;                               // taps read the other parity
+        const float* same = p ? Eo : Ee;                              // x[i - 32] has the parity of i
+        const int n_groups = (n_st + 7) / 8;
+        for (int g = 8 + (tid & 127); g < n_groups; g += 128) {       // local output index li = 8 g + 2 u + p >= 64
+            float q[4];
+            if (p) hilbert4<1>(src, taps, g, q); else hilbert4<0>(src, taps, g, q);
+            const float4 re4 = *reinterpret_cast<const float4*>(same + 4 * g - 16);     // x[i - 32], u = 0..3
+            const float re[4] = {re4.x, re4.y, re4.z, re4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = j0 + 8 * g + 2 * u + p;
+                if (i >= alo && i < hi) an_tile[an_pad(i - alo)] = make_float2(i >= kDelay ? re[u] : 0.0f, q[u]);
+            }
+        }
         __syncthreads();
     };
     float2* an = an_tile;
