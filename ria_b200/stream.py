@@ -14,9 +14,8 @@ Built: the connected OFDM_CHIRP branch complete (control-first peek at the DQPSK
 drift clamp, the R1/4 / data-rate codeword-0 peek, QAM partial-frame escalation, decodeFrame, small-frame recovery, the
 multi-candidate light-sync recovery) and the PING energy test a disconnected receiver classifies chirp-only
 transmissions with (`ping_energy_batch`), and burst-interleaved groups (`OfdmConnectedStep.burst_group`).  Not built:
-CSS frame typing, the burst timeout clock, the MC-DPSK handshake rules around the
-codeword-0 peek with their retries at the alternate modulation / neighbouring sync offsets (:1443-1795; the decode
-itself is `mcdpsk.McdpskFrameDecoder`).
+CSS frame typing, the burst timeout clock and the retries a disconnected MC-DPSK receiver makes after a FAILED handshake
+decode (alternate modulation, neighbouring sync offsets, :1646-1795); the MC-DPSK branch up to there is `McdpskStep`.
 """
 from __future__ import annotations
 
@@ -405,6 +404,134 @@ class OfdmConnectedStep:
                 r["queued"][done] = (d["success"] != 0) | (d["codewords_ok"] > 0)
             results.append(r)
         return results, last_cfo
+
+
+class McdpskStep:
+    """decodeCurrentFrame for MC-DPSK receivers (streaming_decoder.cpp:1060-1644): one-codeword frame buffer, PING energy
+    test (disconnected receivers), process, the codeword-0 peek with the handshake rules (a disconnected receiver waits
+    for at least the three codewords of a CONNECT before it decodes), the early-window rule, decodeFrame
+    (= decodeMCDPSKFrame) and the header salvage.  The disconnected-handshake retries that follow a FAILED decode in the
+    reference (alternate modulation, neighbouring sync offsets, :1646-1795) are not built: a failure is reported as
+    the reference would report it if those retries found nothing."""
+
+    PING, CONNECT_PAYLOAD = 0x01, 25                       # v2::FrameType::PING; ConnectFrame::PAYLOAD_SIZE (frame_v2.hpp:556)
+
+    def __init__(self, config, connected: bool, rate: int = R1_4, ctx: Optional[Context] = None, chase_cache=None):
+        from . import mcdpsk
+        self.config, self.connected, self.ctx = config, bool(connected), ctx
+        self.rate = int(rate) if connected else R1_4                              # :1437
+        self.dem = mcdpsk.MCDPSKDemodulator(config, ctx)
+        self.decoder = mcdpsk.McdpskFrameDecoder(self.rate, ctx, chase_cache)
+        self.robust = fec.LDPCDecoder(self.rate, ctx)
+        self.bpc = fec.code_params(self.rate)[0] // 8
+        k = fec.code_params(self.rate)[0]
+        # min_handshake_cw = max(2, DataFrame::calculateCodewords(ConnectFrame::PAYLOAD_SIZE, rate)) (:1448-1451)
+        self.min_handshake_cw = 0 if connected else max(2, ((17 + self.CONNECT_PAYLOAD + 2) * 8 + k - 1) // k)
+        self.min_handshake_cw_r14 = max(2, ((17 + self.CONNECT_PAYLOAD + 2) * 8 + 162 - 1) // 162)
+
+    def samples_for_cw(self, n_cw: int) -> int:               # MCDPSKWaveform::getMinSamplesForCWCount (mc_dpsk_waveform.cpp:470-484)
+        c = self.config
+        bits = int(c.num_carriers) * int(c.bits_per_symbol)
+        per_cw = (LDPC_BLOCK + bits - 1) // bits
+        return int(c.training_symbols) * int(c.samples_per_symbol) + int(c.samples_per_symbol) + \
+            n_cw * per_cw * int(c.samples_per_symbol) * int(c.spreading)
+
+    def step(self, window: torch.Tensor, sync_pos, sync_cfo, pending_total_cw=None):
+        """window CUDA fp32 [n, L]; sync_pos int[n] = training start; sync_cfo f32[n]; pending_total_cw int[n].
+        Returns numpy arrays: state, pending_total_cw, has_frame, success, is_ping, frame_type, codewords_ok,
+        codewords_failed, frame_len, frame u8[n, W]."""
+        if not (isinstance(window, torch.Tensor) and window.is_cuda and window.dtype == torch.float32 and window.dim() == 2):
+            raise RiaError("step wants CUDA fp32 [n, L] windows (no CPU fallback)")
+        n, L = window.shape
+        dev = window.device
+        sync_pos = np.asarray(sync_pos, np.int64)
+        sync_cfo = np.asarray(sync_cfo, np.float32)
+        pending = np.zeros(n, np.int32) if pending_total_cw is None else np.asarray(pending_total_cw, np.int32).copy()
+        out = dict(state=np.full(n, SEARCHING, np.int32), pending_total_cw=pending.copy(), has_frame=np.zeros(n, np.uint8),
+                   success=np.zeros(n, np.uint8), is_ping=np.zeros(n, np.uint8), frame_type=np.zeros(n, np.int32),
+                   codewords_ok=np.zeros(n, np.int32), codewords_failed=np.zeros(n, np.int32),
+                   frame_len=np.zeros(n, np.int32), frame=np.zeros((n, 1024), np.uint8))
+        frame_len = np.array([self.samples_for_cw(int(p) if p > 0 else 1) for p in pending], np.int64)
+        frame_len = np.minimum(frame_len, L - sync_pos)
+        alive = frame_len > 0
+        for ln in np.unique(frame_len[alive]):
+            idx = np.nonzero(alive & (frame_len == ln))[0]
+            cols = torch.from_numpy(sync_pos[idx]).to(dev)[:, None] + torch.arange(int(ln), device=dev)[None, :]
+            frames = torch.gather(window.index_select(0, torch.from_numpy(idx).to(dev)), 1, cols).contiguous()
+            live = np.ones(len(idx), bool)
+            # ---- PING energy test, disconnected receivers only (:1127-1266) ----
+            if not self.connected:
+                e = ping_energy_batch(frames, 4608, self.ctx)
+                hit = np.nonzero(e["is_ping"])[0]
+                g = idx[hit]
+                out["has_frame"][g] = 1; out["success"][g] = 1; out["is_ping"][g] = 1; out["frame_type"][g] = self.PING
+                live[hit] = False
+            sel = np.nonzero(live)[0]
+            if len(sel) == 0:
+                continue
+            idx2 = idx[sel]
+            fr = frames.index_select(0, torch.from_numpy(sel).to(dev))
+            # ---- waveform_->setFrequencyOffset(sync_cfo_); process(frame_buffer) ----
+            d = self.dem.process_batch(fr, torch.from_numpy(sync_cfo[idx2]).to(dev))
+            n_soft = d["n_llr"].cpu().numpy()
+            soft = d["llr"]
+            okp = n_soft > 0                                                    # process() false / no soft bits -> SEARCHING
+            pend = pending[idx2]
+            go = okp.copy()
+            avail = n_soft // LDPC_BLOCK
+            # ---- codeword-0 peek (:1443-1503) ----
+            peek = np.nonzero(okp & (pend == 0) & (n_soft >= LDPC_BLOCK))[0]
+            if len(peek):
+                info, ok, _, _ = self.robust.robust_decode_batch(soft.index_select(0, torch.from_numpy(peek).to(dev))[:, :LDPC_BLOCK].contiguous(),
+                                                                 info_stride=64)
+                info = info.cpu().numpy(); ok = ok.cpu().numpy().astype(bool)
+                dd = info[:, : max(self.bpc, 20)].copy()
+                valid, ftype, total_cw, _ = _parse_header(dd)
+                magic = ok & (dd[:, 0] == 0x55) & (dd[:, 1] == 0x4C)
+                needed = total_cw.copy()
+                handshake = np.isin(ftype, (0x12, 0x13, 0x14))                   # isConnectFrame minus DISCONNECT
+                if self.min_handshake_cw > 0:
+                    needed = np.where(handshake & (needed < self.min_handshake_cw), self.min_handshake_cw, needed)
+                esc = magic & valid & (needed > 1) & (avail[peek] < needed)
+                new_p = np.where(esc, needed, 0)
+                if self.min_handshake_cw > 1:
+                    fb = ~esc & (avail[peek] < self.min_handshake_cw)
+                    new_p = np.where(fb, self.min_handshake_cw, new_p)
+                    esc = esc | fb
+                g = idx2[peek[esc]]
+                out["state"][g] = SYNC_FOUND
+                out["pending_total_cw"][g] = new_p[esc]
+                go[peek[esc]] = False
+            if not self.connected:
+                # early window (:1598-1608) and the full-handshake window (:1610-1624)
+                early = go & (pend == 0) & (n_soft < LDPC_BLOCK)
+                out["state"][idx2[early]] = SYNC_FOUND
+                out["pending_total_cw"][idx2[early]] = 1
+                go &= ~early
+                hs = go & (avail < self.min_handshake_cw_r14) & (pend < self.min_handshake_cw_r14)
+                out["state"][idx2[hs]] = SYNC_FOUND
+                out["pending_total_cw"][idx2[hs]] = self.min_handshake_cw_r14
+                go &= ~hs
+            dec = np.nonzero(go & (n_soft >= LDPC_BLOCK))[0]
+            for ns in np.unique(n_soft[dec]):
+                sub = dec[n_soft[dec] == ns]
+                slots = int(ns) // LDPC_BLOCK
+                r = self.decoder.decode_batch(soft.index_select(0, torch.from_numpy(sub).to(dev))[:, : slots * LDPC_BLOCK].contiguous())
+                g = idx2[sub]
+                for key in ("success", "frame_type", "codewords_ok", "codewords_failed", "frame_len"):
+                    out[key][g] = r[key]
+                out["frame"][g, : r["frame"].shape[1]] = r["frame"]
+                # header salvage (:1631-1644)
+                salv = (r["success"] == 0) & (pend[sub] == 0) & (r["codewords_ok"] > 0)
+                if salv.any():
+                    hv, _, ht, _ = _parse_header(np.pad(r["frame"], ((0, 0), (0, max(0, 20 - r["frame"].shape[1]))))[:, :64])
+                    need = salv & hv & (ht > 1) & (avail[sub] < ht)
+                    out["state"][g[need]] = SYNC_FOUND
+                    out["pending_total_cw"][g[need]] = ht[need]
+                    out["codewords_ok"][g[need]] = 0
+                queued = (out["state"][g] == SEARCHING) & ((r["success"] != 0) | (r["codewords_ok"] > 0))
+                out["has_frame"][g] = queued
+        return out
 
 
 def ping_energy_batch(frames: torch.Tensor, training_skip: int = 4608, ctx: Optional[Context] = None) -> np.ndarray:

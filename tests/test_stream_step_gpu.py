@@ -197,3 +197,84 @@ def test_burst_group_matches_the_reference(ctx, ref, modulation, rate):
             assert res == []
     ref.stream_decoder_free(h)
     assert n_ok >= 16, n_ok
+
+
+@pytest.mark.parametrize("connected,modulation,rate,spread", [(False, DBPSK, R1_4, 0), (True, DQPSK, R1_2, 0), (False, DBPSK, R1_4, 1)])
+def test_mcdpsk_step_matches_the_reference_state_machine(ctx, ref, connected, modulation, rate, spread):
+    """MC-DPSK receivers: PING classification, the codeword-0 peek with the handshake rules (a disconnected receiver asks
+    for the three codewords of a CONNECT), escalation to the announced codeword count, decodeMCDPSKFrame."""
+    from oracle.bindings import McdpskConfig, ZcConfig
+    from ria_b200 import mcdpsk, stream
+    rng = np.random.default_rng(50 + 10 * connected + spread)
+    h = ref.stream_decoder()
+    ref.stream_setup_mcdpsk(h, connected, 10, modulation, rate, spread)
+    bits = 1 if modulation == DBPSK else 2
+    cfg = McdpskConfig.make(bits, (1, 2, 4)[spread], 10)
+    rcfg = mcdpsk.MultiCarrierDPSKConfig.from_buffer_copy(bytes(cfg))
+    stepper = stream.McdpskStep(rcfg, connected, rate, ctx)
+    assert stepper.samples_for_cw(1) == ref.stream_min_control_samples(h)
+    pre = len(ref.zc_preamble(ZcConfig.default(), 2)) if connected else 57600
+    kinds = (["ping", "ack", "data3", "data5", "ping", "data3", "noise", "ack", "data5", "data3"] if not connected
+             else ["ack", "data3", "data5", "noise", "ack", "data5", "data3", "data3"])
+    txs = []
+    for i, kind in enumerate(kinds):
+        if kind == "ping":
+            tx = ref.stream_encode(2, modulation, rate, 2, b"", 10, spread)
+        elif kind == "noise":
+            tx = np.zeros(pre + 100000, np.float32)
+        else:
+            frame = (ref.make_ack_frame("K1ABC", "W2XYZ", i) if kind == "ack" else
+                     ref.make_data_frame("K1ABC", "W2XYZ", i, rng.integers(0, 256, size=(30 if kind == "data3" else 70), dtype=np.uint8)))
+            tx = ref.stream_encode(2, modulation, rate, 1 if connected else 0, frame, 10, spread)
+        txs.append(tx)
+    Lw = max(len(t) for t in txs) + 20000
+    wins = []
+    for kind, tx in zip(kinds, txs):
+        p = float(np.mean(tx.astype(np.float64) ** 2)) if kind != "noise" else 0.01
+        w = np.zeros(Lw, np.float32)
+        w[: len(tx)] = tx
+        wins.append(_noisy(w, 12.0, rng, p))
+    n = len(kinds)
+    x = torch.from_numpy(np.stack(wins)).cuda()
+    sync = np.full(n, pre, np.int64)
+    cfo = np.zeros(n, np.float32)
+    pending = np.zeros(n, np.int32)
+    active = np.ones(n, bool)
+    seen = dict(ping=0, escalated=0, decoded=0)
+    for it in range(4):
+        idx = np.nonzero(active)[0]
+        if len(idx) == 0:
+            break
+        got = stepper.step(x[torch.from_numpy(idx).cuda()], sync[idx], cfo[idx], pending[idx])
+        for j, i in enumerate(idx):
+            res, data = ref.stream_step(h, wins[i], int(sync[i]), 0.0, 10.0, int(pending[i]), 0.0)
+            tag = (it, i, kinds[i])
+            final_failure = res.state == 0 and not (res.has_frame and res.frame.success)
+            if final_failure and not connected:
+                # the reference went through its handshake retries (alternate modulation, neighbouring offsets) before
+                # giving up; that ladder is not built: a failure stays a failure
+                assert got["state"][j] == 0 and not got["success"][j], tag
+                active[i] = False
+                continue
+            assert got["state"][j] == res.state, (tag, got["state"][j], res.state, got["pending_total_cw"][j], res.pending_total_cw)
+            if res.state == 1:
+                assert got["pending_total_cw"][j] == res.pending_total_cw, (tag, got["pending_total_cw"][j], res.pending_total_cw)
+                seen["escalated"] += 1
+            assert bool(got["has_frame"][j]) == bool(res.has_frame), tag
+            if res.has_frame:
+                f = res.frame
+                assert (got["success"][j], got["is_ping"][j]) == (f.success, f.is_ping), tag
+                if f.is_ping:
+                    seen["ping"] += 1
+                else:
+                    assert (got["codewords_ok"][j], got["codewords_failed"][j]) == (f.codewords_ok, f.codewords_failed), tag
+                if f.success and not f.is_ping:
+                    assert got["frame_type"][j] == f.frame_type and got["frame_len"][j] == f.n_bytes, tag
+                    assert bytes(got["frame"][j, : f.n_bytes]) == data, tag
+                    seen["decoded"] += 1
+            pending[i] = res.pending_total_cw
+            active[i] = res.state == 1
+    ref.stream_decoder_free(h)
+    assert seen["decoded"] >= 6 and seen["escalated"] >= 4, seen
+    if not connected:
+        assert seen["ping"] == 2, seen
