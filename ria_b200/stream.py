@@ -14,8 +14,8 @@ Built: the connected OFDM_CHIRP branch complete (control-first peek at the DQPSK
 drift clamp, the R1/4 / data-rate codeword-0 peek, QAM partial-frame escalation, decodeFrame, small-frame recovery, the
 multi-candidate light-sync recovery) and the PING energy test a disconnected receiver classifies chirp-only
 transmissions with (`ping_energy_batch`), and burst-interleaved groups (`OfdmConnectedStep.burst_group`).  Not built:
-CSS frame typing, the burst timeout clock and the retries a disconnected MC-DPSK receiver makes after a FAILED handshake
-decode (alternate modulation, neighbouring sync offsets, :1646-1795); the MC-DPSK branch up to there is `McdpskStep`.
+CSS frame typing and the ring buffer with its clocks (burst timeout); the MC-DPSK branch of the step, its
+disconnected-handshake retries included, is `McdpskStep`.
 """
 from __future__ import annotations
 
@@ -410,9 +410,9 @@ class McdpskStep:
     """decodeCurrentFrame for MC-DPSK receivers (streaming_decoder.cpp:1060-1644): one-codeword frame buffer, PING energy
     test (disconnected receivers), process, the codeword-0 peek with the handshake rules (a disconnected receiver waits
     for at least the three codewords of a CONNECT before it decodes), the early-window rule, decodeFrame
-    (= decodeMCDPSKFrame) and the header salvage.  The disconnected-handshake retries that follow a FAILED decode in the
-    reference (alternate modulation, neighbouring sync offsets, :1646-1795) are not built: a failure is reported as
-    the reference would report it if those retries found nothing."""
+    (= decodeMCDPSKFrame), the header salvage, and the retries a disconnected receiver makes when the handshake decode
+    fails outright: once with the other differential modulation (:1646-1690), then at the neighbouring sync offsets
+    +-8 .. +-64 with both modulations (:1692-1795)."""
 
     PING, CONNECT_PAYLOAD = 0x01, 25                       # v2::FrameType::PING; ConnectFrame::PAYLOAD_SIZE (frame_v2.hpp:556)
 
@@ -428,6 +428,12 @@ class McdpskStep:
         # min_handshake_cw = max(2, DataFrame::calculateCodewords(ConnectFrame::PAYLOAD_SIZE, rate)) (:1448-1451)
         self.min_handshake_cw = 0 if connected else max(2, ((17 + self.CONNECT_PAYLOAD + 2) * 8 + k - 1) // k)
         self.min_handshake_cw_r14 = max(2, ((17 + self.CONNECT_PAYLOAD + 2) * 8 + 162 - 1) // 162)
+        # the other differential modulation, for the disconnected-handshake retries (DBPSK <-> DQPSK, :1650-1660)
+        self.dem_alt = None
+        if not connected and int(config.bits_per_symbol) in (1, 2):
+            alt = type(config).from_buffer_copy(bytes(config))
+            alt.bits_per_symbol = 3 - int(config.bits_per_symbol)
+            self.dem_alt = mcdpsk.MCDPSKDemodulator(alt, ctx)
 
     def samples_for_cw(self, n_cw: int) -> int:               # MCDPSKWaveform::getMinSamplesForCWCount (mc_dpsk_waveform.cpp:470-484)
         c = self.config
@@ -439,7 +445,7 @@ class McdpskStep:
     def step(self, window: torch.Tensor, sync_pos, sync_cfo, pending_total_cw=None):
         """window CUDA fp32 [n, L]; sync_pos int[n] = training start; sync_cfo f32[n]; pending_total_cw int[n].
         Returns numpy arrays: state, pending_total_cw, has_frame, success, is_ping, frame_type, codewords_ok,
-        codewords_failed, frame_len, frame u8[n, W]."""
+        codewords_failed, frame_len, frame u8[n, W], sync_pos (moved by the handshake sync recovery)."""
         if not (isinstance(window, torch.Tensor) and window.is_cuda and window.dtype == torch.float32 and window.dim() == 2):
             raise RiaError("step wants CUDA fp32 [n, L] windows (no CPU fallback)")
         n, L = window.shape
@@ -450,10 +456,11 @@ class McdpskStep:
         out = dict(state=np.full(n, SEARCHING, np.int32), pending_total_cw=pending.copy(), has_frame=np.zeros(n, np.uint8),
                    success=np.zeros(n, np.uint8), is_ping=np.zeros(n, np.uint8), frame_type=np.zeros(n, np.int32),
                    codewords_ok=np.zeros(n, np.int32), codewords_failed=np.zeros(n, np.int32),
-                   frame_len=np.zeros(n, np.int32), frame=np.zeros((n, 1024), np.uint8))
+                   frame_len=np.zeros(n, np.int32), frame=np.zeros((n, 1024), np.uint8), sync_pos=sync_pos.copy())
         frame_len = np.array([self.samples_for_cw(int(p) if p > 0 else 1) for p in pending], np.int64)
         frame_len = np.minimum(frame_len, L - sync_pos)
         alive = frame_len > 0
+        reached = np.zeros(n, bool)                                     # receptions whose decodeFrame ran and settled the step
         for ln in np.unique(frame_len[alive]):
             idx = np.nonzero(alive & (frame_len == ln))[0]
             cols = torch.from_numpy(sync_pos[idx]).to(dev)[:, None] + torch.arange(int(ln), device=dev)[None, :]
@@ -531,7 +538,64 @@ class McdpskStep:
                     out["codewords_ok"][g[need]] = 0
                 queued = (out["state"][g] == SEARCHING) & ((r["success"] != 0) | (r["codewords_ok"] > 0))
                 out["has_frame"][g] = queued
+                reached[g] = out["state"][g] == SEARCHING
+        if not self.connected:
+            self._handshake_retries(window, sync_pos, sync_cfo, frame_len, reached, out)
         return out
+
+    def _try(self, dem, window, idx, pos, ln, sync_cfo):
+        """process + decodeMCDPSKFrame(R1/4) of receptions idx at positions pos with ln samples -> decode dict or None"""
+        dev = window.device
+        cols = torch.from_numpy(pos).to(dev)[:, None] + torch.arange(int(ln), device=dev)[None, :]
+        frames = torch.gather(window.index_select(0, torch.from_numpy(idx).to(dev)), 1, cols).contiguous()
+        d = dem.process_batch(frames, torch.from_numpy(sync_cfo[idx]).to(dev))
+        n_soft = d["n_llr"].cpu().numpy()
+        ns = int(n_soft[0]) if len(n_soft) else 0                   # same length, same configuration: same count
+        if ns < LDPC_BLOCK:
+            return None
+        return self.decoder.decode_batch(d["llr"][:, : (ns // LDPC_BLOCK) * LDPC_BLOCK].contiguous())
+
+    def _accept(self, out, g, r, rows):
+        for key in ("success", "frame_type", "codewords_ok", "codewords_failed", "frame_len"):
+            out[key][g] = r[key][rows]
+        out["frame"][g] = 0
+        out["frame"][g, : r["frame"].shape[1]] = r["frame"][rows]
+        out["has_frame"][g] = 1
+
+    def _handshake_retries(self, window, sync_pos, sync_cfo, frame_len, reached, out):
+        L = window.shape[1]
+        fail = lambda: np.nonzero(reached & (out["success"] == 0) & (out["codewords_ok"] == 0))[0]
+        # ---- once more with the other modulation on the same samples (:1646-1690) ----
+        if self.dem_alt is not None:
+            todo = fail()
+            for ln in np.unique(frame_len[todo]):
+                idx = todo[frame_len[todo] == ln]
+                r = self._try(self.dem_alt, window, idx, sync_pos[idx], ln, sync_cfo)
+                if r is not None:
+                    good = np.nonzero(r["success"] != 0)[0]
+                    self._accept(out, idx[good], r, good)
+        # ---- neighbouring sync offsets, both modulations (:1692-1795) ----
+        ctl = self.samples_for_cw(1)
+        for delta in (8, -8, 16, -16, 24, -24, 32, -32, 48, -48, 64, -64):
+            todo = fail()
+            if len(todo) == 0:
+                break
+            pos = sync_pos[todo] + delta
+            ln_all = np.minimum(frame_len[todo], L - pos)
+            usable = (pos >= 0) & (ln_all >= ctl)
+            for dem in (self.dem, self.dem_alt):
+                if dem is None:
+                    continue
+                cur = np.isin(todo, fail()) & usable                    # a hit of the first modulation ends the delta
+                for ln in np.unique(ln_all[cur]):
+                    sel = np.nonzero(cur & (ln_all == ln))[0]
+                    r = self._try(dem, window, todo[sel], pos[sel], ln, sync_cfo)
+                    if r is None:
+                        continue
+                    good = np.nonzero(r["success"] != 0)[0]
+                    g = todo[sel[good]]
+                    self._accept(out, g, r, good)
+                    out["sync_pos"][g] = pos[sel[good]]
 
 
 def ping_energy_batch(frames: torch.Tensor, training_skip: int = 4608, ctx: Optional[Context] = None) -> np.ndarray:

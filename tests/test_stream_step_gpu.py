@@ -214,7 +214,9 @@ def test_mcdpsk_step_matches_the_reference_state_machine(ctx, ref, connected, mo
     stepper = stream.McdpskStep(rcfg, connected, rate, ctx)
     assert stepper.samples_for_cw(1) == ref.stream_min_control_samples(h)
     pre = len(ref.zc_preamble(ZcConfig.default(), 2)) if connected else 57600
-    kinds = (["ping", "ack", "data3", "data5", "ping", "data3", "noise", "ack", "data5", "data3"] if not connected
+    # "+16" / "-24": the sync position handed to the step is off by that much (a disconnected receiver recovers through
+    # its neighbouring-offset retries, :1692-1795)
+    kinds = (["ping", "ack", "data3", "data5", "ping", "data3+16", "noise", "ack", "data5-24", "data3"] if not connected
              else ["ack", "data3", "data5", "noise", "ack", "data5", "data3", "data3"])
     txs = []
     for i, kind in enumerate(kinds):
@@ -224,7 +226,7 @@ def test_mcdpsk_step_matches_the_reference_state_machine(ctx, ref, connected, mo
             tx = np.zeros(pre + 100000, np.float32)
         else:
             frame = (ref.make_ack_frame("K1ABC", "W2XYZ", i) if kind == "ack" else
-                     ref.make_data_frame("K1ABC", "W2XYZ", i, rng.integers(0, 256, size=(30 if kind == "data3" else 70), dtype=np.uint8)))
+                     ref.make_data_frame("K1ABC", "W2XYZ", i, rng.integers(0, 256, size=(30 if kind.startswith("data3") else 70), dtype=np.uint8)))
             tx = ref.stream_encode(2, modulation, rate, 1 if connected else 0, frame, 10, spread)
         txs.append(tx)
     Lw = max(len(t) for t in txs) + 20000
@@ -236,11 +238,11 @@ def test_mcdpsk_step_matches_the_reference_state_machine(ctx, ref, connected, mo
         wins.append(_noisy(w, 12.0, rng, p))
     n = len(kinds)
     x = torch.from_numpy(np.stack(wins)).cuda()
-    sync = np.full(n, pre, np.int64)
+    sync = np.array([pre + (int(k[5:]) if len(k) > 5 and k.startswith("data") else 0) for k in kinds], np.int64)
     cfo = np.zeros(n, np.float32)
     pending = np.zeros(n, np.int32)
     active = np.ones(n, bool)
-    seen = dict(ping=0, escalated=0, decoded=0)
+    seen = dict(ping=0, escalated=0, decoded=0, recovered=0)
     for it in range(4):
         idx = np.nonzero(active)[0]
         if len(idx) == 0:
@@ -249,13 +251,6 @@ def test_mcdpsk_step_matches_the_reference_state_machine(ctx, ref, connected, mo
         for j, i in enumerate(idx):
             res, data = ref.stream_step(h, wins[i], int(sync[i]), 0.0, 10.0, int(pending[i]), 0.0)
             tag = (it, i, kinds[i])
-            final_failure = res.state == 0 and not (res.has_frame and res.frame.success)
-            if final_failure and not connected:
-                # the reference went through its handshake retries (alternate modulation, neighbouring offsets) before
-                # giving up; that ladder is not built: a failure stays a failure
-                assert got["state"][j] == 0 and not got["success"][j], tag
-                active[i] = False
-                continue
             assert got["state"][j] == res.state, (tag, got["state"][j], res.state, got["pending_total_cw"][j], res.pending_total_cw)
             if res.state == 1:
                 assert got["pending_total_cw"][j] == res.pending_total_cw, (tag, got["pending_total_cw"][j], res.pending_total_cw)
@@ -272,6 +267,8 @@ def test_mcdpsk_step_matches_the_reference_state_machine(ctx, ref, connected, mo
                     assert got["frame_type"][j] == f.frame_type and got["frame_len"][j] == f.n_bytes, tag
                     assert bytes(got["frame"][j, : f.n_bytes]) == data, tag
                     seen["decoded"] += 1
+                    assert got["sync_pos"][j] == res.sync_pos, (tag, got["sync_pos"][j], res.sync_pos)
+                    seen["recovered"] += int(res.sync_pos != sync[i])
             pending[i] = res.pending_total_cw
             active[i] = res.state == 1
     ref.stream_decoder_free(h)
