@@ -269,6 +269,7 @@ ofdm_data_sync_kernel(const SyncArgs a) {
     const int hop = sym / 8, n_blocks = sym / 8;
     // a pass of nc candidates needs 8 (nc + hop - 1) + sym terms (term planes) or 8 (nc - 1) + 2 sym analytic samples
     const int pass_cand = share ? (max(8, (a.an_cap - sym) / 8 + 1 - hop - 8) & ~3) : max(8, (a.an_cap - 2 * sym) / 8);
+    __syncthreads();                                                // every thread has read the gate's s_f[0] / s_f[1]
     if (tid == 0) { s_f[2] = 0.0f; s_n[0] = 0; s_f[0] = 0.f; s_f[1] = 0.f; s_n[1] = 0; }
     __syncthreads();
     for (int c_lo = 0; c_lo < n_cand; c_lo += pass_cand) {

@@ -316,3 +316,126 @@ def test_c3_mcdpsk_chirp_chain_awgn_wide(ctx, ref):
 def test_c3_mcdpsk_chirp_chain_watterson_wide(ctx, ref, cond, cname):
     e = _mcdpsk_case(ctx, f"c3_mcdpsk_dbpsk4x_chirp_watterson_{cname}_0dB", 0.0, max(128, N_FADED // 2), fade_cond=cond)
     assert all(v == 0 for v in e["mismatches"].values()), e
+
+
+# ---------------------------------------------------------------------------------------------
+# Synchronisers added in round 2: OFDM_COX acquisition and the rewritten OFDM data sync, wide
+# ---------------------------------------------------------------------------------------------
+def _cox_ref_worker(span):
+    ref = Ref()
+    ref.lib.ref_quiet()
+    cfg, wins = _G["cox_cfg"], _G["cox_wins"]
+    return [ref.ofdm_cox_search_sync(cfg, wins[i], 0.8, 0.0) for i in range(span[0], span[1])]
+
+
+def _dsync_ref_worker(span):
+    ref = Ref()
+    ref.lib.ref_quiet()
+    cfg, wins, cfos = _G["ds_cfg"], _G["ds_wins"], _G["ds_cfo"]
+    out = []
+    for i in range(span[0], span[1]):
+        r = ref.ofdm_data_sync(cfg, wins[i], float(cfos[i]), 0.3)
+        out.append((r.detected, r.start_sample, r.correlation, r.aux))
+    return out
+
+
+def test_ofdm_cox_search_sync_wide(ctx, ref):
+    """RIA_PARITY_FADED (default 1024) windows through the batched searchForSync and the reference's: found flag, LTS
+    position, CFO bits and the noise floor left behind must be identical"""
+    import torch
+    from ria_b200 import ofdm, sync
+    n, window = N_FADED, 30000
+    rng = np.random.default_rng(404)
+    cfg = ModemConfig.make(QAM64, 4, 1)
+    bps = cfg.data_carriers() * BITS_PER_CARRIER[cfg.modulation]
+    pool = []
+    for i in range(8):
+        frame = ref.make_data_frame("K1ABC", "W2XYZ", i, rng.integers(0, 256, size=4 * BYTES_PER_CW[R3_4] - 19, dtype=np.uint8))
+        pool.append(ref.ofdm_cox_tx_frame(cfg, ref.encode_fixed_frame(frame, R3_4, True, bps)))
+    wins = np.zeros((n, window), np.float32)
+    for i in range(n):
+        kind = i % 10
+        if kind == 9:                                           # noise only
+            wins[i] = rng.standard_normal(window).astype(np.float32) * np.float32(0.05)
+            continue
+        tx = pool[i % 8]
+        lead = int(rng.integers(0, 9000))
+        seg = tx[: window - lead]
+        wins[i, lead:lead + len(seg)] = seg
+        p = float(np.mean(tx[1120:].astype(np.float64) ** 2))
+        snr = float(rng.choice([6.0, 10.0, 14.0, 20.0, 28.0]))
+        wins[i] += rng.standard_normal(window).astype(np.float32) * np.float32(np.sqrt(p / 10 ** (snr / 10)))
+    _G["cox_cfg"], _G["cox_wins"] = cfg, wins
+    t0 = time.time()
+    want = _fan_out(_cox_ref_worker, n)
+    t_ref = time.time() - t0
+    rcfg = ofdm.ModemConfig.from_buffer_copy(bytes(cfg))
+    nf = torch.zeros(n, device="cuda")
+    got = sync.results(sync.ofdm_cox_search_sync_batch(rcfg, torch.from_numpy(wins).cuda(), 0.8, nf, ctx))
+    nf = nf.cpu().numpy()
+    bad = dict(found=0, position=0, cfo=0, noise_floor=0)
+    n_found = 0
+    for i, (f, pos, cfo, nfr) in enumerate(want):
+        bad["found"] += int(bool(got["detected"][i]) != f)
+        bad["noise_floor"] += int(np.float32(nfr).view(np.uint32) != nf[i].view(np.uint32))
+        if f and got["detected"][i]:
+            n_found += 1
+            bad["position"] += int(got["start_sample"][i] != pos)
+            bad["cfo"] += int(np.float32(got["cfo_hz"][i]).view(np.uint32) != np.float32(cfo).view(np.uint32))
+    _report("ofdm_cox_search_sync", dict(windows=n, found=n_found, mismatches=bad, reference_seconds=round(t_ref, 1)))
+    assert sum(bad.values()) == 0 and n_found > n // 3, (bad, n_found)
+
+
+def test_ofdm_data_sync_wide(ctx, ref):
+    """RIA_PARITY_FRAMES (default 4096) windows through the batched detectDataSync and the reference's: detection flag,
+    training position and burst marker identical, correlation within 1e-5"""
+    import torch
+    from ria_b200 import ofdm, sync
+    from tests.ofdm_common import apply_cfo
+    n, window = N_AWGN, 9 * 1120
+    rng = np.random.default_rng(505)
+    cfg = ModemConfig.make(DQPSK, 10, 1)
+    bps = cfg.data_carriers() * BITS_PER_CARRIER[cfg.modulation]
+    pool = []
+    for i in range(8):
+        frame = ref.make_data_frame("K1ABC", "W2XYZ", i, rng.integers(0, 256, size=4 * BYTES_PER_CW[R1_2] - 19, dtype=np.uint8))
+        tx = ref.ofdm_tx_frame(cfg, ref.encode_fixed_frame(frame, R1_2, True, bps))
+        pool.append(tx)
+        m = tx.copy(); m[:1120] = -m[:1120]                      # burst-interleave marker
+        pool.append(m)
+    wins = np.zeros((n, window), np.float32)
+    cfos = np.zeros(n, np.float32)
+    for i in range(n):
+        tx = pool[i % 16]
+        mode = i % 5
+        if mode == 4:                                           # starts inside a burst: no quiet lead, eight-symbol search
+            start = int(rng.integers(1200, 6000))
+            seg = np.concatenate([pool[(i + 3) % 16][-start:], tx])[:window]
+            wins[i, : len(seg)] = seg
+            sc = 1.0
+        else:
+            lead = int(rng.integers(100, 3500))
+            seg = tx[: window - lead]
+            wins[i, lead:lead + len(seg)] = seg
+            sc = 0.2
+        p = float(np.mean(tx.astype(np.float64) ** 2))
+        snr = float(rng.choice([6.0, 10.0, 16.0, 24.0]))
+        wins[i] += rng.standard_normal(window).astype(np.float32) * np.float32(np.sqrt(p / 10 ** (snr / 10)) * sc)
+        cfos[i] = np.float32(rng.uniform(-5, 5)) if i % 3 == 0 else np.float32(0)
+    _G["ds_cfg"], _G["ds_wins"], _G["ds_cfo"] = cfg, wins, cfos
+    t0 = time.time()
+    want = _fan_out(_dsync_ref_worker, n)
+    t_ref = time.time() - t0
+    rcfg = ofdm.ModemConfig.from_buffer_copy(bytes(cfg))
+    got = sync.results(sync.ofdm_data_sync_batch(rcfg, torch.from_numpy(wins).cuda(), torch.from_numpy(cfos).cuda(), 0.3, ctx))
+    bad = dict(detected=0, position=0, marker=0, correlation=0)
+    n_det = 0
+    for i, (det, pos, corr, aux) in enumerate(want):
+        bad["detected"] += int(bool(got["detected"][i]) != bool(det))
+        bad["correlation"] += int(abs(got["correlation"][i] - corr) > 1e-5 * max(1.0, corr))
+        if det and got["detected"][i]:
+            n_det += 1
+            bad["position"] += int(got["start_sample"][i] != pos)
+            bad["marker"] += int(got["aux"][i] != aux)
+    _report("ofdm_data_sync", dict(windows=n, detected=n_det, mismatches=bad, reference_seconds=round(t_ref, 1)))
+    assert sum(bad.values()) == 0 and n_det > n // 2, (bad, n_det)
