@@ -439,3 +439,60 @@ def test_ofdm_data_sync_wide(ctx, ref):
             bad["marker"] += int(got["aux"][i] != aux)
     _report("ofdm_data_sync", dict(windows=n, detected=n_det, mismatches=bad, reference_seconds=round(t_ref, 1)))
     assert sum(bad.values()) == 0 and n_det > n // 2, (bad, n_det)
+
+
+def _zc_ref_worker(span):
+    ref = Ref()
+    ref.lib.ref_quiet()
+    z, wins, cfos = _G["zc_cfg"], _G["zc_wins"], _G["zc_cfo"]
+    out = []
+    for i in range(span[0], span[1]):
+        r = ref.zc_detect(z, wins[i], 0.2, 4 | 8, float(cfos[i]))
+        out.append((r.detected, r.start_sample, r.root, r.correlation, r.cfo_hz))
+    return out
+
+
+def test_zc_detect_production_window_wide(ctx, ref):
+    """RIA_PARITY_FADED (default 1024) production-size windows (31 120 samples, roots DATA | CONTROL, known CFO on a third
+    of them): detection flag, position, root and CFO bits identical, correlation within 1e-5"""
+    import torch
+    from oracle.bindings import ZcConfig
+    from ria_b200 import sync
+    from tests.ofdm_common import apply_cfo
+    n, window = N_FADED, 31120
+    rng = np.random.default_rng(606)
+    z = ZcConfig.default()
+    pre = {t: ref.zc_preamble(z, t) for t in (2, 3)}
+    wins = np.zeros((n, window), np.float32)
+    cfos = np.zeros(n, np.float32)
+    for i in range(n):
+        if i % 9 != 8:
+            sig = pre[2 + (i % 2)]
+            cfo = float(rng.uniform(-25, 25)) if i % 3 == 0 else 0.0
+            if cfo:
+                sig = apply_cfo(sig, cfo)
+                cfos[i] = np.float32(cfo + rng.uniform(-2, 2)) if i % 2 else np.float32(0)
+            pos = int(rng.integers(0, window - len(sig) - 600))
+            wins[i, pos:pos + len(sig)] += sig
+            tail = window - pos - len(sig)
+            wins[i, pos + len(sig):] += 0.3 * np.sin(2 * np.pi * 1200 * np.arange(tail) / 48000).astype(np.float32)
+        snr = float(rng.choice([-12.0, -6.0, 0.0, 6.0, 15.0]))
+        wins[i] += rng.standard_normal(window).astype(np.float32) * np.float32(np.sqrt(0.32 / 10 ** (snr / 10)))
+    _G["zc_cfg"], _G["zc_wins"], _G["zc_cfo"] = z, wins, cfos
+    t0 = time.time()
+    want = _fan_out(_zc_ref_worker, n)
+    t_ref = time.time() - t0
+    zs = sync.ZCSync(sync.ZCConfig.from_buffer_copy(bytes(z)), ctx)
+    got = sync.results(zs.detect_batch(torch.from_numpy(wins).cuda(), 0.2, 4 | 8, torch.from_numpy(cfos).cuda()))
+    bad = dict(detected=0, position=0, root=0, correlation=0, cfo=0)
+    n_det = 0
+    for i, (det, pos, root, corr, cfo) in enumerate(want):
+        bad["detected"] += int(bool(got["detected"][i]) != bool(det))
+        bad["root"] += int(got["root"][i] != root)
+        bad["correlation"] += int(abs(got["correlation"][i] - corr) > 1e-5 * max(1.0, abs(corr)))
+        if det and got["detected"][i]:
+            n_det += 1
+            bad["position"] += int(got["start_sample"][i] != pos)
+            bad["cfo"] += int(np.float32(got["cfo_hz"][i]).view(np.uint32) != np.float32(cfo).view(np.uint32))
+    _report("zc_detect_31120", dict(windows=n, detected=n_det, mismatches=bad, reference_seconds=round(t_ref, 1)))
+    assert sum(bad.values()) == 0 and n_det > n // 2, (bad, n_det)
