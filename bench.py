@@ -365,8 +365,7 @@ class OfdmQam64Workload:
 class OfdmCoxWorkload(OfdmQam64Workload):
     LEAD, WINDOW = 2000, 24000                          # [2000 quiet][silent symbol][4 STS][2 LTS][10 data symbols][tail]
     CPU_SAMPLE = 150
-    e2e_api = ("pinned host windows -> device copy -> ria_ofdm_cox_search_sync_batch_dev + ria_ofdm_rx_frames_dev -> "
-               "decoded frames and status copied back (ria_b200.sync / ria_b200.ofdm)")
+    e2e_api = "ria_ofdm_cox_rx_frames_host (pinned host windows)"
 
     def __init__(self, n_frames: int):
         super().__init__(n_frames)
@@ -382,8 +381,8 @@ class OfdmCoxWorkload(OfdmQam64Workload):
     def describe(self):
         d = super().describe()
         d["window_samples"] = self.WINDOW
-        d["chain"] = ("searchForSync (energy walk, Schmidl-Cox metric, plateau, LTS timing, coarse CFO) -> gather at the LTS "
-                      "position -> " + d["chain"])
+        d["chain"] = ("ria_ofdm_cox_rx_frames_dev: searchForSync (energy walk, Schmidl-Cox metric, plateau, LTS timing, coarse "
+                      "CFO) -> frame at the LTS position with the CFO / phase found -> " + d["chain"])
         d["l2"] = f"input batch ({self.n * self.WINDOW * 4 / 1e9:.1f} GB) exceeds the 126 MB L2; no flush needed"
         return d
 
@@ -417,31 +416,19 @@ class OfdmCoxWorkload(OfdmQam64Workload):
             sim.awgn_batch(rows, m, self.SNR_DB, seed=2027, first_frame_id=gid, out=self.windows[off:off + m], ctx=ctx)
             del tx, coded, fr_dev, rows
         ctx.set_decode_flags(ria_b200.DECODE_FULL)
-        self.chain = ofdm.OfdmRxChain(cfg, self.RATE, True, ctx)
-        self.cols = torch.arange(self.FRAME_LEN, device=device)[None, :]
+        self.chain = ofdm.OfdmCoxRxChain(cfg, self.RATE, True, ctx)
         self.out = None
         torch.cuda.synchronize()
 
     def release(self):
-        self.windows = self.sent_dev = self.out = self.cols = None
-        self._pin = None
+        self.windows = self.sent_dev = self.out = None
+        self._pin = self.e2e_host = None
 
     def _run(self, windows):
         torch = self.torch
-        res = self.sync.ofdm_cox_search_sync_batch(self.cfg, windows, 0.8, None, self.ctx)
-        r32 = res.view(torch.int32)                        # ria_sync_result: detected, start_sample, correlation, cfo_hz, ...
-        det = r32[:, 0] != 0
-        start = torch.where(det, r32[:, 1], torch.zeros_like(r32[:, 1])).clamp_(0, windows.shape[1] - self.FRAME_LEN).long()
-        cfo = torch.where(det, r32[:, 3].view(torch.float32), torch.zeros(len(det), device=windows.device)).contiguous()
-        # OFDMNvisWaveform::process: initial mixer phase from the CFO and the LTS position (fp64 expression -> fp32, wrapped)
-        ph = (-2.0 * np.pi) * cfo.double() * start.double() / 48000.0
-        ph = ph.float()
-        ph = torch.where(ph > np.pi, (ph.double() - 2.0 * np.pi).float(), ph)
-        ph = torch.where(ph < -np.pi, (ph.double() + 2.0 * np.pi).float(), ph)
-        frames = torch.gather(windows, 1, start[:, None] + self.cols)
-        out = self.chain.process_batch(frames, cfo, ph.contiguous())
-        self.detected = det
-        return out
+        data, status, snr, sync = self.chain.process_windows(windows, self.FRAME_LEN, 0.8)
+        self.detected = sync.view(torch.int32)[:, 0] != 0
+        return data, status, snr
 
     def step(self):
         self.out = self._run(self.windows)
@@ -493,13 +480,10 @@ class OfdmCoxWorkload(OfdmQam64Workload):
         pin.copy_(self.windows[:n_e2e])
         torch.cuda.synchronize()
         self._pin = pin
-        self._dev_in = torch.empty((n_e2e, self.WINDOW), dtype=torch.float32, device=self.windows.device)
+        self.e2e_host = pin.numpy()
 
     def step_e2e(self):
-        # pinned host windows -> device -> acquisition + chain -> decoded frames and status back on the host
-        self._dev_in.copy_(self._pin, non_blocking=True)
-        data, status, snr = self._run(self._dev_in)
-        return data.cpu(), status.cpu(), snr.cpu()
+        return self.chain.process_windows_host(self.e2e_host, self.FRAME_LEN, 0.8)
 
     def e2e_bytes(self):
         from ria_b200 import ofdm

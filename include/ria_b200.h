@@ -374,6 +374,23 @@ int ria_ofdm_cox_search_sync_batch_dev(ria_ctx* ctx, const ria_modem_config* cfg
                                        float threshold, float* noise_floor_dev, int64_t n_windows,
                                        ria_sync_result* out_dev);
 
+/* Whole receive chain for OFDM_COX frames, one call: OFDMNvisWaveform::detectSync (the batched searchForSync of
+ * ria_ofdm_cox_search_sync_batch_dev) -> OFDMNvisWaveform::process at the LTS position found, with the CFO found and the
+ * initial mixer phase -2 pi cfo pos / fs (src/waveform/ofdm_cox_waveform.cpp:121-218) -> the frame decode of
+ * ria_ofdm_rx_frames_dev.  samples [n][window_stride] windows of `window` samples, frame_len = samples handed to
+ * process() from the LTS on (2 training symbols + data).  A window in which nothing is found (or whose frame would
+ * run past the window) yields a status with nothing valid.  noise_floor (nullable, in/out [n]) as in the search;
+ * sync (nullable, [n]) receives the search results. */
+int ria_ofdm_cox_rx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg, int rate, int use_channel_interleave,
+                               const float* samples_dev, int64_t window_stride, int32_t window, int32_t frame_len,
+                               float threshold, float* noise_floor_dev, int64_t n_windows,
+                               uint8_t* data_dev, ria_frame_status* status_dev, float* snr_db_dev,
+                               ria_sync_result* sync_dev);
+int ria_ofdm_cox_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg, int rate, int use_channel_interleave,
+                                const float* samples, int64_t window_stride, int32_t window, int32_t frame_len,
+                                float threshold, float* noise_floor, int64_t n_windows,
+                                uint8_t* data, ria_frame_status* status, float* snr_db, ria_sync_result* sync);
+
 /* Tap of the search above: OFDMDemodulator::Impl::measureCorrelation(offset) (src/ofdm/ofdm_sync.cpp:118-190), the
  * Schmidl-Cox metric of the FFT window that follows offset + cyclic prefix, one offset per window. */
 int ria_ofdm_cox_correlation_batch_dev(ria_ctx* ctx, const ria_modem_config* cfg,

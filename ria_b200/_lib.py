@@ -72,6 +72,8 @@ _SIGNATURES = {
     "ria_ping_energy_batch_dev": (_i32, [_vp, _vp, _i64, _i32, _i32, _i64, _vp]),
     "ria_mcdpsk_zc_rx_frames_dev": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _f32, C.c_uint32, _i64, _i32, _i32, _f32,
                                         _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "ria_ofdm_cox_rx_frames_dev": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _i32, _i32, _f32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "ria_ofdm_cox_rx_frames_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _i32, _i32, _f32, _vp, _i64, _vp, _vp, _vp, _vp]),
     "ria_burst_deinterleave_batch_dev": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _i32]),
     "ria_zc_config_default": (_i32, [_vp]),
     "ria_zc_detect_batch_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _f32, C.c_uint32, _i64, _vp]),

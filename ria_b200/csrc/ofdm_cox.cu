@@ -460,6 +460,37 @@ cox_decide_kernel(const CoxArgs a) {
     }
 }
 
+// ---- chain glue: what OFDMNvisWaveform::process derives from the search result (ofdm_cox_waveform.cpp:160-190) ----
+// cfo[f] = CFO found (0 when nothing was found), phase[f] = -2 pi cfo pos / fs (a double expression rounded to float,
+// wrapped to [-pi, pi] in double steps rounded to float), and the frame copied out of the window at the LTS position.
+__global__ void cox_prepare_kernel(const ria_sync_result* __restrict__ sync, long long n, int window, int frame_len,
+                                   double sample_rate, int* __restrict__ start, float* __restrict__ cfo, float* __restrict__ phase) {
+    const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (f >= n) return;
+    const ria_sync_result r = sync[f];
+    const bool ok = r.detected && r.start_sample >= 0 && r.start_sample + frame_len <= window;
+    start[f] = ok ? r.start_sample : -1;
+    const float c = ok ? r.cfo_hz : 0.0f;
+    cfo[f] = c;
+    const double two_pi_f = static_cast<double>(-2.0f) * M_PI;
+    float ph = static_cast<float>(__ddiv_rn(__dmul_rn(__dmul_rn(two_pi_f, static_cast<double>(c)),
+                                                      static_cast<double>(ok ? r.start_sample : 0)), sample_rate));
+    const double two_pi = static_cast<double>(2.0f) * M_PI;
+    while (static_cast<double>(ph) > M_PI) ph = static_cast<float>(static_cast<double>(ph) - two_pi);
+    while (static_cast<double>(ph) < -M_PI) ph = static_cast<float>(static_cast<double>(ph) + two_pi);
+    phase[f] = ph;
+}
+
+__global__ void cox_gather_kernel(const float* __restrict__ win, long long stride, const int* __restrict__ start,
+                                  int frame_len, float* __restrict__ frames) {
+    const long long f = blockIdx.x;
+    const int s0 = start[f];
+    const float* src = win + f * stride + (s0 >= 0 ? s0 : 0);
+    float* dst = frames + f * static_cast<long long>(frame_len);
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < frame_len; i += gridDim.y * blockDim.x)
+        dst[i] = (s0 >= 0) ? src[i] : 0.0f;                      // nothing found: a silent frame (decodes to "not valid")
+}
+
 // tap: Impl::measureCorrelation at one offset per window (parity tests)
 __global__ void __launch_bounds__(kThreads)
 cox_corr_tap_kernel(const CoxArgs a, const int* offsets, float* out) {
@@ -625,5 +656,98 @@ extern "C" int ria_ofdm_cox_correlation_batch_dev(ria_ctx* ctx, const ria_modem_
     cox_corr_tap_kernel<<<static_cast<unsigned>(g), kThreads, kTileSmem, ctx->stream>>>(a, offsets_dev, corr_dev);
     RIA_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
+    return RIA_OK;
+}
+
+// OFDMNvisWaveform::detectSync + process + the frame decoder for a batch of windows: search, then the presynced chain
+// (ria_ofdm_rx_frames_dev) on the frame that starts at the LTS position found, with the CFO found and the initial mixer
+// phase the waveform derives from them.  A window without sync yields a status with nothing valid; sync_dev (optional)
+// receives the search results.
+extern "C" int ria_ofdm_cox_rx_frames_dev(ria_ctx* ctx, const ria_modem_config* cfg, int rate, int use_channel_interleave,
+                                          const float* samples_dev, int64_t window_stride, int32_t window, int32_t frame_len,
+                                          float threshold, float* noise_floor_dev, int64_t n_windows,
+                                          uint8_t* data_dev, ria_frame_status* status_dev, float* snr_db_dev,
+                                          ria_sync_result* sync_dev) {
+    using namespace ria;
+    if (!ctx || !cfg) return RIA_E_INVAL;
+    if (n_windows < 0 || window < 0 || frame_len <= 0 || window_stride < window) return set_error(ctx, RIA_E_INVAL, "ofdm cox rx: bad sizes");
+    if (n_windows == 0) return RIA_OK;
+    if (!samples_dev || !data_dev || !status_dev) return set_error(ctx, RIA_E_INVAL, "ofdm cox rx: null buffer");
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    // buffers between the stages live in the chain scratch: sync results, start / cfo / phase, the gathered frames
+    const size_t b_sync = align256(static_cast<size_t>(n_windows) * sizeof(ria_sync_result));
+    const size_t b_i = align256(static_cast<size_t>(n_windows) * 4);
+    const size_t b_fr = align256(static_cast<size_t>(n_windows) * frame_len * sizeof(float));
+    const size_t need = b_sync + 3 * b_i + b_fr + 256;
+    if (need > ctx->chain_scratch_bytes) {
+        if (ctx->chain_scratch) RIA_CUDA(ctx, cudaFree(ctx->chain_scratch));
+        ctx->chain_scratch = nullptr; ctx->chain_scratch_bytes = 0;
+        RIA_CUDA(ctx, cudaMalloc(&ctx->chain_scratch, need));
+        ctx->chain_scratch_bytes = need;
+    }
+    unsigned char* base = static_cast<unsigned char*>(ctx->chain_scratch);
+    ria_sync_result* d_sync = sync_dev ? sync_dev : reinterpret_cast<ria_sync_result*>(base);
+    int* d_start = reinterpret_cast<int*>(base + b_sync);
+    float* d_cfo = reinterpret_cast<float*>(base + b_sync + b_i);
+    float* d_phase = reinterpret_cast<float*>(base + b_sync + 2 * b_i);
+    float* d_frames = reinterpret_cast<float*>(base + b_sync + 3 * b_i);
+    int rc = ria_ofdm_cox_search_sync_batch_dev(ctx, cfg, samples_dev, window_stride, window, threshold, noise_floor_dev,
+                                                n_windows, d_sync);
+    if (rc != RIA_OK) return rc;
+    cox_prepare_kernel<<<static_cast<unsigned>((n_windows + 255) / 256), 256, 0, ctx->stream>>>(
+        d_sync, n_windows, window, frame_len, static_cast<double>(cfg->sample_rate), d_start, d_cfo, d_phase);
+    cox_gather_kernel<<<dim3(static_cast<unsigned>(n_windows), 4), 256, 0, ctx->stream>>>(
+        samples_dev, window_stride, d_start, frame_len, d_frames);
+    RIA_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return ria_ofdm_rx_frames_dev(ctx, cfg, rate, use_channel_interleave, d_frames, frame_len, frame_len, d_cfo, d_phase,
+                                  n_windows, data_dev, status_dev, snr_db_dev);
+}
+
+extern "C" int ria_ofdm_cox_rx_frames_host(ria_ctx* ctx, const ria_modem_config* cfg, int rate, int use_channel_interleave,
+                                           const float* samples, int64_t window_stride, int32_t window, int32_t frame_len,
+                                           float threshold, float* noise_floor, int64_t n_windows,
+                                           uint8_t* data, ria_frame_status* status, float* snr_db, ria_sync_result* sync) {
+    using namespace ria;
+    if (!ctx || !cfg) return RIA_E_INVAL;
+    if (n_windows < 0 || window <= 0 || frame_len <= 0 || window_stride < window) return set_error(ctx, RIA_E_INVAL, "ofdm cox rx host: bad sizes");
+    if (n_windows == 0) return RIA_OK;
+    if (!samples || !data || !status) return set_error(ctx, RIA_E_INVAL, "ofdm cox rx host: null buffer");
+    const LdpcCodeHost* code = nullptr;
+    try { code = &ldpc_code_host(rate); } catch (...) { return set_error(ctx, RIA_E_INVAL, "ofdm cox rx host: bad rate %d", rate); }
+    const int out_row = 4 * (code->k / 8);
+    RIA_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t chunk = n_windows < 8192 ? n_windows : 8192;
+    const size_t b_in = align256(static_cast<size_t>(chunk) * window * sizeof(float));
+    const size_t b_nf = align256(static_cast<size_t>(chunk) * 4);
+    const size_t b_data = align256(static_cast<size_t>(chunk) * out_row);
+    const size_t b_st = align256(static_cast<size_t>(chunk) * sizeof(ria_frame_status));
+    const size_t b_sy = align256(static_cast<size_t>(chunk) * sizeof(ria_sync_result));
+    int rc = ensure_stage(ctx, 0, b_in + 2 * b_nf + b_data + b_st + b_sy + 256, 0);
+    if (rc != RIA_OK) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->stage_dev[0]);
+    float* d_in = reinterpret_cast<float*>(base);
+    float* d_nf = reinterpret_cast<float*>(base + b_in);
+    float* d_snr = reinterpret_cast<float*>(base + b_in + b_nf);
+    uint8_t* d_data = base + b_in + 2 * b_nf;
+    ria_frame_status* d_st = reinterpret_cast<ria_frame_status*>(base + b_in + 2 * b_nf + b_data);
+    ria_sync_result* d_sy = reinterpret_cast<ria_sync_result*>(base + b_in + 2 * b_nf + b_data + b_st);
+    cudaStream_t s = ctx->stream;
+    for (int64_t off = 0; off < n_windows; off += chunk) {
+        const int64_t n = std::min<int64_t>(chunk, n_windows - off);
+        RIA_CUDA(ctx, cudaMemcpy2DAsync(d_in, static_cast<size_t>(window) * sizeof(float), samples + off * window_stride,
+                                        static_cast<size_t>(window_stride) * sizeof(float), static_cast<size_t>(window) * sizeof(float),
+                                        static_cast<size_t>(n), cudaMemcpyHostToDevice, s));
+        if (noise_floor) RIA_CUDA(ctx, cudaMemcpyAsync(d_nf, noise_floor + off, n * sizeof(float), cudaMemcpyHostToDevice, s));
+        rc = ria_ofdm_cox_rx_frames_dev(ctx, cfg, rate, use_channel_interleave, d_in, window, window, frame_len, threshold,
+                                        noise_floor ? d_nf : nullptr, n, d_data, d_st, d_snr, d_sy);
+        if (rc != RIA_OK) return rc;
+        RIA_CUDA(ctx, cudaMemcpyAsync(data + off * out_row, d_data, static_cast<size_t>(n) * out_row, cudaMemcpyDeviceToHost, s));
+        RIA_CUDA(ctx, cudaMemcpyAsync(status + off, d_st, n * sizeof(ria_frame_status), cudaMemcpyDeviceToHost, s));
+        if (snr_db) RIA_CUDA(ctx, cudaMemcpyAsync(snr_db + off, d_snr, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (sync) RIA_CUDA(ctx, cudaMemcpyAsync(sync + off, d_sy, n * sizeof(ria_sync_result), cudaMemcpyDeviceToHost, s));
+        if (noise_floor) RIA_CUDA(ctx, cudaMemcpyAsync(noise_floor + off, d_nf, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        RIA_CUDA(ctx, cudaStreamSynchronize(s));
+    }
     return RIA_OK;
 }

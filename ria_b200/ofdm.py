@@ -306,6 +306,48 @@ class OfdmRxChain:
         return data, status, snr
 
 
+class OfdmCoxRxChain(OfdmRxChain):
+    """OFDM_COX windows -> info bytes + per-frame status, one C call per batch (``ria_ofdm_cox_rx_frames_dev`` / ``_host``):
+    OFDMNvisWaveform::detectSync (Schmidl-Cox search) -> process at the LTS position with the CFO and phase found -> frame
+    decode.  ``frame_len`` = samples from the first LTS symbol to the end of the frame."""
+
+    def process_windows(self, windows: torch.Tensor, frame_len: int, threshold: float = 0.8, noise_floor=None):
+        """windows CUDA fp32 [n, window] -> (data, status, snr, sync uint8 [n, 32])"""
+        from .sync import SYNC_RESULT_DTYPE
+        if not (isinstance(windows, torch.Tensor) and windows.is_cuda and windows.dtype == torch.float32 and windows.dim() == 2):
+            raise RiaError("process_windows wants CUDA fp32 [n, window] (no CPU fallback)")
+        if windows.stride(1) != 1:
+            windows = windows.contiguous()
+        n, window = windows.shape
+        dev = windows.device
+        data = torch.empty((n, 4 * self.bytes_per_cw), dtype=torch.uint8, device=dev)
+        status = torch.empty((n, FRAME_STATUS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        snr = torch.empty((n,), dtype=torch.float32, device=dev)
+        sync = torch.empty((n, SYNC_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        ctx = self.ctx
+        ctx.set_stream(torch.cuda.current_stream(dev))
+        ctx.check(lib().ria_ofdm_cox_rx_frames_dev(
+            ctx.handle, C.addressof(self.config), self.rate, int(self.use_ci), _ptr(windows), windows.stride(0), window,
+            int(frame_len), float(threshold), _ptr(noise_floor), n, _ptr(data), _ptr(status), _ptr(snr), _ptr(sync)))
+        return data, status, snr, sync
+
+    def process_windows_host(self, windows: np.ndarray, frame_len: int, threshold: float = 0.8):
+        """Host windows (numpy, ideally pinned) through ria_ofdm_cox_rx_frames_host -> (data, status, snr, sync)"""
+        from .sync import SYNC_RESULT_DTYPE
+        assert windows.dtype == np.float32 and windows.ndim == 2 and windows.strides[1] == 4
+        n, window = windows.shape
+        data = np.empty((n, 4 * self.bytes_per_cw), np.uint8)
+        status = np.empty(n, FRAME_STATUS_DTYPE)
+        snr = np.empty(n, np.float32)
+        sync = np.empty(n, SYNC_RESULT_DTYPE)
+        ctx = self.ctx
+        ctx.check(lib().ria_ofdm_cox_rx_frames_host(
+            ctx.handle, C.addressof(self.config), self.rate, int(self.use_ci), windows.ctypes.data, windows.strides[0] // 4,
+            window, int(frame_len), float(threshold), None, n, data.ctypes.data, status.ctypes.data, snr.ctypes.data,
+            sync.ctypes.data))
+        return data, status, snr, sync
+
+
 class OFDMChirpWaveform:
     """RX half of ultra::OFDMChirpWaveform (IWaveform) with batch = 1 semantics.
 

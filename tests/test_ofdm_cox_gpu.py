@@ -195,3 +195,74 @@ def test_acquire_then_demodulate_like_the_cox_waveform(ctx, ref):
         r = ref.ofdm_process_presynced(cfg_o, wins[i][starts[i]:starts[i] + flen], float(cfos[i]), float(wrapped[i]))
         assert r["ready"] and n_llr[i] == len(r["soft"])
         assert np.array_equal(llr[i, :n_llr[i]].view(np.uint32), r["soft"].view(np.uint32)), i
+
+
+def test_cox_chain_one_call_matches_the_stages(ctx, ref):
+    """ria_ofdm_cox_rx_frames_dev / _host: search + process + complete frame decode in one call; the decoded frames are the
+    ones that were sent, the sync results those of the search alone, windows without a frame come back not valid"""
+    import ria_b200
+    from ria_b200 import ofdm, sync
+    cfg_o = make_cfg(QAM64, 4, 1)
+    cfg = _ria_cfg(cfg_o)
+    rng = np.random.default_rng(77)
+    n, window, frame_len = 20, 26000, 12 * 1120
+    bps = cfg_o.data_carriers() * BITS_PER_CARRIER[cfg_o.modulation]
+    wins, sent = [], []
+    for i in range(n):
+        w = np.zeros(window, np.float32)
+        frame = None
+        if i % 5 != 4:
+            frame = ref.make_data_frame("K1ABC", "W2XYZ", i, rng.integers(0, 256, size=4 * BYTES_PER_CW[R3_4] - 19, dtype=np.uint8))
+            tx = ref.ofdm_cox_tx_frame(cfg_o, ref.encode_fixed_frame(frame, R3_4, True, bps))
+            # QAM64 survives almost no residual CFO in the reference itself: the CFO windows check the sync fields and the
+            # bit-exact failure, the others the decoded frames
+            cfo = float(rng.uniform(-1.5, 1.5)) if i % 4 == 1 else 0.0
+            lead = int(rng.integers(0, 5000))
+            if cfo:
+                tx = apply_cfo(np.concatenate([np.zeros(lead, np.float32), tx]), cfo)[lead:]
+            w[lead:lead + len(tx)] = tx
+            p = float(np.mean(tx[1120:].astype(np.float64) ** 2))
+            w += rng.standard_normal(window).astype(np.float32) * np.float32(np.sqrt(p / 10 ** (30.0 / 10)))
+        else:
+            w += rng.standard_normal(window).astype(np.float32) * np.float32(0.05)
+        wins.append(w); sent.append(frame)
+    x = np.stack(wins)
+    ctx.set_decode_flags(ria_b200.DECODE_FULL)
+    chain = ofdm.OfdmCoxRxChain(cfg, R3_4, True, ctx)
+    data, status, snr, sy = chain.process_windows(torch.from_numpy(x).cuda(), frame_len, 0.8)
+    torch.cuda.synchronize()
+    data = data.cpu().numpy(); st = ofdm.status_array(status); sy = sync.results(sy)
+    alone = sync.results(sync.ofdm_cox_search_sync_batch(cfg, torch.from_numpy(x).cuda(), 0.8, None, ctx))
+    h_data, h_st, h_snr, h_sy = chain.process_windows_host(x, frame_len, 0.8)
+    ctx.set_decode_flags(0)
+    n_ok = n_repaired_wrong = 0
+    for i in range(n):
+        assert sy["detected"][i] == alone["detected"][i] and sy["start_sample"][i] == alone["start_sample"][i]
+        assert np.float32(sy["cfo_hz"][i]).view(np.uint32) == np.float32(alone["cfo_hz"][i]).view(np.uint32)
+        f, pos, cfo, _ = ref.ofdm_cox_search_sync(cfg_o, wins[i], 0.8, 0.0)
+        assert bool(sy["detected"][i]) == f and (not f or sy["start_sample"][i] == pos)
+        ok = bool(st["all_ok"][i]) and bool(st["header_valid"][i]) and bool(st["frame_crc_ok"][i])
+        if f and pos + frame_len <= window:
+            # the reference's own process + decodeFixedFrame at the position / CFO / phase the waveform would use
+            ph = np.float32(-2.0 * np.pi * float(cfo) * float(pos) / 48000.0)
+            while float(ph) > np.pi:
+                ph = np.float32(float(ph) - 2.0 * np.pi)
+            while float(ph) < -np.pi:
+                ph = np.float32(float(ph) + 2.0 * np.pi)
+            r = ref.ofdm_process_presynced(cfg_o, wins[i][pos:pos + frame_len], float(cfo), float(ph))
+            rd, rok = ref.decode_fixed_frame_full(r["soft"], R3_4, True, bps)
+            rst = ref.frame_status_reassembled(rd, rok, BYTES_PER_CW[R3_4])
+            assert ok == bool(rok.all() and rst.header_valid and rst.frame_crc_ok), (i, ok, rok)
+            assert np.array_equal(data[i], np.frombuffer(bytes(rd), np.uint8)[: data.shape[1]]), i
+        if sent[i] is None:
+            assert not ok
+        elif ok:
+            # decodeFixedFrame's CRC-guided bit-flip search (frame_v2.cpp:1559-1874, up to 4 suspect bits against a 16-bit
+            # CRC) can settle on a wrong frame whose CRC matches; the reference does the same (asserted above) and it must
+            # stay the exception
+            if bytes(data[i, : len(sent[i])]) == sent[i]:
+                n_ok += 1
+            else:
+                n_repaired_wrong += 1
+        assert np.array_equal(h_data[i], data[i]) and h_st[i] == st[i] and h_sy["start_sample"][i] == sy["start_sample"][i]
+    assert n_ok >= 10 and n_repaired_wrong <= 2, (n_ok, n_repaired_wrong)
