@@ -955,10 +955,15 @@ __device__ __forceinline__ void frame_outputs(CarState& cs, const OfdmCarrierTab
 }
 
 // ======================================= FFT ================================================
-// The 1024-point tile lives in shared memory as float2, element j at fft_addr(j): j with the
-// rotated bits j9..j6 XORed into j3..j0.  For each pass the 16 lanes of every half-warp then hit
-// 16 different bank pairs, so all 64-bit loads/stores are conflict-free.
-__device__ __forceinline__ int fft_addr(int j) { return j ^ (((j >> 5) & 14) | ((j >> 9) & 1)); }
+// The 1024-point tile lives in shared memory as float2, element j at fft_addr(j): the 16 rows of 64 elements
+// (row = j9..j6) are shifted by 2 * (row & 7) + 17 * (row >> 3) elements (monotone, so rows do not overlap; 32 extra
+// elements).  For each pass the 16 lanes of every half-warp then hit 16 different bank pairs, so all 64-bit
+// loads/stores are conflict-free, and -- unlike an XOR swizzle -- every access of a pass is a per-thread base
+// plus a compile-time offset (the eight elements of a thread stay in one row, or step one row at a time in
+// pass 3: + 64 + 2 elements), which removes the address arithmetic from the per-frame loop.
+constexpr int kFftTilePad = 32;
+__device__ __forceinline__ int fft_addr(int j) { return j + 2 * ((j >> 6) & 7) + 17 * (j >> 9); }
+constexpr int kFftRowStep = 64 + 2;        // fft_addr(j + 64) - fft_addr(j) while (j >> 6) & 7 < 7
 // stage-major twiddle table: tw_L[k] = W[k * (1024 / L)], k < L/2, stored at offset L/2 - 2
 __device__ __forceinline__ int tw_off(int L) { return (L >> 1) - 2; }
 
@@ -1008,12 +1013,26 @@ __device__ __forceinline__ float2 bfly_half(float2 a, float2 b, float2 w_signed)
 }
 
 struct FftTile {
-    float2 x[kFft];
+    float2 x[kFft + kFftTilePad];
 };
+
+// Tile offsets (in elements) of the first element a thread touches in each pass; per-thread constants.  `pin` makes
+// them opaque to the compiler so they stay in registers instead of being recomputed for every frame.
+struct FftOffsets { int p1, p2, p3; };
+__device__ __forceinline__ FftOffsets fft_offsets(int tid, bool pin) {
+    const int lane = tid & 31, warp = tid >> 5;
+    FftOffsets o;
+    o.p1 = fft_addr(static_cast<int>(__brev(static_cast<unsigned>(tid)) >> 25) << 3);          // rows of 8 at brev7(tid)
+    o.p2 = fft_addr(((lane >> 1) << 6) | (warp << 1) | (lane & 1));                             // j9..j6 | j2 j1 j0
+    o.p3 = fft_addr(((warp >> 1) << 9) | ((warp & 1) << 5) | lane);                             // j9 | j5..j0
+    if (pin) asm volatile("" : "+r"(o.p1), "+r"(o.p2), "+r"(o.p3));
+    return o;
+}
 
 // passes 1 and 2 (stages L = 2 .. 64) on the 8 mixed samples each thread holds; v[t] = baseband
 // sample (tid + 128 * brev3(t)) of the FFT window.  Leaves the stage-64 result in the tile.
-__device__ __forceinline__ void fft_stages_2_to_64(FftTile& ft, const float2* __restrict__ tw, float2 (&v)[8], int tid) {
+__device__ __forceinline__ void fft_stages_2_to_64(FftTile& ft, const float2* __restrict__ tw, float2 (&v)[8], int tid,
+                                                   const FftOffsets& fo) {
     // ---- pass 1: stages L = 2, 4, 8 on data[8g .. 8g+7], g = brev7(tid) ----
     bfly0(v[0], v[1]); bfly0(v[2], v[3]); bfly0(v[4], v[5]); bfly0(v[6], v[7]);
     {
@@ -1024,19 +1043,18 @@ __device__ __forceinline__ void fft_stages_2_to_64(FftTile& ft, const float2* __
         bfly0(v[0], v[4]); bfly(v[1], v[5], x1); bfly(v[2], v[6], x2); bfly(v[3], v[7], x3);
     }
     {
-        const int g = __brev(static_cast<unsigned>(tid)) >> 25;      // brev7
+        float2* p = ft.x + fo.p1;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) ft.x[fft_addr((g << 3) | t)] = v[t];
+        for (int t = 0; t < 8; ++t) p[t] = v[t];
     }
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5;
     // ---- pass 2: stages L = 16, 32, 64; thread owns bits j5..j3 ----
     {
         const int lo = (warp << 1) | (lane & 1);                      // j2 j1 j0
-        const int hi = lane >> 1;                                     // j9..j6
-        const int jb = (hi << 6) | lo;
+        float2* p = ft.x + fo.p2;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ft.x[fft_addr(jb | (u << 3))];
+        for (int u = 0; u < 8; ++u) v[u] = p[u << 3];
         const float2 w16 = tw[tw_off(16) + lo];
         bfly(v[0], v[1], w16); bfly(v[2], v[3], w16); bfly(v[4], v[5], w16); bfly(v[6], v[7], w16);
         const float2 w32a = tw[tw_off(32) + lo], w32b = tw[tw_off(32) + 8 + lo];
@@ -1047,7 +1065,7 @@ __device__ __forceinline__ void fft_stages_2_to_64(FftTile& ft, const float2* __
         bfly(v[2], v[6], tw[tw_off(64) + 16 + lo]);
         bfly(v[3], v[7], tw[tw_off(64) + 24 + lo]);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) ft.x[fft_addr(jb | (u << 3))] = v[u];
+        for (int u = 0; u < 8; ++u) p[u << 3] = v[u];
     }
     __syncthreads();
 }
@@ -1056,14 +1074,14 @@ __device__ __forceinline__ void fft_stages_2_to_64(FftTile& ft, const float2* __
 // general path, used by the monolithic kernel and when the bins do not allow pruning.
 __device__ __forceinline__ void fft_stages_128_to_1024_full(FftTile& ft, const float2* __restrict__ tw,
                                                             const OfdmCarrierTable& car, float2* __restrict__ bin_out,
-                                                            int tid) {
+                                                            int tid, const FftOffsets& fo) {
     const int lane = tid & 31, warp = tid >> 5;
     float2 v[8];
     {
         const int lo6 = ((warp & 1) << 5) | lane;                     // j5..j0
-        const int jb = ((warp >> 1) << 9) | lo6;
+        float2* p = ft.x + fo.p3;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ft.x[fft_addr(jb | (u << 6))];
+        for (int u = 0; u < 8; ++u) v[u] = p[u * kFftRowStep];
         const float2 w128 = tw[tw_off(128) + lo6];
         bfly(v[0], v[1], w128); bfly(v[2], v[3], w128); bfly(v[4], v[5], w128); bfly(v[6], v[7], w128);
         const float2 w256a = tw[tw_off(256) + lo6], w256b = tw[tw_off(256) + 64 + lo6];
@@ -1074,7 +1092,7 @@ __device__ __forceinline__ void fft_stages_128_to_1024_full(FftTile& ft, const f
         bfly(v[2], v[6], tw[tw_off(512) + 128 + lo6]);
         bfly(v[3], v[7], tw[tw_off(512) + 192 + lo6]);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) ft.x[fft_addr(jb | (u << 6))] = v[u];
+        for (int u = 0; u < 8; ++u) p[u * kFftRowStep] = v[u];
     }
     __syncthreads();
     if (tid < car.num_carriers) {
@@ -1112,16 +1130,16 @@ __device__ __forceinline__ PrunedPlan make_pruned_plan(const float2* __restrict_
 }
 
 __device__ __forceinline__ void fft_stages_128_to_1024_pruned(FftTile& ft, float2* xch, const PrunedPlan& p,
-                                                              float2* __restrict__ bin_out, int tid) {
+                                                              float2* __restrict__ bin_out, int tid, const FftOffsets& fo) {
     const int lane = tid & 31, warp = tid >> 5;
     const int r = ((warp & 1) << 5) | lane;
     const int j9 = warp >> 1;
     float2 x = make_float2(0.f, 0.f);
     if (p.carrier >= 0) {
-        const int jb = (j9 << 9) | r;
+        const float2* pt = ft.x + fo.p3;
         float2 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ft.x[fft_addr(jb | (u << 6))];
+        for (int u = 0; u < 8; ++u) v[u] = pt[u * kFftRowStep];
         const float2 y0 = bfly_half(v[0], v[1], p.w128);
         const float2 y1 = bfly_half(v[2], v[3], p.w128);
         const float2 y2 = bfly_half(v[4], v[5], p.w128);
@@ -1173,10 +1191,8 @@ struct FftSmem {
     float2 tw[kTwCount];
     float2 nco[kFft];           // conj(mixer phasor) over the FFT window of the current symbol
     FftTile ft;
-    float2 xch[64];
+    float2 xch[64];             // before the item loop: residue -> carrier / bin maps (short[64] each) of the pruned plan
     OfdmCarrierTable car;
-    short res_car[64];
-    short res_k[64];
 };
 
 // MODE 0: first pass, no CFO vector; 1: first pass with the CFO handed in; 2: second pass (listed
@@ -1199,23 +1215,27 @@ ofdm_fft_kernel(const KernelArgs a) {
         int* dst = reinterpret_cast<int*>(&sm.car);
         for (int i = tid; i < static_cast<int>(sizeof(OfdmCarrierTable) / 4); i += kThreads) dst[i] = src[i];
     }
-    if (tid < 64) { sm.res_car[tid] = -1; sm.res_k[tid] = 0; }
+    short* res_car = reinterpret_cast<short*>(sm.xch);
+    short* res_k = res_car + 64;
+    if (tid < 64) { res_car[tid] = -1; res_k[tid] = 0; }
     __syncthreads();
     const int nc = sm.car.num_carriers;
     if (tid < nc) {
         const int k = sm.car.fft_idx[tid];
-        sm.res_car[k & 63] = static_cast<short>(tid);
-        sm.res_k[k & 63] = static_cast<short>(k);
+        res_car[k & 63] = static_cast<short>(tid);
+        res_k[k & 63] = static_cast<short>(k);
     }
     __syncthreads();
     PrunedPlan plan;
-    if (PRUNED) plan = make_pruned_plan(sm.tw, sm.res_car, sm.res_k, (((tid >> 5) & 1) << 5) | (tid & 31));
+    if (PRUNED) plan = make_pruned_plan(sm.tw, res_car, res_k, (((tid >> 5) & 1) << 5) | (tid & 31));
 
     const int n_sym = a.frame_len / a.sym_len;
     // first pass: every frame of the chunk; second pass: the frames the carrier stage listed
     const long long n_local = kSecond ? static_cast<long long>(*a.rerun_count) : a.frame_end - a.frame_begin;
     const unsigned n_groups = static_cast<unsigned>((n_local + kFftGroup - 1) / kFftGroup);
     const unsigned n_items = n_groups * static_cast<unsigned>(n_sym);
+    const long long out_step = static_cast<long long>(n_sym) * nc;
+    const FftOffsets fo = fft_offsets(tid, true);
     int cur_sym = -1;
 
     for (;;) {
@@ -1237,12 +1257,12 @@ ofdm_fft_kernel(const KernelArgs a) {
         const long long i1 = (i0 + kFftGroup < n_local) ? i0 + kFftGroup : n_local;
         auto frame_of = [&](long long i) -> long long { return a.frame_begin + (kSecond ? a.rerun_list[i] : i); };
 
+        // first pass: the frames of an item are consecutive, so the sample and bin pointers just step
+        const float* psrc = a.samples + frame_of(i0) * a.frame_stride + win + tid;
+        float2* out = a.bins + ((frame_of(i0) - a.bins_frame0) * n_sym + s) * nc;
         float nxt[8];
-        {
-            const float* p = a.samples + frame_of(i0) * a.frame_stride + win + tid;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) nxt[q] = __ldcs(p + 128 * q);
-        }
+        for (int q = 0; q < 8; ++q) nxt[q] = __ldcs(psrc + 128 * q);
         for (long long i = i0; i < i1; ++i) {
             const long long f = frame_of(i);
             // ---- mix: v[t] = baseband sample (tid + 128 * brev3(t)) of the FFT window ----
@@ -1251,13 +1271,14 @@ ofdm_fft_kernel(const KernelArgs a) {
             for (int t = 0; t < 8; ++t) {
                 const int q = ((t & 1) << 2) | (t & 2) | ((t & 4) >> 2);      // brev3
                 const float2 osc = sm.nco[tid + 128 * q];
-                // samples[i] * conj(osc)  ->  (osc.re * s, (-osc.im) * s)
-                v[t] = make_float2(__fmul_rn(osc.x, nxt[q]), __fmul_rn(osc.y, nxt[q]));
+                // samples[i] * conj(osc)  ->  (osc.re * s, (-osc.im) * s), one packed multiply
+                v[t] = mul2s(nxt[q], osc);
             }
             if (i + 1 < i1) {
-                const float* p = a.samples + frame_of(i + 1) * a.frame_stride + win + tid;
+                if (kSecond) psrc = a.samples + frame_of(i + 1) * a.frame_stride + win + tid;
+                else psrc += a.frame_stride;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) nxt[q] = __ldcs(p + 128 * q);
+                for (int q = 0; q < 8; ++q) nxt[q] = __ldcs(psrc + 128 * q);
             }
             if (kCfo) {
                 const float cfo = kSecond ? a.rerun_cfo[f - a.frame_begin] : a.cfo_hz[f];
@@ -1275,10 +1296,11 @@ ofdm_fft_kernel(const KernelArgs a) {
                     }
                 }
             }
-            fft_stages_2_to_64(sm.ft, sm.tw, v, tid);
-            float2* out = a.bins + ((f - a.bins_frame0) * n_sym + s) * nc;
-            if (PRUNED) fft_stages_128_to_1024_pruned(sm.ft, sm.xch, plan, out, tid);
-            else        fft_stages_128_to_1024_full(sm.ft, sm.tw, sm.car, out, tid);
+            fft_stages_2_to_64(sm.ft, sm.tw, v, tid, fo);
+            if (PRUNED) fft_stages_128_to_1024_pruned(sm.ft, sm.xch, plan, out, tid, fo);
+            else        fft_stages_128_to_1024_full(sm.ft, sm.tw, sm.car, out, tid, fo);
+            if (kSecond) { if (i + 1 < i1) out = a.bins + ((frame_of(i + 1) - a.bins_frame0) * n_sym + s) * nc; }
+            else out += out_step;
         }
     }
 }
@@ -1490,8 +1512,9 @@ __device__ void mono_fft_symbol(MonoSmem& sm, const KernelArgs& a, const float* 
         if (cfo_on) m = cmul(m, cexpj(sm.cph[i]));
         v[t] = m;
     }
-    fft_stages_2_to_64(sm.ft, sm.tw, v, tid);
-    fft_stages_128_to_1024_full(sm.ft, sm.tw, sm.car, sm.cs.bin, tid);
+    const FftOffsets fo = fft_offsets(tid, false);
+    fft_stages_2_to_64(sm.ft, sm.tw, v, tid, fo);
+    fft_stages_128_to_1024_full(sm.ft, sm.tw, sm.car, sm.cs.bin, tid, fo);
 }
 
 __global__ void __launch_bounds__(kThreads, 4)
