@@ -1029,10 +1029,22 @@ __device__ __forceinline__ FftOffsets fft_offsets(int tid, bool pin) {
     return o;
 }
 
+// twiddles of pass 2 (stages 16, 32, 64): per-thread constants, index = j2 j1 j0 of the thread
+struct Pass2Tw { float2 w16, w32a, w32b, w64[4]; };
+__device__ __forceinline__ Pass2Tw load_pass2_tw(const float2* __restrict__ tw, int tid) {
+    const int lo = ((tid >> 5) << 1) | (tid & 1);
+    Pass2Tw w;
+    w.w16 = tw[tw_off(16) + lo];
+    w.w32a = tw[tw_off(32) + lo]; w.w32b = tw[tw_off(32) + 8 + lo];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w.w64[q] = tw[tw_off(64) + 8 * q + lo];
+    return w;
+}
+
 // passes 1 and 2 (stages L = 2 .. 64) on the 8 mixed samples each thread holds; v[t] = baseband
 // sample (tid + 128 * brev3(t)) of the FFT window.  Leaves the stage-64 result in the tile.
 __device__ __forceinline__ void fft_stages_2_to_64(FftTile& ft, const float2* __restrict__ tw, float2 (&v)[8], int tid,
-                                                   const FftOffsets& fo) {
+                                                   const FftOffsets& fo, const Pass2Tw& w2) {
     // ---- pass 1: stages L = 2, 4, 8 on data[8g .. 8g+7], g = brev7(tid) ----
     bfly0(v[0], v[1]); bfly0(v[2], v[3]); bfly0(v[4], v[5]); bfly0(v[6], v[7]);
     {
@@ -1048,22 +1060,18 @@ __device__ __forceinline__ void fft_stages_2_to_64(FftTile& ft, const float2* __
         for (int t = 0; t < 8; ++t) p[t] = v[t];
     }
     __syncthreads();
-    const int lane = tid & 31, warp = tid >> 5;
     // ---- pass 2: stages L = 16, 32, 64; thread owns bits j5..j3 ----
     {
-        const int lo = (warp << 1) | (lane & 1);                      // j2 j1 j0
         float2* p = ft.x + fo.p2;
 #pragma unroll
         for (int u = 0; u < 8; ++u) v[u] = p[u << 3];
-        const float2 w16 = tw[tw_off(16) + lo];
-        bfly(v[0], v[1], w16); bfly(v[2], v[3], w16); bfly(v[4], v[5], w16); bfly(v[6], v[7], w16);
-        const float2 w32a = tw[tw_off(32) + lo], w32b = tw[tw_off(32) + 8 + lo];
-        bfly(v[0], v[2], w32a); bfly(v[4], v[6], w32a);
-        bfly(v[1], v[3], w32b); bfly(v[5], v[7], w32b);
-        bfly(v[0], v[4], tw[tw_off(64) + lo]);
-        bfly(v[1], v[5], tw[tw_off(64) + 8 + lo]);
-        bfly(v[2], v[6], tw[tw_off(64) + 16 + lo]);
-        bfly(v[3], v[7], tw[tw_off(64) + 24 + lo]);
+        bfly(v[0], v[1], w2.w16); bfly(v[2], v[3], w2.w16); bfly(v[4], v[5], w2.w16); bfly(v[6], v[7], w2.w16);
+        bfly(v[0], v[2], w2.w32a); bfly(v[4], v[6], w2.w32a);
+        bfly(v[1], v[3], w2.w32b); bfly(v[5], v[7], w2.w32b);
+        bfly(v[0], v[4], w2.w64[0]);
+        bfly(v[1], v[5], w2.w64[1]);
+        bfly(v[2], v[6], w2.w64[2]);
+        bfly(v[3], v[7], w2.w64[3]);
 #pragma unroll
         for (int u = 0; u < 8; ++u) p[u << 3] = v[u];
     }
@@ -1198,8 +1206,11 @@ struct FftSmem {
 // MODE 0: first pass, no CFO vector; 1: first pass with the CFO handed in; 2: second pass (listed
 // frames, corrected CFO).  Separate instances keep the rotation code and the list indirection out
 // of the plain transform (no spills at 64 registers).
+// Five CTAs per SM: the kernel is bound by shared-memory wavefronts and the fp32 pipe, not by occupancy, so the
+// registers go to what is constant per thread -- the mixer phasors of the item's symbol (16), the pass-2 twiddles
+// (14), the pruned plan (8) and the tile offsets -- instead of being re-read from shared memory for every frame.
 template <bool PRUNED, int MODE>
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads, 5)
 ofdm_fft_kernel(const KernelArgs a) {
     constexpr bool kSecond = (MODE == 2);
     constexpr bool kCfo = (MODE != 0);
@@ -1236,6 +1247,7 @@ ofdm_fft_kernel(const KernelArgs a) {
     const unsigned n_items = n_groups * static_cast<unsigned>(n_sym);
     const long long out_step = static_cast<long long>(n_sym) * nc;
     const FftOffsets fo = fft_offsets(tid, true);
+    const Pass2Tw w2 = load_pass2_tw(sm.tw, tid);      // sm.tw is complete: staged before the barriers above
     int cur_sym = -1;
 
     for (;;) {
@@ -1263,6 +1275,9 @@ ofdm_fft_kernel(const KernelArgs a) {
         float nxt[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) nxt[q] = __ldcs(psrc + 128 * q);
+        float2 oscr[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) oscr[q] = sm.nco[tid + 128 * q];
         for (long long i = i0; i < i1; ++i) {
             const long long f = frame_of(i);
             // ---- mix: v[t] = baseband sample (tid + 128 * brev3(t)) of the FFT window ----
@@ -1270,7 +1285,7 @@ ofdm_fft_kernel(const KernelArgs a) {
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 const int q = ((t & 1) << 2) | (t & 2) | ((t & 4) >> 2);      // brev3
-                const float2 osc = sm.nco[tid + 128 * q];
+                const float2 osc = oscr[q];
                 // samples[i] * conj(osc)  ->  (osc.re * s, (-osc.im) * s), one packed multiply
                 v[t] = mul2s(nxt[q], osc);
             }
@@ -1296,7 +1311,7 @@ ofdm_fft_kernel(const KernelArgs a) {
                     }
                 }
             }
-            fft_stages_2_to_64(sm.ft, sm.tw, v, tid, fo);
+            fft_stages_2_to_64(sm.ft, sm.tw, v, tid, fo, w2);
             if (PRUNED) fft_stages_128_to_1024_pruned(sm.ft, sm.xch, plan, out, tid, fo);
             else        fft_stages_128_to_1024_full(sm.ft, sm.tw, sm.car, out, tid, fo);
             if (kSecond) { if (i + 1 < i1) out = a.bins + ((frame_of(i + 1) - a.bins_frame0) * n_sym + s) * nc; }
@@ -1513,7 +1528,7 @@ __device__ void mono_fft_symbol(MonoSmem& sm, const KernelArgs& a, const float* 
         v[t] = m;
     }
     const FftOffsets fo = fft_offsets(tid, false);
-    fft_stages_2_to_64(sm.ft, sm.tw, v, tid, fo);
+    fft_stages_2_to_64(sm.ft, sm.tw, v, tid, fo, load_pass2_tw(sm.tw, tid));
     fft_stages_128_to_1024_full(sm.ft, sm.tw, sm.car, sm.cs.bin, tid, fo);
 }
 
