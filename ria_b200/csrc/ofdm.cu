@@ -1209,11 +1209,14 @@ struct FftSmem {
 // Five CTAs per SM: the kernel is bound by shared-memory wavefronts and the fp32 pipe, not by occupancy, so the
 // registers go to what is constant per thread -- the mixer phasors of the item's symbol (16), the pass-2 twiddles
 // (14), the pruned plan (8) and the tile offsets -- instead of being re-read from shared memory for every frame.
+// The CFO variants are bound by instruction issue (glibc's sincosf per sample) and keep eight CTAs at 64 registers,
+// re-reading those constants from shared memory.
 template <bool PRUNED, int MODE>
-__global__ void __launch_bounds__(kThreads, 5)
+__global__ void __launch_bounds__(kThreads, MODE == 0 ? 5 : 8)
 ofdm_fft_kernel(const KernelArgs a) {
     constexpr bool kSecond = (MODE == 2);
     constexpr bool kCfo = (MODE != 0);
+    constexpr bool kRegConst = (MODE == 0);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FftSmem& sm = *reinterpret_cast<FftSmem*>(smem_raw);
     __shared__ unsigned int item_sh;
@@ -1247,7 +1250,8 @@ ofdm_fft_kernel(const KernelArgs a) {
     const unsigned n_items = n_groups * static_cast<unsigned>(n_sym);
     const long long out_step = static_cast<long long>(n_sym) * nc;
     const FftOffsets fo = fft_offsets(tid, true);
-    const Pass2Tw w2 = load_pass2_tw(sm.tw, tid);      // sm.tw is complete: staged before the barriers above
+    Pass2Tw w2{};
+    if (kRegConst) w2 = load_pass2_tw(sm.tw, tid);      // sm.tw is complete: staged before the barriers above
     int cur_sym = -1;
 
     for (;;) {
@@ -1276,8 +1280,10 @@ ofdm_fft_kernel(const KernelArgs a) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) nxt[q] = __ldcs(psrc + 128 * q);
         float2 oscr[8];
+        if (kRegConst) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) oscr[q] = sm.nco[tid + 128 * q];
+            for (int q = 0; q < 8; ++q) oscr[q] = sm.nco[tid + 128 * q];
+        }
         for (long long i = i0; i < i1; ++i) {
             const long long f = frame_of(i);
             // ---- mix: v[t] = baseband sample (tid + 128 * brev3(t)) of the FFT window ----
@@ -1285,7 +1291,7 @@ ofdm_fft_kernel(const KernelArgs a) {
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 const int q = ((t & 1) << 2) | (t & 2) | ((t & 4) >> 2);      // brev3
-                const float2 osc = oscr[q];
+                const float2 osc = kRegConst ? oscr[q] : sm.nco[tid + 128 * q];
                 // samples[i] * conj(osc)  ->  (osc.re * s, (-osc.im) * s), one packed multiply
                 v[t] = mul2s(nxt[q], osc);
             }
@@ -1311,7 +1317,7 @@ ofdm_fft_kernel(const KernelArgs a) {
                     }
                 }
             }
-            fft_stages_2_to_64(sm.ft, sm.tw, v, tid, fo, w2);
+            fft_stages_2_to_64(sm.ft, sm.tw, v, tid, fo, kRegConst ? w2 : load_pass2_tw(sm.tw, tid));
             if (PRUNED) fft_stages_128_to_1024_pruned(sm.ft, sm.xch, plan, out, tid, fo);
             else        fft_stages_128_to_1024_full(sm.ft, sm.tw, sm.car, out, tid, fo);
             if (kSecond) { if (i + 1 < i1) out = a.bins + ((frame_of(i + 1) - a.bins_frame0) * n_sym + s) * nc; }
@@ -1736,15 +1742,14 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
         return RIA_OK;
     }
 
-    int fft_per_sm = 0, car_per_sm = 0;
+    int car_per_sm = 0;
     void (*fft_kernels[3])(const KernelArgs);
     if (a.pruned) { fft_kernels[0] = ofdm_fft_kernel<true, 0>; fft_kernels[1] = ofdm_fft_kernel<true, 1>; fft_kernels[2] = ofdm_fft_kernel<true, 2>; }
     else          { fft_kernels[0] = ofdm_fft_kernel<false, 0>; fft_kernels[1] = ofdm_fft_kernel<false, 1>; fft_kernels[2] = ofdm_fft_kernel<false, 2>; }
+    int fft_per_sm_mode[3] = {0, 0, 0};          // the plain variant runs fewer, register-heavier CTAs than the CFO ones
     for (int m = 0; m < 3; ++m) {
-        int per = 0;
-        rc = blocks_per_sm(ctx, fft_kernels[m], kThreads, sizeof(FftSmem), &per);
+        rc = blocks_per_sm(ctx, fft_kernels[m], kThreads, sizeof(FftSmem), &fft_per_sm_mode[m]);
         if (rc != RIA_OK) return rc;
-        if (m == 0 || per < fft_per_sm) fft_per_sm = per;
     }
     void (*carrier_kernel)(const KernelArgs) = nullptr;
     static const bool carrier_g32 = getenv("RIA_CARRIER_G32") != nullptr;      // A/B: one frame per warp
@@ -1802,8 +1807,6 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
         else          { a.bins = bins_scratch; a.bins_frame0 = off; }
         RIA_CUDA(ctx, cudaMemsetAsync(ctr, 0, 5 * sizeof(unsigned int), st));
         const long long items = ((n + kFftGroup - 1) / kFftGroup) * n_sym;
-        long long fft_grid = static_cast<long long>(ctx->sm_count) * fft_per_sm;
-        if (fft_grid > items) fft_grid = items;
         long long car_grid = static_cast<long long>(ctx->sm_count) * car_per_sm;
         if (car_grid > (n + kCarWarps - 1) / kCarWarps) car_grid = (n + kCarWarps - 1) / kCarWarps;
         // pass 0: every frame with the CFO it was handed; pass 1: the frames whose LTS asked for
@@ -1819,8 +1822,11 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
                 ctx->launches += 1;
             }
             a.counter = ctr + (pass ? 3 : 0);
+            const int mode = pass ? 2 : (cfo_hz_dev ? 1 : 0);
+            long long fft_grid = static_cast<long long>(ctx->sm_count) * fft_per_sm_mode[mode];
+            if (fft_grid > items) fft_grid = items;
             time_begin(ctx, KK_OFDM_FFT);
-            fft_kernels[pass ? 2 : (cfo_hz_dev ? 1 : 0)]<<<static_cast<unsigned>(fft_grid), kThreads, sizeof(FftSmem), st>>>(a);
+            fft_kernels[mode]<<<static_cast<unsigned>(fft_grid), kThreads, sizeof(FftSmem), st>>>(a);
             time_end(ctx);
             a.counter = ctr + (pass ? 4 : 1);
             time_begin(ctx, KK_OFDM_CARRIER);

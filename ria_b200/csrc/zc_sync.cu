@@ -187,12 +187,13 @@ __device__ __forceinline__ void better(float& bv, int& bi, float v, int i) {
 
 __global__ void __launch_bounds__(128)
 zc_finish_kernel(const FinishArgs a) {
-    extern __shared__ float2 sm_zc[];                       // [ref_samples]
+    extern __shared__ float2 sm_zc[];                       // [ref_samples] template | [3 * ref_samples] baseband span
     __shared__ float red_v[128];
     __shared__ int red_i[128];
     __shared__ float2 fine_corr[160];
-    __shared__ float2 aux_sum[3];
-    __shared__ float aux_en[3];
+    __shared__ float2 lag_sum[4];                           // correlations at peak - R, peak, peak + R
+    __shared__ float lag_en[4];
+    float2* span = sm_zc + a.ref_samples;
     const long long f = blockIdx.x;
     const int tid = threadIdx.x;
     const float2* bb = a.bb + f * a.bb_stride;
@@ -223,9 +224,14 @@ zc_finish_kernel(const FinishArgs a) {
         const int fine_end = min(corr_len, coarse_best + a.step + 1);
         __syncthreads();
         // ---- fine lags (:568-596) ----
-        if (tid < fine_end - fine_start) {
+        // The 1016-term sums are sequential per lag; read from global memory they were bound by load latency
+        // (one thread, four loads in flight).  The span the lags touch is staged in shared memory first.
+        const int n_fine = fine_end - fine_start;
+        for (int i = tid; i < n_fine - 1 + R; i += 128) span[i] = bb[fine_start + i];
+        __syncthreads();
+        if (tid < n_fine) {
             float2 sum; float en;
-            corr_at(bb, sm_zc, R, fine_start + tid, &sum, &en);
+            corr_at(span, sm_zc, R, tid, &sum, &en);
             const float denom = sqrtf(__fmul_rn(en, ref_energy));
             fine_corr[tid] = (denom > 1e-10f) ? make_float2(__fdiv_rn(sum.x, denom), __fdiv_rn(sum.y, denom)) : make_float2(0.f, 0.f);
         }
@@ -236,7 +242,7 @@ zc_finish_kernel(const FinishArgs a) {
             const int lag = k * a.step;
             if (lag < fine_start || lag >= fine_end) better(bv, bi, cabs_d(ccorr[k]), lag);
         }
-        if (tid < fine_end - fine_start) better(bv, bi, cabs_d(fine_corr[tid]), fine_start + tid);
+        if (tid < n_fine) better(bv, bi, cabs_d(fine_corr[tid]), fine_start + tid);
         red_v[tid] = bv; red_i[tid] = bi;
         __syncthreads();
         for (int s = 64; s > 0; s >>= 1) {
@@ -245,25 +251,34 @@ zc_finish_kernel(const FinishArgs a) {
         }
         const float peak_mag = red_v[0];
         const int peak_pos = red_i[0];
-        // ---- rep-1 check (:255-277) ----
-        const bool check_earlier = (peak_mag > a.threshold) && (peak_pos >= R);
-        if (check_earlier && tid == 0) corr_at(bb, sm_zc, R, peak_pos - R, &aux_sum[0], &aux_en[0]);
+        // ---- rep-1 check (:255-277) and the two repetitions (:279-370) ----
+        // The reference correlates at peak - R (rep-1 check), then at timing_pos and timing_pos + R with timing_pos one of
+        // {peak, peak - R}: all of them are among the lags peak - R, peak, peak + R, which three threads evaluate at once
+        // from one staged span (a correlation nobody asks for has no side effect).
+        const int lo = max(0, peak_pos - R), hi = min(a.window, peak_pos + 2 * R);
+        for (int i = tid; i < hi - lo; i += 128) span[i] = bb[lo + i];
         __syncthreads();
+        if (tid < 3) {
+            const int lag = peak_pos + (tid - 1) * R;
+            if (lag >= 0 && lag + R <= a.window) corr_at(span, sm_zc, R, lag - lo, &lag_sum[tid], &lag_en[tid]);
+        }
+        __syncthreads();
+        const bool check_earlier = (peak_mag > a.threshold) && (peak_pos >= R);
         int timing_pos = peak_pos;
         if (check_earlier) {
-            const float earlier_mag = norm_mag(aux_sum[0], aux_en[0], ref_energy);      // lag >= 0 and fits by construction
+            const float earlier_mag = norm_mag(lag_sum[0], lag_en[0], ref_energy);        // lag >= 0 and fits by construction
             if (earlier_mag > peak_mag * 0.4f) timing_pos = peak_pos - R;
         }
         const int rep2_pos = timing_pos + R;
         const bool rep2_fits = rep2_pos + R <= a.window;
-        __syncthreads();
-        if (rep2_fits && tid < 2) corr_at(bb, sm_zc, R, tid == 0 ? timing_pos : rep2_pos, &aux_sum[1 + tid], &aux_en[1 + tid]);
-        __syncthreads();
+        const int t1 = (timing_pos == peak_pos) ? 1 : 0;                                  // slot of timing_pos; rep2 is the next one
+        const float2 rep_sum1 = lag_sum[t1], rep_sum2 = lag_sum[t1 + 1];
+        const float rep_en1 = lag_en[t1], rep_en2 = lag_en[t1 + 1];
         // ---- low-SNR combining (:279-299) ----
         float combined = peak_mag;
         if (peak_mag > 0.0f && peak_mag < 0.25f && rep2_fits) {
-            const float r1 = norm_mag(aux_sum[1], aux_en[1], ref_energy);
-            const float r2 = norm_mag(aux_sum[2], aux_en[2], ref_energy);
+            const float r1 = norm_mag(rep_sum1, rep_en1, ref_energy);
+            const float r2 = norm_mag(rep_sum2, rep_en2, ref_energy);
             combined = sqrtf(r1 * r1 + r2 * r2) / sqrtf(2.0f);
             combined = (combined < peak_mag) ? peak_mag : combined;                      // std::max(combined, peak)
         }
@@ -271,9 +286,9 @@ zc_finish_kernel(const FinishArgs a) {
         if (combined > best_corr) {
             best_corr = combined; best_root = a.roots[r]; best_pos = timing_pos;
             if (rep2_fits) {
-                const float c1 = cabs_d(aux_sum[1]) / R, c2 = cabs_d(aux_sum[2]) / R;
+                const float c1 = cabs_d(rep_sum1) / R, c2 = cabs_d(rep_sum2) / R;
                 if (c1 > 0.1f && c2 > 0.1f) {
-                    const float2 x = aux_sum[2], y = aux_sum[1];                          // corr2 * conj(corr1)
+                    const float2 x = rep_sum2, y = rep_sum1;                              // corr2 * conj(corr1)
                     const float re = __fsub_rn(__fmul_rn(x.x, y.x), __fmul_rn(x.y, -y.y));
                     const float im = __fadd_rn(__fmul_rn(x.x, -y.y), __fmul_rn(x.y, y.x));
                     const float phase_diff = glibc_atan2f(im, re);                        // std::arg (:351) = glibc atan2f, restated
@@ -441,7 +456,10 @@ extern "C" int ria_zc_detect_batch_dev(ria_ctx* ctx, const ria_zc_config* cfg,
     fa.zc_g = t->zc_interp; fa.ref_samples = R; fa.step = step; fa.n_coarse = n_coarse; fa.n_roots = n_roots;
     fa.coarse_corr = d_cc; fa.coarse_mag = d_cm; fa.threshold = threshold; fa.sample_rate = cfg->sample_rate;
     fa.preamble_len = preamble_len; fa.cfg = *cfg; fa.out = out_dev;
-    zc_finish_kernel<<<static_cast<unsigned>(n_frames), 128, R * sizeof(float2), ctx->stream>>>(fa);
+    const size_t finish_smem = static_cast<size_t>(4) * R * sizeof(float2);
+    if (finish_smem > ctx->smem_optin) return set_error(ctx, RIA_E_UNSUPPORTED, "zc: preamble of %d samples does not fit in shared memory", R);
+    RIA_CUDA(ctx, cudaFuncSetAttribute(zc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(finish_smem)));
+    zc_finish_kernel<<<static_cast<unsigned>(n_frames), 128, finish_smem, ctx->stream>>>(fa);
     time_end(ctx);
     RIA_CUDA(ctx, cudaGetLastError());
     ctx->launches += 3;
