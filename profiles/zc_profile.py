@@ -12,7 +12,7 @@ from ria_b200 import sim, sync
 
 ctx = ria_b200.Context(0)
 dev = torch.device("cuda", 0)
-pre = sync.zc_preamble(root=2, device=dev, ctx=ctx)
+pre = sync.zc_preamble(root=5, device=dev, ctx=ctx)
 window = 31120
 rows = torch.zeros((8, window), device=dev)
 rows[:, 5000:5000 + pre.numel()] = pre
@@ -23,3 +23,12 @@ for _ in range(3):
 torch.cuda.synchronize()
 r = sync.results(out)
 print("detected", int(r["detected"].sum()), "of", len(r))
+if os.environ.get("ZC_TIME"):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        zc.detect_batch(rows, 0.2, sync.ZC_ROOT_MASK_DATA | sync.ZC_ROOT_MASK_CONTROL, None)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print("ms per %d windows: %.3f  (%.3f M windows/s)" % (rows.shape[0], ms, rows.shape[0] / ms / 1e3))
