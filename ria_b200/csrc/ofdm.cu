@@ -1408,21 +1408,20 @@ ofdm_carrier_kernel(const KernelArgs a) {
 // for two frames at once.  The halves advance in lock step through the frame loop; a half whose frame leaves early
 // (too short, residual-CFO re-run, end of the batch) sits out the rest of the iteration.
 constexpr int kCar2Warps = 2;       // 4 frames per CTA
+// The carrier tables (2 KB, read-only, the same for every CTA) are read from global memory through L1 here: without
+// them in shared memory a tenth CTA fits on the SM.
+struct Car2Smem {
+    CarState cs[2 * kCar2Warps];
+};
 
 template <int MOD>
 __global__ void __launch_bounds__(kCar2Warps * 32)
 ofdm_carrier2_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CarSmem& sm = *reinterpret_cast<CarSmem*>(smem_raw);
+    Car2Smem& sm = *reinterpret_cast<Car2Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, g = tid & 15, grp = tid >> 4;
     if (a.second_pass && *a.rerun_count == 0) return;
-    {
-        const int* src = reinterpret_cast<const int*>(a.car_g);
-        int* dst = reinterpret_cast<int*>(&sm.car);
-        for (int i = tid; i < static_cast<int>(sizeof(OfdmCarrierTable) / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    const OfdmCarrierTable& car = sm.car;
+    const OfdmCarrierTable& car = *a.car_g;
     CarState& cs = sm.cs[grp];
     const int nc = car.num_carriers;
     const int n_sym = a.frame_len / a.sym_len;
@@ -1778,7 +1777,8 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
         case RIA_QAM256: carrier_kernel = ofdm_carrier_kernel<RIA_QAM256>; break;
         default: return set_error(ctx, RIA_E_UNSUPPORTED, "ofdm: modulation %u has no demapper", cfg->modulation);
     }
-    rc = blocks_per_sm(ctx, carrier_kernel, car_threads, sizeof(CarSmem), &car_per_sm);
+    const size_t car_smem = carrier_g32 ? sizeof(CarSmem) : sizeof(Car2Smem);
+    rc = blocks_per_sm(ctx, carrier_kernel, car_threads, car_smem, &car_per_sm);
     if (rc != RIA_OK) return rc;
 
     // chunk of frames whose carrier bins live in scratch between the stages
@@ -1830,7 +1830,7 @@ extern "C" int ria_ofdm_presynced_batch_taps_dev(ria_ctx* ctx, const ria_modem_c
             time_end(ctx);
             a.counter = ctr + (pass ? 4 : 1);
             time_begin(ctx, KK_OFDM_CARRIER);
-            carrier_kernel<<<static_cast<unsigned>(car_grid), car_threads, sizeof(CarSmem), st>>>(a);
+            carrier_kernel<<<static_cast<unsigned>(car_grid), car_threads, car_smem, st>>>(a);
             time_end(ctx);
             ctx->launches += 2;
         }
