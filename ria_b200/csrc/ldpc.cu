@@ -83,7 +83,7 @@ ldpc_decode_kernel(const float* __restrict__ llr_g, long long n_cw, const LdpcGa
         ldpc_core::decode_codeword(llr, tot, msg, chk_var, var_slot, k, m, dv_max, max_iter, factor, lane, success, iters,
                                    try_sc, &took);
         if (try_sc) { ++sc_tries; sc_hits += took ? 1 : 0; }
-        ldpc_core::pack_info(tot, k, info_g + cw * info_stride, info_stride, lane);
+        ldpc_core::pack_info((try_sc && took) ? llr : tot, k, info_g + cw * info_stride, info_stride, lane);
         if (lane == 0) {
             ok_g[cw] = success ? 1 : 0;
             iters_g[cw] = iters;

@@ -122,13 +122,13 @@ __device__ __forceinline__ void decode_codeword(float* llr, float* tot, float4* 
                                                 int max_iter, float factor, int lane, bool& success, int& iters,
                                                 bool try_shortcut = false, bool* took_shortcut = nullptr) {
     __syncwarp();
-    for (int j = lane; j < k; j += 32) tot[j] = llr[j];
     // Clean codeword shortcut.  If the channel hard decisions already satisfy every check, each
     // check-to-variable message of the first iteration carries the sign of "the other bits' parity",
     // which is the variable's own sign, so no total changes sign: the reference stops after its first
     // iteration with exactly these bits and reports 0 iterations (ldpc_decoder.cpp:226-238).  The first
     // check / variable update is skipped; the result (bits, success, count) is the same.  max_iter = 0
-    // runs no iteration and never succeeds (:170), so the shortcut needs max_iter >= 1.
+    // runs no iteration and never succeeds (:170), so the shortcut needs max_iter >= 1.  The totals of a shortcut
+    // codeword are its channel values: the caller packs the info bits from llr[] (tot[] is not written).
     if (took_shortcut) *took_shortcut = false;
     if (try_shortcut && max_iter >= 1) {
         bool bad = false;
@@ -150,6 +150,7 @@ __device__ __forceinline__ void decode_codeword(float* llr, float* tot, float4* 
             return;
         }
     }
+    for (int j = lane; j < k; j += 32) tot[j] = llr[j];
     for (int i = lane; i < m; i += 32) {
         msg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         msg[m + i] = make_float4(0.f, 0.f, 0.f, llr[k + i]);   // slot 7 = parity total
