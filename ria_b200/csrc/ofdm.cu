@@ -1422,7 +1422,11 @@ ofdm_carrier2_kernel(const KernelArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, g = tid & 15, grp = tid >> 4;
     if (a.second_pass && *a.rerun_count == 0) return;
     const OfdmCarrierTable& car = *a.car_g;
-    CarState& cs = sm.cs[grp];
+    // The two groups of a warp touch the same element of their states in the same instruction.  sizeof(CarState) is
+    // 96 mod 128 bytes, so neighbouring states would overlap in 8 of their 16 banks (2-way conflict on every 32-bit
+    // access); two states apart the offset is 64 mod 128 bytes and the halves of the warp use disjoint banks.
+    static_assert((2 * sizeof(CarState)) % 128 == 64, "group states of one warp must sit 16 banks apart");
+    CarState& cs = sm.cs[((grp & 1) << 1) | (grp >> 1)];
     const int nc = car.num_carriers;
     const int n_sym = a.frame_len / a.sym_len;
     const int n_data_sym = n_sym - 2;
