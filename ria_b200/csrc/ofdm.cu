@@ -1449,7 +1449,7 @@ ofdm_carrier2_kernel(const KernelArgs a) {
             frame_reset<16>(cs, a, f, g);
             // ---- LTS: estimateChannelFromLTS (channel_equalizer.cpp:193-643) ----
             for (int s = 0; s < 2; ++s) {
-                for (int c = g; c < nc; c += 16) cs.bin[c] = fb[s * nc + c];
+                for (int c = g; c < nc; c += 16) cs.bin[c] = __ldcs(fb + s * nc + c);      // streamed: keep L1 for the tables
                 gsync<16>();
                 lts_symbol<16>(cs, car, s, g);
             }
@@ -1471,7 +1471,7 @@ ofdm_carrier2_kernel(const KernelArgs a) {
 #pragma unroll
             for (int q = 0; q < kPer; ++q) {
                 nb[q] = make_float2(0.f, 0.f);
-                if (n_data_sym > 0 && g + 16 * q < nc) nb[q] = fb[2 * nc + g + 16 * q];
+                if (n_data_sym > 0 && g + 16 * q < nc) nb[q] = __ldcs(fb + 2 * nc + g + 16 * q);
             }
             for (int sd = 0; sd < n_data_sym; ++sd) {
 #pragma unroll
@@ -1479,7 +1479,7 @@ ofdm_carrier2_kernel(const KernelArgs a) {
                 gsync<16>();
                 if (sd + 1 < n_data_sym) {          // prefetch the next symbol's bins
 #pragma unroll
-                    for (int q = 0; q < kPer; ++q) if (g + 16 * q < nc) nb[q] = fb[(3 + sd) * nc + g + 16 * q];
+                    for (int q = 0; q < kPer; ++q) if (g + 16 * q < nc) nb[q] = __ldcs(fb + (3 + sd) * nc + g + 16 * q);
                 }
                 data_symbol<16, MOD>(cs, car, a, llr_out, sd, g);
             }
