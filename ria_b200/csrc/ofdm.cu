@@ -57,7 +57,7 @@ constexpr int kThreads = 128;
 constexpr int kFft = 1024;
 constexpr int kMaxSymLen = 1160;    // fft 1024 + CP <= 128 + guard <= 8
 constexpr int kTwCount = 1024;      // stage-major twiddle table (1022 used)
-constexpr int kFftGroup = 16;       // frames per (symbol, group) work item of the FFT kernel
+constexpr int kFftGroup = 32;       // frames per (symbol, group) work item of the FFT kernel
 constexpr int kCarWarps = 4;        // frames per CTA of the carrier kernel
 
 // ------------------------------- complex helpers -------------------------------------------
@@ -1030,7 +1030,7 @@ __device__ __forceinline__ FftOffsets fft_offsets(int tid, bool pin) {
 }
 
 // twiddles of pass 2 (stages 16, 32, 64): per-thread constants, index = j2 j1 j0 of the thread
-struct Pass2Tw { float2 w16, w32a, w32b, w64[4]; };
+struct Pass2Tw { float2 w16, w32a, w32b, w64[4], w4, w8[3]; };       // + the (uniform) twiddles of stages 4 and 8
 __device__ __forceinline__ Pass2Tw load_pass2_tw(const float2* __restrict__ tw, int tid) {
     const int lo = ((tid >> 5) << 1) | (tid & 1);
     Pass2Tw w;
@@ -1038,6 +1038,9 @@ __device__ __forceinline__ Pass2Tw load_pass2_tw(const float2* __restrict__ tw, 
     w.w32a = tw[tw_off(32) + lo]; w.w32b = tw[tw_off(32) + 8 + lo];
 #pragma unroll
     for (int q = 0; q < 4; ++q) w.w64[q] = tw[tw_off(64) + 8 * q + lo];
+    w.w4 = tw[tw_off(4) + 1];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) w.w8[q] = tw[tw_off(8) + 1 + q];
     return w;
 }
 
@@ -1048,11 +1051,9 @@ __device__ __forceinline__ void fft_stages_2_to_64(FftTile& ft, const float2* __
     // ---- pass 1: stages L = 2, 4, 8 on data[8g .. 8g+7], g = brev7(tid) ----
     bfly0(v[0], v[1]); bfly0(v[2], v[3]); bfly0(v[4], v[5]); bfly0(v[6], v[7]);
     {
-        const float2 w1 = tw[tw_off(4) + 1];
-        bfly0(v[0], v[2]); bfly(v[1], v[3], w1);
-        bfly0(v[4], v[6]); bfly(v[5], v[7], w1);
-        const float2 x1 = tw[tw_off(8) + 1], x2 = tw[tw_off(8) + 2], x3 = tw[tw_off(8) + 3];
-        bfly0(v[0], v[4]); bfly(v[1], v[5], x1); bfly(v[2], v[6], x2); bfly(v[3], v[7], x3);
+        bfly0(v[0], v[2]); bfly(v[1], v[3], w2.w4);
+        bfly0(v[4], v[6]); bfly(v[5], v[7], w2.w4);
+        bfly0(v[0], v[4]); bfly(v[1], v[5], w2.w8[0]); bfly(v[2], v[6], w2.w8[1]); bfly(v[3], v[7], w2.w8[2]);
     }
     {
         float2* p = ft.x + fo.p1;
