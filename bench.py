@@ -285,7 +285,7 @@ class OfdmQam64Workload:
         return {
             KK_OFDM_PHASE: ("ofdm_phase_scan_kernel (CFO phase accumulator, CFO frames only)", self.n * 8 if self.cfo_span else 0),
             KK_OFDM_FFT: ("ofdm_fft_kernel", self.n * (samples + bins)),
-            KK_OFDM_CARRIER: ("ofdm_carrier_kernel", self.n * (bins + llr)),
+            KK_OFDM_CARRIER: ("ofdm_carrier2_kernel", self.n * (bins + llr)),
             KK_OFDM_DEMOD: ("ofdm_presynced_kernel (residual-CFO re-run frames only)", 0),
             KK_LDPC: ("ldpc_decode_kernel", self.n * (llr + 4 * (61 + 5))),
             KK_FRAME_STATUS: ("frame_status_kernel", self.n * (4 * 72 + 4 * 5 + 40)),
