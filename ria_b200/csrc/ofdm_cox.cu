@@ -87,15 +87,30 @@ struct WarpTile {
     float s[kN];
 };
 
+// Tile element i lives at xi(i): bit 4 of the index flips the four low bits, so in the first four stages (partners 1, 2,
+// 4, 8 apart: a half-warp touches 16 elements spread over 32) the two halves of the spread land in complementary
+// bank pairs, and from stage 5 on a half-warp's 16 consecutive elements are only permuted -- every 64-bit access of
+// every stage is conflict-free.
+__device__ __forceinline__ int xi(int i) { return i ^ (((i >> 4) & 1) * 15); }
+
+// Stage-major copy of the reference's twiddle table: stage `half` (butterfly span) holds W[k * (N / 2 / half)], k < half,
+// at offset half - 1.  In natural order the lanes of a stage read the table with a stride of N / (2 half) entries, all
+// in one bank for the middle stages (16- and 32-way conflicts: ncu showed 57 % of the kernel's wavefronts were replays).
+__device__ __forceinline__ void stage_twiddles(float2* tws, const float2* __restrict__ tw_nat, int tid, int n_threads) {
+    for (int i = tid; i < kN - 1; i += n_threads) {
+        const int half = 1 << (31 - __clz(i + 1));
+        tws[i] = tw_nat[(i + 1 - half) * (kN / 2 / half)];
+    }
+}
+
 // The reference's butterflies in stage order on a bit-reversed tile (fft.cpp:107-120); one warp, 16 butterflies per lane
 // and stage.
-__device__ void warp_fft_stages(float2* x, const float2* tw, bool inverse, int lane) {
-    for (int len = 2, step = kN >> 1; len <= kN; len <<= 1, step >>= 1) {
-        const int half = len >> 1;
+__device__ void warp_fft_stages(float2* x, const float2* tws, bool inverse, int lane) {
+    for (int half = 1; half < kN; half <<= 1) {
         for (int b = lane; b < (kN >> 1); b += 32) {
             const int k = b & (half - 1);
-            const int i0 = ((b - k) << 1) + k, i1 = i0 + half;
-            float2 w = tw[k * step];
+            const int i0 = xi(((b - k) << 1) + k), i1 = xi(((b - k) << 1) + k + half);
+            float2 w = tws[half - 1 + k];
             if (inverse) w.y = -w.y;
             const float2 u = x[i0];
             const float2 t = cmul_ref(w, x[i1]);
@@ -128,26 +143,26 @@ __device__ void warp_schmidl_cox(const float* __restrict__ src, bool remove_dc, 
         dc = __shfl_sync(kFull, dc, 0);
     }
     for (int i = lane; i < kN; i += 32)
-        t.x[brev10(i)] = make_float2(remove_dc ? __fsub_rn(t.s[i], dc) : t.s[i], 0.0f);
+        t.x[xi(brev10(i))] = make_float2(remove_dc ? __fsub_rn(t.s[i], dc) : t.s[i], 0.0f);
     __syncwarp();
     warp_fft_stages(t.x, tw, false, lane);
     // positive frequencies x 2, negative ones dropped (:72-77), and the bit reversal of the inverse transform in one sweep
     for (int i = lane; i < kN; i += 32) {
         const int j = static_cast<int>(brev10(i));
         if (i > j) continue;
-        float2 a = t.x[i], b = t.x[j];
+        float2 a = t.x[xi(i)], b = t.x[xi(j)];
         if (i >= 1 && i < kN / 2) a = make_float2(__fmul_rn(a.x, 2.0f), __fmul_rn(a.y, 2.0f));
         else if (i > kN / 2) a = make_float2(0.0f, 0.0f);
         if (j >= 1 && j < kN / 2) b = make_float2(__fmul_rn(b.x, 2.0f), __fmul_rn(b.y, 2.0f));
         else if (j > kN / 2) b = make_float2(0.0f, 0.0f);
-        t.x[i] = b;
-        t.x[j] = a;
+        t.x[xi(i)] = b;
+        t.x[xi(j)] = a;
     }
     __syncwarp();
     warp_fft_stages(t.x, tw, true, lane);
     const float scale = 1.0f / static_cast<float>(kN);
     for (int i = lane; i < kN; i += 32) {
-        const float2 v = t.x[i];
+        const float2 v = t.x[i];                                        // every element once: the placement does not matter
         t.x[i] = make_float2(__fmul_rn(v.x, scale), __fmul_rn(v.y, scale));
     }
     __syncwarp();
@@ -158,7 +173,7 @@ __device__ void warp_schmidl_cox(const float* __restrict__ src, bool remove_dc, 
     float* term_b = reinterpret_cast<float*>(t.x);                      // [0, 512): |a|^2          [512, 1024): |b|^2
     float2 av[kN / 64], bv[kN / 64];
 #pragma unroll
-    for (int q = 0; q < kN / 64; ++q) { av[q] = t.x[lane + 32 * q]; bv[q] = t.x[lane + 32 * q + kN / 2]; }
+    for (int q = 0; q < kN / 64; ++q) { av[q] = t.x[xi(lane + 32 * q)]; bv[q] = t.x[xi(lane + 32 * q + kN / 2)]; }
     __syncwarp();                                                       // every a / b is in registers before the tile is reused
 #pragma unroll
     for (int q = 0; q < kN / 64; ++q) {
@@ -252,7 +267,8 @@ cox_scan_kernel(const CoxArgs a) {
     }
 }
 
-constexpr size_t kTileSmem = sizeof(float2) * (kN / 2) + sizeof(WarpTile) * kWarps;
+constexpr size_t kTwSmem = sizeof(float2) * kN;           // stage-major twiddles (N - 1 used)
+constexpr size_t kTileSmem = kTwSmem + sizeof(WarpTile) * kWarps;
 
 // ---------------------------------------------------------------------------------------------
 // per window: candidates in order -> plateau -> LTS -> CFO
@@ -263,7 +279,7 @@ __global__ void __launch_bounds__(kThreads)
 cox_decide_kernel(const CoxArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* tw = reinterpret_cast<float2*>(smem_raw);
-    unsigned char* region = smem_raw + sizeof(float2) * (kN / 2);
+    unsigned char* region = smem_raw + kTwSmem;
     WarpTile* tiles = reinterpret_cast<WarpTile*>(region);
     __shared__ float pc[kPlateauWindow / 8 + 2];
     __shared__ float chunk_c[kWarps];
@@ -271,7 +287,7 @@ cox_decide_kernel(const CoxArgs a) {
     __shared__ float red_c[kWarps];
     __shared__ int red_o[kWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < kN / 2; i += kThreads) tw[i] = a.tw[i];
+    stage_twiddles(tw, a.tw, tid, kThreads);
     __syncthreads();
 
     const int psym = a.cp + kN;                             // preamble symbol: FFT + CP (demodulator.cpp:1463)
@@ -496,9 +512,9 @@ __global__ void __launch_bounds__(kThreads)
 cox_corr_tap_kernel(const CoxArgs a, const int* offsets, float* out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* tw = reinterpret_cast<float2*>(smem_raw);
-    WarpTile* tiles = reinterpret_cast<WarpTile*>(smem_raw + sizeof(float2) * (kN / 2));
+    WarpTile* tiles = reinterpret_cast<WarpTile*>(smem_raw + kTwSmem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < kN / 2; i += kThreads) tw[i] = a.tw[i];
+    stage_twiddles(tw, a.tw, tid, kThreads);
     __syncthreads();
     for (long long w = static_cast<long long>(blockIdx.x) * kWarps + warp; w < a.n; w += static_cast<long long>(gridDim.x) * kWarps) {
         const int off = offsets[w];
