@@ -87,11 +87,12 @@ struct WarpTile {
     float s[kN];
 };
 
-// Tile element i lives at xi(i): bit 4 of the index flips the four low bits, so in the first four stages (partners 1, 2,
-// 4, 8 apart: a half-warp touches 16 elements spread over 32) the two halves of the spread land in complementary
-// bank pairs, and from stage 5 on a half-warp's 16 consecutive elements are only permuted -- every 64-bit access of
-// every stage is conflict-free.
-__device__ __forceinline__ int xi(int i) { return i ^ (((i >> 4) & 1) * 15); }
+// Tile element i lives at xi(i): the four low bits are flipped by bit 4 and XORed with bits 9..6.  In the first four
+// stages (partners 1, 2, 4, 8 apart: a half-warp touches 16 elements spread over one block of 32) the two halves of the
+// spread land in complementary bank pairs; from stage 5 on a half-warp's 16 consecutive elements are only permuted;
+// and in the bit-reversed sweeps (a half-warp's lanes differ in bits 9..6 only) the 16 elements land in 16 different
+// bank pairs -- every 64-bit access of the transform is conflict-free.
+__device__ __forceinline__ int xi(int i) { return i ^ (((i >> 4) & 1) * 15) ^ ((i >> 6) & 15); }
 
 // Stage-major copy of the reference's twiddle table: stage `half` (butterfly span) holds W[k * (N / 2 / half)], k < half,
 // at offset half - 1.  In natural order the lanes of a stage read the table with a stride of N / (2 half) entries, all
@@ -107,15 +108,28 @@ __device__ __forceinline__ void stage_twiddles(float2* tws, const float2* __rest
 // and stage.
 __device__ void warp_fft_stages(float2* x, const float2* tws, bool inverse, int lane) {
     for (int half = 1; half < kN; half <<= 1) {
-        for (int b = lane; b < (kN >> 1); b += 32) {
-            const int k = b & (half - 1);
-            const int i0 = xi(((b - k) << 1) + k), i1 = xi(((b - k) << 1) + k + half);
-            float2 w = tws[half - 1 + k];
-            if (inverse) w.y = -w.y;
-            const float2 u = x[i0];
-            const float2 t = cmul_ref(w, x[i1]);
-            x[i1] = make_float2(__fsub_rn(u.x, t.x), __fsub_rn(u.y, t.y));
-            x[i0] = make_float2(__fadd_rn(u.x, t.x), __fadd_rn(u.y, t.y));
+        // four butterflies in flight per lane: the loads of all four are issued before the first store (the compiler
+        // cannot move a load of x[] above a store to x[] by itself; the butterflies of one stage touch disjoint elements)
+        for (int b0 = lane; b0 < (kN >> 1); b0 += 128) {
+            int i0[4], i1[4];
+            float2 u[4], v[4], w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int b = b0 + 32 * q;
+                const int k = b & (half - 1);
+                i0[q] = xi(((b - k) << 1) + k);
+                i1[q] = xi(((b - k) << 1) + k + half);
+                w[q] = tws[half - 1 + k];
+                u[q] = x[i0[q]];
+                v[q] = x[i1[q]];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (inverse) w[q].y = -w[q].y;
+                const float2 t = cmul_ref(w[q], v[q]);
+                x[i1[q]] = make_float2(__fsub_rn(u[q].x, t.x), __fsub_rn(u[q].y, t.y));
+                x[i0[q]] = make_float2(__fadd_rn(u[q].x, t.x), __fadd_rn(u[q].y, t.y));
+            }
         }
         __syncwarp();
     }
