@@ -16,20 +16,22 @@
 // see below).  The batch therefore runs as a short pipeline of kernels over chunks of frames:
 //   ofdm_phase_scan_kernel  (only when a CFO is given) one warp per frame: value of the fp32
 //                           CFO phase accumulator at every 32nd sample, exact (cfo_phase.cuh);
-//   ofdm_fft_kernel         128-thread CTAs, work item = (symbol index, 16 frames): the mixer
-//                           phasors of that symbol are staged once in shared memory, then every
-//                           frame's samples are read from HBM exactly once (coalesced, CP never
-//                           loaded, next frame prefetched into registers), mixed and transformed
-//                           with the reference's radix-2 DIT butterflies in the reference's
-//                           order -- three stages per pass in registers, exchanged through an
-//                           XOR-swizzled shared-memory tile (conflict-free for every pass).  The
-//                           last four stages are evaluated only for the <= 63 used bins (output
+//   ofdm_fft_kernel         128-thread CTAs, work item = (symbol index, 32 frames): the mixer
+//                           phasors of that symbol are staged once in shared memory (the plain
+//                           variant keeps its share in registers), then every frame's samples are
+//                           read from HBM exactly once (coalesced, CP never loaded, next frame
+//                           prefetched into registers), mixed and transformed with the reference's
+//                           radix-2 DIT butterflies in the reference's order -- three stages per
+//                           pass in registers, exchanged through an additively padded shared-memory
+//                           tile (conflict-free for every pass, per-thread base + constant offsets).
+//                           The last four stages are evaluated only for the <= 63 used bins (output
 //                           pruning: 7 half-butterflies per thread instead of 12 + 1 full ones).
 //                           Every used bin is bit-identical to the reference FFT.
-//   ofdm_carrier_kernel     one warp per frame, two carriers per lane, no block barriers: LTS
+//   ofdm_carrier2_kernel    two frames per warp (half-warp groups), no block barriers: LTS
 //                           estimate, then the data symbols in order (pilot tracking, MMSE,
 //                           LLRs).  Reductions whose fp32 summation order is observable (they
-//                           feed thresholds) are done in the reference's order by lane 0.
+//                           feed thresholds) are done in the reference's order by the group's
+//                           first lane.  ofdm_carrier_kernel (one frame per warp) is the A/B path.
 //   ofdm_presynced_kernel   the monolithic per-frame kernel (FFT + carriers in one CTA); runs
 //                           only for the frames whose LTS reports a residual CFO in (0.3, 5) Hz:
 //                           the reference then re-mixes the whole frame with the corrected CFO
