@@ -116,8 +116,41 @@ def frame_golden(ref, out_dir):
     print("frame_golden.npz written")
 
 
+def cox_golden(ref, out_dir):
+    """OFDM_COX acquisition (OFDMDemodulator::searchForSync): windows in, found / LTS position / CFO / noise floor out,
+    for two thresholds and a carried noise floor, plus Impl::measureCorrelation at a few offsets."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_ofdm_cox_gpu import _windows            # the same window generator the live-reference test uses
+    from tests.ofdm_common import make_cfg, QAM64, DQPSK
+    out = {}
+    for name, mod, spacing, pilots, rate in (("qam64_sp4", QAM64, 4, 1, R3_4), ("dqpsk_sp5", DQPSK, 5, 1, R1_2)):
+        cfg = make_cfg(mod, spacing, pilots)
+        rng = np.random.default_rng(sum(map(ord, name)))
+        window = 20000
+        wins, _ = _windows(ref, rng, 8, window, cfg, rate)
+        x = np.stack(wins).astype(np.float16)              # stored quantised: the expected values are computed on these
+        xf = x.astype(np.float32)
+        out[f"{name}_win"] = x
+        for tag, thr, nf_in in (("a", 0.8, 0.0), ("b", 0.6, 0.002)):
+            res = [ref.ofdm_cox_search_sync(cfg, xf[i], thr, nf_in) for i in range(len(xf))]
+            out[f"{name}_{tag}_thr"] = np.float32(thr)
+            out[f"{name}_{tag}_nf_in"] = np.float32(nf_in)
+            out[f"{name}_{tag}_found"] = np.array([r[0] for r in res], np.uint8)
+            out[f"{name}_{tag}_pos"] = np.array([r[1] if r[0] else -1 for r in res], np.int64)
+            out[f"{name}_{tag}_cfo"] = np.array([r[2] if r[0] else 0.0 for r in res], np.float32)
+            out[f"{name}_{tag}_nf_out"] = np.array([r[3] for r in res], np.float32)
+        offs = np.array([0, 64, 1000, 2048, 4096, 6000, 7777, 9000], np.int32)
+        out[f"{name}_corr_off"] = offs
+        out[f"{name}_corr"] = np.array([ref.ofdm_cox_correlation(cfg, xf[i], int(offs[i])) for i in range(len(xf))], np.float32)
+        print(name, "found:", out[f"{name}_a_found"].tolist(), out[f"{name}_b_found"].tolist())
+    np.savez_compressed(os.path.join(out_dir, "cox_golden.npz"), **out)
+    print("cox_golden.npz written")
+
+
 if __name__ == "__main__":
     ref = Ref()
+    if "cox" in sys.argv[1:] or len(sys.argv) == 1:
+        cox_golden(ref, HERE)
     if "frame" in sys.argv[1:] or len(sys.argv) == 1:
         frame_golden(ref, HERE)
     if "ldpc" in sys.argv[1:] or len(sys.argv) == 1:

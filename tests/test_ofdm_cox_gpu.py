@@ -1,6 +1,8 @@
 """GPU parity of the OFDM_COX acquisition against the unmodified reference:
 OFDMModulator::generatePreamble + modulate (transmit), Impl::measureCorrelation (tap) and
 OFDMDemodulator::searchForSync = OFDMNvisWaveform::detectSync, then processPresynced at the position found."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -266,3 +268,26 @@ def test_cox_chain_one_call_matches_the_stages(ctx, ref):
                 n_repaired_wrong += 1
         assert np.array_equal(h_data[i], data[i]) and h_st[i] == st[i] and h_sy["start_sample"][i] == sy["start_sample"][i]
     assert n_ok >= 10 and n_repaired_wrong <= 2, (n_ok, n_repaired_wrong)
+
+
+GOLD_COX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cox_golden.npz")
+
+
+@pytest.mark.parametrize("name,mod,spacing", [("qam64_sp4", QAM64, 4), ("dqpsk_sp5", DQPSK, 5)])
+def test_search_sync_against_committed_golden(ctx, name, mod, spacing):
+    """tests/golden/cox_golden.npz: outputs of the unmodified reference's searchForSync / measureCorrelation on seeded
+    windows (tests/golden/make_golden.py cox); runs without oracle/_ref."""
+    from ria_b200 import sync
+    g = np.load(GOLD_COX)
+    cfg = _ria_cfg(make_cfg(mod, spacing, 1))
+    x = torch.from_numpy(g[f"{name}_win"].astype(np.float32)).cuda()
+    for tag in ("a", "b"):
+        nf = torch.full((x.shape[0],), float(g[f"{name}_{tag}_nf_in"]), device="cuda")
+        got = sync.results(sync.ofdm_cox_search_sync_batch(cfg, x, float(g[f"{name}_{tag}_thr"]), nf, ctx))
+        assert np.array_equal(got["detected"].astype(np.uint8), g[f"{name}_{tag}_found"])
+        assert np.array_equal(nf.cpu().numpy().view(np.uint32), g[f"{name}_{tag}_nf_out"].view(np.uint32))
+        hit = g[f"{name}_{tag}_found"].astype(bool)
+        assert np.array_equal(got["start_sample"][hit].astype(np.int64), g[f"{name}_{tag}_pos"][hit])
+        assert np.array_equal(got["cfo_hz"][hit].astype(np.float32).view(np.uint32), g[f"{name}_{tag}_cfo"][hit].view(np.uint32))
+    corr = sync.ofdm_cox_correlation_batch(cfg, x, torch.from_numpy(g[f"{name}_corr_off"]).cuda(), ctx).cpu().numpy()
+    assert np.array_equal(corr.view(np.uint32), g[f"{name}_corr"].view(np.uint32))
