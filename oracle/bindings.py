@@ -154,6 +154,8 @@ class Port:
         L.orc_mt_seed.argtypes = [C.c_void_p, C.c_uint32]
         L.orc_mt_next.argtypes = [C.c_void_p]
         L.orc_mt_next.restype = C.c_uint32
+        L.orc_cox_correlation.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_float)] * 5
+        L.orc_cox_correlation.restype = C.c_int
         self._codes = {}
 
     def code(self, rate: int) -> _Code:
@@ -162,6 +164,15 @@ class Port:
             self.lib.orc_ldpc_build(rate, C.byref(c))
             self._codes[rate] = c
         return self._codes[rate]
+
+    def cox_correlation(self, samples, offset: int, cp_len: int, fft_len: int = 1024):
+        """Schmidl-Cox metric at `offset` (ofdm_sync.cpp:118-163) -> (metric, P, R1, R2)"""
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        m, pr, pi, r1, r2 = (C.c_float() for _ in range(5))
+        rc = self.lib.orc_cox_correlation(samples, len(samples), int(offset), int(cp_len), int(fft_len),
+                                          C.byref(m), C.byref(pr), C.byref(pi), C.byref(r1), C.byref(r2))
+        assert rc >= 0
+        return np.float32(m.value), complex(pr.value, pi.value), np.float32(r1.value), np.float32(r2.value)
 
     def ldpc_edges(self, rate: int):
         c = self.code(rate)

@@ -7,8 +7,8 @@
  *
  * Pinning: the reference ships no golden vectors, so every function here
  * is pinned against outputs of the unmodified reference compiled into oracle/_ref/libria_ref.so
- * (tests/test_oracle_vs_ref.py) and against fixtures generated from it and committed under
- * tests/golden/ (tests/golden/make_golden.py).
+ * (tests/test_oracle_ldpc.py, tests/test_oracle_cox_cpu.py) and against fixtures generated from it and
+ * committed under tests/golden/ (tests/golden/make_golden.py).
  */
 #ifndef RIA_ORACLE_H
 #define RIA_ORACLE_H
@@ -55,6 +55,13 @@ uint32_t orc_mt_next(orc_mt19937* g);
 
 /* src/protocol/frame_v2.cpp:115-128 : CRC-16/CCITT-FALSE */
 uint16_t orc_crc16(const uint8_t* data, int len);
+
+/* Schmidl-Cox timing metric of the OFDM_COX acquisition for the FFT window that follows offset + cp_len:
+ * DC removal, analytic signal through the reference's radix-2 FFT pair, P / R1 / R2 over the two halves
+ * (src/ofdm/ofdm_sync.cpp:56-84, 118-163; src/dsp/fft.cpp:83-128).  Returns 1 (0 when the window does not
+ * fit: the metric is then 0, :123-126; -1 on a bad size). */
+int orc_cox_correlation(const float* samples, int n_samples, int offset, int cp_len, int fft_len,
+                        float* metric, float* p_re, float* p_im, float* r1, float* r2);
 
 #ifdef __cplusplus
 }
