@@ -156,6 +156,8 @@ class Port:
         L.orc_mt_next.restype = C.c_uint32
         L.orc_cox_correlation.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_float)] * 5
         L.orc_cox_correlation.restype = C.c_int
+        L.orc_cox_coarse_cfo.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]
+        L.orc_cox_coarse_cfo.restype = C.c_float
         self._codes = {}
 
     def code(self, rate: int) -> _Code:
@@ -173,6 +175,11 @@ class Port:
                                           C.byref(m), C.byref(pr), C.byref(pi), C.byref(r1), C.byref(r2))
         assert rc >= 0
         return np.float32(m.value), complex(pr.value, pi.value), np.float32(r1.value), np.float32(r2.value)
+
+    def cox_coarse_cfo(self, samples, sync_offset: int, cp_len: int, fft_len: int = 1024, sample_rate: int = 48000):
+        """Impl::estimateCoarseCFO (ofdm_sync.cpp:230-261)"""
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        return np.float32(self.lib.orc_cox_coarse_cfo(samples, len(samples), int(sync_offset), int(cp_len), int(fft_len), int(sample_rate)))
 
     def ldpc_edges(self, rate: int):
         c = self.code(rate)

@@ -4,6 +4,7 @@
  *   FFT (fallback Cooley-Tukey build, no FFTW)      src/dsp/fft.cpp:83-128
  *   OFDMDemodulator::Impl::toAnalytic               src/ofdm/ofdm_sync.cpp:56-84
  *   Impl::measureSchmidlCoxCorrelation              src/ofdm/ofdm_sync.cpp:118-163
+ *   Impl::estimateCoarseCFO                         src/ofdm/ofdm_sync.cpp:230-261
  * Float expressions keep the reference's types and order (compiled with -ffp-contract=off, the same
  * glibc cosf / sinf / hypotf / sqrtf the reference calls), so the value is the reference's bit for bit;
  * tests/test_oracle_cox_cpu.py pins it against oracle/_ref and tests/golden/cox_golden.npz. */
@@ -57,27 +58,35 @@ static void fft_inplace(cf* x, int n, const cf* tw, int inverse) {
     }
 }
 
+/* the FFT window at s -> analytic signal in x (toAnalytic, ofdm_sync.cpp:56-84), optionally after the DC removal of
+ * measureSchmidlCoxCorrelation (:130-140).  Returns 0 on allocation failure. */
+static cf* analytic_window(const float* s, int fft_len, int remove_dc) {
+    cf* x = (cf*)malloc(sizeof(cf) * (size_t)fft_len);
+    cf* tw = (cf*)malloc(sizeof(cf) * (size_t)(fft_len / 2));
+    if (!x || !tw) { free(x); free(tw); return 0; }
+    for (int k = 0; k < fft_len / 2; ++k) tw[k] = twiddle(k, fft_len);
+    float dc = 0.0f;
+    if (remove_dc) {
+        float dc_sum = 0.0f;                                  /* a sequential fp32 sum */
+        for (int i = 0; i < fft_len; ++i) dc_sum += s[i];
+        dc = dc_sum / (float)fft_len;
+    }
+    for (int i = 0; i < fft_len; ++i) { x[i].re = remove_dc ? s[i] - dc : s[i]; x[i].im = 0.0f; }
+    fft_inplace(x, fft_len, tw, 0);
+    for (int i = 1; i < fft_len / 2; ++i) { x[i].re *= 2.0f; x[i].im *= 2.0f; }     /* :72-74 */
+    for (int i = fft_len / 2 + 1; i < fft_len; ++i) { x[i].re = 0.0f; x[i].im = 0.0f; }   /* :75-77 */
+    fft_inplace(x, fft_len, tw, 1);
+    free(tw);
+    return x;
+}
+
 int orc_cox_correlation(const float* samples, int n_samples, int offset, int cp_len, int fft_len,
                         float* metric, float* p_re, float* p_im, float* r1, float* r2) {
     *metric = 0.0f; *p_re = 0.0f; *p_im = 0.0f; *r1 = 0.0f; *r2 = 0.0f;
     if (fft_len < 2 || (fft_len & (fft_len - 1)) != 0) return -1;
     if (offset < 0 || (long long)offset + cp_len + fft_len > n_samples) return 0;      /* :123-126 */
-    const float* s = samples + offset + cp_len;
-    cf* x = (cf*)malloc(sizeof(cf) * (size_t)fft_len);
-    cf* tw = (cf*)malloc(sizeof(cf) * (size_t)(fft_len / 2));
-    if (!x || !tw) { free(x); free(tw); return -1; }
-    for (int k = 0; k < fft_len / 2; ++k) tw[k] = twiddle(k, fft_len);
-
-    float dc_sum = 0.0f;                                      /* :130-135, a sequential fp32 sum */
-    for (int i = 0; i < fft_len; ++i) dc_sum += s[i];
-    const float dc = dc_sum / (float)fft_len;
-    for (int i = 0; i < fft_len; ++i) { x[i].re = s[i] - dc; x[i].im = 0.0f; }      /* :137-140, toAnalytic :63-66 */
-
-    fft_inplace(x, fft_len, tw, 0);
-    for (int i = 1; i < fft_len / 2; ++i) { x[i].re *= 2.0f; x[i].im *= 2.0f; }     /* :72-74 */
-    for (int i = fft_len / 2 + 1; i < fft_len; ++i) { x[i].re = 0.0f; x[i].im = 0.0f; }   /* :75-77 */
-    fft_inplace(x, fft_len, tw, 1);
-
+    cf* x = analytic_window(samples + offset + cp_len, fft_len, 1);
+    if (!x) return -1;
     const int half = fft_len / 2;
     float pr = 0.0f, pi = 0.0f, e1 = 0.0f, e2 = 0.0f;         /* :145-153 */
     for (int i = 0; i < half; ++i) {
@@ -88,10 +97,33 @@ int orc_cox_correlation(const float* samples, int n_samples, int offset, int cp_
         e1 += a.re * a.re + a.im * a.im;                      /* std::norm */
         e2 += b.re * b.re + b.im * b.im;
     }
-    free(x); free(tw);
+    free(x);
     *p_re = pr; *p_im = pi; *r1 = e1; *r2 = e2;
     const float normalization = sqrtf(e1 * e2);               /* :158-163 */
     if (normalization < 1e-10f) return 1;
     *metric = hypotf(pr, pi) / normalization;                 /* std::abs(complex<float>) = cabsf = hypotf */
     return 1;
+}
+
+/* Impl::estimateCoarseCFO (ofdm_sync.cpp:230-261): no DC removal here, P over the two halves, CFO from its angle */
+float orc_cox_coarse_cfo(const float* samples, int n_samples, int sync_offset, int cp_len, int fft_len,
+                         unsigned sample_rate) {
+    if (fft_len < 2 || (fft_len & (fft_len - 1)) != 0) return 0.0f;
+    if (sync_offset < 0 || (long long)sync_offset + cp_len + fft_len > n_samples) return 0.0f;   /* :237-239 */
+    cf* x = analytic_window(samples + sync_offset + cp_len, fft_len, 0);
+    if (!x) return 0.0f;
+    const int half = fft_len / 2;
+    float pr = 0.0f, pi = 0.0f;
+    for (int i = 0; i < half; ++i) {
+        cf ca = { x[i].re, -x[i].im };
+        const cf t = cmul(ca, x[i + half]);
+        pr += t.re; pi += t.im;
+    }
+    free(x);
+    const float phase = atan2f(pi, pr);                                             /* :248 */
+    float cfo_hz = (float)((double)(phase * (float)sample_rate) / (ORC_PI * (double)fft_len));   /* :251 */
+    const float max_cfo = (float)(sample_rate / (unsigned)fft_len);                 /* :254, an integer division */
+    if (cfo_hz > max_cfo) cfo_hz = max_cfo;                                         /* std::min(max_cfo, cfo) */
+    if (cfo_hz < -max_cfo) cfo_hz = -max_cfo;                                       /* std::max(-max_cfo, ...) */
+    return cfo_hz;
 }

@@ -63,6 +63,10 @@ uint16_t orc_crc16(const uint8_t* data, int len);
 int orc_cox_correlation(const float* samples, int n_samples, int offset, int cp_len, int fft_len,
                         float* metric, float* p_re, float* p_im, float* r1, float* r2);
 
+/* Impl::estimateCoarseCFO (src/ofdm/ofdm_sync.cpp:230-261) at the Schmidl-Cox peak */
+float orc_cox_coarse_cfo(const float* samples, int n_samples, int sync_offset, int cp_len, int fft_len,
+                         unsigned sample_rate);
+
 #ifdef __cplusplus
 }
 #endif

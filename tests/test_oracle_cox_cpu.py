@@ -48,3 +48,21 @@ def test_port_metric_edges(port):
     assert port.cox_correlation(z[:1000], 0, CP)[0] == 0.0               # window does not fit
     dc = np.full(4096, 0.25, np.float32)
     assert port.cox_correlation(dc, 100, CP)[0] == 0.0                   # pure DC is removed before the transform
+
+
+@pytest.mark.parametrize("name,mod,spacing", [("qam64_sp4", QAM64, 4), ("dqpsk_sp5", DQPSK, 5)])
+def test_port_coarse_cfo_matches_reference(port, ref, name, mod, spacing):
+    """orc_cox_coarse_cfo against Impl::estimateCoarseCFO (through the checker's refineLTSTiming tap)"""
+    g = np.load(GOLD)
+    cfg = make_cfg(mod, spacing, 1)
+    x = g[f"{name}_win"].astype(np.float32)
+    rng = np.random.default_rng(9)
+    n = clamped = 0
+    for i in range(len(x)):
+        for off in rng.integers(0, len(x[i]) - 8000, size=10).tolist() + [len(x[i]) - 1120, len(x[i]) - 1119]:
+            _, want = ref.ofdm_cox_refine_lts(cfg, x[i], int(off))
+            got = port.cox_coarse_cfo(x[i], int(off), CP)
+            assert got.view(np.uint32) == np.float32(want).view(np.uint32), (name, i, off, got, want)
+            n += 1
+            clamped += abs(float(got)) == 46.0
+    assert n >= 90
